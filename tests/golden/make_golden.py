@@ -1,0 +1,389 @@
+"""Generate the committed golden fixtures by running the UNMODIFIED reference with injected randomness.
+
+Run in the build container only (needs /root/reference):   python tests/golden/make_golden.py
+Writes tests/golden/*.npz.  Each fixture stores the initial learnable state, the replay contents, every
+injected random draw and the reference's outputs (TD targets, Bellman weights, gradients, post-step
+parameters, post-Polyak targets, logged scalars) so that the oracle (CPU) and the CUDA path (GPU box,
+where the reference does not exist) can be checked against the reference itself.
+"""
+import copy
+import math
+import os
+import sys
+from itertools import chain
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_harness as rh  # noqa: E402
+
+ssac = rh.import_reference()
+from super_sac import learning, learning_utils as lu, replay as rreplay, augmentations as raug, nets as rnets  # noqa: E402
+
+torch.set_num_threads(1)
+
+
+class IdentityEncoder(rnets.Encoder):
+    def __init__(self, dim):
+        super().__init__()
+        self._dim = dim
+
+    @property
+    def embedding_dim(self):
+        return self._dim
+
+    def forward(self, obs_dict):
+        return obs_dict["obs"]
+
+
+class SharedEncoder(rnets.Encoder):
+    """Trainable state encoder in the style of experiments/gym/train_gym.py:31-45."""
+
+    def __init__(self, dim, hid=16):
+        super().__init__()
+        self.fc0 = torch.nn.Linear(dim, hid)
+        self.fc1 = torch.nn.Linear(hid, dim)
+        self._dim = dim
+
+    @property
+    def embedding_dim(self):
+        return self._dim
+
+    def forward(self, obs_dict):
+        x = torch.relu(self.fc0(obs_dict["obs"]))
+        return torch.relu(self.fc1(x))
+
+
+def stack_of(modules):
+    last = lambda m: m.out if hasattr(m, "out") else m.fc3
+    return {
+        "W1": np.stack([m.fc1.weight.detach().numpy().copy() for m in modules]),
+        "b1": np.stack([m.fc1.bias.detach().numpy().copy() for m in modules]),
+        "W2": np.stack([m.fc2.weight.detach().numpy().copy() for m in modules]),
+        "b2": np.stack([m.fc2.bias.detach().numpy().copy() for m in modules]),
+        "W3": np.stack([last(m).weight.detach().numpy().copy() for m in modules]),
+        "b3": np.stack([last(m).bias.detach().numpy().copy() for m in modules]),
+    }
+
+
+def grads_of(modules):
+    last = lambda m: m.out if hasattr(m, "out") else m.fc3
+    g = lambda p: p.grad.detach().numpy().copy()
+    return {
+        "W1": np.stack([g(m.fc1.weight) for m in modules]),
+        "b1": np.stack([g(m.fc1.bias) for m in modules]),
+        "W2": np.stack([g(m.fc2.weight) for m in modules]),
+        "b2": np.stack([g(m.fc2.bias) for m in modules]),
+        "W3": np.stack([g(last(m).weight) for m in modules]),
+        "b3": np.stack([g(last(m).bias) for m in modules]),
+    }
+
+
+def critic_nets(agent):
+    return [net for c in agent.critics for net in c.nets]
+
+
+def put(d, prefix, sub):
+    for k, v in sub.items():
+        d[f"{prefix}/{k}"] = np.array(v, copy=True)
+
+
+def popart_state(agent):
+    out = {}
+    for i, p in enumerate(agent.popart):
+        if p:
+            out[f"{i}/mu"], out[f"{i}/nu"] = p.mu.numpy().copy(), p.nu.numpy().copy()
+            out[f"{i}/w"], out[f"{i}/b"] = p.w.numpy().copy(), p.b.numpy().copy()
+            out[f"{i}/t"] = np.array(p._t)
+            out[f"{i}/stable"] = np.array(int(p._stable))
+    return out
+
+
+def run_update_case(name, cfg):
+    """Drives critic_update (+Polyak by the target_delay rule of main.py:409), then online_actor_update and
+    alpha_update, exactly as main.py:380-414 / :491-543 call them."""
+    rng = np.random.default_rng(cfg.get("seed", 0))
+    torch.manual_seed(cfg.get("seed", 0))
+    E, N, M = cfg["E"], cfg["N"], cfg["M"]
+    S, A, H, B = cfg["S"], cfg["A"], cfg["H"], cfg["B"]
+    det = cfg.get("deterministic", False)
+    popart_on = cfg.get("popart", False)
+    enc = SharedEncoder(S) if cfg.get("encoder") == "shared" else IdentityEncoder(S)
+    agent = ssac.Agent(
+        act_space_size=A, encoder=enc,
+        actor_network_cls=rnets.mlps.ContinuousDeterministicActor if det else rnets.mlps.ContinuousStochasticActor,
+        critic_network_cls=rnets.mlps.ContinuousCritic,
+        ensemble_size=E, num_critics=N, hidden_size=H, auto_rescale_targets=popart_on,
+        log_std_low=-5.0, log_std_high=2.0,
+    )
+    # give the biases some mass so that every gradient path is exercised from step 0
+    for m in critic_nets(agent) + list(agent.actors):
+        for p in m.parameters():
+            if p.dim() == 1:
+                p.data.add_(0.05 * torch.randn_like(p))
+    if popart_on and cfg.get("popart_warm", False):
+        for p in agent.popart:
+            p._t = 1500
+            p.mu = torch.tensor([0.3])
+            p.nu = torch.tensor([1.7])
+            p.w = torch.tensor([0.9])
+            p.b = torch.tensor([0.1])
+    target = copy.deepcopy(agent)
+    # main.py:322-325 hard updates: identical at creation; perturb the target so Polyak is non-trivial
+    for m in critic_nets(target):
+        for p in m.parameters():
+            p.data.add_(0.01 * torch.randn_like(p))
+
+    nbuf = cfg.get("nbuf", 64)
+    s = rng.standard_normal((nbuf, S)).astype(np.float32)
+    a = rng.uniform(-1, 1, (nbuf, A)).astype(np.float32)
+    r = rng.standard_normal((nbuf,)).astype(np.float32)
+    s1 = rng.standard_normal((nbuf, S)).astype(np.float32)
+    d = (rng.uniform(size=(nbuf,)) < 0.1).astype(np.float32)
+    buffer = rreplay.ReplayBuffer(size=nbuf + 8)
+    buffer.load_experience({"obs": s}, a, r, {"obs": s1}, d)
+
+    out = {}
+    out["cfg"] = np.array(repr(cfg))
+    put(out, "buffer", dict(s=s, a=a, r=r, s1=s1, d=d))
+    put(out, "init/actors", stack_of(agent.actors))
+    put(out, "init/critics", stack_of(critic_nets(agent)))
+    put(out, "init/target_critics", stack_of(critic_nets(target)))
+    put(out, "init/popart", popart_state(agent))
+    if cfg.get("encoder") == "shared":
+        put(out, "init/encoder", {k: v.numpy().copy() for k, v in enc.state_dict().items()})
+        put(out, "init/target_encoder", {k: v.numpy().copy() for k, v in target.encoder.state_dict().items()})
+
+    critic_opt = torch.optim.Adam(chain(*(c.parameters() for c in agent.critics)), lr=cfg.get("critic_lr", 3e-4),
+                                  weight_decay=cfg.get("critic_l2", 0.0), betas=(0.9, 0.999))
+    actor_opt = torch.optim.Adam(chain(*(ac.parameters() for ac in agent.actors)), lr=cfg.get("actor_lr", 3e-4),
+                                 betas=(0.9, 0.999))
+    enc_opt = torch.optim.Adam(agent.encoder.parameters(), lr=cfg.get("encoder_lr", 1e-4), betas=(0.9, 0.999))
+    init_alpha = max(cfg.get("init_alpha", 0.1), 1e-15)
+    log_alphas, alpha_opts = [], []
+    for _ in range(E):
+        la = torch.Tensor([math.log(init_alpha)])
+        la.requires_grad = True
+        log_alphas.append(la)
+        alpha_opts.append(torch.optim.Adam([la], lr=cfg.get("alpha_lr", 1e-4), betas=(0.5, 0.999)))
+
+    sigma = cfg.get("noise_sigma")
+    random_process = None
+    if sigma is not None:
+        random_process = lu.GaussianExplorationNoise(rh.ActionSpace(A), start_scale=sigma, final_scale=min(sigma, 0.1))
+    augmenter = raug.AugmentationSequence([raug.IdentityAug(B)])
+    gamma = cfg.get("gamma", 0.99)
+    wt, wtemp = cfg.get("weight_type"), cfg.get("weight_temp")
+    softmax_w = wt == "softmax" and E > 1
+
+    # record intermediates without touching the reference's code
+    rec = {}
+    o_td, o_bw = lu.compute_td_targets, lu.compute_backup_weights
+
+    def td_rec(*a_, **k_):
+        res = o_td(*a_, **k_)
+        rec.setdefault("td", []).append(res[0].detach().numpy().copy())
+        rec.setdefault("a1", []).append(res[1][1].detach().numpy().copy())
+        return res
+
+    def bw_rec(*a_, **k_):
+        res = o_bw(*a_, **k_)
+        rec.setdefault("w", []).append(res.detach().numpy().copy() if torch.is_tensor(res) else np.array(res, dtype=np.float32))
+        return res
+
+    lu.compute_td_targets, lu.compute_backup_weights = td_rec, bw_rec
+    try:
+        replay_dicts = None
+        for t in range(cfg["steps"]):
+            idx = rng.integers(0, nbuf, size=(E, B))
+            subsets = [list(rng.permutation(N)[:M]) for _ in range(E)]
+            eps = rng.standard_normal((E, B, A)).astype(np.float32)
+            noise = rng.standard_normal((E, B, A)).astype(np.float32)
+            weps = rng.standard_normal((E, E, B, A)).astype(np.float32)
+            put(out, f"step{t}/rand", dict(idx=idx, subsets=np.array(subsets), eps=eps, noise=noise, weight_eps=weps))
+            # draw order inside one member iteration (learning.py:47-80): indices, [actor eps], [td3 noise],
+            # subset, then for softmax weights one actor sample per ensemble member
+            normal_q, randn_q = [], []
+            for i in range(E):
+                if not det:
+                    normal_q.append(eps[i])
+                if sigma is not None:
+                    randn_q.append(noise[i])
+                if softmax_w and not det:
+                    normal_q.extend(list(weps[i]))
+            rec.clear()
+            with rh.injected(randint=list(idx), subsets=subsets, normal_eps=normal_q, randn=randn_q) as q:
+                logs, replay_dicts = learning.critic_update(
+                    buffer=buffer, agent=agent, target_agent=target, critic_optimizer=critic_opt,
+                    encoder_optimizer=enc_opt, log_alphas=log_alphas, batch_size=B, gamma=gamma,
+                    critic_clip=cfg.get("critic_clip"), encoder_clip=cfg.get("encoder_clip"),
+                    target_critic_ensemble_n=M, weighted_bellman_temp=wtemp, weight_type=wt,
+                    pop=cfg.get("pop", False), augmenter=augmenter, encoder_lambda=0.0, aug_mix=0.0,
+                    discrete=False, random_process=random_process, noise_clip=cfg.get("noise_clip"),
+                    per=False, update_priorities=False, dr3_coeff=cfg.get("dr3_coeff", 0.0))
+                assert not q["randint"].items and not q["normal_eps"].items and not q["randn"].items
+            put(out, f"step{t}/td_target", {str(i): v for i, v in enumerate(rec["td"])})
+            put(out, f"step{t}/a1", {str(i): v for i, v in enumerate(rec["a1"])})
+            put(out, f"step{t}/weights", {str(i): v for i, v in enumerate(rec["w"])})
+            put(out, f"step{t}/critic_grads", grads_of(critic_nets(agent)))
+            put(out, f"step{t}/logs", {k.replace("/", "|"): float(v) for k, v in logs.items()})
+            if (t + cfg.get("step0", 0)) % cfg.get("target_delay", 1) == 0:
+                for ac, tc in zip(agent.critics, target.critics):
+                    lu.soft_update(tc, ac, cfg.get("tau", 0.005))
+                lu.soft_update(target.encoder, agent.encoder, cfg.get("encoder_tau", 0.01))
+            put(out, f"step{t}/critics", stack_of(critic_nets(agent)))
+            put(out, f"step{t}/target_critics", stack_of(critic_nets(target)))
+            put(out, f"step{t}/popart", popart_state(agent))
+            if cfg.get("encoder") == "shared":
+                put(out, f"step{t}/encoder", {k: v.numpy().copy() for k, v in enc.state_dict().items()})
+                put(out, f"step{t}/target_encoder", {k: v.numpy().copy() for k, v in target.encoder.state_dict().items()})
+    finally:
+        lu.compute_td_targets, lu.compute_backup_weights = o_td, o_bw
+
+    # actor + alpha update on the last critic batch (reuse_replay_dicts=True, main.py:491-543)
+    eps = rng.standard_normal((E, B, A)).astype(np.float32)
+    noise = rng.standard_normal((E, B, A)).astype(np.float32)
+    put(out, "actor/rand", dict(eps=eps, noise=noise))
+    with rh.injected(normal_eps=list(eps), randn=list(noise) if sigma is not None else []):
+        # (the deterministic actor's rsample() is Normal(loc, 1e-4).rsample(): it draws too)
+        alogs = learning.online_actor_update(
+            buffer=buffer, agent=agent, pop=cfg.get("pop", False), actor_optimizer=actor_opt, log_alphas=log_alphas,
+            batch_size=B, clip=cfg.get("actor_clip"), random_process=random_process, noise_clip=cfg.get("noise_clip"),
+            augmenter=augmenter, aug_mix=0.0, premade_replay_dicts=replay_dicts, per=False, discrete=False,
+            use_baseline=False)
+    put(out, "actor/grads", grads_of(agent.actors))
+    put(out, "actor/actors", stack_of(agent.actors))
+    put(out, "actor/logs", {k.replace("/", "|"): float(v) for k, v in alogs.items()})
+    if cfg.get("alpha_update", True):
+        eps = rng.standard_normal((E, B, A)).astype(np.float32)
+        put(out, "alpha/rand", dict(eps=eps))
+        with rh.injected(normal_eps=[] if det else list(eps)):
+            llogs = learning.alpha_update(
+                buffer=buffer, agent=agent, optimizers=alpha_opts, batch_size=B, log_alphas=log_alphas,
+                augmenter=augmenter, aug_mix=0.0, target_entropy=-float(A), premade_replay_dicts=replay_dicts,
+                discrete=False)
+        put(out, "alpha/log_alphas", {str(i): la.detach().numpy().copy() for i, la in enumerate(log_alphas)})
+        put(out, "alpha/logs", {k.replace("/", "|"): float(v) for k, v in llogs.items()})
+    path = os.path.join(HERE, f"update_{name}.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}  ({os.path.getsize(path)/1024:.1f} KiB)")
+
+
+UPDATE_CASES = {
+    # C1-shaped: plain SAC, 2 critics
+    "sac": dict(E=1, N=2, M=2, S=3, A=1, H=32, B=16, steps=3, target_delay=2, seed=1),
+    # C2-shaped: REDQ, random subset of 2 target critics out of N
+    "redq": dict(E=1, N=5, M=2, S=17, A=6, H=48, B=32, steps=2, target_delay=2, seed=2),
+    # C3-shaped: SUNRISE ensemble with weighted Bellman backups + PopArt (warm, so the POP branch is live)
+    "sunrise_popart": dict(E=3, N=2, M=2, S=5, A=2, H=32, B=16, steps=3, weight_type="sunrise", weight_temp=20.0,
+                           popart=True, pop=True, popart_warm=True, seed=3),
+    # C4-shaped learner: deterministic actor + TD3 noise + trainable encoder + clipping
+    "td3_encoder": dict(E=1, N=2, M=2, S=6, A=3, H=32, B=16, steps=2, deterministic=True, noise_sigma=0.5,
+                        noise_clip=0.3, encoder="shared", critic_clip=0.05, encoder_clip=40.0, actor_clip=40.0,
+                        tau=0.01, encoder_tau=1.0, gamma=0.99 ** 3, init_alpha=0.0, alpha_update=False, seed=4),
+    # C5-shaped extras: softmax weights + DR3 + L2 + cold PopArt
+    "softmax_dr3": dict(E=2, N=2, M=1, S=4, A=2, H=32, B=16, steps=2, weight_type="softmax", weight_temp=10.0,
+                        dr3_coeff=0.01, critic_clip=40.0, critic_l2=1e-3, popart=True, pop=True, seed=5),
+}
+
+
+def run_replay_case():
+    """ReplayBuffer ring + PER trees: replay.py:10-353."""
+    rng = np.random.default_rng(11)
+    out = {}
+    size, S, A = 50, 4, 2
+    buf = rreplay.ReplayBuffer(size=size, alpha=0.6, beta=0.7)
+    ops = []
+    # single pushes, batched pushes with wrap-around, priority pushes
+    n_ops = 0
+    for t in range(30):
+        s, a = rng.standard_normal(S).astype(np.float32), rng.uniform(-1, 1, A).astype(np.float32)
+        r, s1, d = float(rng.standard_normal()), rng.standard_normal(S).astype(np.float32), bool(rng.uniform() < 0.2)
+        buf.push({"obs": s}, a, r, {"obs": s1}, d)
+        put(out, f"op{n_ops}", dict(kind="push1", s=s, a=a, r=r, s1=s1, d=d)); n_ops += 1
+    for t in range(3):
+        n = 12
+        s, a = rng.standard_normal((n, S)).astype(np.float32), rng.uniform(-1, 1, (n, A)).astype(np.float32)
+        r, s1 = rng.standard_normal((n, 1)).astype(np.float32), rng.standard_normal((n, S)).astype(np.float32)
+        d = (rng.uniform(size=(n, 1)) < 0.2)
+        pr = rng.uniform(0.1, 3.0, n)
+        buf.push({"obs": s}, a, r, {"obs": s1}, d, priorities=pr)
+        put(out, f"op{n_ops}", dict(kind="pushN", s=s, a=a, r=r, s1=s1, d=d, priorities=pr)); n_ops += 1
+    st = buf._storage
+    put(out, "after_push", dict(s=st.s_stack["obs"], s1=st.s1_stack["obs"], a=st.action_stack, r=st.reward_stack,
+                                d=st.done_stack, next_idx=st._next_idx, filled=st._max_filled,
+                                sum_tree=buf._it_sum._value, min_tree=buf._it_min._value, max_priority=buf._max_priority))
+    # uniform sample with injected indices
+    idx = rng.integers(0, len(buf), size=8)
+    with rh.injected(randint=[idx]):
+        (s_, a_, r_, s1_, d_), ridx = buf.sample_uniform(8)
+    put(out, "uniform", dict(idx=idx, s=s_["obs"].numpy(), a=a_.numpy(), r=r_.numpy(), s1=s1_["obs"].numpy(), d=d_.numpy(), ridx=ridx))
+    # PER sample / update rounds (duplicates in idxes are likely with B=16 over 50 slots)
+    for t in range(4):
+        u = rng.uniform(size=16)
+        with rh.injected(np_random=[u]):
+            (s_, a_, r_, s1_, d_), w, idxes = buf.sample(16)
+        newp = rng.uniform(1e-3, 5.0, 16)
+        buf.update_priorities(idxes, newp)
+        put(out, f"per{t}", dict(u=u, idxes=idxes, weights=w.numpy(), s=s_["obs"].numpy(), a=a_.numpy(), new_priorities=newp,
+                                 sum_tree=buf._it_sum._value, min_tree=buf._it_min._value, max_priority=buf._max_priority))
+    out["n_ops"] = np.array(n_ops)
+    path = os.path.join(HERE, "replay_per.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}  ({os.path.getsize(path)/1024:.1f} KiB)")
+
+
+def run_aug_case():
+    """DrQ / DrQv2 augmentation + sample_move_and_augment on a uint8 pixel buffer."""
+    rng = np.random.default_rng(21)
+    out = {}
+    B, C, HW, nbuf, A = 8, 3, 20, 24, 2
+    s = rng.integers(0, 256, (nbuf, C, HW, HW), dtype=np.uint8)
+    s1 = rng.integers(0, 256, (nbuf, C, HW, HW), dtype=np.uint8)
+    a = rng.uniform(-1, 1, (nbuf, A)).astype(np.float32)
+    r = rng.standard_normal(nbuf).astype(np.float32)
+    d = (rng.uniform(size=nbuf) < 0.1)
+    buf = rreplay.ReplayBuffer(size=nbuf)
+    buf.load_experience({"pixels": s}, a, r, {"pixels": s1}, d)
+    put(out, "buffer", dict(s=s, s1=s1, a=a, r=r, d=d))
+    idx = rng.integers(0, nbuf, B)
+    # --- DrQv2 (bilinear in the reference) ---
+    shift = rng.integers(0, 9, (B, 1, 1, 2))
+    aug = raug.AugmentationSequence([raug.Drqv2Aug(B)])
+    with rh.injected(randint=[idx, shift]):
+        rd = lu.sample_move_and_augment(buf, B, aug, aug_mix=0.75, per=False)
+    o, a_, r_, o1, d_ = rd["primary_batch"]
+    put(out, "drqv2", dict(idx=idx, shift=shift, o=o["pixels"].numpy(), o1=o1["pixels"].numpy(),
+                           ao=rd["augmented_obs"][0]["pixels"].numpy(), ao1=rd["augmented_obs"][1]["pixels"].numpy(),
+                           oo=rd["original_obs"][0]["pixels"].numpy(), a=a_.numpy(), r=r_.numpy(), d=d_.numpy()))
+    # --- DrQ v1 without noise (exact integer crop in the reference) ---
+    w1, h1 = rng.integers(0, 8, B), rng.integers(0, 8, B)
+    with rh.injected(randint=[raug_dummy for raug_dummy in (w1, h1)]):
+        augobj = raug.DrqNoNoiseAug(B)  # constructor draws once
+    aug = raug.AugmentationSequence([augobj])
+    with rh.injected(randint=[idx, w1, h1]):
+        rd = lu.sample_move_and_augment(buf, B, aug, aug_mix=1.0, per=False)
+    o, _, _, o1, _ = rd["primary_batch"]
+    put(out, "drqv1", dict(idx=idx, w1=w1, h1=h1, o=o["pixels"].numpy(), o1=o1["pixels"].numpy()))
+    # --- DrQ v1 with N(0,1) noise ---
+    with rh.injected(randint=[w1, h1]):
+        augobj = raug.DrqAug(B)
+    aug = raug.AugmentationSequence([augobj])
+    n0 = rng.standard_normal((B, C, HW, HW)).astype(np.float32)
+    n1 = rng.standard_normal((B, C, HW, HW)).astype(np.float32)
+    with rh.injected(randint=[idx, w1, h1], randn_like=[n0, n1]):
+        rd = lu.sample_move_and_augment(buf, B, aug, aug_mix=0.5, per=False)
+    o, _, _, o1, _ = rd["primary_batch"]
+    put(out, "drqv1_noise", dict(idx=idx, w1=w1, h1=h1, n0=n0, n1=n1, o=o["pixels"].numpy(), o1=o1["pixels"].numpy()))
+    path = os.path.join(HERE, "aug_pixels.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}  ({os.path.getsize(path)/1024:.1f} KiB)")
+
+
+if __name__ == "__main__":
+    for name, cfg in UPDATE_CASES.items():
+        run_update_case(name, cfg)
+    run_replay_case()
+    run_aug_case()
