@@ -1,0 +1,201 @@
+/*
+ * ssac_b200.h -- C ABI of libssac_b200.so: the off-policy update step of jakegrigsby/super_sac as
+ * hand-written sm_100a CUDA.  The reference is pure Python/PyTorch and has no FFI of its own; each
+ * entry point below replaces the ATen call sequence of the cited reference lines (paths relative to the
+ * reference root).  INTEGRATION.md shows the ctypes binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no C++ / torch types cross the boundary.
+ *   - every pointer named *_dev / documented "device" is a CUDA device pointer owned by the caller
+ *     (PyTorch owns all tensors); the library never frees or allocates caller memory on the hot path.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises.
+ *     Every call is CUDA-graph capturable (no malloc, no sync, pointer-stable arguments); values that
+ *     change between replays (Adam step, PopArt state, Philox offset, log_alpha) live in device memory.
+ *   - return 0 on success, else a cudaError_t or a negative SSAC_E_* code; ssac_last_error() gives the
+ *     message of the last failure on the calling thread.  No exceptions cross the ABI.
+ *   - all floating point is IEEE fp32 (the reference runs true-fp32 SGEMM); replay / gather /
+ *     augmentation / segment-tree entry points are bit-exact integer, byte or float64 work.
+ *   - matrices are row-major; "ld" = elements between consecutive rows; "gs" = elements between groups.
+ */
+#ifndef SSAC_B200_H
+#define SSAC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSAC_E_BADARG (-1)
+#define SSAC_E_UNSUPPORTED (-2)
+#define SSAC_E_ARCH (-3)
+
+/* ---- library ------------------------------------------------------------------------------------- */
+const char* ssac_last_error(void);
+int ssac_version(void);
+/* 0 iff `device` is an sm_100 part (the library carries sm_100a SASS only: no fallback). */
+int ssac_device_check(int device);
+
+/* ---- target networks: learning_utils.py:160-167 (soft_update / hard_update), main.py:409-414 ------ */
+/* target <- target*(1-tau) + source*tau, three separately rounded fp32 ops: bit-exact with the reference. */
+int ssac_polyak(float* target_dev, const float* source_dev, int64_t n, float tau, void* stream);
+/* Same over a table of tensors (user encoders are arbitrary nn.Modules): table_dev = n_tensors x
+ * {uint64 target_ptr, uint64 source_ptr, uint64 numel}; total_chunks = sum ceil(numel/chunk). */
+int ssac_polyak_multi(const uint64_t* table_dev, int n_tensors, int64_t max_numel, float tau, void* stream);
+
+/* ---- optimiser: torch.optim.Adam as configured in main.py:188-239 (coupled L2, no amsgrad) -------- */
+/* ctl_dev: int32[2] = {step, blocks_done}; the kernel reads step, uses t = step+1 for the bias
+ * corrections and the last block to finish stores step+1 (graph replays advance it).
+ * gnorm_sq_dev (nullable): if given with max_norm > 0, grads are scaled by
+ * min(1, max_norm/(sqrt(*gnorm_sq_dev)+1e-6)) (torch.nn.utils.clip_grad_norm_, learning.py:122-128) and,
+ * if write_back_grad, the scaled gradient is stored to g_dev like clip_grad_norm_ does. */
+int ssac_adam_step(float* p_dev, float* g_dev, float* m_dev, float* v_dev, int64_t n, int32_t* ctl_dev,
+                   float lr, float beta1, float beta2, float eps, float weight_decay,
+                   const float* gnorm_sq_dev, float max_norm, int write_back_grad, void* stream);
+/* Adam followed by the Polyak update of the matching target parameters in one pass (36 B/param). */
+int ssac_adam_polyak_step(float* p_dev, float* g_dev, float* m_dev, float* v_dev, float* target_dev, int64_t n,
+                          int32_t* ctl_dev, float lr, float beta1, float beta2, float eps, float weight_decay,
+                          const float* gnorm_sq_dev, float max_norm, int write_back_grad, float tau, void* stream);
+/* out_dev[0] (+)= sum x^2  (global grad norm for clipping / get_grad_norm, learning_utils.py:95-106). */
+int ssac_sumsq(const float* x_dev, int64_t n, float* out_dev, int accumulate, void* stream);
+
+/* ---- random draws: replay.py:122 (indices), agent.py:29 (REDQ subset), Normal sampling, ------------
+ * learning_utils.py:49 (TD3 noise), augmentations.py:180-181,227-231 (shifts).  Philox4x32-10.
+ * rng_dev: uint64[4] = {seed, offset, blocks_done, reserved}; the kernel's last block advances offset so that
+ * graph replays draw fresh numbers.  Any output may be NULL.
+ *   idx_dev     int64[n_idx]            uniform in [0, n_filled); n_filled_dev (nullable device int64[1]) overrides
+ *                                       n_filled so that a captured graph follows a growing buffer
+ *   normal_dev  float[n_normal]         N(0,1)
+ *   subset_dev  int32[n_subsets*M]      n_subsets independent M-subsets of {0..N-1} (without replacement)
+ *   shift_dev   int32[n_shift]          uniform in [0, shift_range)                                      */
+int ssac_rng_fill(uint64_t* rng_dev, int64_t* idx_dev, int64_t n_idx, int64_t n_filled, const int64_t* n_filled_dev,
+                  float* normal_dev, int64_t n_normal, int32_t* subset_dev, int n_subsets, int N, int M, int32_t* shift_dev,
+                  int64_t n_shift, int shift_range, void* stream);
+
+/* ---- replay gather: replay.py:66-84 + learning_utils.py:186-197 (H2D + .float()) ------------------ */
+/* For each of n_arrays arrays: dst[b, :] = src[idx[b], :].  row_elems[k] elements per row;
+ * mode[k]: 0 = f32 -> f32 copy, 1 = u8 -> f32 cast, 2 = raw bytes (row_elems = bytes per row).
+ * dst_ld[k] = elements between dst rows (lets a gather write straight into a column block of a wider
+ * matrix such as cat(s, a)).  srcs/dsts/... are HOST arrays of n_arrays (<= 16) entries. */
+int ssac_gather_rows(const void* const* srcs_dev, void* const* dsts_dev, const int64_t* row_elems,
+                     const int64_t* dst_ld, const int32_t* mode, int n_arrays, const int64_t* idx_dev, int B,
+                     void* stream);
+/* Fused pixel gather + DrQ / DrQv2 random shift + uint8 -> fp32 + aug_mix: augmentations.py:165-269,
+ * learning_utils.py:193-206.   src u8 [capacity, C, H, W] -> dst f32 [B, C, H, W].
+ * pad_mode 0: no shift, 1: replicate (DrQv2 integer crop), 2: reflect (DrQ v1).
+ * shift_dev int32 [B,2] = (x, y) with 0 <= shift <= 2*pad (v2) / < 2*pad (v1).  Rows b < aug_rows are
+ * augmented, the rest are a plain cast.  noise_dev (nullable) f32 [B,C,H,W] is added before the clamp to
+ * [0,255] (DrqAug noise=True). */
+int ssac_gather_aug_u8(const uint8_t* src_dev, float* dst_dev, const int64_t* idx_dev, const int32_t* shift_dev,
+                       const float* noise_dev, int B, int C, int H, int W, int pad, int pad_mode, int aug_rows,
+                       void* stream);
+
+/* ---- prioritised replay: replay.py:163-190, :207-353 (float64 sum / min segment trees) ------------ */
+/* tree layout identical to the reference: value[2*capacity], root at 1, leaves at capacity + i. */
+int ssac_tree_set(double* sum_tree_dev, double* min_tree_dev, int64_t capacity, const int64_t* idx_dev,
+                  const double* val_dev, int64_t n, void* stream);
+/* idx_out[b] = find_prefixsum_idx(u[b] * sum(0, n_filled-1)); weights as replay.py:173-176. */
+int ssac_tree_sample(const double* sum_tree_dev, const double* min_tree_dev, int64_t capacity, int64_t n_filled,
+                     const double* u01_dev, int B, double beta, int64_t* idx_out_dev, double* weight_out_dev,
+                     void* stream);
+
+/* ---- ensemble MLPs: agent.py:13-40 (Critic), nets/mlps.py:11-41,78-93,113-129 --------------------- */
+/* G independent 3-Linear ReLU MLPs  D -> H -> H -> O.  Parameters: W1 [nets,H,D] b1 [nets,H] W2 [nets,H,H]
+ * b2 [nets,H] W3 [nets,O,H] b3 [nets,O] (nn.Linear layout).  Group g uses net net_index_dev[g] (device
+ * int32, e.g. the REDQ subset) or net g when NULL.  Input x_dev: row-major [.,B,D] with row stride ldx and
+ * group stride x_gs (0 = every group reads the same batch).  Outputs h1/h2 [G,B,H] (nullable: not saved),
+ * y [G,B,O].  impl: 0 = auto, 1 = fp32 FFMA tiles, 2 = tcgen05 3xTF32 tensor-core path. */
+int ssac_mlp_forward(const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
+                     const float* b3, const int32_t* net_index_dev, int G, int D, int H, int O,
+                     const float* x_dev, int64_t ldx, int64_t x_gs, int B, float* h1_dev, float* h2_dev,
+                     float* y_dev, int impl, void* stream);
+/* Backward of the above.  dy [G,B,O] (nullable = 0), dh2_extra [G,B,H] (nullable) is added to dL/dh2 scaled
+ * by extra_scale (DR3, learning.py:100-108).  Weight grads gW1..gb3 laid out like the parameters (all NULL =
+ * input-gradient only, the actor update's pass through the critics); accumulate != 0 adds to them.
+ * dx_dev [G,B,D] (nullable) with row stride lddx.  ws_dev: workspace of ssac_mlp_backward_ws(G,B,H) floats. */
+int64_t ssac_mlp_backward_ws(int G, int B, int H);
+int ssac_mlp_backward(const float* W1, const float* W2, const float* W3, const int32_t* net_index_dev, int G,
+                      int D, int H, int O, const float* x_dev, int64_t ldx, int64_t x_gs, int B,
+                      const float* h1_dev, const float* h2_dev, const float* dy_dev, const float* dh2_extra_dev,
+                      float extra_scale, float* gW1, float* gb1, float* gW2, float* gb2, float* gW3, float* gb3,
+                      int accumulate, float* dx_dev, int64_t lddx, float* ws_dev, int impl, void* stream);
+
+/* ---- policy heads: nets/distributions.py:9-15,64-114; learning_utils.py:48-59 --------------------- */
+/* out [B,2A] = [mu | raw_log_std], eps [B,A] -> a [B,A] (row stride lda: may be a column block of cat(s,a)),
+ * logp [B] (sum over A of Normal.log_prob(x) - log|d tanh|).  Saves nothing: backward recomputes. */
+int ssac_tanh_normal_forward(const float* out_dev, const float* eps_dev, int B, int A, float log_std_lo,
+                             float log_std_hi, float* a_dev, int64_t lda, float* logp_dev, void* stream);
+/* d(out) from d(a) [B,A] (row stride ldda, nullable) and d(logp) [B] given as a device scalar multiplier:
+ * dlogp[b] = dlogp_scale * exp(*log_alpha_dev) (log_alpha_dev nullable = 1).  rsample path, learning.py:392-399. */
+int ssac_tanh_normal_backward(const float* out_dev, const float* eps_dev, int B, int A, float log_std_lo,
+                              float log_std_hi, const float* da_dev, int64_t ldda, float dlogp_scale,
+                              const float* log_alpha_dev, float* dout_dev, void* stream);
+/* log-prob of dataset actions (cache miss: atanh(clamp(a, +-0.99))), AFBC: learning_utils.py:259-267.
+ * dlogp_dev nullable: when given also writes d(out) = dlogp * d logp/d out. */
+int ssac_tanh_normal_logprob(const float* out_dev, const float* a_dev, int64_t lda, int B, int A, float log_std_lo,
+                             float log_std_hi, float* logp_dev, const float* dlogp_dev, float* dout_dev,
+                             void* stream);
+/* Deterministic actor head (+ optional rsample jitter 1e-4*eps, + optional TD3 noise):
+ * a = clamp(tanh(out) [+ 1e-4*eps] + clamp(sigma*noise, +-clip), -1+1e-6, 1-1e-6); clip <= 0 means no clip;
+ * noise NULL means no noise / no clamp.  tanh_out_dev (nullable) keeps tanh(out) for the backward. */
+int ssac_det_head_forward(const float* out_dev, const float* eps_dev, const float* noise_dev, int B, int A,
+                          float sigma, float clip, float* a_dev, int64_t lda, float* tanh_out_dev, void* stream);
+/* dout = da * (1 - tanh(out)^2)  (straight-through clamp). */
+int ssac_det_head_backward(const float* tanh_out_dev, const float* da_dev, int64_t ldda, int B, int A,
+                           float* dout_dev, void* stream);
+
+/* ---- PopArt state: popart.py:8-59.  popart_dev float[4] = {mu, nu, w, b}; popart_ctl_dev int32[2] = {t, stable} */
+
+/* ---- TD target: learning_utils.py:298-354 --------------------------------------------------------- */
+/* q_t [M,B] target-critic values on (s1, a1); v = min_M q_t - exp(log_alpha)*logp  (logp NULL: no entropy
+ * term, the TD3 branch); PopArt de-normalise if pop; y = r + gamma*(1-d)*v; PopArt update_stats + normalise
+ * if popart_dev given.  logs_dev float[3] = {mean(y), std(y) (unbiased), mean(entropy_bonus)}. */
+int ssac_td_target(const float* q_t_dev, int M, int B, const float* logp_dev, const float* log_alpha_dev,
+                   const float* r_dev, const float* d_dev, float gamma, float* popart_dev, int32_t* popart_ctl_dev,
+                   int pop, float popart_beta, int popart_min_steps, float* y_dev, float* logs_dev, void* stream);
+
+/* ---- weighted Bellman backups: learning_utils.py:357-398 ------------------------------------------ */
+/* kind 0 'sunrise': q [E,N,B] -> min over N -> unbiased std over E -> sigmoid(-std*T)+0.5
+ * kind 1 'softmax': q [E,N,B] -> min over N -> std over E -> B*softmax_batch(-std*T)
+ * popart of member j (nullable table popart_dev [E,4]) is NOT applied (the reference does not either).
+ * logs_dev float[4] = {mean, max, min, std(unbiased)}. */
+int ssac_backup_weights(const float* q_dev, int E, int N, int B, float temperature, int kind, float* w_dev,
+                        float* logs_dev, void* stream);
+
+/* ---- critic loss seed: learning.py:90-98,112 ------------------------------------------------------ */
+/* q [N,B] predictions of one member, y [B], w [B] (nullable = 1), imp [B] (nullable = 1).
+ * q' = popw*q+popb if pop.  dq[k,b] = -2*w*imp*(y-q')*popw * inv_count (inv_count = 1/(B*E*N));
+ * loss_dev[0] += sum_k mean_b(w*imp*(y-q')^2) * (1/(E*N));  loss_dev[1] = mean_b(y - q'_{N-1}). */
+int ssac_critic_loss_seed(const float* q_dev, int N, int B, const float* y_dev, const float* w_dev,
+                          const float* imp_dev, const float* popart_dev, int pop, int E, float* dq_dev,
+                          float* loss_dev, void* stream);
+/* DR3 feature co-adaptation: f, f1 [N,B,H]: out_dev[0] = mean_{N,B} sum_H f*f1. */
+int ssac_dr3_dot(const float* f_dev, const float* f1_dev, int N, int B, int H, float* out_dev, void* stream);
+
+/* ---- actor loss seed: learning.py:400-408 --------------------------------------------------------- */
+/* q [N,B] = critics on (s, pi(s)); vals = min_N (popart if pop); dq[k,b] = -(popw)/(E*B) on the arg-min net,
+ * 0 elsewhere.  loss_dev[0] += -(1/E) * mean_b(vals - exp(log_alpha)*logp) (logp NULL: no entropy term). */
+int ssac_actor_loss_seed(const float* q_dev, int N, int B, const float* logp_dev, const float* log_alpha_dev,
+                         const float* popart_dev, int pop, int E, float* vals_dev, float* dq_dev, float* loss_dev,
+                         void* stream);
+/* out[b, a] = sum_k dx[k, b, col0 + a]   (action-gradient of the arg-min routing, summed over nets). */
+int ssac_sum_groups(const float* dx_dev, int G, int B, int64_t lddx, int col0, int A, float* out_dev, void* stream);
+
+/* ---- temperature: learning.py:222-263 ------------------------------------------------------------- */
+/* loss = -mean(log_alpha*(logp + target_entropy)); Adam(beta1, beta2) on the scalar, state {m, v} in
+ * state_dev float[2], step in ctl_dev int32[2].  logs_dev float[2] = {alpha_loss, exp(new log_alpha)}. */
+int ssac_alpha_step(float* log_alpha_dev, const float* logp_dev, int B, float target_entropy, float* state_dev,
+                    int32_t* ctl_dev, float lr, float beta1, float beta2, float eps, float* logs_dev, void* stream);
+
+/* ---- advantage filter: adv_estimator.py:58-79, learning_utils.py:241-269,288-295 ------------------ */
+/* q_pi [n,B] = min-critic values of n policy samples, q_data [B]: adv = q_data - mean_n q_pi;
+ * mask = (adv >= 0); priority (float64) = relu(adv) + 1e-4.  Any output nullable. */
+int ssac_advantage(const float* q_pi_dev, int n, const float* q_data_dev, int B, float* adv_dev, float* mask_dev,
+                   double* priority_dev, void* stream);
+/* min over the N rows of q [N,B] with optional PopArt affine (agent.py:37-38, adv_estimator.py:30-35). */
+int ssac_min_over_nets(const float* q_dev, int N, int B, const float* popart_dev, float* out_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSAC_B200_H */

@@ -1,0 +1,31 @@
+"""super_sac_b200 -- the off-policy update step of jakegrigsby/super_sac as hand-written sm_100a CUDA.
+
+Drop-in surface (same names as the reference package, reference super_sac/__init__.py:5-11):
+``Agent``, ``nets`` (``Encoder`` plugin base, ``mlps``, ``cnns``), ``replay.ReplayBuffer``,
+``learning.critic_update / online_actor_update / alpha_update / offline_actor_update``,
+``learning_utils.soft_update / hard_update / sample_move_and_augment``, ``augmentations``, ``popart``.
+
+Host code is Python/PyTorch plumbing (tensors, streams, autograd hand-off to user encoders); all arithmetic of
+the path runs in ``libssac_b200.so`` through the C ABI in ``include/ssac_b200.h``.  There is no CPU or PyTorch
+fallback: a missing library or a non-sm_100 device raises.
+"""
+import torch
+
+device = torch.device("cuda") if torch.cuda.is_available() else "cpu"
+
+from . import _lib  # noqa: E402
+from . import _rng  # noqa: E402
+from . import nets  # noqa: E402
+from . import popart  # noqa: E402
+from . import adv_estimator  # noqa: E402
+from . import agent  # noqa: E402
+from .agent import Agent  # noqa: E402
+from . import replay  # noqa: E402
+from . import augmentations  # noqa: E402
+from . import learning_utils  # noqa: E402
+from . import learning  # noqa: E402
+
+manual_seed = _rng.manual_seed
+
+__all__ = ["Agent", "agent", "nets", "replay", "learning", "learning_utils", "augmentations", "popart",
+           "adv_estimator", "device", "manual_seed"]

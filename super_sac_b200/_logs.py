@@ -1,0 +1,73 @@
+"""Logged scalars without a host sync per value.
+
+The reference calls ``.item()`` ~70 times per REDQ update (learning_utils.py:351-353, :394-397, :95-106,
+learning.py:132-137).  Here kernels write their scalars into slots of one small device buffer; ``finalize()`` does
+ONE device->host copy and fills the dict with plain floats under the reference's key names.
+"""
+import contextlib
+
+import torch
+
+_defer_depth = 0
+
+
+@contextlib.contextmanager
+def deferred():
+    """Inside this context ``finalize()`` does not synchronise (used while a CUDA graph is being captured);
+    call ``fetch()`` on the returned logs after the work has run."""
+    global _defer_depth
+    _defer_depth += 1
+    try:
+        yield
+    finally:
+        _defer_depth -= 1
+
+
+class DeviceLogs(dict):
+    def __init__(self, device, capacity=256):
+        super().__init__()
+        self._buf = torch.zeros(capacity, dtype=torch.float32, device=device)
+        self._n = 0
+        self._pending = []  # (key, slot, transform)
+
+    def slots(self, n):
+        """Reserve n consecutive float slots; returns (tensor view, first slot index)."""
+        if self._n + n > self._buf.numel():
+            raise RuntimeError("DeviceLogs: out of slots")
+        v = self._buf[self._n:self._n + n]
+        first = self._n
+        self._n += n
+        return v, first
+
+    def defer(self, key, slot, transform=None):
+        self._pending.append((key, slot, transform))
+
+    def put_tensor(self, key, scalar_tensor, transform=None):
+        """Copy a 0-d / 1-element device tensor into a slot (no sync) and register it under ``key``."""
+        v, s = self.slots(1)
+        v.copy_(scalar_tensor.reshape(1))
+        self.defer(key, s, transform)
+
+    def finalize(self):
+        if _defer_depth > 0:
+            return self
+        return self.fetch()
+
+    def fetch(self, keep=False):
+        """Resolve pending entries with one device->host copy.  keep=True leaves them registered so the same
+        buffer can be read again after the next graph replay."""
+        if self._pending:
+            host = self._buf[: self._n].cpu()  # the one sync
+            for key, slot, transform in self._pending:
+                val = float(host[slot])
+                self[key] = transform(val) if transform is not None else val
+            if not keep:
+                self._pending = []
+        return self
+
+
+def as_device_logs(logs, device):
+    """Update functions accept a plain dict too (reference signature); values are then synced on finalize into it."""
+    if isinstance(logs, DeviceLogs):
+        return logs, None
+    return DeviceLogs(device), logs

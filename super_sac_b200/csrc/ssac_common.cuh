@@ -1,0 +1,67 @@
+// Shared helpers for libssac_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <string>
+
+#include "../../include/ssac_b200.h"
+
+namespace ssac {
+
+void set_error(const std::string& msg);
+int fail(int code, const char* what);
+
+#define SSAC_REQUIRE(cond, msg)                               \
+  do {                                                        \
+    if (!(cond)) return ::ssac::fail(SSAC_E_BADARG, msg);     \
+  } while (0)
+
+#define SSAC_CHECK_LAUNCH(name)                                        \
+  do {                                                                 \
+    cudaError_t e__ = cudaGetLastError();                              \
+    if (e__ != cudaSuccess) {                                          \
+      ::ssac::set_error(std::string(name) + ": " + cudaGetErrorString(e__)); \
+      return (int)e__;                                                 \
+    }                                                                  \
+  } while (0)
+
+constexpr int kNumSMs = 148;  // B200
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block-wide reductions for blockDim.x <= 1024 (multiple of 32).  `scratch` is 32 floats of shared memory.
+// Every thread gets the result.
+template <typename Op>
+__device__ __forceinline__ float block_reduce(float v, float* scratch, Op op, float identity) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();  // protect scratch reuse
+  if (lane == 0) scratch[wid] = v;
+  __syncthreads();
+  float r = (lane < nw) ? scratch[lane] : identity;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) r = op(r, __shfl_xor_sync(0xffffffffu, r, o));
+  return r;
+}
+struct OpSum { __device__ float operator()(float a, float b) const { return a + b; } };
+struct OpMax { __device__ float operator()(float a, float b) const { return fmaxf(a, b); } };
+struct OpMin { __device__ float operator()(float a, float b) const { return fminf(a, b); } };
+
+}  // namespace ssac

@@ -1,0 +1,234 @@
+// Ensemble MLP forward / backward, fp32 FFMA implementation (impl = 1).  sm_100a.
+//
+// One generic grouped, tiled SGEMM with fused epilogues serves every layer of the G stacked 3-Linear MLPs
+// (agent.py:13-40 Critic, nets/mlps.py:113-129 ContinuousCritic, :11-41 / :78-93 actors) and of their backward:
+//   NT  C = A * W^T (+bias, relu)            forward layers        (nn.Linear, weight [out,in])
+//   NN  C = (A * W (+s*extra)) .* (mask>0)   backward data path    dZ_prev = (dZ * W) .* relu'
+//   TN  C = A^T * B (+colsum)                backward weight path  dW = dZ^T * act, db = colsum(dZ)
+// This is the exact-fp32 path (the reference runs fp32 SGEMM); the tcgen05 path (impl = 2) in
+// ssac_mlp_tc.cu is checked against it.
+#include "ssac_common.cuh"
+
+namespace ssac {
+
+enum { L_NT = 0, L_NN = 1, L_TN = 2 };
+
+struct GemmP {
+  const float* A; int64_t lda, a_gs;
+  const float* Bm; int64_t ldb, b_gs;
+  const int32_t* b_index;  // group -> weight block (REDQ subset); NULL = identity
+  float* C; int64_t ldc, c_gs;
+  const float* bias; int64_t bias_gs;
+  const float* mask; int64_t ldmask, mask_gs;
+  const float* extra; int64_t ldextra, extra_gs; float extra_scale;
+  float* colsum; int64_t colsum_gs;
+  int M, N, K;
+  int relu, accumulate;
+};
+
+constexpr int BM = 64, BN = 64, BK = 16, PADT = 4;
+
+// tile of a K-contiguous source ([rows][K] row-major) -> smem [BK][64+PADT] (transposed on the way in)
+__device__ __forceinline__ void load_kcontig(float (*S)[BM + PADT], const float* __restrict__ src, int64_t ld, int row0,
+                                             int nrows, int k0, int K) {
+  const int t = threadIdx.x, k = t & 15, r0 = t >> 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + 16 * i;
+    float v = 0.f;
+    if (row0 + r < nrows && k0 + k < K) v = __ldg(src + (int64_t)(row0 + r) * ld + k0 + k);
+    S[k][r] = v;
+  }
+}
+// tile of an MN-contiguous source ([K][cols] row-major) -> smem [BK][64+PADT]
+__device__ __forceinline__ void load_mncontig(float (*S)[BM + PADT], const float* __restrict__ src, int64_t ld, int col0,
+                                              int ncols, int k0, int K) {
+  const int t = threadIdx.x, c = t & 63, kk0 = t >> 6;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int kk = kk0 + 4 * i;
+    float v = 0.f;
+    if (col0 + c < ncols && k0 + kk < K) v = __ldg(src + (int64_t)(k0 + kk) * ld + col0 + c);
+    S[kk][c] = v;
+  }
+}
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(256) grouped_gemm_kernel(GemmP p) {
+  __shared__ __align__(16) float As[BK][BM + PADT];
+  __shared__ __align__(16) float Bs[BK][BN + PADT];
+  const int g = blockIdx.z;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int wg = p.b_index ? p.b_index[g] : g;
+  const float* A = p.A + (int64_t)g * p.a_gs;
+  // weights are the B operand for NT / NN; for TN the B operand is an activation (indexed by group)
+  const float* Bm = p.Bm + (int64_t)(LAYOUT == L_TN ? g : wg) * p.b_gs;
+  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float cs = 0.f;  // column-sum accumulator (TN, n-tile 0, threads < BM)
+  const bool do_colsum = (LAYOUT == L_TN) && p.colsum != nullptr && blockIdx.x == 0;
+
+  for (int k0 = 0; k0 < p.K; k0 += BK) {
+    if (LAYOUT == L_TN) load_mncontig(As, A, p.lda, m0, p.M, k0, p.K);
+    else load_kcontig(As, A, p.lda, m0, p.M, k0, p.K);
+    if (LAYOUT == L_NT) load_kcontig(Bs, Bm, p.ldb, n0, p.N, k0, p.K);
+    else load_mncontig(Bs, Bm, p.ldb, n0, p.N, k0, p.K);
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (do_colsum && t < BM) {
+#pragma unroll
+      for (int kk = 0; kk < BK; ++kk) cs += As[kk][t];
+    }
+    __syncthreads();
+  }
+
+  float* C = p.C + (int64_t)(LAYOUT == L_TN ? wg : g) * p.c_gs;
+  const float* bias = p.bias ? p.bias + (int64_t)wg * p.bias_gs : nullptr;
+  const float* mask = p.mask ? p.mask + (int64_t)g * p.mask_gs : nullptr;
+  const float* extra = p.extra ? p.extra + (int64_t)g * p.extra_gs : nullptr;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= p.N) continue;
+      float v = acc[i][j];
+      if (bias) v += bias[n];
+      if (p.relu) v = fmaxf(v, 0.f);
+      if (extra) v += p.extra_scale * extra[(int64_t)m * p.ldextra + n];
+      if (mask) v = (mask[(int64_t)m * p.ldmask + n] > 0.f) ? v : 0.f;
+      float* c = C + (int64_t)m * p.ldc + n;
+      *c = p.accumulate ? (*c + v) : v;
+    }
+  }
+  if (do_colsum && t < BM && m0 + t < p.M) {
+    float* c = p.colsum + (int64_t)wg * p.colsum_gs + m0 + t;
+    *c = p.accumulate ? (*c + cs) : cs;
+  }
+}
+
+static int launch_gemm(int layout, const GemmP& p, int G, cudaStream_t s, const char* what) {
+  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, G);
+  if (layout == L_NT) grouped_gemm_kernel<L_NT><<<grid, 256, 0, s>>>(p);
+  else if (layout == L_NN) grouped_gemm_kernel<L_NN><<<grid, 256, 0, s>>>(p);
+  else grouped_gemm_kernel<L_TN><<<grid, 256, 0, s>>>(p);
+  SSAC_CHECK_LAUNCH(what);
+  return 0;
+}
+
+static GemmP blank() {
+  GemmP p;
+  p.A = nullptr; p.lda = 0; p.a_gs = 0; p.Bm = nullptr; p.ldb = 0; p.b_gs = 0; p.b_index = nullptr;
+  p.C = nullptr; p.ldc = 0; p.c_gs = 0; p.bias = nullptr; p.bias_gs = 0; p.mask = nullptr; p.ldmask = 0; p.mask_gs = 0;
+  p.extra = nullptr; p.ldextra = 0; p.extra_gs = 0; p.extra_scale = 0.f; p.colsum = nullptr; p.colsum_gs = 0;
+  p.M = p.N = p.K = 0; p.relu = 0; p.accumulate = 0;
+  return p;
+}
+
+int mlp_forward_simt(const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
+                     const float* b3, const int32_t* net_index, int G, int D, int H, int O, const float* x, int64_t ldx,
+                     int64_t x_gs, int B, float* h1, float* h2, float* y, cudaStream_t s) {
+  SSAC_REQUIRE(h1 && h2, "ssac_mlp_forward(impl=1): h1/h2 buffers are required");
+  GemmP p = blank();
+  // layer 1: h1 = relu(x W1^T + b1)
+  p.A = x; p.lda = ldx; p.a_gs = x_gs; p.Bm = W1; p.ldb = D; p.b_gs = (int64_t)H * D; p.b_index = net_index;
+  p.C = h1; p.ldc = H; p.c_gs = (int64_t)B * H; p.bias = b1; p.bias_gs = H; p.relu = 1; p.M = B; p.N = H; p.K = D;
+  int rc = launch_gemm(L_NT, p, G, s, "mlp_forward L1");
+  if (rc) return rc;
+  // layer 2: h2 = relu(h1 W2^T + b2)
+  p.A = h1; p.lda = H; p.a_gs = (int64_t)B * H; p.Bm = W2; p.ldb = H; p.b_gs = (int64_t)H * H;
+  p.C = h2; p.bias = b2; p.K = H;
+  rc = launch_gemm(L_NT, p, G, s, "mlp_forward L2");
+  if (rc) return rc;
+  // layer 3: y = h2 W3^T + b3
+  p.A = h2; p.Bm = W3; p.ldb = H; p.b_gs = (int64_t)O * H; p.C = y; p.ldc = O; p.c_gs = (int64_t)B * O;
+  p.bias = b3; p.bias_gs = O; p.relu = 0; p.N = O; p.K = H;
+  return launch_gemm(L_NT, p, G, s, "mlp_forward L3");
+}
+
+int mlp_backward_simt(const float* W1, const float* W2, const float* W3, const int32_t* net_index, int G, int D, int H,
+                      int O, const float* x, int64_t ldx, int64_t x_gs, int B, const float* h1, const float* h2,
+                      const float* dy, const float* dh2_extra, float extra_scale, float* gW1, float* gb1, float* gW2,
+                      float* gb2, float* gW3, float* gb3, int accumulate, float* dx, int64_t lddx, float* ws,
+                      cudaStream_t s) {
+  const bool need_dw = gW1 != nullptr;
+  SSAC_REQUIRE(!need_dw || (gb1 && gW2 && gb2 && gW3 && gb3), "ssac_mlp_backward: weight grads come as a full set");
+  SSAC_REQUIRE(!need_dw || net_index == nullptr, "ssac_mlp_backward: weight grads with a net subset are unsupported");
+  SSAC_REQUIRE(ws, "ssac_mlp_backward: workspace required");
+  SSAC_REQUIRE(dy || dh2_extra, "ssac_mlp_backward: need dy or dh2_extra");
+  float* dz2 = ws;
+  float* dz1 = ws + (int64_t)G * B * H;
+  int rc;
+  GemmP p = blank();
+  // dz2 = (dy W3 + s*extra) .* (h2 > 0)
+  p.A = dy; p.lda = O; p.a_gs = (int64_t)B * O; p.Bm = W3; p.ldb = H; p.b_gs = (int64_t)O * H; p.b_index = net_index;
+  p.C = dz2; p.ldc = H; p.c_gs = (int64_t)B * H; p.mask = h2; p.ldmask = H; p.mask_gs = (int64_t)B * H;
+  p.extra = dh2_extra; p.ldextra = H; p.extra_gs = (int64_t)B * H; p.extra_scale = extra_scale;
+  p.M = B; p.N = H; p.K = dy ? O : 0;
+  if (!dy) p.A = h2;  // never dereferenced (K = 0), keeps pointer arithmetic valid
+  rc = launch_gemm(L_NN, p, G, s, "mlp_backward dz2");
+  if (rc) return rc;
+  if (need_dw) {
+    if (dy) {
+      // gW3 = dy^T h2, gb3 = colsum(dy)
+      GemmP q = blank();
+      q.A = dy; q.lda = O; q.a_gs = (int64_t)B * O; q.Bm = h2; q.ldb = H; q.b_gs = (int64_t)B * H;
+      q.C = gW3; q.ldc = H; q.c_gs = (int64_t)O * H; q.colsum = gb3; q.colsum_gs = O; q.M = O; q.N = H; q.K = B;
+      q.accumulate = accumulate;
+      rc = launch_gemm(L_TN, q, G, s, "mlp_backward gW3");
+      if (rc) return rc;
+    } else if (!accumulate) {
+      cudaMemsetAsync(gW3, 0, sizeof(float) * (size_t)G * O * H, s);
+      cudaMemsetAsync(gb3, 0, sizeof(float) * (size_t)G * O, s);
+    }
+    // gW2 = dz2^T h1, gb2 = colsum(dz2)
+    GemmP q = blank();
+    q.A = dz2; q.lda = H; q.a_gs = (int64_t)B * H; q.Bm = h1; q.ldb = H; q.b_gs = (int64_t)B * H;
+    q.C = gW2; q.ldc = H; q.c_gs = (int64_t)H * H; q.colsum = gb2; q.colsum_gs = H; q.M = H; q.N = H; q.K = B;
+    q.accumulate = accumulate;
+    rc = launch_gemm(L_TN, q, G, s, "mlp_backward gW2");
+    if (rc) return rc;
+  }
+  // dz1 = (dz2 W2) .* (h1 > 0)
+  p = blank();
+  p.A = dz2; p.lda = H; p.a_gs = (int64_t)B * H; p.Bm = W2; p.ldb = H; p.b_gs = (int64_t)H * H; p.b_index = net_index;
+  p.C = dz1; p.ldc = H; p.c_gs = (int64_t)B * H; p.mask = h1; p.ldmask = H; p.mask_gs = (int64_t)B * H;
+  p.M = B; p.N = H; p.K = H;
+  rc = launch_gemm(L_NN, p, G, s, "mlp_backward dz1");
+  if (rc) return rc;
+  if (need_dw) {
+    // gW1 = dz1^T x, gb1 = colsum(dz1)
+    GemmP q = blank();
+    q.A = dz1; q.lda = H; q.a_gs = (int64_t)B * H; q.Bm = x; q.ldb = ldx; q.b_gs = x_gs;
+    q.C = gW1; q.ldc = D; q.c_gs = (int64_t)H * D; q.colsum = gb1; q.colsum_gs = H; q.M = H; q.N = D; q.K = B;
+    q.accumulate = accumulate;
+    rc = launch_gemm(L_TN, q, G, s, "mlp_backward gW1");
+    if (rc) return rc;
+  }
+  if (dx) {
+    // dx = dz1 W1
+    p = blank();
+    p.A = dz1; p.lda = H; p.a_gs = (int64_t)B * H; p.Bm = W1; p.ldb = D; p.b_gs = (int64_t)H * D; p.b_index = net_index;
+    p.C = dx; p.ldc = lddx; p.c_gs = (int64_t)B * lddx; p.M = B; p.N = D; p.K = H;
+    rc = launch_gemm(L_NN, p, G, s, "mlp_backward dx");
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+}  // namespace ssac

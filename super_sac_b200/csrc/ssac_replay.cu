@@ -1,0 +1,409 @@
+// Device-resident replay: Philox draws, coalesced batch gather, fused pixel gather + DrQ/DrQv2 shift,
+// float64 segment trees for prioritised replay.  sm_100a.  Integer / byte / float64 work: bit-exact with the
+// reference (replay.py, augmentations.py) -- see include/ssac_b200.h for the lines each entry point restates.
+#include "ssac_common.cuh"
+
+namespace ssac {
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al.), counter = (i, stream, offset_lo, offset_hi), key = seed
+// ------------------------------------------------------------------------------------------------
+struct Philox {
+  uint32_t c[4];
+  __device__ Philox(uint64_t seed, uint32_t i, uint32_t stream, uint64_t offset) {
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    c[0] = i; c[1] = stream; c[2] = (uint32_t)offset; c[3] = (uint32_t)(offset >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+      const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+      const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+      c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+      k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+  }
+};
+
+__device__ __forceinline__ float u01(uint32_t x) {  // (0, 1]
+  return ((float)(x >> 8) + 1.0f) * (1.0f / 16777216.0f);
+}
+
+__global__ void __launch_bounds__(256) rng_fill_kernel(uint64_t* __restrict__ rng, int64_t* __restrict__ idx,
+                                                       int64_t n_idx, int64_t n_filled,
+                                                       const int64_t* __restrict__ n_filled_dev,
+                                                       float* __restrict__ normal,
+                                                       int64_t n_normal, int32_t* __restrict__ subset, int n_subsets,
+                                                       int N, int M, int32_t* __restrict__ shift, int64_t n_shift,
+                                                       int shift_range) {
+  const uint64_t seed = rng[0], offset = rng[1];
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+  if (idx) {
+    if (n_filled_dev) n_filled = *n_filled_dev;
+    for (int64_t i = tid; i < n_idx; i += nth) {
+      Philox p(seed, (uint32_t)i, 0u, offset);
+      const uint64_t r = ((uint64_t)p.c[0] << 32) | p.c[1];
+      idx[i] = (int64_t)(r % (uint64_t)n_filled);
+    }
+  }
+  if (normal) {
+    const int64_t n4 = (n_normal + 3) / 4;
+    for (int64_t i = tid; i < n4; i += nth) {
+      Philox p(seed, (uint32_t)i, 1u, offset);
+      float z[4];
+      const float r0 = sqrtf(-2.f * logf(u01(p.c[0]))), r1 = sqrtf(-2.f * logf(u01(p.c[2])));
+      float s0, c0, s1, c1;
+      sincospif(2.f * u01(p.c[1]), &s0, &c0);
+      sincospif(2.f * u01(p.c[3]), &s1, &c1);
+      z[0] = r0 * c0; z[1] = r0 * s0; z[2] = r1 * c1; z[3] = r1 * s1;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (4 * i + j < n_normal) normal[4 * i + j] = z[j];
+    }
+  }
+  if (subset) {
+    // partial Fisher-Yates over {0..N-1}; N <= 64 (checked on the host)
+    for (int64_t s = tid; s < n_subsets; s += nth) {
+      uint8_t perm[64];
+      for (int k = 0; k < N; ++k) perm[k] = (uint8_t)k;
+      for (int k = 0; k < M; ++k) {
+        Philox p(seed, (uint32_t)(s * 64 + k), 2u, offset);
+        const int j = k + (int)(p.c[0] % (uint32_t)(N - k));
+        const uint8_t t = perm[k]; perm[k] = perm[j]; perm[j] = t;
+        subset[s * M + k] = perm[k];
+      }
+    }
+  }
+  if (shift) {
+    for (int64_t i = tid; i < n_shift; i += nth) {
+      Philox p(seed, (uint32_t)i, 3u, offset);
+      shift[i] = (int32_t)(p.c[0] % (uint32_t)shift_range);
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long prev = atomicAdd((unsigned long long*)&rng[2], 1ull);
+    if (prev == (unsigned long long)gridDim.x - 1ull) {
+      rng[1] = offset + 1;
+      rng[2] = 0;
+      __threadfence();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// row gather: replay.py:76-83 (+ the .float() of learning_utils.py:193-197)
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxGatherArrays = 16;
+struct GatherArgs {
+  const void* src[kMaxGatherArrays];
+  void* dst[kMaxGatherArrays];
+  int64_t row_elems[kMaxGatherArrays];
+  int64_t dst_ld[kMaxGatherArrays];
+  int32_t mode[kMaxGatherArrays];
+};
+
+__global__ void __launch_bounds__(256) gather_rows_kernel(GatherArgs args, const int64_t* __restrict__ idx, int B) {
+  const int k = blockIdx.y;
+  const int64_t re = args.row_elems[k], ld = args.dst_ld[k];
+  const int mode = args.mode[k];
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+  if (mode == 2 && (re & 15) == 0 && ((((uintptr_t)args.src[k]) | ((uintptr_t)args.dst[k])) & 15) == 0 &&
+      ((ld & 15) == 0)) {
+    // raw rows, 16-byte vectors (pixel rows: 63504 B = 3969 x 16)
+    const int64_t rv = re >> 4, ldv = ld >> 4;
+    const int4* src = (const int4*)args.src[k];
+    int4* dst = (int4*)args.dst[k];
+    for (int64_t i = tid; i < (int64_t)B * rv; i += nth) {
+      const int64_t b = i / rv, e = i - b * rv;
+      dst[b * ldv + e] = __ldg(src + idx[b] * rv + e);
+    }
+    return;
+  }
+  const int64_t total = (int64_t)B * re;
+  for (int64_t i = tid; i < total; i += nth) {
+    const int64_t b = i / re, e = i - b * re;
+    const int64_t row = idx[b];
+    if (mode == 0) {
+      ((float*)args.dst[k])[b * ld + e] = __ldg((const float*)args.src[k] + row * re + e);
+    } else if (mode == 1) {
+      ((float*)args.dst[k])[b * ld + e] = (float)__ldg((const uint8_t*)args.src[k] + row * re + e);
+    } else {
+      ((uint8_t*)args.dst[k])[b * ld + e] = __ldg((const uint8_t*)args.src[k] + row * re + e);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused pixel gather + shift (+noise) + uint8->fp32: augmentations.py:165-269, learning_utils.py:193-206
+// One block per (sample, channel-plane): the u8 plane is staged in shared memory with 16-byte loads, then
+// shifted rows are written as float4.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int map_coord(int p, int n, int pad_mode) {
+  // p = output coord + shift - pad, i.e. a coordinate in the un-padded image's frame
+  if (pad_mode == 2) {  // reflect (nn.ReflectionPad2d)
+    if (p < 0) p = -p;
+    if (p >= n) p = 2 * (n - 1) - p;
+    return p;
+  }
+  return p < 0 ? 0 : (p >= n ? n - 1 : p);  // replicate
+}
+
+__global__ void __launch_bounds__(256) gather_aug_u8_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst,
+                                                            const int64_t* __restrict__ idx,
+                                                            const int32_t* __restrict__ shift,
+                                                            const float* __restrict__ noise, int C, int H, int W,
+                                                            int pad, int pad_mode, int aug_rows) {
+  extern __shared__ __align__(16) uint8_t plane[];
+  const int b = blockIdx.x / C, c = blockIdx.x - b * C;
+  const int64_t plane_elems = (int64_t)H * W;
+  const uint8_t* sp = src + (idx[b] * C + c) * plane_elems;
+  if ((plane_elems & 15) == 0 && (((uintptr_t)sp) & 15) == 0) {
+    const int4* sp4 = (const int4*)sp;
+    int4* pl4 = (int4*)plane;
+    for (int i = threadIdx.x; i < (int)(plane_elems >> 4); i += blockDim.x) pl4[i] = __ldg(sp4 + i);
+  } else {
+    for (int i = threadIdx.x; i < (int)plane_elems; i += blockDim.x) plane[i] = __ldg(sp + i);
+  }
+  __syncthreads();
+  const bool aug = (b < aug_rows) && pad_mode != 0;
+  const int sx = aug ? shift[2 * b] - pad : 0, sy = aug ? shift[2 * b + 1] - pad : 0;
+  float* dp = dst + ((int64_t)b * C + c) * plane_elems;
+  const float* np = (noise && aug) ? noise + ((int64_t)b * C + c) * plane_elems : nullptr;
+  if ((W & 3) == 0 && (((uintptr_t)dp) & 15) == 0) {
+    const int w4 = W >> 2;
+    for (int i = threadIdx.x; i < H * w4; i += blockDim.x) {
+      const int y = i / w4, x0 = (i - y * w4) << 2;
+      const uint8_t* row = plane + (aug ? map_coord(y + sy, H, pad_mode) : y) * W;
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int xs = aug ? map_coord(x0 + j + sx, W, pad_mode) : x0 + j;
+        v[j] = (float)row[xs];
+      }
+      if (np) {
+        const float4 nz = __ldg((const float4*)(np + (int64_t)y * W + x0));
+        v[0] += nz.x; v[1] += nz.y; v[2] += nz.z; v[3] += nz.w;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = fminf(fmaxf(v[j], 0.f), 255.f);
+      }
+      *(float4*)(dp + (int64_t)y * W + x0) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  } else {
+    for (int i = threadIdx.x; i < H * W; i += blockDim.x) {
+      const int y = i / W, x = i - y * W;
+      const int ys = aug ? map_coord(y + sy, H, pad_mode) : y, xs = aug ? map_coord(x + sx, W, pad_mode) : x;
+      float v = (float)plane[ys * W + xs];
+      if (np) v = fminf(fmaxf(v + np[i], 0.f), 255.f);
+      dp[i] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// float64 segment trees: replay.py:207-353
+// ------------------------------------------------------------------------------------------------
+// small update (n <= 1024): one block, last write wins on duplicate indices (numpy fancy assignment),
+// then the touched ancestors are recomputed level by level.
+__global__ void __launch_bounds__(1024) tree_set_small_kernel(double* __restrict__ sum_tree,
+                                                              double* __restrict__ min_tree, int64_t capacity,
+                                                              const int64_t* __restrict__ idx,
+                                                              const double* __restrict__ val, int n) {
+  __shared__ int64_t sidx[1024];
+  const int t = threadIdx.x;
+  if (t < n) sidx[t] = idx[t];
+  __syncthreads();
+  int64_t node = 0;
+  if (t < n) {
+    bool last = true;
+    for (int j = t + 1; j < n; ++j)
+      if (sidx[j] == sidx[t]) { last = false; break; }
+    node = sidx[t] + capacity;
+    if (last) {
+      sum_tree[node] = val[t];
+      min_tree[node] = val[t];
+    }
+  }
+  __threadfence_block();
+  __syncthreads();
+  for (int64_t c = capacity; c > 1; c >>= 1) {
+    if (t < n) {
+      node >>= 1;
+      const double a = sum_tree[2 * node], b = sum_tree[2 * node + 1];
+      const double ma = min_tree[2 * node], mb = min_tree[2 * node + 1];
+      sum_tree[node] = a + b;
+      min_tree[node] = fmin(ma, mb);
+    }
+    __threadfence_block();
+    __syncthreads();
+  }
+}
+
+__global__ void tree_set_leaves_kernel(double* __restrict__ sum_tree, double* __restrict__ min_tree, int64_t capacity,
+                                       const int64_t* __restrict__ idx, const double* __restrict__ val, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    sum_tree[capacity + idx[i]] = val[i];
+    min_tree[capacity + idx[i]] = val[i];
+  }
+}
+__global__ void tree_rebuild_level_kernel(double* __restrict__ sum_tree, double* __restrict__ min_tree,
+                                          int64_t level_start, int64_t level_n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < level_n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t node = level_start + i;
+    sum_tree[node] = sum_tree[2 * node] + sum_tree[2 * node + 1];
+    min_tree[node] = fmin(min_tree[2 * node], min_tree[2 * node + 1]);
+  }
+}
+
+// SegmentTree.reduce(0, end) with the reference's recursion order (replay.py:232-261): the result is the
+// right-nested sum v1 + (v2 + (v3 + ...)) of the maximal left-aligned nodes.
+__device__ double tree_prefix_total(const double* __restrict__ tree, int64_t capacity, int64_t end_inclusive) {
+  double vals[64];
+  int nv = 0;
+  int64_t node = 1, lo = 0, hi = capacity - 1;
+  while (true) {
+    if (end_inclusive == hi) { vals[nv++] = tree[node]; break; }
+    const int64_t mid = (lo + hi) / 2;
+    if (end_inclusive <= mid) { node = 2 * node; hi = mid; }
+    else { vals[nv++] = tree[2 * node]; node = 2 * node + 1; lo = mid + 1; }
+  }
+  double acc = vals[nv - 1];
+  for (int i = nv - 2; i >= 0; --i) acc = vals[i] + acc;
+  return acc;
+}
+
+__global__ void tree_sample_kernel(const double* __restrict__ sum_tree, const double* __restrict__ min_tree,
+                                   int64_t capacity, int64_t n_filled, const double* __restrict__ u, int B, double beta,
+                                   int64_t* __restrict__ idx_out, double* __restrict__ w_out) {
+  __shared__ double total_sh;
+  if (threadIdx.x == 0) {
+    // replay.py:165: self._it_sum.sum(0, len-1) -> reduce(end = len-1) -> inclusive end len-2
+    total_sh = tree_prefix_total(sum_tree, capacity, n_filled - 2);
+  }
+  __syncthreads();
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double prefix = u[b] * total_sh;
+  int64_t idx = 1;
+  while (idx < capacity) {  // replay.py:320-335
+    idx = 2 * idx;
+    const double v = sum_tree[idx];
+    if (!(v > prefix)) { prefix -= v; idx += 1; }
+  }
+  const int64_t leaf = idx - capacity;
+  idx_out[b] = leaf;
+  if (w_out) {  // replay.py:173-176
+    const double sum_all = sum_tree[1];
+    const double p_min = min_tree[1] / sum_all;
+    const double max_weight = pow(p_min * (double)n_filled, -beta);
+    const double p_sample = sum_tree[capacity + leaf] / sum_all;
+    w_out[b] = pow(p_sample * (double)n_filled, -beta) / max_weight;
+  }
+}
+
+}  // namespace ssac
+
+using namespace ssac;
+
+extern "C" {
+
+int ssac_rng_fill(uint64_t* rng, int64_t* idx, int64_t n_idx, int64_t n_filled, const int64_t* n_filled_dev,
+                  float* normal, int64_t n_normal,
+                  int32_t* subset, int n_subsets, int N, int M, int32_t* shift, int64_t n_shift, int shift_range,
+                  void* stream) {
+  SSAC_REQUIRE(rng, "ssac_rng_fill: null rng state");
+  SSAC_REQUIRE(!idx || n_filled > 0 || n_filled_dev, "ssac_rng_fill: n_filled must be > 0");
+  SSAC_REQUIRE(!subset || (N > 0 && N <= 64 && M > 0 && M <= N), "ssac_rng_fill: need 0 < M <= N <= 64");
+  SSAC_REQUIRE(!shift || shift_range > 0, "ssac_rng_fill: shift_range must be > 0");
+  int64_t work = n_idx;
+  if (normal && (n_normal + 3) / 4 > work) work = (n_normal + 3) / 4;
+  if (shift && n_shift > work) work = n_shift;
+  if (subset && n_subsets > work) work = n_subsets;
+  int grid = (int)((work + 255) / 256);
+  if (grid < 1) grid = 1;
+  if (grid > 4 * kNumSMs) grid = 4 * kNumSMs;
+  rng_fill_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rng, idx, n_idx, n_filled, n_filled_dev, normal, n_normal, subset,
+                                                          n_subsets, N, M, shift, n_shift, shift_range);
+  SSAC_CHECK_LAUNCH("ssac_rng_fill");
+  return 0;
+}
+
+int ssac_gather_rows(const void* const* srcs, void* const* dsts, const int64_t* row_elems, const int64_t* dst_ld,
+                     const int32_t* mode, int n_arrays, const int64_t* idx, int B, void* stream) {
+  SSAC_REQUIRE(n_arrays > 0 && n_arrays <= kMaxGatherArrays, "ssac_gather_rows: 1..16 arrays");
+  SSAC_REQUIRE(srcs && dsts && row_elems && dst_ld && mode && idx && B > 0, "ssac_gather_rows: bad args");
+  GatherArgs a;
+  int64_t max_work = 0;
+  for (int k = 0; k < n_arrays; ++k) {
+    SSAC_REQUIRE(srcs[k] && dsts[k] && row_elems[k] > 0 && dst_ld[k] >= row_elems[k], "ssac_gather_rows: bad array");
+    SSAC_REQUIRE(mode[k] >= 0 && mode[k] <= 2, "ssac_gather_rows: mode must be 0, 1 or 2");
+    a.src[k] = srcs[k]; a.dst[k] = dsts[k]; a.row_elems[k] = row_elems[k]; a.dst_ld[k] = dst_ld[k]; a.mode[k] = mode[k];
+    int64_t w = (int64_t)B * (mode[k] == 2 && (row_elems[k] & 15) == 0 ? row_elems[k] >> 4 : row_elems[k]);
+    if (w > max_work) max_work = w;
+  }
+  int gx = (int)((max_work + 255) / 256);
+  if (gx < 1) gx = 1;
+  if (gx > 8 * kNumSMs) gx = 8 * kNumSMs;
+  dim3 grid(gx, n_arrays);
+  gather_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, idx, B);
+  SSAC_CHECK_LAUNCH("ssac_gather_rows");
+  return 0;
+}
+
+int ssac_gather_aug_u8(const uint8_t* src, float* dst, const int64_t* idx, const int32_t* shift, const float* noise,
+                       int B, int C, int H, int W, int pad, int pad_mode, int aug_rows, void* stream) {
+  SSAC_REQUIRE(src && dst && idx && B > 0 && C > 0 && H > 0 && W > 0, "ssac_gather_aug_u8: bad args");
+  SSAC_REQUIRE(pad_mode >= 0 && pad_mode <= 2, "ssac_gather_aug_u8: pad_mode must be 0, 1 or 2");
+  SSAC_REQUIRE(pad_mode == 0 || shift, "ssac_gather_aug_u8: shift required when pad_mode != 0");
+  SSAC_REQUIRE(pad_mode != 2 || (pad < H && pad < W), "ssac_gather_aug_u8: reflect pad must be < image size");
+  const size_t smem = ((size_t)H * W + 15) & ~(size_t)15;
+  SSAC_REQUIRE(smem <= 200 * 1024, "ssac_gather_aug_u8: image plane too large for shared memory");
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(gather_aug_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error(std::string("ssac_gather_aug_u8 attr: ") + cudaGetErrorString(e)); return (int)e; }
+  }
+  gather_aug_u8_kernel<<<B * C, 256, smem, (cudaStream_t)stream>>>(src, dst, idx, shift, noise, C, H, W, pad, pad_mode,
+                                                                   aug_rows);
+  SSAC_CHECK_LAUNCH("ssac_gather_aug_u8");
+  return 0;
+}
+
+int ssac_tree_set(double* sum_tree, double* min_tree, int64_t capacity, const int64_t* idx, const double* val,
+                  int64_t n, void* stream) {
+  SSAC_REQUIRE(sum_tree && min_tree && idx && val, "ssac_tree_set: null pointer");
+  SSAC_REQUIRE(capacity > 0 && (capacity & (capacity - 1)) == 0, "ssac_tree_set: capacity must be a power of two");
+  if (n <= 0) return 0;
+  if (n <= 1024) {
+    tree_set_small_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(sum_tree, min_tree, capacity, idx, val, (int)n);
+    SSAC_CHECK_LAUNCH("ssac_tree_set(small)");
+    return 0;
+  }
+  // bulk write (load_experience / batched push: indices are distinct) + full rebuild, level by level
+  int grid = (int)((n + 255) / 256);
+  if (grid > 8 * kNumSMs) grid = 8 * kNumSMs;
+  tree_set_leaves_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(sum_tree, min_tree, capacity, idx, val, n);
+  SSAC_CHECK_LAUNCH("ssac_tree_set(leaves)");
+  for (int64_t level_n = capacity >> 1; level_n >= 1; level_n >>= 1) {
+    int g = (int)((level_n + 255) / 256);
+    if (g > 8 * kNumSMs) g = 8 * kNumSMs;
+    tree_rebuild_level_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(sum_tree, min_tree, level_n, level_n);
+    SSAC_CHECK_LAUNCH("ssac_tree_set(level)");
+  }
+  return 0;
+}
+
+int ssac_tree_sample(const double* sum_tree, const double* min_tree, int64_t capacity, int64_t n_filled,
+                     const double* u01_dev, int B, double beta, int64_t* idx_out, double* w_out, void* stream) {
+  SSAC_REQUIRE(sum_tree && min_tree && u01_dev && idx_out && B > 0, "ssac_tree_sample: bad args");
+  SSAC_REQUIRE(capacity > 0 && (capacity & (capacity - 1)) == 0, "ssac_tree_sample: capacity must be a power of two");
+  SSAC_REQUIRE(n_filled >= 2 && n_filled <= capacity, "ssac_tree_sample: need 2 <= n_filled <= capacity");
+  SSAC_REQUIRE(B <= 1024, "ssac_tree_sample: B <= 1024");
+  tree_sample_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(sum_tree, min_tree, capacity, n_filled, u01_dev, B, beta,
+                                                           idx_out, w_out);
+  SSAC_CHECK_LAUNCH("ssac_tree_sample");
+  return 0;
+}
+
+}  // extern "C"

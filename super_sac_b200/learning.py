@@ -1,0 +1,293 @@
+"""The update entry points, drop-in for reference learning.py: critic_update (:18-141), online_actor_update
+(:344-421), alpha_update (:222-263), offline_actor_update (:144-219).
+
+Same signatures, same returned log keys, same arithmetic (fp32) -- but every member's critics run as one grouped
+launch, the backward is explicit (no autograd tape on the ensemble), Adam is one fused pass over the flat parameter
+arena, and the logged scalars come back with a single device->host copy.  The caller still owns the optimizer
+objects, ``log_alphas`` and the target agent exactly as main.py:188-244 / :321 builds them.
+"""
+import random
+
+import torch
+
+from . import _arena, _lib, _logs, _ops, _rng
+from . import learning_utils as lu
+
+
+def _encoder_has_grad_path(s_rep):
+    return torch.is_tensor(s_rep) and s_rep.requires_grad
+
+
+def critic_update(buffer, agent, target_agent, critic_optimizer, encoder_optimizer, log_alphas, batch_size, gamma,
+                  critic_clip, encoder_clip, target_critic_ensemble_n, weighted_bellman_temp, weight_type, pop,
+                  augmenter, encoder_lambda, random_process, noise_clip, aug_mix=0.75, discrete=False, per=False,
+                  update_priorities=False, dr3_coeff=0.0):
+    if discrete:
+        raise NotImplementedError("discrete actions are out of scope")
+    if encoder_lambda:
+        raise NotImplementedError("encoder invariance regulariser (lambda = 0 in every shipped config) is out of scope")
+    ca = agent._critic_arena
+    dev = ca.device
+    _ops.check_cuda(ca.flat)
+    L, stream = _lib.lib(), _lib.stream_ptr()
+    E, N, B = agent.ensemble_size, agent.num_critics, batch_size
+    S, A = lu._dims(agent)
+    logs = _logs.DeviceLogs(dev)
+    loss_v, loss_slot = logs.slots(2)
+    loss_v.zero_()
+    opt = _arena.FlatAdam.attach(critic_optimizer, ca)
+
+    replay_dicts, enc_outs = [], []
+    for i in range(E):
+        rd = lu.sample_move_and_augment(buffer=buffer, batch_size=B, augmenter=augmenter, aug_mix=aug_mix, per=per)
+        td_target, (s1, a1) = lu.compute_td_targets(
+            logs=logs, replay_dict=rd, agent=agent, target_agent=target_agent, log_alphas=log_alphas, ensemble_idx=i,
+            ensemble_n=target_critic_ensemble_n, pop=pop, gamma=gamma, random_process=random_process,
+            noise_clip=noise_clip)
+        w = lu.compute_backup_weights(logs=logs, replay_dict=rd, agent=agent, target_agent=target_agent,
+                                      weight_type=weight_type, weight_temp=weighted_bellman_temp, batch_size=B)
+        o, a, *_ = rd["primary_batch"]
+        packed = lu._packed_of(rd)
+        s_rep = agent.encoder(o)
+        need_ds = _encoder_has_grad_path(s_rep)
+        X = lu._first_layer_input(s_rep, a, packed["XA"] if packed else None, S, A)
+        q, h1, h2 = lu._critic_values(agent, i * N, N, X, B, keep=True)
+        popart = agent.popart[i]
+        dq = torch.empty((N, B, 1), dtype=torch.float32, device=dev)
+        imp = rd["imp_weights"]
+        imp_ptr = imp.float().contiguous() if per else None  # per=False: ones(1), i.e. no weighting (main.py:401)
+        L.critic_loss_seed(q.data_ptr(), N, B, td_target.data_ptr(), w.data_ptr() if torch.is_tensor(w) else None,
+                           None if imp_ptr is None else imp_ptr.data_ptr(), popart.state_ptr() if popart else None,
+                           int(bool(pop)), E, dq.data_ptr(), loss_v.data_ptr(), stream)
+        extra, extra_scale, f1 = None, 0.0, None
+        if dr3_coeff > 0:
+            # DR3 (learning.py:100-108): second forward on (s1, a1); both feature sets carry gradient
+            X1 = packed["X1"] if packed else torch.cat((s1, a1), dim=-1).contiguous()
+            _, h1b, h2b = lu._critic_values(agent, i * N, N, X1, B, keep=True)
+            dv, dslot = logs.slots(1)
+            L.dr3_dot(h2.data_ptr(), h2b.data_ptr(), N, B, ca.H, dv.data_ptr(), stream)
+            logs.defer(f"dr3_dotproduct_{i}", dslot)
+            # critic_loss += dr3 * dot, then the whole loss is divided by E*N (learning.py:108,112)
+            loss_v[0:1].add_(dv, alpha=dr3_coeff / (E * N))
+            extra, extra_scale, f1 = h2b, dr3_coeff / (E * N) / (N * B), (X1, h1b, h2b)
+        dxg = torch.empty((N, B, S + A), dtype=torch.float32, device=dev) if need_ds else None
+        _ops.mlp_backward(ca, i * N, N, X, B, h1, h2, dq, ldx=S + A, dh2_extra=extra, extra_scale=extra_scale,
+                          want_dw=True, accumulate=False, dx=dxg, lddx=S + A)
+        if f1 is not None:
+            X1, h1b, h2b = f1
+            _ops.mlp_backward(ca, i * N, N, X1, B, h1b, h2b, None, ldx=S + A, dh2_extra=h2, extra_scale=extra_scale,
+                              want_dw=True, accumulate=True)
+        if need_ds:
+            enc_outs.append((s_rep, dxg.sum(0)[:, :S]))
+        replay_dicts.append(rd)
+
+    encoder_optimizer.zero_grad()
+    if enc_outs:
+        torch.autograd.backward([s for s, _ in enc_outs], [g for _, g in enc_outs])
+    if critic_clip:
+        opt.grad_norm_sq(stream)
+    if encoder_clip and enc_outs:
+        torch.nn.utils.clip_grad_norm_(agent.encoder.parameters(), encoder_clip)
+    if enc_outs:
+        encoder_optimizer.step()
+    opt.step(stream, max_norm=critic_clip if critic_clip else None)
+
+    logs.defer("losses/last_member_critic_td_error", loss_slot + 1)
+    logs.defer("losses/critic_overall_loss", loss_slot)
+    member = random.choice(range(E))
+    gslot = lu._member_grad_norm_slot(logs, ca, member * N, (member + 1) * N)
+    logs.defer("gradients/critic_random_grad", gslot, transform=lambda v: v**0.5)
+    if enc_outs:
+        gn = torch.linalg.vector_norm(torch.stack([p.grad.norm() for p in agent.encoder.parameters() if p.grad is not None]))
+        logs.put_tensor("gradients/encoder_criticloss_grad_norm", gn)
+    else:
+        logs["gradients/encoder_criticloss_grad_norm"] = 0.0
+    if update_priorities:
+        lu.adjust_priorities(logs, rd, agent, buffer)
+    return logs.finalize(), replay_dicts
+
+
+def online_actor_update(buffer, agent, pop, actor_optimizer, log_alphas, batch_size, clip, random_process, noise_clip,
+                        augmenter, aug_mix, premade_replay_dicts=None, per=False, discrete=False, use_baseline=False):
+    if discrete or use_baseline:
+        raise NotImplementedError("discrete actions / advantage baselines are out of scope")
+    aa, ca = agent._actor_arena, agent._critic_arena
+    dev = aa.device
+    _ops.check_cuda(aa.flat)
+    L, stream = _lib.lib(), _lib.stream_ptr()
+    E, N, B = agent.ensemble_size, agent.num_critics, batch_size
+    S, A = lu._dims(agent)
+    logs = _logs.DeviceLogs(dev)
+    loss_v, loss_slot = logs.slots(1)
+    loss_v.zero_()
+    opt = _arena.FlatAdam.attach(actor_optimizer, aa)
+    for i in range(E):
+        if premade_replay_dicts is not None:
+            rd = premade_replay_dicts[i]
+        else:
+            rd = lu.sample_move_and_augment(buffer=buffer, batch_size=B, augmenter=augmenter, aug_mix=aug_mix, per=per)
+        o, *_ = rd["primary_batch"]
+        packed = lu._packed_of(rd)
+        with torch.no_grad():  # actor gradients do not train the encoder (learning.py:378-380)
+            s_rep = agent.encoder(o)
+        XPI = lu._first_layer_input(s_rep, None, packed["XPI"] if packed else None, S, A)
+        pol = lu._policy_sample(agent, i, XPI, B, S, A, random_process, noise_clip, rsample=True)
+        q, h1c, h2c = lu._critic_values(agent, i * N, N, XPI, B, keep=True)
+        popart = agent.popart[i]
+        dq = torch.empty((N, B, 1), dtype=torch.float32, device=dev)
+        entropy_on = pol["logp"] is not None
+        L.actor_loss_seed(q.data_ptr(), N, B, pol["logp"].data_ptr() if entropy_on else None,
+                          log_alphas[i].data_ptr(), popart.state_ptr() if popart else None, int(bool(pop)), E, None,
+                          dq.data_ptr(), loss_v.data_ptr(), stream)
+        # through the critics to the action: input-gradient only (the reference's critic dW here is discarded anyway)
+        dxg = torch.empty((N, B, S + A), dtype=torch.float32, device=dev)
+        _ops.mlp_backward(ca, i * N, N, XPI, B, h1c, h2c, dq, ldx=S + A, want_dw=False, dx=dxg, lddx=S + A)
+        da = torch.empty((B, A), dtype=torch.float32, device=dev)
+        L.sum_groups(dxg.data_ptr(), N, B, S + A, S, A, da.data_ptr(), stream)
+        O = aa.O
+        dout = torch.empty((1, B, O), dtype=torch.float32, device=dev)
+        if agent.deterministic:
+            L.det_head_backward(pol["tanh_out"].data_ptr(), da.data_ptr(), A, B, A, dout.data_ptr(), stream)
+        else:
+            L.tanh_normal_backward(pol["out"].data_ptr(), pol["eps"].data_ptr(), B, A, float(agent.log_std_low),
+                                   float(agent.log_std_high), da.data_ptr(), A, 1.0 / (E * B),
+                                   log_alphas[i].data_ptr(), dout.data_ptr(), stream)
+        _ops.mlp_backward(aa, i, 1, XPI, B, pol["h1"], pol["h2"], dout, ldx=S + A, want_dw=True, accumulate=False)
+    if clip:
+        opt.grad_norm_sq(stream)
+    opt.step(stream, max_norm=clip if clip else None)
+    member = random.choice(range(E))
+    gslot = lu._member_grad_norm_slot(logs, aa, member, member + 1)
+    logs.defer("gradients/random_actor_online_grad", gslot, transform=lambda v: v**0.5)
+    logs.defer("losses/actor_pg_loss", loss_slot)
+    return logs.finalize()
+
+
+class _AlphaState:
+    """Adam state of one 1-element ``log_alpha`` optimiser (main.py:230-239), kept on the device."""
+
+    def __init__(self, optimizer, log_alpha):
+        self.state = torch.zeros(2, dtype=torch.float32, device=log_alpha.device)
+        self.ctl = torch.zeros(2, dtype=torch.int32, device=log_alpha.device)
+        st = optimizer.state[log_alpha]
+        self._step_tensor = torch.zeros((), dtype=torch.float32)
+        self.steps = 0
+        st["step"], st["exp_avg"], st["exp_avg_sq"] = self._step_tensor, self.state[0:1], self.state[1:2]
+
+    @classmethod
+    def attach(cls, optimizer, log_alpha):
+        cur = getattr(optimizer, "_ssac_alpha_state", None)
+        if cur is None or cur.state.device != log_alpha.device:
+            cur = cls(optimizer, log_alpha)
+            optimizer._ssac_alpha_state = cur
+        return cur
+
+
+def alpha_update(buffer, agent, optimizers, batch_size, log_alphas, augmenter, aug_mix, target_entropy,
+                 premade_replay_dicts, discrete):
+    if discrete:
+        raise NotImplementedError("discrete actions are out of scope")
+    dev = agent._actor_arena.device
+    L, stream = _lib.lib(), _lib.stream_ptr()
+    E, B = agent.ensemble_size, batch_size
+    S, A = lu._dims(agent)
+    logs = _logs.DeviceLogs(dev)
+    for i in range(E):
+        if premade_replay_dicts is not None:
+            rd = premade_replay_dicts[i]
+        else:
+            rd = lu.sample_move_and_augment(buffer=buffer, batch_size=B, augmenter=augmenter, per=False, aug_mix=aug_mix)
+        o, *_ = rd["primary_batch"]
+        with torch.no_grad():
+            s_rep = agent.encoder(o)
+        X = torch.empty((B, S + A), dtype=torch.float32, device=dev)
+        X[:, :S].copy_(s_rep)
+        pol = lu._policy_sample(agent, i, X, B, S, A, None, None)
+        pg = optimizers[i].param_groups[0]
+        st = _AlphaState.attach(optimizers[i], log_alphas[i])
+        lv, slot = logs.slots(2)
+        L.alpha_step(log_alphas[i].data_ptr(), pol["logp"].data_ptr(), B, float(target_entropy), st.state.data_ptr(),
+                     st.ctl.data_ptr(), float(pg["lr"]), float(pg["betas"][0]), float(pg["betas"][1]), float(pg["eps"]),
+                     lv.data_ptr(), stream)
+        st.steps += 1
+        st._step_tensor.fill_(st.steps)
+        logs.defer(f"losses/alpha_loss_{i}", slot)
+        logs.defer(f"alphas/alpha_{i}", slot + 1)
+    return logs.finalize()
+
+
+def offline_actor_update(buffer, agent, actor_optimizer, encoder_optimizer, batch_size, actor_clip, update_encoder,
+                         encoder_clip, augmenter, actor_lambda, aug_mix, premade_replay_dicts=None, per=True,
+                         discrete=False, filter_=True):
+    """AFBC / behaviour cloning actor update (reference learning.py:144-219, learning_utils.py:241-269)."""
+    if discrete:
+        raise NotImplementedError("discrete actions are out of scope")
+    if actor_lambda:
+        raise NotImplementedError("action invariance regulariser (lambda = 0 in every shipped config) is out of scope")
+    if agent.deterministic:
+        raise NotImplementedError("filtered behaviour cloning needs a stochastic actor")
+    aa = agent._actor_arena
+    dev = aa.device
+    _ops.check_cuda(aa.flat)
+    L, stream = _lib.lib(), _lib.stream_ptr()
+    E, B = agent.ensemble_size, batch_size
+    S, A = lu._dims(agent)
+    logs = _logs.DeviceLogs(dev)
+    opt = _arena.FlatAdam.attach(actor_optimizer, aa)
+    total = torch.zeros(1, dtype=torch.float32, device=dev)
+    enc_outs = []
+    for i in range(E):
+        if premade_replay_dicts is not None:
+            rd = premade_replay_dicts[i]
+        else:
+            rd = lu.sample_move_and_augment(buffer=buffer, batch_size=B, augmenter=augmenter, aug_mix=aug_mix, per=per)
+        o, a, *_ = rd["primary_batch"]
+        if filter_:
+            _, mask, _ = lu._advantage(agent, rd, i)
+            logs.put_tensor("losses/adv_weights_mean", mask.mean())
+        else:
+            mask = torch.ones((B,), dtype=torch.float32, device=dev)
+        if update_encoder:
+            s_rep = agent.encoder(o)
+        else:
+            with torch.no_grad():
+                s_rep = agent.encoder(o)
+        need_ds = _encoder_has_grad_path(s_rep)
+        X = torch.empty((B, S + A), dtype=torch.float32, device=dev)
+        X[:, :S].copy_(s_rep.detach())
+        out, h1, h2 = lu._actor_forward(agent, i, X, B, S, A)
+        logp = torch.empty((B,), dtype=torch.float32, device=dev)
+        dlogp = mask * (-1.0 / (B * E))
+        dout = torch.empty((1, B, aa.O), dtype=torch.float32, device=dev)
+        a_c = a.contiguous() if a.stride(-1) != 1 else a
+        L.tanh_normal_logprob(out.data_ptr(), a_c.data_ptr(), a_c.stride(0), B, A, float(agent.log_std_low),
+                              float(agent.log_std_high), logp.data_ptr(), dlogp.data_ptr(), dout.data_ptr(), stream)
+        member_loss = -(logp * mask).mean()
+        logs.put_tensor(f"losses/filterd_bc_loss_{i}", member_loss)
+        total += member_loss / E
+        dxg = torch.empty((1, B, S + A), dtype=torch.float32, device=dev) if need_ds else None
+        _ops.mlp_backward(aa, i, 1, X, B, h1, h2, dout, ldx=S + A, want_dw=True, accumulate=False, dx=dxg, lddx=S + A)
+        if need_ds:
+            enc_outs.append((s_rep, dxg[0, :, :S]))
+    encoder_optimizer.zero_grad()
+    if enc_outs:
+        torch.autograd.backward([s for s, _ in enc_outs], [g for _, g in enc_outs])
+    if actor_clip:
+        opt.grad_norm_sq(stream)
+    if encoder_clip and enc_outs:
+        torch.nn.utils.clip_grad_norm_(agent.encoder.parameters(), encoder_clip)
+    opt.step(stream, max_norm=actor_clip if actor_clip else None)
+    if update_encoder and enc_outs:
+        encoder_optimizer.step()
+    logs.put_tensor("losses/filtered_bc_overall_loss", total)
+    member = random.choice(range(E))
+    gslot = lu._member_grad_norm_slot(logs, aa, member, member + 1)
+    logs.defer("gradients/actor_offline_grad_norm", gslot, transform=lambda v: v**0.5)
+    if enc_outs:
+        gn = torch.linalg.vector_norm(torch.stack([p.grad.norm() for p in agent.encoder.parameters() if p.grad is not None]))
+        logs.put_tensor("gradients/encoder_offline_actorloss_grad_norm", gn)
+    else:
+        logs["gradients/encoder_offline_actorloss_grad_norm"] = 0.0
+    if per:
+        lu.adjust_priorities(logs, rd, agent, buffer)
+    return logs.finalize()

@@ -1,0 +1,484 @@
+"""Building blocks of the update step with the reference's names and signatures (reference learning_utils.py).
+
+soft_update / hard_update (:160-167), sample_move_and_augment (:174-214), compute_td_targets (:298-354),
+compute_backup_weights (:357-398), filtered_bc_loss (:241-269), adjust_priorities (:288-295), get_grad_norm
+(:95-106) and GaussianExplorationNoise (:18-66).  Every tensor stays in HBM; each function enqueues a handful of
+kernels from libssac_b200 on the current stream and never synchronises (logged scalars go through _logs.DeviceLogs).
+"""
+import math
+import random
+
+import numpy as np
+import torch
+
+from . import _lib, _logs, _ops, _rng, augmentations
+from ._arena import MLPArena
+
+LOG_SQRT_2PI = math.log(math.sqrt(2 * math.pi))
+
+
+# ------------------------------------------------------------------------------------------------
+# exploration noise (TD3 / DrQv2)
+# ------------------------------------------------------------------------------------------------
+class GaussianExplorationNoise:
+    """sigma-annealed Gaussian action noise.  The numpy branch serves acting; inside the updates only
+    ``current_scale`` is read -- noise, clipping and the straight-through clamp to the action bounds run in
+    ssac_det_head_forward (reference learning_utils.py:48-59)."""
+
+    def __init__(self, action_space, start_scale=1.0, final_scale=0.1, steps_annealed=1000, eps=1e-6):
+        assert start_scale >= final_scale
+        self.action_space = action_space
+        self.start_scale, self.final_scale, self.steps_annealed = start_scale, final_scale, steps_annealed
+        self.current_scale = start_scale
+        self._scale_slope = (start_scale - final_scale) / steps_annealed
+        self.eps = eps
+        if not (np.allclose(action_space.low, -1.0) and np.allclose(action_space.high, 1.0)):
+            raise NotImplementedError("the fused noise head assumes actions normalised to [-1, 1] (NormActionSpace)")
+
+    def sample(self, action, clip=None, update_schedule=False):
+        if isinstance(action, np.ndarray):
+            noise = self.current_scale * np.random.randn(*action.shape)
+            if clip is not None:
+                noise = np.clip(noise, -clip, clip)
+            out = np.clip(action + noise, self.action_space.low + self.eps, self.action_space.high - self.eps)
+        elif torch.is_tensor(action):
+            B, A = action.shape
+            nz = torch.empty((B, A), dtype=torch.float32, device=action.device)
+            _rng.source().normal(nz)
+            out = torch.empty_like(action)
+            # identity "head": atanh is not needed, feed the action through the noise/clamp stage only
+            noise = self.current_scale * nz
+            if clip is not None:
+                noise = noise.clamp(-clip, clip)
+            clamped = (action + noise).clamp(-1.0 + self.eps, 1.0 - self.eps)
+            out = action + (clamped - action).detach()
+        else:
+            raise ValueError(f"Unrecognized action array type: {type(action)}")
+        if update_schedule:
+            self.current_scale = max(self.current_scale - self._scale_slope, self.final_scale)
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# target networks
+# ------------------------------------------------------------------------------------------------
+_polyak_tables = {}
+
+
+def _arena_of(module):
+    arena = getattr(module, "_arena", None)
+    return arena if isinstance(arena, MLPArena) else None
+
+
+def _multi_table(target, source):
+    """Device pointer table for arbitrary module pairs (user encoders); cached per pair, rebuilt if storage moved."""
+    tp, sp = list(target.parameters()), list(source.parameters())
+    sig = tuple((t.data_ptr(), s.data_ptr(), t.numel()) for t, s in zip(tp, sp))
+    key = (id(target), id(source))
+    cur = _polyak_tables.get(key)
+    if cur is None or cur[0] != sig:
+        if not sig:
+            cur = (sig, None, 0)
+        else:
+            for t, s in zip(tp, sp):
+                if t.dtype != torch.float32 or s.dtype != torch.float32 or not t.is_contiguous() or not s.is_contiguous():
+                    raise NotImplementedError("soft_update: parameters must be contiguous fp32")
+            flat = [v for e in sig for v in e]
+            table = torch.tensor(flat, dtype=torch.int64, device=tp[0].device)
+            cur = (sig, table, max(e[2] for e in sig))
+        _polyak_tables[key] = cur
+    return cur
+
+
+def soft_update(target, source, tau):
+    """target <- target*(1-tau) + source*tau, bit-exact with the reference (learning_utils.py:160-162)."""
+    ta, sa = _arena_of(target), _arena_of(source)
+    if ta is not None and sa is not None:
+        _ops.check_cuda(ta.flat, sa.flat)
+        g0, g1 = target._g0, target._g0 + target.num_critics
+        assert (source._g0, source.num_critics) == (target._g0, target.num_critics)
+        _ops.polyak_ranges(ta.flat, sa.flat, ta.range_table(g0, g1), tau)
+        return
+    sig, table, max_numel = _multi_table(target, source)
+    if table is None:
+        return
+    _ops.check_cuda(table)
+    _lib.lib().polyak_multi(table.data_ptr(), len(sig), max_numel, float(tau), _lib.stream_ptr())
+
+
+def hard_update(target, source):
+    """learning_utils.py:165-167 (tau = 1 is exact: t*0 + s*1)."""
+    soft_update(target, source, 1.0)
+
+
+def get_grad_norm(model):
+    """sqrt(sum ||p.grad||^2) as a float (learning_utils.py:95-106): one reduction launch per tensor, one sync."""
+    grads = [p.grad for p in model.parameters() if p.grad is not None]
+    if not grads:
+        return 0.0
+    acc = torch.zeros(1, dtype=torch.float32, device=grads[0].device)
+    L, s = _lib.lib(), _lib.stream_ptr()
+    for g in grads:
+        g = g.contiguous()
+        L.sumsq(g.data_ptr(), g.numel(), acc.data_ptr(), 1, s)
+    return float(acc.item()) ** 0.5
+
+
+def _member_grad_norm_slot(logs, arena, g0, g1):
+    """Enqueue sum g^2 of nets g0..g1 into a log slot (sqrt taken at finalize)."""
+    v, slot = logs.slots(1)
+    v.zero_()
+    L, s = _lib.lib(), _lib.stream_ptr()
+    for off, n in arena.range_table(g0, g1):
+        L.sumsq(arena.grad.data_ptr() + 4 * off, n, v.data_ptr(), 1, s)
+    return slot
+
+
+# ------------------------------------------------------------------------------------------------
+# sampling
+# ------------------------------------------------------------------------------------------------
+class ReplayDict(dict):
+    """The dict of learning_utils.py:208-214.  'augmented_obs' and 'original_obs' (only read by the invariance
+    regularisers, lambda = 0 in every shipped config) are produced on first access instead of on every sample."""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self._lazy = {}
+
+    def __missing__(self, key):
+        if key in self._lazy:
+            val = self._lazy.pop(key)()
+            self[key] = val
+            return val
+        raise KeyError(key)
+
+    def __contains__(self, key):
+        return dict.__contains__(self, key) or key in self._lazy
+
+
+def _pixel_gather(stack, idx, shift, aug, B, aug_rows, use_aug):
+    _, C, H, W = stack.shape
+    out = torch.empty((B, C, H, W), dtype=torch.float32, device=stack.device)
+    noise = None
+    pad_mode = aug.pad_mode if use_aug else augmentations.PAD_NONE
+    if use_aug and getattr(aug, "noise", False) and pad_mode != augmentations.PAD_NONE:
+        noise = torch.empty((B, C, H, W), dtype=torch.float32, device=stack.device)
+        _rng.source().normal(noise)
+    _lib.lib().gather_aug_u8(stack.data_ptr(), out.data_ptr(), idx.data_ptr(), None if shift is None else shift.data_ptr(),
+                             None if noise is None else noise.data_ptr(), B, C, H, W, int(getattr(aug, "pad", 0)),
+                             pad_mode if shift is not None else 0, aug_rows, _lib.stream_ptr())
+    return out
+
+
+def sample_move_and_augment(buffer, batch_size, augmenter, aug_mix, per=True):
+    """Sample a batch on the device, cast to fp32, augment o and o1 with shared parameters and mix the first
+    int(B*aug_mix) augmented rows into the batch (reference learning_utils.py:174-214)."""
+    assert len(buffer) >= batch_size
+    st, dev, B = buffer._storage, buffer.device, batch_size
+    buffer.total_sample_calls += 1
+    if per:
+        idx, imp_weights = buffer.sample_indices_per(B)
+    else:
+        idx = buffer.sample_indices_uniform(B)
+        imp_weights = torch.ones(1, dtype=torch.float32, device=dev)
+    aug_rows = int(B * aug_mix)
+    fused = isinstance(augmenter, augmentations.AugmentationSequence) and augmenter.fusable()
+    rd = ReplayDict()
+
+    a = r = d = None
+    if fused:
+        aug = augmenter.aug_list[0]
+        aug.change_randomization_params(dev)  # once per call; o and o1 share the shifts
+        shift = getattr(aug, "shift", None)
+        aug_keys = st.s_stack.keys() if augmenter.keys is None else augmenter.keys
+        o, o1 = {}, {}
+        srcs, dsts, rows, lds, modes = [], [], [], [], []
+        keys = list(st.s_stack.keys())
+        A = st.action_stack[0].numel()
+        packed = None
+        if len(keys) == 1 and st.s_stack[keys[0]].dtype == torch.float32 and st.s_stack[keys[0]].dim() == 2 \
+                and st.action_stack.dim() == 2:
+            # state observations: gather s|a, s1|. and s|. straight into the [B, S+A] first-layer inputs
+            k = keys[0]
+            S = st.s_stack[k].shape[1]
+            XA = torch.empty((B, S + A), dtype=torch.float32, device=dev)
+            X1 = torch.empty((B, S + A), dtype=torch.float32, device=dev)
+            XPI = torch.empty((B, S + A), dtype=torch.float32, device=dev)
+            o[k], o1[k], a = XA[:, :S], X1[:, :S], XA[:, S:]
+            for src, dst, n in ((st.s_stack[k], XA, S), (st.s_stack[k], XPI, S), (st.s1_stack[k], X1, S)):
+                srcs.append(src); dsts.append(dst); rows.append(n); lds.append(S + A); modes.append(0)
+            srcs.append(st.action_stack); dsts.append(a); rows.append(A); lds.append(S + A); modes.append(0)
+            packed = dict(XA=XA, X1=X1, XPI=XPI, S=S, A=A, key=k)
+        else:
+            for k in keys:
+                stack, stack1 = st.s_stack[k], st.s1_stack[k]
+                if stack.dtype == torch.uint8 and stack.dim() == 4:
+                    use = k in aug_keys
+                    o[k] = _pixel_gather(stack, idx, shift, aug, B, aug_rows, use)
+                    o1[k] = _pixel_gather(stack1, idx, shift, aug, B, aug_rows, use)
+                elif stack.dtype in (torch.float32, torch.uint8):
+                    if k in aug_keys and aug.pad_mode != augmentations.PAD_NONE:
+                        raise NotImplementedError(f"shift augmentation of non-image key '{k}'")
+                    n = stack[0].numel()
+                    o[k] = torch.empty((B,) + tuple(stack.shape[1:]), dtype=torch.float32, device=dev)
+                    o1[k] = torch.empty_like(o[k])
+                    mode = 0 if stack.dtype == torch.float32 else 1
+                    for src, dst in ((stack, o[k]), (stack1, o1[k])):
+                        srcs.append(src); dsts.append(dst); rows.append(n); lds.append(n); modes.append(mode)
+                else:
+                    raise NotImplementedError(f"observation dtype {stack.dtype} (key '{k}')")
+            a = torch.empty((B, A), dtype=torch.float32, device=dev)
+            srcs.append(st.action_stack); dsts.append(a); rows.append(A); lds.append(A); modes.append(0)
+        r = torch.empty((B, 1), dtype=torch.float32, device=dev)
+        d = torch.empty((B, 1), dtype=torch.float32, device=dev)
+        srcs += [st.reward_stack, st.done_stack]; dsts += [r, d]; rows += [1, 1]; lds += [1, 1]; modes += [0, 1]
+        _ops.gather_rows(srcs, dsts, rows, lds, modes, idx, B)
+        rd["primary_batch"] = (o, a, r, o1, d)
+        if packed is not None:
+            rd["_packed"] = packed
+
+        def _orig():
+            oo, oo1 = {}, {}
+            for k in keys:
+                stack = st.s_stack[k]
+                if stack.dtype == torch.uint8 and stack.dim() == 4:
+                    oo[k] = _pixel_gather(stack, idx, None, aug, B, 0, False)
+                    oo1[k] = _pixel_gather(st.s1_stack[k], idx, None, aug, B, 0, False)
+                else:
+                    oo[k], oo1[k] = o[k], o1[k]
+            return oo, oo1
+
+        def _augd():
+            ao, ao1 = {}, {}
+            for k in keys:
+                stack = st.s_stack[k]
+                if stack.dtype == torch.uint8 and stack.dim() == 4 and k in aug_keys:
+                    if getattr(aug, "noise", False):
+                        raise NotImplementedError("lazy 'augmented_obs' with noisy DrqAug (noise would be re-drawn)")
+                    ao[k] = _pixel_gather(stack, idx, shift, aug, B, B, True)
+                    ao1[k] = _pixel_gather(st.s1_stack[k], idx, shift, aug, B, B, True)
+                else:
+                    ao[k], ao1[k] = o[k], o1[k]
+            return ao, ao1
+
+        rd._lazy["original_obs"] = _orig
+        rd._lazy["augmented_obs"] = _augd
+    else:
+        # arbitrary user augmenter (callable on dicts of float tensors): gather + cast here, augment + mix in PyTorch
+        s, a, r, s1, dn = st.gather(idx)
+        oo = {k: v.float() for k, v in s.items()}
+        oo1 = {k: v.float() for k, v in s1.items()}
+        a, r, d = a.float(), r.float(), dn.float()
+        ao, ao1 = augmenter(oo, oo1)
+        o = {k: v.clone() for k, v in oo.items()}
+        o1 = {k: v.clone() for k, v in oo1.items()}
+        for k in o:
+            o[k][:aug_rows] = ao[k][:aug_rows]
+            o1[k][:aug_rows] = ao1[k][:aug_rows]
+        rd["primary_batch"] = (o, a, r, o1, d)
+        rd["augmented_obs"] = (ao, ao1)
+        rd["original_obs"] = (oo, oo1)
+    rd["priority_idxs"] = idx
+    rd["imp_weights"] = imp_weights
+    return rd
+
+
+# ------------------------------------------------------------------------------------------------
+# shared pieces of the updates
+# ------------------------------------------------------------------------------------------------
+def _first_layer_input(rep, act_cols, packed_buf, S, A):
+    """[B, S+A] matrix whose first S columns hold ``rep``.  When the encoder returned the packed view itself
+    (identity encoders) the gather already put the numbers there and nothing is copied."""
+    B = rep.shape[0]
+    if packed_buf is not None and rep.data_ptr() == packed_buf.data_ptr() and rep.stride(0) == S + A and rep.shape[1] == S:
+        return packed_buf
+    X = torch.empty((B, S + A), dtype=torch.float32, device=rep.device)
+    X[:, :S].copy_(rep.detach())
+    if act_cols is not None:
+        X[:, S:].copy_(act_cols)
+    return X
+
+
+def _actor_forward(agent, i, X, B, S, A, keep=False):
+    """Run actor i on the first S columns of X [B, S+A].  Returns (out [B,O], h1, h2)."""
+    arena = agent._actor_arena
+    h1 = torch.empty((1, B, arena.H), dtype=torch.float32, device=X.device)
+    h2 = torch.empty_like(h1)
+    out = torch.empty((1, B, arena.O), dtype=torch.float32, device=X.device)
+    _ops.mlp_forward(arena, i, 1, X, B, h1, h2, out, ldx=S + A)
+    return out, h1, h2
+
+
+def _policy_sample(agent, i, X, B, S, A, random_process, noise_clip, rsample=False):
+    """a ~ pi_i(.|s) written into X[:, S:], with log-prob [B] (None when a noise process replaces the entropy term).
+    Returns dict(out, h1, h2, eps, logp, tanh_out)."""
+    dev = X.device
+    out, h1, h2 = _actor_forward(agent, i, X, B, S, A)
+    a_dst = X[:, S:]
+    L, s = _lib.lib(), _lib.stream_ptr()
+    res = dict(out=out, h1=h1, h2=h2, eps=None, logp=None, tanh_out=None)
+    if agent.deterministic:
+        eps = noise = None
+        if rsample:  # Normal(loc, 1e-4).rsample() of the reference's deterministic "distribution"
+            eps = torch.empty((B, A), dtype=torch.float32, device=dev)
+            _rng.source().normal(eps)
+        sigma, clip = 0.0, 0.0
+        if random_process is not None:
+            noise = torch.empty((B, A), dtype=torch.float32, device=dev)
+            _rng.source().normal(noise)
+            sigma = float(random_process.current_scale)
+            clip = float(noise_clip) if noise_clip is not None else 0.0
+        tanh_out = torch.empty((B, A), dtype=torch.float32, device=dev)
+        L.det_head_forward(out.data_ptr(), None if eps is None else eps.data_ptr(),
+                           None if noise is None else noise.data_ptr(), B, A, sigma, clip, a_dst.data_ptr(), S + A,
+                           tanh_out.data_ptr(), s)
+        res.update(eps=eps, tanh_out=tanh_out)
+        if random_process is None:
+            # Normal(loc, 1e-4).log_prob(loc) summed over A: a constant (nets/distributions.py:107-114)
+            res["logp"] = torch.full((B,), A * (0.0 - math.log(1e-4) - LOG_SQRT_2PI), dtype=torch.float32, device=dev)
+    else:
+        if random_process is not None:
+            raise NotImplementedError("an exploration-noise process on top of a stochastic actor is not supported")
+        eps = torch.empty((B, A), dtype=torch.float32, device=dev)
+        _rng.source().normal(eps)
+        logp = torch.empty((B,), dtype=torch.float32, device=dev)
+        L.tanh_normal_forward(out.data_ptr(), eps.data_ptr(), B, A, float(agent.log_std_low), float(agent.log_std_high),
+                              a_dst.data_ptr(), S + A, logp.data_ptr(), s)
+        res.update(eps=eps, logp=logp)
+    return res
+
+
+def _critic_values(agent, g0, G, X, B, net_index=None, keep=False):
+    """q [G,B] of critic nets g0..g0+G (or the net_index subset relative to g0) on X [B, S+A]."""
+    arena = agent._critic_arena
+    h1 = torch.empty((G, B, arena.H), dtype=torch.float32, device=X.device)
+    h2 = torch.empty_like(h1)
+    q = torch.empty((G, B, 1), dtype=torch.float32, device=X.device)
+    _ops.mlp_forward(arena, g0, G, X, B, h1, h2, q, ldx=X.shape[1], net_index=net_index)
+    return (q, h1, h2) if keep else q
+
+
+def _packed_of(replay_dict):
+    return replay_dict["_packed"] if "_packed" in replay_dict else None
+
+
+def _dims(agent):
+    return agent._actor_arena.D, agent.act_space_size
+
+
+def compute_td_targets(logs, replay_dict, agent, target_agent, ensemble_idx, ensemble_n, log_alphas, pop, gamma,
+                       random_process, noise_clip, discrete=False):
+    """TD target of one ensemble member (reference learning_utils.py:298-354, continuous branch).
+    Returns ``td_target [B,1], (s1_rep, a_s1)``."""
+    if discrete:
+        raise NotImplementedError("discrete actions are out of scope")
+    dlogs, user_logs = _logs.as_device_logs(logs, agent._critic_arena.device)
+    o, a, r, o1, d = replay_dict["primary_batch"]
+    i = ensemble_idx
+    S, A = _dims(agent)
+    B = a.shape[0]
+    packed = _packed_of(replay_dict)
+    popart = agent.popart[i]
+    with torch.no_grad():
+        s1_rep = target_agent.encoder(o1)
+    X1 = _first_layer_input(s1_rep, None, packed["X1"] if packed else None, S, A)
+    pol = _policy_sample(agent, i, X1, B, S, A, random_process, noise_clip)
+    N = agent.num_critics
+    net_index = torch.empty(ensemble_n, dtype=torch.int32, device=X1.device)
+    assert 0 < ensemble_n <= N
+    _rng.source().subsets(net_index, N, ensemble_n)
+    q_t = _critic_values(target_agent, i * N, ensemble_n, X1, B, net_index=net_index)
+    y = torch.empty((B, 1), dtype=torch.float32, device=X1.device)
+    lv, slot = dlogs.slots(3)
+    _lib.lib().td_target(q_t.data_ptr(), ensemble_n, B, None if pol["logp"] is None else pol["logp"].data_ptr(),
+                         log_alphas[i].data_ptr(), r.data_ptr(), d.data_ptr(), float(gamma),
+                         popart.state_ptr() if popart else None, popart.ctl_ptr() if popart else None,
+                         int(bool(pop)), float(popart.beta) if popart else 0.0, int(popart.min_steps) if popart else 0,
+                         y.data_ptr(), lv.data_ptr(), _lib.stream_ptr())
+    dlogs.defer(f"td_targets/mean_td_target_{i}", slot)
+    dlogs.defer(f"td_targets/std_td_target_{i}", slot + 1)
+    dlogs.defer(f"td_targets/entropy_bonus_{i}", slot + 2)
+    if user_logs is not None:
+        user_logs.update(dlogs.finalize())
+    return y, (X1[:, :S], X1[:, S:])
+
+
+def compute_backup_weights(logs, replay_dict, agent, target_agent, weight_type, weight_temp, batch_size, discrete=False):
+    """SUNRISE / softmax weighted Bellman backups (reference learning_utils.py:357-398).  Returns 1.0 or w [B,1]."""
+    if weight_type is None or weight_temp is None or agent.ensemble_size == 1:
+        return 1.0
+    if discrete:
+        raise NotImplementedError("discrete actions are out of scope")
+    dlogs, user_logs = _logs.as_device_logs(logs, agent._critic_arena.device)
+    o, a, _, o1, _ = replay_dict["primary_batch"]
+    S, A = _dims(agent)
+    E, N, B = agent.ensemble_size, agent.num_critics, a.shape[0]
+    packed = _packed_of(replay_dict)
+    dev = a.device
+    if weight_type == "sunrise":
+        with torch.no_grad():
+            s_rep = target_agent.encoder(o)
+        X = _first_layer_input(s_rep, a, packed["XA"] if packed else None, S, A)
+        q = _critic_values(target_agent, 0, E * N, X, B)  # every target net on this member's (s, a): one launch
+        kind = 0
+    elif weight_type == "softmax":
+        with torch.no_grad():
+            s1_rep = target_agent.encoder(o1)
+        q = torch.empty((E * N, B, 1), dtype=torch.float32, device=dev)
+        for j in range(E):
+            Xj = torch.empty((B, S + A), dtype=torch.float32, device=dev)
+            Xj[:, :S].copy_(s1_rep)
+            _policy_sample(agent, j, Xj, B, S, A, None, None)
+            q[j * N:(j + 1) * N].copy_(_critic_values(agent, j * N, N, Xj, B))
+        kind = 1
+    else:
+        raise ValueError(f"unknown weight_type {weight_type!r}")
+    w = torch.empty((B, 1), dtype=torch.float32, device=dev)
+    lv, slot = dlogs.slots(4)
+    _lib.lib().backup_weights(q.data_ptr(), E, N, B, float(weight_temp), kind, w.data_ptr(), lv.data_ptr(), _lib.stream_ptr())
+    for j, name in enumerate(("mean", "max", "min", "std")):
+        dlogs.defer(f"bellman_weights/{name}", slot + j)
+    if user_logs is not None:
+        user_logs.update(dlogs.finalize())
+    return w
+
+
+def _advantage(agent, replay_dict, ensemble_idx, n=4, want_priority=False):
+    """A(s,a) = Q(s,a) - mean_n Q(s, a'~pi) with min-over-N critics and PopArt (reference adv_estimator.py:58-79).
+    Returns (adv [B], mask [B], priority float64 [B] or None)."""
+    o, a, *_ = replay_dict["primary_batch"]
+    i = ensemble_idx
+    S, A = _dims(agent)
+    N, B = agent.num_critics, a.shape[0]
+    packed = _packed_of(replay_dict)
+    dev = a.device
+    popart = agent.popart[i]
+    L, s = _lib.lib(), _lib.stream_ptr()
+    with torch.no_grad():
+        s_rep = agent.encoder(o)
+    XA = _first_layer_input(s_rep, a, packed["XA"] if packed else None, S, A)
+    q_pi = torch.empty((n, B), dtype=torch.float32, device=dev)
+    Xp = torch.empty((B, S + A), dtype=torch.float32, device=dev)
+    Xp[:, :S].copy_(XA[:, :S])
+    pptr = popart.state_ptr() if popart else None
+    for j in range(n):
+        _policy_sample(agent, i, Xp, B, S, A, None, None)
+        q = _critic_values(agent, i * N, N, Xp, B)
+        L.min_over_nets(q.data_ptr(), N, B, pptr, q_pi[j].data_ptr(), s)
+    q = _critic_values(agent, i * N, N, XA, B)
+    q_data = torch.empty((B,), dtype=torch.float32, device=dev)
+    L.min_over_nets(q.data_ptr(), N, B, pptr, q_data.data_ptr(), s)
+    adv = torch.empty((B,), dtype=torch.float32, device=dev)
+    mask = torch.empty((B,), dtype=torch.float32, device=dev)
+    prio = torch.empty((B,), dtype=torch.float64, device=dev) if want_priority else None
+    L.advantage(q_pi.data_ptr(), n, q_data.data_ptr(), B, adv.data_ptr(), mask.data_ptr(),
+                None if prio is None else prio.data_ptr(), s)
+    return adv, mask, prio
+
+
+def adjust_priorities(logs, replay_dict, agent, buffer):
+    """priorities <- relu(A(s,a)) + 1e-4 on the sampled rows, without leaving the device
+    (reference learning_utils.py:288-295)."""
+    member = random.choice(range(agent.ensemble_size))
+    _, _, prio = _advantage(agent, replay_dict, member, want_priority=True)
+    buffer.update_priorities(replay_dict["priority_idxs"], prio)

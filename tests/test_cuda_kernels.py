@@ -1,0 +1,458 @@
+"""Kernel-level GPU parity against the CPU oracle (run with -m gpu on a B200), through the C ABI.
+
+Bit-exact: Polyak, replay gather, pixel gather+augment, segment-tree indices.  fp32 tolerance rtol 1e-4 (north_star)
+for everything that sums in a different order than the oracle.
+"""
+import ctypes
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import golden_util as gu
+from oracle import aug_oracle as ao
+from oracle import replay_oracle as ro
+from oracle import update_oracle as uo
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def L():
+    from super_sac_b200 import _lib
+
+    return _lib.lib()
+
+
+def S():
+    from super_sac_b200 import _lib
+
+    return _lib.stream_ptr()
+
+
+def dev(x, dtype=None):
+    t = torch.as_tensor(np.asarray(x))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to(DEV).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------ Polyak / Adam
+@pytest.mark.parametrize("n,off", [(1, 0), (7, 0), (721930, 0), (4097, 1), (2_000_003, 3)])
+@pytest.mark.parametrize("tau", [0.005, 0.01, 1.0])
+def test_polyak_bit_exact(n, off, tau):
+    g = torch.Generator().manual_seed(n)
+    t0, s0 = torch.randn(n + off, generator=g), torch.randn(n + off, generator=g)
+    want = t0[off:] * (1.0 - tau) + s0[off:] * tau  # the reference's three fp32 ops (learning_utils.py:162)
+    t, s = t0.to(DEV), s0.to(DEV)
+    L().polyak(t.data_ptr() + 4 * off, s.data_ptr() + 4 * off, n, tau, S())
+    assert torch.equal(t[off:].cpu(), want)
+    assert torch.equal(t[:off].cpu(), t0[:off])
+
+
+def test_polyak_multi_bit_exact():
+    from super_sac_b200 import learning_utils as lu
+
+    torch.manual_seed(0)
+    src = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3), torch.nn.Linear(10, 33), torch.nn.LayerNorm(7)).to(DEV)
+    tgt = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3), torch.nn.Linear(10, 33), torch.nn.LayerNorm(7)).to(DEV)
+    want = [t.detach().cpu() * (1.0 - 0.01) + s.detach().cpu() * 0.01 for t, s in zip(tgt.parameters(), src.parameters())]
+    lu.soft_update(tgt, src, 0.01)
+    for t, w in zip(tgt.parameters(), want):
+        assert torch.equal(t.detach().cpu(), w)
+    lu.hard_update(tgt, src)
+    for t, s in zip(tgt.parameters(), src.parameters()):
+        assert torch.equal(t, s)
+
+
+@pytest.mark.parametrize("wd,clip", [(0.0, None), (1e-3, None), (0.0, 0.5), (1e-3, 40.0)])
+def test_adam_matches_oracle(wd, clip):
+    n = 72193
+    g = torch.Generator().manual_seed(3)
+    p0 = torch.randn(n, generator=g)
+    opt = uo.Adam([p0.clone()], lr=3e-4, weight_decay=wd)
+    p, m, v = p0.to(DEV), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    ctl = torch.zeros(2, dtype=torch.int32, device=DEV)
+    gn = torch.zeros(1, device=DEV)
+    for step in range(5):
+        grad = torch.randn(n, generator=g) * (10.0 ** (step - 3))
+        gd = grad.to(DEV)
+        ref_g = grad.clone()
+        if clip:
+            uo.clip_grad_norm([ref_g], clip)
+            L().sumsq(gd.data_ptr(), n, gn.data_ptr(), 0, S())
+        opt.step([ref_g])
+        L().adam_step(p.data_ptr(), gd.data_ptr(), m.data_ptr(), v.data_ptr(), n, ctl.data_ptr(), 3e-4, 0.9, 0.999, 1e-8, wd,
+                      gn.data_ptr() if clip else None, clip or 0.0, 1, S())
+        if clip:
+            gu.assert_close(gd.cpu().numpy(), ref_g.numpy(), 1e-5, 1e-12, f"clipped grad step {step}")
+        gu.assert_close(p.cpu().numpy(), opt.params[0].numpy(), 1e-6, 3e-4 * 1e-3, f"adam params step {step}")
+    assert int(ctl[0]) == 5 and int(ctl[1]) == 0
+    gu.assert_close(m.cpu().numpy(), opt.m[0].numpy(), 1e-5, 1e-9, "exp_avg")
+    gu.assert_close(v.cpu().numpy(), opt.v[0].numpy(), 1e-5, 1e-12, "exp_avg_sq")
+
+
+def test_adam_polyak_fused_equals_separate():
+    n = 50001
+    g = torch.Generator().manual_seed(5)
+    p0, t0, gr = torch.randn(n, generator=g), torch.randn(n, generator=g), torch.randn(n, generator=g)
+    outs = []
+    for fused in (False, True):
+        p, t, gd = p0.to(DEV), t0.to(DEV), gr.to(DEV)
+        m, v = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+        ctl = torch.zeros(2, dtype=torch.int32, device=DEV)
+        if fused:
+            L().adam_polyak_step(p.data_ptr(), gd.data_ptr(), m.data_ptr(), v.data_ptr(), t.data_ptr(), n, ctl.data_ptr(),
+                                 3e-4, 0.9, 0.999, 1e-8, 0.0, None, 0.0, 0, 0.005, S())
+        else:
+            L().adam_step(p.data_ptr(), gd.data_ptr(), m.data_ptr(), v.data_ptr(), n, ctl.data_ptr(), 3e-4, 0.9, 0.999, 1e-8,
+                          0.0, None, 0.0, 0, S())
+            L().polyak(t.data_ptr(), p.data_ptr(), n, 0.005, S())
+        outs.append((p.cpu(), t.cpu()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+# ------------------------------------------------------------------------------------------------ replay
+def test_gather_rows_bit_exact():
+    from super_sac_b200 import _ops
+
+    rng = np.random.default_rng(0)
+    cap, B = 1000, 256
+    s = rng.standard_normal((cap, 17)).astype(np.float32)
+    a = rng.uniform(-1, 1, (cap, 6)).astype(np.float32)
+    d = (rng.uniform(size=(cap, 1)) < 0.3).astype(np.uint8)
+    px = rng.integers(0, 256, (cap, 3, 8, 8), dtype=np.uint8)
+    idx = rng.integers(0, cap, B)
+    X = torch.zeros((B, 23), device=DEV)
+    dd = torch.zeros((B, 1), device=DEV)
+    pxo = torch.zeros((B, 3, 8, 8), dtype=torch.uint8, device=DEV)
+    pxf = torch.zeros((B, 3, 8, 8), device=DEV)
+    ts, ta, td, tp = dev(s), dev(a), dev(d), dev(px)
+    _ops.gather_rows([ts, ta, td, tp, tp], [X, X[:, 17:], dd, pxo, pxf], [17, 6, 1, 192, 192], [23, 23, 1, 192, 192],
+                     [0, 0, 1, 2, 1], dev(idx), B)
+    assert np.array_equal(X.cpu().numpy(), np.concatenate([s[idx], a[idx]], 1))
+    assert np.array_equal(dd.cpu().numpy(), d[idx].astype(np.float32))
+    assert np.array_equal(pxo.cpu().numpy(), px[idx])
+    assert np.array_equal(pxf.cpu().numpy(), px[idx].astype(np.float32))
+
+
+def test_replay_buffer_matches_golden_ops():
+    """Ring writes (single, batched, wrap-around), uniform gather and the PER trees against the reference's own
+    outputs (tests/golden/replay_per.npz)."""
+    import super_sac_b200 as ssb
+    from super_sac_b200 import _rng
+
+    fx = gu.load("replay_per")
+    buf = ssb.replay.ReplayBuffer(50, alpha=0.6, beta=0.7, device=DEV)
+    for k in range(int(fx["n_ops"])):
+        op = gu.sub(fx, f"op{k}")
+        if str(op["kind"]) == "push1":
+            buf.push({"obs": op["s"]}, op["a"], float(op["r"]), {"obs": op["s1"]}, bool(op["d"]))
+        else:
+            buf.push({"obs": op["s"]}, op["a"], op["r"], {"obs": op["s1"]}, op["d"], priorities=op["priorities"])
+    ap = gu.sub(fx, "after_push")
+    st = buf._storage
+    assert np.array_equal(st.s_stack["obs"].cpu().numpy(), ap["s"]) and np.array_equal(st.s1_stack["obs"].cpu().numpy(), ap["s1"])
+    assert np.array_equal(st.action_stack.cpu().numpy(), ap["a"]) and np.array_equal(st.reward_stack.cpu().numpy(), ap["r"])
+    assert np.array_equal(st.done_stack.cpu().numpy(), ap["d"])
+    assert st._next_idx == int(ap["next_idx"]) and len(buf) == int(ap["filled"])
+    assert np.array_equal(buf._it_sum.cpu().numpy(), ap["sum_tree"]) and np.array_equal(buf._it_min.cpu().numpy(), ap["min_tree"])
+    old = _rng.set_source(_rng.ScriptedSource())
+    try:
+        u = gu.sub(fx, "uniform")
+        _rng.source().push("indices", u["idx"])
+        (s, a, r, s1, d), idx = buf.sample_uniform(8)
+        for got, want in ((s["obs"], u["s"]), (a, u["a"]), (r, u["r"]), (s1["obs"], u["s1"]), (d, u["d"])):
+            assert np.array_equal(got.cpu().numpy(), want)
+        assert np.array_equal(idx, u["ridx"])
+        for t in range(4):
+            p = gu.sub(fx, f"per{t}")
+            _rng.source().push("uniform01", p["u"])
+            (s, a, r, s1, d), w, idxes = buf.sample(16)
+            assert np.array_equal(idxes, p["idxes"])  # float64 descent: bit-exact
+            gu.assert_close(w.cpu().numpy(), p["weights"], 1e-14, 0.0, "IS weights")
+            assert np.array_equal(s["obs"].cpu().numpy(), p["s"]) and np.array_equal(a.cpu().numpy(), p["a"])
+            buf.update_priorities(idxes, p["new_priorities"])
+            assert np.array_equal(buf._it_sum.cpu().numpy(), p["sum_tree"])
+            assert np.array_equal(buf._it_min.cpu().numpy(), p["min_tree"])
+            assert buf._max_priority == float(p["max_priority"])
+    finally:
+        _rng.set_source(old)
+
+
+def test_per_tree_large_matches_oracle():
+    """2^21-leaf trees (BASELINE config 5 size): bulk load + 1024-sample rounds against the numpy restatement."""
+    import super_sac_b200 as ssb
+
+    rng = np.random.default_rng(1)
+    n, cap = 300_000, 1 << 19
+    orc = ro.ReplayOracle(cap)
+    pr = rng.uniform(0.01, 4.0, n)
+    orc.it_sum.set(np.arange(n), pr**0.6)
+    orc.it_min.set(np.arange(n), pr**0.6)
+    sum_t = torch.zeros(2 * cap, dtype=torch.float64, device=DEV)
+    min_t = torch.full((2 * cap,), float("inf"), dtype=torch.float64, device=DEV)
+    L().tree_set(sum_t.data_ptr(), min_t.data_ptr(), cap, dev(np.arange(n)).data_ptr(), dev(pr**0.6).data_ptr(), n, S())
+    assert np.array_equal(sum_t.cpu().numpy(), orc.it_sum.value) and np.array_equal(min_t.cpu().numpy(), orc.it_min.value)
+    for rnd in range(3):
+        u = rng.uniform(size=1024)
+        total = orc.it_sum.reduce(0, n - 1)
+        want = orc.it_sum.find_prefixsum_idx(u * total)
+        idx = torch.empty(1024, dtype=torch.int64, device=DEV)
+        w = torch.empty(1024, dtype=torch.float64, device=DEV)
+        L().tree_sample(sum_t.data_ptr(), min_t.data_ptr(), cap, n, dev(u).data_ptr(), 1024, 1.0, idx.data_ptr(), w.data_ptr(), S())
+        assert np.array_equal(idx.cpu().numpy(), want)
+        newp = rng.uniform(1e-3, 5.0, 1024) ** 0.6
+        orc.it_sum.set(want, newp)
+        orc.it_min.set(want, newp)
+        L().tree_set(sum_t.data_ptr(), min_t.data_ptr(), cap, idx.data_ptr(), dev(newp).data_ptr(), 1024, S())
+        assert np.array_equal(sum_t.cpu().numpy(), orc.it_sum.value) and np.array_equal(min_t.cpu().numpy(), orc.it_min.value)
+
+
+# ------------------------------------------------------------------------------------------------ pixels
+def _aug_call(src, idx, shift, B, C, H, W, pad, mode, aug_rows, noise=None):
+    out = torch.empty((B, C, H, W), device=DEV)
+    L().gather_aug_u8(src.data_ptr(), out.data_ptr(), idx.data_ptr(), None if shift is None else shift.data_ptr(),
+                      None if noise is None else noise.data_ptr(), B, C, H, W, pad, mode, aug_rows, S())
+    return out.cpu().numpy()
+
+
+def test_pixel_gather_aug_matches_golden_reference():
+    fx = gu.load("aug_pixels")
+    b = gu.sub(fx, "buffer")
+    s, s1 = dev(b["s"]), dev(b["s1"])
+    _, C, H, W = b["s"].shape
+    g = gu.sub(fx, "drqv1")
+    B = len(g["idx"])
+    idx = dev(g["idx"])
+    sh = dev(np.stack([g["w1"], g["h1"]], 1), torch.int32)
+    assert np.array_equal(_aug_call(s, idx, sh, B, C, H, W, 4, 2, B), g["o"])     # DrqNoNoiseAug: exact in the reference
+    assert np.array_equal(_aug_call(s1, idx, sh, B, C, H, W, 4, 2, B), g["o1"])
+    g = gu.sub(fx, "drqv1_noise")
+    assert np.array_equal(_aug_call(s, idx, sh, B, C, H, W, 4, 2, B // 2, dev(g["n0"])), g["o"])
+    assert np.array_equal(_aug_call(s1, idx, sh, B, C, H, W, 4, 2, B // 2, dev(g["n1"])), g["o1"])
+    g = gu.sub(fx, "drqv2")
+    sh2 = dev(g["shift"].reshape(B, 2), torch.int32)
+    got = _aug_call(s, idx, sh2, B, C, H, W, 4, 1, int(B * 0.75))
+    assert np.array_equal(got, ao.mix(b["s"][g["idx"]].astype(np.float32), ao.drq_v2_crop(b["s"][g["idx"]], g["shift"]), 0.75))
+    assert np.abs(got - g["o"]).max() <= 4e-3  # vs the reference's bilinear grid_sample
+    assert np.array_equal(_aug_call(s, idx, None, B, C, H, W, 4, 0, 0), g["oo"])
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_pixel_gather_aug_full_size(mode):
+    """BASELINE config 4 shape: B=512 of 9x84x84 uint8 frames.  Oracle on a sample of rows + exact properties."""
+    rng = np.random.default_rng(2)
+    cap, B, C, H, W = 2048, 512, 9, 84, 84
+    src = torch.randint(0, 256, (cap, C, H, W), dtype=torch.uint8, device=DEV)
+    idx = rng.integers(0, cap, B)
+    hi = 9 if mode == 1 else 8
+    shift = rng.integers(0, hi, (B, 2))
+    aug_rows = 384
+    got = _aug_call(src, dev(idx), dev(shift, torch.int32), B, C, H, W, 4, mode, aug_rows)
+    rows = np.concatenate([np.arange(0, 8), np.arange(380, 392), np.arange(504, 512)])
+    sub = src[dev(idx[rows])].cpu().numpy()
+    if mode == 1:
+        want = ao.drq_v2_crop(sub, shift[rows])
+    else:
+        want = ao.drq_v1_crop(sub, shift[rows, 0], shift[rows, 1])
+    plain = sub.astype(np.float32)
+    for j, rrow in enumerate(rows):
+        assert np.array_equal(got[rrow], want[j] if rrow < aug_rows else plain[j])
+    # properties over the whole batch: values are uint8-valued; a centre shift (= pad) is the identity
+    assert np.array_equal(got, np.round(got)) and got.min() >= 0 and got.max() <= 255
+    ident = _aug_call(src, dev(idx), dev(np.full((B, 2), 4), torch.int32), B, C, H, W, 4, mode, B)
+    assert np.array_equal(ident, src[dev(idx)].float().cpu().numpy())
+
+
+# ------------------------------------------------------------------------------------------------ MLP
+def _arena_from(stack):
+    from super_sac_b200._arena import MLPArena
+
+    ar = MLPArena(stack.G, stack.D, stack.H, stack.O, DEV)
+    for n in uo.PARAM_NAMES:
+        ar.p[n].copy_(getattr(stack, n).to(DEV))
+    return ar
+
+
+@pytest.mark.parametrize("G,D,H,O,B", [(10, 23, 256, 1, 256), (3, 5, 33, 3, 17), (2, 67, 1024, 1, 512), (1, 17, 256, 12, 256)])
+def test_mlp_forward_backward_matches_oracle(G, D, H, O, B):
+    from super_sac_b200 import _ops
+
+    gen = torch.Generator().manual_seed(G * 1000 + H)
+    st = uo.MLPStack(G, D, H, O).random_init(gen)
+    ar = _arena_from(st)
+    x = torch.randn(B, D, generator=gen)
+    dy = torch.randn(G, B, O, generator=gen) / B
+    extra = torch.randn(G, B, H, generator=gen)
+    xd = x.to(DEV)
+    h1 = torch.empty((G, B, H), device=DEV)
+    h2 = torch.empty_like(h1)
+    y = torch.empty((G, B, O), device=DEV)
+    _ops.mlp_forward(ar, 0, G, xd, B, h1, h2, y)
+    grads = st.zeros_like()
+    dx_want = torch.zeros(G, B, D)
+    for g in range(G):
+        yw, h1w, h2w = uo.mlp_forward(st, g, x)
+        gu.assert_close(y[g].cpu().numpy(), yw.numpy(), 1e-4, 1e-5, f"y[{g}]")
+        gu.assert_close(h2[g].cpu().numpy(), h2w.numpy(), 1e-4, 1e-5, f"h2[{g}]")
+        dx_want[g] = uo.mlp_backward(st, g, x, h1w, h2w, dy[g], grads, dh2_extra=0.25 * extra[g], need_dx=True)
+    dx = torch.empty((G, B, D), device=DEV)
+    _ops.mlp_backward(ar, 0, G, xd, B, h1, h2, dy.to(DEV), dh2_extra=extra.to(DEV), extra_scale=0.25, want_dw=True,
+                      accumulate=False, dx=dx, lddx=D)
+    scale = {n: float(getattr(grads, n).abs().max()) for n in uo.PARAM_NAMES}
+    for n in uo.PARAM_NAMES:
+        gu.assert_close(ar.g[n].cpu().numpy(), getattr(grads, n).numpy(), 1e-4, 1e-5 * scale[n], f"grad {n}")
+    gu.assert_close(dx.cpu().numpy(), dx_want.numpy(), 1e-4, 1e-5 * float(dx_want.abs().max()), "dx")
+    # accumulate = True adds a second identical pass
+    _ops.mlp_backward(ar, 0, G, xd, B, h1, h2, dy.to(DEV), dh2_extra=extra.to(DEV), extra_scale=0.25, want_dw=True,
+                      accumulate=True)
+    for n in uo.PARAM_NAMES:
+        gu.assert_close(ar.g[n].cpu().numpy(), 2 * getattr(grads, n).numpy(), 1e-4, 2e-5 * scale[n], f"accumulated grad {n}")
+    # input-gradient-only pass with dy = None is the DR3 second pass
+    dx2 = torch.empty((G, B, D), device=DEV)
+    _ops.mlp_backward(ar, 0, G, xd, B, h1, h2, None, dh2_extra=extra.to(DEV), extra_scale=1.0, want_dw=False, dx=dx2, lddx=D)
+    for g in range(G):
+        _, h1w, h2w = uo.mlp_forward(st, g, x)
+        want = uo.mlp_backward(st, g, x, h1w, h2w, torch.zeros(B, O), st.zeros_like(), dh2_extra=extra[g], need_dx=True, need_dw=False)
+        gu.assert_close(dx2[g].cpu().numpy(), want.numpy(), 1e-4, 1e-5 * float(want.abs().max()), f"dx-only[{g}]")
+
+
+def test_mlp_subset_and_per_group_inputs():
+    from super_sac_b200 import _ops
+
+    gen = torch.Generator().manual_seed(9)
+    G, D, H, O, B = 6, 23, 64, 1, 40
+    st = uo.MLPStack(G, D, H, O).random_init(gen)
+    ar = _arena_from(st)
+    # REDQ subset: groups {4, 1} of member starting at net 1, inputs embedded in a wider matrix (ldx > D)
+    xw = torch.randn(B, D + 7, generator=gen)
+    sub = torch.tensor([4, 1], dtype=torch.int32)
+    h1 = torch.empty((2, B, H), device=DEV); h2 = torch.empty_like(h1); y = torch.empty((2, B, O), device=DEV)
+    _ops.mlp_forward(ar, 1, 2, xw.to(DEV), B, h1, h2, y, ldx=D + 7, net_index=sub.to(DEV))
+    for j, k in enumerate(sub.tolist()):
+        gu.assert_close(y[j].cpu().numpy(), uo.mlp_forward(st, 1 + k, xw[:, :D].contiguous())[0].numpy(), 1e-4, 1e-5, f"subset {k}")
+    # per-group inputs (x_gs != 0)
+    xg = torch.randn(G, B, D, generator=gen)
+    h1 = torch.empty((G, B, H), device=DEV); h2 = torch.empty_like(h1); y = torch.empty((G, B, O), device=DEV)
+    _ops.mlp_forward(ar, 0, G, xg.to(DEV), B, h1, h2, y, x_gs=B * D)
+    for g in range(G):
+        gu.assert_close(y[g].cpu().numpy(), uo.mlp_forward(st, g, xg[g])[0].numpy(), 1e-4, 1e-5, f"per-group {g}")
+
+
+# ------------------------------------------------------------------------------------------------ heads / TD / weights
+def test_policy_heads_match_oracle():
+    gen = torch.Generator().manual_seed(4)
+    B, A, lo, hi = 300, 6, -5.0, 2.0
+    out = torch.randn(B, 2 * A, generator=gen) * 1.5
+    eps = torch.randn(B, A, generator=gen)
+    a_w, logp_w, cache = uo.tanh_normal_sample(out, eps, lo, hi)
+    od, ed = out.to(DEV), eps.to(DEV)
+    X = torch.zeros((B, 17 + A), device=DEV)
+    logp = torch.empty(B, device=DEV)
+    L().tanh_normal_forward(od.data_ptr(), ed.data_ptr(), B, A, lo, hi, X[:, 17:].data_ptr(), 17 + A, logp.data_ptr(), S())
+    gu.assert_close(X[:, 17:].cpu().numpy(), a_w.numpy(), 1e-5, 1e-6, "a")
+    gu.assert_close(logp.cpu().numpy(), logp_w[:, 0].numpy(), 1e-4, 1e-4, "logp")
+    assert float(X[:, :17].abs().max()) == 0.0
+    da = torch.randn(B, A, generator=gen)
+    la = torch.tensor([math.log(0.2)])
+    dout_w = uo.tanh_normal_sample_backward(cache, da, torch.full((B, 1), 0.2 / B))
+    dout = torch.empty((B, 2 * A), device=DEV)
+    L().tanh_normal_backward(od.data_ptr(), ed.data_ptr(), B, A, lo, hi, da.to(DEV).data_ptr(), A, 1.0 / B, la.to(DEV).data_ptr(),
+                             dout.data_ptr(), S())
+    gu.assert_close(dout.cpu().numpy(), dout_w.numpy(), 1e-4, 1e-6, "dout")
+    # dataset actions (cache miss), incl. |a| > 0.99
+    act = (torch.rand(B, A, generator=gen) * 2 - 1) * 1.05
+    lp_w, c2 = uo.tanh_normal_logprob_data(out, act.clamp(-1, 1), lo, hi)
+    dl = torch.randn(B, 1, generator=gen)
+    dw = uo.tanh_normal_logprob_data_backward(c2, dl)
+    lp = torch.empty(B, device=DEV)
+    dout2 = torch.empty((B, 2 * A), device=DEV)
+    L().tanh_normal_logprob(od.data_ptr(), act.clamp(-1, 1).to(DEV).data_ptr(), A, B, A, lo, hi, lp.data_ptr(),
+                            dl[:, 0].contiguous().to(DEV).data_ptr(), dout2.data_ptr(), S())
+    gu.assert_close(lp.cpu().numpy(), lp_w[:, 0].numpy(), 1e-4, 1e-3, "logp(data)")
+    gu.assert_close(dout2.cpu().numpy(), dw.numpy(), 2e-4, 1e-3 * float(dw.abs().max()) * 1e-2, "dout(data)")
+    # deterministic head + TD3 noise
+    o2 = torch.randn(B, A, generator=gen)
+    nz = torch.randn(B, A, generator=gen)
+    want = uo.gaussian_noise_clamp(torch.tanh(o2), nz, 0.7, 0.3, -1.0, 1.0)
+    a2 = torch.empty((B, A), device=DEV); th = torch.empty((B, A), device=DEV)
+    L().det_head_forward(o2.to(DEV).data_ptr(), None, nz.to(DEV).data_ptr(), B, A, 0.7, 0.3, a2.data_ptr(), A, th.data_ptr(), S())
+    gu.assert_close(a2.cpu().numpy(), want.numpy(), 1e-6, 1e-6, "td3 action")
+
+
+@pytest.mark.parametrize("use_popart,pop,warm", [(False, False, False), (True, True, False), (True, True, True)])
+def test_td_target_matches_oracle(use_popart, pop, warm):
+    gen = torch.Generator().manual_seed(6)
+    M, B = 2, 256
+    q = torch.randn(M, B, generator=gen) * 3
+    logp = torch.randn(B, 1, generator=gen)
+    r = torch.randn(B, 1, generator=gen)
+    d = (torch.rand(B, 1, generator=gen) < 0.1).float()
+    la = torch.tensor([math.log(0.1)])
+    pa = None
+    if use_popart:
+        pa = uo.PopArt()
+        if warm:
+            pa.t, pa.mu, pa.nu, pa.w, pa.b = 1500, torch.tensor([0.3]), torch.tensor([1.7]), torch.tensor([0.9]), torch.tensor([0.1])
+    val = q.min(0).values.unsqueeze(1) - la.exp() * logp
+    if pa is not None and pop:
+        val = pa.forward(val, normalized=False)
+    y_w = r + 0.99 * (1.0 - d) * val
+    st = ctl = None
+    if pa is not None:
+        st = torch.cat([pa.mu, pa.nu, pa.w, pa.b]).to(DEV)
+        ctl = torch.tensor([pa.t, 0], dtype=torch.int32, device=DEV)
+        pa.update_stats(y_w)
+        y_w = pa.normalize_values(y_w)
+    y = torch.empty(B, device=DEV); logs = torch.zeros(3, device=DEV)
+    L().td_target(q.to(DEV).data_ptr(), M, B, logp.to(DEV).data_ptr(), la.to(DEV).data_ptr(), r.to(DEV).data_ptr(),
+                  d.to(DEV).data_ptr(), 0.99, None if st is None else st.data_ptr(), None if ctl is None else ctl.data_ptr(),
+                  int(pop), 1e-4, 1000, y.data_ptr(), logs.data_ptr(), S())
+    gu.assert_close(y.cpu().numpy(), y_w[:, 0].numpy(), 1e-4, 1e-5, "td target")
+    gu.assert_close(logs.cpu().numpy(), [y_w.mean().item(), y_w.std().item(), (la.exp() * logp).mean().item()], 1e-4, 1e-5, "logs")
+    if pa is not None:
+        gu.assert_close(st.cpu().numpy(), torch.cat([pa.mu, pa.nu, pa.w, pa.b]).numpy(), 1e-5, 1e-7, "popart state")
+        assert ctl.cpu().tolist() == [pa.t, int(pa.stable)]
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_backup_weights_match_oracle(kind):
+    gen = torch.Generator().manual_seed(8)
+    E, N, B, T = 5, 2, 256, 20.0
+    q = torch.randn(E, N, B, generator=gen)
+    std = q.min(1).values.std(0)
+    want = torch.sigmoid(-std * T) + 0.5 if kind == 0 else B * torch.softmax(-std * T, dim=0)
+    w = torch.empty(B, device=DEV); logs = torch.zeros(4, device=DEV)
+    L().backup_weights(q.to(DEV).data_ptr(), E, N, B, T, kind, w.data_ptr(), logs.data_ptr(), S())
+    gu.assert_close(w.cpu().numpy(), want.numpy(), 1e-4, 1e-6, "weights")
+    gu.assert_close(logs.cpu().numpy(), [want.mean().item(), want.max().item(), want.min().item(), want.std().item()], 1e-4, 1e-6, "logs")
+
+
+def test_rng_fill_statistics_and_replay_advance():
+    from super_sac_b200 import _rng
+
+    src = _rng.PhiloxSource(123)
+    idx = torch.empty(1 << 16, dtype=torch.int64, device=DEV)
+    nrm = torch.empty(1 << 18, device=DEV)
+    sub = torch.empty(4096 * 2, dtype=torch.int32, device=DEV)
+    sh = torch.empty(1 << 14, dtype=torch.int32, device=DEV)
+    src.fill(DEV, idx=idx, n_filled=1000, normal=nrm, subset=sub, N=10, M=2, shift=sh, shift_range=9)
+    i1 = idx.clone()
+    assert int(idx.min()) >= 0 and int(idx.max()) < 1000
+    cnt = torch.bincount(idx, minlength=1000).float()
+    assert abs(float(cnt.mean()) - 65.536) < 1e-3 and float(cnt.std()) < 12
+    assert abs(float(nrm.mean())) < 0.01 and abs(float(nrm.std()) - 1.0) < 0.01
+    assert abs(float((nrm**4).mean()) - 3.0) < 0.1
+    s2 = sub.view(-1, 2)
+    assert int(s2.min()) >= 0 and int(s2.max()) < 10 and bool((s2[:, 0] != s2[:, 1]).all())
+    pair = torch.bincount(s2[:, 0] * 10 + s2[:, 1], minlength=100).float()
+    assert float(pair[pair > 0].min()) > 15  # 90 ordered pairs, ~45 each
+    assert int(sh.min()) == 0 and int(sh.max()) == 8
+    src.fill(DEV, idx=idx, n_filled=1000)
+    assert not torch.equal(idx, i1)  # the offset advanced on the device
+    src2 = _rng.PhiloxSource(123)
+    j = torch.empty(1 << 16, dtype=torch.int64, device=DEV)
+    src2.fill(DEV, idx=j, n_filled=1000)
+    assert torch.equal(j, i1)  # same seed, same first draw
