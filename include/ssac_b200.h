@@ -13,6 +13,8 @@
  *     change between replays (Adam step, PopArt state, Philox offset, log_alpha) live in device memory.
  *   - return 0 on success, else a cudaError_t or a negative SSAC_E_* code; ssac_last_error() gives the
  *     message of the last failure on the calling thread.  No exceptions cross the ABI.
+ *   - hyper-parameters the reference keeps as Python floats (lr, betas, eps, tau, ...) cross as double so that
+ *     derived constants (1-beta2, 1-tau, bias corrections) round exactly like the reference's.
  *   - all floating point is IEEE fp32 (the reference runs true-fp32 SGEMM); replay / gather /
  *     augmentation / segment-tree entry points are bit-exact integer, byte or float64 work.
  *   - matrices are row-major; "ld" = elements between consecutive rows; "gs" = elements between groups.
@@ -38,10 +40,10 @@ int ssac_device_check(int device);
 
 /* ---- target networks: learning_utils.py:160-167 (soft_update / hard_update), main.py:409-414 ------ */
 /* target <- target*(1-tau) + source*tau, three separately rounded fp32 ops: bit-exact with the reference. */
-int ssac_polyak(float* target_dev, const float* source_dev, int64_t n, float tau, void* stream);
+int ssac_polyak(float* target_dev, const float* source_dev, int64_t n, double tau, void* stream);
 /* Same over a table of tensors (user encoders are arbitrary nn.Modules): table_dev = n_tensors x
  * {uint64 target_ptr, uint64 source_ptr, uint64 numel}; total_chunks = sum ceil(numel/chunk). */
-int ssac_polyak_multi(const uint64_t* table_dev, int n_tensors, int64_t max_numel, float tau, void* stream);
+int ssac_polyak_multi(const uint64_t* table_dev, int n_tensors, int64_t max_numel, double tau, void* stream);
 
 /* ---- optimiser: torch.optim.Adam as configured in main.py:188-239 (coupled L2, no amsgrad) -------- */
 /* ctl_dev: int32[2] = {step, blocks_done}; the kernel reads step, uses t = step+1 for the bias
@@ -50,12 +52,12 @@ int ssac_polyak_multi(const uint64_t* table_dev, int n_tensors, int64_t max_nume
  * min(1, max_norm/(sqrt(*gnorm_sq_dev)+1e-6)) (torch.nn.utils.clip_grad_norm_, learning.py:122-128) and,
  * if write_back_grad, the scaled gradient is stored to g_dev like clip_grad_norm_ does. */
 int ssac_adam_step(float* p_dev, float* g_dev, float* m_dev, float* v_dev, int64_t n, int32_t* ctl_dev,
-                   float lr, float beta1, float beta2, float eps, float weight_decay,
-                   const float* gnorm_sq_dev, float max_norm, int write_back_grad, void* stream);
+                   double lr, double beta1, double beta2, double eps, double weight_decay,
+                   const float* gnorm_sq_dev, double max_norm, int write_back_grad, void* stream);
 /* Adam followed by the Polyak update of the matching target parameters in one pass (36 B/param). */
 int ssac_adam_polyak_step(float* p_dev, float* g_dev, float* m_dev, float* v_dev, float* target_dev, int64_t n,
-                          int32_t* ctl_dev, float lr, float beta1, float beta2, float eps, float weight_decay,
-                          const float* gnorm_sq_dev, float max_norm, int write_back_grad, float tau, void* stream);
+                          int32_t* ctl_dev, double lr, double beta1, double beta2, double eps, double weight_decay,
+                          const float* gnorm_sq_dev, double max_norm, int write_back_grad, double tau, void* stream);
 /* out_dev[0] (+)= sum x^2  (global grad norm for clipping / get_grad_norm, learning_utils.py:95-106). */
 int ssac_sumsq(const float* x_dev, int64_t n, float* out_dev, int accumulate, void* stream);
 
@@ -152,7 +154,7 @@ int ssac_det_head_backward(const float* tanh_out_dev, const float* da_dev, int64
  * if popart_dev given.  logs_dev float[3] = {mean(y), std(y) (unbiased), mean(entropy_bonus)}. */
 int ssac_td_target(const float* q_t_dev, int M, int B, const float* logp_dev, const float* log_alpha_dev,
                    const float* r_dev, const float* d_dev, float gamma, float* popart_dev, int32_t* popart_ctl_dev,
-                   int pop, float popart_beta, int popart_min_steps, float* y_dev, float* logs_dev, void* stream);
+                   int pop, double popart_beta, int popart_min_steps, float* y_dev, float* logs_dev, void* stream);
 
 /* ---- weighted Bellman backups: learning_utils.py:357-398 ------------------------------------------ */
 /* kind 0 'sunrise': q [E,N,B] -> min over N -> unbiased std over E -> sigmoid(-std*T)+0.5
@@ -185,7 +187,7 @@ int ssac_sum_groups(const float* dx_dev, int G, int B, int64_t lddx, int col0, i
 /* loss = -mean(log_alpha*(logp + target_entropy)); Adam(beta1, beta2) on the scalar, state {m, v} in
  * state_dev float[2], step in ctl_dev int32[2].  logs_dev float[2] = {alpha_loss, exp(new log_alpha)}. */
 int ssac_alpha_step(float* log_alpha_dev, const float* logp_dev, int B, float target_entropy, float* state_dev,
-                    int32_t* ctl_dev, float lr, float beta1, float beta2, float eps, float* logs_dev, void* stream);
+                    int32_t* ctl_dev, double lr, double beta1, double beta2, double eps, float* logs_dev, void* stream);
 
 /* ---- advantage filter: adv_estimator.py:58-79, learning_utils.py:241-269,288-295 ------------------ */
 /* q_pi [n,B] = min-critic values of n policy samples, q_data [B]: adv = q_data - mean_n q_pi;

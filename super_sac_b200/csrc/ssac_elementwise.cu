@@ -101,15 +101,15 @@ __device__ __forceinline__ void adam1(float& p, float& g, float& m, float& v, co
 template <bool POLYAK>
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, float* __restrict__ tgt, int64_t n,
-                                                   int32_t* __restrict__ ctl, float lr, float b1, float b2, float eps,
+                                                   int32_t* __restrict__ ctl, double lr, double b1d, double b2d, float eps,
                                                    float wd, const float* __restrict__ gnorm_sq, float max_norm,
                                                    int write_back, float c1, float c2) {
   __shared__ AdamScalars sc;
   if (threadIdx.x == 0) {
     const int t = ctl[0] + 1;
-    const double bc1 = 1.0 - pow((double)b1, (double)t);
-    const double bc2 = 1.0 - pow((double)b2, (double)t);
-    sc.step_size = (float)((double)lr / bc1);
+    const double bc1 = 1.0 - pow(b1d, (double)t);
+    const double bc2 = 1.0 - pow(b2d, (double)t);
+    sc.step_size = (float)(lr / bc1);
     sc.bc2_sqrt = (float)sqrt(bc2);
     float coef = 1.f;
     if (gnorm_sq != nullptr && max_norm > 0.f) coef = fminf(1.f, max_norm / (sqrtf(*gnorm_sq) + 1e-6f));
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float*
   __syncthreads();
   const bool clip = (gnorm_sq != nullptr && max_norm > 0.f);
   const bool wb = clip && write_back;
-  const float one_m_b1 = (float)(1.0 - (double)b1), one_m_b2 = (float)(1.0 - (double)b2);
+  const float one_m_b1 = (float)(1.0 - b1d), one_m_b2 = (float)(1.0 - b2d), b2 = (float)b2d;
   const AdamScalars s = sc;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(1024) td_target_kernel(const float* __restrict
                                                          const float* __restrict__ log_alpha,
                                                          const float* __restrict__ r, const float* __restrict__ d,
                                                          float gamma, float* __restrict__ popart,
-                                                         int32_t* __restrict__ popart_ctl, int pop, float pa_beta,
+                                                         int32_t* __restrict__ popart_ctl, int pop, double pa_beta,
                                                          int pa_min_steps, float* __restrict__ y,
                                                          float* __restrict__ logs) {
   __shared__ float scratch[32];
@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(1024) td_target_kernel(const float* __restrict
     if (threadIdx.x == 0) {
       const int t = popart_ctl[0] + 1;
       const float old_sigma = sigma, old_mu = mu;
-      const double beta_t_d = (double)pa_beta / (1.0 - pow(1.0 - (double)pa_beta, (double)t));
+      const double beta_t_d = pa_beta / (1.0 - pow(1.0 - pa_beta, (double)t));
       const float beta_t = (float)beta_t_d, one_m = (float)(1.0 - beta_t_d);
       const float new_mu = __fadd_rn(__fmul_rn(one_m, mu), __fmul_rn(beta_t, mean_y));
       const float new_nu = __fadd_rn(__fmul_rn(one_m, nu), __fmul_rn(beta_t, mean_y2));
@@ -549,7 +549,7 @@ __global__ void sum_groups_kernel(const float* __restrict__ dx, int G, int B, in
 __global__ void __launch_bounds__(1024) alpha_step_kernel(float* __restrict__ log_alpha,
                                                           const float* __restrict__ logp, int B, float target_entropy,
                                                           float* __restrict__ state, int32_t* __restrict__ ctl,
-                                                          float lr, float b1, float b2, float eps,
+                                                          double lr, double b1, double b2, float eps,
                                                           float* __restrict__ logs) {
   __shared__ float scratch[32];
   float s = 0.f;
@@ -562,11 +562,11 @@ __global__ void __launch_bounds__(1024) alpha_step_kernel(float* __restrict__ lo
     const float g = -mean_t;
     const int t = ctl[0] + 1;
     float m = state[0], v = state[1];
-    m = m + (float)(1.0 - (double)b1) * (g - m);
-    v = v * b2;
-    v = v + (float)(1.0 - (double)b2) * g * g;
-    const double bc1 = 1.0 - pow((double)b1, (double)t), bc2 = 1.0 - pow((double)b2, (double)t);
-    const float step_size = (float)((double)lr / bc1);
+    m = m + (float)(1.0 - b1) * (g - m);
+    v = v * (float)b2;
+    v = v + (float)(1.0 - b2) * g * g;
+    const double bc1 = 1.0 - pow(b1, (double)t), bc2 = 1.0 - pow(b2, (double)t);
+    const float step_size = (float)(lr / bc1);
     const float denom = sqrtf(v) / (float)sqrt(bc2) + eps;
     const float nla = la - step_size * (m / denom);
     *log_alpha = nla;
@@ -622,20 +622,20 @@ int ssac_device_check(int device) {
   return 0;
 }
 
-int ssac_polyak(float* target, const float* source, int64_t n, float tau, void* stream) {
+int ssac_polyak(float* target, const float* source, int64_t n, double tau, void* stream) {
   if (n <= 0) return 0;
   SSAC_REQUIRE(target && source, "ssac_polyak: null pointer");
-  const float c1 = (float)(1.0 - (double)tau), c2 = tau;
+  const float c1 = (float)(1.0 - tau), c2 = (float)tau;
   const int grid = grid_for((n + 3) / 4, 256 * 4, 8);
   polyak_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(target, source, n, c1, c2);
   SSAC_CHECK_LAUNCH("ssac_polyak");
   return 0;
 }
 
-int ssac_polyak_multi(const uint64_t* table_dev, int n_tensors, int64_t max_numel, float tau, void* stream) {
+int ssac_polyak_multi(const uint64_t* table_dev, int n_tensors, int64_t max_numel, double tau, void* stream) {
   if (n_tensors <= 0) return 0;
   SSAC_REQUIRE(table_dev, "ssac_polyak_multi: null table");
-  const float c1 = (float)(1.0 - (double)tau), c2 = tau;
+  const float c1 = (float)(1.0 - tau), c2 = (float)tau;
   int gx = (int)((max_numel + 256 * 8 - 1) / (256 * 8));
   if (gx < 1) gx = 1;
   if (gx > 4 * kNumSMs) gx = 4 * kNumSMs;
@@ -646,34 +646,34 @@ int ssac_polyak_multi(const uint64_t* table_dev, int n_tensors, int64_t max_nume
 }
 
 static int adam_launch(bool polyak, float* p, float* g, float* m, float* v, float* tgt, int64_t n, int32_t* ctl,
-                       float lr, float b1, float b2, float eps, float wd, const float* gnorm_sq, float max_norm,
-                       int wb, float tau, void* stream) {
+                       double lr, double b1, double b2, double eps, double wd, const float* gnorm_sq, double max_norm,
+                       int wb, double tau, void* stream) {
   if (n <= 0) return 0;
   SSAC_REQUIRE(p && g && m && v && ctl, "ssac_adam_step: null pointer");
   const int grid = grid_for((n + 3) / 4, 256, 8);
-  const float c1 = (float)(1.0 - (double)tau), c2 = tau;
+  const float c1 = (float)(1.0 - tau), c2 = (float)tau;
   if (polyak) {
     SSAC_REQUIRE(tgt, "ssac_adam_polyak_step: null target");
-    adam_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, tgt, n, ctl, lr, b1, b2, eps, wd, gnorm_sq,
-                                                               max_norm, wb, c1, c2);
+    adam_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, tgt, n, ctl, lr, b1, b2, (float)eps, (float)wd,
+                                                               gnorm_sq, (float)max_norm, wb, c1, c2);
   } else {
-    adam_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, nullptr, n, ctl, lr, b1, b2, eps, wd,
-                                                                gnorm_sq, max_norm, wb, 0.f, 0.f);
+    adam_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, nullptr, n, ctl, lr, b1, b2, (float)eps,
+                                                                (float)wd, gnorm_sq, (float)max_norm, wb, 0.f, 0.f);
   }
   SSAC_CHECK_LAUNCH("ssac_adam_step");
   return 0;
 }
 
-int ssac_adam_step(float* p, float* g, float* m, float* v, int64_t n, int32_t* ctl, float lr, float beta1, float beta2,
-                   float eps, float weight_decay, const float* gnorm_sq_dev, float max_norm, int write_back_grad,
-                   void* stream) {
+int ssac_adam_step(float* p, float* g, float* m, float* v, int64_t n, int32_t* ctl, double lr, double beta1,
+                   double beta2, double eps, double weight_decay, const float* gnorm_sq_dev, double max_norm,
+                   int write_back_grad, void* stream) {
   return adam_launch(false, p, g, m, v, nullptr, n, ctl, lr, beta1, beta2, eps, weight_decay, gnorm_sq_dev, max_norm,
-                     write_back_grad, 0.f, stream);
+                     write_back_grad, 0.0, stream);
 }
 
-int ssac_adam_polyak_step(float* p, float* g, float* m, float* v, float* target, int64_t n, int32_t* ctl, float lr,
-                          float beta1, float beta2, float eps, float weight_decay, const float* gnorm_sq_dev,
-                          float max_norm, int write_back_grad, float tau, void* stream) {
+int ssac_adam_polyak_step(float* p, float* g, float* m, float* v, float* target, int64_t n, int32_t* ctl, double lr,
+                          double beta1, double beta2, double eps, double weight_decay, const float* gnorm_sq_dev,
+                          double max_norm, int write_back_grad, double tau, void* stream) {
   return adam_launch(true, p, g, m, v, target, n, ctl, lr, beta1, beta2, eps, weight_decay, gnorm_sq_dev, max_norm,
                      write_back_grad, tau, stream);
 }
@@ -737,7 +737,7 @@ int ssac_det_head_backward(const float* tanh_out, const float* da, int64_t ldda,
 }
 
 int ssac_td_target(const float* q_t, int M, int B, const float* logp, const float* log_alpha, const float* r,
-                   const float* d, float gamma, float* popart, int32_t* popart_ctl, int pop, float popart_beta,
+                   const float* d, float gamma, float* popart, int32_t* popart_ctl, int pop, double popart_beta,
                    int popart_min_steps, float* y, float* logs, void* stream) {
   SSAC_REQUIRE(q_t && r && d && y && M > 0 && B > 1, "ssac_td_target: bad args");
   SSAC_REQUIRE((popart == nullptr) == (popart_ctl == nullptr), "ssac_td_target: popart state and ctl go together");
@@ -791,10 +791,10 @@ int ssac_sum_groups(const float* dx, int G, int B, int64_t lddx, int col0, int A
 }
 
 int ssac_alpha_step(float* log_alpha, const float* logp, int B, float target_entropy, float* state, int32_t* ctl,
-                    float lr, float beta1, float beta2, float eps, float* logs, void* stream) {
+                    double lr, double beta1, double beta2, double eps, float* logs, void* stream) {
   SSAC_REQUIRE(log_alpha && logp && state && ctl && B > 0, "ssac_alpha_step: bad args");
   alpha_step_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(log_alpha, logp, B, target_entropy, state, ctl, lr, beta1,
-                                                          beta2, eps, logs);
+                                                          beta2, (float)eps, logs);
   SSAC_CHECK_LAUNCH("ssac_alpha_step");
   return 0;
 }

@@ -89,8 +89,8 @@ def test_adam_matches_oracle(wd, clip):
             gu.assert_close(gd.cpu().numpy(), ref_g.numpy(), 1e-5, 1e-12, f"clipped grad step {step}")
         gu.assert_close(p.cpu().numpy(), opt.params[0].numpy(), 1e-6, 3e-4 * 1e-3, f"adam params step {step}")
     assert int(ctl[0]) == 5 and int(ctl[1]) == 0
-    gu.assert_close(m.cpu().numpy(), opt.m[0].numpy(), 1e-5, 1e-9, "exp_avg")
-    gu.assert_close(v.cpu().numpy(), opt.v[0].numpy(), 1e-5, 1e-12, "exp_avg_sq")
+    gu.assert_close(m.cpu().numpy(), opt.m[0].numpy(), 1e-5, 1e-6 * float(opt.m[0].abs().max()), "exp_avg")
+    gu.assert_close(v.cpu().numpy(), opt.v[0].numpy(), 1e-5, 1e-6 * float(opt.v[0].abs().max()), "exp_avg_sq")
 
 
 def test_adam_polyak_fused_equals_separate():
@@ -193,7 +193,8 @@ def test_per_tree_large_matches_oracle():
     orc.it_min.set(np.arange(n), pr**0.6)
     sum_t = torch.zeros(2 * cap, dtype=torch.float64, device=DEV)
     min_t = torch.full((2 * cap,), float("inf"), dtype=torch.float64, device=DEV)
-    L().tree_set(sum_t.data_ptr(), min_t.data_ptr(), cap, dev(np.arange(n)).data_ptr(), dev(pr**0.6).data_ptr(), n, S())
+    all_idx, all_val = dev(np.arange(n)), dev(pr**0.6)  # keep the device tensors alive across the async launch
+    L().tree_set(sum_t.data_ptr(), min_t.data_ptr(), cap, all_idx.data_ptr(), all_val.data_ptr(), n, S())
     assert np.array_equal(sum_t.cpu().numpy(), orc.it_sum.value) and np.array_equal(min_t.cpu().numpy(), orc.it_min.value)
     for rnd in range(3):
         u = rng.uniform(size=1024)
@@ -201,12 +202,14 @@ def test_per_tree_large_matches_oracle():
         want = orc.it_sum.find_prefixsum_idx(u * total)
         idx = torch.empty(1024, dtype=torch.int64, device=DEV)
         w = torch.empty(1024, dtype=torch.float64, device=DEV)
-        L().tree_sample(sum_t.data_ptr(), min_t.data_ptr(), cap, n, dev(u).data_ptr(), 1024, 1.0, idx.data_ptr(), w.data_ptr(), S())
+        ud = dev(u)
+        L().tree_sample(sum_t.data_ptr(), min_t.data_ptr(), cap, n, ud.data_ptr(), 1024, 1.0, idx.data_ptr(), w.data_ptr(), S())
         assert np.array_equal(idx.cpu().numpy(), want)
         newp = rng.uniform(1e-3, 5.0, 1024) ** 0.6
         orc.it_sum.set(want, newp)
         orc.it_min.set(want, newp)
-        L().tree_set(sum_t.data_ptr(), min_t.data_ptr(), cap, idx.data_ptr(), dev(newp).data_ptr(), 1024, S())
+        npd = dev(newp)
+        L().tree_set(sum_t.data_ptr(), min_t.data_ptr(), cap, idx.data_ptr(), npd.data_ptr(), 1024, S())
         assert np.array_equal(sum_t.cpu().numpy(), orc.it_sum.value) and np.array_equal(min_t.cpu().numpy(), orc.it_min.value)
 
 
@@ -359,7 +362,8 @@ def test_policy_heads_match_oracle():
     la = torch.tensor([math.log(0.2)])
     dout_w = uo.tanh_normal_sample_backward(cache, da, torch.full((B, 1), 0.2 / B))
     dout = torch.empty((B, 2 * A), device=DEV)
-    L().tanh_normal_backward(od.data_ptr(), ed.data_ptr(), B, A, lo, hi, da.to(DEV).data_ptr(), A, 1.0 / B, la.to(DEV).data_ptr(),
+    dad, lad = da.to(DEV), la.to(DEV)
+    L().tanh_normal_backward(od.data_ptr(), ed.data_ptr(), B, A, lo, hi, dad.data_ptr(), A, 1.0 / B, lad.data_ptr(),
                              dout.data_ptr(), S())
     gu.assert_close(dout.cpu().numpy(), dout_w.numpy(), 1e-4, 1e-6, "dout")
     # dataset actions (cache miss), incl. |a| > 0.99
@@ -369,8 +373,8 @@ def test_policy_heads_match_oracle():
     dw = uo.tanh_normal_logprob_data_backward(c2, dl)
     lp = torch.empty(B, device=DEV)
     dout2 = torch.empty((B, 2 * A), device=DEV)
-    L().tanh_normal_logprob(od.data_ptr(), act.clamp(-1, 1).to(DEV).data_ptr(), A, B, A, lo, hi, lp.data_ptr(),
-                            dl[:, 0].contiguous().to(DEV).data_ptr(), dout2.data_ptr(), S())
+    actd, dld = act.clamp(-1, 1).to(DEV), dl[:, 0].contiguous().to(DEV)
+    L().tanh_normal_logprob(od.data_ptr(), actd.data_ptr(), A, B, A, lo, hi, lp.data_ptr(), dld.data_ptr(), dout2.data_ptr(), S())
     gu.assert_close(lp.cpu().numpy(), lp_w[:, 0].numpy(), 1e-4, 1e-3, "logp(data)")
     gu.assert_close(dout2.cpu().numpy(), dw.numpy(), 2e-4, 1e-3 * float(dw.abs().max()) * 1e-2, "dout(data)")
     # deterministic head + TD3 noise
@@ -378,7 +382,8 @@ def test_policy_heads_match_oracle():
     nz = torch.randn(B, A, generator=gen)
     want = uo.gaussian_noise_clamp(torch.tanh(o2), nz, 0.7, 0.3, -1.0, 1.0)
     a2 = torch.empty((B, A), device=DEV); th = torch.empty((B, A), device=DEV)
-    L().det_head_forward(o2.to(DEV).data_ptr(), None, nz.to(DEV).data_ptr(), B, A, 0.7, 0.3, a2.data_ptr(), A, th.data_ptr(), S())
+    o2d, nzd = o2.to(DEV), nz.to(DEV)
+    L().det_head_forward(o2d.data_ptr(), None, nzd.data_ptr(), B, A, 0.7, 0.3, a2.data_ptr(), A, th.data_ptr(), S())
     gu.assert_close(a2.cpu().numpy(), want.numpy(), 1e-6, 1e-6, "td3 action")
 
 
@@ -407,8 +412,9 @@ def test_td_target_matches_oracle(use_popart, pop, warm):
         pa.update_stats(y_w)
         y_w = pa.normalize_values(y_w)
     y = torch.empty(B, device=DEV); logs = torch.zeros(3, device=DEV)
-    L().td_target(q.to(DEV).data_ptr(), M, B, logp.to(DEV).data_ptr(), la.to(DEV).data_ptr(), r.to(DEV).data_ptr(),
-                  d.to(DEV).data_ptr(), 0.99, None if st is None else st.data_ptr(), None if ctl is None else ctl.data_ptr(),
+    qd, lpd, lad, rd, dd = q.to(DEV), logp.to(DEV), la.to(DEV), r.to(DEV), d.to(DEV)
+    L().td_target(qd.data_ptr(), M, B, lpd.data_ptr(), lad.data_ptr(), rd.data_ptr(),
+                  dd.data_ptr(), 0.99, None if st is None else st.data_ptr(), None if ctl is None else ctl.data_ptr(),
                   int(pop), 1e-4, 1000, y.data_ptr(), logs.data_ptr(), S())
     gu.assert_close(y.cpu().numpy(), y_w[:, 0].numpy(), 1e-4, 1e-5, "td target")
     gu.assert_close(logs.cpu().numpy(), [y_w.mean().item(), y_w.std().item(), (la.exp() * logp).mean().item()], 1e-4, 1e-5, "logs")
@@ -425,7 +431,8 @@ def test_backup_weights_match_oracle(kind):
     std = q.min(1).values.std(0)
     want = torch.sigmoid(-std * T) + 0.5 if kind == 0 else B * torch.softmax(-std * T, dim=0)
     w = torch.empty(B, device=DEV); logs = torch.zeros(4, device=DEV)
-    L().backup_weights(q.to(DEV).data_ptr(), E, N, B, T, kind, w.data_ptr(), logs.data_ptr(), S())
+    qd = q.to(DEV)
+    L().backup_weights(qd.data_ptr(), E, N, B, T, kind, w.data_ptr(), logs.data_ptr(), S())
     gu.assert_close(w.cpu().numpy(), want.numpy(), 1e-4, 1e-6, "weights")
     gu.assert_close(logs.cpu().numpy(), [want.mean().item(), want.max().item(), want.min().item(), want.std().item()], 1e-4, 1e-6, "logs")
 
