@@ -221,6 +221,7 @@ def run_gpu_arm(args, cfg, rank, world, local_rank):
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=device)
+    ssb.set_mlp_impl(args.mlp_impl)
     agent, target, critic_opt, enc_opt, log_alphas, buf = build_gpu(cfg, device, seed=rank)
     B = cfg["B"]
     augmenter = augmentations.AugmentationSequence([augmentations.IdentityAug(B)])
@@ -325,7 +326,7 @@ def run_gpu_arm(args, cfg, rank, world, local_rank):
                 "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_tflops"], "traffic": None, "us_per_launch_group": roof["ms"] * 1e3,
                 "peak_source": peaks["source"],
-                "note": "fp32 FFMA path (impl=1); peak is the measured dense bf16 tensor figure, fp32 SIMT peak is ~75 TFLOP/s"}
+                "note": "3xTF32 on tcgen05 (3 MMAs per fp32 product, so at most 1/6 of the bf16 figure); the step is launch/latency bound"}
 
     cpu_steps = 300
     cpu_ups, cpu_dt = time_cpu(cfg, cpu_steps, 10)
@@ -337,7 +338,7 @@ def run_gpu_arm(args, cfg, rank, world, local_rank):
                    "parallelism": "1 learner" if world == 1 else f"{world} independent learner replicas (no data-path collective)",
                    "l2": "replay ring %.0f MB > 126 MB L2 (random rows); parameters+moments (11.6 MB) are L2-resident by design"
                          % (buf_bytes(buf) / 1e6),
-                   "impl": "fp32 FFMA grouped GEMM (impl=1)"},
+                   "impl": "ensemble MLP GEMMs: " + ssb.get_mlp_impl()},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_steps, "path": "buffer.push(host transition) + learning.critic_update + soft_update + logs readback"},
@@ -432,6 +433,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="redq", choices=sorted(CONFIGS))
+    ap.add_argument("--mlp-impl", default="tcgen05", choices=["tcgen05", "ffma"])
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))

@@ -106,7 +106,10 @@ int ssac_tree_sample(const double* sum_tree_dev, const double* min_tree_dev, int
  * b2 [nets,H] W3 [nets,O,H] b3 [nets,O] (nn.Linear layout).  Group g uses net net_index_dev[g] (device
  * int32, e.g. the REDQ subset) or net g when NULL.  Input x_dev: row-major [.,B,D] with row stride ldx and
  * group stride x_gs (0 = every group reads the same batch).  Outputs h1/h2 [G,B,H] (nullable: not saved),
- * y [G,B,O].  impl: 0 = auto, 1 = fp32 FFMA tiles, 2 = tcgen05 3xTF32 tensor-core path. */
+ * y [G,B,O].  impl: 0 = library default (ssac_set_default_mlp_impl), 1 = fp32 FFMA tiles, 2 = tcgen05 tensor cores
+ * with 3xTF32 operand splitting (fp32-accurate: hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM). */
+int ssac_default_mlp_impl(void);
+int ssac_set_default_mlp_impl(int impl);
 int ssac_mlp_forward(const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
                      const float* b3, const int32_t* net_index_dev, int G, int D, int H, int O,
                      const float* x_dev, int64_t ldx, int64_t x_gs, int B, float* h1_dev, float* h2_dev,

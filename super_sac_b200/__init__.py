@@ -27,5 +27,18 @@ from . import learning  # noqa: E402
 
 manual_seed = _rng.manual_seed
 
+MLP_IMPLS = {"ffma": 1, "tcgen05": 2}
+
+
+def set_mlp_impl(name):
+    """Select how the ensemble MLP GEMMs run: "tcgen05" (default; 5th-gen tensor cores, 3xTF32 operand splitting,
+    fp32 accumulation in TMEM) or "ffma" (exact-fp32 CUDA-core tiles, the in-library cross-check)."""
+    _lib.lib().set_default_mlp_impl(MLP_IMPLS[name])
+
+
+def get_mlp_impl():
+    cur = _lib.lib().default_mlp_impl()
+    return next(k for k, v in MLP_IMPLS.items() if v == cur)
+
 __all__ = ["Agent", "agent", "nets", "replay", "learning", "learning_utils", "augmentations", "popart",
-           "adv_estimator", "device", "manual_seed"]
+           "adv_estimator", "device", "manual_seed", "set_mlp_impl", "get_mlp_impl"]

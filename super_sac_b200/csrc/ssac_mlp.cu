@@ -4,17 +4,26 @@
 namespace ssac {
 int mlp_forward_simt(const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
                      const float* b3, const int32_t* net_index, int G, int D, int H, int O, const float* x, int64_t ldx,
-                     int64_t x_gs, int B, float* h1, float* h2, float* y, cudaStream_t s);
+                     int64_t x_gs, int B, float* h1, float* h2, float* y, cudaStream_t s, int impl);
 int mlp_backward_simt(const float* W1, const float* W2, const float* W3, const int32_t* net_index, int G, int D, int H,
                       int O, const float* x, int64_t ldx, int64_t x_gs, int B, const float* h1, const float* h2,
                       const float* dy, const float* dh2_extra, float extra_scale, float* gW1, float* gb1, float* gW2,
                       float* gb2, float* gW3, float* gb3, int accumulate, float* dx, int64_t lddx, float* ws,
-                      cudaStream_t s);
+                      cudaStream_t s, int impl);
 }  // namespace ssac
 
 using namespace ssac;
 
+static int g_default_impl = 2;  // tcgen05 3xTF32 tensor-core path
+
 extern "C" {
+
+int ssac_default_mlp_impl(void) { return g_default_impl; }
+int ssac_set_default_mlp_impl(int impl) {
+  if (impl != 1 && impl != 2) return fail(SSAC_E_BADARG, "ssac_set_default_mlp_impl: impl must be 1 (fp32 FFMA) or 2 (tcgen05 3xTF32)");
+  g_default_impl = impl;
+  return 0;
+}
 
 int ssac_mlp_forward(const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
                      const float* b3, const int32_t* net_index_dev, int G, int D, int H, int O, const float* x_dev,
@@ -22,9 +31,10 @@ int ssac_mlp_forward(const float* W1, const float* b1, const float* W2, const fl
                      void* stream) {
   SSAC_REQUIRE(W1 && b1 && W2 && b2 && W3 && b3 && x_dev && y_dev, "ssac_mlp_forward: null pointer");
   SSAC_REQUIRE(G > 0 && D > 0 && H > 0 && O > 0 && B > 0 && ldx >= D, "ssac_mlp_forward: bad sizes");
-  if (impl == 0 || impl == 1)
+  if (impl == 0) impl = ssac_default_mlp_impl();
+  if (impl == 1 || impl == 2)
     return mlp_forward_simt(W1, b1, W2, b2, W3, b3, net_index_dev, G, D, H, O, x_dev, ldx, x_gs, B, h1_dev, h2_dev,
-                            y_dev, (cudaStream_t)stream);
+                            y_dev, (cudaStream_t)stream, impl);
   return fail(SSAC_E_UNSUPPORTED, "ssac_mlp_forward: unknown impl");
 }
 
@@ -38,10 +48,11 @@ int ssac_mlp_backward(const float* W1, const float* W2, const float* W3, const i
   SSAC_REQUIRE(W1 && W2 && W3 && x_dev && h1_dev && h2_dev, "ssac_mlp_backward: null pointer");
   SSAC_REQUIRE(G > 0 && D > 0 && H > 0 && O > 0 && B > 0 && ldx >= D, "ssac_mlp_backward: bad sizes");
   SSAC_REQUIRE(!dx_dev || lddx >= D, "ssac_mlp_backward: lddx < D");
-  if (impl == 0 || impl == 1)
+  if (impl == 0) impl = ssac_default_mlp_impl();
+  if (impl == 1 || impl == 2)
     return mlp_backward_simt(W1, W2, W3, net_index_dev, G, D, H, O, x_dev, ldx, x_gs, B, h1_dev, h2_dev, dy_dev,
                              dh2_extra_dev, extra_scale, gW1, gb1, gW2, gb2, gW3, gb3, accumulate, dx_dev, lddx,
-                             ws_dev, (cudaStream_t)stream);
+                             ws_dev, (cudaStream_t)stream, impl);
   return fail(SSAC_E_UNSUPPORTED, "ssac_mlp_backward: unknown impl");
 }
 

@@ -1,0 +1,28 @@
+// Shared declarations of the ensemble-MLP GEMM paths (fp32 FFMA tiles and tcgen05 3xTF32 tiles).
+#pragma once
+#include "ssac_common.cuh"
+
+namespace ssac {
+
+enum { L_NT = 0, L_NN = 1, L_TN = 2 };
+
+// C[g] (M x N, ldc) = epilogue( opA(A[g]) * opB(B[g]) )
+//   L_NT: A [M x K] row-major, B = W [N x K] row-major (nn.Linear weight)      -> forward layers
+//   L_NN: A [M x K] row-major, B = W [K x N] row-major                         -> backward data path
+//   L_TN: A given as [K x M] row-major, B [K x N] row-major                    -> backward weight path
+struct GemmP {
+  const float* A; int64_t lda, a_gs;
+  const float* Bm; int64_t ldb, b_gs;
+  const int32_t* b_index;  // group -> weight block (REDQ subset); NULL = identity
+  float* C; int64_t ldc, c_gs;
+  const float* bias; int64_t bias_gs;                                  // + bias[n]
+  const float* mask; int64_t ldmask, mask_gs;                          // .* (mask[m][n] > 0)
+  const float* extra; int64_t ldextra, extra_gs; float extra_scale;   // + s * extra[m][n] (before the mask)
+  float* colsum; int64_t colsum_gs;                                    // L_TN: colsum[m] = sum_k A[k][m]  (bias grads)
+  int M, N, K;
+  int relu, accumulate;
+};
+
+int launch_gemm_tc(int layout, const GemmP& p, int G, cudaStream_t s, const char* what);
+
+}  // namespace ssac

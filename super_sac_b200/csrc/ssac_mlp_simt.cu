@@ -7,24 +7,9 @@
 //   TN  C = A^T * B (+colsum)                backward weight path  dW = dZ^T * act, db = colsum(dZ)
 // This is the exact-fp32 path (the reference runs fp32 SGEMM); the tcgen05 path (impl = 2) in
 // ssac_mlp_tc.cu is checked against it.
-#include "ssac_common.cuh"
+#include "ssac_mlp.cuh"
 
 namespace ssac {
-
-enum { L_NT = 0, L_NN = 1, L_TN = 2 };
-
-struct GemmP {
-  const float* A; int64_t lda, a_gs;
-  const float* Bm; int64_t ldb, b_gs;
-  const int32_t* b_index;  // group -> weight block (REDQ subset); NULL = identity
-  float* C; int64_t ldc, c_gs;
-  const float* bias; int64_t bias_gs;
-  const float* mask; int64_t ldmask, mask_gs;
-  const float* extra; int64_t ldextra, extra_gs; float extra_scale;
-  float* colsum; int64_t colsum_gs;
-  int M, N, K;
-  int relu, accumulate;
-};
 
 constexpr int BM = 64, BN = 64, BK = 16, PADT = 4;
 
@@ -122,7 +107,137 @@ __global__ void __launch_bounds__(256) grouped_gemm_kernel(GemmP p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Narrow-head special cases (O <= kSmallO: critics have O = 1, actors O = A or 2A).  A 64x64 GEMM tile would be
+// almost empty for these; they are a mat-vec, an outer product and a batch reduction.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSmallO = 32;
+
+// y[g][b][o] = sum_h h2[g][b][h] * W3[wg][o][h] + b3[wg][o]      one warp per (g, b), h2 row read once
+template <int OMAX>
+__global__ void __launch_bounds__(256) head_forward_kernel(const float* __restrict__ h2, const float* __restrict__ W3,
+                                                           const float* __restrict__ b3,
+                                                           const int32_t* __restrict__ net_index, int G, int B, int H,
+                                                           int O, float* __restrict__ y) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= G * B) return;
+  const int g = warp / B;
+  const int wg = net_index ? net_index[g] : g;
+  const float* hrow = h2 + (int64_t)warp * H;
+  const float* W = W3 + (int64_t)wg * O * H;
+  float acc[OMAX];
+#pragma unroll
+  for (int o = 0; o < OMAX; ++o) acc[o] = 0.f;
+  for (int h = lane; h < H; h += 32) {
+    const float hv = hrow[h];
+#pragma unroll
+    for (int o = 0; o < OMAX; ++o)
+      if (o < O) acc[o] = fmaf(hv, __ldg(W + (int64_t)o * H + h), acc[o]);
+  }
+#pragma unroll
+  for (int o = 0; o < OMAX; ++o) {
+    if (o < O) {
+      const float tot = warp_sum(acc[o]);
+      if (lane == 0) y[(int64_t)warp * O + o] = tot + b3[(int64_t)wg * O + o];
+    }
+  }
+}
+
+// dz2[g][b][h] = (sum_o dy[g][b][o] * W3[wg][o][h] + s * extra[g][b][h]) * (h2[g][b][h] > 0)
+__global__ void __launch_bounds__(256) head_backward_data_kernel(const float* __restrict__ dy,
+                                                                 const float* __restrict__ W3,
+                                                                 const int32_t* __restrict__ net_index,
+                                                                 const float* __restrict__ extra, float extra_scale,
+                                                                 const float* __restrict__ h2, int G, int B, int H, int O,
+                                                                 float* __restrict__ dz2) {
+  const int64_t n = (int64_t)G * B * H;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int h = (int)(i % H);
+    const int64_t gb = i / H;
+    const int g = (int)(gb / B);
+    const int wg = net_index ? net_index[g] : g;
+    float acc = 0.f;
+    if (dy) {
+      const float* d = dy + gb * O;
+      const float* W = W3 + (int64_t)wg * O * H + h;
+      for (int o = 0; o < O; ++o) acc = fmaf(d[o], __ldg(W + (int64_t)o * H), acc);
+    }
+    if (extra) acc += extra_scale * extra[i];
+    dz2[i] = h2[i] > 0.f ? acc : 0.f;
+  }
+}
+
+// gW3[g][o][h] (+)= sum_b dy[g][b][o] * h2[g][b][h];  gb3[g][o] (+)= sum_b dy[g][b][o]
+// grid (ceil(H/32), O, G), block 32 x 8: lane = h, 8 batch slices reduced through shared memory
+__global__ void __launch_bounds__(256) head_backward_weight_kernel(const float* __restrict__ dy,
+                                                                   const float* __restrict__ h2, int B, int H, int O,
+                                                                   float* __restrict__ gW3, float* __restrict__ gb3,
+                                                                   int accumulate) {
+  __shared__ float part[8][33];
+  __shared__ float bpart[8];
+  const int g = blockIdx.z, o = blockIdx.y, lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int h = blockIdx.x * 32 + lane;
+  const float* d = dy + (int64_t)g * B * O + o;
+  const float* hp = h2 + (int64_t)g * B * H + h;
+  float acc = 0.f, bsum = 0.f;
+  for (int b = slice; b < B; b += 8) {
+    const float dv = __ldg(d + (int64_t)b * O);
+    if (h < H) acc = fmaf(dv, hp[(int64_t)b * H], acc);
+    bsum += dv;
+  }
+  part[slice][lane] = acc;
+  if (lane == 0) bpart[slice] = bsum;
+  __syncthreads();
+  if (slice == 0) {
+    float tot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tot += part[k][lane];
+    if (h < H) {
+      float* w = gW3 + ((int64_t)g * O + o) * H + h;
+      *w = accumulate ? (*w + tot) : tot;
+    }
+    if (blockIdx.x == 0 && lane == 0) {
+      float bt = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) bt += bpart[k];
+      float* bb = gb3 + (int64_t)g * O + o;
+      *bb = accumulate ? (*bb + bt) : bt;
+    }
+  }
+}
+
+int head_forward(const float* h2, const float* W3, const float* b3, const int32_t* net_index, int G, int B, int H, int O,
+                 float* y, cudaStream_t s) {
+  const int64_t warps = (int64_t)G * B;
+  const unsigned grid = (unsigned)((warps * 32 + 255) / 256);
+  if (O <= 2) head_forward_kernel<2><<<grid, 256, 0, s>>>(h2, W3, b3, net_index, G, B, H, O, y);
+  else if (O <= 8) head_forward_kernel<8><<<grid, 256, 0, s>>>(h2, W3, b3, net_index, G, B, H, O, y);
+  else if (O <= 16) head_forward_kernel<16><<<grid, 256, 0, s>>>(h2, W3, b3, net_index, G, B, H, O, y);
+  else head_forward_kernel<32><<<grid, 256, 0, s>>>(h2, W3, b3, net_index, G, B, H, O, y);
+  SSAC_CHECK_LAUNCH("mlp head forward");
+  return 0;
+}
+int head_backward_data(const float* dy, const float* W3, const int32_t* net_index, const float* extra, float extra_scale,
+                       const float* h2, int G, int B, int H, int O, float* dz2, cudaStream_t s) {
+  const int64_t n = (int64_t)G * B * H;
+  int grid = (int)((n + 255) / 256);
+  if (grid > 16 * kNumSMs) grid = 16 * kNumSMs;
+  head_backward_data_kernel<<<grid, 256, 0, s>>>(dy, W3, net_index, extra, extra_scale, h2, G, B, H, O, dz2);
+  SSAC_CHECK_LAUNCH("mlp head backward (data)");
+  return 0;
+}
+int head_backward_weight(const float* dy, const float* h2, int G, int B, int H, int O, float* gW3, float* gb3,
+                         int accumulate, cudaStream_t s) {
+  dim3 grid((H + 31) / 32, O, G);
+  head_backward_weight_kernel<<<grid, 256, 0, s>>>(dy, h2, B, H, O, gW3, gb3, accumulate);
+  SSAC_CHECK_LAUNCH("mlp head backward (weights)");
+  return 0;
+}
+
+static thread_local int g_impl = 1;  // set by the entry points for the duration of one call
+
 static int launch_gemm(int layout, const GemmP& p, int G, cudaStream_t s, const char* what) {
+  if (g_impl == 2) return launch_gemm_tc(layout, p, G, s, what);
   dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, G);
   if (layout == L_NT) grouped_gemm_kernel<L_NT><<<grid, 256, 0, s>>>(p);
   else if (layout == L_NN) grouped_gemm_kernel<L_NN><<<grid, 256, 0, s>>>(p);
@@ -142,8 +257,9 @@ static GemmP blank() {
 
 int mlp_forward_simt(const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
                      const float* b3, const int32_t* net_index, int G, int D, int H, int O, const float* x, int64_t ldx,
-                     int64_t x_gs, int B, float* h1, float* h2, float* y, cudaStream_t s) {
-  SSAC_REQUIRE(h1 && h2, "ssac_mlp_forward(impl=1): h1/h2 buffers are required");
+                     int64_t x_gs, int B, float* h1, float* h2, float* y, cudaStream_t s, int impl) {
+  SSAC_REQUIRE(h1 && h2, "ssac_mlp_forward: h1/h2 buffers are required");
+  g_impl = impl;
   GemmP p = blank();
   // layer 1: h1 = relu(x W1^T + b1)
   p.A = x; p.lda = ldx; p.a_gs = x_gs; p.Bm = W1; p.ldb = D; p.b_gs = (int64_t)H * D; p.b_index = net_index;
@@ -156,6 +272,7 @@ int mlp_forward_simt(const float* W1, const float* b1, const float* W2, const fl
   rc = launch_gemm(L_NT, p, G, s, "mlp_forward L2");
   if (rc) return rc;
   // layer 3: y = h2 W3^T + b3
+  if (O <= kSmallO) return head_forward(h2, W3, b3, net_index, G, B, H, O, y, s);
   p.A = h2; p.Bm = W3; p.ldb = H; p.b_gs = (int64_t)O * H; p.C = y; p.ldc = O; p.c_gs = (int64_t)B * O;
   p.bias = b3; p.bias_gs = O; p.relu = 0; p.N = O; p.K = H;
   return launch_gemm(L_NT, p, G, s, "mlp_forward L3");
@@ -165,7 +282,8 @@ int mlp_backward_simt(const float* W1, const float* W2, const float* W3, const i
                       int O, const float* x, int64_t ldx, int64_t x_gs, int B, const float* h1, const float* h2,
                       const float* dy, const float* dh2_extra, float extra_scale, float* gW1, float* gb1, float* gW2,
                       float* gb2, float* gW3, float* gb3, int accumulate, float* dx, int64_t lddx, float* ws,
-                      cudaStream_t s) {
+                      cudaStream_t s, int impl) {
+  g_impl = impl;
   const bool need_dw = gW1 != nullptr;
   SSAC_REQUIRE(!need_dw || (gb1 && gW2 && gb2 && gW3 && gb3), "ssac_mlp_backward: weight grads come as a full set");
   SSAC_REQUIRE(!need_dw || net_index == nullptr, "ssac_mlp_backward: weight grads with a net subset are unsupported");
@@ -181,10 +299,14 @@ int mlp_backward_simt(const float* W1, const float* W2, const float* W3, const i
   p.extra = dh2_extra; p.ldextra = H; p.extra_gs = (int64_t)B * H; p.extra_scale = extra_scale;
   p.M = B; p.N = H; p.K = dy ? O : 0;
   if (!dy) p.A = h2;  // never dereferenced (K = 0), keeps pointer arithmetic valid
-  rc = launch_gemm(L_NN, p, G, s, "mlp_backward dz2");
+  if (O <= kSmallO) rc = head_backward_data(dy, W3, net_index, dh2_extra, extra_scale, h2, G, B, H, O, dz2, s);
+  else rc = launch_gemm(L_NN, p, G, s, "mlp_backward dz2");
   if (rc) return rc;
   if (need_dw) {
-    if (dy) {
+    if (dy && O <= kSmallO) {
+      rc = head_backward_weight(dy, h2, G, B, H, O, gW3, gb3, accumulate, s);
+      if (rc) return rc;
+    } else if (dy) {
       // gW3 = dy^T h2, gb3 = colsum(dy)
       GemmP q = blank();
       q.A = dy; q.lda = O; q.a_gs = (int64_t)B * O; q.Bm = h2; q.ldb = H; q.b_gs = (int64_t)B * H;

@@ -279,8 +279,10 @@ def _arena_from(stack):
     return ar
 
 
-@pytest.mark.parametrize("G,D,H,O,B", [(10, 23, 256, 1, 256), (3, 5, 33, 3, 17), (2, 67, 1024, 1, 512), (1, 17, 256, 12, 256)])
-def test_mlp_forward_backward_matches_oracle(G, D, H, O, B):
+@pytest.mark.parametrize("impl", [1, 2], ids=["ffma", "tcgen05"])
+@pytest.mark.parametrize("G,D,H,O,B", [(10, 23, 256, 1, 256), (3, 5, 33, 3, 17), (2, 67, 1024, 1, 512), (1, 17, 256, 12, 256),
+                                       (2, 40, 200, 40, 130)])
+def test_mlp_forward_backward_matches_oracle(G, D, H, O, B, impl):
     from super_sac_b200 import _ops
 
     gen = torch.Generator().manual_seed(G * 1000 + H)
@@ -293,7 +295,7 @@ def test_mlp_forward_backward_matches_oracle(G, D, H, O, B):
     h1 = torch.empty((G, B, H), device=DEV)
     h2 = torch.empty_like(h1)
     y = torch.empty((G, B, O), device=DEV)
-    _ops.mlp_forward(ar, 0, G, xd, B, h1, h2, y)
+    _ops.mlp_forward(ar, 0, G, xd, B, h1, h2, y, impl=impl)
     grads = st.zeros_like()
     dx_want = torch.zeros(G, B, D)
     for g in range(G):
@@ -303,26 +305,28 @@ def test_mlp_forward_backward_matches_oracle(G, D, H, O, B):
         dx_want[g] = uo.mlp_backward(st, g, x, h1w, h2w, dy[g], grads, dh2_extra=0.25 * extra[g], need_dx=True)
     dx = torch.empty((G, B, D), device=DEV)
     _ops.mlp_backward(ar, 0, G, xd, B, h1, h2, dy.to(DEV), dh2_extra=extra.to(DEV), extra_scale=0.25, want_dw=True,
-                      accumulate=False, dx=dx, lddx=D)
+                      accumulate=False, dx=dx, lddx=D, impl=impl)
     scale = {n: float(getattr(grads, n).abs().max()) for n in uo.PARAM_NAMES}
     for n in uo.PARAM_NAMES:
         gu.assert_close(ar.g[n].cpu().numpy(), getattr(grads, n).numpy(), 1e-4, 1e-5 * scale[n], f"grad {n}")
     gu.assert_close(dx.cpu().numpy(), dx_want.numpy(), 1e-4, 1e-5 * float(dx_want.abs().max()), "dx")
     # accumulate = True adds a second identical pass
     _ops.mlp_backward(ar, 0, G, xd, B, h1, h2, dy.to(DEV), dh2_extra=extra.to(DEV), extra_scale=0.25, want_dw=True,
-                      accumulate=True)
+                      accumulate=True, impl=impl)
     for n in uo.PARAM_NAMES:
         gu.assert_close(ar.g[n].cpu().numpy(), 2 * getattr(grads, n).numpy(), 1e-4, 2e-5 * scale[n], f"accumulated grad {n}")
     # input-gradient-only pass with dy = None is the DR3 second pass
     dx2 = torch.empty((G, B, D), device=DEV)
-    _ops.mlp_backward(ar, 0, G, xd, B, h1, h2, None, dh2_extra=extra.to(DEV), extra_scale=1.0, want_dw=False, dx=dx2, lddx=D)
+    _ops.mlp_backward(ar, 0, G, xd, B, h1, h2, None, dh2_extra=extra.to(DEV), extra_scale=1.0, want_dw=False, dx=dx2, lddx=D,
+                      impl=impl)
     for g in range(G):
         _, h1w, h2w = uo.mlp_forward(st, g, x)
         want = uo.mlp_backward(st, g, x, h1w, h2w, torch.zeros(B, O), st.zeros_like(), dh2_extra=extra[g], need_dx=True, need_dw=False)
         gu.assert_close(dx2[g].cpu().numpy(), want.numpy(), 1e-4, 1e-5 * float(want.abs().max()), f"dx-only[{g}]")
 
 
-def test_mlp_subset_and_per_group_inputs():
+@pytest.mark.parametrize("impl", [1, 2], ids=["ffma", "tcgen05"])
+def test_mlp_subset_and_per_group_inputs(impl):
     from super_sac_b200 import _ops
 
     gen = torch.Generator().manual_seed(9)
@@ -333,13 +337,13 @@ def test_mlp_subset_and_per_group_inputs():
     xw = torch.randn(B, D + 7, generator=gen)
     sub = torch.tensor([4, 1], dtype=torch.int32)
     h1 = torch.empty((2, B, H), device=DEV); h2 = torch.empty_like(h1); y = torch.empty((2, B, O), device=DEV)
-    _ops.mlp_forward(ar, 1, 2, xw.to(DEV), B, h1, h2, y, ldx=D + 7, net_index=sub.to(DEV))
+    _ops.mlp_forward(ar, 1, 2, xw.to(DEV), B, h1, h2, y, ldx=D + 7, net_index=sub.to(DEV), impl=impl)
     for j, k in enumerate(sub.tolist()):
         gu.assert_close(y[j].cpu().numpy(), uo.mlp_forward(st, 1 + k, xw[:, :D].contiguous())[0].numpy(), 1e-4, 1e-5, f"subset {k}")
     # per-group inputs (x_gs != 0)
     xg = torch.randn(G, B, D, generator=gen)
     h1 = torch.empty((G, B, H), device=DEV); h2 = torch.empty_like(h1); y = torch.empty((G, B, O), device=DEV)
-    _ops.mlp_forward(ar, 0, G, xg.to(DEV), B, h1, h2, y, x_gs=B * D)
+    _ops.mlp_forward(ar, 0, G, xg.to(DEV), B, h1, h2, y, x_gs=B * D, impl=impl)
     for g in range(G):
         gu.assert_close(y[g].cpu().numpy(), uo.mlp_forward(st, g, xg[g])[0].numpy(), 1e-4, 1e-5, f"per-group {g}")
 

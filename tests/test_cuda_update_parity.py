@@ -31,12 +31,14 @@ def _cmp_logs(logs, want, what):
         gu.assert_close(float(logs[k2]), float(v), 2e-4, 2e-5, f"{what} log {k2}")
 
 
+@pytest.mark.parametrize("impl", ["tcgen05", "ffma"])
 @pytest.mark.parametrize("case", gu.UPDATE_CASES)
-def test_update_matches_reference(case):
+def test_update_matches_reference(case, impl):
     import cuda_util as cu
     import super_sac_b200 as ssb
     from super_sac_b200 import _rng, augmentations, learning, learning_utils as lu
 
+    ssb.set_mlp_impl(impl)
     fx = gu.load("update_" + case)
     cfg, agent, target = cu.agent_from_fixture(fx)
     E, N, M, B, A = cfg["E"], cfg["N"], cfg["M"], cfg["B"], cfg["A"]
@@ -155,3 +157,4 @@ def test_update_matches_reference(case):
     finally:
         lu.compute_td_targets, lu.compute_backup_weights = o_td, o_bw
         _rng.set_source(old_src)
+        ssb.set_mlp_impl("tcgen05")
