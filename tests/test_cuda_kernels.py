@@ -298,11 +298,18 @@ def test_mlp_forward_backward_matches_oracle(G, D, H, O, B, impl):
     _ops.mlp_forward(ar, 0, G, xd, B, h1, h2, y, impl=impl)
     grads = st.zeros_like()
     dx_want = torch.zeros(G, B, D)
+    h1_ref, h2_ref = torch.empty(G, B, H), torch.empty(G, B, H)
     for g in range(G):
         yw, h1w, h2w = uo.mlp_forward(st, g, x)
-        gu.assert_close(y[g].cpu().numpy(), yw.numpy(), 1e-4, 1e-5, f"y[{g}]")
-        gu.assert_close(h2[g].cpu().numpy(), h2w.numpy(), 1e-4, 1e-5, f"h2[{g}]")
+        scale = float(h2w.abs().max())
+        gu.assert_close(y[g].cpu().numpy(), yw.numpy(), 1e-4, 2e-5 * max(1.0, float(yw.abs().max())), f"y[{g}]")
+        gu.assert_close(h2[g].cpu().numpy(), h2w.numpy(), 1e-4, 2e-5 * scale, f"h2[{g}]")
+        h1_ref[g], h2_ref[g] = h1w, h2w
         dx_want[g] = uo.mlp_backward(st, g, x, h1w, h2w, dy[g], grads, dh2_extra=0.25 * extra[g], need_dx=True)
+    # the backward is checked on the oracle's activations: a pre-activation within rounding of zero may land on
+    # either side of the ReLU in two correct fp32 forwards, which flips a whole gradient row (not a kernel property)
+    h1.copy_(h1_ref.to(DEV))
+    h2.copy_(h2_ref.to(DEV))
     dx = torch.empty((G, B, D), device=DEV)
     _ops.mlp_backward(ar, 0, G, xd, B, h1, h2, dy.to(DEV), dh2_extra=extra.to(DEV), extra_scale=0.25, want_dw=True,
                       accumulate=False, dx=dx, lddx=D, impl=impl)
@@ -320,8 +327,8 @@ def test_mlp_forward_backward_matches_oracle(G, D, H, O, B, impl):
     _ops.mlp_backward(ar, 0, G, xd, B, h1, h2, None, dh2_extra=extra.to(DEV), extra_scale=1.0, want_dw=False, dx=dx2, lddx=D,
                       impl=impl)
     for g in range(G):
-        _, h1w, h2w = uo.mlp_forward(st, g, x)
-        want = uo.mlp_backward(st, g, x, h1w, h2w, torch.zeros(B, O), st.zeros_like(), dh2_extra=extra[g], need_dx=True, need_dw=False)
+        want = uo.mlp_backward(st, g, x, h1_ref[g], h2_ref[g], torch.zeros(B, O), st.zeros_like(), dh2_extra=extra[g], need_dx=True,
+                               need_dw=False)
         gu.assert_close(dx2[g].cpu().numpy(), want.numpy(), 1e-4, 1e-5 * float(want.abs().max()), f"dx-only[{g}]")
 
 
