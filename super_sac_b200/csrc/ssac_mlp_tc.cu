@@ -25,21 +25,12 @@
 namespace ssac {
 namespace tc {
 
-#ifdef SSAC_TRACE
-__device__ long long* g_trace = nullptr;
-#define TRACE(slot)                                                        \
-  do {                                                                     \
-    if (g_trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == TRACE_TID) g_trace[slot] = clock64(); \
-  } while (0)
-#else
-#define TRACE(slot) do {} while (0)
-#endif
-
 constexpr int TM = 128;      // MMA M (one CTA, cta_group::1)
 constexpr int TN = 128;      // tile N (MMA N = 16..128, multiple of 16)
 constexpr int TK = 32;       // k per pipeline stage (4 MMA k-steps of 8)
 constexpr int kStages = 2;
-constexpr int kThreads = 256;  // 8 warps: all stage operands; warps w and w+4 share TMEM lane quarter w%4
+constexpr int kProducerThreads = 256;  // warps 0-7 stage operands and run the epilogue (warps w, w+4 share TMEM lane quarter w%4)
+constexpr int kThreads = kProducerThreads + 32;  // + warp 8: the MMA issuer
 constexpr int kOperandBytes = TM * TK * 4;            // one hi or lo plane of one operand: 16 KB
 constexpr int kStageBytes = 4 * kOperandBytes;        // A_hi, A_lo, B_hi, B_lo
 constexpr int kSmemBytes = kStages * kStageBytes;     // 128 KB
@@ -69,6 +60,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (++spins > 50000000u) __trap();
   }
 }
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void producers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kProducerThreads) : "memory"); }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
@@ -133,6 +129,17 @@ __device__ __forceinline__ float tf32_hi(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
   return __uint_as_float(u);
 }
+#ifdef SSAC_TRUNC_SPLIT
+// experiment: the "hi" plane is the raw fp32 value (the tensor core ignores the low 13 mantissa bits of a tf32
+// operand), lo = x - trunc_tf32(x)
+__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+__device__ __forceinline__ void split_store(uint8_t* hi_plane, uint8_t* lo_plane, uint32_t off, float4 v) {
+  float4 l;
+  l.x = v.x - tf32_trunc(v.x); l.y = v.y - tf32_trunc(v.y); l.z = v.z - tf32_trunc(v.z); l.w = v.w - tf32_trunc(v.w);
+  *reinterpret_cast<float4*>(hi_plane + off) = v;
+  *reinterpret_cast<float4*>(lo_plane + off) = l;
+}
+#else
 __device__ __forceinline__ void split_store(uint8_t* hi_plane, uint8_t* lo_plane, uint32_t off, float4 v) {
   float4 h, l;
   h.x = tf32_hi(v.x); h.y = tf32_hi(v.y); h.z = tf32_hi(v.z); h.w = tf32_hi(v.w);
@@ -140,6 +147,7 @@ __device__ __forceinline__ void split_store(uint8_t* hi_plane, uint8_t* lo_plane
   *reinterpret_cast<float4*>(hi_plane + off) = h;
   *reinterpret_cast<float4*>(lo_plane + off) = l;
 }
+#endif
 
 // ---- operand staging -------------------------------------------------------------------------------------------
 // K-contiguous source [rows][K] (row-major, ld) -> K-major planes (SWIZZLE_128B).  Thread t owns the 4-k chunk
@@ -215,15 +223,14 @@ __device__ __forceinline__ void store_mnmajor(uint8_t* hi, uint8_t* lo, const fl
 template <int LAYOUT>
 __global__ void __launch_bounds__(kThreads, 1) grouped_gemm_tc_kernel(GemmP p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar_stage[kStages];
+  __shared__ __align__(8) uint64_t bar_full[kStages];    // producers -> MMA warp: stage s holds chunk kc
+  __shared__ __align__(8) uint64_t bar_empty[kStages];   // tensor core -> producers: the MMAs reading stage s are done
   __shared__ __align__(8) uint64_t bar_done;
   __shared__ uint32_t tmem_base_sh;
   __shared__ float colsum_sh[8][TM];
 
   constexpr bool A_MN = (LAYOUT == L_TN);   // A given as [K][M]
   constexpr bool B_MN = (LAYOUT != L_NT);   // B given as [K][N] for NN / TN
-  constexpr int TRACE_TID = 33;
-  TRACE(0);
   const int g = blockIdx.z;
   const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
   const int wg = p.b_index ? p.b_index[g] : g;
@@ -238,7 +245,10 @@ __global__ void __launch_bounds__(kThreads, 1) grouped_gemm_tc_kernel(GemmP p) {
 
   if (warp == 0) tmem_alloc(&tmem_base_sh, tmem_cols);
   if (t == 0) {
-    for (int s = 0; s < kStages; ++s) mbar_init(&bar_stage[s], 1);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&bar_full[s], kProducerThreads);
+      mbar_init(&bar_empty[s], 1);
+    }
     mbar_init(&bar_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -246,170 +256,185 @@ __global__ void __launch_bounds__(kThreads, 1) grouped_gemm_tc_kernel(GemmP p) {
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_d = tmem_base_sh;
-  TRACE(1);
-
-  const bool a_vec = ((p.lda & 3) == 0) && ((((uintptr_t)A) & 15) == 0) && (A_MN ? ((m0 & 3) == 0) : true);
-  const bool b_vec = ((p.ldb & 3) == 0) && ((((uintptr_t)Bm) & 15) == 0) && (B_MN ? ((n0 & 3) == 0) : true);
-  const bool do_colsum = (LAYOUT == L_TN) && p.colsum != nullptr && blockIdx.x == 0;
-  float cs[4] = {0.f, 0.f, 0.f, 0.f};
-
-  const uint32_t idesc = instr_desc(n_mma, A_MN ? 1 : 0, B_MN ? 1 : 0);
   const int nk = (p.K + TK - 1) / TK;
-  for (int kc = 0; kc < nk; ++kc) {
-    const int s = kc & 1, k0 = kc * TK;
-    uint8_t* st = smem + s * kStageBytes;
-    uint8_t *a_hi = st, *a_lo = st + kOperandBytes, *b_hi = st + 2 * kOperandBytes, *b_lo = st + 3 * kOperandBytes;
-    TRACE(2 + 4 * kc);
-    float4 va[4], vb[4];
-    if (A_MN) load_mnmajor(va, A, p.lda, m0, p.M, k0, p.K, a_vec);
-    else load_kmajor(va, A, p.lda, m0, p.M, k0, p.K, a_vec);
-    if (B_MN) load_mnmajor(vb, Bm, p.ldb, n0, p.N, k0, p.K, b_vec);
-    else load_kmajor(vb, Bm, p.ldb, n0, p.N, k0, p.K, b_vec);
-    if (do_colsum) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { cs[0] += va[i].x; cs[1] += va[i].y; cs[2] += va[i].z; cs[3] += va[i].w; }
-    }
-    if (kc >= kStages) mbar_wait(&bar_stage[s], (uint32_t)(((kc >> 1) - 1) & 1));  // MMAs of chunk kc-2 done
-    TRACE(3 + 4 * kc);
-    if (A_MN) store_mnmajor(a_hi, a_lo, va); else store_kmajor(a_hi, a_lo, va);
-    if (B_MN) store_mnmajor(b_hi, b_lo, vb); else store_kmajor(b_hi, b_lo, vb);
-    TRACE(4 + 4 * kc);
-    fence_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
-    __syncthreads();
-    TRACE(5 + 4 * kc);
-    if (t == 0) {
+
+  if (warp == 8) {
+    // ===== MMA issuer: one elected lane feeds the tensor core; completion is tracked by tcgen05.commit =====
+    const uint32_t idesc = instr_desc(n_mma, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    for (int kc = 0; kc < nk; ++kc) {
+      const int s = kc & 1, k0 = kc * TK;
+      mbar_wait(&bar_full[s], (uint32_t)((kc >> 1) & 1));
       fence_after_sync();
-      const int ksteps = min(TK / 8, (p.K - k0 + 7) / 8);
-      for (int j = 0; j < ksteps; ++j) {
+      if (lane == 0) {
+        const uint32_t st = smem_u32(smem) + (uint32_t)(s * kStageBytes);
+        const uint32_t a_hi = st, a_lo = st + kOperandBytes, b_hi = st + 2 * kOperandBytes, b_lo = st + 3 * kOperandBytes;
         // K-major (SWIZZLE_128B)        : a k-step of 8 = 32 bytes further along the swizzled 128-byte rows,
         //                                 8-row groups SBO = 1024 apart (LBO unused)
         // MN-major (SWIZZLE_128B_BASE32B): a k-step of 8 = two 4-row k-groups SBO = 2048 apart,
         //                                 32-column groups LBO = 512 apart
-        const uint32_t a_off = A_MN ? (uint32_t)j * 4096u : (uint32_t)j * 32u;
-        const uint32_t b_off = B_MN ? (uint32_t)j * 4096u : (uint32_t)j * 32u;
+        const uint32_t a_step = A_MN ? 4096u : 32u, b_step = B_MN ? 4096u : 32u;
         const uint32_t a_lbo = A_MN ? 512u : 16u, a_sbo = A_MN ? 2048u : 1024u, a_lt = A_MN ? 1u : 2u;
         const uint32_t b_lbo = B_MN ? 512u : 16u, b_sbo = B_MN ? 2048u : 1024u, b_lt = B_MN ? 1u : 2u;
-        const uint64_t dah = smem_desc(smem_u32(a_hi) + a_off, a_lbo, a_sbo, a_lt);
-        const uint64_t dal = smem_desc(smem_u32(a_lo) + a_off, a_lbo, a_sbo, a_lt);
-        const uint64_t dbh = smem_desc(smem_u32(b_hi) + b_off, b_lbo, b_sbo, b_lt);
-        const uint64_t dbl = smem_desc(smem_u32(b_lo) + b_off, b_lbo, b_sbo, b_lt);
-        mma_tf32(tmem_d, dal, dbh, idesc, (kc | j) != 0);
-        mma_tf32(tmem_d, dah, dbl, idesc, 1u);
-        mma_tf32(tmem_d, dah, dbh, idesc, 1u);
+        const int ksteps = min(TK / 8, (p.K - k0 + 7) / 8);
+        for (int j = 0; j < ksteps; ++j) {
+          const uint64_t dah = smem_desc(a_hi + j * a_step, a_lbo, a_sbo, a_lt);
+          const uint64_t dal = smem_desc(a_lo + j * a_step, a_lbo, a_sbo, a_lt);
+          const uint64_t dbh = smem_desc(b_hi + j * b_step, b_lbo, b_sbo, b_lt);
+          const uint64_t dbl = smem_desc(b_lo + j * b_step, b_lbo, b_sbo, b_lt);
+          mma_tf32(tmem_d, dal, dbh, idesc, (kc | j) != 0);
+          mma_tf32(tmem_d, dah, dbl, idesc, 1u);
+          mma_tf32(tmem_d, dah, dbh, idesc, 1u);
+        }
+        mma_commit(&bar_empty[s]);
+        if (kc == nk - 1) mma_commit(&bar_done);
       }
-      mma_commit(&bar_stage[s]);
-      if (kc == nk - 1) mma_commit(&bar_done);
+      __syncwarp();
     }
-  }
-  TRACE(40);
-  if (nk > 0) mbar_wait(&bar_done, 0);
-  fence_after_sync();
-  TRACE(41);
-
-  // ---- epilogue ---------------------------------------------------------------------------------------------
-  // phase 1: thread = accumulator row (TMEM lane 32*warp + lane) -> padded fp32 tile in shared memory (the stage
-  //          buffers are free: every MMA has completed).  phase 2: coalesced pass, a warp per output row.
-  constexpr int kTilePitch = TN + 4;   // floats; +4 keeps 16-byte stores of 8 consecutive rows on distinct banks
-  float* tile = reinterpret_cast<float*>(smem);
-  {
-    const int q = warp & 3, row = q * 32 + lane;
-    for (int c0 = (warp >> 2) * 32; c0 < n_mma; c0 += 64) {
-      float v[32];
-      if (nk > 0) {
-        tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);   // warp-collective
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0.f;
-      }
-      float* dst = tile + row * kTilePitch + c0;
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+  } else {
+    // ===== producers: global (L2) -> registers -> hi/lo split -> swizzled shared memory, one chunk ahead =====
+    const bool a_vec = ((p.lda & 3) == 0) && ((((uintptr_t)A) & 15) == 0) && (A_MN ? ((m0 & 3) == 0) : true);
+    const bool b_vec = ((p.ldb & 3) == 0) && ((((uintptr_t)Bm) & 15) == 0) && (B_MN ? ((n0 & 3) == 0) : true);
+    const bool do_colsum = (LAYOUT == L_TN) && p.colsum != nullptr && blockIdx.x == 0;
+    float cs[4] = {0.f, 0.f, 0.f, 0.f};
+    float4 va[4], vb[4];
+    if (nk > 0) {
+      if (A_MN) load_mnmajor(va, A, p.lda, m0, p.M, 0, p.K, a_vec); else load_kmajor(va, A, p.lda, m0, p.M, 0, p.K, a_vec);
+      if (B_MN) load_mnmajor(vb, Bm, p.ldb, n0, p.N, 0, p.K, b_vec); else load_kmajor(vb, Bm, p.ldb, n0, p.N, 0, p.K, b_vec);
     }
-  }
-  __syncthreads();
-  TRACE(42);
-  {
-    float* C = p.C + (int64_t)(LAYOUT == L_TN ? wg : g) * p.c_gs;
+    // epilogue operands whose latency can hide behind the main loop
     const float* bias = p.bias ? p.bias + (int64_t)wg * p.bias_gs : nullptr;
-    const float* mask = p.mask ? p.mask + (int64_t)g * p.mask_gs : nullptr;
-    const float* extra = p.extra ? p.extra + (int64_t)g * p.extra_gs : nullptr;
-    const int nc = n0 + 4 * lane;                       // this lane's first output column
-    const bool c_vec = ((p.ldc & 3) == 0) && ((((uintptr_t)C) & 15) == 0) && (nc + 3 < p.N);
-    const bool x_vec = extra && ((p.ldextra & 3) == 0) && ((((uintptr_t)extra) & 15) == 0) && (nc + 3 < p.N);
-    const bool m_vec = mask && ((p.ldmask & 3) == 0) && ((((uintptr_t)mask) & 15) == 0) && (nc + 3 < p.N);
+    const int nc = n0 + 4 * lane;                       // this lane's first output column in the coalesced pass
     float bv[4] = {0.f, 0.f, 0.f, 0.f};
     if (bias) {
 #pragma unroll
       for (int e = 0; e < 4; ++e)
         if (nc + e < p.N) bv[e] = __ldg(bias + nc + e);
     }
-    if (4 * lane < n_mma && nc < p.N) {
-#pragma unroll 4
-      for (int r = warp; r < TM; r += 8) {
-        const int m = m0 + r;
-        if (m >= p.M) break;
-        const float4 t4 = *reinterpret_cast<const float4*>(tile + r * kTilePitch + 4 * lane);
-        float x[4] = {t4.x + bv[0], t4.y + bv[1], t4.z + bv[2], t4.w + bv[3]};
-        if (p.relu) {
+    for (int kc = 0; kc < nk; ++kc) {
+      const int s = kc & 1;
+      uint8_t* st = smem + s * kStageBytes;
+      uint8_t *a_hi = st, *a_lo = st + kOperandBytes, *b_hi = st + 2 * kOperandBytes, *b_lo = st + 3 * kOperandBytes;
+      if (do_colsum) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e], 0.f);
-        }
-        if (extra) {
-          const float* ep = extra + (int64_t)m * p.ldextra + nc;
-          float ev[4] = {0.f, 0.f, 0.f, 0.f};
-          if (x_vec) { const float4 q = *reinterpret_cast<const float4*>(ep); ev[0] = q.x; ev[1] = q.y; ev[2] = q.z; ev[3] = q.w; }
-          else { for (int e = 0; e < 4; ++e) if (nc + e < p.N) ev[e] = ep[e]; }
-#pragma unroll
-          for (int e = 0; e < 4; ++e) x[e] += p.extra_scale * ev[e];
-        }
-        if (mask) {
-          const float* mp = mask + (int64_t)m * p.ldmask + nc;
-          float mv[4] = {0.f, 0.f, 0.f, 0.f};
-          if (m_vec) { const float4 q = *reinterpret_cast<const float4*>(mp); mv[0] = q.x; mv[1] = q.y; mv[2] = q.z; mv[3] = q.w; }
-          else { for (int e = 0; e < 4; ++e) if (nc + e < p.N) mv[e] = mp[e]; }
-#pragma unroll
-          for (int e = 0; e < 4; ++e) x[e] = mv[e] > 0.f ? x[e] : 0.f;
-        }
-        float* cp = C + (int64_t)m * p.ldc + nc;
-        if (c_vec) {
-          float4 o = make_float4(x[0], x[1], x[2], x[3]);
-          if (p.accumulate) { const float4 q = *reinterpret_cast<const float4*>(cp); o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w; }
-          *reinterpret_cast<float4*>(cp) = o;
+        for (int i = 0; i < 4; ++i) { cs[0] += va[i].x; cs[1] += va[i].y; cs[2] += va[i].z; cs[3] += va[i].w; }
+      }
+      if (kc >= kStages) mbar_wait(&bar_empty[s], (uint32_t)(((kc >> 1) - 1) & 1));  // MMAs of chunk kc-2 done
+      if (A_MN) store_mnmajor(a_hi, a_lo, va); else store_kmajor(a_hi, a_lo, va);
+      if (B_MN) store_mnmajor(b_hi, b_lo, vb); else store_kmajor(b_hi, b_lo, vb);
+      if (kc + 1 < nk) {   // next chunk's loads fly while the tensor core works on this one
+        const int k1 = (kc + 1) * TK;
+        if (A_MN) load_mnmajor(va, A, p.lda, m0, p.M, k1, p.K, a_vec); else load_kmajor(va, A, p.lda, m0, p.M, k1, p.K, a_vec);
+        if (B_MN) load_mnmajor(vb, Bm, p.ldb, n0, p.N, k1, p.K, b_vec); else load_kmajor(vb, Bm, p.ldb, n0, p.N, k1, p.K, b_vec);
+      }
+      fence_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
+      mbar_arrive(&bar_full[s]);
+    }
+    if (nk > 0) mbar_wait(&bar_done, 0);
+    fence_after_sync();
+
+    // ---- epilogue -----------------------------------------------------------------------------------------
+    // phase 1: thread = accumulator row (TMEM lane quarter warp%4, column half warp/4) -> padded fp32 tile in
+    //          shared memory (the stage buffers are free: every MMA has completed).
+    // phase 2: coalesced pass, a warp per output row, fused bias / ReLU / extra / mask / accumulate.
+    constexpr int kTilePitch = TN + 4;   // floats; +4 keeps 16-byte stores of 8 consecutive rows on distinct banks
+    float* tile = reinterpret_cast<float*>(smem);
+    {
+      const int q = warp & 3, row = q * 32 + lane;
+      for (int c0 = (warp >> 2) * 32; c0 < n_mma; c0 += 64) {
+        float v[32];
+        if (nk > 0) {
+          tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);   // warp-collective
         } else {
-          for (int e = 0; e < 4; ++e)
-            if (nc + e < p.N) cp[e] = p.accumulate ? (cp[e] + x[e]) : x[e];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+        float* dst = tile + row * kTilePitch + c0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+    }
+    producers_sync();
+    {
+      float* C = p.C + (int64_t)(LAYOUT == L_TN ? wg : g) * p.c_gs;
+      const float* mask = p.mask ? p.mask + (int64_t)g * p.mask_gs : nullptr;
+      const float* extra = p.extra ? p.extra + (int64_t)g * p.extra_gs : nullptr;
+      const bool full4 = nc + 3 < p.N;
+      const bool c_vec = ((p.ldc & 3) == 0) && ((((uintptr_t)C) & 15) == 0) && full4;
+      const bool x_vec = extra && ((p.ldextra & 3) == 0) && ((((uintptr_t)extra) & 15) == 0) && full4;
+      const bool m_vec = mask && ((p.ldmask & 3) == 0) && ((((uintptr_t)mask) & 15) == 0) && full4;
+      if (4 * lane < n_mma && nc < p.N) {
+        // 16 rows per warp, 4 at a time: all loads of a group are issued before the first store
+        for (int r0 = warp; r0 < TM; r0 += 32) {
+          float x[4][4], ev[4][4], mv[4][4], cv[4][4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int r = r0 + 8 * u, m = m0 + r;
+            const float4 t4 = *reinterpret_cast<const float4*>(tile + r * kTilePitch + 4 * lane);
+            x[u][0] = t4.x; x[u][1] = t4.y; x[u][2] = t4.z; x[u][3] = t4.w;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { ev[u][e] = 0.f; mv[u][e] = 1.f; cv[u][e] = 0.f; }
+            if (m < p.M) {
+              if (extra) {
+                const float* ep = extra + (int64_t)m * p.ldextra + nc;
+                if (x_vec) { const float4 q4 = *reinterpret_cast<const float4*>(ep); ev[u][0] = q4.x; ev[u][1] = q4.y; ev[u][2] = q4.z; ev[u][3] = q4.w; }
+                else { for (int e = 0; e < 4; ++e) if (nc + e < p.N) ev[u][e] = ep[e]; }
+              }
+              if (mask) {
+                const float* mp = mask + (int64_t)m * p.ldmask + nc;
+                if (m_vec) { const float4 q4 = *reinterpret_cast<const float4*>(mp); mv[u][0] = q4.x; mv[u][1] = q4.y; mv[u][2] = q4.z; mv[u][3] = q4.w; }
+                else { for (int e = 0; e < 4; ++e) if (nc + e < p.N) mv[u][e] = mp[e]; }
+              }
+              if (p.accumulate) {
+                const float* cp = C + (int64_t)m * p.ldc + nc;
+                if (c_vec) { const float4 q4 = *reinterpret_cast<const float4*>(cp); cv[u][0] = q4.x; cv[u][1] = q4.y; cv[u][2] = q4.z; cv[u][3] = q4.w; }
+                else { for (int e = 0; e < 4; ++e) if (nc + e < p.N) cv[u][e] = cp[e]; }
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int r = r0 + 8 * u, m = m0 + r;
+            if (m >= p.M) continue;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float y = x[u][e] + bv[e];
+              if (p.relu) y = fmaxf(y, 0.f);
+              y += p.extra_scale * ev[u][e];
+              y = mv[u][e] > 0.f ? y : 0.f;
+              x[u][e] = y + cv[u][e];
+            }
+            float* cp = C + (int64_t)m * p.ldc + nc;
+            if (c_vec) {
+              *reinterpret_cast<float4*>(cp) = make_float4(x[u][0], x[u][1], x[u][2], x[u][3]);
+            } else {
+              for (int e = 0; e < 4; ++e)
+                if (nc + e < p.N) cp[e] = x[u][e];
+            }
+          }
         }
       }
     }
-  }
-  if (LAYOUT == L_TN && p.colsum != nullptr && blockIdx.x == 0) {
-    // thread t summed column chunk t%32 over its k rows (k = t/32 mod 8): combine the eight warps through smem
+    if (LAYOUT == L_TN && p.colsum != nullptr && blockIdx.x == 0) {
+      // thread t summed column chunk t%32 over its k rows (k = t/32 mod 8): combine the eight warps through smem
 #pragma unroll
-    for (int e = 0; e < 4; ++e) colsum_sh[warp][4 * lane + e] = cs[e];
-    __syncthreads();
-    const int mm = m0 + t;
-    if (t < TM && mm < p.M) {
-      float tot = 0.f;
+      for (int e = 0; e < 4; ++e) colsum_sh[warp][4 * lane + e] = cs[e];
+      producers_sync();
+      const int mm = m0 + t;
+      if (t < TM && mm < p.M) {
+        float tot = 0.f;
 #pragma unroll
-      for (int w8 = 0; w8 < 8; ++w8) tot += colsum_sh[w8][t];
-      float* out = p.colsum + (int64_t)wg * p.colsum_gs;
-      out[mm] = p.accumulate ? (out[mm] + tot) : tot;
+        for (int w8 = 0; w8 < 8; ++w8) tot += colsum_sh[w8][t];
+        float* out = p.colsum + (int64_t)wg * p.colsum_gs;
+        out[mm] = p.accumulate ? (out[mm] + tot) : tot;
+      }
     }
   }
-  TRACE(43);
   fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_d, tmem_cols);
-  TRACE(44);
 }
 
 }  // namespace tc
-
-#ifdef SSAC_TRACE
-extern "C" int ssac_debug_set_trace(long long* dev_ptr) {
-  return (int)cudaMemcpyToSymbol(tc::g_trace, &dev_ptr, sizeof(dev_ptr));
-}
-#endif
 
 int launch_gemm_tc(int layout, const GemmP& p, int G, cudaStream_t s, const char* what) {
   static bool attr_set[3] = {false, false, false};
