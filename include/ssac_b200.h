@@ -110,6 +110,9 @@ int ssac_tree_sample(const double* sum_tree_dev, const double* min_tree_dev, int
  * with 3xTF32 operand splitting (fp32-accurate: hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM). */
 int ssac_default_mlp_impl(void);
 int ssac_set_default_mlp_impl(int impl);
+/* impl 2 stages operands with TMA (cp.async.bulk.tensor) when their pitch allows; 0 forces the register-staged path
+ * (kept for cross-checking the two staging paths against each other). */
+int ssac_set_tma_enabled(int on);
 int ssac_mlp_forward(const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
                      const float* b3, const int32_t* net_index_dev, int G, int D, int H, int O,
                      const float* x_dev, int64_t ldx, int64_t x_gs, int B, float* h1_dev, float* h2_dev,

@@ -1,25 +1,29 @@
 // Ensemble MLP GEMMs on the 5th-generation tensor cores (impl = 2).  sm_100a only.
 //
-// Grouped tiles of C = opA(A) * opB(B) with fp32-accurate 3xTF32 arithmetic: every fp32 operand x is split into
-// hi = tf32(x) and lo = x - hi, both staged in shared memory in canonical swizzled UMMA layouts, and each
-// 8-deep k-step issues three tcgen05.mma.kind::tf32 (lo*hi, hi*lo, hi*hi) into one fp32 accumulator tile in
-// tensor memory (TMEM).  The dropped lo*lo term is O(2^-22) relative, so results agree with an fp32 SGEMM to
-// ~1e-6 (the reference runs true-fp32 SGEMM and north_star's tolerance is rtol 1e-4).
+// Grouped tiles of C = opA(A) * opB(B) with fp32-accurate 3xTF32 arithmetic.  Every fp32 operand x is used as
+//   hi = x as the tensor core sees it (kind::tf32 ignores the low 13 mantissa bits: measured on B200)
+//   lo = x - trunc_tf32(x)   (exact in fp32)
+// and each 8-deep k-step issues three tcgen05.mma.kind::tf32 (lo*hi, hi*lo, hi*hi) into one fp32 accumulator tile
+// in tensor memory (TMEM).  The dropped lo*lo term is O(2^-20) relative (the reference runs true-fp32 SGEMM and
+// north_star's tolerance is rtol 1e-4).
 //
-// Pipeline per CTA (one 128 x 128 output tile of one net, 256 threads):
-//   all threads : global (L2) -> registers -> hi/lo split -> st.shared into stage s   (2 stages x 64 KB)
-//                 (256 threads, four 16-byte loads per operand in flight per thread)
-//   thread 0    : tcgen05.mma x (k-steps x 3) on stage s, tcgen05.commit -> mbarrier[s]  (frees the stage)
-//   all threads : after the last commit, tcgen05.ld the 128 x N accumulator (thread = row), fused epilogue
-//                 (bias, ReLU, ReLU-mask, extra gradient, accumulate), store.
-// Operand layouts follow the contiguity of the source so that a 16-byte global load is a 16-byte shared store:
-//   K-major  (source [rows][K] row-major):  addr(r,k) = (r/8)*1024 + (r%8)*128 + (((k/4) ^ (r%8)) * 16) + (k%4)*4
-//             (SWIZZLE_128B: one 128-byte row per operand row and stage, 16-byte chunks XOR-swizzled with r%8, so
-//              eight threads reading one contiguous 128-byte global row segment write eight distinct bank groups)
-//   MN-major (source [K][cols] row-major):  addr(m,k) = (k/4)*2048 + (m/32)*512 + (k%4)*128
-//                                                        + ((((m%32)/8) ^ (k%4)) * 32) + (m%8)*4
-//             (SWIZZLE_128B_BASE32B: the only layout the tensor core accepts for MN-major 32-bit operands --
-//              4 k-rows of 128 bytes per atom, 32-byte chunks XOR-swizzled with the k-row index)
+// Pipeline per CTA (one 128 x 128 output tile of one net; 10 warps, 3 stages of 64 KB):
+//   warp 9      : TMA producer -- cp.async.bulk.tensor (3-D maps: k, row, net) drops the raw fp32 operand tiles
+//                 straight into the swizzled UMMA layouts ("hi" planes), completion by mbarrier transaction bytes
+//   warps 0-7   : element-wise lo pass smem -> smem (same offsets, no layout math); operands TMA cannot address
+//                 (row pitch not a multiple of 16 bytes, e.g. the 23-wide first layer) are staged through registers
+//   warp 8      : one elected lane issues the MMAs; tcgen05.commit releases the stage / signals the epilogue
+//   warps 0-7   : epilogue -- tcgen05.ld (thread = accumulator row) -> padded smem tile -> coalesced pass with fused
+//                 bias, ReLU, ReLU-mask, extra gradient, accumulate; bias gradients (column sums) ride along
+// Operand layouts in shared memory (both what TMA writes and what the register path writes):
+//   K-major  (source [rows][K] row-major):  SWIZZLE_128B          addr(r,k) = (r/8)*1024 + (r%8)*128
+//                                                                            + (((k/4) ^ (r%8))*16) + (k%4)*4
+//   MN-major (source [K][cols] row-major):  SWIZZLE_128B_BASE32B  addr(m,k) = (m/32)*4096 + k*128
+//            (the only MN-major layout for 32-bit operands)                  + ((((m%32)/8) ^ (k%4))*32) + (m%8)*4
+#include <cuda.h>
+
+#include <vector>
+
 #include "ssac_mlp.cuh"
 
 namespace ssac {
@@ -27,16 +31,23 @@ namespace tc {
 
 constexpr int TM = 128;      // MMA M (one CTA, cta_group::1)
 constexpr int TN = 128;      // tile N (MMA N = 16..128, multiple of 16)
-constexpr int TK = 32;       // k per pipeline stage (4 MMA k-steps of 8)
-constexpr int kStages = 2;
-constexpr int kProducerThreads = 256;  // warps 0-7 stage operands and run the epilogue (warps w, w+4 share TMEM lane quarter w%4)
-constexpr int kThreads = kProducerThreads + 32;  // + warp 8: the MMA issuer
-constexpr int kOperandBytes = TM * TK * 4;            // one hi or lo plane of one operand: 16 KB
-constexpr int kStageBytes = 4 * kOperandBytes;        // A_hi, A_lo, B_hi, B_lo
-constexpr int kSmemBytes = kStages * kStageBytes;     // 128 KB
+constexpr int TK = 32;       // k per pipeline stage (4 MMA k-steps of 8) = one 128-byte swizzle row
+constexpr int kStages = 3;
+constexpr int kWorkerThreads = 256;               // warps 0-7
+constexpr int kThreads = kWorkerThreads + 64;     // + warp 8 (MMA issuer) + warp 9 (TMA producer)
+constexpr int kPlaneBytes = TM * TK * 4;          // one hi or lo plane of one operand: 16 KB
+constexpr int kStageBytes = 4 * kPlaneBytes;      // A_hi, A_lo, B_hi, B_lo
+constexpr int kSmemBytes = kStages * kStageBytes + 1024;   // + slack for 1024-byte alignment of the swizzle atoms
+
+struct GemmTC {
+  GemmP p;
+  CUtensorMap tmA, tmB;   // valid when a_tma / b_tma
+  int a_tma, b_tma;
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// ---- mbarrier ----------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -60,12 +71,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (++spins > 50000000u) __trap();
   }
 }
-
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void producers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kProducerThreads) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void workers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kWorkerThreads) : "memory"); }
 
+// ---- TMA ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+// ---- tensor memory / tcgen05 -------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
                : "memory");
@@ -113,7 +135,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// shared-memory matrix descriptor, version 1 (Blackwell).  layout_type: 0 = none, 1 = SWIZZLE_128B_BASE32B, 2 = SWIZZLE_128B
+// shared-memory matrix descriptor, version 1 (Blackwell).  layout_type: 1 = SWIZZLE_128B_BASE32B, 2 = SWIZZLE_128B
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | ((uint64_t)layout_type << 61);
@@ -124,36 +146,11 @@ __device__ __forceinline__ uint32_t instr_desc(int n, int a_mn_major, int b_mn_m
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 }
 
-__device__ __forceinline__ float tf32_hi(float x) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
-}
-#ifdef SSAC_TRUNC_SPLIT
-// experiment: the "hi" plane is the raw fp32 value (the tensor core ignores the low 13 mantissa bits of a tf32
-// operand), lo = x - trunc_tf32(x)
-__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
-__device__ __forceinline__ void split_store(uint8_t* hi_plane, uint8_t* lo_plane, uint32_t off, float4 v) {
-  float4 l;
-  l.x = v.x - tf32_trunc(v.x); l.y = v.y - tf32_trunc(v.y); l.z = v.z - tf32_trunc(v.z); l.w = v.w - tf32_trunc(v.w);
-  *reinterpret_cast<float4*>(hi_plane + off) = v;
-  *reinterpret_cast<float4*>(lo_plane + off) = l;
-}
-#else
-__device__ __forceinline__ void split_store(uint8_t* hi_plane, uint8_t* lo_plane, uint32_t off, float4 v) {
-  float4 h, l;
-  h.x = tf32_hi(v.x); h.y = tf32_hi(v.y); h.z = tf32_hi(v.z); h.w = tf32_hi(v.w);
-  l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-  *reinterpret_cast<float4*>(hi_plane + off) = h;
-  *reinterpret_cast<float4*>(lo_plane + off) = l;
-}
-#endif
+__device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+__device__ __forceinline__ float4 lo4(float4 v) { return make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w)); }
 
-// ---- operand staging -------------------------------------------------------------------------------------------
-// K-contiguous source [rows][K] (row-major, ld) -> K-major planes (SWIZZLE_128B).  Thread t owns the 4-k chunk
-// c = t%8 of rows r = t/8 + 32i: a quarter-warp reads one contiguous 128-byte row segment and writes the eight
-// swizzled 16-byte slots of one 128-byte shared row (coalesced and bank-conflict free).  All loads are issued
-// before the first store so that four 16-byte requests per thread are in flight.
+// ---- register staging for operands TMA cannot address ------------------------------------------------------------
+// K-contiguous source [rows][K] -> K-major planes.  Thread t owns the 4-k chunk c = t%8 of rows r = t/8 + 32i.
 __device__ __forceinline__ void load_kmajor(float4 (&v)[4], const float* __restrict__ src, int64_t ld, int row0,
                                             int nrows, int k0, int K, bool vec_ok) {
   const int t = threadIdx.x, c = t & 7;
@@ -181,13 +178,12 @@ __device__ __forceinline__ void store_kmajor(uint8_t* hi, uint8_t* lo, const flo
   for (int i = 0; i < 4; ++i) {
     const int r = (t >> 3) + 32 * i;
     const uint32_t r7 = (uint32_t)(r & 7);
-    split_store(hi, lo, (uint32_t)(r >> 3) * 1024u + r7 * 128u + (((uint32_t)c ^ r7) << 4), v[i]);
+    const uint32_t off = (uint32_t)(r >> 3) * 1024u + r7 * 128u + (((uint32_t)c ^ r7) << 4);
+    *reinterpret_cast<float4*>(hi + off) = v[i];
+    *reinterpret_cast<float4*>(lo + off) = lo4(v[i]);
   }
 }
-
-// MN-contiguous source [K][cols] (row-major, ld) -> MN-major planes (SWIZZLE_128B_BASE32B).  Thread t owns the
-// 4-column chunk mc = t%32 of rows k = t/32 + 8i: a quarter-warp reads 128 contiguous global bytes and writes one
-// 128-byte shared row.
+// MN-contiguous source [K][cols] -> MN-major planes.  Thread t owns the 4-column chunk mc = t%32 of rows k = t/32 + 8i.
 __device__ __forceinline__ void load_mnmajor(float4 (&v)[4], const float* __restrict__ src, int64_t ld, int col0,
                                              int ncols, int k0, int K, bool vec_ok) {
   const int t = threadIdx.x, mc = t & 31, c = col0 + 4 * mc;
@@ -210,33 +206,40 @@ __device__ __forceinline__ void load_mnmajor(float4 (&v)[4], const float* __rest
 }
 __device__ __forceinline__ void store_mnmajor(uint8_t* hi, uint8_t* lo, const float4 (&v)[4]) {
   const int t = threadIdx.x, mc = t & 31;
-  const uint32_t mn_off = (uint32_t)(mc >> 3) * 512u + (uint32_t)(mc & 1) * 16u;
+  const uint32_t mn_off = (uint32_t)(mc >> 3) * 4096u + (uint32_t)(mc & 1) * 16u;
   const uint32_t chunk32 = (uint32_t)((mc & 7) >> 1);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int kl = (t >> 5) + 8 * i;  // 0..31 inside the stage
-    const uint32_t kr = (uint32_t)(kl & 3);
-    split_store(hi, lo, (uint32_t)(kl >> 2) * 2048u + mn_off + kr * 128u + ((chunk32 ^ kr) << 5), v[i]);
+    const uint32_t kl = (uint32_t)((t >> 5) + 8 * i);  // 0..31 inside the stage
+    const uint32_t off = mn_off + kl * 128u + ((chunk32 ^ (kl & 3u)) << 5);
+    *reinterpret_cast<float4*>(hi + off) = v[i];
+    *reinterpret_cast<float4*>(lo + off) = lo4(v[i]);
   }
 }
 
 template <int LAYOUT>
-__global__ void __launch_bounds__(kThreads, 1) grouped_gemm_tc_kernel(GemmP p) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar_full[kStages];    // producers -> MMA warp: stage s holds chunk kc
+__global__ void __launch_bounds__(kThreads, 1) grouped_gemm_tc_kernel(const __grid_constant__ GemmTC q) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_raw[kStages];     // TMA -> workers: the raw tiles of stage s have landed
+  __shared__ __align__(8) uint64_t bar_full[kStages];    // workers -> MMA warp: lo planes written, stage s complete
   __shared__ __align__(8) uint64_t bar_empty[kStages];   // tensor core -> producers: the MMAs reading stage s are done
   __shared__ __align__(8) uint64_t bar_done;
   __shared__ uint32_t tmem_base_sh;
-  __shared__ float colsum_sh[8][TM];
+  __shared__ float colsum_sh[TM];
 
+  const GemmP& p = q.p;
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle atoms need 1024-byte alignment
   constexpr bool A_MN = (LAYOUT == L_TN);   // A given as [K][M]
   constexpr bool B_MN = (LAYOUT != L_NT);   // B given as [K][N] for NN / TN
   const int g = blockIdx.z;
   const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
   const int wg = p.b_index ? p.b_index[g] : g;
+  const int bz = (LAYOUT == L_TN) ? g : wg;   // group index of the B operand
   const float* A = p.A + (int64_t)g * p.a_gs;
-  const float* Bm = p.Bm + (int64_t)(LAYOUT == L_TN ? g : wg) * p.b_gs;
+  const float* Bm = p.Bm + (int64_t)bz * p.b_gs;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const bool a_tma = q.a_tma != 0, b_tma = q.b_tma != 0, any_tma = a_tma || b_tma;
+  const int az_tma = p.a_gs ? g : 0, bz_tma = p.b_gs ? bz : 0;   // a shared operand has a single-group tensor map
 
   const int n_valid = min(TN, p.N - n0);
   const int n_mma = (n_valid + 15) & ~15;                 // MMA N: multiple of 16, 16..128
@@ -246,35 +249,64 @@ __global__ void __launch_bounds__(kThreads, 1) grouped_gemm_tc_kernel(GemmP p) {
   if (warp == 0) tmem_alloc(&tmem_base_sh, tmem_cols);
   if (t == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&bar_full[s], kProducerThreads);
+      mbar_init(&bar_raw[s], 1);
+      mbar_init(&bar_full[s], kWorkerThreads);
       mbar_init(&bar_empty[s], 1);
     }
     mbar_init(&bar_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (t < TM) colsum_sh[t] = 0.f;
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_d = tmem_base_sh;
   const int nk = (p.K + TK - 1) / TK;
 
-  if (warp == 8) {
-    // ===== MMA issuer: one elected lane feeds the tensor core; completion is tracked by tcgen05.commit =====
+  if (warp == 9) {
+    // ===== TMA producer ===========================================================================================
+    if (any_tma && lane == 0) {
+      const uint32_t bytes = (a_tma ? kPlaneBytes : 0) + (b_tma ? kPlaneBytes : 0);
+      for (int kc = 0; kc < nk; ++kc) {
+        const int s = kc % kStages, use = kc / kStages, k0 = kc * TK;
+        if (kc >= kStages) mbar_wait(&bar_empty[s], (uint32_t)((use - 1) & 1));   // stage free again
+        mbar_arrive_expect_tx(&bar_raw[s], bytes);
+        const uint32_t st = smem_u32(smem) + (uint32_t)(s * kStageBytes);
+        if (a_tma) {
+          if (A_MN) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) tma_load_3d(st + j * 4096, &q.tmA, &bar_raw[s], m0 + 32 * j, k0, az_tma);
+          } else {
+            tma_load_3d(st, &q.tmA, &bar_raw[s], k0, m0, az_tma);
+          }
+        }
+        if (b_tma) {
+          if (B_MN) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) tma_load_3d(st + 2 * kPlaneBytes + j * 4096, &q.tmB, &bar_raw[s], n0 + 32 * j, k0, bz_tma);
+          } else {
+            tma_load_3d(st + 2 * kPlaneBytes, &q.tmB, &bar_raw[s], k0, n0, bz_tma);
+          }
+        }
+      }
+    }
+  } else if (warp == 8) {
+    // ===== MMA issuer: one elected lane feeds the tensor core; completion is tracked by tcgen05.commit ===========
     const uint32_t idesc = instr_desc(n_mma, A_MN ? 1 : 0, B_MN ? 1 : 0);
     for (int kc = 0; kc < nk; ++kc) {
-      const int s = kc & 1, k0 = kc * TK;
-      mbar_wait(&bar_full[s], (uint32_t)((kc >> 1) & 1));
+      const int s = kc % kStages, use = kc / kStages, k0 = kc * TK;
+      mbar_wait(&bar_full[s], (uint32_t)(use & 1));
       fence_after_sync();
       if (lane == 0) {
         const uint32_t st = smem_u32(smem) + (uint32_t)(s * kStageBytes);
-        const uint32_t a_hi = st, a_lo = st + kOperandBytes, b_hi = st + 2 * kOperandBytes, b_lo = st + 3 * kOperandBytes;
+        const uint32_t a_hi = st, a_lo = st + kPlaneBytes, b_hi = st + 2 * kPlaneBytes, b_lo = st + 3 * kPlaneBytes;
         // K-major (SWIZZLE_128B)        : a k-step of 8 = 32 bytes further along the swizzled 128-byte rows,
         //                                 8-row groups SBO = 1024 apart (LBO unused)
-        // MN-major (SWIZZLE_128B_BASE32B): a k-step of 8 = two 4-row k-groups SBO = 2048 apart,
-        //                                 32-column groups LBO = 512 apart
-        const uint32_t a_step = A_MN ? 4096u : 32u, b_step = B_MN ? 4096u : 32u;
-        const uint32_t a_lbo = A_MN ? 512u : 16u, a_sbo = A_MN ? 2048u : 1024u, a_lt = A_MN ? 1u : 2u;
-        const uint32_t b_lbo = B_MN ? 512u : 16u, b_sbo = B_MN ? 2048u : 1024u, b_lt = B_MN ? 1u : 2u;
+        // MN-major (SWIZZLE_128B_BASE32B): a k-step of 8 = two 4-row k-groups SBO = 512 apart (1024 bytes per step),
+        //                                 32-column groups LBO = 4096 apart
+        const uint32_t a_step = A_MN ? 1024u : 32u, b_step = B_MN ? 1024u : 32u;
+        const uint32_t a_lbo = A_MN ? 4096u : 16u, a_sbo = A_MN ? 512u : 1024u, a_lt = A_MN ? 1u : 2u;
+        const uint32_t b_lbo = B_MN ? 4096u : 16u, b_sbo = B_MN ? 512u : 1024u, b_lt = B_MN ? 1u : 2u;
         const int ksteps = min(TK / 8, (p.K - k0 + 7) / 8);
         for (int j = 0; j < ksteps; ++j) {
           const uint64_t dah = smem_desc(a_hi + j * a_step, a_lbo, a_sbo, a_lt);
@@ -291,15 +323,17 @@ __global__ void __launch_bounds__(kThreads, 1) grouped_gemm_tc_kernel(GemmP p) {
       __syncwarp();
     }
   } else {
-    // ===== producers: global (L2) -> registers -> hi/lo split -> swizzled shared memory, one chunk ahead =====
+    // ===== workers ================================================================================================
     const bool a_vec = ((p.lda & 3) == 0) && ((((uintptr_t)A) & 15) == 0) && (A_MN ? ((m0 & 3) == 0) : true);
     const bool b_vec = ((p.ldb & 3) == 0) && ((((uintptr_t)Bm) & 15) == 0) && (B_MN ? ((n0 & 3) == 0) : true);
     const bool do_colsum = (LAYOUT == L_TN) && p.colsum != nullptr && blockIdx.x == 0;
-    float cs[4] = {0.f, 0.f, 0.f, 0.f};
+    float cs[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) cs[e] = 0.f;
     float4 va[4], vb[4];
     if (nk > 0) {
-      if (A_MN) load_mnmajor(va, A, p.lda, m0, p.M, 0, p.K, a_vec); else load_kmajor(va, A, p.lda, m0, p.M, 0, p.K, a_vec);
-      if (B_MN) load_mnmajor(vb, Bm, p.ldb, n0, p.N, 0, p.K, b_vec); else load_kmajor(vb, Bm, p.ldb, n0, p.N, 0, p.K, b_vec);
+      if (!a_tma) { if (A_MN) load_mnmajor(va, A, p.lda, m0, p.M, 0, p.K, a_vec); else load_kmajor(va, A, p.lda, m0, p.M, 0, p.K, a_vec); }
+      if (!b_tma) { if (B_MN) load_mnmajor(vb, Bm, p.ldb, n0, p.N, 0, p.K, b_vec); else load_kmajor(vb, Bm, p.ldb, n0, p.N, 0, p.K, b_vec); }
     }
     // epilogue operands whose latency can hide behind the main loop
     const float* bias = p.bias ? p.bias + (int64_t)wg * p.bias_gs : nullptr;
@@ -311,20 +345,40 @@ __global__ void __launch_bounds__(kThreads, 1) grouped_gemm_tc_kernel(GemmP p) {
         if (nc + e < p.N) bv[e] = __ldg(bias + nc + e);
     }
     for (int kc = 0; kc < nk; ++kc) {
-      const int s = kc & 1;
+      const int s = kc % kStages, use = kc / kStages;
       uint8_t* st = smem + s * kStageBytes;
-      uint8_t *a_hi = st, *a_lo = st + kOperandBytes, *b_hi = st + 2 * kOperandBytes, *b_lo = st + 3 * kOperandBytes;
-      if (do_colsum) {
+      uint8_t *a_hi = st, *a_lo = st + kPlaneBytes, *b_hi = st + 2 * kPlaneBytes, *b_lo = st + 3 * kPlaneBytes;
+      if (any_tma) mbar_wait(&bar_raw[s], (uint32_t)(use & 1));                   // raw tiles landed (=> stage was free)
+      else if (kc >= kStages) mbar_wait(&bar_empty[s], (uint32_t)((use - 1) & 1));  // no TMA operand: wait for the MMAs
+      if (a_tma) {
+        // lo pass: same (swizzled) offsets in and out, 4 x 16 bytes per thread
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { cs[0] += va[i].x; cs[1] += va[i].y; cs[2] += va[i].z; cs[3] += va[i].w; }
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t off = (uint32_t)(t + kWorkerThreads * i) * 16u;
+          const float4 v = *reinterpret_cast<const float4*>(a_hi + off);
+          *reinterpret_cast<float4*>(a_lo + off) = lo4(v);
+          if (do_colsum) { cs[4 * i + 0] += v.x; cs[4 * i + 1] += v.y; cs[4 * i + 2] += v.z; cs[4 * i + 3] += v.w; }
+        }
+      } else {
+        if (do_colsum) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { cs[0] += va[i].x; cs[1] += va[i].y; cs[2] += va[i].z; cs[3] += va[i].w; }
+        }
+        if (A_MN) store_mnmajor(a_hi, a_lo, va); else store_kmajor(a_hi, a_lo, va);
       }
-      if (kc >= kStages) mbar_wait(&bar_empty[s], (uint32_t)(((kc >> 1) - 1) & 1));  // MMAs of chunk kc-2 done
-      if (A_MN) store_mnmajor(a_hi, a_lo, va); else store_kmajor(a_hi, a_lo, va);
-      if (B_MN) store_mnmajor(b_hi, b_lo, vb); else store_kmajor(b_hi, b_lo, vb);
-      if (kc + 1 < nk) {   // next chunk's loads fly while the tensor core works on this one
+      if (b_tma) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t off = (uint32_t)(t + kWorkerThreads * i) * 16u;
+          *reinterpret_cast<float4*>(b_lo + off) = lo4(*reinterpret_cast<const float4*>(b_hi + off));
+        }
+      } else {
+        if (B_MN) store_mnmajor(b_hi, b_lo, vb); else store_kmajor(b_hi, b_lo, vb);
+      }
+      if (kc + 1 < nk) {   // register-staged operands: next chunk's loads fly while the tensor core works
         const int k1 = (kc + 1) * TK;
-        if (A_MN) load_mnmajor(va, A, p.lda, m0, p.M, k1, p.K, a_vec); else load_kmajor(va, A, p.lda, m0, p.M, k1, p.K, a_vec);
-        if (B_MN) load_mnmajor(vb, Bm, p.ldb, n0, p.N, k1, p.K, b_vec); else load_kmajor(vb, Bm, p.ldb, n0, p.N, k1, p.K, b_vec);
+        if (!a_tma) { if (A_MN) load_mnmajor(va, A, p.lda, m0, p.M, k1, p.K, a_vec); else load_kmajor(va, A, p.lda, m0, p.M, k1, p.K, a_vec); }
+        if (!b_tma) { if (B_MN) load_mnmajor(vb, Bm, p.ldb, n0, p.N, k1, p.K, b_vec); else load_kmajor(vb, Bm, p.ldb, n0, p.N, k1, p.K, b_vec); }
       }
       fence_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
       mbar_arrive(&bar_full[s]);
@@ -339,11 +393,11 @@ __global__ void __launch_bounds__(kThreads, 1) grouped_gemm_tc_kernel(GemmP p) {
     constexpr int kTilePitch = TN + 4;   // floats; +4 keeps 16-byte stores of 8 consecutive rows on distinct banks
     float* tile = reinterpret_cast<float*>(smem);
     {
-      const int q = warp & 3, row = q * 32 + lane;
+      const int qd = warp & 3, row = qd * 32 + lane;
       for (int c0 = (warp >> 2) * 32; c0 < n_mma; c0 += 64) {
         float v[32];
         if (nk > 0) {
-          tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);   // warp-collective
+          tmem_ld32(tmem_d + ((uint32_t)(qd * 32) << 16) + (uint32_t)c0, v);   // warp-collective
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = 0.f;
@@ -353,7 +407,24 @@ __global__ void __launch_bounds__(kThreads, 1) grouped_gemm_tc_kernel(GemmP p) {
         for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
       }
     }
-    producers_sync();
+    if (do_colsum) {
+      // fold this thread's partial column sums into shared memory (shared atomics, once per kernel)
+      if (a_tma) {
+        // chunk i of thread t sits at byte offset 16*(t + 256 i): m-group i, k row t/8, physical 32-byte chunk (t%8)/2
+        const int kr = (t >> 3) & 3;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int mbase = 32 * i + ((((t & 7) >> 1) ^ kr) << 3) + ((t & 1) << 2);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) atomicAdd(&colsum_sh[mbase + e], cs[4 * i + e]);
+        }
+      } else {
+        const int mbase = 4 * (t & 31);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) atomicAdd(&colsum_sh[mbase + e], cs[e]);
+      }
+    }
+    workers_sync();
     {
       float* C = p.C + (int64_t)(LAYOUT == L_TN ? wg : g) * p.c_gs;
       const float* mask = p.mask ? p.mask + (int64_t)g * p.mask_gs : nullptr;
@@ -414,18 +485,11 @@ __global__ void __launch_bounds__(kThreads, 1) grouped_gemm_tc_kernel(GemmP p) {
         }
       }
     }
-    if (LAYOUT == L_TN && p.colsum != nullptr && blockIdx.x == 0) {
-      // thread t summed column chunk t%32 over its k rows (k = t/32 mod 8): combine the eight warps through smem
-#pragma unroll
-      for (int e = 0; e < 4; ++e) colsum_sh[warp][4 * lane + e] = cs[e];
-      producers_sync();
+    if (do_colsum) {
       const int mm = m0 + t;
       if (t < TM && mm < p.M) {
-        float tot = 0.f;
-#pragma unroll
-        for (int w8 = 0; w8 < 8; ++w8) tot += colsum_sh[w8][t];
         float* out = p.colsum + (int64_t)wg * p.colsum_gs;
-        out[mm] = p.accumulate ? (out[mm] + tot) : tot;
+        out[mm] = p.accumulate ? (out[mm] + colsum_sh[t]) : colsum_sh[t];
       }
     }
   }
@@ -435,6 +499,71 @@ __global__ void __launch_bounds__(kThreads, 1) grouped_gemm_tc_kernel(GemmP p) {
 }
 
 }  // namespace tc
+
+// ---- host: tensor maps ---------------------------------------------------------------------------------------------
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+struct MapKey {
+  const void* base; int64_t ld, gs; int inner, outer; bool mn;
+  bool operator==(const MapKey& o) const {
+    return base == o.base && ld == o.ld && gs == o.gs && inner == o.inner && outer == o.outer && mn == o.mn;
+  }
+};
+struct MapEntry { MapKey key; CUtensorMap map; };
+std::vector<MapEntry>& map_cache() {
+  static thread_local std::vector<MapEntry> cache;
+  return cache;
+}
+
+// 3-D map (inner, outer, group) over a row-major fp32 matrix stack.  K-major operands: inner = k, outer = rows,
+// box 32 x 128, SWIZZLE_128B.  MN-major operands: inner = cols, outer = k, box 32 x 32, SWIZZLE_128B_ATOM_32B.
+bool make_map(const float* base, int64_t ld, int64_t gs, int inner, int outer, bool mn, CUtensorMap* out) {
+  if (!encode_fn()) return false;
+  if ((((uintptr_t)base) & 15) != 0 || (ld & 3) != 0 || ld <= 0 || (gs & 3) != 0 || inner <= 0 || outer <= 0) return false;
+  MapKey key{base, ld, gs, inner, outer, mn};
+  auto& cache = map_cache();
+  for (auto& e : cache)
+    if (e.key == key) { *out = e.map; return true; }
+  const cuuint64_t ngroups = gs > 0 ? 65536 : 1;
+  cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)outer, ngroups};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)(gs > 0 ? gs : (int64_t)outer * ld) * 4};
+  cuuint32_t box[3] = {32, (cuuint32_t)(mn ? 32 : 128), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = encode_fn()(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           mn ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return false;
+  if (cache.size() >= 256) cache.clear();
+  cache.push_back(MapEntry{key, *out});
+  return true;
+}
+
+}  // namespace
+
+static bool g_tma_enabled = true;
+extern "C" int ssac_set_tma_enabled(int on) {
+  g_tma_enabled = on != 0;
+  return 0;
+}
 
 int launch_gemm_tc(int layout, const GemmP& p, int G, cudaStream_t s, const char* what) {
   static bool attr_set[3] = {false, false, false};
@@ -449,10 +578,21 @@ int launch_gemm_tc(int layout, const GemmP& p, int G, cudaStream_t s, const char
     }
     attr_set[layout] = true;
   }
+  tc::GemmTC q;
+  q.p = p;
+  q.a_tma = q.b_tma = 0;
+  if (g_tma_enabled && p.K > 0) {
+    const bool a_mn = layout == L_TN, b_mn = layout != L_NT;
+    // group strides are baked into the maps; base pointers are the group-0 matrices
+    if (a_mn) q.a_tma = make_map(p.A, p.lda, p.a_gs, p.M, p.K, true, &q.tmA);
+    else q.a_tma = make_map(p.A, p.lda, p.a_gs, p.K, p.M, false, &q.tmA);
+    if (b_mn) q.b_tma = make_map(p.Bm, p.ldb, p.b_gs, p.N, p.K, true, &q.tmB);
+    else q.b_tma = make_map(p.Bm, p.ldb, p.b_gs, p.K, p.N, false, &q.tmB);
+  }
   dim3 grid((p.N + tc::TN - 1) / tc::TN, (p.M + tc::TM - 1) / tc::TM, G);
-  if (layout == L_NT) tc::grouped_gemm_tc_kernel<L_NT><<<grid, tc::kThreads, tc::kSmemBytes, s>>>(p);
-  else if (layout == L_NN) tc::grouped_gemm_tc_kernel<L_NN><<<grid, tc::kThreads, tc::kSmemBytes, s>>>(p);
-  else tc::grouped_gemm_tc_kernel<L_TN><<<grid, tc::kThreads, tc::kSmemBytes, s>>>(p);
+  if (layout == L_NT) tc::grouped_gemm_tc_kernel<L_NT><<<grid, tc::kThreads, tc::kSmemBytes, s>>>(q);
+  else if (layout == L_NN) tc::grouped_gemm_tc_kernel<L_NN><<<grid, tc::kThreads, tc::kSmemBytes, s>>>(q);
+  else tc::grouped_gemm_tc_kernel<L_TN><<<grid, tc::kThreads, tc::kSmemBytes, s>>>(q);
   SSAC_CHECK_LAUNCH(what);
   return 0;
 }

@@ -172,7 +172,7 @@ class ReplayBuffer:
             priorities = self._max_priority
         vals = np.broadcast_to(np.asarray(priorities, dtype=np.float64) ** self.alpha, R.shape)
         self._tree_set(torch.from_numpy(R.astype(np.int64)).to(self.device),
-                       torch.from_numpy(np.ascontiguousarray(vals)).to(self.device))
+                       torch.from_numpy(np.array(vals, dtype=np.float64, copy=True)).to(self.device))
         return R
 
     def load_experience(self, s, a, r, s1, d):

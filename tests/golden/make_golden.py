@@ -382,8 +382,68 @@ def run_aug_case():
     print(f"wrote {path}  ({os.path.getsize(path)/1024:.1f} KiB)")
 
 
+def run_afbc_case():
+    """Offline AFBC actor update with prioritised sampling and priority refresh (learning.py:144-219,
+    learning_utils.py:241-295, adv_estimator.py:58-79, replay.py:163-190) -- BASELINE config 5's actor side."""
+    rng = np.random.default_rng(31)
+    torch.manual_seed(31)
+    E, N, S, A, H, B, nbuf = 2, 2, 5, 2, 32, 16, 48
+    agent = ssac.Agent(act_space_size=A, encoder=IdentityEncoder(S), actor_network_cls=rnets.mlps.ContinuousStochasticActor,
+                       critic_network_cls=rnets.mlps.ContinuousCritic, ensemble_size=E, num_critics=N, hidden_size=H,
+                       auto_rescale_targets=True, log_std_low=-5.0, log_std_high=2.0)
+    for m in critic_nets(agent) + list(agent.actors):
+        for p_ in m.parameters():
+            if p_.dim() == 1:
+                p_.data.add_(0.05 * torch.randn_like(p_))
+    for pa in agent.popart:
+        pa.w = torch.tensor([0.8]); pa.b = torch.tensor([-0.2])
+    s = rng.standard_normal((nbuf, S)).astype(np.float32)
+    a = rng.uniform(-1, 1, (nbuf, A)).astype(np.float32)
+    a[::7] = np.sign(a[::7])  # some actions exactly at +-1: exercises the clamp(+-0.99) of the atanh cache miss
+    r = rng.standard_normal(nbuf).astype(np.float32)
+    s1 = rng.standard_normal((nbuf, S)).astype(np.float32)
+    d = (rng.uniform(size=nbuf) < 0.1)
+    pri = rng.uniform(0.05, 2.0, nbuf)
+    buf = rreplay.ReplayBuffer(size=64, alpha=0.6, beta=1.0)
+    buf.push({"obs": s}, a, r[:, None], {"obs": s1}, d[:, None], priorities=pri)
+    out = {"cfg": np.array(repr(dict(E=E, N=N, S=S, A=A, H=H, B=B, nbuf=nbuf, popart=True)))}
+    put(out, "buffer", dict(s=s, a=a, r=r, s1=s1, d=d, priorities=pri))
+    put(out, "init/actors", stack_of(agent.actors))
+    put(out, "init/critics", stack_of(critic_nets(agent)))
+    put(out, "init/popart", popart_state(agent))
+    actor_opt = torch.optim.Adam(chain(*(ac.parameters() for ac in agent.actors)), lr=3e-4, betas=(0.9, 0.999))
+    enc_opt = torch.optim.Adam(agent.encoder.parameters(), lr=1e-4)
+    augmenter = raug.AugmentationSequence([raug.IdentityAug(B)])
+    for t in range(2):
+        u = rng.uniform(size=(E, B))
+        adv_eps = rng.standard_normal((E, 4, B, A)).astype(np.float32)
+        prio_member = int(rng.integers(0, E))
+        prio_eps = rng.standard_normal((4, B, A)).astype(np.float32)
+        put(out, f"step{t}/rand", dict(u=u, adv_eps=adv_eps, prio_member=prio_member, prio_eps=prio_eps))
+        normal_q = [e for i in range(E) for e in adv_eps[i]] + list(prio_eps)
+        o_choice = rh._py_random.choice
+        rh._py_random.choice = lambda seq: (list(seq)[prio_member] if isinstance(seq, range) else o_choice(seq))
+        try:
+            with rh.injected(np_random=list(u), normal_eps=normal_q) as q:
+                logs = learning.offline_actor_update(
+                    buffer=buf, agent=agent, actor_optimizer=actor_opt, encoder_optimizer=enc_opt, batch_size=B,
+                    actor_clip=40.0, update_encoder=False, encoder_clip=40.0, augmenter=augmenter, actor_lambda=0.0,
+                    aug_mix=0.0, premade_replay_dicts=None, per=True, discrete=False, filter_=True)
+                assert not q["normal_eps"].items and not q["np_random"].items
+        finally:
+            rh._py_random.choice = o_choice
+        put(out, f"step{t}/actor_grads", grads_of(agent.actors))
+        put(out, f"step{t}/actors", stack_of(agent.actors))
+        put(out, f"step{t}/logs", {k.replace("/", "|"): float(v) for k, v in logs.items()})
+        put(out, f"step{t}/trees", dict(sum_tree=buf._it_sum._value, min_tree=buf._it_min._value, max_priority=buf._max_priority))
+    path = os.path.join(HERE, "afbc.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}  ({os.path.getsize(path)/1024:.1f} KiB)")
+
+
 if __name__ == "__main__":
     for name, cfg in UPDATE_CASES.items():
         run_update_case(name, cfg)
     run_replay_case()
     run_aug_case()
+    run_afbc_case()

@@ -279,10 +279,21 @@ def _arena_from(stack):
     return ar
 
 
-@pytest.mark.parametrize("impl", [1, 2], ids=["ffma", "tcgen05"])
+@pytest.fixture
+def tma(request):
+    """impl 2 has two operand-staging paths (TMA and registers); run both."""
+    L().set_tma_enabled(int(getattr(request, "param", 1)))
+    yield
+    L().set_tma_enabled(1)
+
+
+IMPLS = [pytest.param(1, 1, id="ffma"), pytest.param(2, 1, id="tcgen05-tma"), pytest.param(2, 0, id="tcgen05-regs")]
+
+
+@pytest.mark.parametrize("impl,tma", IMPLS, indirect=["tma"])
 @pytest.mark.parametrize("G,D,H,O,B", [(10, 23, 256, 1, 256), (3, 5, 33, 3, 17), (2, 67, 1024, 1, 512), (1, 17, 256, 12, 256),
-                                       (2, 40, 200, 40, 130)])
-def test_mlp_forward_backward_matches_oracle(G, D, H, O, B, impl):
+                                       (2, 40, 200, 40, 130), (3, 24, 64, 48, 300)])
+def test_mlp_forward_backward_matches_oracle(G, D, H, O, B, impl, tma):
     from super_sac_b200 import _ops
 
     gen = torch.Generator().manual_seed(G * 1000 + H)
@@ -332,19 +343,19 @@ def test_mlp_forward_backward_matches_oracle(G, D, H, O, B, impl):
         gu.assert_close(dx2[g].cpu().numpy(), want.numpy(), 1e-4, 1e-5 * float(want.abs().max()), f"dx-only[{g}]")
 
 
-@pytest.mark.parametrize("impl", [1, 2], ids=["ffma", "tcgen05"])
-def test_mlp_subset_and_per_group_inputs(impl):
+@pytest.mark.parametrize("impl,tma", IMPLS, indirect=["tma"])
+def test_mlp_subset_and_per_group_inputs(impl, tma):
     from super_sac_b200 import _ops
 
     gen = torch.Generator().manual_seed(9)
-    G, D, H, O, B = 6, 23, 64, 1, 40
+    G, D, H, O, B = 6, 24, 64, 1, 40
     st = uo.MLPStack(G, D, H, O).random_init(gen)
     ar = _arena_from(st)
     # REDQ subset: groups {4, 1} of member starting at net 1, inputs embedded in a wider matrix (ldx > D)
-    xw = torch.randn(B, D + 7, generator=gen)
+    xw = torch.randn(B, D + 8, generator=gen)
     sub = torch.tensor([4, 1], dtype=torch.int32)
     h1 = torch.empty((2, B, H), device=DEV); h2 = torch.empty_like(h1); y = torch.empty((2, B, O), device=DEV)
-    _ops.mlp_forward(ar, 1, 2, xw.to(DEV), B, h1, h2, y, ldx=D + 7, net_index=sub.to(DEV), impl=impl)
+    _ops.mlp_forward(ar, 1, 2, xw.to(DEV), B, h1, h2, y, ldx=D + 8, net_index=sub.to(DEV), impl=impl)
     for j, k in enumerate(sub.tolist()):
         gu.assert_close(y[j].cpu().numpy(), uo.mlp_forward(st, 1 + k, xw[:, :D].contiguous())[0].numpy(), 1e-4, 1e-5, f"subset {k}")
     # per-group inputs (x_gs != 0)

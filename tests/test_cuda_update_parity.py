@@ -158,3 +158,174 @@ def test_update_matches_reference(case, impl):
         lu.compute_td_targets, lu.compute_backup_weights = o_td, o_bw
         _rng.set_source(old_src)
         ssb.set_mlp_impl("tcgen05")
+
+
+def test_afbc_matches_reference():
+    """offline_actor_update (advantage-filtered BC, learning.py:144-219) with prioritised sampling and the priority
+    refresh of learning_utils.py:288-295, against the reference's golden vectors (tests/golden/afbc.npz)."""
+    import random as pyrandom
+
+    import cuda_util as cu
+    import super_sac_b200 as ssb
+    from super_sac_b200 import _rng, augmentations, learning, learning_utils as lu, nets
+
+    fx = gu.load("afbc")
+    cfg = gu.cfg_of(fx)
+    E, N, S, A, H, B = cfg["E"], cfg["N"], cfg["S"], cfg["A"], cfg["H"], cfg["B"]
+    agent = ssb.Agent(act_space_size=A, encoder=cu.IdentityEncoder(S), actor_network_cls=nets.mlps.ContinuousStochasticActor,
+                      critic_network_cls=nets.mlps.ContinuousCritic, ensemble_size=E, num_critics=N, hidden_size=H,
+                      auto_rescale_targets=True, log_std_low=-5.0, log_std_high=2.0)
+    agent.to("cuda")
+    cu.load_stack(agent._actor_arena, gu.sub(fx, "init/actors"))
+    cu.load_stack(agent._critic_arena, gu.sub(fx, "init/critics"))
+    pst = gu.sub(fx, "init/popart")
+    for i, p in enumerate(agent.popart):
+        p.mu, p.nu, p.w, p.b = pst[f"{i}/mu"], pst[f"{i}/nu"], pst[f"{i}/w"], pst[f"{i}/b"]
+    b = gu.sub(fx, "buffer")
+    buf = ssb.replay.ReplayBuffer(64, alpha=0.6, beta=1.0, device="cuda")
+    buf.push({"obs": b["s"]}, b["a"], b["r"][:, None], {"obs": b["s1"]}, b["d"][:, None], priorities=b["priorities"])
+    from itertools import chain
+
+    actor_opt = torch.optim.Adam(chain(*(a.parameters() for a in agent.actors)), lr=3e-4, betas=(0.9, 0.999))
+    enc_opt = torch.optim.Adam(agent.encoder.parameters(), lr=1e-4)
+    augmenter = augmentations.AugmentationSequence([augmentations.IdentityAug(B)])
+    old_src = _rng.set_source(_rng.ScriptedSource())
+    o_choice = pyrandom.choice
+    try:
+        for step in range(2):
+            r = gu.sub(fx, f"step{step}/rand")
+            src = _rng.ScriptedSource()
+            _rng.set_source(src)
+            for i in range(E):
+                src.push("uniform01", r["u"][i])
+                for e in r["adv_eps"][i]:
+                    src.push("normal", e)
+            for e in r["prio_eps"]:
+                src.push("normal", e)
+            member = int(r["prio_member"])
+            pyrandom.choice = lambda seq: (list(seq)[member] if isinstance(seq, range) else o_choice(seq))
+            logs = learning.offline_actor_update(
+                buffer=buf, agent=agent, actor_optimizer=actor_opt, encoder_optimizer=enc_opt, batch_size=B, actor_clip=40.0,
+                update_encoder=False, encoder_clip=40.0, augmenter=augmenter, actor_lambda=0.0, aug_mix=0.0,
+                premade_replay_dicts=None, per=True, discrete=False, filter_=True)
+            pyrandom.choice = o_choice
+            assert src.empty()
+            _cmp_stack(cu.grads_of(agent._actor_arena), gu.sub(fx, f"step{step}/actor_grads"), f"step{step} actor grads", atol=2e-7)
+            _cmp_stack(cu.stack_of(agent._actor_arena), gu.sub(fx, f"step{step}/actors"), f"step{step} actors", atol=3e-4 * 0.05)
+            _cmp_logs(logs, gu.sub(fx, f"step{step}/logs"), f"afbc step{step}")
+            tr = gu.sub(fx, f"step{step}/trees")
+            gu.assert_close(buf._it_sum.cpu().numpy(), tr["sum_tree"], 1e-4, 1e-8, "sum tree")
+            fin = np.isfinite(tr["min_tree"])
+            assert np.array_equal(np.isfinite(buf._it_min.cpu().numpy()), fin)
+            gu.assert_close(buf._it_min.cpu().numpy()[fin], tr["min_tree"][fin], 1e-4, 1e-8, "min tree")
+            assert abs(buf._max_priority - float(tr["max_priority"])) <= 1e-4 * float(tr["max_priority"])
+    finally:
+        pyrandom.choice = o_choice
+        _rng.set_source(old_src)
+
+
+def test_pixel_critic_update_matches_oracle():
+    """BASELINE config 4 in miniature: uint8 frames in the device ring, fused gather + DrQ (v1, exact) shift, a conv
+    encoder (user plugin, PyTorch/cuDNN) trained through grad(s_rep), deterministic actor + TD3 noise, n-step gamma.
+    Checked against the CPU oracle on the same draws (the encoder runs in PyTorch on both sides)."""
+    import copy
+
+    import cuda_util as cu
+    import super_sac_b200 as ssb
+    from oracle import aug_oracle as ao
+    from oracle import update_oracle as uo
+    from super_sac_b200 import _rng, augmentations, learning, learning_utils as lu, nets
+
+    class TinyPixelEncoder(nets.Encoder):
+        def __init__(self, c, hw, out_dim=10):
+            super().__init__()
+            self.conv1 = torch.nn.Conv2d(c, 8, 3, stride=2)
+            self.conv2 = torch.nn.Conv2d(8, 8, 3, stride=1)
+            n = ((hw - 3) // 2 + 1) - 2
+            self.fc = torch.nn.Linear(8 * n * n, out_dim)
+            self.ln = torch.nn.LayerNorm(out_dim)
+            self._dim = out_dim
+
+        @property
+        def embedding_dim(self):
+            return self._dim
+
+        def forward(self, obs):
+            x = obs["pixels"] / 255.0 - 0.5
+            x = torch.relu(self.conv2(torch.relu(self.conv1(x))))
+            return torch.tanh(self.ln(self.fc(x.flatten(1))))
+
+    rng = np.random.default_rng(5)
+    torch.manual_seed(5)
+    C, HW, A, Hd, B, nbuf, N = 3, 20, 3, 64, 16, 40, 2
+    enc = TinyPixelEncoder(C, HW)
+    agent = ssb.Agent(act_space_size=A, encoder=enc, actor_network_cls=nets.mlps.ContinuousDeterministicActor,
+                      critic_network_cls=nets.mlps.ContinuousCritic, ensemble_size=1, num_critics=N, hidden_size=Hd,
+                      auto_rescale_targets=False)
+    for arena in (agent._actor_arena, agent._critic_arena):
+        arena.flat.add_(0.02 * torch.randn_like(arena.flat))
+    # oracle twin (CPU) before anything moves
+    o_agent = uo.OracleAgent(1, N, enc.embedding_dim, A, Hd, deterministic=True, encoder=copy.deepcopy(enc))
+    for n in uo.PARAM_NAMES:
+        getattr(o_agent.actors, n).copy_(agent._actor_arena.p[n])
+        getattr(o_agent.critics, n).copy_(agent._critic_arena.p[n])
+    o_target = o_agent.clone()
+    agent.to("cuda")
+    target = copy.deepcopy(agent)
+    s = rng.integers(0, 256, (nbuf, C, HW, HW), dtype=np.uint8)
+    s1 = rng.integers(0, 256, (nbuf, C, HW, HW), dtype=np.uint8)
+    a = rng.uniform(-1, 1, (nbuf, A)).astype(np.float32)
+    r = rng.standard_normal(nbuf).astype(np.float32)
+    d = rng.uniform(size=nbuf) < 0.1
+    buf = ssb.replay.ReplayBuffer(nbuf, device="cuda")
+    buf.load_experience({"pixels": s}, a, r, {"pixels": s1}, d)
+    from itertools import chain
+
+    critic_opt = torch.optim.Adam(chain(*(c.parameters() for c in agent.critics)), lr=1e-4)
+    enc_opt = torch.optim.Adam(agent.encoder.parameters(), lr=1e-4)
+    o_opt = uo.Adam(o_agent.critics.tensors(), lr=1e-4)
+    o_enc_opt = torch.optim.Adam(o_agent.encoder.parameters(), lr=1e-4)
+    log_alphas = [torch.tensor([-30.0], device="cuda", requires_grad=True)]
+    noise_proc = lu.GaussianExplorationNoise(cu.ActionSpace(A), start_scale=0.6, final_scale=0.1)
+    augmenter = augmentations.AugmentationSequence([augmentations.DrqNoNoiseAug(B)])
+    gamma = 0.99**3
+    old_src = _rng.set_source(_rng.ScriptedSource())
+    try:
+        for step in range(2):
+            idx = rng.integers(0, nbuf, B)
+            shift = rng.integers(0, 8, (B, 2))
+            noise = rng.standard_normal((B, A)).astype(np.float32)
+            subset = rng.permutation(N)[:2]
+            src = _rng.ScriptedSource()
+            _rng.set_source(src)
+            src.push("indices", idx).push("shifts", shift.astype(np.int32)).push("normal", noise).push("subsets", subset.astype(np.int32))
+            logs, _ = learning.critic_update(
+                buffer=buf, agent=agent, target_agent=target, critic_optimizer=critic_opt, encoder_optimizer=enc_opt,
+                log_alphas=log_alphas, batch_size=B, gamma=gamma, critic_clip=None, encoder_clip=None,
+                target_critic_ensemble_n=2, weighted_bellman_temp=None, weight_type=None, pop=False, augmenter=augmenter,
+                encoder_lambda=0.0, random_process=noise_proc, noise_clip=0.3, aug_mix=1.0)
+            assert src.empty()
+            for ac, tc in zip(agent.critics, target.critics):
+                lu.soft_update(tc, ac, 0.01)
+            lu.soft_update(target.encoder, agent.encoder, 1.0)
+            # oracle on the same draws
+            t32 = lambda x: torch.as_tensor(np.asarray(x, dtype=np.float32))
+            o = {"pixels": t32(ao.drq_v1_crop(s[idx], shift[:, 0], shift[:, 1]))}
+            o1 = {"pixels": t32(ao.drq_v1_crop(s1[idx], shift[:, 0], shift[:, 1]))}
+            batch = (o, t32(a[idx]), t32(r[idx]).reshape(-1, 1), o1, t32(d[idx]).reshape(-1, 1))
+            hp = dict(gamma=gamma, noise_sigma=0.6, noise_clip=0.3)
+            ologs, aux = uo.critic_update(o_agent, o_target, [batch], [dict(eps=None, noise=t32(noise), subset=[int(x) for x in subset])],
+                                          hp, [torch.tensor([-30.0])], o_opt, o_enc_opt)
+            uo.soft_update(o_target.critics.tensors(), o_agent.critics.tensors(), 0.01)
+            uo.soft_update([p.data for p in o_target.encoder.parameters()], [p.data for p in o_agent.encoder.parameters()], 1.0)
+            for n in uo.PARAM_NAMES:
+                gu.assert_close(agent._critic_arena.g[n].cpu().numpy(), getattr(aux["grads"], n).numpy(), 2e-4, 2e-6, f"step{step} grad {n}")
+                gu.assert_close(agent._critic_arena.p[n].cpu().numpy(), getattr(o_agent.critics, n).numpy(), 1e-4, 1e-4 * 0.05, f"step{step} critics {n}")
+                gu.assert_close(target._critic_arena.p[n].cpu().numpy(), getattr(o_target.critics, n).numpy(), 1e-4, 1e-4 * 0.05, f"step{step} target {n}")
+            for (k, v), (_, w) in zip(agent.encoder.state_dict().items(), o_agent.encoder.state_dict().items()):
+                gu.assert_close(v.cpu().numpy(), w.numpy(), 2e-4, 1e-4 * 0.05, f"step{step} encoder {k}")
+            for v, w in zip(target.encoder.parameters(), agent.encoder.parameters()):
+                assert torch.equal(v, w)  # encoder_tau = 1.0 is a copy
+            gu.assert_close(logs["losses/critic_overall_loss"], ologs["losses/critic_overall_loss"], 2e-4, 1e-6, "loss")
+    finally:
+        _rng.set_source(old_src)

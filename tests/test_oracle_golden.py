@@ -147,3 +147,50 @@ def test_aug_oracle_matches_reference():
     assert np.array_equal(b["s"][idx].astype(np.float32), g["oo"])
     aug1 = ao.drq_v2_crop(b["s1"][idx], g["shift"])
     assert np.abs(aug1 - g["ao1"]).max() <= 4e-3
+
+
+def _afbc_setup(fx):
+    cfg = gu.cfg_of(fx)
+    E, N, S, A, H = cfg["E"], cfg["N"], cfg["S"], cfg["A"], cfg["H"]
+    agent = uo.OracleAgent(E, N, S, A, H, log_std_low=-5.0, log_std_high=2.0)
+    agent.actors = uo.MLPStack.from_arrays(gu.sub(fx, "init/actors"))
+    agent.critics = uo.MLPStack.from_arrays(gu.sub(fx, "init/critics"))
+    agent.popart = gu.popart_from(fx, "init/popart", E)
+    b = gu.sub(fx, "buffer")
+    buf = ro.ReplayOracle(64, alpha=0.6, beta=1.0)
+    buf.push({"obs": b["s"]}, b["a"], b["r"][:, None], {"obs": b["s1"]}, b["d"][:, None], priorities=b["priorities"])
+    return cfg, agent, buf
+
+
+def test_afbc_oracle_matches_reference():
+    """offline_actor_update (advantage-filtered BC) + PER sampling + priority refresh."""
+    torch.set_num_threads(1)
+    fx = gu.load("afbc")
+    cfg, agent, buf = _afbc_setup(fx)
+    E, B = cfg["E"], cfg["B"]
+    opt = uo.Adam(agent.actors.tensors(), lr=3e-4)
+    t32 = lambda x: torch.as_tensor(np.asarray(x, dtype=np.float32))
+    for step in range(2):
+        r = gu.sub(fx, f"step{step}/rand")
+        batches, rands, last_idx = [], [], None
+        for i in range(E):
+            (s, a, rew, s1, d), w, idxes = buf.sample(r["u"][i])
+            batches.append(({"obs": t32(s["obs"])}, t32(a), t32(rew), {"obs": t32(s1["obs"])}, t32(d)))
+            rands.append(dict(adv_eps=[t32(e) for e in r["adv_eps"][i]]))
+            last_idx = idxes
+        logs, aux = uo.offline_actor_update(agent, batches, rands, dict(actor_clip=40.0, filter=True), opt)
+        want = gu.sub(fx, f"step{step}/actor_grads")
+        for n in uo.PARAM_NAMES:
+            gu.assert_close(getattr(aux["grads"], n).numpy(), want[n], 1e-4, 1e-7, f"step{step} actor grad {n}")
+        want = gu.sub(fx, f"step{step}/actors")
+        for n in uo.PARAM_NAMES:
+            gu.assert_close(getattr(agent.actors, n).numpy(), want[n], 1e-5, 3e-4 * 2e-2, f"step{step} actors {n}")
+        _cmp_logs(logs, gu.sub(fx, f"step{step}/logs"), f"afbc step{step}")
+        o, a = batches[-1][0], batches[-1][1]
+        adv = uo.advantage(agent, int(r["prio_member"]), o, a, [t32(e) for e in r["prio_eps"]])
+        newp = (torch.relu(adv) + 1e-4).squeeze(1).numpy()
+        buf.update_priorities(last_idx, newp)
+        tr = gu.sub(fx, f"step{step}/trees")
+        gu.assert_close(buf.it_sum.value, tr["sum_tree"], 1e-5, 1e-9, "sum tree")  # priorities come from fp32 advantages
+        assert np.array_equal(np.isinf(buf.it_min.value), np.isinf(tr["min_tree"]))
+        assert abs(buf.max_priority - float(tr["max_priority"])) <= 1e-5 * float(tr["max_priority"])
