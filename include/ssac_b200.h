@@ -172,10 +172,11 @@ int ssac_backup_weights(const float* q_dev, int E, int N, int B, float temperatu
 
 /* ---- critic loss seed: learning.py:90-98,112 ------------------------------------------------------ */
 /* q [N,B] predictions of one member, y [B], w [B] (nullable = 1), imp [B] (nullable = 1).
- * q' = popw*q+popb if pop.  dq[k,b] = -2*w*imp*(y-q')*popw * inv_count (inv_count = 1/(B*E*N));
- * loss_dev[0] += sum_k mean_b(w*imp*(y-q')^2) * (1/(E*N));  loss_dev[1] = mean_b(y - q'_{N-1}). */
+ * q' = popw*q+popb if pop.  dq[k,b] = -2*w*imp*(y-q')*popw * inv_count, inv_count = 1/(B*E*n_total) where n_total
+ * is the ensemble-wide number of critics per member (= N unless the critics are sharded over ranks; 0 means N);
+ * loss_dev[0] += sum_k mean_b(w*imp*(y-q')^2) * (1/(E*n_total));  loss_dev[1] = mean_b(y - q'_{N-1}). */
 int ssac_critic_loss_seed(const float* q_dev, int N, int B, const float* y_dev, const float* w_dev,
-                          const float* imp_dev, const float* popart_dev, int pop, int E, float* dq_dev,
+                          const float* imp_dev, const float* popart_dev, int pop, int E, int n_total, float* dq_dev,
                           float* loss_dev, void* stream);
 /* DR3 feature co-adaptation: f, f1 [N,B,H]: out_dev[0] = mean_{N,B} sum_H f*f1. */
 int ssac_dr3_dot(const float* f_dev, const float* f1_dev, int N, int B, int H, float* out_dev, void* stream);

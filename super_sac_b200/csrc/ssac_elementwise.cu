@@ -471,10 +471,11 @@ __global__ void __launch_bounds__(1024) critic_loss_seed_kernel(const float* __r
                                                                 const float* __restrict__ w,
                                                                 const float* __restrict__ imp,
                                                                 const float* __restrict__ popart, int pop, int E,
-                                                                float* __restrict__ dq, float* __restrict__ loss) {
+                                                                int n_total, float* __restrict__ dq,
+                                                                float* __restrict__ loss) {
   __shared__ float scratch[32];
   const float pw = (popart && pop) ? popart[2] : 1.f, pb = (popart && pop) ? popart[3] : 0.f;
-  const float inv_count = 1.f / ((float)B * (float)E * (float)N);
+  const float inv_count = 1.f / ((float)B * (float)E * (float)n_total);
   float s_loss = 0.f, s_td = 0.f;
   for (int i = threadIdx.x; i < N * B; i += blockDim.x) {
     const int k = i / B, b = i - k * B;
@@ -757,9 +758,10 @@ int ssac_backup_weights(const float* q, int E, int N, int B, float temperature, 
 }
 
 int ssac_critic_loss_seed(const float* q, int N, int B, const float* y, const float* w, const float* imp,
-                          const float* popart, int pop, int E, float* dq, float* loss, void* stream) {
-  SSAC_REQUIRE(q && y && dq && N > 0 && B > 0 && E > 0, "ssac_critic_loss_seed: bad args");
-  critic_loss_seed_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(q, N, B, y, w, imp, popart, pop, E, dq, loss);
+                          const float* popart, int pop, int E, int n_total, float* dq, float* loss, void* stream) {
+  SSAC_REQUIRE(q && y && dq && N > 0 && B > 0 && E > 0 && n_total >= 0, "ssac_critic_loss_seed: bad args");
+  critic_loss_seed_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(q, N, B, y, w, imp, popart, pop, E,
+                                                                n_total > 0 ? n_total : N, dq, loss);
   SSAC_CHECK_LAUNCH("ssac_critic_loss_seed");
   return 0;
 }

@@ -225,7 +225,6 @@ __global__ void __launch_bounds__(kThreads, 1) grouped_gemm_tc_kernel(const __gr
   __shared__ __align__(8) uint64_t bar_empty[kStages];   // tensor core -> producers: the MMAs reading stage s are done
   __shared__ __align__(8) uint64_t bar_done;
   __shared__ uint32_t tmem_base_sh;
-  __shared__ float colsum_sh[TM];
 
   const GemmP& p = q.p;
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle atoms need 1024-byte alignment
@@ -256,7 +255,6 @@ __global__ void __launch_bounds__(kThreads, 1) grouped_gemm_tc_kernel(const __gr
     mbar_init(&bar_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (t < TM) colsum_sh[t] = 0.f;
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -407,8 +405,11 @@ __global__ void __launch_bounds__(kThreads, 1) grouped_gemm_tc_kernel(const __gr
         for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
       }
     }
+    // bias gradients: every (k-row slot, column) partial has exactly one owner thread; they are written to a
+    // [slots][128] scratch above the output tile and summed in a fixed order (bit-reproducible, no atomics)
+    float* part = reinterpret_cast<float*>(smem + 96 * 1024);
+    const int n_slots = a_tma ? 32 : 8;
     if (do_colsum) {
-      // fold this thread's partial column sums into shared memory (shared atomics, once per kernel)
       if (a_tma) {
         // chunk i of thread t sits at byte offset 16*(t + 256 i): m-group i, k row t/8, physical 32-byte chunk (t%8)/2
         const int kr = (t >> 3) & 3;
@@ -416,12 +417,12 @@ __global__ void __launch_bounds__(kThreads, 1) grouped_gemm_tc_kernel(const __gr
         for (int i = 0; i < 4; ++i) {
           const int mbase = 32 * i + ((((t & 7) >> 1) ^ kr) << 3) + ((t & 1) << 2);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) atomicAdd(&colsum_sh[mbase + e], cs[4 * i + e]);
+          for (int e = 0; e < 4; ++e) part[(t >> 3) * TM + mbase + e] = cs[4 * i + e];
         }
       } else {
         const int mbase = 4 * (t & 31);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) atomicAdd(&colsum_sh[mbase + e], cs[e]);
+        for (int e = 0; e < 4; ++e) part[(t >> 5) * TM + mbase + e] = cs[e];
       }
     }
     workers_sync();
@@ -488,8 +489,10 @@ __global__ void __launch_bounds__(kThreads, 1) grouped_gemm_tc_kernel(const __gr
     if (do_colsum) {
       const int mm = m0 + t;
       if (t < TM && mm < p.M) {
+        float tot = 0.f;
+        for (int sl = 0; sl < n_slots; ++sl) tot += part[sl * TM + t];
         float* out = p.colsum + (int64_t)wg * p.colsum_gs;
-        out[mm] = p.accumulate ? (out[mm] + colsum_sh[t]) : colsum_sh[t];
+        out[mm] = p.accumulate ? (out[mm] + tot) : tot;
       }
     }
   }

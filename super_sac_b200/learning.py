@@ -10,7 +10,7 @@ import random
 
 import torch
 
-from . import _arena, _lib, _logs, _ops, _rng
+from . import _arena, _lib, _logs, _ops, _rng, parallel
 from . import learning_utils as lu
 
 
@@ -34,8 +34,9 @@ def critic_update(buffer, agent, target_agent, critic_optimizer, encoder_optimiz
     S, A = lu._dims(agent)
     logs = _logs.DeviceLogs(dev)
     loss_v, loss_slot = logs.slots(2)
-    loss_v.zero_()
     opt = _arena.FlatAdam.attach(critic_optimizer, ca)
+    if parallel.is_sharded() and (E != 1 or dr3_coeff > 0 or critic_clip):
+        raise NotImplementedError("critic sharding covers the REDQ shape (one member, no DR3 / global-norm clip)")
 
     replay_dicts, enc_outs = [], []
     for i in range(E):
@@ -56,9 +57,10 @@ def critic_update(buffer, agent, target_agent, critic_optimizer, encoder_optimiz
         dq = torch.empty((N, B, 1), dtype=torch.float32, device=dev)
         imp = rd["imp_weights"]
         imp_ptr = imp.float().contiguous() if per else None  # per=False: ones(1), i.e. no weighting (main.py:401)
+        n_total = parallel.n_global() if parallel.is_sharded() else 0   # sharded critics: normalise by the global N
         L.critic_loss_seed(q.data_ptr(), N, B, td_target.data_ptr(), w.data_ptr() if torch.is_tensor(w) else None,
                            None if imp_ptr is None else imp_ptr.data_ptr(), popart.state_ptr() if popart else None,
-                           int(bool(pop)), E, dq.data_ptr(), loss_v.data_ptr(), stream)
+                           int(bool(pop)), E, n_total, dq.data_ptr(), loss_v.data_ptr(), stream)
         extra, extra_scale, f1 = None, 0.0, None
         if dr3_coeff > 0:
             # DR3 (learning.py:100-108): second forward on (s1, a1); both feature sets carry gradient
@@ -92,6 +94,8 @@ def critic_update(buffer, agent, target_agent, critic_optimizer, encoder_optimiz
         encoder_optimizer.step()
     opt.step(stream, max_norm=critic_clip if critic_clip else None)
 
+    if parallel.is_sharded():
+        parallel.all_reduce_sum_(loss_v[0:1])   # each rank summed its own critics
     logs.defer("losses/last_member_critic_td_error", loss_slot + 1)
     logs.defer("losses/critic_overall_loss", loss_slot)
     member = random.choice(range(E))
@@ -119,7 +123,6 @@ def online_actor_update(buffer, agent, pop, actor_optimizer, log_alphas, batch_s
     S, A = lu._dims(agent)
     logs = _logs.DeviceLogs(dev)
     loss_v, loss_slot = logs.slots(1)
-    loss_v.zero_()
     opt = _arena.FlatAdam.attach(actor_optimizer, aa)
     for i in range(E):
         if premade_replay_dicts is not None:
@@ -134,16 +137,30 @@ def online_actor_update(buffer, agent, pop, actor_optimizer, log_alphas, batch_s
         pol = lu._policy_sample(agent, i, XPI, B, S, A, random_process, noise_clip, rsample=True)
         q, h1c, h2c = lu._critic_values(agent, i * N, N, XPI, B, keep=True)
         popart = agent.popart[i]
-        dq = torch.empty((N, B, 1), dtype=torch.float32, device=dev)
         entropy_on = pol["logp"] is not None
-        L.actor_loss_seed(q.data_ptr(), N, B, pol["logp"].data_ptr() if entropy_on else None,
-                          log_alphas[i].data_ptr(), popart.state_ptr() if popart else None, int(bool(pop)), E, None,
-                          dq.data_ptr(), loss_v.data_ptr(), stream)
+        if parallel.is_sharded():
+            # every rank sees all N_global values, picks the arg-min net per row, and back-propagates only the rows
+            # whose arg-min critic it owns; the partial dL/da are summed below
+            q_all = parallel.all_gather_q(q)
+            Ng = q_all.shape[0]
+            dq_all = torch.empty((Ng, B, 1), dtype=torch.float32, device=dev)
+            L.actor_loss_seed(q_all.data_ptr(), Ng, B, pol["logp"].data_ptr() if entropy_on else None,
+                              log_alphas[i].data_ptr(), popart.state_ptr() if popart else None, int(bool(pop)), E, None,
+                              dq_all.data_ptr(), loss_v.data_ptr(), stream)
+            lo, hi = parallel.my_range()
+            dq = dq_all[lo:hi].contiguous()
+        else:
+            dq = torch.empty((N, B, 1), dtype=torch.float32, device=dev)
+            L.actor_loss_seed(q.data_ptr(), N, B, pol["logp"].data_ptr() if entropy_on else None,
+                              log_alphas[i].data_ptr(), popart.state_ptr() if popart else None, int(bool(pop)), E, None,
+                              dq.data_ptr(), loss_v.data_ptr(), stream)
         # through the critics to the action: input-gradient only (the reference's critic dW here is discarded anyway)
         dxg = torch.empty((N, B, S + A), dtype=torch.float32, device=dev)
         _ops.mlp_backward(ca, i * N, N, XPI, B, h1c, h2c, dq, ldx=S + A, want_dw=False, dx=dxg, lddx=S + A)
         da = torch.empty((B, A), dtype=torch.float32, device=dev)
         L.sum_groups(dxg.data_ptr(), N, B, S + A, S, A, da.data_ptr(), stream)
+        if parallel.is_sharded():
+            parallel.all_reduce_sum_(da)
         O = aa.O
         dout = torch.empty((1, B, O), dtype=torch.float32, device=dev)
         if agent.deterministic:

@@ -11,7 +11,7 @@ import random
 import numpy as np
 import torch
 
-from . import _lib, _logs, _ops, _rng, augmentations
+from . import _lib, _logs, _ops, _rng, augmentations, parallel
 from ._arena import MLPArena
 
 LOG_SQRT_2PI = math.log(math.sqrt(2 * math.pi))
@@ -126,8 +126,7 @@ def get_grad_norm(model):
 
 def _member_grad_norm_slot(logs, arena, g0, g1):
     """Enqueue sum g^2 of nets g0..g1 into a log slot (sqrt taken at finalize)."""
-    v, slot = logs.slots(1)
-    v.zero_()
+    v, slot = logs.slots(1)   # slots are zero-initialised with the buffer
     L, s = _lib.lib(), _lib.stream_ptr()
     for off, n in arena.range_table(g0, g1):
         L.sumsq(arena.grad.data_ptr() + 4 * off, n, v.data_ptr(), 1, s)
@@ -156,6 +155,17 @@ class ReplayDict(dict):
         return dict.__contains__(self, key) or key in self._lazy
 
 
+_ones_cache = {}
+
+
+def _ones1(dev):
+    t = _ones_cache.get(dev)
+    if t is None:
+        t = torch.ones(1, dtype=torch.float32, device=dev)
+        _ones_cache[dev] = t
+    return t
+
+
 def _pixel_gather(stack, idx, shift, aug, B, aug_rows, use_aug):
     _, C, H, W = stack.shape
     out = torch.empty((B, C, H, W), dtype=torch.float32, device=stack.device)
@@ -180,7 +190,7 @@ def sample_move_and_augment(buffer, batch_size, augmenter, aug_mix, per=True):
         idx, imp_weights = buffer.sample_indices_per(B)
     else:
         idx = buffer.sample_indices_uniform(B)
-        imp_weights = torch.ones(1, dtype=torch.float32, device=dev)
+        imp_weights = _ones1(dev)
     aug_rows = int(B * aug_mix)
     fused = isinstance(augmenter, augmentations.AugmentationSequence) and augmenter.fusable()
     rd = ReplayDict()
@@ -385,9 +395,18 @@ def compute_td_targets(logs, replay_dict, agent, target_agent, ensemble_idx, ens
     pol = _policy_sample(agent, i, X1, B, S, A, random_process, noise_clip)
     N = agent.num_critics
     net_index = torch.empty(ensemble_n, dtype=torch.int32, device=X1.device)
-    assert 0 < ensemble_n <= N
-    _rng.source().subsets(net_index, N, ensemble_n)
-    q_t = _critic_values(target_agent, i * N, ensemble_n, X1, B, net_index=net_index)
+    if parallel.is_sharded():
+        # every rank draws the same subset of the GLOBAL ensemble (replicated Philox state), evaluates its own target
+        # critics and all-gathers the [N_global, B] values; the subset-min is then identical on every rank
+        Ng = parallel.n_global()
+        assert 0 < ensemble_n <= Ng
+        _rng.source().subsets(net_index, Ng, ensemble_n)
+        q_all = parallel.all_gather_q(_critic_values(target_agent, i * N, N, X1, B))
+        q_t = q_all.index_select(0, net_index.long())
+    else:
+        assert 0 < ensemble_n <= N
+        _rng.source().subsets(net_index, N, ensemble_n)
+        q_t = _critic_values(target_agent, i * N, ensemble_n, X1, B, net_index=net_index)
     y = torch.empty((B, 1), dtype=torch.float32, device=X1.device)
     lv, slot = dlogs.slots(3)
     _lib.lib().td_target(q_t.data_ptr(), ensemble_n, B, None if pol["logp"] is None else pol["logp"].data_ptr(),

@@ -329,3 +329,21 @@ def test_pixel_critic_update_matches_oracle():
             gu.assert_close(logs["losses/critic_overall_loss"], ologs["losses/critic_overall_loss"], 2e-4, 1e-6, "loss")
     finally:
         _rng.set_source(old_src)
+
+
+def test_sharded_update_equals_single_gpu():
+    """critics sharded over 2 GPUs (NCCL all-gather of target Q / Q(s,pi), all-reduce of dL/da) give the
+    single-GPU result.  Needs 2 GPUs on the box (skipped otherwise); the host logic is covered on CPU by
+    tests/test_parallel_gloo.py."""
+    import os
+    import subprocess
+    import sys
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29517", os.path.join(root, "tests", "dist_sharded_check.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "[rank 0] sharded critics" in res.stdout and "[rank 1] sharded critics" in res.stdout
