@@ -128,6 +128,22 @@ int ssac_mlp_backward(const float* W1, const float* W2, const float* W3, const i
                       float extra_scale, float* gW1, float* gb1, float* gW2, float* gb2, float* gW3, float* gb3,
                       int accumulate, float* dx_dev, int64_t lddx, float* ws_dev, int impl, void* stream);
 
+/* Actor forward with the policy head fused into the output-layer kernel (one member): replaces ssac_mlp_forward +
+ * ssac_tanh_normal_forward / ssac_det_head_forward.  out [B, 2A] (stochastic) or [B, A] (deterministic) is kept for the
+ * backward.  deterministic: eps (nullable) is the 1e-4 rsample jitter, noise (nullable) the TD3 noise. */
+int ssac_actor_forward_sample(const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
+                              const float* b3, int D, int H, int A, int deterministic, const float* x_dev, int64_t ldx,
+                              int B, float* h1_dev, float* h2_dev, float* out_dev, const float* eps_dev,
+                              const float* noise_dev, float sigma, float clip, float log_std_lo, float log_std_hi,
+                              float* a_dev, int64_t lda, float* logp_dev, float* tanh_out_dev, int impl, void* stream);
+/* Critic forward of one member (N nets, shared input) with the loss seed of ssac_critic_loss_seed fused into the
+ * output-layer kernel: q [N,B], dq [N,B], loss_dev[0] += loss, loss_dev[1] += mean td of the last net. */
+int ssac_critic_forward_loss(const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
+                             const float* b3, int N, int D, int H, const float* x_dev, int64_t ldx, int B,
+                             float* h1_dev, float* h2_dev, float* q_dev, const float* y_dev, const float* w_dev,
+                             const float* imp_dev, const float* popart_dev, int pop, int E, int n_total, float* dq_dev,
+                             float* loss_dev, int impl, void* stream);
+
 /* ---- policy heads: nets/distributions.py:9-15,64-114; learning_utils.py:48-59 --------------------- */
 /* out [B,2A] = [mu | raw_log_std], eps [B,A] -> a [B,A] (row stride lda: may be a column block of cat(s,a)),
  * logp [B] (sum over A of Normal.log_prob(x) - log|d tanh|).  Saves nothing: backward recomputes. */

@@ -40,6 +40,7 @@ class DeviceLogs(dict):
         return v, first
 
     def defer(self, key, slot, transform=None):
+        """``slot`` may be a list of slots: their sum is reported."""
         self._pending.append((key, slot, transform))
 
     def put_tensor(self, key, scalar_tensor, transform=None):
@@ -59,7 +60,7 @@ class DeviceLogs(dict):
         if self._pending:
             host = self._buf[: self._n].cpu()  # the one sync
             for key, slot, transform in self._pending:
-                val = float(host[slot])
+                val = sum(float(host[s_]) for s_ in slot) if isinstance(slot, (list, tuple)) else float(host[slot])
                 self[key] = transform(val) if transform is not None else val
             if not keep:
                 self._pending = []

@@ -1,10 +1,12 @@
 // C-ABI dispatch for the ensemble MLP entry points (see include/ssac_b200.h).
-#include "ssac_common.cuh"
+#include <cstring>
+
+#include "ssac_mlp.cuh"
 
 namespace ssac {
 int mlp_forward_simt(const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
                      const float* b3, const int32_t* net_index, int G, int D, int H, int O, const float* x, int64_t ldx,
-                     int64_t x_gs, int B, float* h1, float* h2, float* y, cudaStream_t s, int impl);
+                     int64_t x_gs, int B, float* h1, float* h2, float* y, cudaStream_t s, int impl, const HeadEpi* epi);
 int mlp_backward_simt(const float* W1, const float* W2, const float* W3, const int32_t* net_index, int G, int D, int H,
                       int O, const float* x, int64_t ldx, int64_t x_gs, int B, const float* h1, const float* h2,
                       const float* dy, const float* dh2_extra, float extra_scale, float* gW1, float* gb1, float* gW2,
@@ -34,8 +36,46 @@ int ssac_mlp_forward(const float* W1, const float* b1, const float* W2, const fl
   if (impl == 0) impl = ssac_default_mlp_impl();
   if (impl == 1 || impl == 2)
     return mlp_forward_simt(W1, b1, W2, b2, W3, b3, net_index_dev, G, D, H, O, x_dev, ldx, x_gs, B, h1_dev, h2_dev,
-                            y_dev, (cudaStream_t)stream, impl);
+                            y_dev, (cudaStream_t)stream, impl, nullptr);
   return fail(SSAC_E_UNSUPPORTED, "ssac_mlp_forward: unknown impl");
+}
+
+int ssac_actor_forward_sample(const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
+                              const float* b3, int D, int H, int A, int deterministic, const float* x_dev, int64_t ldx,
+                              int B, float* h1_dev, float* h2_dev, float* out_dev, const float* eps_dev,
+                              const float* noise_dev, float sigma, float clip, float log_std_lo, float log_std_hi,
+                              float* a_dev, int64_t lda, float* logp_dev, float* tanh_out_dev, int impl, void* stream) {
+  SSAC_REQUIRE(W1 && b1 && W2 && b2 && W3 && b3 && x_dev && out_dev && a_dev && h1_dev && h2_dev,
+               "ssac_actor_forward_sample: null pointer");
+  SSAC_REQUIRE(D > 0 && H > 0 && A > 0 && A <= 16 && B > 0 && ldx >= D && lda >= A, "ssac_actor_forward_sample: bad sizes");
+  SSAC_REQUIRE(deterministic || eps_dev, "ssac_actor_forward_sample: a stochastic actor needs eps");
+  if (impl == 0) impl = ssac_default_mlp_impl();
+  HeadEpi e;
+  memset(&e, 0, sizeof(e));
+  e.kind = deterministic ? 2 : 1;
+  e.eps = eps_dev; e.noise = noise_dev; e.sigma = sigma; e.clip = clip; e.lo = log_std_lo; e.hi = log_std_hi;
+  e.a = a_dev; e.lda = lda; e.logp = logp_dev; e.tanh_out = tanh_out_dev; e.A = A;
+  return mlp_forward_simt(W1, b1, W2, b2, W3, b3, nullptr, 1, D, H, deterministic ? A : 2 * A, x_dev, ldx, 0, B, h1_dev,
+                          h2_dev, out_dev, (cudaStream_t)stream, impl, &e);
+}
+
+int ssac_critic_forward_loss(const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
+                             const float* b3, int N, int D, int H, const float* x_dev, int64_t ldx, int B,
+                             float* h1_dev, float* h2_dev, float* q_dev, const float* y_dev, const float* w_dev,
+                             const float* imp_dev, const float* popart_dev, int pop, int E, int n_total, float* dq_dev,
+                             float* loss_dev, int impl, void* stream) {
+  SSAC_REQUIRE(W1 && b1 && W2 && b2 && W3 && b3 && x_dev && q_dev && y_dev && dq_dev && h1_dev && h2_dev,
+               "ssac_critic_forward_loss: null pointer");
+  SSAC_REQUIRE(N > 0 && D > 0 && H > 0 && B > 0 && E > 0 && ldx >= D, "ssac_critic_forward_loss: bad sizes");
+  if (impl == 0) impl = ssac_default_mlp_impl();
+  HeadEpi e;
+  memset(&e, 0, sizeof(e));
+  e.kind = 3;
+  e.y = y_dev; e.w = w_dev; e.imp = imp_dev; e.popart = popart_dev; e.pop = pop;
+  e.inv_count = 1.f / ((float)B * (float)E * (float)(n_total > 0 ? n_total : N));
+  e.dq = dq_dev; e.loss = loss_dev;
+  return mlp_forward_simt(W1, b1, W2, b2, W3, b3, nullptr, N, D, H, 1, x_dev, ldx, 0, B, h1_dev, h2_dev, q_dev,
+                          (cudaStream_t)stream, impl, &e);
 }
 
 int64_t ssac_mlp_backward_ws(int G, int B, int H) { return 2 * (int64_t)G * B * H; }

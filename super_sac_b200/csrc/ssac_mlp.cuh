@@ -25,4 +25,15 @@ struct GemmP {
 
 int launch_gemm_tc(int layout, const GemmP& p, int G, cudaStream_t s, const char* what);
 
+// Work fused into the output-layer kernel of a forward pass (narrow heads, O <= 32): what the reference does with a
+// dozen element-wise launches after the last nn.Linear.
+struct HeadEpi {
+  int kind;  // 0 = none, 1 = tanh-Normal sample + log-prob, 2 = deterministic head (+TD3 noise), 3 = critic loss seed
+  // kinds 1 / 2: nets/distributions.py:9-15,64-114, learning_utils.py:48-59
+  const float* eps; const float* noise; float sigma, clip, lo, hi;
+  float* a; int64_t lda; float* logp; float* tanh_out; int A;
+  // kind 3: learning.py:90-98,112
+  const float* y; const float* w; const float* imp; const float* popart; int pop; float inv_count; float* dq; float* loss;
+};
+
 }  // namespace ssac

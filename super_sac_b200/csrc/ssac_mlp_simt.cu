@@ -7,6 +7,8 @@
 //   TN  C = A^T * B (+colsum)                backward weight path  dW = dZ^T * act, db = colsum(dZ)
 // This is the exact-fp32 path (the reference runs fp32 SGEMM); the tcgen05 path (impl = 2) in
 // ssac_mlp_tc.cu is checked against it.
+#include <cstring>
+
 #include "ssac_mlp.cuh"
 
 namespace ssac {
@@ -113,32 +115,104 @@ __global__ void __launch_bounds__(256) grouped_gemm_kernel(GemmP p) {
 // ------------------------------------------------------------------------------------------------
 constexpr int kSmallO = 32;
 
-// y[g][b][o] = sum_h h2[g][b][h] * W3[wg][o][h] + b3[wg][o]      one warp per (g, b), h2 row read once
-template <int OMAX>
+// y[g][b][o] = sum_h h2[g][b][h] * W3[wg][o][h] + b3[wg][o]
+// grid (ceil(B/8), G), 8 warps = 8 batch rows of one net; W3 of that net is staged in shared memory once per block and
+// every row is read once.  The epilogue (HeadEpi) turns the outputs into actions / log-probs or the loss seed.
+#define SSAC_LOG2F 0.6931471805599453f
+#define SSAC_LOG_SQRT_2PIF 0.9189385332046727f
+__device__ __forceinline__ float softplus_th(float z) { return z > 20.f ? z : log1pf(expf(z)); }
+
 __global__ void __launch_bounds__(256) head_forward_kernel(const float* __restrict__ h2, const float* __restrict__ W3,
                                                            const float* __restrict__ b3,
                                                            const int32_t* __restrict__ net_index, int G, int B, int H,
-                                                           int O, float* __restrict__ y) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= G * B) return;
-  const int g = warp / B;
+                                                           int O, float* __restrict__ y, HeadEpi epi) {
+  extern __shared__ float W3s[];   // [O][H]
+  __shared__ float red[2][8];
+  const int g = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wg = net_index ? net_index[g] : g;
-  const float* hrow = h2 + (int64_t)warp * H;
   const float* W = W3 + (int64_t)wg * O * H;
-  float acc[OMAX];
+  for (int i = threadIdx.x; i < O * H; i += blockDim.x) W3s[i] = __ldg(W + i);
+  const int b = blockIdx.x * 8 + warp;
+  const bool row_ok = b < B;
+  const float* hrow = h2 + ((int64_t)g * B + (row_ok ? b : 0)) * H;
+  float hv[32];   // H <= 1024
 #pragma unroll
-  for (int o = 0; o < OMAX; ++o) acc[o] = 0.f;
-  for (int h = lane; h < H; h += 32) {
-    const float hv = hrow[h];
-#pragma unroll
-    for (int o = 0; o < OMAX; ++o)
-      if (o < O) acc[o] = fmaf(hv, __ldg(W + (int64_t)o * H + h), acc[o]);
+  for (int i = 0; i < 32; ++i) {
+    const int h = lane + 32 * i;
+    hv[i] = (row_ok && h < H) ? hrow[h] : 0.f;
   }
+  __syncthreads();
+  float outv = 0.f;   // lane o ends up holding output o
+  for (int o = 0; o < O; ++o) {
+    float acc = 0.f;
 #pragma unroll
-  for (int o = 0; o < OMAX; ++o) {
-    if (o < O) {
-      const float tot = warp_sum(acc[o]);
-      if (lane == 0) y[(int64_t)warp * O + o] = tot + b3[(int64_t)wg * O + o];
+    for (int i = 0; i < 32; ++i) {
+      const int h = lane + 32 * i;
+      if (h < H) acc = fmaf(hv[i], W3s[o * H + h], acc);
+    }
+    acc = warp_sum(acc) + b3[(int64_t)wg * O + o];
+    if (lane == o) outv = acc;
+  }
+  if (row_ok && lane < O && y) y[((int64_t)g * B + b) * O + lane] = outv;
+  if (epi.kind == 1) {
+    // a = tanh(mu + eps*std), logp = sum_j [Normal.log_prob(x_j) - log|d tanh|]
+    const int A = epi.A;
+    const float mu = __shfl_sync(0xffffffffu, outv, lane < A ? lane : 0);
+    const float raw = __shfl_sync(0xffffffffu, outv, lane < A ? A + lane : 0);
+    float lp = 0.f;
+    if (row_ok && lane < A) {
+      const float e = epi.eps[(int64_t)b * A + lane];
+      const float t_raw = tanhf(raw);
+      const float log_std = epi.lo + 0.5f * (epi.hi - epi.lo) * (t_raw + 1.f);
+      const float sd = expf(log_std);
+      const float x = mu + e * sd;
+      const float av = tanhf(x);
+      const float ladj = 2.f * (SSAC_LOG2F - x - softplus_th(-2.f * x));
+      const float dxm = x - mu;
+      lp = (0.f - ladj) + (-(dxm * dxm) / (2.f * (sd * sd)) - logf(sd) - SSAC_LOG_SQRT_2PIF);
+      if (epi.a) epi.a[(int64_t)b * epi.lda + lane] = av;
+    }
+    lp = warp_sum(lp);
+    if (row_ok && lane == 0 && epi.logp) epi.logp[b] = lp;
+  } else if (epi.kind == 2) {
+    if (row_ok && lane < epi.A) {
+      const int64_t i = (int64_t)b * epi.A + lane;
+      const float th = tanhf(outv);
+      if (epi.tanh_out) epi.tanh_out[i] = th;
+      float v = th;
+      if (epi.eps) v = __fadd_rn(v, __fmul_rn(epi.eps[i], 1e-4f));
+      if (epi.noise) {
+        float nz = __fmul_rn(epi.sigma, epi.noise[i]);
+        if (epi.clip > 0.f) nz = fminf(fmaxf(nz, -epi.clip), epi.clip);
+        v = __fadd_rn(v, nz);
+        v = fminf(fmaxf(v, __fadd_rn(-1.f, 1e-6f)), __fadd_rn(1.f, -1e-6f));
+      }
+      epi.a[(int64_t)b * epi.lda + lane] = v;
+    }
+  } else if (epi.kind == 3) {
+    // dq = -2 w imp (y - q') popw / (B E N_total);  loss += w imp (y - q')^2 / (B E N_total)
+    float l = 0.f, tdv = 0.f;
+    if (row_ok && lane == 0) {
+      const float pw = (epi.popart && epi.pop) ? epi.popart[2] : 1.f, pb = (epi.popart && epi.pop) ? epi.popart[3] : 0.f;
+      const float qq = (epi.popart && epi.pop) ? __fadd_rn(__fmul_rn(pw, outv), pb) : outv;
+      const float td = epi.y[b] - qq;
+      const float ww = (epi.w ? epi.w[b] : 1.f) * (epi.imp ? epi.imp[b] : 1.f);
+      epi.dq[(int64_t)g * B + b] = -2.f * ww * td * pw * epi.inv_count;
+      l = ww * td * td * epi.inv_count;
+      tdv = td;
+      red[0][warp] = l;
+      red[1][warp] = tdv;
+    } else if (lane == 0) {
+      red[0][warp] = 0.f;
+      red[1][warp] = 0.f;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && epi.loss) {
+      float sl = 0.f, st = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { sl += red[0][k]; st += red[1][k]; }
+      atomicAdd(&epi.loss[0], sl);
+      if (g == G - 1) atomicAdd(&epi.loss[1], st / (float)B);
     }
   }
 }
@@ -207,13 +281,18 @@ __global__ void __launch_bounds__(256) head_backward_weight_kernel(const float* 
 }
 
 int head_forward(const float* h2, const float* W3, const float* b3, const int32_t* net_index, int G, int B, int H, int O,
-                 float* y, cudaStream_t s) {
-  const int64_t warps = (int64_t)G * B;
-  const unsigned grid = (unsigned)((warps * 32 + 255) / 256);
-  if (O <= 2) head_forward_kernel<2><<<grid, 256, 0, s>>>(h2, W3, b3, net_index, G, B, H, O, y);
-  else if (O <= 8) head_forward_kernel<8><<<grid, 256, 0, s>>>(h2, W3, b3, net_index, G, B, H, O, y);
-  else if (O <= 16) head_forward_kernel<16><<<grid, 256, 0, s>>>(h2, W3, b3, net_index, G, B, H, O, y);
-  else head_forward_kernel<32><<<grid, 256, 0, s>>>(h2, W3, b3, net_index, G, B, H, O, y);
+                 float* y, const HeadEpi* epi, cudaStream_t s) {
+  SSAC_REQUIRE(H <= 1024, "mlp head: hidden size > 1024 is not supported by the narrow-head kernel");
+  HeadEpi e;
+  if (epi) e = *epi; else { memset(&e, 0, sizeof(e)); }
+  const size_t smem = (size_t)O * H * sizeof(float);
+  static bool attr_set = false;
+  if (smem > 48 * 1024 && !attr_set) {
+    cudaFuncSetAttribute(head_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+    attr_set = true;
+  }
+  dim3 grid((B + 7) / 8, G);
+  head_forward_kernel<<<grid, 256, smem, s>>>(h2, W3, b3, net_index, G, B, H, O, y, e);
   SSAC_CHECK_LAUNCH("mlp head forward");
   return 0;
 }
@@ -257,8 +336,9 @@ static GemmP blank() {
 
 int mlp_forward_simt(const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
                      const float* b3, const int32_t* net_index, int G, int D, int H, int O, const float* x, int64_t ldx,
-                     int64_t x_gs, int B, float* h1, float* h2, float* y, cudaStream_t s, int impl) {
+                     int64_t x_gs, int B, float* h1, float* h2, float* y, cudaStream_t s, int impl, const HeadEpi* epi) {
   SSAC_REQUIRE(h1 && h2, "ssac_mlp_forward: h1/h2 buffers are required");
+  SSAC_REQUIRE(!epi || O <= kSmallO, "fused head epilogues need O <= 32");
   g_impl = impl;
   GemmP p = blank();
   // layer 1: h1 = relu(x W1^T + b1)
@@ -272,7 +352,7 @@ int mlp_forward_simt(const float* W1, const float* b1, const float* W2, const fl
   rc = launch_gemm(L_NT, p, G, s, "mlp_forward L2");
   if (rc) return rc;
   // layer 3: y = h2 W3^T + b3
-  if (O <= kSmallO) return head_forward(h2, W3, b3, net_index, G, B, H, O, y, s);
+  if (O <= kSmallO) return head_forward(h2, W3, b3, net_index, G, B, H, O, y, epi, s);
   p.A = h2; p.Bm = W3; p.ldb = H; p.b_gs = (int64_t)O * H; p.C = y; p.ldc = O; p.c_gs = (int64_t)B * O;
   p.bias = b3; p.bias_gs = O; p.relu = 0; p.N = O; p.K = H;
   return launch_gemm(L_NT, p, G, s, "mlp_forward L3");

@@ -33,18 +33,21 @@ def critic_update(buffer, agent, target_agent, critic_optimizer, encoder_optimiz
     E, N, B = agent.ensemble_size, agent.num_critics, batch_size
     S, A = lu._dims(agent)
     logs = _logs.DeviceLogs(dev)
-    loss_v, loss_slot = logs.slots(2)
+    loss_all, loss_slot = logs.slots(2 * E)   # per member: {loss contribution, mean td error of its last net}
     opt = _arena.FlatAdam.attach(critic_optimizer, ca)
     if parallel.is_sharded() and (E != 1 or dr3_coeff > 0 or critic_clip):
         raise NotImplementedError("critic sharding covers the REDQ shape (one member, no DR3 / global-norm clip)")
 
     replay_dicts, enc_outs = [], []
     for i in range(E):
-        rd = lu.sample_move_and_augment(buffer=buffer, batch_size=B, augmenter=augmenter, aug_mix=aug_mix, per=per)
+        loss_v = loss_all[2 * i:2 * i + 2]
+        draws = lu.draw_for_critic_member(buffer, agent, B, target_critic_ensemble_n, random_process, per)
+        rd = lu.sample_move_and_augment(buffer=buffer, batch_size=B, augmenter=augmenter, aug_mix=aug_mix, per=per,
+                                        _idx=draws["idx"])
         td_target, (s1, a1) = lu.compute_td_targets(
             logs=logs, replay_dict=rd, agent=agent, target_agent=target_agent, log_alphas=log_alphas, ensemble_idx=i,
             ensemble_n=target_critic_ensemble_n, pop=pop, gamma=gamma, random_process=random_process,
-            noise_clip=noise_clip)
+            noise_clip=noise_clip, _draws=draws)
         w = lu.compute_backup_weights(logs=logs, replay_dict=rd, agent=agent, target_agent=target_agent,
                                       weight_type=weight_type, weight_temp=weighted_bellman_temp, batch_size=B)
         o, a, *_ = rd["primary_batch"]
@@ -52,15 +55,20 @@ def critic_update(buffer, agent, target_agent, critic_optimizer, encoder_optimiz
         s_rep = agent.encoder(o)
         need_ds = _encoder_has_grad_path(s_rep)
         X = lu._first_layer_input(s_rep, a, packed["XA"] if packed else None, S, A)
-        q, h1, h2 = lu._critic_values(agent, i * N, N, X, B, keep=True)
         popart = agent.popart[i]
+        h1 = torch.empty((N, B, ca.H), dtype=torch.float32, device=dev)
+        h2 = torch.empty_like(h1)
+        q = torch.empty((N, B, 1), dtype=torch.float32, device=dev)
         dq = torch.empty((N, B, 1), dtype=torch.float32, device=dev)
         imp = rd["imp_weights"]
         imp_ptr = imp.float().contiguous() if per else None  # per=False: ones(1), i.e. no weighting (main.py:401)
         n_total = parallel.n_global() if parallel.is_sharded() else 0   # sharded critics: normalise by the global N
-        L.critic_loss_seed(q.data_ptr(), N, B, td_target.data_ptr(), w.data_ptr() if torch.is_tensor(w) else None,
-                           None if imp_ptr is None else imp_ptr.data_ptr(), popart.state_ptr() if popart else None,
-                           int(bool(pop)), E, n_total, dq.data_ptr(), loss_v.data_ptr(), stream)
+        # N critic forwards + loss value + seed gradient dL/dq in one entry point (loss seed fused into the head kernel)
+        W1, b1, W2, b2, W3, b3 = ca.ptrs(i * N)
+        L.critic_forward_loss(W1, b1, W2, b2, W3, b3, N, ca.D, ca.H, X.data_ptr(), S + A, B, h1.data_ptr(), h2.data_ptr(),
+                              q.data_ptr(), td_target.data_ptr(), w.data_ptr() if torch.is_tensor(w) else None,
+                              None if imp_ptr is None else imp_ptr.data_ptr(), popart.state_ptr() if popart else None,
+                              int(bool(pop)), E, n_total, dq.data_ptr(), loss_v.data_ptr(), 0, stream)
         extra, extra_scale, f1 = None, 0.0, None
         if dr3_coeff > 0:
             # DR3 (learning.py:100-108): second forward on (s1, a1); both feature sets carry gradient
@@ -95,9 +103,9 @@ def critic_update(buffer, agent, target_agent, critic_optimizer, encoder_optimiz
     opt.step(stream, max_norm=critic_clip if critic_clip else None)
 
     if parallel.is_sharded():
-        parallel.all_reduce_sum_(loss_v[0:1])   # each rank summed its own critics
-    logs.defer("losses/last_member_critic_td_error", loss_slot + 1)
-    logs.defer("losses/critic_overall_loss", loss_slot)
+        parallel.all_reduce_sum_(loss_all[0:1])   # each rank summed its own critics
+    logs.defer("losses/last_member_critic_td_error", loss_slot + 2 * (E - 1) + 1)
+    logs.defer("losses/critic_overall_loss", [loss_slot + 2 * i for i in range(E)])
     member = random.choice(range(E))
     gslot = lu._member_grad_norm_slot(logs, ca, member * N, (member + 1) * N)
     logs.defer("gradients/critic_random_grad", gslot, transform=lambda v: v**0.5)

@@ -180,7 +180,7 @@ def _pixel_gather(stack, idx, shift, aug, B, aug_rows, use_aug):
     return out
 
 
-def sample_move_and_augment(buffer, batch_size, augmenter, aug_mix, per=True):
+def sample_move_and_augment(buffer, batch_size, augmenter, aug_mix, per=True, _idx=None):
     """Sample a batch on the device, cast to fp32, augment o and o1 with shared parameters and mix the first
     int(B*aug_mix) augmented rows into the batch (reference learning_utils.py:174-214)."""
     assert len(buffer) >= batch_size
@@ -189,7 +189,7 @@ def sample_move_and_augment(buffer, batch_size, augmenter, aug_mix, per=True):
     if per:
         idx, imp_weights = buffer.sample_indices_per(B)
     else:
-        idx = buffer.sample_indices_uniform(B)
+        idx = _idx if _idx is not None else buffer.sample_indices_uniform(B)
         imp_weights = _ones1(dev)
     aug_rows = int(B * aug_mix)
     fused = isinstance(augmenter, augmentations.AugmentationSequence) and augmenter.fusable()
@@ -319,42 +319,51 @@ def _actor_forward(agent, i, X, B, S, A, keep=False):
     return out, h1, h2
 
 
-def _policy_sample(agent, i, X, B, S, A, random_process, noise_clip, rsample=False):
-    """a ~ pi_i(.|s) written into X[:, S:], with log-prob [B] (None when a noise process replaces the entropy term).
-    Returns dict(out, h1, h2, eps, logp, tanh_out)."""
+def _policy_sample(agent, i, X, B, S, A, random_process, noise_clip, rsample=False, eps=None, noise=None):
+    """a ~ pi_i(.|s) written into X[:, S:], with log-prob [B] (None when a noise process replaces the entropy term):
+    actor MLP + policy head in one entry point (the head is fused into the output-layer kernel).  ``eps`` / ``noise``:
+    pre-drawn N(0,1) tensors (drawn here otherwise).  Returns dict(out, h1, h2, eps, logp, tanh_out)."""
     dev = X.device
-    out, h1, h2 = _actor_forward(agent, i, X, B, S, A)
+    arena = agent._actor_arena
+    h1 = torch.empty((1, B, arena.H), dtype=torch.float32, device=dev)
+    h2 = torch.empty_like(h1)
+    out = torch.empty((1, B, arena.O), dtype=torch.float32, device=dev)
     a_dst = X[:, S:]
-    L, s = _lib.lib(), _lib.stream_ptr()
     res = dict(out=out, h1=h1, h2=h2, eps=None, logp=None, tanh_out=None)
-    if agent.deterministic:
-        eps = noise = None
-        if rsample:  # Normal(loc, 1e-4).rsample() of the reference's deterministic "distribution"
+    det = agent.deterministic
+    sigma, clip, tanh_out, logp = 0.0, 0.0, None, None
+    if det:
+        if rsample and eps is None:  # Normal(loc, 1e-4).rsample() of the reference's deterministic "distribution"
             eps = torch.empty((B, A), dtype=torch.float32, device=dev)
             _rng.source().normal(eps)
-        sigma, clip = 0.0, 0.0
+        if not rsample:
+            eps = None
         if random_process is not None:
-            noise = torch.empty((B, A), dtype=torch.float32, device=dev)
-            _rng.source().normal(noise)
+            if noise is None:
+                noise = torch.empty((B, A), dtype=torch.float32, device=dev)
+                _rng.source().normal(noise)
             sigma = float(random_process.current_scale)
             clip = float(noise_clip) if noise_clip is not None else 0.0
+        else:
+            noise = None
         tanh_out = torch.empty((B, A), dtype=torch.float32, device=dev)
-        L.det_head_forward(out.data_ptr(), None if eps is None else eps.data_ptr(),
-                           None if noise is None else noise.data_ptr(), B, A, sigma, clip, a_dst.data_ptr(), S + A,
-                           tanh_out.data_ptr(), s)
-        res.update(eps=eps, tanh_out=tanh_out)
-        if random_process is None:
-            # Normal(loc, 1e-4).log_prob(loc) summed over A: a constant (nets/distributions.py:107-114)
-            res["logp"] = torch.full((B,), A * (0.0 - math.log(1e-4) - LOG_SQRT_2PI), dtype=torch.float32, device=dev)
     else:
         if random_process is not None:
             raise NotImplementedError("an exploration-noise process on top of a stochastic actor is not supported")
-        eps = torch.empty((B, A), dtype=torch.float32, device=dev)
-        _rng.source().normal(eps)
+        if eps is None:
+            eps = torch.empty((B, A), dtype=torch.float32, device=dev)
+            _rng.source().normal(eps)
+        noise = None
         logp = torch.empty((B,), dtype=torch.float32, device=dev)
-        L.tanh_normal_forward(out.data_ptr(), eps.data_ptr(), B, A, float(agent.log_std_low), float(agent.log_std_high),
-                              a_dst.data_ptr(), S + A, logp.data_ptr(), s)
-        res.update(eps=eps, logp=logp)
+    W1, b1, W2, b2, W3, b3 = arena.ptrs(i)
+    _lib.lib().actor_forward_sample(W1, b1, W2, b2, W3, b3, arena.D, arena.H, A, int(det), X.data_ptr(), S + A, B,
+                                    h1.data_ptr(), h2.data_ptr(), out.data_ptr(), _ops._p(eps), _ops._p(noise), sigma, clip,
+                                    float(agent.log_std_low), float(agent.log_std_high), a_dst.data_ptr(), S + A,
+                                    _ops._p(logp), _ops._p(tanh_out), 0, _lib.stream_ptr())
+    res.update(eps=eps, logp=logp, tanh_out=tanh_out)
+    if det and random_process is None:
+        # Normal(loc, 1e-4).log_prob(loc) summed over A: a constant (nets/distributions.py:107-114)
+        res["logp"] = torch.full((B,), A * (0.0 - math.log(1e-4) - LOG_SQRT_2PI), dtype=torch.float32, device=dev)
     return res
 
 
@@ -376,8 +385,24 @@ def _dims(agent):
     return agent._actor_arena.D, agent.act_space_size
 
 
+def draw_for_critic_member(buffer, agent, B, ensemble_n, random_process, per):
+    """Every random draw one member's critic update consumes up front -- replay indices (replay.py:122), the policy's
+    N(0,1) draw or the TD3 noise (learning_utils.py:49,330), the REDQ target subset (agent.py:29) -- in ONE launch."""
+    dev = buffer.device
+    S, A = _dims(agent)
+    n_sub_pool = parallel.n_global() if parallel.is_sharded() else agent.num_critics
+    assert 0 < ensemble_n <= n_sub_pool
+    idx = None if per else torch.empty(B, dtype=torch.int64, device=dev)
+    need_normal = (not agent.deterministic) or (random_process is not None)
+    normal = torch.empty((B, A), dtype=torch.float32, device=dev) if need_normal else None
+    subset = torch.empty(ensemble_n, dtype=torch.int32, device=dev)
+    _rng.source().fill(dev, idx=idx, n_filled=len(buffer), n_filled_dev=buffer._n_filled_dev, normal=normal,
+                       subset=subset, N=n_sub_pool, M=ensemble_n)
+    return dict(idx=idx, normal=normal, subset=subset)
+
+
 def compute_td_targets(logs, replay_dict, agent, target_agent, ensemble_idx, ensemble_n, log_alphas, pop, gamma,
-                       random_process, noise_clip, discrete=False):
+                       random_process, noise_clip, discrete=False, _draws=None):
     """TD target of one ensemble member (reference learning_utils.py:298-354, continuous branch).
     Returns ``td_target [B,1], (s1_rep, a_s1)``."""
     if discrete:
@@ -392,20 +417,25 @@ def compute_td_targets(logs, replay_dict, agent, target_agent, ensemble_idx, ens
     with torch.no_grad():
         s1_rep = target_agent.encoder(o1)
     X1 = _first_layer_input(s1_rep, None, packed["X1"] if packed else None, S, A)
-    pol = _policy_sample(agent, i, X1, B, S, A, random_process, noise_clip)
     N = agent.num_critics
-    net_index = torch.empty(ensemble_n, dtype=torch.int32, device=X1.device)
+    # REDQ subset: drawn over the GLOBAL ensemble when the critics are sharded over ranks (replicated Philox state)
+    pool = parallel.n_global() if parallel.is_sharded() else N
+    assert 0 < ensemble_n <= pool
+    if _draws is not None:   # critic_update drew indices, policy noise and the subset in ONE launch
+        pol = _policy_sample(agent, i, X1, B, S, A, random_process, noise_clip,
+                             eps=None if agent.deterministic else _draws["normal"],
+                             noise=_draws["normal"] if agent.deterministic else None)
+        net_index = _draws["subset"]
+    else:
+        pol = _policy_sample(agent, i, X1, B, S, A, random_process, noise_clip)
+        net_index = torch.empty(ensemble_n, dtype=torch.int32, device=X1.device)
+        _rng.source().subsets(net_index, pool, ensemble_n)
     if parallel.is_sharded():
-        # every rank draws the same subset of the GLOBAL ensemble (replicated Philox state), evaluates its own target
-        # critics and all-gathers the [N_global, B] values; the subset-min is then identical on every rank
-        Ng = parallel.n_global()
-        assert 0 < ensemble_n <= Ng
-        _rng.source().subsets(net_index, Ng, ensemble_n)
+        # every rank evaluates its own target critics and all-gathers the [N_global, B] values; the subset-min is then
+        # identical on every rank
         q_all = parallel.all_gather_q(_critic_values(target_agent, i * N, N, X1, B))
         q_t = q_all.index_select(0, net_index.long())
     else:
-        assert 0 < ensemble_n <= N
-        _rng.source().subsets(net_index, N, ensemble_n)
         q_t = _critic_values(target_agent, i * N, ensemble_n, X1, B, net_index=net_index)
     y = torch.empty((B, 1), dtype=torch.float32, device=X1.device)
     lv, slot = dlogs.slots(3)
