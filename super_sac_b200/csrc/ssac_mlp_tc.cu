@@ -29,6 +29,16 @@
 namespace ssac {
 namespace tc {
 
+#ifdef SSAC_TRACE
+__device__ long long* g_trace = nullptr;
+#define TRACE(slot)                                                                                   \
+  do {                                                                                                \
+    if (g_trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_trace[slot] = clock64(); \
+  } while (0)
+#else
+#define TRACE(slot) do {} while (0)
+#endif
+
 constexpr int TM = 128;      // MMA M (one CTA, cta_group::1)
 constexpr int TN = 128;      // tile N (MMA N = 16..128, multiple of 16)
 constexpr int TK = 32;       // k per pipeline stage (4 MMA k-steps of 8) = one 128-byte swizzle row
@@ -41,8 +51,8 @@ constexpr int kSmemBytes = kStages * kStageBytes + 1024;   // + slack for 1024-b
 
 struct GemmTC {
   GemmP p;
-  CUtensorMap tmA, tmB;   // valid when a_tma / b_tma
-  int a_tma, b_tma;
+  CUtensorMap tmA, tmB, tmC;   // valid when a_tma / b_tma / c_tma
+  int a_tma, b_tma, c_tma;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -85,6 +95,16 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const CUtensorMap
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src_smem, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_and_wait_read() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 // ---- tensor memory / tcgen05 -------------------------------------------------------------------------------------
@@ -225,7 +245,9 @@ __global__ void __launch_bounds__(kThreads, 1) grouped_gemm_tc_kernel(const __gr
   __shared__ __align__(8) uint64_t bar_empty[kStages];   // tensor core -> producers: the MMAs reading stage s are done
   __shared__ __align__(8) uint64_t bar_done;
   __shared__ uint32_t tmem_base_sh;
+  __shared__ float bias_sh[TN];
 
+  if (threadIdx.x == 0) TRACE(0);
   const GemmP& p = q.p;
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle atoms need 1024-byte alignment
   constexpr bool A_MN = (LAYOUT == L_TN);   // A given as [K][M]
@@ -255,11 +277,13 @@ __global__ void __launch_bounds__(kThreads, 1) grouped_gemm_tc_kernel(const __gr
     mbar_init(&bar_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (t < TN) bias_sh[t] = (p.bias && n0 + t < p.N) ? __ldg(p.bias + (int64_t)wg * p.bias_gs + n0 + t) : 0.f;
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_d = tmem_base_sh;
   const int nk = (p.K + TK - 1) / TK;
+  if (threadIdx.x == 0) TRACE(1);
 
   if (warp == 9) {
     // ===== TMA producer ===========================================================================================
@@ -346,8 +370,10 @@ __global__ void __launch_bounds__(kThreads, 1) grouped_gemm_tc_kernel(const __gr
       const int s = kc % kStages, use = kc / kStages;
       uint8_t* st = smem + s * kStageBytes;
       uint8_t *a_hi = st, *a_lo = st + kPlaneBytes, *b_hi = st + 2 * kPlaneBytes, *b_lo = st + 3 * kPlaneBytes;
+      if (t == 0 && kc < 8) TRACE(2 + 3 * kc);
       if (any_tma) mbar_wait(&bar_raw[s], (uint32_t)(use & 1));                   // raw tiles landed (=> stage was free)
       else if (kc >= kStages) mbar_wait(&bar_empty[s], (uint32_t)((use - 1) & 1));  // no TMA operand: wait for the MMAs
+      if (t == 0 && kc < 8) TRACE(3 + 3 * kc);
       if (a_tma) {
         // lo pass: same (swizzled) offsets in and out, 4 x 16 bytes per thread
 #pragma unroll
@@ -380,10 +406,73 @@ __global__ void __launch_bounds__(kThreads, 1) grouped_gemm_tc_kernel(const __gr
       }
       fence_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
       mbar_arrive(&bar_full[s]);
+      if (t == 0 && kc < 8) TRACE(4 + 3 * kc);
     }
+    if (t == 0) TRACE(30);
     if (nk > 0) mbar_wait(&bar_done, 0);
     fence_after_sync();
+    if (t == 0) TRACE(31);
 
+    if (q.c_tma) {
+      // ---- epilogue A (no mask / extra / accumulate): bias + ReLU in registers (thread = accumulator row), tile
+      // written in the SWIZZLE_128B layout of a [32 col x 128 row] TMA box per column block, then ONE thread issues
+      // cp.async.bulk.tensor stores; rows / columns beyond M / N are clipped by the tensor map.
+      const int qd = warp & 3, row = qd * 32 + lane;
+      const uint32_t r7 = (uint32_t)(row & 7);
+      for (int c0 = (warp >> 2) * 32; c0 < n_mma; c0 += 64) {
+        float v[32];
+        if (nk > 0) {
+          tmem_ld32(tmem_d + ((uint32_t)(qd * 32) << 16) + (uint32_t)c0, v);   // warp-collective
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+        uint8_t* box = smem + (c0 >> 5) * kPlaneBytes + (uint32_t)(row >> 3) * 1024u + r7 * 128u;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float4 o;
+          o.x = v[4 * c + 0] + bias_sh[c0 + 4 * c + 0]; o.y = v[4 * c + 1] + bias_sh[c0 + 4 * c + 1];
+          o.z = v[4 * c + 2] + bias_sh[c0 + 4 * c + 2]; o.w = v[4 * c + 3] + bias_sh[c0 + 4 * c + 3];
+          if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          *reinterpret_cast<float4*>(box + (((uint32_t)c ^ r7) << 4)) = o;
+        }
+      }
+      if (do_colsum) {
+        float* part = reinterpret_cast<float*>(smem + 96 * 1024);
+        if (a_tma) {
+          const int kr = (t >> 3) & 3;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int mbase = 32 * i + ((((t & 7) >> 1) ^ kr) << 3) + ((t & 1) << 2);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) part[(t >> 3) * TM + mbase + e] = cs[4 * i + e];
+          }
+        } else {
+          const int mbase = 4 * (t & 31);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) part[(t >> 5) * TM + mbase + e] = cs[e];
+        }
+      }
+      fence_async_smem();
+      workers_sync();
+      if (t == 0) {
+        const int cz = (LAYOUT == L_TN) ? wg : g;
+        for (int c0 = 0; c0 < n_mma; c0 += 32)
+          if (n0 + c0 < p.N) tma_store_3d(&q.tmC, smem_u32(smem) + (uint32_t)((c0 >> 5) * kPlaneBytes), n0 + c0, m0, p.c_gs ? cz : 0);
+        tma_store_commit_and_wait_read();
+      }
+      if (do_colsum) {
+        const float* part = reinterpret_cast<const float*>(smem + 96 * 1024);
+        const int n_slots = a_tma ? 32 : 8;
+        const int mm = m0 + t;
+        if (t < TM && mm < p.M) {
+          float tot = 0.f;
+          for (int sl = 0; sl < n_slots; ++sl) tot += part[sl * TM + t];
+          float* out = p.colsum + (int64_t)wg * p.colsum_gs;
+          out[mm] = p.accumulate ? (out[mm] + tot) : tot;
+        }
+      }
+    } else {
     // ---- epilogue -----------------------------------------------------------------------------------------
     // phase 1: thread = accumulator row (TMEM lane quarter warp%4, column half warp/4) -> padded fp32 tile in
     //          shared memory (the stage buffers are free: every MMA has completed).
@@ -426,6 +515,7 @@ __global__ void __launch_bounds__(kThreads, 1) grouped_gemm_tc_kernel(const __gr
       }
     }
     workers_sync();
+    if (t == 0) TRACE(32);
     {
       float* C = p.C + (int64_t)(LAYOUT == L_TN ? wg : g) * p.c_gs;
       const float* mask = p.mask ? p.mask + (int64_t)g * p.mask_gs : nullptr;
@@ -495,10 +585,13 @@ __global__ void __launch_bounds__(kThreads, 1) grouped_gemm_tc_kernel(const __gr
         out[mm] = p.accumulate ? (out[mm] + tot) : tot;
       }
     }
+    }  // epilogue B
   }
+  if (t == 0) TRACE(33);
   fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_d, tmem_cols);
+  if (t == 0) TRACE(34);
 }
 
 }  // namespace tc
@@ -562,6 +655,10 @@ bool make_map(const float* base, int64_t ld, int64_t gs, int inner, int outer, b
 
 }  // namespace
 
+#ifdef SSAC_TRACE
+extern "C" int ssac_debug_set_trace(long long* dev_ptr) { return (int)cudaMemcpyToSymbol(tc::g_trace, &dev_ptr, sizeof(dev_ptr)); }
+#endif
+
 static bool g_tma_enabled = true;
 extern "C" int ssac_set_tma_enabled(int on) {
   g_tma_enabled = on != 0;
@@ -583,7 +680,7 @@ int launch_gemm_tc(int layout, const GemmP& p, int G, cudaStream_t s, const char
   }
   tc::GemmTC q;
   q.p = p;
-  q.a_tma = q.b_tma = 0;
+  q.a_tma = q.b_tma = q.c_tma = 0;
   if (g_tma_enabled && p.K > 0) {
     const bool a_mn = layout == L_TN, b_mn = layout != L_NT;
     // group strides are baked into the maps; base pointers are the group-0 matrices
@@ -591,6 +688,7 @@ int launch_gemm_tc(int layout, const GemmP& p, int G, cudaStream_t s, const char
     else q.a_tma = make_map(p.A, p.lda, p.a_gs, p.K, p.M, false, &q.tmA);
     if (b_mn) q.b_tma = make_map(p.Bm, p.ldb, p.b_gs, p.N, p.K, true, &q.tmB);
     else q.b_tma = make_map(p.Bm, p.ldb, p.b_gs, p.K, p.N, false, &q.tmB);
+    if (!p.mask && !p.extra && !p.accumulate) q.c_tma = make_map(p.C, p.ldc, p.c_gs, p.N, p.M, false, &q.tmC);
   }
   dim3 grid((p.N + tc::TN - 1) / tc::TN, (p.M + tc::TM - 1) / tc::TM, G);
   if (layout == L_NT) tc::grouped_gemm_tc_kernel<L_NT><<<grid, tc::kThreads, tc::kSmemBytes, s>>>(q);

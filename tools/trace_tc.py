@@ -2,7 +2,8 @@ import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 import torch
 lib = ctypes.CDLL(os.path.join(ROOT, "super_sac_b200", "libssac_b200_trace.so"))
-G, D, H, O, B = 10, 256, 256, 1, 256
+import sys as _s
+G, D, H, O, B = 10, int(_s.argv[1]) if len(_s.argv) > 1 else 256, 256, 1, 256
 dev = "cuda"
 trace = torch.zeros(64, dtype=torch.int64, device=dev)
 lib.ssac_debug_set_trace.argtypes = [ctypes.c_void_p]
@@ -18,8 +19,8 @@ for it in range(3):
 t = trace.cpu().tolist()
 print("rc", rc)
 base = t[0]
-names = {0: "entry", 1: "setup done", 40: "loop done", 41: "mma done", 42: "tile in smem", 43: "stored", 44: "exit"}
+names = {0: "entry", 1: "setup done", 30: "loop done", 31: "mma done", 32: "tile in smem", 33: "stored", 34: "exit"}
 for i in range(45):
     if t[i]:
-        nm = names.get(i) or {2: "iter start", 3: "stage free", 0: "staged", 1: "synced"}[(i - 2) % 4 + 2 if (i-2)%4 < 2 else (i-2)%4 - 2] + f" kc={(i-2)//4}"
+        nm = names.get(i) or ["iter start", "raw landed", "arrived full"][(i - 2) % 3] + f" kc={(i-2)//3}"
         print(f"{i:3d} {nm:24s} {t[i]-base:8d} cycles")
