@@ -285,7 +285,6 @@ def run_gpu_arm(args, cfg, rank, world, local_rank):
     # ---- e2e through the drop-in API with host inputs ---------------------------------------------
     e2e_steps = min(args.steps, 2000)
     hs, ha, hr, hs1, hd = synthetic_transitions(cfg, 4096, seed=123 + rank)
-    h2d = hs[0].nbytes + hs1[0].nbytes + ha[0].nbytes + 4 + 1 + 16  # transition + (index, priority) of the PER trees
 
     def e2e_step(k):
         j = k % 4096
@@ -295,9 +294,13 @@ def run_gpu_arm(args, cfg, rank, world, local_rank):
             polyak()
         return logs
 
-    for k in range(5):
+    graphed.enable_auto_graphs(True)   # the drop-in calls below replay captured graphs from their third call on
+    eager_logs = learning._critic_update_impl(**kw)[0]
+    d2h = 4 * eager_logs._n
+    for k in range(6):
         logs = e2e_step(k)
-    d2h = 4 * logs._n
+    # one pinned staging row per pushed transition: s, s1, a, r, d, tree index, priority, fill level (16-byte aligned)
+    h2d = buf._stage_bytes
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
@@ -341,7 +344,8 @@ def run_gpu_arm(args, cfg, rank, world, local_rank):
                    "impl": "ensemble MLP GEMMs: " + ssb.get_mlp_impl()},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "steps": e2e_steps, "path": "buffer.push(host transition) + learning.critic_update + soft_update + logs readback"},
+                "steps": e2e_steps, "path": "buffer.push(host transition, H2D) + learning.critic_update (auto CUDA graph) + "
+                                            "soft_update + logged scalars read back (D2H)"},
         "gpu_launches": int(round(launch_count * args.steps)),
         "gpu_launches_per_step": launch_count,
         "roofline": roofline,
@@ -369,7 +373,7 @@ def count_launches(fn, _lib):
     from super_sac_b200 import _lib as L
 
     lib = L.lib()
-    per_call = {"mlp_forward": 3, "polyak": 1, "polyak_multi": 1, "adam_step": 1, "adam_polyak_step": 1, "sumsq": 1,
+    per_call = {"mlp_forward": 3, "actor_forward_sample": 3, "critic_forward_loss": 3, "scatter_fields": 1, "polyak": 1, "polyak_multi": 1, "adam_step": 1, "adam_polyak_step": 1, "sumsq": 1,
                 "rng_fill": 1, "gather_rows": 1, "gather_aug_u8": 1, "tanh_normal_forward": 1, "td_target": 1,
                 "critic_loss_seed": 1, "backup_weights": 1, "tree_set": 1, "tree_sample": 1}
     counter = {"n": 0}

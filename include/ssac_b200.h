@@ -82,6 +82,11 @@ int ssac_rng_fill(uint64_t* rng_dev, int64_t* idx_dev, int64_t n_idx, int64_t n_
 int ssac_gather_rows(const void* const* srcs_dev, void* const* dsts_dev, const int64_t* row_elems,
                      const int64_t* dst_ld, const int32_t* mode, int n_arrays, const int64_t* idx_dev, int B,
                      void* stream);
+/* Ring write of one pushed transition (replay.py:48-61): the host packs every field (s, s1, action, reward, done, tree
+ * index / priority, fill level) into ONE pinned staging buffer that crosses PCIe with a single copy; this kernel then
+ * scatters field k (nbytes[k] bytes at staging_dev + src_off[k]) to dsts_dev[k].  Host arrays of n_fields (<= 16). */
+int ssac_scatter_fields(const void* staging_dev, void* const* dsts_dev, const int64_t* nbytes, const int64_t* src_off,
+                        int n_fields, void* stream);
 /* Fused pixel gather + DrQ / DrQv2 random shift + uint8 -> fp32 + aug_mix: augmentations.py:165-269,
  * learning_utils.py:193-206.   src u8 [capacity, C, H, W] -> dst f32 [B, C, H, W].
  * pad_mode 0: no shift, 1: replicate (DrQv2 integer crop), 2: reflect (DrQ v1).

@@ -193,6 +193,12 @@ class FlatAdam:
         else:
             _lib.lib().adam_step(a.flat.data_ptr(), a.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), a.numel,
                                  self.ctl.data_ptr(), lr, b1, b2, eps, wd, gptr, float(max_norm or 0.0), 1, stream)
+        if not torch.cuda.is_current_stream_capturing():   # a captured step executes (and is counted) at replay time
+            self.steps += 1
+            self._step_tensor.fill_(self.steps)
+
+    def note_replayed_step(self):
+        """A captured graph containing this optimiser's step was replayed: the device counter advanced by itself."""
         self.steps += 1
         self._step_tensor.fill_(self.steps)
 

@@ -136,6 +136,24 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(GatherArgs args, const
   }
 }
 
+struct ScatterArgs {
+  void* dst[kMaxGatherArrays];
+  int64_t nbytes[kMaxGatherArrays];
+  int64_t src_off[kMaxGatherArrays];
+};
+__global__ void __launch_bounds__(256) scatter_fields_kernel(const uint8_t* __restrict__ staging, ScatterArgs a) {
+  const int k = blockIdx.y;
+  const uint8_t* src = staging + a.src_off[k];
+  uint8_t* dst = (uint8_t*)a.dst[k];
+  const int64_t n = a.nbytes[k];
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  if (((((uintptr_t)src) | ((uintptr_t)dst) | (uintptr_t)n) & 15) == 0) {
+    for (int64_t i = tid; i < (n >> 4); i += nth) ((int4*)dst)[i] = ((const int4*)src)[i];
+  } else {
+    for (int64_t i = tid; i < n; i += nth) dst[i] = src[i];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // fused pixel gather + shift (+noise) + uint8->fp32: augmentations.py:165-269, learning_utils.py:193-206
 // One block per (sample, channel-plane): the u8 plane is staged in shared memory with 16-byte loads, then
@@ -349,6 +367,25 @@ int ssac_gather_rows(const void* const* srcs, void* const* dsts, const int64_t* 
   dim3 grid(gx, n_arrays);
   gather_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, idx, B);
   SSAC_CHECK_LAUNCH("ssac_gather_rows");
+  return 0;
+}
+
+int ssac_scatter_fields(const void* staging, void* const* dsts, const int64_t* nbytes, const int64_t* src_off,
+                        int n_fields, void* stream) {
+  SSAC_REQUIRE(staging && dsts && nbytes && src_off && n_fields > 0 && n_fields <= kMaxGatherArrays,
+               "ssac_scatter_fields: bad args (1..16 fields)");
+  ScatterArgs a;
+  int64_t mx = 0;
+  for (int k = 0; k < n_fields; ++k) {
+    SSAC_REQUIRE(dsts[k] && nbytes[k] > 0 && src_off[k] >= 0, "ssac_scatter_fields: bad field");
+    a.dst[k] = dsts[k]; a.nbytes[k] = nbytes[k]; a.src_off[k] = src_off[k];
+    if (nbytes[k] > mx) mx = nbytes[k];
+  }
+  int gx = (int)((mx / 16 + 255) / 256);
+  if (gx < 1) gx = 1;
+  if (gx > 64) gx = 64;
+  scatter_fields_kernel<<<dim3(gx, n_fields), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)staging, a);
+  SSAC_CHECK_LAUNCH("ssac_scatter_fields");
   return 0;
 }
 

@@ -10,7 +10,7 @@ import random
 
 import torch
 
-from . import _arena, _lib, _logs, _ops, _rng, parallel
+from . import _arena, _lib, _logs, _ops, _rng, graphed, parallel
 from . import learning_utils as lu
 
 
@@ -18,10 +18,46 @@ def _encoder_has_grad_path(s_rep):
     return torch.is_tensor(s_rep) and s_rep.requires_grad
 
 
+def _opt_sig(opt):
+    pg = opt.param_groups[0]
+    return (id(opt), pg["lr"], tuple(pg["betas"]), pg["eps"], pg["weight_decay"])
+
+
+def _graphable(agent, random_process, per, update_priorities):
+    """Static shapes, device-side randomness, no PyTorch autograd hand-off, no host-side decisions."""
+    return (graphed.auto_graphs_enabled() and isinstance(_rng.source(), _rng.PhiloxSource) and not per and
+            not update_priorities and random_process is None and not parallel.is_sharded() and
+            not any(p.requires_grad for p in agent.encoder.parameters() if p.numel() > 2))
+
+
 def critic_update(buffer, agent, target_agent, critic_optimizer, encoder_optimizer, log_alphas, batch_size, gamma,
                   critic_clip, encoder_clip, target_critic_ensemble_n, weighted_bellman_temp, weight_type, pop,
                   augmenter, encoder_lambda, random_process, noise_clip, aug_mix=0.75, discrete=False, per=False,
                   update_priorities=False, dr3_coeff=0.0):
+    """Drop-in for reference learning.py:18-141.  With ``graphed.enable_auto_graphs()`` repeated calls with the same
+    objects and hyper-parameters replay a captured CUDA graph."""
+    args = (buffer, agent, target_agent, critic_optimizer, encoder_optimizer, log_alphas, batch_size, gamma, critic_clip,
+            encoder_clip, target_critic_ensemble_n, weighted_bellman_temp, weight_type, pop, augmenter, encoder_lambda,
+            random_process, noise_clip, aug_mix, discrete, per, update_priorities, dr3_coeff)
+    if not discrete and not encoder_lambda and _graphable(agent, random_process, per, update_priorities):
+        key = ("critic", id(buffer), id(agent), id(target_agent), _opt_sig(critic_optimizer), id(encoder_optimizer),
+               tuple(id(l) for l in log_alphas), batch_size, gamma, critic_clip, encoder_clip, target_critic_ensemble_n,
+               weighted_bellman_temp, weight_type, pop, id(augmenter), noise_clip, aug_mix, dr3_coeff,
+               _lib.lib().default_mlp_impl())
+        opt = _arena.FlatAdam.attach(critic_optimizer, agent._critic_arena)
+
+        def on_replay():
+            opt.note_replayed_step()
+            buffer.total_sample_calls += agent.ensemble_size
+
+        return graphed.run_cached(key, lambda: _critic_update_impl(*args), on_replay)
+    return _critic_update_impl(*args)
+
+
+def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_optimizer, log_alphas, batch_size, gamma,
+                        critic_clip, encoder_clip, target_critic_ensemble_n, weighted_bellman_temp, weight_type, pop,
+                        augmenter, encoder_lambda, random_process, noise_clip, aug_mix=0.75, discrete=False, per=False,
+                        update_priorities=False, dr3_coeff=0.0):
     if discrete:
         raise NotImplementedError("discrete actions are out of scope")
     if encoder_lambda:
@@ -121,6 +157,22 @@ def critic_update(buffer, agent, target_agent, critic_optimizer, encoder_optimiz
 
 def online_actor_update(buffer, agent, pop, actor_optimizer, log_alphas, batch_size, clip, random_process, noise_clip,
                         augmenter, aug_mix, premade_replay_dicts=None, per=False, discrete=False, use_baseline=False):
+    """Drop-in for reference learning.py:344-421 (graph-replayed under ``graphed.enable_auto_graphs()`` when the replay
+    dicts come from a graph-replayed critic update, i.e. are the same static buffers on every call)."""
+    args = (buffer, agent, pop, actor_optimizer, log_alphas, batch_size, clip, random_process, noise_clip, augmenter,
+            aug_mix, premade_replay_dicts, per, discrete, use_baseline)
+    if (not discrete and not use_baseline and premade_replay_dicts is not None
+            and _graphable(agent, random_process, per, False)):
+        key = ("actor", id(agent), _opt_sig(actor_optimizer), tuple(id(l) for l in log_alphas), batch_size, clip, pop,
+               tuple(id(rd) for rd in premade_replay_dicts), _lib.lib().default_mlp_impl())
+        opt = _arena.FlatAdam.attach(actor_optimizer, agent._actor_arena)
+        return graphed.run_cached(key, lambda: _online_actor_update_impl(*args), opt.note_replayed_step)
+    return _online_actor_update_impl(*args)
+
+
+def _online_actor_update_impl(buffer, agent, pop, actor_optimizer, log_alphas, batch_size, clip, random_process,
+                              noise_clip, augmenter, aug_mix, premade_replay_dicts=None, per=False, discrete=False,
+                              use_baseline=False):
     if discrete or use_baseline:
         raise NotImplementedError("discrete actions / advantage baselines are out of scope")
     aa, ca = agent._actor_arena, agent._critic_arena

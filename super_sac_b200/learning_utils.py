@@ -185,7 +185,8 @@ def sample_move_and_augment(buffer, batch_size, augmenter, aug_mix, per=True, _i
     int(B*aug_mix) augmented rows into the batch (reference learning_utils.py:174-214)."""
     assert len(buffer) >= batch_size
     st, dev, B = buffer._storage, buffer.device, batch_size
-    buffer.total_sample_calls += 1
+    if not torch.cuda.is_current_stream_capturing():
+        buffer.total_sample_calls += 1
     if per:
         idx, imp_weights = buffer.sample_indices_per(B)
     else:

@@ -164,8 +164,83 @@ class ReplayBuffer:
         _lib.lib().tree_set(self._it_sum.data_ptr(), self._it_min.data_ptr(), self._capacity, idx_dev.data_ptr(),
                             val_dev.data_ptr(), idx_dev.numel(), _lib.stream_ptr())
 
+    # --- single-transition fast path: one pinned staging buffer, one H2D copy, one scatter kernel ----------------
+    _STAGE_SLOTS = 64
+
+    def _push_one(self, state, action, reward, next_state, done, priority):
+        import ctypes
+
+        st = self._storage
+        if not hasattr(self, "_stage"):
+            fields = []   # (dst tensor getter, nbytes)
+            off = 0
+            lay = []
+            for label in st.s_stack:
+                for stack in (st.s_stack[label], st.s1_stack[label]):
+                    nb = stack[0].numel() * stack.element_size()
+                    lay.append((off, nb)); off = (off + nb + 15) // 16 * 16
+            for nb in (st.action_stack[0].numel() * 4, 4, 1, 8, 8, 8):   # action, reward, done, tree idx, priority, fill
+                lay.append((off, nb)); off = (off + nb + 15) // 16 * 16
+            self._stage_layout, self._stage_bytes = lay, off
+            self._stage = torch.empty((self._STAGE_SLOTS, off), dtype=torch.uint8).pin_memory()
+            self._stage_dev = torch.empty((self._STAGE_SLOTS, off), dtype=torch.uint8, device=self.device)
+            self._stage_events = [None] * self._STAGE_SLOTS
+            self._stage_next = 0
+            self._tree_idx_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
+            self._tree_val_dev = torch.zeros(1, dtype=torch.float64, device=self.device)
+        slot = self._stage_next
+        self._stage_next = (slot + 1) % self._STAGE_SLOTS
+        ev = self._stage_events[slot]
+        if ev is not None:
+            ev.synchronize()   # the H2D copy that last used this pinned slot has finished
+        host = self._stage[slot].numpy()
+        lay = self._stage_layout
+        pos = st._next_idx
+        k = 0
+        dsts = []
+        for label in st.s_stack:
+            for stack, src in ((st.s_stack[label], state[label]), (st.s1_stack[label], next_state[label])):
+                off, nb = lay[k]; k += 1
+                host[off:off + nb] = np.ascontiguousarray(np.asarray(src).astype(st.s_dtypes[label])).view(np.uint8).reshape(-1)
+                dsts.append(stack[pos].data_ptr())
+        off, nb = lay[k]; k += 1
+        host[off:off + nb] = np.asarray(action, dtype=np.float32).view(np.uint8).reshape(-1)
+        dsts.append(st.action_stack[pos].data_ptr())
+        off, nb = lay[k]; k += 1
+        host[off:off + nb] = np.asarray([reward], dtype=np.float32).view(np.uint8)
+        dsts.append(st.reward_stack[pos].data_ptr())
+        off, nb = lay[k]; k += 1
+        host[off] = np.uint8(bool(done))
+        dsts.append(st.done_stack[pos].data_ptr())
+        filled = min(max(pos + 1, st._max_filled), st.size)
+        off, nb = lay[k]; k += 1
+        host[off:off + 8] = np.asarray([pos], dtype=np.int64).view(np.uint8)
+        dsts.append(self._tree_idx_dev.data_ptr())
+        off, nb = lay[k]; k += 1
+        host[off:off + 8] = np.asarray([priority], dtype=np.float64).view(np.uint8)
+        dsts.append(self._tree_val_dev.data_ptr())
+        off, nb = lay[k]; k += 1
+        host[off:off + 8] = np.asarray([filled], dtype=np.int64).view(np.uint8)
+        dsts.append(self._n_filled_dev.data_ptr())
+        self._stage_dev[slot].copy_(self._stage[slot], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._stage_events[slot] = ev
+        L = _lib.lib()
+        n = len(lay)
+        L.scatter_fields(self._stage_dev[slot].data_ptr(), _lib.host_array(ctypes.c_void_p, dsts),
+                         _lib.host_array(ctypes.c_int64, [nb for _, nb in lay]),
+                         _lib.host_array(ctypes.c_int64, [o for o, _ in lay]), n, _lib.stream_ptr())
+        self._tree_set(self._tree_idx_dev, self._tree_val_dev)
+        st._max_filled = filled
+        st._next_idx = (pos + 1) % st.size
+        return np.array([pos])
+
     def push(self, state, action, reward, next_state, done, priorities=None, **kwargs):
         self._ensure_storage(state, action)
+        if np.asarray(action).ndim == 1 and (priorities is None or np.ndim(priorities) == 0):
+            p = self._max_priority if priorities is None else float(priorities)
+            return self._push_one(state, action, reward, next_state, done, p**self.alpha)
         R = self._storage.add(state, action, reward, next_state, done)
         self._n_filled_dev.fill_(len(self._storage))
         if priorities is None:

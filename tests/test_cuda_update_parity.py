@@ -347,3 +347,61 @@ def test_sharded_update_equals_single_gpu():
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "[rank 0] sharded critics" in res.stdout and "[rank 1] sharded critics" in res.stdout
+
+
+def test_auto_graph_replay_equals_eager():
+    """graphed.enable_auto_graphs(): from the third identical call on, critic_update / online_actor_update replay a
+    captured CUDA graph.  Same Philox seed => the replayed run must reproduce the eager run bit for bit (same kernels,
+    device-side step / rng counters), and return the same log keys."""
+    import copy
+    from itertools import chain
+
+    import cuda_util as cu
+    import super_sac_b200 as ssb
+    from super_sac_b200 import augmentations, graphed, learning, learning_utils as lu, nets
+
+    def run(auto):
+        ssb.manual_seed(11)
+        torch.manual_seed(11)
+        agent = ssb.Agent(act_space_size=6, encoder=cu.IdentityEncoder(17), actor_network_cls=nets.mlps.ContinuousStochasticActor,
+                          critic_network_cls=nets.mlps.ContinuousCritic, ensemble_size=1, num_critics=4, hidden_size=64,
+                          auto_rescale_targets=False, log_std_low=-5.0, log_std_high=2.0)
+        agent.to("cuda")
+        target = copy.deepcopy(agent)
+        rng = np.random.default_rng(0)
+        buf = ssb.replay.ReplayBuffer(2048, device="cuda")
+        buf.load_experience({"obs": rng.standard_normal((2048, 17), dtype=np.float32)}, rng.uniform(-1, 1, (2048, 6)).astype(np.float32),
+                            rng.standard_normal(2048, dtype=np.float32), {"obs": rng.standard_normal((2048, 17), dtype=np.float32)},
+                            rng.uniform(size=2048) < 0.05)
+        c_opt = torch.optim.Adam(chain(*(c.parameters() for c in agent.critics)), lr=3e-4)
+        a_opt = torch.optim.Adam(chain(*(a.parameters() for a in agent.actors)), lr=3e-4)
+        e_opt = torch.optim.Adam(agent.encoder.parameters(), lr=1e-4)
+        la = [torch.tensor([-2.3], device="cuda", requires_grad=True)]
+        aug = augmentations.AugmentationSequence([augmentations.IdentityAug(64)])
+        graphed.enable_auto_graphs(auto)
+        try:
+            for k in range(7):
+                logs, rds = learning.critic_update(
+                    buffer=buf, agent=agent, target_agent=target, critic_optimizer=c_opt, encoder_optimizer=e_opt, log_alphas=la,
+                    batch_size=64, gamma=0.99, critic_clip=None, encoder_clip=None, target_critic_ensemble_n=2,
+                    weighted_bellman_temp=None, weight_type=None, pop=False, augmenter=aug, encoder_lambda=0.0,
+                    random_process=None, noise_clip=None, aug_mix=0.0)
+                if k % 2 == 0:
+                    lu.soft_update(target.critics[0], agent.critics[0], 0.005)
+                alogs = learning.online_actor_update(
+                    buffer=buf, agent=agent, pop=False, actor_optimizer=a_opt, log_alphas=la, batch_size=64, clip=None,
+                    random_process=None, noise_clip=None, augmenter=aug, aug_mix=0.0, premade_replay_dicts=rds)
+        finally:
+            graphed.enable_auto_graphs(False)
+        assert c_opt._ssac_flat_adam.steps == 7 and int(c_opt._ssac_flat_adam.ctl[0]) == 7
+        assert buf.total_sample_calls == 7
+        return agent, target, logs, alogs
+
+    a0, t0, l0, al0 = run(False)
+    a1, t1, l1, al1 = run(True)
+    assert torch.equal(a0._critic_arena.flat, a1._critic_arena.flat)
+    assert torch.equal(t0._critic_arena.flat, t1._critic_arena.flat)
+    assert torch.equal(a0._actor_arena.flat, a1._actor_arena.flat)
+    assert set(l0.keys()) == set(l1.keys()) and set(al0.keys()) == set(al1.keys())
+    for k in l0:
+        gu.assert_close(float(l1[k]), float(l0[k]), 1e-5, 1e-7, f"log {k}")
