@@ -315,6 +315,10 @@ def run_gpu_arm(args, cfg, rank, world, local_rank):
         e2e_dt = float(t.item())
     e2e_value = world * e2e_steps / e2e_dt
 
+    sharded = None
+    if dist is not None and cfg["E"] == 1 and cfg["N"] >= world:
+        graphed.enable_auto_graphs(False)
+        sharded = time_sharded(cfg, args, device, rank, world, dist)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -352,11 +356,77 @@ def run_gpu_arm(args, cfg, rank, world, local_rank):
         "cpu_baseline": {"value": cpu_ups, "unit": "updates/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"{cpu_steps} oracle updates (same workload) after 10 warm-up, torch-CPU fp32"},
         "flops_per_update": fl["update"],
+        "sharded_ensemble": sharded,
         "sample_logs": {k: float(v) for k, v in list(glogs.items())[:4]},
     }
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def time_sharded(cfg, args, device, rank, world, dist):
+    """Secondary multi-GPU number: ONE learner whose N critics are sharded over the ranks, NCCL all-gather of
+    the target Q values inside every update.  Returns updates/s of that single learner (max over ranks)."""
+    import copy
+
+    import cuda_util as cu
+    import super_sac_b200 as ssb
+    from super_sac_b200 import augmentations, graphed, learning, learning_utils as lu, nets, parallel
+
+    lo, hi = parallel.enable_critic_sharding(cfg["N"])
+    try:
+        ssb.manual_seed(1234)          # identical Philox stream on every rank: same indices / eps / subset
+        torch.manual_seed(1234)        # identical actor replica
+        agent = ssb.Agent(act_space_size=cfg["A"], encoder=cu.IdentityEncoder(cfg["S"]),
+                          actor_network_cls=nets.mlps.ContinuousStochasticActor, critic_network_cls=nets.mlps.ContinuousCritic,
+                          ensemble_size=1, num_critics=hi - lo, hidden_size=cfg["H"], auto_rescale_targets=False,
+                          log_std_low=-5.0, log_std_high=2.0)
+        agent.to(device)
+        target = copy.deepcopy(agent)
+        critic_opt, actor_opt, enc_opt, log_alphas, _ = cu.optimizers(agent, dict(E=1, critic_lr=cfg["lr"], actor_lr=cfg["lr"]))
+        buf = ssb.replay.ReplayBuffer(200_000, device=device)
+        s, a, r, s1, d = synthetic_transitions(cfg, 200_000, 0)
+        buf.load_experience({"obs": s}, a, r, {"obs": s1}, d)
+        B = cfg["B"]
+        kw = dict(buffer=buf, agent=agent, target_agent=target, critic_optimizer=critic_opt, encoder_optimizer=enc_opt,
+                  log_alphas=log_alphas, batch_size=B, gamma=0.99, critic_clip=None, encoder_clip=None,
+                  target_critic_ensemble_n=cfg["M"], weighted_bellman_temp=None, weight_type=None, pop=False,
+                  augmenter=augmentations.AugmentationSequence([augmentations.IdentityAug(B)]), encoder_lambda=0.0,
+                  random_process=None, noise_clip=None, aug_mix=0.0)
+
+        def upd():
+            out = learning.critic_update(**kw)
+            lu.soft_update(target.critics[0], agent.critics[0], cfg["tau"])
+            return out
+
+        mode = "cuda-graph replay (NCCL all-gather captured)"
+        try:
+            g = graphed.GraphedCall(upd)
+            step = g.replay
+        except Exception as e:  # noqa: BLE001  (capture of the collective is driver/NCCL dependent)
+            mode = "eager launches (graph capture of the collective unavailable: %s)" % type(e).__name__
+            step = upd
+        steps = min(args.steps, 1000)
+        for _ in range(10):
+            step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        return {"value": steps / (ms * 1e-3), "unit": "updates/s of ONE learner", "ms_per_step": ms / steps, "mode": mode,
+                "critics_per_rank": [parallel.local_range(cfg["N"], world, r)[1] - parallel.local_range(cfg["N"], world, r)[0]
+                                     for r in range(world)],
+                "collectives_per_update": "1 all-gather of Q_target [N,B] fp32 (%d B per rank)" % (4 * B * -(-cfg["N"] // world))}
+    finally:
+        parallel.disable()
 
 
 def buf_bytes(buf):
