@@ -287,7 +287,7 @@ int head_forward(const float* h2, const float* W3, const float* b3, const int32_
   if (epi) e = *epi; else { memset(&e, 0, sizeof(e)); }
   const size_t smem = (size_t)O * H * sizeof(float);
   static bool attr_set = false;
-  if (smem > 48 * 1024 && !attr_set) {
+  if (smem > 40 * 1024 && !attr_set) {   // static shared memory counts towards the 48 KB default limit
     cudaFuncSetAttribute(head_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
     attr_set = true;
   }
