@@ -222,6 +222,7 @@ def run_gpu_arm(args, cfg, rank, world, local_rank):
 
         dist.init_process_group("nccl", device_id=device)
     ssb.set_mlp_impl(args.mlp_impl)
+    ssb.set_overlap(not args.no_overlap)
     agent, target, critic_opt, enc_opt, log_alphas, buf = build_gpu(cfg, device, seed=rank)
     B = cfg["B"]
     augmenter = augmentations.AugmentationSequence([augmentations.IdentityAug(B)])
@@ -345,7 +346,8 @@ def run_gpu_arm(args, cfg, rank, world, local_rank):
                    "parallelism": "1 learner" if world == 1 else f"{world} independent learner replicas (no data-path collective)",
                    "l2": "replay ring %.0f MB > 126 MB L2 (random rows); parameters+moments (11.6 MB) are L2-resident by design"
                          % (buf_bytes(buf) / 1e6),
-                   "impl": "ensemble MLP GEMMs: " + ssb.get_mlp_impl()},
+                   "impl": "ensemble MLP GEMMs: " + ssb.get_mlp_impl(),
+                   "overlap": "two-stream fork/join inside the update" if not args.no_overlap else "off"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_steps, "path": "buffer.push(host transition, H2D) + learning.critic_update (auto CUDA graph) + "
@@ -451,7 +453,9 @@ def count_launches(fn, _lib):
 
     def wrap(name, f, mult):
         def g(*a):
-            if name == "mlp_backward":
+            if name == "critic_forward_loss":
+                counter["n"] += {0: 3, 1: 2, 2: 1}[a[24]]   # phase: whole forward / hidden layers / output layer + loss
+            elif name == "mlp_backward":
                 # dz2, gW3, gW2, dz1, gW1 (+dx): 5 launches with weight grads, 2 (+1) without
                 want_dw = a[17] is not None
                 counter["n"] += (5 if want_dw else 2) + (1 if a[24] is not None else 0)
@@ -508,6 +512,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="redq", choices=sorted(CONFIGS))
     ap.add_argument("--mlp-impl", default="tcgen05", choices=["tcgen05", "ffma"])
+    ap.add_argument("--no-overlap", action="store_true", help="serialise the independent branches of the update (A/B switch)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))

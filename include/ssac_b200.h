@@ -118,6 +118,11 @@ int ssac_set_default_mlp_impl(int impl);
 /* impl 2 stages operands with TMA (cp.async.bulk.tensor) when their pitch allows; 0 forces the register-staged path
  * (kept for cross-checking the two staging paths against each other). */
 int ssac_set_tma_enabled(int on);
+/* ssac_mlp_backward runs its weight-gradient branch (gW3, gW2, and gW1 when dx is also wanted) on an internal side
+ * stream, forked from / joined into `stream` with events (graph edges under stream capture); 0 serialises everything
+ * on `stream`.  Results are identical either way.  Default 1. */
+int ssac_set_overlap(int on);
+int ssac_get_overlap(void);
 int ssac_mlp_forward(const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
                      const float* b3, const int32_t* net_index_dev, int G, int D, int H, int O,
                      const float* x_dev, int64_t ldx, int64_t x_gs, int B, float* h1_dev, float* h2_dev,
@@ -142,12 +147,14 @@ int ssac_actor_forward_sample(const float* W1, const float* b1, const float* W2,
                               const float* noise_dev, float sigma, float clip, float log_std_lo, float log_std_hi,
                               float* a_dev, int64_t lda, float* logp_dev, float* tanh_out_dev, int impl, void* stream);
 /* Critic forward of one member (N nets, shared input) with the loss seed of ssac_critic_loss_seed fused into the
- * output-layer kernel: q [N,B], dq [N,B], loss_dev[0] += loss, loss_dev[1] += mean td of the last net. */
+ * output-layer kernel: q [N,B], dq [N,B], loss_dev[0] += loss, loss_dev[1] += mean td of the last net.
+ * phase 0 = everything; 1 = hidden layers only (h1, h2: independent of the TD target, so the caller can run it on a
+ * second stream next to the target networks); 2 = output layer + loss only (h2 from an earlier phase-1 call). */
 int ssac_critic_forward_loss(const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
                              const float* b3, int N, int D, int H, const float* x_dev, int64_t ldx, int B,
                              float* h1_dev, float* h2_dev, float* q_dev, const float* y_dev, const float* w_dev,
                              const float* imp_dev, const float* popart_dev, int pop, int E, int n_total, float* dq_dev,
-                             float* loss_dev, int impl, void* stream);
+                             float* loss_dev, int phase, int impl, void* stream);
 
 /* ---- policy heads: nets/distributions.py:9-15,64-114; learning_utils.py:48-59 --------------------- */
 /* out [B,2A] = [mu | raw_log_std], eps [B,A] -> a [B,A] (row stride lda: may be a column block of cat(s,a)),

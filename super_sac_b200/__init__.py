@@ -40,5 +40,12 @@ def get_mlp_impl():
     cur = _lib.lib().default_mlp_impl()
     return next(k for k, v in MLP_IMPLS.items() if v == cur)
 
+
+def set_overlap(on):
+    """Run the independent branches of an update on a second stream (weight-gradient GEMMs next to the data-gradient
+    GEMMs, the online critics' hidden layers next to the target networks).  On by default; results do not change."""
+    _lib.lib().set_overlap(int(bool(on)))
+
+
 __all__ = ["Agent", "agent", "nets", "replay", "learning", "learning_utils", "augmentations", "popart",
-           "adv_estimator", "device", "manual_seed", "set_mlp_impl", "get_mlp_impl"]
+           "adv_estimator", "device", "manual_seed", "set_mlp_impl", "get_mlp_impl", "set_overlap"]

@@ -6,7 +6,10 @@
 namespace ssac {
 int mlp_forward_simt(const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
                      const float* b3, const int32_t* net_index, int G, int D, int H, int O, const float* x, int64_t ldx,
-                     int64_t x_gs, int B, float* h1, float* h2, float* y, cudaStream_t s, int impl, const HeadEpi* epi);
+                     int64_t x_gs, int B, float* h1, float* h2, float* y, cudaStream_t s, int impl, const HeadEpi* epi,
+                     int phase);
+void set_overlap(int on);
+int get_overlap();
 int mlp_backward_simt(const float* W1, const float* W2, const float* W3, const int32_t* net_index, int G, int D, int H,
                       int O, const float* x, int64_t ldx, int64_t x_gs, int B, const float* h1, const float* h2,
                       const float* dy, const float* dh2_extra, float extra_scale, float* gW1, float* gb1, float* gW2,
@@ -27,6 +30,9 @@ int ssac_set_default_mlp_impl(int impl) {
   return 0;
 }
 
+int ssac_set_overlap(int on) { set_overlap(on); return 0; }
+int ssac_get_overlap(void) { return get_overlap(); }
+
 int ssac_mlp_forward(const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
                      const float* b3, const int32_t* net_index_dev, int G, int D, int H, int O, const float* x_dev,
                      int64_t ldx, int64_t x_gs, int B, float* h1_dev, float* h2_dev, float* y_dev, int impl,
@@ -36,7 +42,7 @@ int ssac_mlp_forward(const float* W1, const float* b1, const float* W2, const fl
   if (impl == 0) impl = ssac_default_mlp_impl();
   if (impl == 1 || impl == 2)
     return mlp_forward_simt(W1, b1, W2, b2, W3, b3, net_index_dev, G, D, H, O, x_dev, ldx, x_gs, B, h1_dev, h2_dev,
-                            y_dev, (cudaStream_t)stream, impl, nullptr);
+                            y_dev, (cudaStream_t)stream, impl, nullptr, 0);
   return fail(SSAC_E_UNSUPPORTED, "ssac_mlp_forward: unknown impl");
 }
 
@@ -56,15 +62,15 @@ int ssac_actor_forward_sample(const float* W1, const float* b1, const float* W2,
   e.eps = eps_dev; e.noise = noise_dev; e.sigma = sigma; e.clip = clip; e.lo = log_std_lo; e.hi = log_std_hi;
   e.a = a_dev; e.lda = lda; e.logp = logp_dev; e.tanh_out = tanh_out_dev; e.A = A;
   return mlp_forward_simt(W1, b1, W2, b2, W3, b3, nullptr, 1, D, H, deterministic ? A : 2 * A, x_dev, ldx, 0, B, h1_dev,
-                          h2_dev, out_dev, (cudaStream_t)stream, impl, &e);
+                          h2_dev, out_dev, (cudaStream_t)stream, impl, &e, 0);
 }
 
 int ssac_critic_forward_loss(const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
                              const float* b3, int N, int D, int H, const float* x_dev, int64_t ldx, int B,
                              float* h1_dev, float* h2_dev, float* q_dev, const float* y_dev, const float* w_dev,
                              const float* imp_dev, const float* popart_dev, int pop, int E, int n_total, float* dq_dev,
-                             float* loss_dev, int impl, void* stream) {
-  SSAC_REQUIRE(W1 && b1 && W2 && b2 && W3 && b3 && x_dev && q_dev && y_dev && dq_dev && h1_dev && h2_dev,
+                             float* loss_dev, int phase, int impl, void* stream) {
+  SSAC_REQUIRE(W1 && b1 && W2 && b2 && W3 && b3 && x_dev && h1_dev && h2_dev && (phase == 1 || (q_dev && y_dev && dq_dev)),
                "ssac_critic_forward_loss: null pointer");
   SSAC_REQUIRE(N > 0 && D > 0 && H > 0 && B > 0 && E > 0 && ldx >= D, "ssac_critic_forward_loss: bad sizes");
   if (impl == 0) impl = ssac_default_mlp_impl();
@@ -75,7 +81,7 @@ int ssac_critic_forward_loss(const float* W1, const float* b1, const float* W2, 
   e.inv_count = 1.f / ((float)B * (float)E * (float)(n_total > 0 ? n_total : N));
   e.dq = dq_dev; e.loss = loss_dev;
   return mlp_forward_simt(W1, b1, W2, b2, W3, b3, nullptr, N, D, H, 1, x_dev, ldx, 0, B, h1_dev, h2_dev, q_dev,
-                          (cudaStream_t)stream, impl, &e);
+                          (cudaStream_t)stream, impl, &e, phase);
 }
 
 int64_t ssac_mlp_backward_ws(int G, int B, int H) { return 2 * (int64_t)G * B * H; }

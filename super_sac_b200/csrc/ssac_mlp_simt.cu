@@ -325,6 +325,40 @@ static int launch_gemm(int layout, const GemmP& p, int G, cudaStream_t s, const 
   return 0;
 }
 
+// ---- intra-call overlap -------------------------------------------------------------------------------------------
+// The backward of one ensemble has independent branches (gW3 | dz2, gW2 | dz1, gW1 | dx) whose grids (<= 40 CTAs at
+// REDQ shapes) leave most of the 148 SMs idle, so the weight-gradient branch runs on a side stream, forked from and
+// joined back into the caller's stream with events.  Under stream capture the fork/join become graph edges.
+static int g_overlap = 1;
+struct Side {
+  cudaStream_t s = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+static Side* side_of_current_device() {
+  static Side sides[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  Side& sd = sides[dev];
+  if (!sd.s) {
+    if (cudaStreamCreateWithFlags(&sd.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    for (auto& e : sd.ev)
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  }
+  return &sd;
+}
+// after: work already queued on `from` precedes anything queued on `to` from now on
+static int order_after(cudaStream_t from, cudaStream_t to, cudaEvent_t ev) {
+  cudaError_t e = cudaEventRecord(ev, from);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(to, ev, 0);
+  if (e != cudaSuccess) {
+    set_error(std::string("overlap fork/join: ") + cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+void set_overlap(int on) { g_overlap = on ? 1 : 0; }
+int get_overlap() { return g_overlap; }
+
 static GemmP blank() {
   GemmP p;
   p.A = nullptr; p.lda = 0; p.a_gs = 0; p.Bm = nullptr; p.ldb = 0; p.b_gs = 0; p.b_index = nullptr;
@@ -336,11 +370,21 @@ static GemmP blank() {
 
 int mlp_forward_simt(const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
                      const float* b3, const int32_t* net_index, int G, int D, int H, int O, const float* x, int64_t ldx,
-                     int64_t x_gs, int B, float* h1, float* h2, float* y, cudaStream_t s, int impl, const HeadEpi* epi) {
+                     int64_t x_gs, int B, float* h1, float* h2, float* y, cudaStream_t s, int impl, const HeadEpi* epi,
+                     int phase) {
+  // phase 0: all three layers; 1: trunk only (h1, h2); 2: output layer only (h2 already computed)
   SSAC_REQUIRE(h1 && h2, "ssac_mlp_forward: h1/h2 buffers are required");
   SSAC_REQUIRE(!epi || O <= kSmallO, "fused head epilogues need O <= 32");
+  SSAC_REQUIRE(phase >= 0 && phase <= 2, "ssac_mlp_forward: phase must be 0, 1 or 2");
   g_impl = impl;
   GemmP p = blank();
+  if (phase == 2) {
+    if (O <= kSmallO) return head_forward(h2, W3, b3, net_index, G, B, H, O, y, epi, s);
+    p.a_gs = (int64_t)B * H; p.lda = H; p.b_index = net_index; p.M = B;
+    p.A = h2; p.Bm = W3; p.ldb = H; p.b_gs = (int64_t)O * H; p.C = y; p.ldc = O; p.c_gs = (int64_t)B * O;
+    p.bias = b3; p.bias_gs = O; p.relu = 0; p.N = O; p.K = H;
+    return launch_gemm(L_NT, p, G, s, "mlp_forward L3");
+  }
   // layer 1: h1 = relu(x W1^T + b1)
   p.A = x; p.lda = ldx; p.a_gs = x_gs; p.Bm = W1; p.ldb = D; p.b_gs = (int64_t)H * D; p.b_index = net_index;
   p.C = h1; p.ldc = H; p.c_gs = (int64_t)B * H; p.bias = b1; p.bias_gs = H; p.relu = 1; p.M = B; p.N = H; p.K = D;
@@ -351,6 +395,7 @@ int mlp_forward_simt(const float* W1, const float* b1, const float* W2, const fl
   p.C = h2; p.bias = b2; p.K = H;
   rc = launch_gemm(L_NT, p, G, s, "mlp_forward L2");
   if (rc) return rc;
+  if (phase == 1) return 0;
   // layer 3: y = h2 W3^T + b3
   if (O <= kSmallO) return head_forward(h2, W3, b3, net_index, G, B, H, O, y, epi, s);
   p.A = h2; p.Bm = W3; p.ldb = H; p.b_gs = (int64_t)O * H; p.C = y; p.ldc = O; p.c_gs = (int64_t)B * O;
@@ -372,6 +417,27 @@ int mlp_backward_simt(const float* W1, const float* W2, const float* W3, const i
   float* dz2 = ws;
   float* dz1 = ws + (int64_t)G * B * H;
   int rc;
+  // weight-gradient branch: side stream when overlap is on (and there is such a branch), else the caller's stream
+  Side* sd = (g_overlap && need_dw) ? side_of_current_device() : nullptr;
+  cudaStream_t w = sd ? sd->s : s;
+  if (sd && (rc = order_after(s, w, sd->ev[0]))) return rc;   // fork
+  if (need_dw) {
+    if (dy && O <= kSmallO) {
+      rc = head_backward_weight(dy, h2, G, B, H, O, gW3, gb3, accumulate, w);
+      if (rc) return rc;
+    } else if (dy) {
+      // gW3 = dy^T h2, gb3 = colsum(dy)
+      GemmP q = blank();
+      q.A = dy; q.lda = O; q.a_gs = (int64_t)B * O; q.Bm = h2; q.ldb = H; q.b_gs = (int64_t)B * H;
+      q.C = gW3; q.ldc = H; q.c_gs = (int64_t)O * H; q.colsum = gb3; q.colsum_gs = O; q.M = O; q.N = H; q.K = B;
+      q.accumulate = accumulate;
+      rc = launch_gemm(L_TN, q, G, w, "mlp_backward gW3");
+      if (rc) return rc;
+    } else if (!accumulate) {
+      cudaMemsetAsync(gW3, 0, sizeof(float) * (size_t)G * O * H, w);
+      cudaMemsetAsync(gb3, 0, sizeof(float) * (size_t)G * O, w);
+    }
+  }
   GemmP p = blank();
   // dz2 = (dy W3 + s*extra) .* (h2 > 0)
   p.A = dy; p.lda = O; p.a_gs = (int64_t)B * O; p.Bm = W3; p.ldb = H; p.b_gs = (int64_t)O * H; p.b_index = net_index;
@@ -383,27 +449,13 @@ int mlp_backward_simt(const float* W1, const float* W2, const float* W3, const i
   else rc = launch_gemm(L_NN, p, G, s, "mlp_backward dz2");
   if (rc) return rc;
   if (need_dw) {
-    if (dy && O <= kSmallO) {
-      rc = head_backward_weight(dy, h2, G, B, H, O, gW3, gb3, accumulate, s);
-      if (rc) return rc;
-    } else if (dy) {
-      // gW3 = dy^T h2, gb3 = colsum(dy)
-      GemmP q = blank();
-      q.A = dy; q.lda = O; q.a_gs = (int64_t)B * O; q.Bm = h2; q.ldb = H; q.b_gs = (int64_t)B * H;
-      q.C = gW3; q.ldc = H; q.c_gs = (int64_t)O * H; q.colsum = gb3; q.colsum_gs = O; q.M = O; q.N = H; q.K = B;
-      q.accumulate = accumulate;
-      rc = launch_gemm(L_TN, q, G, s, "mlp_backward gW3");
-      if (rc) return rc;
-    } else if (!accumulate) {
-      cudaMemsetAsync(gW3, 0, sizeof(float) * (size_t)G * O * H, s);
-      cudaMemsetAsync(gb3, 0, sizeof(float) * (size_t)G * O, s);
-    }
+    if (sd && (rc = order_after(s, w, sd->ev[1]))) return rc;   // gW2 needs dz2
     // gW2 = dz2^T h1, gb2 = colsum(dz2)
     GemmP q = blank();
     q.A = dz2; q.lda = H; q.a_gs = (int64_t)B * H; q.Bm = h1; q.ldb = H; q.b_gs = (int64_t)B * H;
     q.C = gW2; q.ldc = H; q.c_gs = (int64_t)H * H; q.colsum = gb2; q.colsum_gs = H; q.M = H; q.N = H; q.K = B;
     q.accumulate = accumulate;
-    rc = launch_gemm(L_TN, q, G, s, "mlp_backward gW2");
+    rc = launch_gemm(L_TN, q, G, w, "mlp_backward gW2");
     if (rc) return rc;
   }
   // dz1 = (dz2 W2) .* (h1 > 0)
@@ -413,13 +465,16 @@ int mlp_backward_simt(const float* W1, const float* W2, const float* W3, const i
   p.M = B; p.N = H; p.K = H;
   rc = launch_gemm(L_NN, p, G, s, "mlp_backward dz1");
   if (rc) return rc;
+  // gW1 and dx both hang off dz1: with both wanted, gW1 goes to the side stream behind gW2 and dx stays on the caller's
+  const bool gw1_on_side = sd && need_dw && dx;
   if (need_dw) {
+    if (gw1_on_side && (rc = order_after(s, w, sd->ev[2]))) return rc;
     // gW1 = dz1^T x, gb1 = colsum(dz1)
     GemmP q = blank();
     q.A = dz1; q.lda = H; q.a_gs = (int64_t)B * H; q.Bm = x; q.ldb = ldx; q.b_gs = x_gs;
     q.C = gW1; q.ldc = D; q.c_gs = (int64_t)H * D; q.colsum = gb1; q.colsum_gs = H; q.M = H; q.N = D; q.K = B;
     q.accumulate = accumulate;
-    rc = launch_gemm(L_TN, q, G, s, "mlp_backward gW1");
+    rc = launch_gemm(L_TN, q, G, gw1_on_side ? w : s, "mlp_backward gW1");
     if (rc) return rc;
   }
   if (dx) {
@@ -430,6 +485,7 @@ int mlp_backward_simt(const float* W1, const float* W2, const float* W3, const i
     rc = launch_gemm(L_NN, p, G, s, "mlp_backward dx");
     if (rc) return rc;
   }
+  if (sd && (rc = order_after(w, s, sd->ev[3]))) return rc;   // join
   return 0;
 }
 

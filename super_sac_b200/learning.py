@@ -80,31 +80,42 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
         draws = lu.draw_for_critic_member(buffer, agent, B, target_critic_ensemble_n, random_process, per)
         rd = lu.sample_move_and_augment(buffer=buffer, batch_size=B, augmenter=augmenter, aug_mix=aug_mix, per=per,
                                         _idx=draws["idx"])
+        o, a, *_ = rd["primary_batch"]
+        packed = lu._packed_of(rd)
+        s_rep = agent.encoder(o)
+        need_ds = _encoder_has_grad_path(s_rep)
+        X = lu._first_layer_input(s_rep, a, packed["XA"] if packed else None, S, A)
+        h1 = torch.empty((N, B, ca.H), dtype=torch.float32, device=dev)
+        h2 = torch.empty_like(h1)
+        q = torch.empty((N, B, 1), dtype=torch.float32, device=dev)
+        dq = torch.empty((N, B, 1), dtype=torch.float32, device=dev)
+        W1, b1, W2, b2, W3, b3 = ca.ptrs(i * N)
+        # The online critics' hidden layers do not depend on the TD target: run them on a second stream next to the
+        # target actor -> target critics chain (their grids leave most SMs idle), join before the output layer + loss.
+        side = None if need_ds else lu.side_stream(dev)
+        if side is not None:
+            main = torch.cuda.current_stream(dev)
+            side.wait_stream(main)
+            L.critic_forward_loss(W1, b1, W2, b2, W3, b3, N, ca.D, ca.H, X.data_ptr(), S + A, B, h1.data_ptr(),
+                                  h2.data_ptr(), None, None, None, None, None, 0, E, 0, None, None, 1, 0, side.cuda_stream)
         td_target, (s1, a1) = lu.compute_td_targets(
             logs=logs, replay_dict=rd, agent=agent, target_agent=target_agent, log_alphas=log_alphas, ensemble_idx=i,
             ensemble_n=target_critic_ensemble_n, pop=pop, gamma=gamma, random_process=random_process,
             noise_clip=noise_clip, _draws=draws)
         w = lu.compute_backup_weights(logs=logs, replay_dict=rd, agent=agent, target_agent=target_agent,
                                       weight_type=weight_type, weight_temp=weighted_bellman_temp, batch_size=B)
-        o, a, *_ = rd["primary_batch"]
-        packed = lu._packed_of(rd)
-        s_rep = agent.encoder(o)
-        need_ds = _encoder_has_grad_path(s_rep)
-        X = lu._first_layer_input(s_rep, a, packed["XA"] if packed else None, S, A)
         popart = agent.popart[i]
-        h1 = torch.empty((N, B, ca.H), dtype=torch.float32, device=dev)
-        h2 = torch.empty_like(h1)
-        q = torch.empty((N, B, 1), dtype=torch.float32, device=dev)
-        dq = torch.empty((N, B, 1), dtype=torch.float32, device=dev)
         imp = rd["imp_weights"]
         imp_ptr = imp.float().contiguous() if per else None  # per=False: ones(1), i.e. no weighting (main.py:401)
         n_total = parallel.n_global() if parallel.is_sharded() else 0   # sharded critics: normalise by the global N
+        if side is not None:
+            main.wait_stream(side)
         # N critic forwards + loss value + seed gradient dL/dq in one entry point (loss seed fused into the head kernel)
-        W1, b1, W2, b2, W3, b3 = ca.ptrs(i * N)
         L.critic_forward_loss(W1, b1, W2, b2, W3, b3, N, ca.D, ca.H, X.data_ptr(), S + A, B, h1.data_ptr(), h2.data_ptr(),
                               q.data_ptr(), td_target.data_ptr(), w.data_ptr() if torch.is_tensor(w) else None,
                               None if imp_ptr is None else imp_ptr.data_ptr(), popart.state_ptr() if popart else None,
-                              int(bool(pop)), E, n_total, dq.data_ptr(), loss_v.data_ptr(), 0, stream)
+                              int(bool(pop)), E, n_total, dq.data_ptr(), loss_v.data_ptr(), 2 if side is not None else 0,
+                              0, stream)
         extra, extra_scale, f1 = None, 0.0, None
         if dr3_coeff > 0:
             # DR3 (learning.py:100-108): second forward on (s1, a1); both feature sets carry gradient
@@ -136,14 +147,23 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
         torch.nn.utils.clip_grad_norm_(agent.encoder.parameters(), encoder_clip)
     if enc_outs:
         encoder_optimizer.step()
+    member = random.choice(range(E))
+    side = None if critic_clip else lu.side_stream(dev)   # clipping rescales the gradients that get logged
+    if side is not None:
+        # logged gradient norm next to Adam (which only reads the gradients)
+        main = torch.cuda.current_stream(dev)
+        side.wait_stream(main)
+        gslot = lu._member_grad_norm_slot(logs, ca, member * N, (member + 1) * N, stream=side)
     opt.step(stream, max_norm=critic_clip if critic_clip else None)
+    if side is not None:
+        main.wait_stream(side)
+    else:
+        gslot = lu._member_grad_norm_slot(logs, ca, member * N, (member + 1) * N)
 
     if parallel.is_sharded():
         parallel.all_reduce_sum_(loss_all[0:1])   # each rank summed its own critics
     logs.defer("losses/last_member_critic_td_error", loss_slot + 2 * (E - 1) + 1)
     logs.defer("losses/critic_overall_loss", [loss_slot + 2 * i for i in range(E)])
-    member = random.choice(range(E))
-    gslot = lu._member_grad_norm_slot(logs, ca, member * N, (member + 1) * N)
     logs.defer("gradients/critic_random_grad", gslot, transform=lambda v: v**0.5)
     if enc_outs:
         gn = torch.linalg.vector_norm(torch.stack([p.grad.norm() for p in agent.encoder.parameters() if p.grad is not None]))

@@ -124,13 +124,28 @@ def get_grad_norm(model):
     return float(acc.item()) ** 0.5
 
 
-def _member_grad_norm_slot(logs, arena, g0, g1):
+def _member_grad_norm_slot(logs, arena, g0, g1, stream=None):
     """Enqueue sum g^2 of nets g0..g1 into a log slot (sqrt taken at finalize)."""
     v, slot = logs.slots(1)   # slots are zero-initialised with the buffer
-    L, s = _lib.lib(), _lib.stream_ptr()
+    L, s = _lib.lib(), (_lib.stream_ptr() if stream is None else stream.cuda_stream)
     for off, n in arena.range_table(g0, g1):
         L.sumsq(arena.grad.data_ptr() + 4 * off, n, v.data_ptr(), 1, s)
     return slot
+
+
+_side_streams = {}
+
+
+def side_stream(device):
+    """One extra stream per device for the independent branches of an update (online trunk next to the target
+    networks, the logged gradient norm next to Adam).  None when overlap is switched off (ssac_set_overlap)."""
+    if not _lib.lib().get_overlap():
+        return None
+    device = torch.device(device)
+    st = _side_streams.get(device)
+    if st is None:
+        st = _side_streams[device] = torch.cuda.Stream(device=device)
+    return st
 
 
 # ------------------------------------------------------------------------------------------------
