@@ -123,10 +123,17 @@ int ssac_set_tma_enabled(int on);
  * on `stream`.  Results are identical either way.  Default 1. */
 int ssac_set_overlap(int on);
 int ssac_get_overlap(void);
+/* impl 2, 2 x 256-class networks (H in 32..256 and a multiple of 16, first-layer width <= 32, O <= 16): the whole forward
+ * (three layers + head epilogue) runs as ONE kernel that keeps the activations in tensor / shared memory.  h1 / h2 are
+ * then written only when keep_hidden != 0 (a backward pass will read them); with keep_hidden == 0 their contents are
+ * unspecified after the call.  Other shapes use the layered path (one launch per layer), which always needs the
+ * h1 / h2 buffers.  ssac_set_fused_forward(0) forces the layered path (cross-check).  Default 1. */
+int ssac_set_fused_forward(int on);
+int ssac_get_fused_forward(void);
 int ssac_mlp_forward(const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
                      const float* b3, const int32_t* net_index_dev, int G, int D, int H, int O,
                      const float* x_dev, int64_t ldx, int64_t x_gs, int B, float* h1_dev, float* h2_dev,
-                     float* y_dev, int impl, void* stream);
+                     int keep_hidden, float* y_dev, int impl, void* stream);
 /* Backward of the above.  dy [G,B,O] (nullable = 0), dh2_extra [G,B,H] (nullable) is added to dL/dh2 scaled
  * by extra_scale (DR3, learning.py:100-108).  Weight grads gW1..gb3 laid out like the parameters (all NULL =
  * input-gradient only, the actor update's pass through the critics); accumulate != 0 adds to them.
@@ -143,7 +150,7 @@ int ssac_mlp_backward(const float* W1, const float* W2, const float* W3, const i
  * backward.  deterministic: eps (nullable) is the 1e-4 rsample jitter, noise (nullable) the TD3 noise. */
 int ssac_actor_forward_sample(const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
                               const float* b3, int D, int H, int A, int deterministic, const float* x_dev, int64_t ldx,
-                              int B, float* h1_dev, float* h2_dev, float* out_dev, const float* eps_dev,
+                              int B, float* h1_dev, float* h2_dev, int keep_hidden, float* out_dev, const float* eps_dev,
                               const float* noise_dev, float sigma, float clip, float log_std_lo, float log_std_hi,
                               float* a_dev, int64_t lda, float* logp_dev, float* tanh_out_dev, int impl, void* stream);
 /* Critic forward of one member (N nets, shared input) with the loss seed of ssac_critic_loss_seed fused into the

@@ -47,5 +47,11 @@ def set_overlap(on):
     _lib.lib().set_overlap(int(bool(on)))
 
 
+def set_fused_forward(on):
+    """Use the single-kernel forward (three layers + head in one launch) for 2 x 256-class networks.  On by default;
+    off = one launch per layer (the cross-check path)."""
+    _lib.lib().set_fused_forward(int(bool(on)))
+
+
 __all__ = ["Agent", "agent", "nets", "replay", "learning", "learning_utils", "augmentations", "popart",
-           "adv_estimator", "device", "manual_seed", "set_mlp_impl", "get_mlp_impl", "set_overlap"]
+           "adv_estimator", "device", "manual_seed", "set_mlp_impl", "get_mlp_impl", "set_overlap", "set_fused_forward"]

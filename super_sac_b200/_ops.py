@@ -26,13 +26,14 @@ def _bwd_ws(G, B, H, device):
     return torch.empty(_lib.lib().mlp_backward_ws(G, B, H), dtype=torch.float32, device=device)
 
 
-def mlp_forward(arena, g0, G, x, B, h1, h2, y, ldx=None, x_gs=0, net_index=None, impl=0):
-    """y[g] = MLP_{g0+g}(x[g]);  x is [B, ldx] (x_gs = 0, shared) or [G, B, ldx]."""
+def mlp_forward(arena, g0, G, x, B, h1, h2, y, ldx=None, x_gs=0, net_index=None, impl=0, keep_hidden=True):
+    """y[g] = MLP_{g0+g}(x[g]);  x is [B, ldx] (x_gs = 0, shared) or [G, B, ldx].  keep_hidden=False: h1 / h2 are
+    scratch (the single-kernel forward skips writing them)."""
     check_cuda(x, y)
     W1, b1, W2, b2, W3, b3 = arena.ptrs(g0)
     _lib.lib().mlp_forward(W1, b1, W2, b2, W3, b3, _p(net_index), G, arena.D, arena.H, arena.O, x.data_ptr(),
-                           arena.D if ldx is None else ldx, x_gs, B, _p(h1), _p(h2), y.data_ptr(), impl,
-                           _lib.stream_ptr())
+                           arena.D if ldx is None else ldx, x_gs, B, _p(h1), _p(h2), int(bool(keep_hidden)),
+                           y.data_ptr(), impl, _lib.stream_ptr())
 
 
 def mlp_backward(arena, g0, G, x, B, h1, h2, dy, ldx=None, x_gs=0, dh2_extra=None, extra_scale=0.0, want_dw=True,

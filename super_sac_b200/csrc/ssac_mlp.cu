@@ -7,7 +7,9 @@ namespace ssac {
 int mlp_forward_simt(const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
                      const float* b3, const int32_t* net_index, int G, int D, int H, int O, const float* x, int64_t ldx,
                      int64_t x_gs, int B, float* h1, float* h2, float* y, cudaStream_t s, int impl, const HeadEpi* epi,
-                     int phase);
+                     int phase, int keep_hidden);
+void set_fused_forward(int on);
+int get_fused_forward();
 void set_overlap(int on);
 int get_overlap();
 int mlp_backward_simt(const float* W1, const float* W2, const float* W3, const int32_t* net_index, int G, int D, int H,
@@ -30,25 +32,27 @@ int ssac_set_default_mlp_impl(int impl) {
   return 0;
 }
 
+int ssac_set_fused_forward(int on) { set_fused_forward(on); return 0; }
+int ssac_get_fused_forward(void) { return get_fused_forward(); }
 int ssac_set_overlap(int on) { set_overlap(on); return 0; }
 int ssac_get_overlap(void) { return get_overlap(); }
 
 int ssac_mlp_forward(const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
                      const float* b3, const int32_t* net_index_dev, int G, int D, int H, int O, const float* x_dev,
-                     int64_t ldx, int64_t x_gs, int B, float* h1_dev, float* h2_dev, float* y_dev, int impl,
-                     void* stream) {
+                     int64_t ldx, int64_t x_gs, int B, float* h1_dev, float* h2_dev, int keep_hidden, float* y_dev,
+                     int impl, void* stream) {
   SSAC_REQUIRE(W1 && b1 && W2 && b2 && W3 && b3 && x_dev && y_dev, "ssac_mlp_forward: null pointer");
   SSAC_REQUIRE(G > 0 && D > 0 && H > 0 && O > 0 && B > 0 && ldx >= D, "ssac_mlp_forward: bad sizes");
   if (impl == 0) impl = ssac_default_mlp_impl();
   if (impl == 1 || impl == 2)
     return mlp_forward_simt(W1, b1, W2, b2, W3, b3, net_index_dev, G, D, H, O, x_dev, ldx, x_gs, B, h1_dev, h2_dev,
-                            y_dev, (cudaStream_t)stream, impl, nullptr, 0);
+                            y_dev, (cudaStream_t)stream, impl, nullptr, 0, keep_hidden);
   return fail(SSAC_E_UNSUPPORTED, "ssac_mlp_forward: unknown impl");
 }
 
 int ssac_actor_forward_sample(const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
                               const float* b3, int D, int H, int A, int deterministic, const float* x_dev, int64_t ldx,
-                              int B, float* h1_dev, float* h2_dev, float* out_dev, const float* eps_dev,
+                              int B, float* h1_dev, float* h2_dev, int keep_hidden, float* out_dev, const float* eps_dev,
                               const float* noise_dev, float sigma, float clip, float log_std_lo, float log_std_hi,
                               float* a_dev, int64_t lda, float* logp_dev, float* tanh_out_dev, int impl, void* stream) {
   SSAC_REQUIRE(W1 && b1 && W2 && b2 && W3 && b3 && x_dev && out_dev && a_dev && h1_dev && h2_dev,
@@ -62,7 +66,7 @@ int ssac_actor_forward_sample(const float* W1, const float* b1, const float* W2,
   e.eps = eps_dev; e.noise = noise_dev; e.sigma = sigma; e.clip = clip; e.lo = log_std_lo; e.hi = log_std_hi;
   e.a = a_dev; e.lda = lda; e.logp = logp_dev; e.tanh_out = tanh_out_dev; e.A = A;
   return mlp_forward_simt(W1, b1, W2, b2, W3, b3, nullptr, 1, D, H, deterministic ? A : 2 * A, x_dev, ldx, 0, B, h1_dev,
-                          h2_dev, out_dev, (cudaStream_t)stream, impl, &e, 0);
+                          h2_dev, out_dev, (cudaStream_t)stream, impl, &e, 0, keep_hidden);
 }
 
 int ssac_critic_forward_loss(const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
@@ -81,7 +85,7 @@ int ssac_critic_forward_loss(const float* W1, const float* b1, const float* W2, 
   e.inv_count = 1.f / ((float)B * (float)E * (float)(n_total > 0 ? n_total : N));
   e.dq = dq_dev; e.loss = loss_dev;
   return mlp_forward_simt(W1, b1, W2, b2, W3, b3, nullptr, N, D, H, 1, x_dev, ldx, 0, B, h1_dev, h2_dev, q_dev,
-                          (cudaStream_t)stream, impl, &e, phase);
+                          (cudaStream_t)stream, impl, &e, phase, 1);
 }
 
 int64_t ssac_mlp_backward_ws(int G, int B, int H) { return 2 * (int64_t)G * B * H; }

@@ -359,6 +359,11 @@ static int order_after(cudaStream_t from, cudaStream_t to, cudaEvent_t ev) {
 void set_overlap(int on) { g_overlap = on ? 1 : 0; }
 int get_overlap() { return g_overlap; }
 
+int launch_mlp3_fused(const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
+                      const float* b3, const int32_t* net_index, int G, int D, int H, int O, const float* x, int64_t ldx,
+                      int64_t x_gs, int B, float* h1, float* h2, int keep_hidden, float* y, const HeadEpi* epi,
+                      cudaStream_t s);   // ssac_mlp_fused.cu
+
 static GemmP blank() {
   GemmP p;
   p.A = nullptr; p.lda = 0; p.a_gs = 0; p.Bm = nullptr; p.ldb = 0; p.b_gs = 0; p.b_index = nullptr;
@@ -371,9 +376,15 @@ static GemmP blank() {
 int mlp_forward_simt(const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
                      const float* b3, const int32_t* net_index, int G, int D, int H, int O, const float* x, int64_t ldx,
                      int64_t x_gs, int B, float* h1, float* h2, float* y, cudaStream_t s, int impl, const HeadEpi* epi,
-                     int phase) {
+                     int phase, int keep_hidden) {
   // phase 0: all three layers; 1: trunk only (h1, h2); 2: output layer only (h2 already computed)
-  SSAC_REQUIRE(h1 && h2, "ssac_mlp_forward: h1/h2 buffers are required");
+  if (phase == 0 && impl == 2) {
+    // one kernel for the whole network when the shapes allow (2 x 256 nets); h1 / h2 only written when kept
+    const int rc = launch_mlp3_fused(W1, b1, W2, b2, W3, b3, net_index, G, D, H, O, x, ldx, x_gs, B, h1, h2, keep_hidden,
+                                     y, epi, s);
+    if (rc >= 0) return rc;
+  }
+  SSAC_REQUIRE(h1 && h2, "ssac_mlp_forward: h1/h2 buffers are required by the layered path");
   SSAC_REQUIRE(!epi || O <= kSmallO, "fused head epilogues need O <= 32");
   SSAC_REQUIRE(phase >= 0 && phase <= 2, "ssac_mlp_forward: phase must be 0, 1 or 2");
   g_impl = impl;

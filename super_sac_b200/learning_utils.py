@@ -335,11 +335,13 @@ def _actor_forward(agent, i, X, B, S, A, keep=False):
     return out, h1, h2
 
 
-def _policy_sample(agent, i, X, B, S, A, random_process, noise_clip, rsample=False, eps=None, noise=None):
+def _policy_sample(agent, i, X, B, S, A, random_process, noise_clip, rsample=False, eps=None, noise=None, keep=None):
     """a ~ pi_i(.|s) written into X[:, S:], with log-prob [B] (None when a noise process replaces the entropy term):
     actor MLP + policy head in one entry point (the head is fused into the output-layer kernel).  ``eps`` / ``noise``:
-    pre-drawn N(0,1) tensors (drawn here otherwise).  Returns dict(out, h1, h2, eps, logp, tanh_out)."""
+    pre-drawn N(0,1) tensors (drawn here otherwise).  Returns dict(out, h1, h2, eps, logp, tanh_out); h1 / h2 are only
+    valid when ``keep`` (default: rsample, i.e. a backward pass follows)."""
     dev = X.device
+    keep = rsample if keep is None else keep
     arena = agent._actor_arena
     h1 = torch.empty((1, B, arena.H), dtype=torch.float32, device=dev)
     h2 = torch.empty_like(h1)
@@ -373,7 +375,8 @@ def _policy_sample(agent, i, X, B, S, A, random_process, noise_clip, rsample=Fal
         logp = torch.empty((B,), dtype=torch.float32, device=dev)
     W1, b1, W2, b2, W3, b3 = arena.ptrs(i)
     _lib.lib().actor_forward_sample(W1, b1, W2, b2, W3, b3, arena.D, arena.H, A, int(det), X.data_ptr(), S + A, B,
-                                    h1.data_ptr(), h2.data_ptr(), out.data_ptr(), _ops._p(eps), _ops._p(noise), sigma, clip,
+                                    h1.data_ptr(), h2.data_ptr(), int(bool(keep)), out.data_ptr(), _ops._p(eps),
+                                    _ops._p(noise), sigma, clip,
                                     float(agent.log_std_low), float(agent.log_std_high), a_dst.data_ptr(), S + A,
                                     _ops._p(logp), _ops._p(tanh_out), 0, _lib.stream_ptr())
     res.update(eps=eps, logp=logp, tanh_out=tanh_out)
@@ -389,7 +392,7 @@ def _critic_values(agent, g0, G, X, B, net_index=None, keep=False):
     h1 = torch.empty((G, B, arena.H), dtype=torch.float32, device=X.device)
     h2 = torch.empty_like(h1)
     q = torch.empty((G, B, 1), dtype=torch.float32, device=X.device)
-    _ops.mlp_forward(arena, g0, G, X, B, h1, h2, q, ldx=X.shape[1], net_index=net_index)
+    _ops.mlp_forward(arena, g0, G, X, B, h1, h2, q, ldx=X.shape[1], net_index=net_index, keep_hidden=keep)
     return (q, h1, h2) if keep else q
 
 

@@ -281,13 +281,18 @@ def _arena_from(stack):
 
 @pytest.fixture
 def tma(request):
-    """impl 2 has two operand-staging paths (TMA and registers); run both."""
-    L().set_tma_enabled(int(getattr(request, "param", 1)))
+    """impl 2 has two operand-staging paths (TMA and registers) and, for 2 x 256-class nets, a single-kernel forward
+    next to the layered one; run all of them.  param: 1 = TMA + fused forward, 0 = registers, 2 = TMA, layered."""
+    mode = int(getattr(request, "param", 1))
+    L().set_tma_enabled(int(mode != 0))
+    L().set_fused_forward(int(mode == 1))
     yield
     L().set_tma_enabled(1)
+    L().set_fused_forward(1)
 
 
-IMPLS = [pytest.param(1, 1, id="ffma"), pytest.param(2, 1, id="tcgen05-tma"), pytest.param(2, 0, id="tcgen05-regs")]
+IMPLS = [pytest.param(1, 1, id="ffma"), pytest.param(2, 1, id="tcgen05-tma"), pytest.param(2, 0, id="tcgen05-regs"),
+         pytest.param(2, 2, id="tcgen05-layered")]
 
 
 @pytest.mark.parametrize("impl,tma", IMPLS, indirect=["tma"])
@@ -315,6 +320,7 @@ def test_mlp_forward_backward_matches_oracle(G, D, H, O, B, impl, tma):
         scale = float(h2w.abs().max())
         gu.assert_close(y[g].cpu().numpy(), yw.numpy(), 1e-4, 2e-5 * max(1.0, float(yw.abs().max())), f"y[{g}]")
         gu.assert_close(h2[g].cpu().numpy(), h2w.numpy(), 1e-4, 2e-5 * scale, f"h2[{g}]")
+        gu.assert_close(h1[g].cpu().numpy(), h1w.numpy(), 1e-4, 2e-5 * float(h1w.abs().max()), f"h1[{g}]")
         h1_ref[g], h2_ref[g] = h1w, h2w
         dx_want[g] = uo.mlp_backward(st, g, x, h1w, h2w, dy[g], grads, dh2_extra=0.25 * extra[g], need_dx=True)
     # the backward is checked on the oracle's activations: a pre-activation within rounding of zero may land on
@@ -364,6 +370,38 @@ def test_mlp_subset_and_per_group_inputs(impl, tma):
     _ops.mlp_forward(ar, 0, G, xg.to(DEV), B, h1, h2, y, x_gs=B * D, impl=impl)
     for g in range(G):
         gu.assert_close(y[g].cpu().numpy(), uo.mlp_forward(st, g, xg[g])[0].numpy(), 1e-4, 1e-5, f"per-group {g}")
+
+
+@pytest.mark.parametrize("G,D,H,O,B", [(10, 23, 256, 1, 256), (1, 17, 256, 12, 256), (3, 32, 256, 16, 200), (2, 4, 128, 2, 129),
+                                       (4, 9, 96, 1, 64), (2, 23, 32, 6, 1000), (3, 17, 48, 12, 300), (1, 8, 240, 3, 128)])
+def test_fused_forward_matches_oracle_and_layered(G, D, H, O, B):
+    """The single-kernel forward against the oracle and against the layered launches: ragged batch tiles, narrow and
+    full hidden widths, kept and discarded activations."""
+    from super_sac_b200 import _ops
+
+    gen = torch.Generator().manual_seed(G * 77 + H + B)
+    st = uo.MLPStack(G, D, H, O).random_init(gen)
+    ar = _arena_from(st)
+    x = torch.randn(B, D, generator=gen).to(DEV)
+    out = {}
+    for mode in ("fused", "fused-nokeep", "layered"):
+        L().set_fused_forward(int(mode != "layered"))
+        h1 = torch.full((G, B, H), float("nan"), device=DEV)
+        h2 = torch.full((G, B, H), float("nan"), device=DEV)
+        y = torch.full((G, B, O), float("nan"), device=DEV)
+        _ops.mlp_forward(ar, 0, G, x, B, h1, h2, y, impl=2, keep_hidden=(mode != "fused-nokeep"))
+        torch.cuda.synchronize()
+        out[mode] = (y.cpu(), h1.cpu(), h2.cpu())
+    L().set_fused_forward(1)
+    assert torch.isnan(out["fused-nokeep"][1]).all(), "keep_hidden=0 must not spend bandwidth on h1 (fused path not taken?)"
+    assert torch.equal(out["fused"][0], out["fused-nokeep"][0])
+    for g in range(G):
+        yw, h1w, h2w = uo.mlp_forward(st, g, x.cpu())
+        for mode in ("fused", "layered"):
+            y, h1, h2 = out[mode]
+            gu.assert_close(y[g].numpy(), yw.numpy(), 1e-4, 2e-5 * max(1.0, float(yw.abs().max())), f"{mode} y[{g}]")
+            gu.assert_close(h1[g].numpy(), h1w.numpy(), 1e-4, 2e-5 * float(h1w.abs().max()), f"{mode} h1[{g}]")
+            gu.assert_close(h2[g].numpy(), h2w.numpy(), 1e-4, 2e-5 * float(h2w.abs().max()), f"{mode} h2[{g}]")
 
 
 # ------------------------------------------------------------------------------------------------ heads / TD / weights
