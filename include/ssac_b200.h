@@ -69,10 +69,12 @@ int ssac_sumsq(const float* x_dev, int64_t n, float* out_dev, int accumulate, vo
  *                                       n_filled so that a captured graph follows a growing buffer
  *   normal_dev  float[n_normal]         N(0,1)
  *   subset_dev  int32[n_subsets*M]      n_subsets independent M-subsets of {0..N-1} (without replacement)
- *   shift_dev   int32[n_shift]          uniform in [0, shift_range)                                      */
+ *   shift_dev   int32[n_shift]          uniform in [0, shift_range)
+ *   zero_dev    float[n_zero]           set to 0 (the update's scalar-log / loss accumulators ride along instead of
+ *                                       costing a memset launch of their own)                            */
 int ssac_rng_fill(uint64_t* rng_dev, int64_t* idx_dev, int64_t n_idx, int64_t n_filled, const int64_t* n_filled_dev,
                   float* normal_dev, int64_t n_normal, int32_t* subset_dev, int n_subsets, int N, int M, int32_t* shift_dev,
-                  int64_t n_shift, int shift_range, void* stream);
+                  int64_t n_shift, int shift_range, float* zero_dev, int64_t n_zero, void* stream);
 
 /* ---- replay gather: replay.py:66-84 + learning_utils.py:186-197 (H2D + .float()) ------------------ */
 /* For each of n_arrays arrays: dst[b, :] = src[idx[b], :].  row_elems[k] elements per row;

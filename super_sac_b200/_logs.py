@@ -24,11 +24,20 @@ def deferred():
 
 
 class DeviceLogs(dict):
-    def __init__(self, device, capacity=256):
+    def __init__(self, device, capacity=256, zeroed=True):
+        """zeroed=False: the caller clears ``take_unzeroed()`` inside its first kernel (saves the memset launch)."""
         super().__init__()
-        self._buf = torch.zeros(capacity, dtype=torch.float32, device=device)
+        self._buf = (torch.zeros if zeroed else torch.empty)(capacity, dtype=torch.float32, device=device)
+        self._needs_zero = not zeroed
         self._n = 0
         self._pending = []  # (key, slot, transform)
+
+    def take_unzeroed(self):
+        """The buffer if it still has to be cleared (once), else None."""
+        if self._needs_zero:
+            self._needs_zero = False
+            return self._buf
+        return None
 
     def slots(self, n):
         """Reserve n consecutive float slots; returns (tensor view, first slot index)."""

@@ -34,8 +34,8 @@ class PhiloxSource:
         self._state.clear()
 
     def fill(self, device, idx=None, n_filled=0, normal=None, subset=None, N=0, M=0, shift=None, shift_range=0,
-             n_filled_dev=None):
-        """Fill any of the given pre-allocated device tensors in ONE launch."""
+             n_filled_dev=None, zero=None):
+        """Fill any of the given pre-allocated device tensors in ONE launch (``zero``: a float tensor to clear)."""
         L = _lib.lib()
         n_sub = 0 if subset is None else subset.numel() // M
         L.rng_fill(self._rng(device).data_ptr(),
@@ -44,6 +44,7 @@ class PhiloxSource:
                    None if normal is None else normal.data_ptr(), 0 if normal is None else normal.numel(),
                    None if subset is None else subset.data_ptr(), n_sub, int(N), int(M),
                    None if shift is None else shift.data_ptr(), 0 if shift is None else shift.numel(), int(shift_range),
+                   None if zero is None else zero.data_ptr(), 0 if zero is None else zero.numel(),
                    _lib.stream_ptr())
 
     # one-tensor conveniences --------------------------------------------------------------
@@ -102,7 +103,9 @@ class ScriptedSource:
         return self._pop("uniform01", out)
 
     def fill(self, device, idx=None, n_filled=0, normal=None, subset=None, N=0, M=0, shift=None, shift_range=0,
-             n_filled_dev=None):
+             n_filled_dev=None, zero=None):
+        if zero is not None:
+            zero.zero_()
         if idx is not None:
             self.indices(idx, n_filled)
         if normal is not None:

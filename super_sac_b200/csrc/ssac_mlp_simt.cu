@@ -218,26 +218,51 @@ __global__ void __launch_bounds__(256) head_forward_kernel(const float* __restri
 }
 
 // dz2[g][b][h] = (sum_o dy[g][b][o] * W3[wg][o][h] + s * extra[g][b][h]) * (h2[g][b][h] > 0)
+// VEC = 4: four consecutive h per thread (H % 4 == 0, 16-byte aligned rows), 32-bit index math
+template <int VEC>
 __global__ void __launch_bounds__(256) head_backward_data_kernel(const float* __restrict__ dy,
                                                                  const float* __restrict__ W3,
                                                                  const int32_t* __restrict__ net_index,
                                                                  const float* __restrict__ extra, float extra_scale,
                                                                  const float* __restrict__ h2, int G, int B, int H, int O,
                                                                  float* __restrict__ dz2) {
-  const int64_t n = (int64_t)G * B * H;
+  const int hv = H / VEC;                       // vectors per row
+  const int64_t n = (int64_t)G * B * hv;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int h = (int)(i % H);
-    const int64_t gb = i / H;
+    const int64_t gb = i / hv;
+    const int h = (int)(i - gb * hv) * VEC;
     const int g = (int)(gb / B);
     const int wg = net_index ? net_index[g] : g;
-    float acc = 0.f;
+    float acc[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
     if (dy) {
       const float* d = dy + gb * O;
       const float* W = W3 + (int64_t)wg * O * H + h;
-      for (int o = 0; o < O; ++o) acc = fmaf(d[o], __ldg(W + (int64_t)o * H), acc);
+      for (int o = 0; o < O; ++o) {
+        const float dv = d[o];
+        if (VEC == 4) {
+          const float4 w = __ldg(reinterpret_cast<const float4*>(W + (int64_t)o * H));
+          acc[0] = fmaf(dv, w.x, acc[0]); acc[1] = fmaf(dv, w.y, acc[1]);
+          acc[2] = fmaf(dv, w.z, acc[2]); acc[3] = fmaf(dv, w.w, acc[3]);
+        } else {
+          acc[0] = fmaf(dv, __ldg(W + (int64_t)o * H), acc[0]);
+        }
+      }
     }
-    if (extra) acc += extra_scale * extra[i];
-    dz2[i] = h2[i] > 0.f ? acc : 0.f;
+    const int64_t off = gb * H + h;
+    if (VEC == 4) {
+      if (extra) {
+        const float4 x = *reinterpret_cast<const float4*>(extra + off);
+        acc[0] += extra_scale * x.x; acc[1] += extra_scale * x.y; acc[2] += extra_scale * x.z; acc[3] += extra_scale * x.w;
+      }
+      const float4 m = *reinterpret_cast<const float4*>(h2 + off);
+      *reinterpret_cast<float4*>(dz2 + off) = make_float4(m.x > 0.f ? acc[0] : 0.f, m.y > 0.f ? acc[1] : 0.f,
+                                                          m.z > 0.f ? acc[2] : 0.f, m.w > 0.f ? acc[3] : 0.f);
+    } else {
+      if (extra) acc[0] += extra_scale * extra[off];
+      dz2[off] = h2[off] > 0.f ? acc[0] : 0.f;
+    }
   }
 }
 
@@ -298,10 +323,12 @@ int head_forward(const float* h2, const float* W3, const float* b3, const int32_
 }
 int head_backward_data(const float* dy, const float* W3, const int32_t* net_index, const float* extra, float extra_scale,
                        const float* h2, int G, int B, int H, int O, float* dz2, cudaStream_t s) {
-  const int64_t n = (int64_t)G * B * H;
+  const bool vec = (H % 4) == 0 && ((((uintptr_t)W3) | ((uintptr_t)h2) | ((uintptr_t)dz2) | ((uintptr_t)extra)) & 15) == 0;
+  const int64_t n = (int64_t)G * B * (vec ? H / 4 : H);
   int grid = (int)((n + 255) / 256);
   if (grid > 16 * kNumSMs) grid = 16 * kNumSMs;
-  head_backward_data_kernel<<<grid, 256, 0, s>>>(dy, W3, net_index, extra, extra_scale, h2, G, B, H, O, dz2);
+  if (vec) head_backward_data_kernel<4><<<grid, 256, 0, s>>>(dy, W3, net_index, extra, extra_scale, h2, G, B, H, O, dz2);
+  else head_backward_data_kernel<1><<<grid, 256, 0, s>>>(dy, W3, net_index, extra, extra_scale, h2, G, B, H, O, dz2);
   SSAC_CHECK_LAUNCH("mlp head backward (data)");
   return 0;
 }
@@ -310,6 +337,87 @@ int head_backward_weight(const float* dy, const float* h2, int G, int B, int H, 
   dim3 grid((H + 31) / 32, O, G);
   head_backward_weight_kernel<<<grid, 256, 0, s>>>(dy, h2, B, H, O, gW3, gb3, accumulate);
   SSAC_CHECK_LAUNCH("mlp head backward (weights)");
+  return 0;
+}
+
+// First-layer weight gradients for narrow inputs (D <= 32: cat(s, a) of the state-based configs):
+//   gW1[g][h][d] (+)= sum_b dz1[g][b][h] * x[g][b][d],   gb1[g][h] (+)= sum_b dz1[g][b][h]
+// A 256 x 23 output with K = 256 is far too small for a tensor-core tile pipeline to amortise its set-up, so this is
+// a plain FFMA kernel: block = (net, 32-wide h slab), lane = h, warp w owns batch rows b = w, w+8, ...; every thread
+// keeps all DP outputs of its h in registers, x rows are broadcast from shared memory, and the eight per-warp
+// partials are summed in a fixed order (bit-reproducible).
+template <int DP>
+__global__ void __launch_bounds__(256) first_layer_wgrad_kernel(const float* __restrict__ dz1, const float* __restrict__ x,
+                                                                int64_t ldx, int64_t x_gs, int B, int H, int D,
+                                                                float* __restrict__ gW1, float* __restrict__ gb1,
+                                                                int accumulate) {
+  constexpr int kRows = 256;                    // batch rows staged per pass
+  constexpr int kPartFloats = 8 * 32 * (DP + 1), kXFloats = kRows * DP;
+  __shared__ __align__(16) float shbuf[kPartFloats > kXFloats ? kPartFloats : kXFloats];   // x rows, then the partials
+  float (*xs)[DP] = reinterpret_cast<float (*)[DP]>(shbuf);
+  float (*part)[32][DP + 1] = reinterpret_cast<float (*)[32][DP + 1]>(shbuf);
+  const int g = blockIdx.y, h0 = blockIdx.x * 32, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int h = h0 + lane;
+  const float* dz = dz1 + (int64_t)g * B * H + (h < H ? h : 0);
+  const float* xg = x + (int64_t)g * x_gs;
+  float acc[DP], bsum = 0.f;
+#pragma unroll
+  for (int d = 0; d < DP; ++d) acc[d] = 0.f;
+  for (int b0 = 0; b0 < B; b0 += kRows) {
+    const int nb = min(kRows, B - b0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nb * DP; i += 256) {
+      const int r = i / DP, d = i - r * DP;
+      xs[r][d] = d < D ? __ldg(xg + (int64_t)(b0 + r) * ldx + d) : 0.f;
+    }
+    __syncthreads();
+    for (int r0 = warp; r0 < nb; r0 += 64) {
+      float dv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {             // eight independent loads in flight per thread
+        const int r = r0 + 8 * u;
+        dv[u] = (r < nb && h < H) ? __ldg(dz + (int64_t)(b0 + r) * H) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int r = r0 + 8 * u;
+        if (r < nb) {
+          bsum += dv[u];
+#pragma unroll
+          for (int d = 0; d < DP; d += 4) {
+            const float4 xv = *reinterpret_cast<const float4*>(&xs[r][d]);
+            acc[d + 0] = fmaf(dv[u], xv.x, acc[d + 0]); acc[d + 1] = fmaf(dv[u], xv.y, acc[d + 1]);
+            acc[d + 2] = fmaf(dv[u], xv.z, acc[d + 2]); acc[d + 3] = fmaf(dv[u], xv.w, acc[d + 3]);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();   // every warp is done with the x rows: the buffer becomes the partials
+#pragma unroll
+  for (int d = 0; d < DP; ++d) part[warp][lane][d] = acc[d];
+  part[warp][lane][DP] = bsum;
+  __syncthreads();
+  // 32 x (D + 1) results, summed over the eight warps in index order
+  for (int i = threadIdx.x; i < 32 * (DP + 1); i += 256) {
+    const int hl = i / (DP + 1), d = i - hl * (DP + 1);
+    if (h0 + hl >= H || (d < DP && d >= D)) continue;
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += part[w][hl][d];
+    float* out = d < DP ? gW1 + ((int64_t)g * H + h0 + hl) * D + d : gb1 + (int64_t)g * H + h0 + hl;
+    *out = accumulate ? *out + tot : tot;
+  }
+}
+
+static int first_layer_wgrad(const float* dz1, const float* x, int64_t ldx, int64_t x_gs, int G, int B, int H, int D,
+                             float* gW1, float* gb1, int accumulate, cudaStream_t s) {
+  dim3 grid((H + 31) / 32, G);
+  if (D <= 8) first_layer_wgrad_kernel<8><<<grid, 256, 0, s>>>(dz1, x, ldx, x_gs, B, H, D, gW1, gb1, accumulate);
+  else if (D <= 16) first_layer_wgrad_kernel<16><<<grid, 256, 0, s>>>(dz1, x, ldx, x_gs, B, H, D, gW1, gb1, accumulate);
+  else if (D <= 24) first_layer_wgrad_kernel<24><<<grid, 256, 0, s>>>(dz1, x, ldx, x_gs, B, H, D, gW1, gb1, accumulate);
+  else first_layer_wgrad_kernel<32><<<grid, 256, 0, s>>>(dz1, x, ldx, x_gs, B, H, D, gW1, gb1, accumulate);
+  SSAC_CHECK_LAUNCH("mlp backward gW1 (narrow input)");
   return 0;
 }
 
@@ -485,7 +593,8 @@ int mlp_backward_simt(const float* W1, const float* W2, const float* W3, const i
     q.A = dz1; q.lda = H; q.a_gs = (int64_t)B * H; q.Bm = x; q.ldb = ldx; q.b_gs = x_gs;
     q.C = gW1; q.ldc = D; q.c_gs = (int64_t)H * D; q.colsum = gb1; q.colsum_gs = H; q.M = H; q.N = D; q.K = B;
     q.accumulate = accumulate;
-    rc = launch_gemm(L_TN, q, G, gw1_on_side ? w : s, "mlp_backward gW1");
+    if (D <= 32) rc = first_layer_wgrad(dz1, x, ldx, x_gs, G, B, H, D, gW1, gb1, accumulate, gw1_on_side ? w : s);
+    else rc = launch_gemm(L_TN, q, G, gw1_on_side ? w : s, "mlp_backward gW1");
     if (rc) return rc;
   }
   if (dx) {

@@ -34,10 +34,12 @@ __global__ void __launch_bounds__(256) rng_fill_kernel(uint64_t* __restrict__ rn
                                                        float* __restrict__ normal,
                                                        int64_t n_normal, int32_t* __restrict__ subset, int n_subsets,
                                                        int N, int M, int32_t* __restrict__ shift, int64_t n_shift,
-                                                       int shift_range) {
+                                                       int shift_range, float* __restrict__ zero, int64_t n_zero) {
   const uint64_t seed = rng[0], offset = rng[1];
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+  if (zero)
+    for (int64_t i = tid; i < n_zero; i += nth) zero[i] = 0.f;
   if (idx) {
     if (n_filled_dev) n_filled = *n_filled_dev;
     for (int64_t i = tid; i < n_idx; i += nth) {
@@ -330,7 +332,7 @@ extern "C" {
 int ssac_rng_fill(uint64_t* rng, int64_t* idx, int64_t n_idx, int64_t n_filled, const int64_t* n_filled_dev,
                   float* normal, int64_t n_normal,
                   int32_t* subset, int n_subsets, int N, int M, int32_t* shift, int64_t n_shift, int shift_range,
-                  void* stream) {
+                  float* zero_dev, int64_t n_zero, void* stream) {
   SSAC_REQUIRE(rng, "ssac_rng_fill: null rng state");
   SSAC_REQUIRE(!idx || n_filled > 0 || n_filled_dev, "ssac_rng_fill: n_filled must be > 0");
   SSAC_REQUIRE(!subset || (N > 0 && N <= 64 && M > 0 && M <= N), "ssac_rng_fill: need 0 < M <= N <= 64");
@@ -343,7 +345,7 @@ int ssac_rng_fill(uint64_t* rng, int64_t* idx, int64_t n_idx, int64_t n_filled, 
   if (grid < 1) grid = 1;
   if (grid > 4 * kNumSMs) grid = 4 * kNumSMs;
   rng_fill_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rng, idx, n_idx, n_filled, n_filled_dev, normal, n_normal, subset,
-                                                          n_subsets, N, M, shift, n_shift, shift_range);
+                                                          n_subsets, N, M, shift, n_shift, shift_range, zero_dev, n_zero);
   SSAC_CHECK_LAUNCH("ssac_rng_fill");
   return 0;
 }

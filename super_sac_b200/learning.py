@@ -68,18 +68,22 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
     L, stream = _lib.lib(), _lib.stream_ptr()
     E, N, B = agent.ensemble_size, agent.num_critics, batch_size
     S, A = lu._dims(agent)
-    logs = _logs.DeviceLogs(dev)
+    logs = _logs.DeviceLogs(dev, zeroed=False)   # cleared by the first member's draw kernel
     loss_all, loss_slot = logs.slots(2 * E)   # per member: {loss contribution, mean td error of its last net}
     opt = _arena.FlatAdam.attach(critic_optimizer, ca)
     if parallel.is_sharded() and (E != 1 or dr3_coeff > 0 or critic_clip):
         raise NotImplementedError("critic sharding covers the REDQ shape (one member, no DR3 / global-norm clip)")
 
     replay_dicts, enc_outs = [], []
+    lu._mark("start")
     for i in range(E):
         loss_v = loss_all[2 * i:2 * i + 2]
-        draws = lu.draw_for_critic_member(buffer, agent, B, target_critic_ensemble_n, random_process, per)
+        draws = lu.draw_for_critic_member(buffer, agent, B, target_critic_ensemble_n, random_process, per,
+                                          zero=logs.take_unzeroed())
+        lu._mark("draws (indices, eps, subset)")
         rd = lu.sample_move_and_augment(buffer=buffer, batch_size=B, augmenter=augmenter, aug_mix=aug_mix, per=per,
                                         _idx=draws["idx"])
+        lu._mark("replay gather")
         o, a, *_ = rd["primary_batch"]
         packed = lu._packed_of(rd)
         s_rep = agent.encoder(o)
@@ -116,6 +120,7 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
                               None if imp_ptr is None else imp_ptr.data_ptr(), popart.state_ptr() if popart else None,
                               int(bool(pop)), E, n_total, dq.data_ptr(), loss_v.data_ptr(), 2 if side is not None else 0,
                               0, stream)
+        lu._mark("join online hidden layers + output layer + loss seed")
         extra, extra_scale, f1 = None, 0.0, None
         if dr3_coeff > 0:
             # DR3 (learning.py:100-108): second forward on (s1, a1); both feature sets carry gradient
@@ -137,6 +142,7 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
         if need_ds:
             enc_outs.append((s_rep, dxg.sum(0)[:, :S]))
         replay_dicts.append(rd)
+        lu._mark("ensemble backward")
 
     encoder_optimizer.zero_grad()
     if enc_outs:
@@ -159,6 +165,7 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
         main.wait_stream(side)
     else:
         gslot = lu._member_grad_norm_slot(logs, ca, member * N, (member + 1) * N)
+    lu._mark("Adam (+ logged grad norm)")
 
     if parallel.is_sharded():
         parallel.all_reduce_sum_(loss_all[0:1])   # each rank summed its own critics

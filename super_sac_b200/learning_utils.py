@@ -133,6 +133,18 @@ def _member_grad_norm_slot(logs, arena, g0, g1, stream=None):
     return slot
 
 
+# ---- stage marks (tools/stage_timeline.py): timing events recorded between the stages of an update, also inside a
+# captured CUDA graph (external events).  Off unless a tool sets ``_marks = []``.
+_marks = None
+
+
+def _mark(name):
+    if _marks is not None:
+        ev = torch.cuda.Event(enable_timing=True, external=True)
+        ev.record()
+        _marks.append((name, ev))
+
+
 _side_streams = {}
 
 
@@ -404,7 +416,7 @@ def _dims(agent):
     return agent._actor_arena.D, agent.act_space_size
 
 
-def draw_for_critic_member(buffer, agent, B, ensemble_n, random_process, per):
+def draw_for_critic_member(buffer, agent, B, ensemble_n, random_process, per, zero=None):
     """Every random draw one member's critic update consumes up front -- replay indices (replay.py:122), the policy's
     N(0,1) draw or the TD3 noise (learning_utils.py:49,330), the REDQ target subset (agent.py:29) -- in ONE launch."""
     dev = buffer.device
@@ -416,7 +428,7 @@ def draw_for_critic_member(buffer, agent, B, ensemble_n, random_process, per):
     normal = torch.empty((B, A), dtype=torch.float32, device=dev) if need_normal else None
     subset = torch.empty(ensemble_n, dtype=torch.int32, device=dev)
     _rng.source().fill(dev, idx=idx, n_filled=len(buffer), n_filled_dev=buffer._n_filled_dev, normal=normal,
-                       subset=subset, N=n_sub_pool, M=ensemble_n)
+                       subset=subset, N=n_sub_pool, M=ensemble_n, zero=zero)
     return dict(idx=idx, normal=normal, subset=subset)
 
 
@@ -456,6 +468,7 @@ def compute_td_targets(logs, replay_dict, agent, target_agent, ensemble_idx, ens
         q_t = q_all.index_select(0, net_index.long())
     else:
         q_t = _critic_values(target_agent, i * N, ensemble_n, X1, B, net_index=net_index)
+    _mark("target critics Q(s1, a1)")
     y = torch.empty((B, 1), dtype=torch.float32, device=X1.device)
     lv, slot = dlogs.slots(3)
     _lib.lib().td_target(q_t.data_ptr(), ensemble_n, B, None if pol["logp"] is None else pol["logp"].data_ptr(),
@@ -463,6 +476,7 @@ def compute_td_targets(logs, replay_dict, agent, target_agent, ensemble_idx, ens
                          popart.state_ptr() if popart else None, popart.ctl_ptr() if popart else None,
                          int(bool(pop)), float(popart.beta) if popart else 0.0, int(popart.min_steps) if popart else 0,
                          y.data_ptr(), lv.data_ptr(), _lib.stream_ptr())
+    _mark("td target")
     dlogs.defer(f"td_targets/mean_td_target_{i}", slot)
     dlogs.defer(f"td_targets/std_td_target_{i}", slot + 1)
     dlogs.defer(f"td_targets/entropy_bonus_{i}", slot + 2)

@@ -49,7 +49,7 @@ def test_bad_arguments_return_error_codes_not_crashes():
     with pytest.raises(_lib.SsacError, match="power of two"):
         lib.tree_set(1, 1, 12, 1, 1, 4, None)
     with pytest.raises(_lib.SsacError, match="M <= N"):
-        lib.rng_fill(1, None, 0, 0, None, None, 0, 1, 1, 4, 9, None, 0, 0, None)
+        lib.rng_fill(1, None, 0, 0, None, None, 0, 1, 1, 4, 9, None, 0, 0, None, 0, None)
 
 
 def test_arena_keeps_reference_parameter_surface():
