@@ -192,24 +192,41 @@ __global__ void __launch_bounds__(256) gather_aug_u8_kernel(const uint8_t* __res
   const int sx = aug ? shift[2 * b] - pad : 0, sy = aug ? shift[2 * b + 1] - pad : 0;
   float* dp = dst + ((int64_t)b * C + c) * plane_elems;
   const float* np = (noise && aug) ? noise + ((int64_t)b * C + c) * plane_elems : nullptr;
-  if ((W & 3) == 0 && (((uintptr_t)dp) & 15) == 0) {
+  if ((W & 3) == 0 && (((uintptr_t)dp) & 15) == 0 && (W >> 2) <= (int)blockDim.x) {
+    // thread = (row slot, 4-pixel column chunk): the column mapping (shift + clamp / reflect) is computed once per
+    // thread, each pass then costs one row mapping, four byte reads, four conversions and one 16-byte store
     const int w4 = W >> 2;
-    for (int i = threadIdx.x; i < H * w4; i += blockDim.x) {
-      const int y = i / w4, x0 = (i - y * w4) << 2;
-      const uint8_t* row = plane + (aug ? map_coord(y + sy, H, pad_mode) : y) * W;
-      float v[4];
+    const int rows_per_pass = (int)blockDim.x / w4;
+    const int slot = (int)threadIdx.x / w4, x0 = ((int)threadIdx.x - slot * w4) << 2;
+    if (slot < rows_per_pass) {
+      int xo[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int xs = aug ? map_coord(x0 + j + sx, W, pad_mode) : x0 + j;
-        v[j] = (float)row[xs];
-      }
-      if (np) {
-        const float4 nz = __ldg((const float4*)(np + (int64_t)y * W + x0));
-        v[0] += nz.x; v[1] += nz.y; v[2] += nz.z; v[3] += nz.w;
+      for (int j = 0; j < 4; ++j) xo[j] = aug ? map_coord(x0 + j + sx, W, pad_mode) : x0 + j;
+      const bool contiguous = (xo[1] == xo[0] + 1) && (xo[2] == xo[0] + 2) && (xo[3] == xo[0] + 3);
+      for (int y = slot; y < H; y += rows_per_pass) {
+        const uint8_t* row = plane + (aug ? map_coord(y + sy, H, pad_mode) : y) * W;
+        uint32_t px;   // four source pixels, byte j = output column x0 + j
+        if (contiguous) {
+          // interior chunk: two aligned 32-bit reads + a byte funnel instead of four byte reads
+          const uintptr_t a = (uintptr_t)(row + xo[0]);
+          const uint32_t* wp = (const uint32_t*)(a & ~(uintptr_t)3);
+          const uint32_t sh = (uint32_t)(a & 3);
+          const uint32_t lo = wp[0], hi = sh ? wp[1] : 0u;   // wp[1] stays inside the (16-byte padded) plane
+          px = __funnelshift_r(lo, hi, sh * 8);
+        } else {
+          px = (uint32_t)row[xo[0]] | ((uint32_t)row[xo[1]] << 8) | ((uint32_t)row[xo[2]] << 16) | ((uint32_t)row[xo[3]] << 24);
+        }
+        float v[4];
+        v[0] = (float)(px & 0xffu); v[1] = (float)((px >> 8) & 0xffu);
+        v[2] = (float)((px >> 16) & 0xffu); v[3] = (float)(px >> 24);
+        if (np) {
+          const float4 nz = __ldg((const float4*)(np + (int64_t)y * W + x0));
+          v[0] += nz.x; v[1] += nz.y; v[2] += nz.z; v[3] += nz.w;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = fminf(fmaxf(v[j], 0.f), 255.f);
+          for (int j = 0; j < 4; ++j) v[j] = fminf(fmaxf(v[j], 0.f), 255.f);
+        }
+        *(float4*)(dp + (int64_t)y * W + x0) = make_float4(v[0], v[1], v[2], v[3]);
       }
-      *(float4*)(dp + (int64_t)y * W + x0) = make_float4(v[0], v[1], v[2], v[3]);
     }
   } else {
     for (int i = threadIdx.x; i < H * W; i += blockDim.x) {
