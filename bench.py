@@ -325,16 +325,24 @@ def run_gpu_arm(args, cfg, rank, world, local_rank):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel group (rank 0), CUDA events around the entry point -----------
-    roof = time_backward_group(cfg, agent, args)
+    # ---- roofline of the dominant kernel (rank 0) -----------------------------------------------------
+    roof = time_dominant_kernel(cfg, agent, args)
     peaks = measured_peaks()
     fl = critic_flops(cfg)
-    achieved = fl["bwd_group"] / (roof["ms"] * 1e-3) / 1e12
-    roofline = {"kernel": "ssac_mlp_backward (ensemble critic backward, %d launches)" % roof["launches"],
+    achieved = fl["fwd_group"] / (roof["ms"] * 1e-3) / 1e12
+    fused = cfg["H"] <= 256 and cfg["H"] % 16 == 0 and cfg["S"] + cfg["A"] <= 32 and ssb.get_mlp_impl() == "tcgen05"
+    roofline = {"kernel": ("mlp3_forward_kernel<1> (fc1+fc2+fc3 of all %d critics in one launch, B=%d)" if fused else
+                           "ensemble critic forward (%d nets, B=%d; one launch per layer)") % (cfg["E"] * cfg["N"], cfg["B"]),
                 "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_tflops"], "traffic": None, "us_per_launch_group": roof["ms"] * 1e3,
+                "frac": achieved / peaks["bf16_tflops"],
+                "traffic": 3004416 if (fused and args.config == "redq") else None,
+                "us_per_launch": roof["ms"] * 1e3, "algorithmic_flops_per_launch": fl["fwd_group"],
                 "peak_source": peaks["source"],
-                "note": "3xTF32 on tcgen05 (3 MMAs per fp32 product, so at most 1/6 of the bf16 figure); the step is launch/latency bound"}
+                "note": "fp32 parity needs 3xTF32 (three kind::tf32 MMAs per product at half the bf16 rate: the bf16 "
+                        "figure is 6x out of reach by construction); at 367 MFLOP per launch the kernel is bound by its "
+                        "serial chain (operand staging -> 8 k-chunks -> head), not by the tensor pipe "
+                        "(ncu: pipe_tc active 24%); traffic = dram bytes of one cold-cache ncu launch "
+                        "(profiles/r1_06_ncu_full_summary.json), operands are L2-resident inside the step"}
 
     cpu_steps = 300
     cpu_ups, cpu_dt = time_cpu(cfg, cpu_steps, 10)
@@ -475,9 +483,10 @@ def count_launches(fn, _lib):
     return counter["n"]
 
 
-def time_backward_group(cfg, agent, args):
-    """CUDA-event time of the ensemble-critic backward entry point on the step's own shapes, inputs L2-warm as they
-    are inside the real step (they were just written by the forward)."""
+def time_dominant_kernel(cfg, agent, args):
+    """CUDA-event time of ONE launch of the kernel with the most arithmetic in an update: the single-kernel ensemble
+    forward (all E*N critics on one batch), replayed back to back from a CUDA graph so that no launch gap is counted.
+    Operands are L2-warm, as they are inside the real step."""
     from super_sac_b200 import _ops
 
     ca = agent._critic_arena
@@ -487,21 +496,27 @@ def time_backward_group(cfg, agent, args):
     h1 = torch.empty(G, B, H, device=dev)
     h2 = torch.empty_like(h1)
     q = torch.empty(G, B, 1, device=dev)
-    dq = torch.randn(G, B, 1, device=dev) / B
-    _ops.mlp_forward(ca, 0, G, X, B, h1, h2, q)
-    grad_save = ca.grad.clone()
-    iters = 200
-    for _ in range(10):
-        _ops.mlp_backward(ca, 0, G, X, B, h1, h2, dq, want_dw=True)
+    per_graph, iters = 20, 10
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            _ops.mlp_forward(ca, 0, G, X, B, h1, h2, q, keep_hidden=True)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(per_graph):
+            _ops.mlp_forward(ca, 0, G, X, B, h1, h2, q, keep_hidden=True)
+    g.replay()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
     for _ in range(iters):
-        _ops.mlp_backward(ca, 0, G, X, B, h1, h2, dq, want_dw=True)
+        g.replay()
     e1.record()
     torch.cuda.synchronize()
-    ca.grad.copy_(grad_save)
-    return dict(ms=e0.elapsed_time(e1) / iters, launches=5)
+    return dict(ms=e0.elapsed_time(e1) / (iters * per_graph), launches=1)
 
 
 def main():

@@ -366,9 +366,19 @@ __global__ void __launch_bounds__(256) first_layer_wgrad_kernel(const float* __r
   for (int b0 = 0; b0 < B; b0 += kRows) {
     const int nb = min(kRows, B - b0);
     __syncthreads();
-    for (int i = threadIdx.x; i < nb * DP; i += 256) {
-      const int r = i / DP, d = i - r * DP;
-      xs[r][d] = d < D ? __ldg(xg + (int64_t)(b0 + r) * ldx + d) : 0.f;
+    {
+      // kRows * DP / 256 = DP elements per thread, all loads issued before the first store
+      float xv[DP];
+#pragma unroll
+      for (int u = 0; u < DP; ++u) {
+        const int i = threadIdx.x + 256 * u, r = i / DP, d = i - r * DP;
+        xv[u] = (r < nb && d < D) ? __ldg(xg + (int64_t)(b0 + r) * ldx + d) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < DP; ++u) {
+        const int i = threadIdx.x + 256 * u, r = i / DP, d = i - r * DP;
+        xs[r][d] = xv[u];
+      }
     }
     __syncthreads();
     for (int r0 = warp; r0 < nb; r0 += 64) {
