@@ -89,6 +89,15 @@ int ssac_gather_rows(const void* const* srcs_dev, void* const* dsts_dev, const i
  * scatters field k (nbytes[k] bytes at staging_dev + src_off[k]) to dsts_dev[k].  Host arrays of n_fields (<= 16). */
 int ssac_scatter_fields(const void* staging_dev, void* const* dsts_dev, const int64_t* nbytes, const int64_t* src_off,
                         int n_fields, void* stream);
+/* The whole single-transition push in one call: H2D copy of the pinned staging row (row_bytes) into staging_dev, the field
+ * scatter of ssac_scatter_fields, and -- when sum_tree is given -- the PER leaf write + ancestor update of ssac_tree_set
+ * for the leaf index (int64 at staging + tree_idx_off) and priority (float64 at staging + tree_val_off).  `slot`
+ * (0..63) names the pinned row: the call records an event behind its copy, and ssac_push_row_wait(slot) blocks the host
+ * until that copy has completed (call it before refilling the pinned row). */
+int ssac_push_row(const void* host_row_pinned, void* staging_dev, int64_t row_bytes, int slot, void* const* dsts_dev,
+                  const int64_t* nbytes, const int64_t* src_off, int n_fields, double* sum_tree_dev, double* min_tree_dev,
+                  int64_t capacity, int64_t tree_idx_off, int64_t tree_val_off, void* stream);
+int ssac_push_row_wait(int slot);
 /* Fused pixel gather + DrQ / DrQv2 random shift + uint8 -> fp32 + aug_mix: augmentations.py:165-269,
  * learning_utils.py:193-206.   src u8 [capacity, C, H, W] -> dst f32 [B, C, H, W].
  * pad_mode 0: no shift, 1: replicate (DrQv2 integer crop), 2: reflect (DrQ v1).

@@ -117,9 +117,14 @@ def require_device(index):
 
 
 def stream_ptr():
+    """Raw handle of torch's current CUDA stream on the current device (the private C accessor is an order of
+    magnitude cheaper than building a torch.cuda.Stream object on every entry-point call)."""
     import torch
 
-    return torch.cuda.current_stream().cuda_stream
+    try:
+        return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
+    except AttributeError:
+        return torch.cuda.current_stream().cuda_stream
 
 
 def host_array(ctype, values):

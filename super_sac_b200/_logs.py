@@ -9,18 +9,39 @@ import contextlib
 import torch
 
 _defer_depth = 0
+_embed_readback = False   # capture the D2H copy of the logged scalars as the last node of the graph (auto-graph path)
 
 
 @contextlib.contextmanager
-def deferred():
+def deferred(embed_readback=False):
     """Inside this context ``finalize()`` does not synchronise (used while a CUDA graph is being captured);
-    call ``fetch()`` on the returned logs after the work has run."""
-    global _defer_depth
+    call ``fetch()`` on the returned logs after the work has run.  embed_readback: the device->host copy of the logged
+    scalars becomes the last node of the captured graph (for callers that read the logs after every replay)."""
+    global _defer_depth, _embed_readback
     _defer_depth += 1
+    prev, _embed_readback = _embed_readback, embed_readback
     try:
         yield
     finally:
         _defer_depth -= 1
+        _embed_readback = prev
+
+
+# Pinned host buffers for the read-back.  They are allocated outside stream capture (a captured update takes one from
+# the pool and owns it for the life of its graph: the D2H copy becomes a node of the graph).
+_pin_pool = []
+_pin_shared = {}
+_PIN_RESERVE = 8
+
+
+def _capturing():
+    return torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+
+
+def _reserve_pinned(capacity):
+    if not _capturing():
+        while len(_pin_pool) < _PIN_RESERVE:
+            _pin_pool.append(torch.empty(capacity, dtype=torch.float32).pin_memory())
 
 
 class DeviceLogs(dict):
@@ -29,6 +50,7 @@ class DeviceLogs(dict):
         super().__init__()
         self._buf = (torch.zeros if zeroed else torch.empty)(capacity, dtype=torch.float32, device=device)
         self._needs_zero = not zeroed
+        self._host = None   # pinned buffer written by a D2H node of the captured graph (set in finalize under capture)
         self._n = 0
         self._pending = []  # (key, slot, transform)
 
@@ -60,6 +82,10 @@ class DeviceLogs(dict):
 
     def finalize(self):
         if _defer_depth > 0:
+            if _embed_readback and self._pending and self._host is None and _capturing() and _pin_pool \
+                    and _pin_pool[-1].numel() >= self._buf.numel():
+                self._host = _pin_pool.pop()
+                self._host[: self._n].copy_(self._buf[: self._n], non_blocking=True)   # captured: replays with the graph
             return self
         return self.fetch()
 
@@ -67,9 +93,19 @@ class DeviceLogs(dict):
         """Resolve pending entries with one device->host copy.  keep=True leaves them registered so the same
         buffer can be read again after the next graph replay."""
         if self._pending:
-            host = self._buf[: self._n].cpu()  # the one sync
+            if self._host is not None:
+                torch.cuda.current_stream(self._buf.device).synchronize()   # the copy is part of the replayed graph
+                host = self._host[: self._n].tolist()
+            else:
+                _reserve_pinned(self._buf.numel())
+                pin = _pin_shared.get(self._buf.numel())
+                if pin is None:
+                    pin = _pin_shared[self._buf.numel()] = torch.empty(self._buf.numel(), dtype=torch.float32).pin_memory()
+                pin[: self._n].copy_(self._buf[: self._n], non_blocking=True)
+                torch.cuda.current_stream(self._buf.device).synchronize()   # the one sync
+                host = pin[: self._n].tolist()
             for key, slot, transform in self._pending:
-                val = sum(float(host[s_]) for s_ in slot) if isinstance(slot, (list, tuple)) else float(host[slot])
+                val = sum(host[s_] for s_ in slot) if isinstance(slot, (list, tuple)) else host[slot]
                 self[key] = transform(val) if transform is not None else val
             if not keep:
                 self._pending = []

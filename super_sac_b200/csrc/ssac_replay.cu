@@ -156,6 +156,35 @@ __global__ void __launch_bounds__(256) scatter_fields_kernel(const uint8_t* __re
   }
 }
 
+// One pushed transition: field scatter (blockIdx.y < n_fields) + the PER leaf / ancestor update (last block row; the
+// leaf index and priority are read from the staging row itself, so there is no dependency between the blocks).
+__global__ void __launch_bounds__(256) push_row_kernel(const uint8_t* __restrict__ staging, ScatterArgs a, int n_fields,
+                                                       double* __restrict__ sum_tree, double* __restrict__ min_tree,
+                                                       int64_t capacity, int64_t idx_off, int64_t val_off) {
+  const int k = blockIdx.y;
+  if (k < n_fields) {
+    const uint8_t* src = staging + a.src_off[k];
+    uint8_t* dst = (uint8_t*)a.dst[k];
+    const int64_t n = a.nbytes[k];
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+    if (((((uintptr_t)src) | ((uintptr_t)dst) | (uintptr_t)n) & 15) == 0) {
+      for (int64_t i = tid; i < (n >> 4); i += nth) ((int4*)dst)[i] = ((const int4*)src)[i];
+    } else {
+      for (int64_t i = tid; i < n; i += nth) dst[i] = src[i];
+    }
+  } else if (blockIdx.x == 0 && threadIdx.x == 0 && sum_tree) {
+    const int64_t leaf = *reinterpret_cast<const int64_t*>(staging + idx_off);
+    const double val = *reinterpret_cast<const double*>(staging + val_off);
+    int64_t node = leaf + capacity;
+    sum_tree[node] = val;
+    min_tree[node] = val;
+    for (node >>= 1; node >= 1; node >>= 1) {
+      sum_tree[node] = sum_tree[2 * node] + sum_tree[2 * node + 1];
+      min_tree[node] = fmin(min_tree[2 * node], min_tree[2 * node + 1]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // fused pixel gather + shift (+noise) + uint8->fp32: augmentations.py:165-269, learning_utils.py:193-206
 // One block per (sample, channel-plane): the u8 plane is staged in shared memory with 16-byte loads, then
@@ -405,6 +434,58 @@ int ssac_scatter_fields(const void* staging, void* const* dsts, const int64_t* n
   if (gx > 64) gx = 64;
   scatter_fields_kernel<<<dim3(gx, n_fields), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)staging, a);
   SSAC_CHECK_LAUNCH("ssac_scatter_fields");
+  return 0;
+}
+
+// one event per pinned slot and device: the host may rewrite a slot once its last H2D copy has completed
+static cudaEvent_t g_push_events[64][64];
+static bool g_push_recorded[64][64];
+
+int ssac_push_row(const void* host_row_pinned, void* staging_dev, int64_t row_bytes, int slot, void* const* dsts,
+                  const int64_t* nbytes, const int64_t* src_off, int n_fields, double* sum_tree, double* min_tree,
+                  int64_t capacity, int64_t tree_idx_off, int64_t tree_val_off, void* stream) {
+  SSAC_REQUIRE(host_row_pinned && staging_dev && row_bytes > 0 && dsts && nbytes && src_off && n_fields > 0 &&
+                   n_fields < kMaxGatherArrays, "ssac_push_row: bad args (1..15 fields)");
+  SSAC_REQUIRE(slot >= 0 && slot < 64, "ssac_push_row: slot must be in 0..63");
+  SSAC_REQUIRE(!sum_tree || (min_tree && capacity > 0 && (capacity & (capacity - 1)) == 0 && tree_idx_off >= 0 &&
+                             tree_val_off >= 0 && (tree_idx_off & 7) == 0 && (tree_val_off & 7) == 0),
+               "ssac_push_row: bad tree arguments");
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess || dev < 0 || dev >= 64) return fail(SSAC_E_BADARG, "ssac_push_row: bad device");
+  if (!g_push_events[dev][slot]) {
+    e = cudaEventCreateWithFlags(&g_push_events[dev][slot], cudaEventDisableTiming);
+    if (e != cudaSuccess) { set_error(std::string("ssac_push_row event: ") + cudaGetErrorString(e)); return (int)e; }
+  }
+  ScatterArgs a;
+  int64_t mx = 0;
+  for (int k = 0; k < n_fields; ++k) {
+    SSAC_REQUIRE(dsts[k] && nbytes[k] > 0 && src_off[k] >= 0, "ssac_push_row: bad field");
+    a.dst[k] = dsts[k]; a.nbytes[k] = nbytes[k]; a.src_off[k] = src_off[k];
+    if (nbytes[k] > mx) mx = nbytes[k];
+  }
+  e = cudaMemcpyAsync(staging_dev, host_row_pinned, (size_t)row_bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream);
+  if (e == cudaSuccess) e = cudaEventRecord(g_push_events[dev][slot], (cudaStream_t)stream);
+  if (e != cudaSuccess) { set_error(std::string("ssac_push_row copy: ") + cudaGetErrorString(e)); return (int)e; }
+  g_push_recorded[dev][slot] = true;
+  int gx = (int)((mx / 16 + 255) / 256);
+  if (gx < 1) gx = 1;
+  if (gx > 64) gx = 64;
+  push_row_kernel<<<dim3(gx, n_fields + 1), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)staging_dev, a, n_fields, sum_tree,
+                                                                           min_tree, capacity, tree_idx_off, tree_val_off);
+  SSAC_CHECK_LAUNCH("ssac_push_row");
+  return 0;
+}
+
+int ssac_push_row_wait(int slot) {
+  SSAC_REQUIRE(slot >= 0 && slot < 64, "ssac_push_row_wait: slot must be in 0..63");
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess || dev < 0 || dev >= 64) return fail(SSAC_E_BADARG, "ssac_push_row_wait: bad device");
+  if (g_push_recorded[dev][slot]) {
+    e = cudaEventSynchronize(g_push_events[dev][slot]);
+    if (e != cudaSuccess) { set_error(std::string("ssac_push_row_wait: ") + cudaGetErrorString(e)); return (int)e; }
+  }
   return 0;
 }
 

@@ -87,7 +87,7 @@ def run_cached(key, fn, on_replay=None):
             return fn()
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
-        with _logs.deferred():
+        with _logs.deferred(embed_readback=True):   # this path fetches the logs after every replay
             with torch.cuda.graph(g):
                 e.result = fn()
         e.graph, e.on_replay = g, on_replay

@@ -23,11 +23,18 @@ def _opt_sig(opt):
     return (id(opt), pg["lr"], tuple(pg["betas"]), pg["eps"], pg["weight_decay"])
 
 
+def _encoder_trainable(agent):
+    ps = agent.__dict__.get("_ssac_encoder_params")
+    if ps is None:   # walking the module tree on every update call costs more than the check itself
+        ps = agent.__dict__["_ssac_encoder_params"] = [p for p in agent.encoder.parameters() if p.numel() > 2]
+    return any(p.requires_grad for p in ps)
+
+
 def _graphable(agent, random_process, per, update_priorities):
     """Static shapes, device-side randomness, no PyTorch autograd hand-off, no host-side decisions."""
     return (graphed.auto_graphs_enabled() and isinstance(_rng.source(), _rng.PhiloxSource) and not per and
             not update_priorities and random_process is None and not parallel.is_sharded() and
-            not any(p.requires_grad for p in agent.encoder.parameters() if p.numel() > 2))
+            not _encoder_trainable(agent))
 
 
 def critic_update(buffer, agent, target_agent, critic_optimizer, encoder_optimizer, log_alphas, batch_size, gamma,

@@ -172,66 +172,77 @@ class ReplayBuffer:
 
         st = self._storage
         if not hasattr(self, "_stage"):
-            fields = []   # (dst tensor getter, nbytes)
-            off = 0
-            lay = []
+            # layout of one staging row: [s, s1 per obs key] action reward done fill | tree idx, priority (not scattered)
+            lay, dst_base, dst_stride, kinds, off = [], [], [], [], 0
+
+            def add(nb, tensor, kind):
+                nonlocal off
+                lay.append((off, nb))
+                dst_base.append(tensor.data_ptr() if tensor is not None else 0)
+                dst_stride.append(tensor.stride(0) * tensor.element_size() if tensor is not None and kind != "fixed" else 0)
+                kinds.append(kind)
+                off = (off + nb + 15) // 16 * 16
+
             for label in st.s_stack:
                 for stack in (st.s_stack[label], st.s1_stack[label]):
-                    nb = stack[0].numel() * stack.element_size()
-                    lay.append((off, nb)); off = (off + nb + 15) // 16 * 16
-            for nb in (st.action_stack[0].numel() * 4, 4, 1, 8, 8, 8):   # action, reward, done, tree idx, priority, fill
-                lay.append((off, nb)); off = (off + nb + 15) // 16 * 16
+                    add(stack[0].numel() * stack.element_size(), stack, "ring")
+            add(st.action_stack[0].numel() * 4, st.action_stack, "ring")
+            add(4, st.reward_stack, "ring")
+            add(1, st.done_stack, "ring")
+            add(8, self._n_filled_dev, "fixed")
+            self._n_scatter = len(lay)
+            add(8, None, "tree")
+            add(8, None, "tree")
             self._stage_layout, self._stage_bytes = lay, off
             self._stage = torch.empty((self._STAGE_SLOTS, off), dtype=torch.uint8).pin_memory()
             self._stage_dev = torch.empty((self._STAGE_SLOTS, off), dtype=torch.uint8, device=self.device)
-            self._stage_events = [None] * self._STAGE_SLOTS
             self._stage_next = 0
-            self._tree_idx_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
-            self._tree_val_dev = torch.zeros(1, dtype=torch.float64, device=self.device)
+            self._dst_base, self._dst_stride = dst_base, dst_stride
+            n = self._n_scatter
+            self._c_dsts = (ctypes.c_void_p * n)()
+            self._c_nbytes = (ctypes.c_int64 * n)(*[nb for _, nb in lay[:n]])
+            self._c_offs = (ctypes.c_int64 * n)(*[o for o, _ in lay[:n]])
+            # typed numpy views of every field of every pinned row: one assignment per field and push
+            host = self._stage.numpy()
+            views = []
+            for slot in range(self._STAGE_SLOTS):
+                row, k, v = host[slot], 0, []
+                for label in st.s_stack:
+                    for _ in range(2):
+                        o, nb = lay[k]; k += 1
+                        v.append(row[o:o + nb].view(st.s_dtypes[label]).reshape(st.s_stack[label].shape[1:]))
+                for dt in (np.float32, np.float32, np.uint8, np.int64, np.int64, np.float64):
+                    o, nb = lay[k]; k += 1
+                    v.append(row[o:o + nb].view(dt))
+                views.append(v)
+            self._stage_views = views
+            self._stage_host_ptr = self._stage.data_ptr()
+            self._stage_dev_ptr = self._stage_dev.data_ptr()
+        L = _lib.lib()
         slot = self._stage_next
         self._stage_next = (slot + 1) % self._STAGE_SLOTS
-        ev = self._stage_events[slot]
-        if ev is not None:
-            ev.synchronize()   # the H2D copy that last used this pinned slot has finished
-        host = self._stage[slot].numpy()
-        lay = self._stage_layout
+        L.push_row_wait(slot)   # the H2D copy that last used this pinned row has finished
+        v = self._stage_views[slot]
         pos = st._next_idx
         k = 0
-        dsts = []
         for label in st.s_stack:
-            for stack, src in ((st.s_stack[label], state[label]), (st.s1_stack[label], next_state[label])):
-                off, nb = lay[k]; k += 1
-                host[off:off + nb] = np.ascontiguousarray(np.asarray(src).astype(st.s_dtypes[label])).view(np.uint8).reshape(-1)
-                dsts.append(stack[pos].data_ptr())
-        off, nb = lay[k]; k += 1
-        host[off:off + nb] = np.asarray(action, dtype=np.float32).view(np.uint8).reshape(-1)
-        dsts.append(st.action_stack[pos].data_ptr())
-        off, nb = lay[k]; k += 1
-        host[off:off + nb] = np.asarray([reward], dtype=np.float32).view(np.uint8)
-        dsts.append(st.reward_stack[pos].data_ptr())
-        off, nb = lay[k]; k += 1
-        host[off] = np.uint8(bool(done))
-        dsts.append(st.done_stack[pos].data_ptr())
+            v[k][...] = state[label]; v[k + 1][...] = next_state[label]
+            k += 2
+        v[k][...] = action
+        v[k + 1][0] = reward
+        v[k + 2][0] = bool(done)
         filled = min(max(pos + 1, st._max_filled), st.size)
-        off, nb = lay[k]; k += 1
-        host[off:off + 8] = np.asarray([pos], dtype=np.int64).view(np.uint8)
-        dsts.append(self._tree_idx_dev.data_ptr())
-        off, nb = lay[k]; k += 1
-        host[off:off + 8] = np.asarray([priority], dtype=np.float64).view(np.uint8)
-        dsts.append(self._tree_val_dev.data_ptr())
-        off, nb = lay[k]; k += 1
-        host[off:off + 8] = np.asarray([filled], dtype=np.int64).view(np.uint8)
-        dsts.append(self._n_filled_dev.data_ptr())
-        self._stage_dev[slot].copy_(self._stage[slot], non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record()
-        self._stage_events[slot] = ev
-        L = _lib.lib()
-        n = len(lay)
-        L.scatter_fields(self._stage_dev[slot].data_ptr(), _lib.host_array(ctypes.c_void_p, dsts),
-                         _lib.host_array(ctypes.c_int64, [nb for _, nb in lay]),
-                         _lib.host_array(ctypes.c_int64, [o for o, _ in lay]), n, _lib.stream_ptr())
-        self._tree_set(self._tree_idx_dev, self._tree_val_dev)
+        v[k + 3][0] = filled
+        v[k + 4][0] = pos
+        v[k + 5][0] = priority
+        dsts, base, stride = self._c_dsts, self._dst_base, self._dst_stride
+        for i in range(self._n_scatter):
+            dsts[i] = base[i] + pos * stride[i]
+        lay = self._stage_layout
+        nb = self._stage_bytes
+        L.push_row(self._stage_host_ptr + slot * nb, self._stage_dev_ptr + slot * nb, nb, slot, dsts, self._c_nbytes,
+                   self._c_offs, self._n_scatter, self._it_sum.data_ptr(), self._it_min.data_ptr(), self._capacity,
+                   lay[-2][0], lay[-1][0], _lib.stream_ptr())
         st._max_filled = filled
         st._next_idx = (pos + 1) % st.size
         return np.array([pos])
