@@ -223,6 +223,7 @@ def run_gpu_arm(args, cfg, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=device)
     ssb.set_mlp_impl(args.mlp_impl)
     ssb.set_overlap(not args.no_overlap)
+    ssb.set_pdl(not args.no_pdl)
     agent, target, critic_opt, enc_opt, log_alphas, buf = build_gpu(cfg, device, seed=rank)
     B = cfg["B"]
     augmenter = augmentations.AugmentationSequence([augmentations.IdentityAug(B)])
@@ -355,7 +356,8 @@ def run_gpu_arm(args, cfg, rank, world, local_rank):
                    "l2": "replay ring %.0f MB > 126 MB L2 (random rows); parameters+moments (11.6 MB) are L2-resident by design"
                          % (buf_bytes(buf) / 1e6),
                    "impl": "ensemble MLP GEMMs: " + ssb.get_mlp_impl(),
-                   "overlap": "two-stream fork/join inside the update" if not args.no_overlap else "off"},
+                   "overlap": "two-stream fork/join inside the update" if not args.no_overlap else "off",
+                   "pdl": "programmatic dependent launch along the critical path" if not args.no_pdl else "off"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_steps, "path": "buffer.push(host transition, H2D) + learning.critic_update (auto CUDA graph) + "
@@ -528,6 +530,7 @@ def main():
     ap.add_argument("--config", default="redq", choices=sorted(CONFIGS))
     ap.add_argument("--mlp-impl", default="tcgen05", choices=["tcgen05", "ffma"])
     ap.add_argument("--no-overlap", action="store_true", help="serialise the independent branches of the update (A/B switch)")
+    ap.add_argument("--no-pdl", action="store_true", help="plain stream-ordered launches instead of programmatic dependent launch")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))

@@ -134,6 +134,12 @@ int ssac_set_tma_enabled(int on);
  * on `stream`.  Results are identical either way.  Default 1. */
 int ssac_set_overlap(int on);
 int ssac_get_overlap(void);
+/* Programmatic dependent launch for the kernels of the update's critical path (replay gather, single-kernel forward, TD
+ * target, dz2, dz1 GEMM, gW1): each is launched so that its set-up (TMEM allocation, barrier init, parameter loads)
+ * overlaps the tail of its predecessor in the stream; `griddepcontrol.wait` guards everything an earlier kernel
+ * produced.  0 = plain stream-ordered launches.  Results are identical.  Default 1. */
+int ssac_set_pdl(int on);
+int ssac_get_pdl(void);
 /* impl 2, 2 x 256-class networks (H in 32..256 and a multiple of 16, first-layer width <= 32, O <= 16): the whole forward
  * (three layers + head epilogue) runs as ONE kernel that keeps the activations in tensor / shared memory.  h1 / h2 are
  * then written only when keep_hidden != 0 (a backward pass will read them); with keep_hidden == 0 their contents are

@@ -53,5 +53,11 @@ def set_fused_forward(on):
     _lib.lib().set_fused_forward(int(bool(on)))
 
 
+def set_pdl(on):
+    """Programmatic dependent launch along the update's critical path (each kernel's set-up overlaps the tail of its
+    predecessor).  On by default; results do not change."""
+    _lib.lib().set_pdl(int(bool(on)))
+
+
 __all__ = ["Agent", "agent", "nets", "replay", "learning", "learning_utils", "augmentations", "popart",
-           "adv_estimator", "device", "manual_seed", "set_mlp_impl", "get_mlp_impl", "set_overlap", "set_fused_forward"]
+           "adv_estimator", "device", "manual_seed", "set_mlp_impl", "get_mlp_impl", "set_overlap", "set_fused_forward", "set_pdl"]

@@ -29,6 +29,33 @@ int fail(int code, const char* what);
 
 constexpr int kNumSMs = 148;  // B200
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------------------------
+// A kernel launched with launch_pdl() may start while its predecessor in the stream is still running; it must execute
+// pdl_wait() before touching anything an earlier kernel produced (or still reads), and only then pdl_trigger(), so that
+// at most ONE predecessor is ever in flight behind it.  Whatever precedes pdl_wait() (TMEM allocation, barrier set-up,
+// loads of parameters that only Adam / Polyak write -- kernels that never trigger early) overlaps the predecessor's
+// tail.  Without the launch attribute both instructions are no-ops, so the same kernels serve every launch site.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();   // ssac_set_pdl (ssac_elementwise.cu)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

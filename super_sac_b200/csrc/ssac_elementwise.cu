@@ -33,6 +33,7 @@ __device__ __forceinline__ float polyak1(float t, float s, float c1, float c2) {
 template <int UNROLL>
 __global__ void __launch_bounds__(256) polyak_kernel(float* __restrict__ t, const float* __restrict__ s, int64_t n,
                                                      float c1, float c2) {
+  pdl_wait();   // no early trigger: writes the target parameters
   const bool vec = ((((uintptr_t)t) | ((uintptr_t)s)) & 15) == 0;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
@@ -106,11 +107,16 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float*
                                                    int write_back, float c1, float c2) {
   __shared__ AdamScalars sc;
   if (threadIdx.x == 0) {
+    // the step counter is only ever written by this optimiser's own previous launch: the (double-precision) bias
+    // corrections can be evaluated while the kernel that produces the last gradients is still running (PDL)
     const int t = ctl[0] + 1;
     const double bc1 = 1.0 - pow(b1d, (double)t);
     const double bc2 = 1.0 - pow(b2d, (double)t);
     sc.step_size = (float)(lr / bc1);
     sc.bc2_sqrt = (float)sqrt(bc2);
+  }
+  pdl_wait();   // no early trigger: this kernel writes the parameters that later kernels prefetch
+  if (threadIdx.x == 0) {
     float coef = 1.f;
     if (gnorm_sq != nullptr && max_norm > 0.f) coef = fminf(1.f, max_norm / (sqrtf(*gnorm_sq) + 1e-6f));
     sc.clip_coef = coef;
@@ -334,6 +340,8 @@ __global__ void __launch_bounds__(1024) td_target_kernel(const float* __restrict
                                                          int32_t* __restrict__ popart_ctl, int pop, double pa_beta,
                                                          int pa_min_steps, float* __restrict__ y,
                                                          float* __restrict__ logs) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float scratch[32];
   __shared__ float sh[4];
   const float alpha = (logp && log_alpha) ? expf(*log_alpha) : (logp ? 1.f : 0.f);
@@ -603,7 +611,19 @@ __global__ void min_over_nets_kernel(const float* __restrict__ q, int N, int B, 
 
 using namespace ssac;
 
+namespace ssac {
+static int g_pdl = 1;
+bool pdl_enabled() { return g_pdl != 0; }
+}  // namespace ssac
+
 extern "C" {
+
+int ssac_set_pdl(int on) {
+  ssac::g_pdl = on ? 1 : 0;
+  return 0;
+}
+int ssac_get_pdl(void) { return ssac::g_pdl; }
+
 
 const char* ssac_last_error(void) { return g_last_error.c_str(); }
 int ssac_version(void) { return 100; }
@@ -628,7 +648,7 @@ int ssac_polyak(float* target, const float* source, int64_t n, double tau, void*
   SSAC_REQUIRE(target && source, "ssac_polyak: null pointer");
   const float c1 = (float)(1.0 - tau), c2 = (float)tau;
   const int grid = grid_for((n + 3) / 4, 256 * 4, 8);
-  polyak_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(target, source, n, c1, c2);
+  launch_pdl(polyak_kernel<4>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, target, source, n, c1, c2);
   SSAC_CHECK_LAUNCH("ssac_polyak");
   return 0;
 }
@@ -655,11 +675,11 @@ static int adam_launch(bool polyak, float* p, float* g, float* m, float* v, floa
   const float c1 = (float)(1.0 - tau), c2 = (float)tau;
   if (polyak) {
     SSAC_REQUIRE(tgt, "ssac_adam_polyak_step: null target");
-    adam_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, tgt, n, ctl, lr, b1, b2, (float)eps, (float)wd,
-                                                               gnorm_sq, (float)max_norm, wb, c1, c2);
+    launch_pdl(adam_kernel<true>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, tgt, n, ctl, lr, b1, b2, (float)eps,
+               (float)wd, gnorm_sq, (float)max_norm, wb, c1, c2);
   } else {
-    adam_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, nullptr, n, ctl, lr, b1, b2, (float)eps,
-                                                                (float)wd, gnorm_sq, (float)max_norm, wb, 0.f, 0.f);
+    launch_pdl(adam_kernel<false>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, (float*)nullptr, n, ctl, lr, b1, b2,
+               (float)eps, (float)wd, gnorm_sq, (float)max_norm, wb, 0.f, 0.f);
   }
   SSAC_CHECK_LAUNCH("ssac_adam_step");
   return 0;
@@ -742,7 +762,7 @@ int ssac_td_target(const float* q_t, int M, int B, const float* logp, const floa
                    int popart_min_steps, float* y, float* logs, void* stream) {
   SSAC_REQUIRE(q_t && r && d && y && M > 0 && B > 1, "ssac_td_target: bad args");
   SSAC_REQUIRE((popart == nullptr) == (popart_ctl == nullptr), "ssac_td_target: popart state and ctl go together");
-  td_target_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(q_t, M, B, logp, log_alpha, r, d, gamma, popart, popart_ctl,
+  launch_pdl(td_target_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream, q_t, M, B, logp, log_alpha, r, d, gamma, popart, popart_ctl,
                                                          pop, popart_beta, popart_min_steps, y, logs);
   SSAC_CHECK_LAUNCH("ssac_td_target");
   return 0;

@@ -21,6 +21,7 @@ struct GemmP {
   float* colsum; int64_t colsum_gs;                                    // L_TN: colsum[m] = sum_k A[k][m]  (bias grads)
   int M, N, K;
   int relu, accumulate;
+  int pdl;   // host side: launch with programmatic stream serialization (the predecessor in the stream is PDL-aware)
 };
 
 int launch_gemm_tc(int layout, const GemmP& p, int G, cudaStream_t s, const char* what);

@@ -137,6 +137,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int rank = (int)cluster_rank();
   const int g = blockIdx.y, m0 = (blockIdx.x >> 1) * FM;
+  // net_index (REDQ subset) was drawn at least two launches ago: complete under the PDL rule (ssac_common.cuh)
   const int wg = q.net_index ? q.net_index[g] : g;
   const int H = q.H, D = q.D, O = q.O, B = q.B;
   const int nk = (H + FK - 1) / FK;               // H is a multiple of 16: the last chunk may be half empty
@@ -150,11 +151,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   // and to whole 128-row tiles; the 23-wide rows of cat(s, a) are neither 16-byte aligned nor TMA-addressable)
   float4 va[4], vb[4], vc[4];
   if (active && warp < 8) {
-    const float* X = q.x + (int64_t)g * q.x_gs;
     const float* W1 = q.W1 + (int64_t)wg * H * D;
-    const bool x_vec = ((q.ldx & 3) == 0) && ((((uintptr_t)X) & 15) == 0);
     const bool w_vec = ((D & 3) == 0) && ((((uintptr_t)W1) & 15) == 0);
-    load_kmajor(va, X, q.ldx, m0, B, 0, D, x_vec);
     load_kmajor(vb, W1, D, 0, H, 0, D, w_vec);
     if (H > 128) load_kmajor(vc, W1, D, 128, H, 0, D, w_vec);
   }
@@ -190,18 +188,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   const uint32_t tmem = tmem_base_sh;
   const uint32_t sbase = smem_u32(smem);
   if (t == 0) FZ_TRACE(1);
+  auto issue_load = [&](int qi) {   // W2[n_lo .. n_lo+127, 32 qi .. 32 qi + 31] -> B_hi plane of stage qi % 3
+    const int s = qi % kNumStages;
+    mbar_arrive_expect_tx(&bar_raw[s], (uint32_t)kPlane);
+    tma_load_3d(sbase + (uint32_t)(s * kStage + 2 * kPlane), &q.tmW2, &bar_raw[s], qi * FK, n_lo, wg);
+  };
+  if (active && warp == 9 && lane == 0)
+    for (int qi = 0; qi < min(nk, kNumStages); ++qi) issue_load(qi);   // every B plane is free at kernel start
+  // Everything so far only touched parameters and on-chip state, and overlapped the tail of the previous kernel when
+  // launched with PDL; the batch (x, eps, td target ...) and the output buffers are the previous kernels' business.
+  pdl_wait();
+  pdl_trigger();
+  if (active && warp < 8) {
+    const float* X = q.x + (int64_t)g * q.x_gs;
+    const bool x_vec = ((q.ldx & 3) == 0) && ((((uintptr_t)X) & 15) == 0);
+    load_kmajor(va, X, q.ldx, m0, B, 0, D, x_vec);
+  }
 
   if (!active) {
     // CTA 1 of a 32-wide network has no layer-2 columns: it only contributes zero partials below
   } else if (warp == 9) {
     // ===== TMA: W2 chunks in, h1 planes out =====================================================================
     if (lane == 0) {
-      auto issue_load = [&](int qi) {
-        const int s = qi % kNumStages;
-        mbar_arrive_expect_tx(&bar_raw[s], (uint32_t)kPlane);
-        tma_load_3d(sbase + (uint32_t)(s * kStage + 2 * kPlane), &q.tmW2, &bar_raw[s], qi * FK, n_lo, wg);
-      };
-      for (int qi = 0; qi < min(nk, kNumStages); ++qi) issue_load(qi);   // every B plane is free at kernel start
       const bool storer = store_h && rank == 0;
       for (int qi = 0; qi < nk; ++qi) {
         const int s = qi % kNumStages;
@@ -546,11 +554,11 @@ int launch_mlp3_fused(const float* W1, const float* b1, const float* W2, const f
   q.G = G; q.B = B; q.D = D; q.H = H; q.O = O; q.store_h = keep_hidden ? 1 : 0;
   if (epi) q.epi = *epi;
   dim3 grid(2 * ((B + fz::FM - 1) / fz::FM), G);   // clusters of two CTAs per 128-row tile
-  if (O == 1) fz::mlp3_forward_kernel<1><<<grid, tc::kThreads, fz::kSmem, s>>>(q);
-  else if (O <= 4) fz::mlp3_forward_kernel<4><<<grid, tc::kThreads, fz::kSmem, s>>>(q);
-  else if (O <= 8) fz::mlp3_forward_kernel<8><<<grid, tc::kThreads, fz::kSmem, s>>>(q);
-  else if (O <= 12) fz::mlp3_forward_kernel<12><<<grid, tc::kThreads, fz::kSmem, s>>>(q);
-  else fz::mlp3_forward_kernel<16><<<grid, tc::kThreads, fz::kSmem, s>>>(q);
+  if (O == 1) launch_pdl(fz::mlp3_forward_kernel<1>, grid, dim3(tc::kThreads), fz::kSmem, s, q);
+  else if (O <= 4) launch_pdl(fz::mlp3_forward_kernel<4>, grid, dim3(tc::kThreads), fz::kSmem, s, q);
+  else if (O <= 8) launch_pdl(fz::mlp3_forward_kernel<8>, grid, dim3(tc::kThreads), fz::kSmem, s, q);
+  else if (O <= 12) launch_pdl(fz::mlp3_forward_kernel<12>, grid, dim3(tc::kThreads), fz::kSmem, s, q);
+  else launch_pdl(fz::mlp3_forward_kernel<16>, grid, dim3(tc::kThreads), fz::kSmem, s, q);
   SSAC_CHECK_LAUNCH("fused mlp forward");
   return 0;
 }

@@ -131,7 +131,9 @@ __global__ void __launch_bounds__(256) head_forward_kernel(const float* __restri
   const int g = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wg = net_index ? net_index[g] : g;
   const float* W = W3 + (int64_t)wg * O * H;
-  for (int i = threadIdx.x; i < O * H; i += blockDim.x) W3s[i] = __ldg(W + i);
+  for (int i = threadIdx.x; i < O * H; i += blockDim.x) W3s[i] = __ldg(W + i);   // parameters: before the PDL wait
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.x * 8 + warp;
   const bool row_ok = b < B;
   const float* hrow = h2 + ((int64_t)g * B + (row_ok ? b : 0)) * H;
@@ -226,6 +228,8 @@ __global__ void __launch_bounds__(256) head_backward_data_kernel(const float* __
                                                                  const float* __restrict__ extra, float extra_scale,
                                                                  const float* __restrict__ h2, int G, int B, int H, int O,
                                                                  float* __restrict__ dz2) {
+  pdl_wait();
+  pdl_trigger();
   const int hv = H / VEC;                       // vectors per row
   const int64_t n = (int64_t)G * B * hv;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -317,7 +321,7 @@ int head_forward(const float* h2, const float* W3, const float* b3, const int32_
     attr_set = true;
   }
   dim3 grid((B + 7) / 8, G);
-  head_forward_kernel<<<grid, 256, smem, s>>>(h2, W3, b3, net_index, G, B, H, O, y, e);
+  launch_pdl(head_forward_kernel, grid, dim3(256), smem, s, h2, W3, b3, net_index, G, B, H, O, y, e);
   SSAC_CHECK_LAUNCH("mlp head forward");
   return 0;
 }
@@ -327,8 +331,8 @@ int head_backward_data(const float* dy, const float* W3, const int32_t* net_inde
   const int64_t n = (int64_t)G * B * (vec ? H / 4 : H);
   int grid = (int)((n + 255) / 256);
   if (grid > 16 * kNumSMs) grid = 16 * kNumSMs;
-  if (vec) head_backward_data_kernel<4><<<grid, 256, 0, s>>>(dy, W3, net_index, extra, extra_scale, h2, G, B, H, O, dz2);
-  else head_backward_data_kernel<1><<<grid, 256, 0, s>>>(dy, W3, net_index, extra, extra_scale, h2, G, B, H, O, dz2);
+  if (vec) launch_pdl(head_backward_data_kernel<4>, dim3(grid), dim3(256), 0, s, dy, W3, net_index, extra, extra_scale, h2, G, B, H, O, dz2);
+  else launch_pdl(head_backward_data_kernel<1>, dim3(grid), dim3(256), 0, s, dy, W3, net_index, extra, extra_scale, h2, G, B, H, O, dz2);
   SSAC_CHECK_LAUNCH("mlp head backward (data)");
   return 0;
 }
@@ -356,6 +360,8 @@ __global__ void __launch_bounds__(256) first_layer_wgrad_kernel(const float* __r
   __shared__ __align__(16) float shbuf[kPartFloats > kXFloats ? kPartFloats : kXFloats];   // x rows, then the partials
   float (*xs)[DP] = reinterpret_cast<float (*)[DP]>(shbuf);
   float (*part)[32][DP + 1] = reinterpret_cast<float (*)[32][DP + 1]>(shbuf);
+  pdl_wait();
+  pdl_trigger();
   const int g = blockIdx.y, h0 = blockIdx.x * 32, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int h = h0 + lane;
   const float* dz = dz1 + (int64_t)g * B * H + (h < H ? h : 0);
@@ -423,10 +429,10 @@ __global__ void __launch_bounds__(256) first_layer_wgrad_kernel(const float* __r
 static int first_layer_wgrad(const float* dz1, const float* x, int64_t ldx, int64_t x_gs, int G, int B, int H, int D,
                              float* gW1, float* gb1, int accumulate, cudaStream_t s) {
   dim3 grid((H + 31) / 32, G);
-  if (D <= 8) first_layer_wgrad_kernel<8><<<grid, 256, 0, s>>>(dz1, x, ldx, x_gs, B, H, D, gW1, gb1, accumulate);
-  else if (D <= 16) first_layer_wgrad_kernel<16><<<grid, 256, 0, s>>>(dz1, x, ldx, x_gs, B, H, D, gW1, gb1, accumulate);
-  else if (D <= 24) first_layer_wgrad_kernel<24><<<grid, 256, 0, s>>>(dz1, x, ldx, x_gs, B, H, D, gW1, gb1, accumulate);
-  else first_layer_wgrad_kernel<32><<<grid, 256, 0, s>>>(dz1, x, ldx, x_gs, B, H, D, gW1, gb1, accumulate);
+  if (D <= 8) launch_pdl(first_layer_wgrad_kernel<8>, grid, dim3(256), 0, s, dz1, x, ldx, x_gs, B, H, D, gW1, gb1, accumulate);
+  else if (D <= 16) launch_pdl(first_layer_wgrad_kernel<16>, grid, dim3(256), 0, s, dz1, x, ldx, x_gs, B, H, D, gW1, gb1, accumulate);
+  else if (D <= 24) launch_pdl(first_layer_wgrad_kernel<24>, grid, dim3(256), 0, s, dz1, x, ldx, x_gs, B, H, D, gW1, gb1, accumulate);
+  else launch_pdl(first_layer_wgrad_kernel<32>, grid, dim3(256), 0, s, dz1, x, ldx, x_gs, B, H, D, gW1, gb1, accumulate);
   SSAC_CHECK_LAUNCH("mlp backward gW1 (narrow input)");
   return 0;
 }
@@ -487,7 +493,7 @@ static GemmP blank() {
   p.A = nullptr; p.lda = 0; p.a_gs = 0; p.Bm = nullptr; p.ldb = 0; p.b_gs = 0; p.b_index = nullptr;
   p.C = nullptr; p.ldc = 0; p.c_gs = 0; p.bias = nullptr; p.bias_gs = 0; p.mask = nullptr; p.ldmask = 0; p.mask_gs = 0;
   p.extra = nullptr; p.ldextra = 0; p.extra_gs = 0; p.extra_scale = 0.f; p.colsum = nullptr; p.colsum_gs = 0;
-  p.M = p.N = p.K = 0; p.relu = 0; p.accumulate = 0;
+  p.M = p.N = p.K = 0; p.relu = 0; p.accumulate = 0; p.pdl = 0;
   return p;
 }
 
@@ -521,7 +527,7 @@ int mlp_forward_simt(const float* W1, const float* b1, const float* W2, const fl
   if (rc) return rc;
   // layer 2: h2 = relu(h1 W2^T + b2)
   p.A = h1; p.lda = H; p.a_gs = (int64_t)B * H; p.Bm = W2; p.ldb = H; p.b_gs = (int64_t)H * H;
-  p.C = h2; p.bias = b2; p.K = H;
+  p.C = h2; p.bias = b2; p.K = H; p.pdl = 1;
   rc = launch_gemm(L_NT, p, G, s, "mlp_forward L2");
   if (rc) return rc;
   if (phase == 1) return 0;
@@ -591,7 +597,7 @@ int mlp_backward_simt(const float* W1, const float* W2, const float* W3, const i
   p = blank();
   p.A = dz2; p.lda = H; p.a_gs = (int64_t)B * H; p.Bm = W2; p.ldb = H; p.b_gs = (int64_t)H * H; p.b_index = net_index;
   p.C = dz1; p.ldc = H; p.c_gs = (int64_t)B * H; p.mask = h1; p.ldmask = H; p.mask_gs = (int64_t)B * H;
-  p.M = B; p.N = H; p.K = H;
+  p.M = B; p.N = H; p.K = H; p.pdl = 1;
   rc = launch_gemm(L_NN, p, G, s, "mlp_backward dz1");
   if (rc) return rc;
   // gW1 and dx both hang off dz1: with both wanted, gW1 goes to the side stream behind gW2 and dx stays on the caller's

@@ -85,6 +85,8 @@ __global__ void __launch_bounds__(kThreads, 1) grouped_gemm_tc_kernel(const __gr
     mbar_init(&bar_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  pdl_wait();      // everything above is on-chip set-up; operands (and wg, below) may come from the previous kernel
+  pdl_trigger();
   if (t < TN) bias_sh[t] = (p.bias && n0 + t < p.N) ? __ldg(p.bias + (int64_t)wg * p.bias_gs + n0 + t) : 0.f;
   fence_before_sync();
   __syncthreads();
@@ -503,9 +505,15 @@ int launch_gemm_tc(int layout, const GemmP& p, int G, cudaStream_t s, const char
     if (!p.mask && !p.extra && !p.accumulate) q.c_tma = make_map(p.C, p.ldc, p.c_gs, p.N, p.M, false, &q.tmC);
   }
   dim3 grid((p.N + tc::TN - 1) / tc::TN, (p.M + tc::TM - 1) / tc::TM, G);
-  if (layout == L_NT) tc::grouped_gemm_tc_kernel<L_NT><<<grid, tc::kThreads, tc::kSmemBytes, s>>>(q);
-  else if (layout == L_NN) tc::grouped_gemm_tc_kernel<L_NN><<<grid, tc::kThreads, tc::kSmemBytes, s>>>(q);
-  else tc::grouped_gemm_tc_kernel<L_TN><<<grid, tc::kThreads, tc::kSmemBytes, s>>>(q);
+  if (p.pdl) {
+    if (layout == L_NT) launch_pdl(tc::grouped_gemm_tc_kernel<L_NT>, grid, dim3(tc::kThreads), tc::kSmemBytes, s, q);
+    else if (layout == L_NN) launch_pdl(tc::grouped_gemm_tc_kernel<L_NN>, grid, dim3(tc::kThreads), tc::kSmemBytes, s, q);
+    else launch_pdl(tc::grouped_gemm_tc_kernel<L_TN>, grid, dim3(tc::kThreads), tc::kSmemBytes, s, q);
+  } else {
+    if (layout == L_NT) tc::grouped_gemm_tc_kernel<L_NT><<<grid, tc::kThreads, tc::kSmemBytes, s>>>(q);
+    else if (layout == L_NN) tc::grouped_gemm_tc_kernel<L_NN><<<grid, tc::kThreads, tc::kSmemBytes, s>>>(q);
+    else tc::grouped_gemm_tc_kernel<L_TN><<<grid, tc::kThreads, tc::kSmemBytes, s>>>(q);
+  }
   SSAC_CHECK_LAUNCH(what);
   return 0;
 }

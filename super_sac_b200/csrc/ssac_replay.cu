@@ -35,6 +35,8 @@ __global__ void __launch_bounds__(256) rng_fill_kernel(uint64_t* __restrict__ rn
                                                        int64_t n_normal, int32_t* __restrict__ subset, int n_subsets,
                                                        int N, int M, int32_t* __restrict__ shift, int64_t n_shift,
                                                        int shift_range, float* __restrict__ zero, int64_t n_zero) {
+  pdl_wait();
+  pdl_trigger();
   const uint64_t seed = rng[0], offset = rng[1];
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nth = (int64_t)gridDim.x * blockDim.x;
@@ -107,6 +109,8 @@ struct GatherArgs {
 };
 
 __global__ void __launch_bounds__(256) gather_rows_kernel(GatherArgs args, const int64_t* __restrict__ idx, int B) {
+  pdl_wait();      // idx comes from the draw kernel
+  pdl_trigger();
   const int k = blockIdx.y;
   const int64_t re = args.row_elems[k], ld = args.dst_ld[k];
   const int mode = args.mode[k];
@@ -390,8 +394,8 @@ int ssac_rng_fill(uint64_t* rng, int64_t* idx, int64_t n_idx, int64_t n_filled, 
   int grid = (int)((work + 255) / 256);
   if (grid < 1) grid = 1;
   if (grid > 4 * kNumSMs) grid = 4 * kNumSMs;
-  rng_fill_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rng, idx, n_idx, n_filled, n_filled_dev, normal, n_normal, subset,
-                                                          n_subsets, N, M, shift, n_shift, shift_range, zero_dev, n_zero);
+  launch_pdl(rng_fill_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, rng, idx, n_idx, n_filled, n_filled_dev, normal,
+             n_normal, subset, n_subsets, N, M, shift, n_shift, shift_range, zero_dev, n_zero);
   SSAC_CHECK_LAUNCH("ssac_rng_fill");
   return 0;
 }
@@ -413,7 +417,7 @@ int ssac_gather_rows(const void* const* srcs, void* const* dsts, const int64_t* 
   if (gx < 1) gx = 1;
   if (gx > 8 * kNumSMs) gx = 8 * kNumSMs;
   dim3 grid(gx, n_arrays);
-  gather_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, idx, B);
+  launch_pdl(gather_rows_kernel, grid, dim3(256), 0, (cudaStream_t)stream, a, idx, B);
   SSAC_CHECK_LAUNCH("ssac_gather_rows");
   return 0;
 }
