@@ -176,15 +176,36 @@ __global__ void __launch_bounds__(256) push_row_kernel(const uint8_t* __restrict
     } else {
       for (int64_t i = tid; i < n; i += nth) dst[i] = src[i];
     }
-  } else if (blockIdx.x == 0 && threadIdx.x == 0 && sum_tree) {
+  } else if (blockIdx.x == 0 && sum_tree) {   // block-uniform condition (the branch contains a barrier)
+    // Leaf write + ancestor update of ONE leaf.  The siblings along the path are not touched by this update, so all of
+    // them are fetched in parallel (thread l owns level l, at most 62 levels) and the chain of parent values is then
+    // evaluated by thread 0 with the reference's operand order (left + right, min(left, right)): replay.py:263-281.
+    __shared__ double sib_sum[64], sib_min[64];
+    __shared__ int levels_sh;
+    const int l = threadIdx.x;
     const int64_t leaf = *reinterpret_cast<const int64_t*>(staging + idx_off);
-    const double val = *reinterpret_cast<const double*>(staging + val_off);
-    int64_t node = leaf + capacity;
-    sum_tree[node] = val;
-    min_tree[node] = val;
-    for (node >>= 1; node >= 1; node >>= 1) {
-      sum_tree[node] = sum_tree[2 * node] + sum_tree[2 * node + 1];
-      min_tree[node] = fmin(min_tree[2 * node], min_tree[2 * node + 1]);
+    const int64_t node0 = leaf + capacity;
+    int levels = 0;
+    for (int64_t c = capacity; c > 1; c >>= 1) ++levels;
+    if (l < levels && l < 64) {
+      const int64_t sib = (node0 >> l) ^ 1;
+      sib_sum[l] = sum_tree[sib];
+      sib_min[l] = min_tree[sib];
+    }
+    if (l == 0) levels_sh = levels;
+    __syncthreads();
+    if (l == 0) {
+      double vs = *reinterpret_cast<const double*>(staging + val_off), vm = vs;
+      sum_tree[node0] = vs;
+      min_tree[node0] = vm;
+      for (int k = 0; k < levels_sh; ++k) {
+        const int64_t node = node0 >> k;
+        const bool is_left = (node & 1) == 0;
+        vs = is_left ? vs + sib_sum[k] : sib_sum[k] + vs;
+        vm = is_left ? fmin(vm, sib_min[k]) : fmin(sib_min[k], vm);
+        sum_tree[node >> 1] = vs;
+        min_tree[node >> 1] = vm;
+      }
     }
   }
 }
