@@ -36,10 +36,10 @@ import torch  # noqa: E402
 
 CONFIGS = {
     # BASELINE.json configs[1]: the configuration the metric is quoted on
-    "redq": dict(E=1, N=10, M=2, S=17, A=6, H=256, B=256, target_delay=2, tau=0.005, lr=3e-4, buffer=1_000_000,
+    "redq": dict(E=1, N=10, M=2, S=17, A=6, H=256, B=256, target_delay=2, tau=0.005, lr=3e-4, buffer=1_000_000, utd=20,
                  workload="REDQ-10 critic_update+Polyak, obs17/act6, B=256, 2x256 MLP, M=2, target_delay=2"),
     # BASELINE.json configs[0]
-    "sac": dict(E=1, N=2, M=2, S=3, A=1, H=256, B=256, target_delay=2, tau=0.005, lr=3e-4, buffer=100_000,
+    "sac": dict(E=1, N=2, M=2, S=3, A=1, H=256, B=256, target_delay=2, tau=0.005, lr=3e-4, buffer=100_000, utd=1,
                 workload="SAC (2 critics) critic_update+Polyak, obs3/act1, B=256, 2x256 MLP"),
 }
 
@@ -195,6 +195,7 @@ def build_gpu(cfg, device, seed=0):
     target.to(device)
     c = dict(E=cfg["E"], critic_lr=cfg["lr"], actor_lr=cfg["lr"])
     critic_opt, actor_opt, enc_opt, log_alphas, alpha_opts = cu.optimizers(agent, c)
+    agent.__dict__["_bench_actor_opts"] = (actor_opt, alpha_opts)   # for the full-SAC-step measurement
     buf = ssb.replay.ReplayBuffer(cfg["buffer"], device=device)
     s, a, r, s1, d = synthetic_transitions(cfg, cfg["buffer"], seed)
     buf.load_experience({"obs": s}, a, r, {"obs": s1}, d)
@@ -326,6 +327,13 @@ def run_gpu_arm(args, cfg, rank, world, local_rank):
             dist.destroy_process_group()
         return
 
+    # ---- the full SAC step, rank 0 --------------------------------------------------------
+    graphed.enable_auto_graphs(False)
+    try:
+        sac_step = time_full_sac_step(cfg, agent, target, kw, polyak, log_alphas)
+    except Exception as e:   # a secondary figure must not take the headline down with it
+        sac_step = {"unavailable": "%s: %s" % (type(e).__name__, e)}
+
     # ---- roofline of the dominant kernel (rank 0) -----------------------------------------------------
     roof = time_dominant_kernel(cfg, agent, args)
     peaks = measured_peaks()
@@ -367,7 +375,7 @@ def run_gpu_arm(args, cfg, rank, world, local_rank):
         "roofline": roofline,
         "cpu_baseline": {"value": cpu_ups, "unit": "updates/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"{cpu_steps} oracle updates (same workload) after 10 warm-up, torch-CPU fp32"},
-        "flops_per_update": fl["update"],
+        "full_sac_step": sac_step, "flops_per_update": fl["update"],
         "sharded_ensemble": sharded,
         "sample_logs": {k: float(v) for k, v in list(glogs.items())[:4]},
     }
@@ -483,6 +491,45 @@ def count_launches(fn, _lib):
         for name, f in saved.items():
             setattr(lib, name, f)
     return counter["n"]
+
+
+def time_full_sac_step(cfg, agent, target, kw, polyak, log_alphas, iters=30):
+    """the full SAC step of main.py:380-543 -- UTD critic updates (+ their Polyak steps), then ONE actor
+    update and ONE temperature update on the last batch -- captured as a single CUDA graph."""
+    from super_sac_b200 import graphed, learning
+
+    actor_opt, alpha_opts = agent.__dict__["_bench_actor_opts"]
+    utd, B = cfg.get("utd", 1), cfg["B"]
+
+    def full_step():
+        rds = None
+        for u in range(utd):
+            _, rds = learning._critic_update_impl(**kw)
+            if u % cfg["target_delay"] == 0:
+                polyak()
+        learning._online_actor_update_impl(buffer=kw["buffer"], agent=agent, pop=False, actor_optimizer=actor_opt,
+                                           log_alphas=log_alphas, batch_size=B, clip=None, random_process=None,
+                                           noise_clip=None, augmenter=kw["augmenter"], aug_mix=0.0,
+                                           premade_replay_dicts=rds)
+        return learning.alpha_update(buffer=kw["buffer"], agent=agent, optimizers=alpha_opts, batch_size=B,
+                                     log_alphas=log_alphas, augmenter=kw["augmenter"], aug_mix=0.0,
+                                     target_entropy=-float(cfg["A"]), premade_replay_dicts=rds, discrete=False)
+
+    g = graphed.GraphedCall(full_step)
+    for _ in range(3):
+        g.replay()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    return {"value": 1e3 / ms, "unit": "SAC steps/s", "ms_per_step": ms, "critic_updates_per_step": utd,
+            "gradient_updates_per_sec": (utd + 1) * 1e3 / ms,
+            "what": "%d x (critic_update + Polyak every %d) + online_actor_update + alpha_update, one CUDA graph" %
+                    (utd, cfg["target_delay"])}
 
 
 def time_dominant_kernel(cfg, agent, args):
