@@ -114,9 +114,10 @@ __device__ __forceinline__ void emit_planes(const float (&v)[16], int row, int h
 
 // OC: compile-time bound on the number of outputs (1, 4, 8, 12 or 16 >= O; rows O..OC-1 of the W3 slice are zero), so
 // that the output-layer FMAs are straight-line code on register-resident accumulators
-template <int OC>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-    mlp3_forward_kernel(const __grid_constant__ FusedFwd q) {
+// CS: CTAs per cluster (2 or 4) = number of column slices of layer 2; 4 halves the per-CTA main loop again and is used
+// while the grid still fits the 148 SMs (small ensembles: the target actor, the REDQ target subset, 10 critics)
+template <int OC, int CS>
+__global__ void __launch_bounds__(kThreads, 1) mlp3_forward_kernel(const __grid_constant__ FusedFwd q) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_raw[kNumStages];    // TMA -> workers: W2 chunk landed (=> B planes were free)
   __shared__ __align__(8) uint64_t bar_full[kNumStages];   // workers -> MMA warp / store issuer: stage complete
@@ -125,7 +126,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   __shared__ uint32_t tmem_base_sh;
   __shared__ float b1s[kMaxH], b2s[kMaxH], b3s[kMaxO];
   __shared__ __align__(16) float W3s[kMaxO][FM];           // this CTA's column slice of the output layer
-  __shared__ __align__(16) float yx[FM][kMaxO];            // CTA 0: partial outputs pushed by CTA 1 (DSMEM)
+  constexpr int OCP = (OC + 3) & ~3;
+  __shared__ __align__(16) float yx[CS - 1][FM][OCP];      // CTA 0: partial outputs pushed by CTAs 1 .. CS-1 (DSMEM)
   __shared__ float red[2][4];
 
   if (threadIdx.x == 0) FZ_TRACE(0);
@@ -136,14 +138,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   float (*ypart)[FM][kYPitch] = reinterpret_cast<float (*)[FM][kYPitch]>(smem + 2 * kStage + 2 * kPlane);
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int rank = (int)cluster_rank();
-  const int g = blockIdx.y, m0 = (blockIdx.x >> 1) * FM;
+  const int g = blockIdx.y, m0 = ((int)blockIdx.x / CS) * FM;
   // net_index (REDQ subset) was drawn at least two launches ago: complete under the PDL rule (ssac_common.cuh)
   const int wg = q.net_index ? q.net_index[g] : g;
   const int H = q.H, D = q.D, O = q.O, B = q.B;
   const int nk = (H + FK - 1) / FK;               // H is a multiple of 16: the last chunk may be half empty
-  const int Hn = ((H + 1) / 2 + 31) & ~31;        // column split, multiple of 32 (TMA store boxes never overlap)
+  const int Hn = ((H + CS - 1) / CS + 31) & ~31;  // column split, multiple of 32 (TMA store boxes never overlap)
   const int n_lo = rank * Hn;
-  const int n_cnt = max(0, min(Hn, H - n_lo));    // multiple of 16; 0 for CTA 1 when H == 32
+  const int n_cnt = max(0, min(Hn, H - n_lo));    // multiple of 16; 0 for the trailing CTAs of narrow networks
   const bool active = n_cnt > 0;
   const bool store_h = q.store_h != 0;
 
@@ -386,23 +388,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   }
 
   // ---- combine the two column halves: CTA 1 pushes its partial outputs into CTA 0's shared memory -----------------
-  if (rank == 1 && warp < 4) {
+  if (rank > 0 && warp < 4) {
     const int row = warp * 32 + lane;
     // one 16-byte remote store per four outputs (remote stores are paid per request, not per byte)
 #pragma unroll
-    for (int o4 = 0; o4 < (OC + 3) / 4; ++o4) {
-      {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (active) {
-          v.x = ypart[0][row][4 * o4 + 0] + ypart[1][row][4 * o4 + 0];
-          if (OC > 1) {
-            v.y = ypart[0][row][4 * o4 + 1] + ypart[1][row][4 * o4 + 1];
-            v.z = ypart[0][row][4 * o4 + 2] + ypart[1][row][4 * o4 + 2];
-            v.w = ypart[0][row][4 * o4 + 3] + ypart[1][row][4 * o4 + 3];
-          }
+    for (int o4 = 0; o4 < OCP / 4; ++o4) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (active) {
+        v.x = ypart[0][row][4 * o4 + 0] + ypart[1][row][4 * o4 + 0];
+        if (OC > 1) {
+          v.y = ypart[0][row][4 * o4 + 1] + ypart[1][row][4 * o4 + 1];
+          v.z = ypart[0][row][4 * o4 + 2] + ypart[1][row][4 * o4 + 2];
+          v.w = ypart[0][row][4 * o4 + 3] + ypart[1][row][4 * o4 + 3];
         }
-        st_cluster_f32x4(&yx[row][4 * o4], 0u, v);
       }
+      st_cluster_f32x4(&yx[rank - 1][row][4 * o4], 0u, v);
     }
   }
   __syncwarp();
@@ -417,7 +417,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     float out[kMaxO];
 #pragma unroll
     for (int o = 0; o < kMaxO; ++o)
-      out[o] = (o < OC) ? ((ypart[0][row][o] + ypart[1][row][o]) + yx[row][o]) + b3s[o] : 0.f;
+    {
+      float v = 0.f;
+      if (o < OC) {
+        v = ypart[0][row][o] + ypart[1][row][o];
+#pragma unroll
+        for (int r = 0; r < CS - 1; ++r) v += yx[r][row][o < OCP ? o : 0];   // fixed order: bit-reproducible
+        v += b3s[o];
+      }
+      out[o] = v;
+    }
     const int b = m0 + row;
     const bool row_ok = b < B;
     const HeadEpi& epi = q.epi;
@@ -537,28 +546,45 @@ int launch_mlp3_fused(const float* W1, const float* b1, const float* W2, const f
     if (!tc::make_map(h1, H, (int64_t)B * H, H, B, false, &q.tmH1)) return -1;
     if (!tc::make_map(h2, H, (int64_t)B * H, H, B, false, &q.tmH2)) return -1;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(fz::mlp3_forward_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fz::kSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(fz::mlp3_forward_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, fz::kSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(fz::mlp3_forward_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, fz::kSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(fz::mlp3_forward_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, fz::kSmem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(fz::mlp3_forward_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, fz::kSmem);
-    if (e != cudaSuccess) {
-      set_error(std::string("fused mlp forward (smem attribute): ") + cudaGetErrorString(e));
-      return (int)e;
-    }
-    attr_set = true;
-  }
+  // column slices per 128-row tile: 4 while the grid fits the SMs (and the DSMEM landing zone fits: O <= 12), else 2
+  const int tiles = (B + fz::FM - 1) / fz::FM;
+  const int cs = (O <= 12 && (int64_t)G * tiles * 4 <= kNumSMs && H >= 128) ? 4 : 2;
   q.x = x; q.ldx = ldx; q.x_gs = x_gs; q.W1 = W1; q.b1 = b1; q.b2 = b2; q.W3 = W3; q.b3 = b3; q.net_index = net_index; q.y = y;
   q.G = G; q.B = B; q.D = D; q.H = H; q.O = O; q.store_h = keep_hidden ? 1 : 0;
   if (epi) q.epi = *epi;
-  dim3 grid(2 * ((B + fz::FM - 1) / fz::FM), G);   // clusters of two CTAs per 128-row tile
-  if (O == 1) launch_pdl(fz::mlp3_forward_kernel<1>, grid, dim3(tc::kThreads), fz::kSmem, s, q);
-  else if (O <= 4) launch_pdl(fz::mlp3_forward_kernel<4>, grid, dim3(tc::kThreads), fz::kSmem, s, q);
-  else if (O <= 8) launch_pdl(fz::mlp3_forward_kernel<8>, grid, dim3(tc::kThreads), fz::kSmem, s, q);
-  else if (O <= 12) launch_pdl(fz::mlp3_forward_kernel<12>, grid, dim3(tc::kThreads), fz::kSmem, s, q);
-  else launch_pdl(fz::mlp3_forward_kernel<16>, grid, dim3(tc::kThreads), fz::kSmem, s, q);
+  dim3 grid(cs * tiles, G);   // clusters of cs CTAs per 128-row tile
+  cudaError_t le;
+#define SSAC_FZ_LAUNCH(OC_, CS_)                                                                                         \
+  do {                                                                                                                   \
+    static bool attr_set = false;                                                                                        \
+    if (!attr_set) {                                                                                                     \
+      cudaError_t e = cudaFuncSetAttribute(fz::mlp3_forward_kernel<OC_, CS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                           fz::kSmem);                                                                   \
+      if (e != cudaSuccess) {                                                                                            \
+        set_error(std::string("fused mlp forward (smem attribute): ") + cudaGetErrorString(e));                          \
+        return (int)e;                                                                                                   \
+      }                                                                                                                  \
+      attr_set = true;                                                                                                   \
+    }                                                                                                                    \
+    le = launch_cluster_pdl(fz::mlp3_forward_kernel<OC_, CS_>, grid, dim3(tc::kThreads), fz::kSmem, s, CS_, q);          \
+  } while (0)
+  if (cs == 4) {
+    if (O == 1) SSAC_FZ_LAUNCH(1, 4);
+    else if (O <= 4) SSAC_FZ_LAUNCH(4, 4);
+    else if (O <= 8) SSAC_FZ_LAUNCH(8, 4);
+    else SSAC_FZ_LAUNCH(12, 4);
+  } else {
+    if (O == 1) SSAC_FZ_LAUNCH(1, 2);
+    else if (O <= 4) SSAC_FZ_LAUNCH(4, 2);
+    else if (O <= 8) SSAC_FZ_LAUNCH(8, 2);
+    else if (O <= 12) SSAC_FZ_LAUNCH(12, 2);
+    else SSAC_FZ_LAUNCH(16, 2);
+  }
+#undef SSAC_FZ_LAUNCH
+  if (le != cudaSuccess) {
+    set_error(std::string("fused mlp forward: ") + cudaGetErrorString(le));
+    return (int)le;
+  }
   SSAC_CHECK_LAUNCH("fused mlp forward");
   return 0;
 }
