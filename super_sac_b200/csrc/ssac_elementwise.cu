@@ -648,7 +648,7 @@ int ssac_polyak(float* target, const float* source, int64_t n, double tau, void*
   SSAC_REQUIRE(target && source, "ssac_polyak: null pointer");
   const float c1 = (float)(1.0 - tau), c2 = (float)tau;
   const int grid = grid_for((n + 3) / 4, 256 * 4, 8);
-  launch_pdl(polyak_kernel<4>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, target, source, n, c1, c2);
+  polyak_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(target, source, n, c1, c2);   // follows Adam (no early trigger): nothing to overlap
   SSAC_CHECK_LAUNCH("ssac_polyak");
   return 0;
 }
