@@ -477,12 +477,16 @@ def count_launches(fn, _lib):
                 # dz2, gW3, gW2, dz1, gW1 (+dx): 5 launches with weight grads, 2 (+1) without
                 want_dw = a[17] is not None
                 counter["n"] += (5 if want_dw else 2) + (1 if a[24] is not None else 0)
+            elif name == "mlp_backward_pre":
+                counter["n"] += 2    # v (unit dz2), u (GEMM)
+            elif name == "mlp_backward_post":
+                counter["n"] += 3    # gW2 GEMM, gW1, gW3
             else:
                 counter["n"] += mult
             return f(*a)
         return g
 
-    for name, mult in list(per_call.items()) + [("mlp_backward", 0)]:
+    for name, mult in list(per_call.items()) + [("mlp_backward", 0), ("mlp_backward_pre", 0), ("mlp_backward_post", 0)]:
         saved[name] = getattr(lib, name)
         setattr(lib, name, wrap(name, saved[name], mult))
     try:

@@ -162,6 +162,18 @@ int ssac_mlp_backward(const float* W1, const float* W2, const float* W3, const i
                       float extra_scale, float* gW1, float* gb1, float* gW2, float* gb2, float* gW3, float* gb3,
                       int accumulate, float* dx_dev, int64_t lddx, float* ws_dev, int impl, void* stream);
 
+/* Split backward of a scalar-output (critic) ensemble, impl 2, D <= 32.  With O == 1 the seed dq[g,b] = dL/dq factors
+ * out of the data-gradient chain: dz2 = dq (x) v, dz1 = dq (x) u with v = W3 .* (h2 > 0), u = (v W2) .* (h1 > 0), neither
+ * of which depends on the TD target.  _pre computes v and u into ws_dev (ssac_mlp_backward_ws floats: v then u) and can
+ * run next to the target networks; _post needs dq and leaves only the three weight-gradient reductions
+ * gW1 = (dq.*u)^T x, gW2 = (dq.*v)^T h1, gW3 = dq^T h2 (+ bias gradients), overwriting the gradient arrays.  Same
+ * results as ssac_mlp_backward up to fp32 rounding of dz1 (dq is applied after, not before, the W2 product). */
+int ssac_mlp_backward_pre(const float* W2, const float* W3, int G, int H, int B, const float* h1_dev, const float* h2_dev,
+                          float* ws_dev, int impl, void* stream);
+int ssac_mlp_backward_post(int G, int D, int H, const float* x_dev, int64_t ldx, int64_t x_gs, int B,
+                           const float* h1_dev, const float* h2_dev, const float* dq_dev, const float* ws_dev, float* gW1,
+                           float* gb1, float* gW2, float* gb2, float* gW3, float* gb3, int impl, void* stream);
+
 /* Actor forward with the policy head fused into the output-layer kernel (one member): replaces ssac_mlp_forward +
  * ssac_tanh_normal_forward / ssac_det_head_forward.  out [B, 2A] (stochastic) or [B, A] (deterministic) is kept for the
  * backward.  deterministic: eps (nullable) is the 1e-4 rsample jitter, noise (nullable) the TD3 noise. */

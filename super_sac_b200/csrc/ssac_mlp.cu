@@ -10,6 +10,11 @@ int mlp_forward_simt(const float* W1, const float* b1, const float* W2, const fl
                      int phase, int keep_hidden);
 void set_fused_forward(int on);
 int get_fused_forward();
+int mlp_backward_pre(const float* W2, const float* W3, int G, int H, int B, const float* h1, const float* h2, float* ws,
+                     cudaStream_t s, int impl);
+int mlp_backward_post(int G, int D, int H, const float* x, int64_t ldx, int64_t x_gs, int B, const float* h1,
+                      const float* h2, const float* dq, const float* ws, float* gW1, float* gb1, float* gW2, float* gb2,
+                      float* gW3, float* gb3, cudaStream_t s, int impl);
 void set_overlap(int on);
 int get_overlap();
 int mlp_backward_simt(const float* W1, const float* W2, const float* W3, const int32_t* net_index, int G, int D, int H,
@@ -104,6 +109,27 @@ int ssac_mlp_backward(const float* W1, const float* W2, const float* W3, const i
                              dh2_extra_dev, extra_scale, gW1, gb1, gW2, gb2, gW3, gb3, accumulate, dx_dev, lddx,
                              ws_dev, (cudaStream_t)stream, impl);
   return fail(SSAC_E_UNSUPPORTED, "ssac_mlp_backward: unknown impl");
+}
+
+int ssac_mlp_backward_pre(const float* W2, const float* W3, int G, int H, int B, const float* h1_dev, const float* h2_dev,
+                          float* ws_dev, int impl, void* stream) {
+  SSAC_REQUIRE(W2 && W3 && h1_dev && h2_dev && ws_dev, "ssac_mlp_backward_pre: null pointer");
+  SSAC_REQUIRE(G > 0 && H > 0 && B > 0, "ssac_mlp_backward_pre: bad sizes");
+  if (impl == 0) impl = ssac_default_mlp_impl();
+  if (impl != 2) return fail(SSAC_E_UNSUPPORTED, "ssac_mlp_backward_pre: the split backward exists for impl 2 (tcgen05) only");
+  return mlp_backward_pre(W2, W3, G, H, B, h1_dev, h2_dev, ws_dev, (cudaStream_t)stream, impl);
+}
+
+int ssac_mlp_backward_post(int G, int D, int H, const float* x_dev, int64_t ldx, int64_t x_gs, int B,
+                           const float* h1_dev, const float* h2_dev, const float* dq_dev, const float* ws_dev, float* gW1,
+                           float* gb1, float* gW2, float* gb2, float* gW3, float* gb3, int impl, void* stream) {
+  SSAC_REQUIRE(x_dev && h1_dev && h2_dev && dq_dev && ws_dev && gW1 && gb1 && gW2 && gb2 && gW3 && gb3,
+               "ssac_mlp_backward_post: null pointer");
+  SSAC_REQUIRE(G > 0 && D > 0 && H > 0 && B > 0 && ldx >= D, "ssac_mlp_backward_post: bad sizes");
+  if (impl == 0) impl = ssac_default_mlp_impl();
+  if (impl != 2) return fail(SSAC_E_UNSUPPORTED, "ssac_mlp_backward_post: the split backward exists for impl 2 (tcgen05) only");
+  return mlp_backward_post(G, D, H, x_dev, ldx, x_gs, B, h1_dev, h2_dev, dq_dev, ws_dev, gW1, gb1, gW2, gb2, gW3, gb3,
+                           (cudaStream_t)stream, impl);
 }
 
 }  // extern "C"

@@ -19,6 +19,7 @@ struct GemmP {
   const float* mask; int64_t ldmask, mask_gs;                          // .* (mask[m][n] > 0)
   const float* extra; int64_t ldextra, extra_gs; float extra_scale;   // + s * extra[m][n] (before the mask)
   float* colsum; int64_t colsum_gs;                                    // L_TN: colsum[m] = sum_k A[k][m]  (bias grads)
+  const float* a_kscale; int64_t a_kscale_gs;                          // L_TN (TMA-fed A only): A[k][m] *= a_kscale[g][k] while staging
   int M, N, K;
   int relu, accumulate;
   int pdl;   // host side: launch with programmatic stream serialization (the predecessor in the stream is PDL-aware)

@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(256) head_backward_data_kernel(const float* __
                                                                  const int32_t* __restrict__ net_index,
                                                                  const float* __restrict__ extra, float extra_scale,
                                                                  const float* __restrict__ h2, int G, int B, int H, int O,
-                                                                 float* __restrict__ dz2) {
+                                                                 float* __restrict__ dz2, int unit_dy) {
   pdl_wait();
   pdl_trigger();
   const int hv = H / VEC;                       // vectors per row
@@ -240,11 +240,11 @@ __global__ void __launch_bounds__(256) head_backward_data_kernel(const float* __
     float acc[VEC];
 #pragma unroll
     for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
-    if (dy) {
+    if (dy || unit_dy) {
       const float* d = dy + gb * O;
       const float* W = W3 + (int64_t)wg * O * H + h;
       for (int o = 0; o < O; ++o) {
-        const float dv = d[o];
+        const float dv = unit_dy ? 1.f : d[o];   // unit_dy: the TD-error-independent factor of dz2 (O == 1)
         if (VEC == 4) {
           const float4 w = __ldg(reinterpret_cast<const float4*>(W + (int64_t)o * H));
           acc[0] = fmaf(dv, w.x, acc[0]); acc[1] = fmaf(dv, w.y, acc[1]);
@@ -326,13 +326,13 @@ int head_forward(const float* h2, const float* W3, const float* b3, const int32_
   return 0;
 }
 int head_backward_data(const float* dy, const float* W3, const int32_t* net_index, const float* extra, float extra_scale,
-                       const float* h2, int G, int B, int H, int O, float* dz2, cudaStream_t s) {
+                       const float* h2, int G, int B, int H, int O, float* dz2, cudaStream_t s, int unit_dy = 0) {
   const bool vec = (H % 4) == 0 && ((((uintptr_t)W3) | ((uintptr_t)h2) | ((uintptr_t)dz2) | ((uintptr_t)extra)) & 15) == 0;
   const int64_t n = (int64_t)G * B * (vec ? H / 4 : H);
   int grid = (int)((n + 255) / 256);
   if (grid > 16 * kNumSMs) grid = 16 * kNumSMs;
-  if (vec) launch_pdl(head_backward_data_kernel<4>, dim3(grid), dim3(256), 0, s, dy, W3, net_index, extra, extra_scale, h2, G, B, H, O, dz2);
-  else launch_pdl(head_backward_data_kernel<1>, dim3(grid), dim3(256), 0, s, dy, W3, net_index, extra, extra_scale, h2, G, B, H, O, dz2);
+  if (vec) launch_pdl(head_backward_data_kernel<4>, dim3(grid), dim3(256), 0, s, dy, W3, net_index, extra, extra_scale, h2, G, B, H, O, dz2, unit_dy);
+  else launch_pdl(head_backward_data_kernel<1>, dim3(grid), dim3(256), 0, s, dy, W3, net_index, extra, extra_scale, h2, G, B, H, O, dz2, unit_dy);
   SSAC_CHECK_LAUNCH("mlp head backward (data)");
   return 0;
 }
@@ -354,7 +354,7 @@ template <int DP>
 __global__ void __launch_bounds__(256) first_layer_wgrad_kernel(const float* __restrict__ dz1, const float* __restrict__ x,
                                                                 int64_t ldx, int64_t x_gs, int B, int H, int D,
                                                                 float* __restrict__ gW1, float* __restrict__ gb1,
-                                                                int accumulate) {
+                                                                int accumulate, const float* __restrict__ row_scale) {
   constexpr int kRows = 256;                    // batch rows staged per pass
   constexpr int kPartFloats = 8 * 32 * (DP + 1), kXFloats = kRows * DP;
   __shared__ __align__(16) float shbuf[kPartFloats > kXFloats ? kPartFloats : kXFloats];   // x rows, then the partials
@@ -393,6 +393,7 @@ __global__ void __launch_bounds__(256) first_layer_wgrad_kernel(const float* __r
       for (int u = 0; u < 8; ++u) {             // eight independent loads in flight per thread
         const int r = r0 + 8 * u;
         dv[u] = (r < nb && h < H) ? __ldg(dz + (int64_t)(b0 + r) * H) : 0.f;
+        if (row_scale && r < nb) dv[u] *= __ldg(row_scale + (int64_t)g * B + b0 + r);   // dz1 = dq (x) u, split backward
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
@@ -427,12 +428,12 @@ __global__ void __launch_bounds__(256) first_layer_wgrad_kernel(const float* __r
 }
 
 static int first_layer_wgrad(const float* dz1, const float* x, int64_t ldx, int64_t x_gs, int G, int B, int H, int D,
-                             float* gW1, float* gb1, int accumulate, cudaStream_t s) {
+                             float* gW1, float* gb1, int accumulate, cudaStream_t s, const float* row_scale = nullptr) {
   dim3 grid((H + 31) / 32, G);
-  if (D <= 8) launch_pdl(first_layer_wgrad_kernel<8>, grid, dim3(256), 0, s, dz1, x, ldx, x_gs, B, H, D, gW1, gb1, accumulate);
-  else if (D <= 16) launch_pdl(first_layer_wgrad_kernel<16>, grid, dim3(256), 0, s, dz1, x, ldx, x_gs, B, H, D, gW1, gb1, accumulate);
-  else if (D <= 24) launch_pdl(first_layer_wgrad_kernel<24>, grid, dim3(256), 0, s, dz1, x, ldx, x_gs, B, H, D, gW1, gb1, accumulate);
-  else launch_pdl(first_layer_wgrad_kernel<32>, grid, dim3(256), 0, s, dz1, x, ldx, x_gs, B, H, D, gW1, gb1, accumulate);
+  if (D <= 8) launch_pdl(first_layer_wgrad_kernel<8>, grid, dim3(256), 0, s, dz1, x, ldx, x_gs, B, H, D, gW1, gb1, accumulate, row_scale);
+  else if (D <= 16) launch_pdl(first_layer_wgrad_kernel<16>, grid, dim3(256), 0, s, dz1, x, ldx, x_gs, B, H, D, gW1, gb1, accumulate, row_scale);
+  else if (D <= 24) launch_pdl(first_layer_wgrad_kernel<24>, grid, dim3(256), 0, s, dz1, x, ldx, x_gs, B, H, D, gW1, gb1, accumulate, row_scale);
+  else launch_pdl(first_layer_wgrad_kernel<32>, grid, dim3(256), 0, s, dz1, x, ldx, x_gs, B, H, D, gW1, gb1, accumulate, row_scale);
   SSAC_CHECK_LAUNCH("mlp backward gW1 (narrow input)");
   return 0;
 }
@@ -493,6 +494,7 @@ static GemmP blank() {
   p.A = nullptr; p.lda = 0; p.a_gs = 0; p.Bm = nullptr; p.ldb = 0; p.b_gs = 0; p.b_index = nullptr;
   p.C = nullptr; p.ldc = 0; p.c_gs = 0; p.bias = nullptr; p.bias_gs = 0; p.mask = nullptr; p.ldmask = 0; p.mask_gs = 0;
   p.extra = nullptr; p.ldextra = 0; p.extra_gs = 0; p.extra_scale = 0.f; p.colsum = nullptr; p.colsum_gs = 0;
+  p.a_kscale = nullptr; p.a_kscale_gs = 0;
   p.M = p.N = p.K = 0; p.relu = 0; p.accumulate = 0; p.pdl = 0;
   return p;
 }
@@ -621,6 +623,51 @@ int mlp_backward_simt(const float* W1, const float* W2, const float* W3, const i
     rc = launch_gemm(L_NN, p, G, s, "mlp_backward dx");
     if (rc) return rc;
   }
+  if (sd && (rc = order_after(w, s, sd->ev[3]))) return rc;   // join
+  return 0;
+}
+
+// ---- split backward of a critic ensemble (O == 1) ------------------------------------------------------------------
+// With a scalar output the TD-error seed factors out of the data-gradient chain:
+//   dz2[b,:] = dq[b] * v[b,:],  v = W3 .* (h2 > 0)            dz1[b,:] = dq[b] * u[b,:],  u = (v W2) .* (h1 > 0)
+// v and u do not depend on the TD target, so mlp_backward_pre computes them next to the target networks (second
+// stream) and mlp_backward_post only has the three weight-gradient reductions left once dq is known:
+//   gW1 = (dq .* u)^T x   gW2 = (dq .* v)^T h1   gW3 = dq^T h2     (+ the bias gradients as their column sums)
+int mlp_backward_pre(const float* W2, const float* W3, int G, int H, int B, const float* h1, const float* h2, float* ws,
+                     cudaStream_t s, int impl) {
+  g_impl = impl;
+  float* v = ws;
+  float* u = ws + (int64_t)G * B * H;
+  int rc = head_backward_data(nullptr, W3, nullptr, nullptr, 0.f, h2, G, B, H, 1, v, s, 1);
+  if (rc) return rc;
+  GemmP p = blank();
+  p.A = v; p.lda = H; p.a_gs = (int64_t)B * H; p.Bm = W2; p.ldb = H; p.b_gs = (int64_t)H * H;
+  p.C = u; p.ldc = H; p.c_gs = (int64_t)B * H; p.mask = h1; p.ldmask = H; p.mask_gs = (int64_t)B * H;
+  p.M = B; p.N = H; p.K = H; p.pdl = 1;
+  return launch_gemm(L_NN, p, G, s, "mlp_backward_pre u");
+}
+
+int mlp_backward_post(int G, int D, int H, const float* x, int64_t ldx, int64_t x_gs, int B, const float* h1,
+                      const float* h2, const float* dq, const float* ws, float* gW1, float* gb1, float* gW2, float* gb2,
+                      float* gW3, float* gb3, cudaStream_t s, int impl) {
+  g_impl = impl;
+  SSAC_REQUIRE(D <= 32, "ssac_mlp_backward_post: first-layer width must be <= 32");
+  const float* v = ws;
+  const float* u = ws + (int64_t)G * B * H;
+  int rc;
+  Side* sd = g_overlap ? side_of_current_device() : nullptr;
+  cudaStream_t w = sd ? sd->s : s;
+  if (sd && (rc = order_after(s, w, sd->ev[0]))) return rc;   // fork: the longest reduction goes to the side stream
+  GemmP q = blank();
+  q.A = v; q.lda = H; q.a_gs = (int64_t)B * H; q.Bm = h1; q.ldb = H; q.b_gs = (int64_t)B * H;
+  q.C = gW2; q.ldc = H; q.c_gs = (int64_t)H * H; q.colsum = gb2; q.colsum_gs = H; q.M = H; q.N = H; q.K = B;
+  q.a_kscale = dq; q.a_kscale_gs = B;
+  rc = launch_gemm(L_TN, q, G, w, "mlp_backward_post gW2");
+  if (rc) return rc;
+  rc = first_layer_wgrad(u, x, ldx, x_gs, G, B, H, D, gW1, gb1, 0, s, dq);
+  if (rc) return rc;
+  rc = head_backward_weight(dq, h2, G, B, H, 1, gW3, gb3, 0, s);
+  if (rc) return rc;
   if (sd && (rc = order_after(w, s, sd->ev[3]))) return rc;   // join
   return 0;
 }

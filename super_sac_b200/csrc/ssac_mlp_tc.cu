@@ -185,11 +185,23 @@ __global__ void __launch_bounds__(kThreads, 1) grouped_gemm_tc_kernel(const __gr
       else if (kc >= kStages) mbar_wait(&bar_empty[s], (uint32_t)((use - 1) & 1));  // no TMA operand: wait for the MMAs
       if (t == 0 && kc < 8) TRACE(3 + 3 * kc);
       if (a_tma) {
-        // lo pass: same (swizzled) offsets in and out, 4 x 16 bytes per thread
+        // lo pass: same (swizzled) offsets in and out, 4 x 16 bytes per thread.  In the MN-major layout all four
+        // chunks of a thread sit on k row t/8 of the stage, so an optional per-k scale (the TD-error seed of the
+        // split critic backward, mlp_backward_post) is one load per thread and stage.
+        float ksc = 1.f;
+        const bool kscale = (LAYOUT == L_TN) && p.a_kscale != nullptr;
+        if (kscale) {
+          const int kk = kc * TK + (t >> 3);
+          ksc = kk < p.K ? __ldg(p.a_kscale + (int64_t)g * p.a_kscale_gs + kk) : 0.f;
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const uint32_t off = (uint32_t)(t + kWorkerThreads * i) * 16u;
-          const float4 v = *reinterpret_cast<const float4*>(a_hi + off);
+          float4 v = *reinterpret_cast<const float4*>(a_hi + off);
+          if (kscale) {
+            v.x *= ksc; v.y *= ksc; v.z *= ksc; v.w *= ksc;
+            *reinterpret_cast<float4*>(a_hi + off) = v;
+          }
           *reinterpret_cast<float4*>(a_lo + off) = lo4(v);
           if (do_colsum) { cs[4 * i + 0] += v.x; cs[4 * i + 1] += v.y; cs[4 * i + 2] += v.z; cs[4 * i + 3] += v.w; }
         }
@@ -504,6 +516,8 @@ int launch_gemm_tc(int layout, const GemmP& p, int G, cudaStream_t s, const char
     else q.b_tma = make_map(p.Bm, p.ldb, p.b_gs, p.K, p.N, false, &q.tmB);
     if (!p.mask && !p.extra && !p.accumulate) q.c_tma = make_map(p.C, p.ldc, p.c_gs, p.N, p.M, false, &q.tmC);
   }
+  if (p.a_kscale && !(layout == L_TN && q.a_tma))
+    return fail(SSAC_E_UNSUPPORTED, "tcgen05 GEMM: a per-k scale needs a TMA-addressable transposed A operand");
   dim3 grid((p.N + tc::TN - 1) / tc::TN, (p.M + tc::TM - 1) / tc::TM, G);
   if (p.pdl) {
     if (layout == L_NT) launch_pdl(tc::grouped_gemm_tc_kernel<L_NT>, grid, dim3(tc::kThreads), tc::kSmemBytes, s, q);

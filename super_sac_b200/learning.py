@@ -104,11 +104,19 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
         # The online critics' hidden layers do not depend on the TD target: run them on a second stream next to the
         # target actor -> target critics chain (their grids leave most SMs idle), join before the output layer + loss.
         side = None if need_ds else lu.side_stream(dev)
+        # With scalar-output critics the TD-error seed factors out of the data-gradient chain (ssac_mlp_backward_pre /
+        # _post), so that chain runs on the second stream as well, before the TD target exists; after the loss only the
+        # three weight-gradient reductions remain.
+        split_bwd = (side is not None and ca.O == 1 and ca.D <= 32 and not dr3_coeff and not parallel.is_sharded()
+                     and L.default_mlp_impl() == 2)
+        bws = _ops._bwd_ws(N, B, ca.H, dev) if split_bwd else None
         if side is not None:
             main = torch.cuda.current_stream(dev)
             side.wait_stream(main)
             L.critic_forward_loss(W1, b1, W2, b2, W3, b3, N, ca.D, ca.H, X.data_ptr(), S + A, B, h1.data_ptr(),
                                   h2.data_ptr(), None, None, None, None, None, 0, E, 0, None, None, 1, 0, side.cuda_stream)
+            if split_bwd:
+                L.mlp_backward_pre(W2, W3, N, ca.H, B, h1.data_ptr(), h2.data_ptr(), bws.data_ptr(), 0, side.cuda_stream)
         td_target, (s1, a1) = lu.compute_td_targets(
             logs=logs, replay_dict=rd, agent=agent, target_agent=target_agent, log_alphas=log_alphas, ensemble_idx=i,
             ensemble_n=target_critic_ensemble_n, pop=pop, gamma=gamma, random_process=random_process,
@@ -140,8 +148,13 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
             loss_v[0:1].add_(dv, alpha=dr3_coeff / (E * N))
             extra, extra_scale, f1 = h2b, dr3_coeff / (E * N) / (N * B), (X1, h1b, h2b)
         dxg = torch.empty((N, B, S + A), dtype=torch.float32, device=dev) if need_ds else None
-        _ops.mlp_backward(ca, i * N, N, X, B, h1, h2, dq, ldx=S + A, dh2_extra=extra, extra_scale=extra_scale,
-                          want_dw=True, accumulate=False, dx=dxg, lddx=S + A)
+        if split_bwd:
+            gW1, gb1, gW2, gb2, gW3, gb3 = ca.ptrs(i * N, grad=True)
+            L.mlp_backward_post(N, ca.D, ca.H, X.data_ptr(), S + A, 0, B, h1.data_ptr(), h2.data_ptr(), dq.data_ptr(),
+                                bws.data_ptr(), gW1, gb1, gW2, gb2, gW3, gb3, 0, stream)
+        else:
+            _ops.mlp_backward(ca, i * N, N, X, B, h1, h2, dq, ldx=S + A, dh2_extra=extra, extra_scale=extra_scale,
+                              want_dw=True, accumulate=False, dx=dxg, lddx=S + A)
         if f1 is not None:
             X1, h1b, h2b = f1
             _ops.mlp_backward(ca, i * N, N, X1, B, h1b, h2b, None, ldx=S + A, dh2_extra=h2, extra_scale=extra_scale,
