@@ -480,7 +480,7 @@ def count_launches(fn, _lib):
             elif name == "mlp_backward_pre":
                 counter["n"] += 2    # v (unit dz2), u (GEMM)
             elif name == "mlp_backward_post":
-                counter["n"] += 3    # gW2 GEMM, gW1, gW3
+                counter["n"] += 2    # gW2 GEMM, gW1 (+ gW3 in the same kernel)
             else:
                 counter["n"] += mult
             return f(*a)

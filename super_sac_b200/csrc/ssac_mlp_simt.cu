@@ -354,19 +354,25 @@ template <int DP>
 __global__ void __launch_bounds__(256) first_layer_wgrad_kernel(const float* __restrict__ dz1, const float* __restrict__ x,
                                                                 int64_t ldx, int64_t x_gs, int B, int H, int D,
                                                                 float* __restrict__ gW1, float* __restrict__ gb1,
-                                                                int accumulate, const float* __restrict__ row_scale) {
+                                                                int accumulate, const float* __restrict__ row_scale,
+                                                                const float* __restrict__ h2, float* __restrict__ gW3,
+                                                                float* __restrict__ gb3) {
   constexpr int kRows = 256;                    // batch rows staged per pass
-  constexpr int kPartFloats = 8 * 32 * (DP + 1), kXFloats = kRows * DP;
+  // h2 / gW3 / gb3 (optional, scalar-output critics with row_scale = dq): the output-layer weight gradients
+  // gW3[g][h] = sum_b dq[b] h2[b][h], gb3[g] = sum_b dq[b] ride along (same rows, same lanes: one more load and FMA per
+  // row), in exactly the summation order of head_backward_weight_kernel
+  constexpr int kPartFloats = 8 * 32 * (DP + 3), kXFloats = kRows * DP;
   __shared__ __align__(16) float shbuf[kPartFloats > kXFloats ? kPartFloats : kXFloats];   // x rows, then the partials
   float (*xs)[DP] = reinterpret_cast<float (*)[DP]>(shbuf);
-  float (*part)[32][DP + 1] = reinterpret_cast<float (*)[32][DP + 1]>(shbuf);
+  float (*part)[32][DP + 3] = reinterpret_cast<float (*)[32][DP + 3]>(shbuf);
   pdl_wait();
   pdl_trigger();
   const int g = blockIdx.y, h0 = blockIdx.x * 32, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int h = h0 + lane;
   const float* dz = dz1 + (int64_t)g * B * H + (h < H ? h : 0);
   const float* xg = x + (int64_t)g * x_gs;
-  float acc[DP], bsum = 0.f;
+  float acc[DP], bsum = 0.f, acc3 = 0.f, bsum3 = 0.f;
+  const float* h2p = h2 ? h2 + (int64_t)g * B * H + (h < H ? h : 0) : nullptr;
 #pragma unroll
   for (int d = 0; d < DP; ++d) acc[d] = 0.f;
   for (int b0 = 0; b0 < B; b0 += kRows) {
@@ -388,17 +394,20 @@ __global__ void __launch_bounds__(256) first_layer_wgrad_kernel(const float* __r
     }
     __syncthreads();
     for (int r0 = warp; r0 < nb; r0 += 64) {
-      float dv[8];
+      float dv[8], sc[8], hv[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {             // eight independent loads in flight per thread
+      for (int u = 0; u < 8; ++u) {             // eight independent loads (per array) in flight per thread
         const int r = r0 + 8 * u;
         dv[u] = (r < nb && h < H) ? __ldg(dz + (int64_t)(b0 + r) * H) : 0.f;
-        if (row_scale && r < nb) dv[u] *= __ldg(row_scale + (int64_t)g * B + b0 + r);   // dz1 = dq (x) u, split backward
+        sc[u] = (row_scale && r < nb) ? __ldg(row_scale + (int64_t)g * B + b0 + r) : 1.f;
+        hv[u] = (h2p && r < nb && h < H) ? __ldg(h2p + (int64_t)(b0 + r) * H) : 0.f;
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int r = r0 + 8 * u;
         if (r < nb) {
+          if (row_scale) dv[u] *= sc[u];        // dz1 = dq (x) u, split backward
+          if (h2p) { acc3 = fmaf(sc[u], hv[u], acc3); bsum3 += sc[u]; }
           bsum += dv[u];
 #pragma unroll
           for (int d = 0; d < DP; d += 4) {
@@ -414,26 +423,37 @@ __global__ void __launch_bounds__(256) first_layer_wgrad_kernel(const float* __r
 #pragma unroll
   for (int d = 0; d < DP; ++d) part[warp][lane][d] = acc[d];
   part[warp][lane][DP] = bsum;
+  part[warp][lane][DP + 1] = acc3;
+  part[warp][lane][DP + 2] = bsum3;
   __syncthreads();
-  // 32 x (D + 1) results, summed over the eight warps in index order
-  for (int i = threadIdx.x; i < 32 * (DP + 1); i += 256) {
-    const int hl = i / (DP + 1), d = i - hl * (DP + 1);
+  // 32 x (D + 1 [+ 2]) results, summed over the eight warps in index order
+  for (int i = threadIdx.x; i < 32 * (DP + 3); i += 256) {
+    const int hl = i / (DP + 3), d = i - hl * (DP + 3);
     if (h0 + hl >= H || (d < DP && d >= D)) continue;
+    if (d > DP && !h2p) continue;
+    if (d == DP + 2 && (blockIdx.x != 0 || hl != 0)) continue;   // gb3: one value per net
     float tot = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) tot += part[w][hl][d];
-    float* out = d < DP ? gW1 + ((int64_t)g * H + h0 + hl) * D + d : gb1 + (int64_t)g * H + h0 + hl;
+    float* out = d < DP ? gW1 + ((int64_t)g * H + h0 + hl) * D + d
+                 : d == DP ? gb1 + (int64_t)g * H + h0 + hl
+                 : d == DP + 1 ? gW3 + (int64_t)g * H + h0 + hl : gb3 + g;
     *out = accumulate ? *out + tot : tot;
   }
 }
 
 static int first_layer_wgrad(const float* dz1, const float* x, int64_t ldx, int64_t x_gs, int G, int B, int H, int D,
-                             float* gW1, float* gb1, int accumulate, cudaStream_t s, const float* row_scale = nullptr) {
+                             float* gW1, float* gb1, int accumulate, cudaStream_t s, const float* row_scale = nullptr,
+                             const float* h2 = nullptr, float* gW3 = nullptr, float* gb3 = nullptr) {
   dim3 grid((H + 31) / 32, G);
-  if (D <= 8) launch_pdl(first_layer_wgrad_kernel<8>, grid, dim3(256), 0, s, dz1, x, ldx, x_gs, B, H, D, gW1, gb1, accumulate, row_scale);
-  else if (D <= 16) launch_pdl(first_layer_wgrad_kernel<16>, grid, dim3(256), 0, s, dz1, x, ldx, x_gs, B, H, D, gW1, gb1, accumulate, row_scale);
-  else if (D <= 24) launch_pdl(first_layer_wgrad_kernel<24>, grid, dim3(256), 0, s, dz1, x, ldx, x_gs, B, H, D, gW1, gb1, accumulate, row_scale);
-  else launch_pdl(first_layer_wgrad_kernel<32>, grid, dim3(256), 0, s, dz1, x, ldx, x_gs, B, H, D, gW1, gb1, accumulate, row_scale);
+  if (D <= 8) launch_pdl(first_layer_wgrad_kernel<8>, grid, dim3(256), 0, s, dz1, x, ldx, x_gs, B, H, D, gW1, gb1, accumulate, row_scale, h2, gW3,
+             gb3);
+  else if (D <= 16) launch_pdl(first_layer_wgrad_kernel<16>, grid, dim3(256), 0, s, dz1, x, ldx, x_gs, B, H, D, gW1, gb1, accumulate, row_scale, h2, gW3,
+             gb3);
+  else if (D <= 24) launch_pdl(first_layer_wgrad_kernel<24>, grid, dim3(256), 0, s, dz1, x, ldx, x_gs, B, H, D, gW1, gb1, accumulate, row_scale, h2, gW3,
+             gb3);
+  else launch_pdl(first_layer_wgrad_kernel<32>, grid, dim3(256), 0, s, dz1, x, ldx, x_gs, B, H, D, gW1, gb1, accumulate, row_scale, h2, gW3,
+             gb3);
   SSAC_CHECK_LAUNCH("mlp backward gW1 (narrow input)");
   return 0;
 }
@@ -664,9 +684,7 @@ int mlp_backward_post(int G, int D, int H, const float* x, int64_t ldx, int64_t 
   q.a_kscale = dq; q.a_kscale_gs = B;
   rc = launch_gemm(L_TN, q, G, w, "mlp_backward_post gW2");
   if (rc) return rc;
-  rc = first_layer_wgrad(u, x, ldx, x_gs, G, B, H, D, gW1, gb1, 0, s, dq);
-  if (rc) return rc;
-  rc = head_backward_weight(dq, h2, G, B, H, 1, gW3, gb3, 0, s);
+  rc = first_layer_wgrad(u, x, ldx, x_gs, G, B, H, D, gW1, gb1, 0, s, dq, h2, gW3, gb3);   // gW1, gb1, gW3, gb3
   if (rc) return rc;
   if (sd && (rc = order_after(w, s, sd->ev[3]))) return rc;   // join
   return 0;
