@@ -677,14 +677,16 @@ int mlp_backward_post(int G, int D, int H, const float* x, int64_t ldx, int64_t 
   int rc;
   Side* sd = g_overlap ? side_of_current_device() : nullptr;
   cudaStream_t w = sd ? sd->s : s;
-  if (sd && (rc = order_after(s, w, sd->ev[0]))) return rc;   // fork: the longest reduction goes to the side stream
+  if (sd && (rc = order_after(s, w, sd->ev[0]))) return rc;   // fork
+  // the short reductions go to the side stream; the GEMM (the longer branch) stays on the caller's stream, where its
+  // set-up overlaps the loss kernel (programmatic dependent launch)
+  rc = first_layer_wgrad(u, x, ldx, x_gs, G, B, H, D, gW1, gb1, 0, w, dq, h2, gW3, gb3);   // gW1, gb1, gW3, gb3
+  if (rc) return rc;
   GemmP q = blank();
   q.A = v; q.lda = H; q.a_gs = (int64_t)B * H; q.Bm = h1; q.ldb = H; q.b_gs = (int64_t)B * H;
   q.C = gW2; q.ldc = H; q.c_gs = (int64_t)H * H; q.colsum = gb2; q.colsum_gs = H; q.M = H; q.N = H; q.K = B;
-  q.a_kscale = dq; q.a_kscale_gs = B;
-  rc = launch_gemm(L_TN, q, G, w, "mlp_backward_post gW2");
-  if (rc) return rc;
-  rc = first_layer_wgrad(u, x, ldx, x_gs, G, B, H, D, gW1, gb1, 0, s, dq, h2, gW3, gb3);   // gW1, gb1, gW3, gb3
+  q.a_kscale = dq; q.a_kscale_gs = B; q.pdl = 1;
+  rc = launch_gemm(L_TN, q, G, s, "mlp_backward_post gW2");
   if (rc) return rc;
   if (sd && (rc = order_after(w, s, sd->ev[3]))) return rc;   // join
   return 0;
