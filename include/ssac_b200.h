@@ -190,7 +190,14 @@ int ssac_critic_forward_loss(const float* W1, const float* b1, const float* W2, 
                              const float* b3, int N, int D, int H, const float* x_dev, int64_t ldx, int B,
                              float* h1_dev, float* h2_dev, float* q_dev, const float* y_dev, const float* w_dev,
                              const float* imp_dev, const float* popart_dev, int pop, int E, int n_total, float* dq_dev,
-                             float* loss_dev, int phase, int impl, void* stream);
+                             float* loss_dev, int phase, const float* qt_dev, int M, const float* logp_dev,
+                             const float* log_alpha_dev, const float* r_dev, const float* d_dev, double gamma,
+                             float* y_out_dev, float* td_logs_dev, int impl, void* stream);
+/* qt_dev != NULL (phase 2, no PopArt): the TD target of ssac_td_target is evaluated inside the loss kernel instead of
+ * being read from y_dev -- y[b] = r[b] + gamma (1 - d[b]) (min_m qt[m][b] - exp(*log_alpha) logp[b]), bit-identical to
+ * ssac_td_target -- which takes one dependent launch off the update's critical path.  y_out_dev (nullable) receives y;
+ * td_logs_dev[0..2] += {sum_b (y - c), sum_b (y - c)^2, sum_b alpha logp} and td_logs_dev[3] = c = y[0], from which the
+ * caller forms the logged mean / unbiased std / entropy bonus (learning_utils.py:351-353). */
 
 /* ---- policy heads: nets/distributions.py:9-15,64-114; learning_utils.py:48-59 --------------------- */
 /* out [B,2A] = [mu | raw_log_std], eps [B,A] -> a [B,A] (row stride lda: may be a column block of cat(s,a)),

@@ -44,6 +44,13 @@ def _reserve_pinned(capacity):
             _pin_pool.append(torch.empty(capacity, dtype=torch.float32).pin_memory())
 
 
+class _Multi:
+    __slots__ = ("fn",)
+
+    def __init__(self, fn):
+        self.fn = fn
+
+
 class DeviceLogs(dict):
     def __init__(self, device, capacity=256, zeroed=True):
         """zeroed=False: the caller clears ``take_unzeroed()`` inside its first kernel (saves the memset launch)."""
@@ -73,6 +80,10 @@ class DeviceLogs(dict):
     def defer(self, key, slot, transform=None):
         """``slot`` may be a list of slots: their sum is reported."""
         self._pending.append((key, slot, transform))
+
+    def defer_fn(self, key, slots, fn):
+        """``fn(*values_of_slots)`` is reported (statistics a kernel leaves as partial sums)."""
+        self._pending.append((key, tuple(slots), _Multi(fn)))
 
     def put_tensor(self, key, scalar_tensor, transform=None):
         """Copy a 0-d / 1-element device tensor into a slot (no sync) and register it under ``key``."""
@@ -105,6 +116,9 @@ class DeviceLogs(dict):
                 torch.cuda.current_stream(self._buf.device).synchronize()   # the one sync
                 host = pin[: self._n].tolist()
             for key, slot, transform in self._pending:
+                if isinstance(transform, _Multi):
+                    self[key] = transform.fn(*[host[s_] for s_ in slot])
+                    continue
                 val = sum(host[s_] for s_ in slot) if isinstance(slot, (list, tuple)) else host[slot]
                 self[key] = transform(val) if transform is not None else val
             if not keep:

@@ -78,10 +78,15 @@ int ssac_critic_forward_loss(const float* W1, const float* b1, const float* W2, 
                              const float* b3, int N, int D, int H, const float* x_dev, int64_t ldx, int B,
                              float* h1_dev, float* h2_dev, float* q_dev, const float* y_dev, const float* w_dev,
                              const float* imp_dev, const float* popart_dev, int pop, int E, int n_total, float* dq_dev,
-                             float* loss_dev, int phase, int impl, void* stream) {
-  SSAC_REQUIRE(W1 && b1 && W2 && b2 && W3 && b3 && x_dev && h1_dev && h2_dev && (phase == 1 || (q_dev && y_dev && dq_dev)),
+                             float* loss_dev, int phase, const float* qt_dev, int M, const float* logp_dev,
+                             const float* log_alpha_dev, const float* r_dev, const float* d_dev, double gamma,
+                             float* y_out_dev, float* td_logs_dev, int impl, void* stream) {
+  SSAC_REQUIRE(W1 && b1 && W2 && b2 && W3 && b3 && x_dev && h1_dev && h2_dev &&
+                   (phase == 1 || (q_dev && (y_dev || qt_dev) && dq_dev)),
                "ssac_critic_forward_loss: null pointer");
   SSAC_REQUIRE(N > 0 && D > 0 && H > 0 && B > 0 && E > 0 && ldx >= D, "ssac_critic_forward_loss: bad sizes");
+  SSAC_REQUIRE(!qt_dev || (phase == 2 && M > 0 && r_dev && d_dev && !(popart_dev && pop)),
+               "ssac_critic_forward_loss: the in-place TD target needs phase 2, M > 0, r, d and no PopArt");
   if (impl == 0) impl = ssac_default_mlp_impl();
   HeadEpi e;
   memset(&e, 0, sizeof(e));
@@ -89,6 +94,8 @@ int ssac_critic_forward_loss(const float* W1, const float* b1, const float* W2, 
   e.y = y_dev; e.w = w_dev; e.imp = imp_dev; e.popart = popart_dev; e.pop = pop;
   e.inv_count = 1.f / ((float)B * (float)E * (float)(n_total > 0 ? n_total : N));
   e.dq = dq_dev; e.loss = loss_dev;
+  e.qt = qt_dev; e.M = M; e.logp_t = logp_dev; e.log_alpha = log_alpha_dev; e.r = r_dev; e.d = d_dev; e.gamma = (float)gamma;
+  e.y_out = y_out_dev; e.td_logs = td_logs_dev;
   return mlp_forward_simt(W1, b1, W2, b2, W3, b3, nullptr, N, D, H, 1, x_dev, ldx, 0, B, h1_dev, h2_dev, q_dev,
                           (cudaStream_t)stream, impl, &e, phase, 1);
 }

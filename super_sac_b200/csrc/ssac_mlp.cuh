@@ -36,6 +36,10 @@ struct HeadEpi {
   float* a; int64_t lda; float* logp; float* tanh_out; int A;
   // kind 3: learning.py:90-98,112
   const float* y; const float* w; const float* imp; const float* popart; int pop; float inv_count; float* dq; float* loss;
+  // kind 3 with the TD target computed in place (no PopArt; learning_utils.py:319-353): y[b] = r + gamma (1-d)
+  // (min_m qt[m][b] - alpha logp[b]); y_out and the logged statistics are written by the blocks of net 0
+  const float* qt; int M; const float* logp_t; const float* log_alpha; const float* r; const float* d; float gamma;
+  float* y_out; float* td_logs;   // td_logs[0..3] += {sum (y - c), sum (y - c)^2, sum alpha logp}, td_logs[3] = c = y[0]
 };
 
 }  // namespace ssac

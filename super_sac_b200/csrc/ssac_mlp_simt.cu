@@ -193,28 +193,63 @@ __global__ void __launch_bounds__(256) head_forward_kernel(const float* __restri
     }
   } else if (epi.kind == 3) {
     // dq = -2 w imp (y - q') popw / (B E N_total);  loss += w imp (y - q')^2 / (B E N_total)
-    float l = 0.f, tdv = 0.f;
+    __shared__ float red_td[3][8];
+    float l = 0.f, tdv = 0.f, s1 = 0.f, s2 = 0.f, se = 0.f;
+    // TD target in place (same operation order as td_target_kernel: bit-identical y)
+    float alpha = 0.f, y0 = 0.f;
+    if (epi.qt && lane == 0) {
+      alpha = (epi.logp_t && epi.log_alpha) ? expf(*epi.log_alpha) : (epi.logp_t ? 1.f : 0.f);
+      if (g == 0) {   // the logged mean / std are accumulated around c = y[0] (one-pass sums stay accurate in fp32)
+        float q0 = epi.qt[0];
+        for (int j = 1; j < epi.M; ++j) q0 = fminf(q0, epi.qt[(int64_t)j * B]);
+        const float e0 = epi.logp_t ? __fmul_rn(alpha, epi.logp_t[0]) : 0.f;
+        y0 = __fadd_rn(epi.r[0], __fmul_rn(__fmul_rn(epi.gamma, __fsub_rn(1.f, epi.d[0])), __fsub_rn(q0, e0)));
+      }
+    }
     if (row_ok && lane == 0) {
+      float yb;
+      if (epi.qt) {
+        float qm = epi.qt[b];
+        for (int j = 1; j < epi.M; ++j) qm = fminf(qm, epi.qt[(int64_t)j * B + b]);
+        const float ent = epi.logp_t ? __fmul_rn(alpha, epi.logp_t[b]) : 0.f;
+        yb = __fadd_rn(epi.r[b], __fmul_rn(__fmul_rn(epi.gamma, __fsub_rn(1.f, epi.d[b])), __fsub_rn(qm, ent)));
+        if (g == 0) {
+          if (epi.y_out) epi.y_out[b] = yb;
+          s1 = yb - y0; s2 = s1 * s1; se = ent;
+        }
+      } else {
+        yb = epi.y[b];
+      }
       const float pw = (epi.popart && epi.pop) ? epi.popart[2] : 1.f, pb = (epi.popart && epi.pop) ? epi.popart[3] : 0.f;
       const float qq = (epi.popart && epi.pop) ? __fadd_rn(__fmul_rn(pw, outv), pb) : outv;
-      const float td = epi.y[b] - qq;
+      const float td = yb - qq;
       const float ww = (epi.w ? epi.w[b] : 1.f) * (epi.imp ? epi.imp[b] : 1.f);
       epi.dq[(int64_t)g * B + b] = -2.f * ww * td * pw * epi.inv_count;
       l = ww * td * td * epi.inv_count;
       tdv = td;
-      red[0][warp] = l;
-      red[1][warp] = tdv;
-    } else if (lane == 0) {
-      red[0][warp] = 0.f;
-      red[1][warp] = 0.f;
+    }
+    if (lane == 0) {
+      red[0][warp] = l; red[1][warp] = tdv;
+      red_td[0][warp] = s1; red_td[1][warp] = s2; red_td[2][warp] = se;
     }
     __syncthreads();
-    if (threadIdx.x == 0 && epi.loss) {
-      float sl = 0.f, st = 0.f;
+    if (threadIdx.x == 0) {
+      if (epi.loss) {
+        float sl = 0.f, st = 0.f;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { sl += red[0][k]; st += red[1][k]; }
-      atomicAdd(&epi.loss[0], sl);
-      if (g == G - 1) atomicAdd(&epi.loss[1], st / (float)B);
+        for (int k = 0; k < 8; ++k) { sl += red[0][k]; st += red[1][k]; }
+        atomicAdd(&epi.loss[0], sl);
+        if (g == G - 1) atomicAdd(&epi.loss[1], st / (float)B);
+      }
+      if (epi.qt && g == 0 && epi.td_logs) {
+        float a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { a1 += red_td[0][k]; a2 += red_td[1][k]; a3 += red_td[2][k]; }
+        atomicAdd(&epi.td_logs[0], a1);
+        atomicAdd(&epi.td_logs[1], a2);
+        atomicAdd(&epi.td_logs[2], a3);
+        if (blockIdx.x == 0) epi.td_logs[3] = y0;
+      }
     }
   }
 }

@@ -114,13 +114,15 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
             main = torch.cuda.current_stream(dev)
             side.wait_stream(main)
             L.critic_forward_loss(W1, b1, W2, b2, W3, b3, N, ca.D, ca.H, X.data_ptr(), S + A, B, h1.data_ptr(),
-                                  h2.data_ptr(), None, None, None, None, None, 0, E, 0, None, None, 1, 0, side.cuda_stream)
+                                  h2.data_ptr(), None, None, None, None, None, 0, E, 0, None, None, 1,
+                                  None, 0, None, None, None, None, 0.0, None, None, 0, side.cuda_stream)
             if split_bwd:
                 L.mlp_backward_pre(W2, W3, N, ca.H, B, h1.data_ptr(), h2.data_ptr(), bws.data_ptr(), 0, side.cuda_stream)
         td_target, (s1, a1) = lu.compute_td_targets(
             logs=logs, replay_dict=rd, agent=agent, target_agent=target_agent, log_alphas=log_alphas, ensemble_idx=i,
             ensemble_n=target_critic_ensemble_n, pop=pop, gamma=gamma, random_process=random_process,
-            noise_clip=noise_clip, _draws=draws)
+            noise_clip=noise_clip, _draws=draws, _fuse_into_loss=side is not None and not parallel.is_sharded())
+        tdp = getattr(td_target, "_ssac_pending", None)   # TD target evaluated inside the loss kernel
         w = lu.compute_backup_weights(logs=logs, replay_dict=rd, agent=agent, target_agent=target_agent,
                                       weight_type=weight_type, weight_temp=weighted_bellman_temp, batch_size=B)
         popart = agent.popart[i]
@@ -134,6 +136,9 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
                               q.data_ptr(), td_target.data_ptr(), w.data_ptr() if torch.is_tensor(w) else None,
                               None if imp_ptr is None else imp_ptr.data_ptr(), popart.state_ptr() if popart else None,
                               int(bool(pop)), E, n_total, dq.data_ptr(), loss_v.data_ptr(), 2 if side is not None else 0,
+                              *((tdp["qt"].data_ptr(), tdp["M"], _ops._p(tdp["logp"]), tdp["log_alpha"].data_ptr(),
+                                 tdp["r"].data_ptr(), tdp["d"].data_ptr(), tdp["gamma"], td_target.data_ptr(),
+                                 tdp["logs"].data_ptr()) if tdp else (None, 0, None, None, None, None, 0.0, None, None)),
                               0, stream)
         lu._mark("join online hidden layers + output layer + loss seed")
         extra, extra_scale, f1 = None, 0.0, None

@@ -433,9 +433,11 @@ def draw_for_critic_member(buffer, agent, B, ensemble_n, random_process, per, ze
 
 
 def compute_td_targets(logs, replay_dict, agent, target_agent, ensemble_idx, ensemble_n, log_alphas, pop, gamma,
-                       random_process, noise_clip, discrete=False, _draws=None):
+                       random_process, noise_clip, discrete=False, _draws=None, _fuse_into_loss=False):
     """TD target of one ensemble member (reference learning_utils.py:298-354, continuous branch).
-    Returns ``td_target [B,1], (s1_rep, a_s1)``."""
+    Returns ``td_target [B,1], (s1_rep, a_s1)``.  ``_fuse_into_loss`` (critic_update only, no PopArt): the final
+    reduction is left to the critic loss kernel -- the returned tensor is filled by that launch and carries the operands
+    as ``_ssac_pending``."""
     if discrete:
         raise NotImplementedError("discrete actions are out of scope")
     dlogs, user_logs = _logs.as_device_logs(logs, agent._critic_arena.device)
@@ -470,6 +472,15 @@ def compute_td_targets(logs, replay_dict, agent, target_agent, ensemble_idx, ens
         q_t = _critic_values(target_agent, i * N, ensemble_n, X1, B, net_index=net_index)
     _mark("target critics Q(s1, a1)")
     y = torch.empty((B, 1), dtype=torch.float32, device=X1.device)
+    if _fuse_into_loss and not popart and user_logs is None:   # popart is False (reference convention) when off
+        lv, slot = dlogs.slots(4)   # {sum (y-c), sum (y-c)^2, sum alpha*logp, c}: zero-initialised with the buffer
+        y._ssac_pending = dict(qt=q_t, M=int(ensemble_n), logp=pol["logp"], log_alpha=log_alphas[i], r=r, d=d,
+                               gamma=float(gamma), logs=lv)
+        dlogs.defer_fn(f"td_targets/mean_td_target_{i}", (slot, slot + 3), lambda s1, c, n=B: c + s1 / n)
+        dlogs.defer_fn(f"td_targets/std_td_target_{i}", (slot, slot + 1),
+                       lambda s1, s2, n=B: max((s2 - s1 * s1 / n) / (n - 1), 0.0) ** 0.5)
+        dlogs.defer_fn(f"td_targets/entropy_bonus_{i}", (slot + 2,), lambda se, n=B: se / n)
+        return y, (X1[:, :S], X1[:, S:])
     lv, slot = dlogs.slots(3)
     _lib.lib().td_target(q_t.data_ptr(), ensemble_n, B, None if pol["logp"] is None else pol["logp"].data_ptr(),
                          log_alphas[i].data_ptr(), r.data_ptr(), d.data_ptr(), float(gamma),
