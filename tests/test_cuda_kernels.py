@@ -404,6 +404,44 @@ def test_fused_forward_matches_oracle_and_layered(G, D, H, O, B):
             gu.assert_close(h2[g].numpy(), h2w.numpy(), 1e-4, 2e-5 * float(h2w.abs().max()), f"{mode} h2[{g}]")
 
 
+@pytest.mark.parametrize("G,D,H,B", [(10, 23, 256, 256), (2, 4, 64, 200), (3, 32, 128, 300)])
+def test_split_critic_backward_matches_oracle(G, D, H, B):
+    """ssac_mlp_backward_pre / _post (TD-independent chain first, seed applied afterwards) against the oracle's backward
+    and against the one-call ssac_mlp_backward."""
+    from super_sac_b200 import _ops
+
+    gen = torch.Generator().manual_seed(G * 31 + H + B)
+    st = uo.MLPStack(G, D, H, 1).random_init(gen)
+    ar = _arena_from(st)
+    x = torch.randn(B, D, generator=gen)
+    dq = torch.randn(G, B, 1, generator=gen) / B
+    grads = st.zeros_like()
+    h1_ref, h2_ref = torch.empty(G, B, H), torch.empty(G, B, H)
+    for g in range(G):
+        _, h1w, h2w = uo.mlp_forward(st, g, x)
+        h1_ref[g], h2_ref[g] = h1w, h2w
+        uo.mlp_backward(st, g, x, h1w, h2w, dq[g], grads, need_dx=False)
+    xd, h1, h2, dqd = x.to(DEV), h1_ref.to(DEV), h2_ref.to(DEV), dq.to(DEV)
+    ws = torch.empty(L().mlp_backward_ws(G, B, H), dtype=torch.float32, device=DEV)
+    W1, _, W2, _, W3, _ = ar.ptrs(0)
+    gW1, gb1, gW2, gb2, gW3, gb3 = ar.ptrs(0, grad=True)
+    ar.grad.fill_(float("nan"))
+    L().mlp_backward_pre(W2, W3, G, H, B, h1.data_ptr(), h2.data_ptr(), ws.data_ptr(), 2, None)
+    L().mlp_backward_post(G, D, H, xd.data_ptr(), D, 0, B, h1.data_ptr(), h2.data_ptr(), dqd.data_ptr(), ws.data_ptr(), gW1, gb1,
+                          gW2, gb2, gW3, gb3, 2, None)
+    torch.cuda.synchronize()
+    split = {n: ar.g[n].cpu().clone() for n in uo.PARAM_NAMES}
+    for n in uo.PARAM_NAMES:
+        want = getattr(grads, n)
+        gu.assert_close(split[n].numpy(), want.numpy(), 1e-4, 1e-5 * float(want.abs().max()), f"split grad {n}")
+    _ops.mlp_backward(ar, 0, G, xd, B, h1, h2, dqd, want_dw=True, accumulate=False, impl=2)
+    torch.cuda.synchronize()
+    for n in ("W2", "b2", "W3", "b3"):   # identical operands and summation order: bit-identical
+        assert torch.equal(ar.g[n].cpu(), split[n]), f"split vs one-call {n}"
+    for n in ("W1", "b1"):               # dq applied after instead of before the W2 product: rounding only
+        gu.assert_close(ar.g[n].cpu().numpy(), split[n].numpy(), 1e-4, 2e-6 * float(split[n].abs().max()), f"split vs one-call {n}")
+
+
 # ------------------------------------------------------------------------------------------------ heads / TD / weights
 def test_policy_heads_match_oracle():
     gen = torch.Generator().manual_seed(4)
