@@ -28,7 +28,7 @@ __device__ __forceinline__ float u01(uint32_t x) {  // (0, 1]
   return ((float)(x >> 8) + 1.0f) * (1.0f / 16777216.0f);
 }
 
-__global__ void __launch_bounds__(256) rng_fill_kernel(uint64_t* __restrict__ rng, int64_t* __restrict__ idx,
+__global__ void __launch_bounds__(1024) rng_fill_kernel(uint64_t* __restrict__ rng, int64_t* __restrict__ idx,
                                                        int64_t n_idx, int64_t n_filled,
                                                        const int64_t* __restrict__ n_filled_dev,
                                                        float* __restrict__ normal,
@@ -83,6 +83,11 @@ __global__ void __launch_bounds__(256) rng_fill_kernel(uint64_t* __restrict__ rn
       Philox p(seed, (uint32_t)i, 3u, offset);
       shift[i] = (int32_t)(p.c[0] % (uint32_t)shift_range);
     }
+  }
+  if (gridDim.x == 1) {   // the usual case (a few hundred draws): no cross-block hand-shake needed
+    __syncthreads();
+    if (threadIdx.x == 0) rng[1] = offset + 1;
+    return;
   }
   __threadfence();
   __syncthreads();
@@ -412,10 +417,15 @@ int ssac_rng_fill(uint64_t* rng, int64_t* idx, int64_t n_idx, int64_t n_filled, 
   if (normal && (n_normal + 3) / 4 > work) work = (n_normal + 3) / 4;
   if (shift && n_shift > work) work = n_shift;
   if (subset && n_subsets > work) work = n_subsets;
-  int grid = (int)((work + 255) / 256);
+  int grid = (int)((work + 255) / 256), block = 256;
   if (grid < 1) grid = 1;
   if (grid > 4 * kNumSMs) grid = 4 * kNumSMs;
-  launch_pdl(rng_fill_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, rng, idx, n_idx, n_filled, n_filled_dev, normal,
+  if (work <= 1024) {   // one block: the offset is advanced without the last-block-done hand-shake
+    grid = 1;
+    block = (int)((work + 31) / 32) * 32;
+    if (block < 32) block = 32;
+  }
+  launch_pdl(rng_fill_kernel, dim3(grid), dim3(block), 0, (cudaStream_t)stream, rng, idx, n_idx, n_filled, n_filled_dev, normal,
              n_normal, subset, n_subsets, N, M, shift, n_shift, shift_range, zero_dev, n_zero);
   SSAC_CHECK_LAUNCH("ssac_rng_fill");
   return 0;
