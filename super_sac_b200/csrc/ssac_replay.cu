@@ -476,9 +476,21 @@ int ssac_scatter_fields(const void* staging, void* const* dsts, const int64_t* n
 static cudaEvent_t g_push_events[64][64];
 static bool g_push_recorded[64][64];
 
+int ssac_push_row_wait(int slot) {
+  SSAC_REQUIRE(slot >= 0 && slot < 64, "ssac_push_row_wait: slot must be in 0..63");
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess || dev < 0 || dev >= 64) return fail(SSAC_E_BADARG, "ssac_push_row_wait: bad device");
+  if (g_push_recorded[dev][slot]) {
+    e = cudaEventSynchronize(g_push_events[dev][slot]);
+    if (e != cudaSuccess) { set_error(std::string("ssac_push_row_wait: ") + cudaGetErrorString(e)); return (int)e; }
+  }
+  return 0;
+}
+
 int ssac_push_row(const void* host_row_pinned, void* staging_dev, int64_t row_bytes, int slot, void* const* dsts,
                   const int64_t* nbytes, const int64_t* src_off, int n_fields, double* sum_tree, double* min_tree,
-                  int64_t capacity, int64_t tree_idx_off, int64_t tree_val_off, void* stream) {
+                  int64_t capacity, int64_t tree_idx_off, int64_t tree_val_off, int wait_slot, void* stream) {
   SSAC_REQUIRE(host_row_pinned && staging_dev && row_bytes > 0 && dsts && nbytes && src_off && n_fields > 0 &&
                    n_fields < kMaxGatherArrays, "ssac_push_row: bad args (1..15 fields)");
   SSAC_REQUIRE(slot >= 0 && slot < 64, "ssac_push_row: slot must be in 0..63");
@@ -509,18 +521,7 @@ int ssac_push_row(const void* host_row_pinned, void* staging_dev, int64_t row_by
   push_row_kernel<<<dim3(gx, n_fields + 1), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)staging_dev, a, n_fields, sum_tree,
                                                                            min_tree, capacity, tree_idx_off, tree_val_off);
   SSAC_CHECK_LAUNCH("ssac_push_row");
-  return 0;
-}
-
-int ssac_push_row_wait(int slot) {
-  SSAC_REQUIRE(slot >= 0 && slot < 64, "ssac_push_row_wait: slot must be in 0..63");
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess || dev < 0 || dev >= 64) return fail(SSAC_E_BADARG, "ssac_push_row_wait: bad device");
-  if (g_push_recorded[dev][slot]) {
-    e = cudaEventSynchronize(g_push_events[dev][slot]);
-    if (e != cudaSuccess) { set_error(std::string("ssac_push_row_wait: ") + cudaGetErrorString(e)); return (int)e; }
-  }
+  if (wait_slot >= 0) return ssac_push_row_wait(wait_slot);   // the row the host fills next (its copy is 63 pushes old)
   return 0;
 }
 

@@ -221,7 +221,7 @@ class ReplayBuffer:
         L = _lib.lib()
         slot = self._stage_next
         self._stage_next = (slot + 1) % self._STAGE_SLOTS
-        L.push_row_wait(slot)   # the H2D copy that last used this pinned row has finished
+        # (the H2D copy that last used this pinned row has finished: the previous push waited for it on its way out)
         v = self._stage_views[slot]
         pos = st._next_idx
         k = 0
@@ -242,7 +242,7 @@ class ReplayBuffer:
         nb = self._stage_bytes
         L.push_row(self._stage_host_ptr + slot * nb, self._stage_dev_ptr + slot * nb, nb, slot, dsts, self._c_nbytes,
                    self._c_offs, self._n_scatter, self._it_sum.data_ptr(), self._it_min.data_ptr(), self._capacity,
-                   lay[-2][0], lay[-1][0], _lib.stream_ptr())
+                   lay[-2][0], lay[-1][0], self._stage_next, _lib.stream_ptr())
         st._max_filled = filled
         st._next_idx = (pos + 1) % st.size
         return np.array([pos])
