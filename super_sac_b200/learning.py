@@ -107,8 +107,7 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
         # With scalar-output critics the TD-error seed factors out of the data-gradient chain (ssac_mlp_backward_pre /
         # _post), so that chain runs on the second stream as well, before the TD target exists; after the loss only the
         # three weight-gradient reductions remain.
-        split_bwd = (side is not None and ca.O == 1 and ca.D <= 32 and not dr3_coeff and not parallel.is_sharded()
-                     and L.default_mlp_impl() == 2)
+        split_bwd = side is not None and ca.O == 1 and ca.D <= 32 and not dr3_coeff and L.default_mlp_impl() == 2
         bws = _ops._bwd_ws(N, B, ca.H, dev) if split_bwd else None
         if side is not None:
             main = torch.cuda.current_stream(dev)
