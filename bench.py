@@ -250,7 +250,8 @@ def run_gpu_arm(args, cfg, rank, world, local_rank):
         return out
 
     # ---- count our kernel launches per step (eager, via the C-ABI entry points) --------------------
-    launch_count = count_launches(lambda: (update_and_polyak(), update_only()), _lib) / 2.0
+    fused_fwd = cfg["H"] <= 256 and cfg["H"] % 16 == 0 and cfg["S"] + cfg["A"] <= 32 and args.mlp_impl == "tcgen05"
+    launch_count = count_launches(lambda: (update_and_polyak(), update_only()), _lib, fused_fwd) / 2.0
 
     # ---- device-resident timed region: graph replay ---------------------------------------------
     g_upd = graphed.GraphedCall(update_only)
@@ -458,12 +459,13 @@ def buf_bytes(buf):
     return n
 
 
-def count_launches(fn, _lib):
-    """Count kernel launches by wrapping the C-ABI entry points with their known launch multiplicities."""
+def count_launches(fn, _lib, fused=False):
+    """Count kernel launches by wrapping the C-ABI entry points with their known launch multiplicities (fused: the
+    single-kernel forward applies, i.e. tcgen05 and a 2x256-class network)."""
     from super_sac_b200 import _lib as L
 
     lib = L.lib()
-    per_call = {"mlp_forward": 3, "actor_forward_sample": 3, "critic_forward_loss": 3, "scatter_fields": 1, "polyak": 1, "polyak_multi": 1, "adam_step": 1, "adam_polyak_step": 1, "sumsq": 1,
+    per_call = {"mlp_forward": 1 if fused else 3, "actor_forward_sample": 1 if fused else 3, "critic_forward_loss": 3, "scatter_fields": 1, "polyak": 1, "polyak_multi": 1, "adam_step": 1, "adam_polyak_step": 1, "sumsq": 1,
                 "rng_fill": 1, "gather_rows": 1, "gather_aug_u8": 1, "tanh_normal_forward": 1, "td_target": 1,
                 "critic_loss_seed": 1, "backup_weights": 1, "tree_set": 1, "tree_sample": 1}
     counter = {"n": 0}
@@ -472,7 +474,7 @@ def count_launches(fn, _lib):
     def wrap(name, f, mult):
         def g(*a):
             if name == "critic_forward_loss":
-                counter["n"] += {0: 3, 1: 2, 2: 1}[a[24]]   # phase: whole forward / hidden layers / output layer + loss
+                counter["n"] += ({0: 1, 1: 1, 2: 1} if fused else {0: 3, 1: 2, 2: 1})[a[24]]   # phase: all / hidden / output + loss
             elif name == "mlp_backward":
                 # dz2, gW3, gW2, dz1, gW1 (+dx): 5 launches with weight grads, 2 (+1) without
                 want_dw = a[17] is not None

@@ -75,6 +75,7 @@ struct FusedFwd {
   float* y;
   int G, B, D, H, O;
   int store_h;
+  int no_head;   // hidden layers only: stop after h2 (the output layer runs later, once the TD target exists)
   HeadEpi epi;
 };
 
@@ -148,6 +149,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_forward_kernel(const __grid_
   const int n_cnt = max(0, min(Hn, H - n_lo));    // multiple of 16; 0 for the trailing CTAs of narrow networks
   const bool active = n_cnt > 0;
   const bool store_h = q.store_h != 0;
+  const bool no_head = q.no_head != 0;
 
   // layer-1 operands: global loads first, so that their latency hides behind the setup below (zero padded to k = 32
   // and to whole 128-row tiles; the 23-wide rows of cat(s, a) are neither 16-byte aligned nor TMA-addressable)
@@ -362,6 +364,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_forward_kernel(const __grid_
         if (t == 0 && v[0] >= 0.f) FZ_TRACE(37 + i);
         // kept activations: swizzled [32 col x 128 row] boxes in the (now idle) B planes of stages 0 / 1, TMA-stored below
         if (store_h) emit_planes(v, row, half, smem + (i >> 1) * kStage + (2 + (i & 1)) * kPlane, nullptr);
+        if (no_head) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
 #pragma unroll
@@ -387,6 +390,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_forward_kernel(const __grid_
     if (t == 0) FZ_TRACE(32);
   }
 
+  if (no_head) {   // uniform over the grid: nothing to exchange, nobody touches a neighbour's shared memory
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, kTmemCols);
+    return;
+  }
   // ---- combine the two column halves: CTA 1 pushes its partial outputs into CTA 0's shared memory -----------------
   if (rank > 0 && warp < 4) {
     const int row = warp * 32 + lane;
@@ -533,8 +542,9 @@ int get_fused_forward() { return g_fused_forward; }
 int launch_mlp3_fused(const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
                       const float* b3, const int32_t* net_index, int G, int D, int H, int O, const float* x, int64_t ldx,
                       int64_t x_gs, int B, float* h1, float* h2, int keep_hidden, float* y, const HeadEpi* epi,
-                      cudaStream_t s) {
+                      cudaStream_t s, int no_head) {
   if (!g_fused_forward || !tc::tma_enabled()) return -1;
+  if (no_head && !keep_hidden) return -1;
   if (H < 32 || H > fz::kMaxH || (H % 16) != 0 || D < 1 || D > fz::FK || O < 1 || O > fz::kMaxO) return -1;
   if (epi && epi->kind == 1 && 2 * epi->A != O) return -1;
   if (epi && epi->kind == 2 && epi->A != O) return -1;
@@ -550,7 +560,7 @@ int launch_mlp3_fused(const float* W1, const float* b1, const float* W2, const f
   const int tiles = (B + fz::FM - 1) / fz::FM;
   const int cs = (O <= 12 && (int64_t)G * tiles * 4 <= kNumSMs && H >= 128) ? 4 : 2;
   q.x = x; q.ldx = ldx; q.x_gs = x_gs; q.W1 = W1; q.b1 = b1; q.b2 = b2; q.W3 = W3; q.b3 = b3; q.net_index = net_index; q.y = y;
-  q.G = G; q.B = B; q.D = D; q.H = H; q.O = O; q.store_h = keep_hidden ? 1 : 0;
+  q.G = G; q.B = B; q.D = D; q.H = H; q.O = O; q.store_h = keep_hidden ? 1 : 0; q.no_head = no_head ? 1 : 0;
   if (epi) q.epi = *epi;
   dim3 grid(cs * tiles, G);   // clusters of cs CTAs per 128-row tile
   cudaError_t le;

@@ -542,7 +542,7 @@ int get_overlap() { return g_overlap; }
 int launch_mlp3_fused(const float* W1, const float* b1, const float* W2, const float* b2, const float* W3,
                       const float* b3, const int32_t* net_index, int G, int D, int H, int O, const float* x, int64_t ldx,
                       int64_t x_gs, int B, float* h1, float* h2, int keep_hidden, float* y, const HeadEpi* epi,
-                      cudaStream_t s);   // ssac_mlp_fused.cu
+                      cudaStream_t s, int no_head);   // ssac_mlp_fused.cu
 
 static GemmP blank() {
   GemmP p;
@@ -559,10 +559,11 @@ int mlp_forward_simt(const float* W1, const float* b1, const float* W2, const fl
                      int64_t x_gs, int B, float* h1, float* h2, float* y, cudaStream_t s, int impl, const HeadEpi* epi,
                      int phase, int keep_hidden) {
   // phase 0: all three layers; 1: trunk only (h1, h2); 2: output layer only (h2 already computed)
-  if (phase == 0 && impl == 2) {
-    // one kernel for the whole network when the shapes allow (2 x 256 nets); h1 / h2 only written when kept
-    const int rc = launch_mlp3_fused(W1, b1, W2, b2, W3, b3, net_index, G, D, H, O, x, ldx, x_gs, B, h1, h2, keep_hidden,
-                                     y, epi, s);
+  if ((phase == 0 || phase == 1) && impl == 2) {
+    // one kernel for the whole network (phase 1: for its hidden layers) when the shapes allow (2 x 256 nets);
+    // h1 / h2 only written when kept
+    const int rc = launch_mlp3_fused(W1, b1, W2, b2, W3, b3, net_index, G, D, H, O, x, ldx, x_gs, B, h1, h2,
+                                     phase == 1 ? 1 : keep_hidden, y, phase == 1 ? nullptr : epi, s, phase == 1);
     if (rc >= 0) return rc;
   }
   SSAC_REQUIRE(h1 && h2, "ssac_mlp_forward: h1/h2 buffers are required by the layered path");
