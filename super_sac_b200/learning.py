@@ -34,7 +34,7 @@ def _graphable(agent, random_process, per, update_priorities):
     """Static shapes, device-side randomness, no PyTorch autograd hand-off, no host-side decisions."""
     return (graphed.auto_graphs_enabled() and isinstance(_rng.source(), _rng.PhiloxSource) and not per and
             not update_priorities and random_process is None and not parallel.is_sharded() and
-            not _encoder_trainable(agent))
+            not parallel.members_sharded() and not _encoder_trainable(agent))
 
 
 def critic_update(buffer, agent, target_agent, critic_optimizer, encoder_optimizer, log_alphas, batch_size, gamma,
@@ -83,13 +83,38 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
 
     replay_dicts, enc_outs = [], []
     lu._mark("start")
+    En = parallel.members_global(E)   # loss normalisation: the global ensemble size when members are sharded over ranks
+    presampled, q_weights = None, None
+    if parallel.members_sharded() and weight_type is not None and weighted_bellman_temp is not None and En > 1:
+        if weight_type != "sunrise":
+            raise NotImplementedError("member-sharded ensembles exchange the sunrise weights only")
+        # every local member samples first; then ONE exchange: all batches to all ranks, every rank's target critics on
+        # every batch, the values back (parallel.py)
+        presampled = []
+        for i in range(E):
+            draws = lu.draw_for_critic_member(buffer, agent, B, target_critic_ensemble_n, random_process, per,
+                                              zero=logs.take_unzeroed())
+            rd = lu.sample_move_and_augment(buffer=buffer, batch_size=B, augmenter=augmenter, aug_mix=aug_mix, per=per,
+                                            _idx=draws["idx"])
+            pk = lu._packed_of(rd)
+            if pk is None:
+                raise NotImplementedError("member-sharded sunrise weights need state observations (packed batches)")
+            presampled.append((draws, rd))
+        x_all = parallel.all_gather_members(torch.stack([lu._packed_of(rd)["XA"] for _, rd in presampled]))   # [En,B,S+A]
+        q_loc = torch.stack([lu._critic_values(target_agent, 0, E * N, x_all[e].contiguous(), B).reshape(E * N, B)
+                             for e in range(En)], dim=1)                                                    # [E*N,En,B]
+        q_weights = parallel.all_gather_members(q_loc)                                                      # [En*N,En,B]
+        g_lo = parallel.my_members()[0]
     for i in range(E):
         loss_v = loss_all[2 * i:2 * i + 2]
-        draws = lu.draw_for_critic_member(buffer, agent, B, target_critic_ensemble_n, random_process, per,
-                                          zero=logs.take_unzeroed())
-        lu._mark("draws (indices, eps, subset)")
-        rd = lu.sample_move_and_augment(buffer=buffer, batch_size=B, augmenter=augmenter, aug_mix=aug_mix, per=per,
-                                        _idx=draws["idx"])
+        if presampled is not None:
+            draws, rd = presampled[i]
+        else:
+            draws = lu.draw_for_critic_member(buffer, agent, B, target_critic_ensemble_n, random_process, per,
+                                              zero=logs.take_unzeroed())
+            lu._mark("draws (indices, eps, subset)")
+            rd = lu.sample_move_and_augment(buffer=buffer, batch_size=B, augmenter=augmenter, aug_mix=aug_mix, per=per,
+                                            _idx=draws["idx"])
         lu._mark("replay gather")
         o, a, *_ = rd["primary_batch"]
         packed = lu._packed_of(rd)
@@ -113,7 +138,7 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
             main = torch.cuda.current_stream(dev)
             side.wait_stream(main)
             L.critic_forward_loss(W1, b1, W2, b2, W3, b3, N, ca.D, ca.H, X.data_ptr(), S + A, B, h1.data_ptr(),
-                                  h2.data_ptr(), None, None, None, None, None, 0, E, 0, None, None, 1,
+                                  h2.data_ptr(), None, None, None, None, None, 0, En, 0, None, None, 1,
                                   None, 0, None, None, None, None, 0.0, None, None, 0, side.cuda_stream)
             if split_bwd:
                 L.mlp_backward_pre(W2, W3, N, ca.H, B, h1.data_ptr(), h2.data_ptr(), bws.data_ptr(), 0, side.cuda_stream)
@@ -123,7 +148,9 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
             noise_clip=noise_clip, _draws=draws, _fuse_into_loss=side is not None and not parallel.is_sharded())
         tdp = getattr(td_target, "_ssac_pending", None)   # TD target evaluated inside the loss kernel
         w = lu.compute_backup_weights(logs=logs, replay_dict=rd, agent=agent, target_agent=target_agent,
-                                      weight_type=weight_type, weight_temp=weighted_bellman_temp, batch_size=B)
+                                      weight_type=weight_type, weight_temp=weighted_bellman_temp, batch_size=B,
+                                      _q_all=None if q_weights is None else
+                                      q_weights[:, g_lo + i, :].reshape(En * N, B, 1).contiguous())
         popart = agent.popart[i]
         imp = rd["imp_weights"]
         imp_ptr = imp.float().contiguous() if per else None  # per=False: ones(1), i.e. no weighting (main.py:401)
@@ -134,7 +161,7 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
         L.critic_forward_loss(W1, b1, W2, b2, W3, b3, N, ca.D, ca.H, X.data_ptr(), S + A, B, h1.data_ptr(), h2.data_ptr(),
                               q.data_ptr(), td_target.data_ptr(), w.data_ptr() if torch.is_tensor(w) else None,
                               None if imp_ptr is None else imp_ptr.data_ptr(), popart.state_ptr() if popart else None,
-                              int(bool(pop)), E, n_total, dq.data_ptr(), loss_v.data_ptr(), 2 if side is not None else 0,
+                              int(bool(pop)), En, n_total, dq.data_ptr(), loss_v.data_ptr(), 2 if side is not None else 0,
                               *((tdp["qt"].data_ptr(), tdp["M"], _ops._p(tdp["logp"]), tdp["log_alpha"].data_ptr(),
                                  tdp["r"].data_ptr(), tdp["d"].data_ptr(), tdp["gamma"], td_target.data_ptr(),
                                  tdp["logs"].data_ptr()) if tdp else (None, 0, None, None, None, None, 0.0, None, None)),
@@ -193,6 +220,11 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
 
     if parallel.is_sharded():
         parallel.all_reduce_sum_(loss_all[0:1])   # each rank summed its own critics
+    if parallel.members_sharded():                # ... or its own members: the logged loss is the global sum
+        tot = loss_all[0:2 * E:2].sum().reshape(1)
+        parallel.all_reduce_members_(tot)
+        loss_all[0:2 * E:2].zero_()
+        loss_all[0:1].copy_(tot)
     logs.defer("losses/last_member_critic_td_error", loss_slot + 2 * (E - 1) + 1)
     logs.defer("losses/critic_overall_loss", [loss_slot + 2 * i for i in range(E)])
     logs.defer("gradients/critic_random_grad", gslot, transform=lambda v: v**0.5)
@@ -231,6 +263,7 @@ def _online_actor_update_impl(buffer, agent, pop, actor_optimizer, log_alphas, b
     _ops.check_cuda(aa.flat)
     L, stream = _lib.lib(), _lib.stream_ptr()
     E, N, B = agent.ensemble_size, agent.num_critics, batch_size
+    En = parallel.members_global(E)   # loss normalisation: the global ensemble size when members are sharded over ranks
     S, A = lu._dims(agent)
     logs = _logs.DeviceLogs(dev)
     loss_v, loss_slot = logs.slots(1)
@@ -256,14 +289,14 @@ def _online_actor_update_impl(buffer, agent, pop, actor_optimizer, log_alphas, b
             Ng = q_all.shape[0]
             dq_all = torch.empty((Ng, B, 1), dtype=torch.float32, device=dev)
             L.actor_loss_seed(q_all.data_ptr(), Ng, B, pol["logp"].data_ptr() if entropy_on else None,
-                              log_alphas[i].data_ptr(), popart.state_ptr() if popart else None, int(bool(pop)), E, None,
+                              log_alphas[i].data_ptr(), popart.state_ptr() if popart else None, int(bool(pop)), En, None,
                               dq_all.data_ptr(), loss_v.data_ptr(), stream)
             lo, hi = parallel.my_range()
             dq = dq_all[lo:hi].contiguous()
         else:
             dq = torch.empty((N, B, 1), dtype=torch.float32, device=dev)
             L.actor_loss_seed(q.data_ptr(), N, B, pol["logp"].data_ptr() if entropy_on else None,
-                              log_alphas[i].data_ptr(), popart.state_ptr() if popart else None, int(bool(pop)), E, None,
+                              log_alphas[i].data_ptr(), popart.state_ptr() if popart else None, int(bool(pop)), En, None,
                               dq.data_ptr(), loss_v.data_ptr(), stream)
         # through the critics to the action: input-gradient only (the reference's critic dW here is discarded anyway)
         dxg = torch.empty((N, B, S + A), dtype=torch.float32, device=dev)
@@ -278,7 +311,7 @@ def _online_actor_update_impl(buffer, agent, pop, actor_optimizer, log_alphas, b
             L.det_head_backward(pol["tanh_out"].data_ptr(), da.data_ptr(), A, B, A, dout.data_ptr(), stream)
         else:
             L.tanh_normal_backward(pol["out"].data_ptr(), pol["eps"].data_ptr(), B, A, float(agent.log_std_low),
-                                   float(agent.log_std_high), da.data_ptr(), A, 1.0 / (E * B),
+                                   float(agent.log_std_high), da.data_ptr(), A, 1.0 / (En * B),
                                    log_alphas[i].data_ptr(), dout.data_ptr(), stream)
         _ops.mlp_backward(aa, i, 1, XPI, B, pol["h1"], pol["h2"], dout, ldx=S + A, want_dw=True, accumulate=False)
     if clip:

@@ -496,9 +496,12 @@ def compute_td_targets(logs, replay_dict, agent, target_agent, ensemble_idx, ens
     return y, (X1[:, :S], X1[:, S:])
 
 
-def compute_backup_weights(logs, replay_dict, agent, target_agent, weight_type, weight_temp, batch_size, discrete=False):
-    """SUNRISE / softmax weighted Bellman backups (reference learning_utils.py:357-398).  Returns 1.0 or w [B,1]."""
-    if weight_type is None or weight_temp is None or agent.ensemble_size == 1:
+def compute_backup_weights(logs, replay_dict, agent, target_agent, weight_type, weight_temp, batch_size, discrete=False,
+                           _q_all=None):
+    """SUNRISE / softmax weighted Bellman backups (reference learning_utils.py:357-398).  Returns 1.0 or w [B,1].
+    ``_q_all`` [E_global*N, B, 1]: the target critics' values on this member's batch, already gathered over the ranks
+    (member-sharded ensembles, parallel.enable_member_sharding)."""
+    if weight_type is None or weight_temp is None or parallel.members_global(agent.ensemble_size) == 1:
         return 1.0
     if discrete:
         raise NotImplementedError("discrete actions are out of scope")
@@ -508,7 +511,11 @@ def compute_backup_weights(logs, replay_dict, agent, target_agent, weight_type, 
     E, N, B = agent.ensemble_size, agent.num_critics, a.shape[0]
     packed = _packed_of(replay_dict)
     dev = a.device
-    if weight_type == "sunrise":
+    if _q_all is not None:
+        q, E, kind = _q_all, _q_all.shape[0] // N, 0
+    elif parallel.members_sharded():
+        raise NotImplementedError("member-sharded ensembles: only the sunrise weights are exchanged (through critic_update)")
+    elif weight_type == "sunrise":
         with torch.no_grad():
             s_rep = target_agent.encoder(o)
         X = _first_layer_input(s_rep, a, packed["XA"] if packed else None, S, A)

@@ -39,6 +39,7 @@ def enable_critic_sharding(num_critics_global, group=None):
 
 def disable():
     _state.update(on=False, group=None, world=1, rank=0, n_global=None)
+    disable_member_sharding()
 
 
 def is_sharded():
@@ -55,12 +56,15 @@ def my_range():
 
 def all_gather_q(q_local):
     """q_local [n_local, B, ...] -> [N_global, B, ...] in global net order (uneven shards are padded on the wire)."""
-    world, n = _state["world"], _state["n_global"]
+    return _all_gather_rows(q_local, _state["n_global"], _state["world"], _state["group"])
+
+
+def _all_gather_rows(q_local, n, world, group):
     n_max = -(-n // world)
     pad = torch.zeros((n_max,) + tuple(q_local.shape[1:]), dtype=q_local.dtype, device=q_local.device)
     pad[: q_local.shape[0]].copy_(q_local)
     out = torch.empty((world * n_max,) + tuple(q_local.shape[1:]), dtype=q_local.dtype, device=q_local.device)
-    dist.all_gather_into_tensor(out, pad, group=_state["group"])
+    dist.all_gather_into_tensor(out, pad, group=group)
     if n == world * n_max:
         return out
     rows = []
@@ -72,4 +76,55 @@ def all_gather_q(q_local):
 
 def all_reduce_sum_(t):
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=_state["group"])
+    return t
+
+
+# ---- SUNRISE-style ensembles: whole members sharded over the ranks ---------------------------------
+# Members are independent learners (own actor, critics, batch); rank r builds its Agent with only its block of members
+# and seeds its own Philox stream.  The single coupling is the SUNRISE weight, a statistic over ALL members' target
+# critics evaluated on each member's batch: one all-gather of the local batches [E_local, B, S+A] and one all-gather of
+# the local target critics' values on every batch [E_local*N, E_global, B] per update.  Loss normalisation keeps the
+# global ensemble size.
+_mstate = {"on": False, "group": None, "world": 1, "rank": 0, "e_global": None}
+
+
+def enable_member_sharding(ensemble_size_global, group=None):
+    """Call after ``dist.init_process_group``; returns (lo, hi), the global ids of this rank's members.  Build the Agent
+    with ``ensemble_size = hi - lo``."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if ensemble_size_global < world:
+        raise ValueError(f"{ensemble_size_global} members cannot be sharded over {world} ranks")
+    _mstate.update(on=True, group=group, world=world, rank=rank, e_global=int(ensemble_size_global))
+    return local_range(ensemble_size_global, world, rank)
+
+
+def disable_member_sharding():
+    _mstate.update(on=False, group=None, world=1, rank=0, e_global=None)
+
+
+def members_sharded():
+    return _mstate["on"]
+
+
+def members_global(e_local):
+    """The ensemble size the losses are normalised with."""
+    return _mstate["e_global"] if _mstate["on"] else e_local
+
+
+def my_members():
+    return local_range(_mstate["e_global"], _mstate["world"], _mstate["rank"])
+
+
+def all_gather_members(x_local):
+    """x_local [E_local * k, ...] (k rows per member, member-major) -> [E_global * k, ...] in global member order."""
+    e_local = my_members()[1] - my_members()[0]
+    k = x_local.shape[0] // e_local
+    x = x_local.reshape((e_local, k) + tuple(x_local.shape[1:]))
+    out = _all_gather_rows(x.contiguous(), _mstate["e_global"], _mstate["world"], _mstate["group"])
+    return out.reshape((_mstate["e_global"] * k,) + tuple(x_local.shape[1:]))
+
+
+def all_reduce_members_(t):
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=_mstate["group"])
     return t

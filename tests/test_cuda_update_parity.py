@@ -347,6 +347,7 @@ def test_sharded_update_equals_single_gpu():
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "[rank 0] sharded critics" in res.stdout and "[rank 1] sharded critics" in res.stdout
+    assert "[rank 0] sharded members" in res.stdout and "[rank 1] sharded members" in res.stdout   # SUNRISE, C3
 
 
 def test_auto_graph_replay_equals_eager():

@@ -68,3 +68,43 @@ def test_sharded_exchange_world2_gloo():
         assert p.exitcode == 0
     got = sorted(q.get(timeout=5) for _ in range(world))
     assert got == [(0, 0, 3), (1, 3, 5)]
+
+
+def _member_worker(rank, world, port, e_global, out_q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lo, hi = parallel.enable_member_sharding(e_global)
+        N, B, D = 2, 4, 3
+        assert parallel.members_sharded() and parallel.members_global(hi - lo) == e_global and parallel.my_members() == (lo, hi)
+        gen = torch.Generator().manual_seed(0)
+        x_full = torch.randn(e_global, B, D, generator=gen)               # one batch per member
+        x_all = parallel.all_gather_members(x_full[lo:hi].clone())
+        assert torch.equal(x_all, x_full), "batches come back in global member order"
+        # every rank's target critics (N per member) on every batch: q[net, batch, b]
+        q_full = torch.randn(e_global * N, e_global, B, generator=gen)
+        q_all = parallel.all_gather_members(q_full[lo * N:hi * N].clone())
+        assert torch.equal(q_all, q_full), "values come back in global (member, net) order"
+        tot = parallel.all_reduce_members_(torch.tensor([float(hi - lo)]))
+        assert float(tot) == e_global
+        out_q.put((rank, lo, hi))
+    finally:
+        parallel.disable()
+        dist.destroy_process_group()
+
+
+def test_member_sharding_exchange_world2_gloo():
+    """SUNRISE members over ranks: uneven member blocks, both all-gathers restore the global order."""
+    world, e_global = 2, 5
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_member_worker, args=(r, world, port, e_global, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    got = sorted(q.get(timeout=5) for _ in range(world))
+    assert got == [(0, 0, 3), (1, 3, 5)]
+    assert not parallel.members_sharded()
