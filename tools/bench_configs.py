@@ -215,15 +215,67 @@ def hbm_kernels():
                           "frac_of_hbm_peak": nb / ms / 1e6 / peaks["hbm_gbs"], "peak_GBps": peaks["hbm_gbs"], "note": note}), flush=True)
 
 
+def mlp_kernels():
+    """Tensor-core ensemble MLP at the shapes of the BASELINE configs: algorithmic TFLOP/s of the forward and of the
+    backward (data + weight gradients) against the measured bf16 peak and against the 3xTF32 ceiling (bf16 / 6)."""
+    from super_sac_b200 import _arena, _ops
+
+    peaks = bench.measured_peaks()
+    for name, G, D, H, B in (("C2 critics 10 x (23-256-256-1), B=256", 10, 23, 256, 256),
+                             ("C3 critics 10 x (23-256-256-1), B=256 per member", 2, 23, 256, 256),
+                             ("C5 critics 2 x (23-1024-1024-1), B=1024", 2, 23, 1024, 1024),
+                             ("C4 critics 2 x (56-1024-1024-1), B=512", 2, 56, 1024, 512)):
+        ar = _arena.MLPArena(G, D, H, 1, DEV)
+        for n in _arena.NAMES:
+            ar.p[n].normal_(0, 0.05)
+        x = torch.randn(B, D, device=DEV)
+        h1 = torch.empty(G, B, H, device=DEV); h2 = torch.empty_like(h1); y = torch.empty(G, B, 1, device=DEV)
+        dy = torch.randn(G, B, 1, device=DEV) / B
+        fwd_fl = 2.0 * G * B * (D * H + H * H + H)
+        bwd_fl = 2.0 * G * B * (2 * H + 2 * H * H + D * H)
+
+        def graph_time(fn, per=10, iters=20):
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    fn()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for _ in range(per):
+                    fn()
+            g.replay()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(iters):
+                g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / (per * iters)
+
+        f_ms = graph_time(lambda: _ops.mlp_forward(ar, 0, G, x, B, h1, h2, y, keep_hidden=True))
+        b_ms = graph_time(lambda: _ops.mlp_backward(ar, 0, G, x, B, h1, h2, dy, want_dw=True))
+        for what, fl, ms in (("forward", fwd_fl, f_ms), ("backward (data + weight gradients)", bwd_fl, b_ms)):
+            tf = fl / ms / 1e9
+            print(json.dumps({"kernel": f"ensemble MLP {what}, {name}", "algorithmic_GFLOP": fl / 1e9, "us": ms * 1e3, "TFLOPs": tf,
+                              "frac_of_bf16_peak": tf / peaks["bf16_tflops"], "frac_of_3xTF32_ceiling": tf / (peaks["bf16_tflops"] / 6),
+                              "peak_bf16_TFLOPs": peaks["bf16_tflops"]}), flush=True)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="sac,sunrise,drqv2,afbc,kernels")
+    ap.add_argument("--only", default="sac,sunrise,drqv2,afbc,kernels,mlp")
     ap.add_argument("--steps", type=int, default=300)
     args = ap.parse_args()
     which = args.only.split(",")
     torch.cuda.set_device(DEV)
     if "kernels" in which:
         hbm_kernels()
+    if "mlp" in which:
+        mlp_kernels()
     if "sac" in which:
         state_config("sac (C1)", 1, 2, 2, 3, 1, 256, 256, args.steps)
     if "sunrise" in which:
