@@ -4,20 +4,23 @@
 // sm_100a only.
 //
 // The layered path (ssac_mlp_tc.cu) spends most of each of its three launches on fixed cost (launch, TMEM allocation,
-// pipeline fill, epilogue, drain) and round-trips h1 / h2 through global memory.  Here a CLUSTER OF TWO CTAs owns 128
-// batch rows of one net and keeps the activations on chip:
+// pipeline fill, epilogue, drain) and round-trips h1 / h2 through global memory.  Here a CLUSTER OF CS = 2 OR 4 CTAs
+// (4 while the grid still fits the 148 SMs) owns 128 batch rows of one net and keeps the activations on chip:
 //
-//   layer 1  : both CTAs compute the full h1 accumulator [128 x H] in tensor memory (K <= 32: one k-chunk, cheap, and
+//   layer 1  : every CTA computes the full h1 accumulator [128 x H] in tensor memory (K <= 32: one k-chunk, cheap, and
 //              it saves exchanging h1 between the CTAs); x and W1 are staged through registers (their 92-byte pitch
-//              is not TMA-addressable)
-//   layer 2  : CTA r computes output columns [r*Hn, r*Hn + n_cnt) (Hn = H/2 rounded up to 32).  The A operand is
+//              is not TMA-addressable); the accumulator is then read into registers ONCE, before layer 2 starts
+//              (a tcgen05.ld issued while MMAs are in flight only completes when they drain)
+//   layer 2  : CTA r computes output columns [r*Hn, r*Hn + n_cnt) (Hn = H/CS rounded up to 32).  The A operand is
 //              produced from the layer-1 accumulator 32 columns at a time (tcgen05.ld -> +bias -> ReLU -> 3xTF32
 //              hi / lo planes in the swizzled UMMA layout) while TMA streams the matching W2 chunk into the B planes
 //              of a 3-stage ring; the three B planes are free from the first cycle, so three chunks are prefetched
 //              while layer 1 is still being staged
 //   layer 3  : O <= 16 outputs: fp32 FMAs straight from the layer-2 accumulator (thread = batch row), partial sums over
-//              each CTA's columns, CTA 1 pushes its partials into CTA 0's shared memory (DSMEM), CTA 0 runs the head
-//              epilogue.  No third GEMM pipeline, no per-chunk TMA latency.
+//              each CTA's columns, CTAs 1.. push their partials into CTA 0's shared memory (DSMEM, 16-byte stores), CTA 0
+//              runs the head epilogue.  No third GEMM pipeline, no per-chunk TMA latency.  (no_head: stop after h2.)
+//   PDL      : everything up to the first read of x (TMEM allocation, barrier init, biases, W1 / W3 loads, the first
+//              three W2 chunks) precedes griddepcontrol.wait and overlaps the previous kernel of the stream
 //
 //   TMEM columns   : [0, 256) layer-1 accumulator, [256, 256 + n_cnt) layer-2 accumulator
 //   shared memory  : 3 stages x { A_hi, A_lo (128 x 32 fp32 each) | B_hi, B_lo (128 x 32 fp32 each) } = 192 KB;
