@@ -81,7 +81,7 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
     if parallel.is_sharded() and (E != 1 or dr3_coeff > 0 or critic_clip):
         raise NotImplementedError("critic sharding covers the REDQ shape (one member, no DR3 / global-norm clip)")
 
-    replay_dicts, enc_outs = [], []
+    enc_outs = []
     lu._mark("start")
     En = parallel.members_global(E)   # loss normalisation: the global ensemble size when members are sharded over ranks
     presampled, q_weights = None, None
@@ -105,16 +105,23 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
                              for e in range(En)], dim=1)                                                    # [E*N,En,B]
         q_weights = parallel.all_gather_members(q_loc)                                                      # [En*N,En,B]
         g_lo = parallel.my_members()[0]
-    for i in range(E):
-        loss_v = loss_all[2 * i:2 * i + 2]
-        if presampled is not None:
-            draws, rd = presampled[i]
-        else:
+    # Members are independent once their batches are drawn (the draws share one device-side Philox offset and stay in
+    # order): with more than one member each runs on its own stream lane, forked from / joined into the caller's stream.
+    # (softmax weights draw policy samples inside the member's work: those stay serial, in the reference's draw order)
+    concurrent = (E > 1 and not per and lu.side_stream(dev) is not None and not _encoder_trainable(agent)
+                  and weight_type != "softmax")
+    if concurrent and presampled is None:
+        presampled = []
+        for i in range(E):
             draws = lu.draw_for_critic_member(buffer, agent, B, target_critic_ensemble_n, random_process, per,
                                               zero=logs.take_unzeroed())
-            lu._mark("draws (indices, eps, subset)")
             rd = lu.sample_move_and_augment(buffer=buffer, batch_size=B, augmenter=augmenter, aug_mix=aug_mix, per=per,
                                             _idx=draws["idx"])
+            presampled.append((draws, rd))
+    replay_dicts = [None] * E
+
+    def member_step(i, draws, rd, lane):
+        loss_v = loss_all[2 * i:2 * i + 2]
         lu._mark("replay gather")
         o, a, *_ = rd["primary_batch"]
         packed = lu._packed_of(rd)
@@ -128,7 +135,7 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
         W1, b1, W2, b2, W3, b3 = ca.ptrs(i * N)
         # The online critics' hidden layers do not depend on the TD target: run them on a second stream next to the
         # target actor -> target critics chain (their grids leave most SMs idle), join before the output layer + loss.
-        side = None if need_ds else lu.side_stream(dev)
+        side = None if need_ds else lu.side_stream(dev, lane)
         # With scalar-output critics the TD-error seed factors out of the data-gradient chain (ssac_mlp_backward_pre /
         # _post), so that chain runs on the second stream as well, before the TD target exists; after the loss only the
         # three weight-gradient reductions remain.
@@ -165,7 +172,7 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
                               *((tdp["qt"].data_ptr(), tdp["M"], _ops._p(tdp["logp"]), tdp["log_alpha"].data_ptr(),
                                  tdp["r"].data_ptr(), tdp["d"].data_ptr(), tdp["gamma"], td_target.data_ptr(),
                                  tdp["logs"].data_ptr()) if tdp else (None, 0, None, None, None, None, 0.0, None, None)),
-                              0, stream)
+                              0, _lib.stream_ptr())
         lu._mark("join online hidden layers + output layer + loss seed")
         extra, extra_scale, f1 = None, 0.0, None
         if dr3_coeff > 0:
@@ -173,7 +180,7 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
             X1 = packed["X1"] if packed else torch.cat((s1, a1), dim=-1).contiguous()
             _, h1b, h2b = lu._critic_values(agent, i * N, N, X1, B, keep=True)
             dv, dslot = logs.slots(1)
-            L.dr3_dot(h2.data_ptr(), h2b.data_ptr(), N, B, ca.H, dv.data_ptr(), stream)
+            L.dr3_dot(h2.data_ptr(), h2b.data_ptr(), N, B, ca.H, dv.data_ptr(), _lib.stream_ptr())
             logs.defer(f"dr3_dotproduct_{i}", dslot)
             # critic_loss += dr3 * dot, then the whole loss is divided by E*N (learning.py:108,112)
             loss_v[0:1].add_(dv, alpha=dr3_coeff / (E * N))
@@ -182,7 +189,7 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
         if split_bwd:
             gW1, gb1, gW2, gb2, gW3, gb3 = ca.ptrs(i * N, grad=True)
             L.mlp_backward_post(N, ca.D, ca.H, X.data_ptr(), S + A, 0, B, h1.data_ptr(), h2.data_ptr(), dq.data_ptr(),
-                                bws.data_ptr(), gW1, gb1, gW2, gb2, gW3, gb3, 0, stream)
+                                bws.data_ptr(), gW1, gb1, gW2, gb2, gW3, gb3, 0, _lib.stream_ptr())
         else:
             _ops.mlp_backward(ca, i * N, N, X, B, h1, h2, dq, ldx=S + A, dh2_extra=extra, extra_scale=extra_scale,
                               want_dw=True, accumulate=False, dx=dxg, lddx=S + A)
@@ -192,8 +199,33 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
                               want_dw=True, accumulate=True)
         if need_ds:
             enc_outs.append((s_rep, dxg.sum(0)[:, :S]))
-        replay_dicts.append(rd)
+        replay_dicts[i] = rd
         lu._mark("ensemble backward")
+
+
+    caller = torch.cuda.current_stream(dev)
+    lanes = []
+    for i in range(E):
+        if presampled is not None:
+            draws, rd = presampled[i]
+        else:
+            draws = lu.draw_for_critic_member(buffer, agent, B, target_critic_ensemble_n, random_process, per,
+                                              zero=logs.take_unzeroed())
+            lu._mark("draws (indices, eps, subset)")
+            rd = lu.sample_move_and_augment(buffer=buffer, batch_size=B, augmenter=augmenter, aug_mix=aug_mix, per=per,
+                                            _idx=draws["idx"])
+        if concurrent:
+            lane = i % lu.MEMBER_LANES
+            st = lu.member_stream(dev, lane)
+            if st not in lanes:
+                lanes.append(st)
+                st.wait_stream(caller)
+            with torch.cuda.stream(st):
+                member_step(i, draws, rd, lane)
+        else:
+            member_step(i, draws, rd, 0)
+    for st in lanes:
+        caller.wait_stream(st)
 
     encoder_optimizer.zero_grad()
     if enc_outs:

@@ -146,17 +146,29 @@ def _mark(name):
 
 
 _side_streams = {}
+_member_streams = {}
+MEMBER_LANES = 4
 
 
-def side_stream(device):
-    """One extra stream per device for the independent branches of an update (online trunk next to the target
-    networks, the logged gradient norm next to Adam).  None when overlap is switched off (ssac_set_overlap)."""
+def side_stream(device, lane=0):
+    """One extra stream per device (and member lane) for the independent branches of an update (online trunk next to
+    the target networks, the logged gradient norm next to Adam).  None when overlap is switched off (ssac_set_overlap)."""
     if not _lib.lib().get_overlap():
         return None
     device = torch.device(device)
-    st = _side_streams.get(device)
+    st = _side_streams.get((device, lane))
     if st is None:
-        st = _side_streams[device] = torch.cuda.Stream(device=device)
+        st = _side_streams[(device, lane)] = torch.cuda.Stream(device=device)
+    return st
+
+
+def member_stream(device, lane):
+    """Stream of ensemble-member lane ``lane``: the members of a SUNRISE-style ensemble are independent once their
+    batches are drawn, so their updates run side by side (each uses at most ~80 of the 148 SMs at a time)."""
+    device = torch.device(device)
+    st = _member_streams.get((device, lane))
+    if st is None:
+        st = _member_streams[(device, lane)] = torch.cuda.Stream(device=device)
     return st
 
 
