@@ -298,19 +298,32 @@ def _online_actor_update_impl(buffer, agent, pop, actor_optimizer, log_alphas, b
     En = parallel.members_global(E)   # loss normalisation: the global ensemble size when members are sharded over ranks
     S, A = lu._dims(agent)
     logs = _logs.DeviceLogs(dev)
-    loss_v, loss_slot = logs.slots(1)
+    loss_all, loss_slot = logs.slots(E)   # one slot per member (members may run side by side)
     opt = _arena.FlatAdam.attach(actor_optimizer, aa)
-    for i in range(E):
-        if premade_replay_dicts is not None:
-            rd = premade_replay_dicts[i]
-        else:
-            rd = lu.sample_move_and_augment(buffer=buffer, batch_size=B, augmenter=augmenter, aug_mix=aug_mix, per=per)
+    # members are independent given their batches and their N(0,1) draws: drawn in order on the caller's stream, then one
+    # stream lane per member (as in critic_update)
+    concurrent = (E > 1 and premade_replay_dicts is not None and lu.side_stream(dev) is not None
+                  and not parallel.is_sharded())
+
+    def draw_member():
+        eps = torch.empty((B, A), dtype=torch.float32, device=dev)
+        _rng.source().normal(eps)
+        noise = None
+        if agent.deterministic and random_process is not None:
+            noise = torch.empty((B, A), dtype=torch.float32, device=dev)
+            _rng.source().normal(noise)
+        return eps, noise
+
+    predrawn = [draw_member() for _ in range(E)] if concurrent else None
+
+    def member_step(i, rd, eps, noise):
+        loss_v = loss_all[i:i + 1]
         o, *_ = rd["primary_batch"]
         packed = lu._packed_of(rd)
         with torch.no_grad():  # actor gradients do not train the encoder (learning.py:378-380)
             s_rep = agent.encoder(o)
         XPI = lu._first_layer_input(s_rep, None, packed["XPI"] if packed else None, S, A)
-        pol = lu._policy_sample(agent, i, XPI, B, S, A, random_process, noise_clip, rsample=True)
+        pol = lu._policy_sample(agent, i, XPI, B, S, A, random_process, noise_clip, rsample=True, eps=eps, noise=noise)
         q, h1c, h2c = lu._critic_values(agent, i * N, N, XPI, B, keep=True)
         popart = agent.popart[i]
         entropy_on = pol["logp"] is not None
@@ -322,37 +335,56 @@ def _online_actor_update_impl(buffer, agent, pop, actor_optimizer, log_alphas, b
             dq_all = torch.empty((Ng, B, 1), dtype=torch.float32, device=dev)
             L.actor_loss_seed(q_all.data_ptr(), Ng, B, pol["logp"].data_ptr() if entropy_on else None,
                               log_alphas[i].data_ptr(), popart.state_ptr() if popart else None, int(bool(pop)), En, None,
-                              dq_all.data_ptr(), loss_v.data_ptr(), stream)
+                              dq_all.data_ptr(), loss_v.data_ptr(), _lib.stream_ptr())
             lo, hi = parallel.my_range()
             dq = dq_all[lo:hi].contiguous()
         else:
             dq = torch.empty((N, B, 1), dtype=torch.float32, device=dev)
             L.actor_loss_seed(q.data_ptr(), N, B, pol["logp"].data_ptr() if entropy_on else None,
                               log_alphas[i].data_ptr(), popart.state_ptr() if popart else None, int(bool(pop)), En, None,
-                              dq.data_ptr(), loss_v.data_ptr(), stream)
+                              dq.data_ptr(), loss_v.data_ptr(), _lib.stream_ptr())
         # through the critics to the action: input-gradient only (the reference's critic dW here is discarded anyway)
         dxg = torch.empty((N, B, S + A), dtype=torch.float32, device=dev)
         _ops.mlp_backward(ca, i * N, N, XPI, B, h1c, h2c, dq, ldx=S + A, want_dw=False, dx=dxg, lddx=S + A)
         da = torch.empty((B, A), dtype=torch.float32, device=dev)
-        L.sum_groups(dxg.data_ptr(), N, B, S + A, S, A, da.data_ptr(), stream)
+        L.sum_groups(dxg.data_ptr(), N, B, S + A, S, A, da.data_ptr(), _lib.stream_ptr())
         if parallel.is_sharded():
             parallel.all_reduce_sum_(da)
         O = aa.O
         dout = torch.empty((1, B, O), dtype=torch.float32, device=dev)
         if agent.deterministic:
-            L.det_head_backward(pol["tanh_out"].data_ptr(), da.data_ptr(), A, B, A, dout.data_ptr(), stream)
+            L.det_head_backward(pol["tanh_out"].data_ptr(), da.data_ptr(), A, B, A, dout.data_ptr(), _lib.stream_ptr())
         else:
             L.tanh_normal_backward(pol["out"].data_ptr(), pol["eps"].data_ptr(), B, A, float(agent.log_std_low),
                                    float(agent.log_std_high), da.data_ptr(), A, 1.0 / (En * B),
-                                   log_alphas[i].data_ptr(), dout.data_ptr(), stream)
+                                   log_alphas[i].data_ptr(), dout.data_ptr(), _lib.stream_ptr())
         _ops.mlp_backward(aa, i, 1, XPI, B, pol["h1"], pol["h2"], dout, ldx=S + A, want_dw=True, accumulate=False)
+
+    caller = torch.cuda.current_stream(dev)
+    lanes = []
+    for i in range(E):
+        if premade_replay_dicts is not None:
+            rd = premade_replay_dicts[i]
+        else:
+            rd = lu.sample_move_and_augment(buffer=buffer, batch_size=B, augmenter=augmenter, aug_mix=aug_mix, per=per)
+        if concurrent:
+            st = lu.member_stream(dev, i % lu.MEMBER_LANES)
+            if st not in lanes:
+                lanes.append(st)
+                st.wait_stream(caller)
+            with torch.cuda.stream(st):
+                member_step(i, rd, *predrawn[i])
+        else:
+            member_step(i, rd, None, None)
+    for st in lanes:
+        caller.wait_stream(st)
     if clip:
         opt.grad_norm_sq(stream)
     opt.step(stream, max_norm=clip if clip else None)
     member = random.choice(range(E))
     gslot = lu._member_grad_norm_slot(logs, aa, member, member + 1)
     logs.defer("gradients/random_actor_online_grad", gslot, transform=lambda v: v**0.5)
-    logs.defer("losses/actor_pg_loss", loss_slot)
+    logs.defer("losses/actor_pg_loss", [loss_slot + i for i in range(E)])
     return logs.finalize()
 
 
