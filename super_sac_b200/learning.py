@@ -417,27 +417,52 @@ def alpha_update(buffer, agent, optimizers, batch_size, log_alphas, augmenter, a
     E, B = agent.ensemble_size, batch_size
     S, A = lu._dims(agent)
     logs = _logs.DeviceLogs(dev)
-    for i in range(E):
-        if premade_replay_dicts is not None:
-            rd = premade_replay_dicts[i]
-        else:
-            rd = lu.sample_move_and_augment(buffer=buffer, batch_size=B, augmenter=augmenter, per=False, aug_mix=aug_mix)
+    # one stream lane per member once the N(0,1) draws are made (in order, on the caller's stream), as in critic_update
+    concurrent = E > 1 and premade_replay_dicts is not None and lu.side_stream(dev) is not None
+    predrawn = None
+    if concurrent and not agent.deterministic:
+        predrawn = []
+        for _ in range(E):
+            eps = torch.empty((B, A), dtype=torch.float32, device=dev)
+            _rng.source().normal(eps)
+            predrawn.append(eps)
+
+    def member_step(i, rd, eps):
         o, *_ = rd["primary_batch"]
         with torch.no_grad():
             s_rep = agent.encoder(o)
         X = torch.empty((B, S + A), dtype=torch.float32, device=dev)
         X[:, :S].copy_(s_rep)
-        pol = lu._policy_sample(agent, i, X, B, S, A, None, None)
+        pol = lu._policy_sample(agent, i, X, B, S, A, None, None, eps=eps)
         pg = optimizers[i].param_groups[0]
         st = _AlphaState.attach(optimizers[i], log_alphas[i])
         lv, slot = logs.slots(2)
         L.alpha_step(log_alphas[i].data_ptr(), pol["logp"].data_ptr(), B, float(target_entropy), st.state.data_ptr(),
                      st.ctl.data_ptr(), float(pg["lr"]), float(pg["betas"][0]), float(pg["betas"][1]), float(pg["eps"]),
-                     lv.data_ptr(), stream)
+                     lv.data_ptr(), _lib.stream_ptr())
         st.steps += 1
         st._step_tensor.fill_(st.steps)
         logs.defer(f"losses/alpha_loss_{i}", slot)
         logs.defer(f"alphas/alpha_{i}", slot + 1)
+
+    caller = torch.cuda.current_stream(dev)
+    lanes = []
+    for i in range(E):
+        if premade_replay_dicts is not None:
+            rd = premade_replay_dicts[i]
+        else:
+            rd = lu.sample_move_and_augment(buffer=buffer, batch_size=B, augmenter=augmenter, per=False, aug_mix=aug_mix)
+        if concurrent:
+            lane = lu.member_stream(dev, i % lu.MEMBER_LANES)
+            if lane not in lanes:
+                lanes.append(lane)
+                lane.wait_stream(caller)
+            with torch.cuda.stream(lane):
+                member_step(i, rd, predrawn[i] if predrawn is not None else None)
+        else:
+            member_step(i, rd, None)
+    for lane in lanes:
+        caller.wait_stream(lane)
     return logs.finalize()
 
 

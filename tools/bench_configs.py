@@ -62,7 +62,7 @@ def state_config(name, E, N, M, S, A, H, B, steps, weight_type=None, temp=None):
                       auto_rescale_targets=False, log_std_low=-5.0, log_std_high=2.0)
     agent.to(DEV)
     target = copy.deepcopy(agent)
-    c_opt, a_opt, e_opt, las, _ = cu.optimizers(agent, dict(E=E))
+    c_opt, a_opt, e_opt, las, al_opts = cu.optimizers(agent, dict(E=E))
     cfg = dict(S=S, A=A)
     buf = ssb.replay.ReplayBuffer(500_000, device=DEV)
     s, a, r, s1, d = bench.synthetic_transitions(cfg, 500_000)
@@ -81,7 +81,23 @@ def state_config(name, E, N, M, S, A, H, B, steps, weight_type=None, temp=None):
 
     step, mode = graph_or_eager(upd)
     ms = timed(lambda k: step(), steps)
+
+    def full():   # main.py:380-543 with UTD 1: critic update + Polyak + actor update + temperature update
+        _, rds = learning._critic_update_impl(**kw)
+        for ac, tc in zip(agent.critics, target.critics):
+            lu.soft_update(tc, ac, 0.005)
+        learning._online_actor_update_impl(buffer=buf, agent=agent, pop=False, actor_optimizer=a_opt, log_alphas=las,
+                                           batch_size=B, clip=None, random_process=None, noise_clip=None,
+                                           augmenter=kw["augmenter"], aug_mix=0.0, premade_replay_dicts=rds)
+        return learning.alpha_update(buffer=buf, agent=agent, optimizers=al_opts, batch_size=B, log_alphas=las,
+                                     augmenter=kw["augmenter"], aug_mix=0.0, target_entropy=-float(A),
+                                     premade_replay_dicts=rds, discrete=False)
+
+    fstep, fmode = graph_or_eager(full)
+    fms = timed(lambda k: fstep(), steps)
     print(json.dumps({"config": name, "metric": "sac_gradient_updates_per_sec", "value": 1e3 / ms, "ms_per_step": ms, "mode": mode,
+                      "full_step_utd1": {"ms": fms, "steps_per_sec": 1e3 / fms, "mode": fmode,
+                                         "what": "critic_update + Polyak + online_actor_update + alpha_update"},
                       "shape": dict(E=E, N=N, M=M, S=S, A=A, H=H, B=B, weight_type=weight_type)}), flush=True)
 
 
