@@ -175,6 +175,14 @@ int ssac_mlp_backward_post(int G, int D, int H, const float* x_dev, int64_t ldx,
                            const float* h1_dev, const float* h2_dev, const float* dq_dev, const float* ws_dev, float* gW1,
                            float* gb1, float* gW2, float* gb2, float* gW3, float* gb3, int impl, void* stream);
 
+/* The actor update's pass through an ensemble of scalar-output critics (learning.py:400-418): from the seed dq [G,B]
+ * (ssac_actor_loss_seed: non-zero on each row's arg-min net only) straight to the action gradient summed over the nets,
+ * da[b][a] = sum_g dQ_g/dx[b][col0 + a] * dq[g][b], without materialising the per-net input gradients (replaces
+ * ssac_mlp_backward(dx only) + ssac_sum_groups).  A <= 32; ws_dev as for ssac_mlp_backward. */
+int ssac_mlp_backward_dact(const float* W1, const float* W2, const float* W3, int G, int D, int H, int col0, int A, int B,
+                           const float* h1_dev, const float* h2_dev, const float* dq_dev, float* da_dev, float* ws_dev,
+                           int impl, void* stream);
+
 /* Actor forward with the policy head fused into the output-layer kernel (one member): replaces ssac_mlp_forward +
  * ssac_tanh_normal_forward / ssac_det_head_forward.  out [B, 2A] (stochastic) or [B, A] (deterministic) is kept for the
  * backward.  deterministic: eps (nullable) is the 1e-4 rsample jitter, noise (nullable) the TD3 noise. */

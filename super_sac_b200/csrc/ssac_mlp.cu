@@ -15,6 +15,8 @@ int mlp_backward_pre(const float* W2, const float* W3, int G, int H, int B, cons
 int mlp_backward_post(int G, int D, int H, const float* x, int64_t ldx, int64_t x_gs, int B, const float* h1,
                       const float* h2, const float* dq, const float* ws, float* gW1, float* gb1, float* gW2, float* gb2,
                       float* gW3, float* gb3, cudaStream_t s, int impl);
+int mlp_backward_dact(const float* W1, const float* W2, const float* W3, int G, int D, int H, int col0, int A, int B,
+                      const float* h1, const float* h2, const float* dq, float* da, float* ws, cudaStream_t s, int impl);
 void set_overlap(int on);
 int get_overlap();
 int mlp_backward_simt(const float* W1, const float* W2, const float* W3, const int32_t* net_index, int G, int D, int H,
@@ -137,6 +139,16 @@ int ssac_mlp_backward_post(int G, int D, int H, const float* x_dev, int64_t ldx,
   if (impl != 2) return fail(SSAC_E_UNSUPPORTED, "ssac_mlp_backward_post: the split backward exists for impl 2 (tcgen05) only");
   return mlp_backward_post(G, D, H, x_dev, ldx, x_gs, B, h1_dev, h2_dev, dq_dev, ws_dev, gW1, gb1, gW2, gb2, gW3, gb3,
                            (cudaStream_t)stream, impl);
+}
+
+int ssac_mlp_backward_dact(const float* W1, const float* W2, const float* W3, int G, int D, int H, int col0, int A, int B,
+                           const float* h1_dev, const float* h2_dev, const float* dq_dev, float* da_dev, float* ws_dev,
+                           int impl, void* stream) {
+  SSAC_REQUIRE(W1 && W2 && W3 && h1_dev && h2_dev && dq_dev && da_dev && ws_dev, "ssac_mlp_backward_dact: null pointer");
+  SSAC_REQUIRE(G > 0 && D > 0 && H > 0 && B > 0, "ssac_mlp_backward_dact: bad sizes");
+  if (impl == 0) impl = ssac_default_mlp_impl();
+  if (impl != 1 && impl != 2) return fail(SSAC_E_UNSUPPORTED, "ssac_mlp_backward_dact: unknown impl");
+  return mlp_backward_dact(W1, W2, W3, G, D, H, col0, A, B, h1_dev, h2_dev, dq_dev, da_dev, ws_dev, (cudaStream_t)stream, impl);
 }
 
 }  // extern "C"

@@ -683,6 +683,61 @@ int mlp_backward_simt(const float* W1, const float* W2, const float* W3, const i
   return 0;
 }
 
+// Action gradient of an ensemble of scalar-output critics, summed over the nets (the actor update's pass through the
+// critics, learning.py:400-408):  da[b][a] = sum_g sum_h dz1[g][b][h] * W1[g][h][col0 + a].
+// With arg-min routing only one net per row carries a non-zero dz1 row; a warp per batch row skips the zero rows of
+// the other nets after one load, which is why this beats the [B x H] x [H x D] GEMM + the sum over nets it replaces.
+template <int AP>
+__global__ void __launch_bounds__(256) action_grad_kernel(const float* __restrict__ dz1, const float* __restrict__ W1, int G,
+                                                          int B, int H, int D, int col0, int A, float* __restrict__ da) {
+  pdl_wait();
+  pdl_trigger();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 8 + warp;
+  if (b >= B) return;
+  float acc[AP];
+#pragma unroll
+  for (int a = 0; a < AP; ++a) acc[a] = 0.f;
+  for (int g = 0; g < G; ++g) {
+    const float* dz = dz1 + ((int64_t)g * B + b) * H;
+    const float* W = W1 + (int64_t)g * H * D + col0;
+    for (int h = lane; h < H; h += 32) {
+      const float d = dz[h];
+      if (d != 0.f) {
+#pragma unroll
+        for (int a = 0; a < AP; ++a)
+          if (a < A) acc[a] = fmaf(d, __ldg(W + (int64_t)h * D + a), acc[a]);
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < AP; ++a) {
+    const float v = warp_sum(acc[a]);
+    if (lane == 0 && a < A) da[(int64_t)b * A + a] = v;
+  }
+}
+
+int mlp_backward_dact(const float* W1, const float* W2, const float* W3, int G, int D, int H, int col0, int A, int B,
+                      const float* h1, const float* h2, const float* dq, float* da, float* ws, cudaStream_t s, int impl) {
+  g_impl = impl;
+  SSAC_REQUIRE(A > 0 && A <= 32 && col0 >= 0 && col0 + A <= D, "ssac_mlp_backward_dact: need 0 < A <= 32 action columns inside D");
+  float* dz2 = ws;
+  float* dz1 = ws + (int64_t)G * B * H;
+  int rc = head_backward_data(dq, W3, nullptr, nullptr, 0.f, h2, G, B, H, 1, dz2, s);
+  if (rc) return rc;
+  GemmP p = blank();
+  p.A = dz2; p.lda = H; p.a_gs = (int64_t)B * H; p.Bm = W2; p.ldb = H; p.b_gs = (int64_t)H * H;
+  p.C = dz1; p.ldc = H; p.c_gs = (int64_t)B * H; p.mask = h1; p.ldmask = H; p.mask_gs = (int64_t)B * H;
+  p.M = B; p.N = H; p.K = H; p.pdl = 1;
+  rc = launch_gemm(L_NN, p, G, s, "mlp_backward_dact dz1");
+  if (rc) return rc;
+  dim3 grid((B + 7) / 8);
+  if (A <= 8) launch_pdl(action_grad_kernel<8>, grid, dim3(256), 0, s, (const float*)dz1, W1, G, B, H, D, col0, A, da);
+  else launch_pdl(action_grad_kernel<32>, grid, dim3(256), 0, s, (const float*)dz1, W1, G, B, H, D, col0, A, da);
+  SSAC_CHECK_LAUNCH("mlp_backward_dact");
+  return 0;
+}
+
 // ---- split backward of a critic ensemble (O == 1) ------------------------------------------------------------------
 // With a scalar output the TD-error seed factors out of the data-gradient chain:
 //   dz2[b,:] = dq[b] * v[b,:],  v = W3 .* (h2 > 0)            dz1[b,:] = dq[b] * u[b,:],  u = (v W2) .* (h1 > 0)

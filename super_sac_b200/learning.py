@@ -344,10 +344,16 @@ def _online_actor_update_impl(buffer, agent, pop, actor_optimizer, log_alphas, b
                               log_alphas[i].data_ptr(), popart.state_ptr() if popart else None, int(bool(pop)), En, None,
                               dq.data_ptr(), loss_v.data_ptr(), _lib.stream_ptr())
         # through the critics to the action: input-gradient only (the reference's critic dW here is discarded anyway)
-        dxg = torch.empty((N, B, S + A), dtype=torch.float32, device=dev)
-        _ops.mlp_backward(ca, i * N, N, XPI, B, h1c, h2c, dq, ldx=S + A, want_dw=False, dx=dxg, lddx=S + A)
         da = torch.empty((B, A), dtype=torch.float32, device=dev)
-        L.sum_groups(dxg.data_ptr(), N, B, S + A, S, A, da.data_ptr(), _lib.stream_ptr())
+        if ca.O == 1 and A <= 32:
+            cW1, _, cW2, _, cW3, _ = ca.ptrs(i * N)
+            bws = _ops._bwd_ws(N, B, ca.H, dev)
+            L.mlp_backward_dact(cW1, cW2, cW3, N, ca.D, ca.H, S, A, B, h1c.data_ptr(), h2c.data_ptr(), dq.data_ptr(),
+                                da.data_ptr(), bws.data_ptr(), 0, _lib.stream_ptr())
+        else:
+            dxg = torch.empty((N, B, S + A), dtype=torch.float32, device=dev)
+            _ops.mlp_backward(ca, i * N, N, XPI, B, h1c, h2c, dq, ldx=S + A, want_dw=False, dx=dxg, lddx=S + A)
+            L.sum_groups(dxg.data_ptr(), N, B, S + A, S, A, da.data_ptr(), _lib.stream_ptr())
         if parallel.is_sharded():
             parallel.all_reduce_sum_(da)
         O = aa.O
