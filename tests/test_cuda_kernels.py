@@ -442,6 +442,40 @@ def test_split_critic_backward_matches_oracle(G, D, H, B):
         gu.assert_close(ar.g[n].cpu().numpy(), split[n].numpy(), 1e-4, 2e-6 * float(split[n].abs().max()), f"split vs one-call {n}")
 
 
+@pytest.mark.parametrize("G,S,A,H,B", [(10, 17, 6, 256, 256), (2, 3, 1, 64, 100), (3, 11, 12, 128, 130)])
+def test_action_gradient_through_critics(G, S, A, H, B):
+    """ssac_mlp_backward_dact == input-gradient pass of ssac_mlp_backward summed over the nets (and the oracle)."""
+    from super_sac_b200 import _ops
+
+    gen = torch.Generator().manual_seed(G * 13 + H + A)
+    D = S + A
+    st = uo.MLPStack(G, D, H, 1).random_init(gen)
+    ar = _arena_from(st)
+    x = torch.randn(B, D, generator=gen)
+    # arg-min routing: one net per row carries the seed
+    dq = torch.zeros(G, B, 1)
+    dq[torch.randint(0, G, (B,), generator=gen), torch.arange(B), 0] = -torch.rand(B, generator=gen) / B
+    h1_ref, h2_ref = torch.empty(G, B, H), torch.empty(G, B, H)
+    want = torch.zeros(B, A)
+    for g in range(G):
+        _, h1w, h2w = uo.mlp_forward(st, g, x)
+        h1_ref[g], h2_ref[g] = h1w, h2w
+        dx = uo.mlp_backward(st, g, x, h1w, h2w, dq[g], st.zeros_like(), need_dx=True, need_dw=False)
+        want += dx[:, S:]
+    xd, h1, h2, dqd = x.to(DEV), h1_ref.to(DEV), h2_ref.to(DEV), dq.to(DEV)
+    ws = torch.empty(L().mlp_backward_ws(G, B, H), dtype=torch.float32, device=DEV)
+    da = torch.full((B, A), float("nan"), device=DEV)
+    W1, _, W2, _, W3, _ = ar.ptrs(0)
+    for impl in (1, 2):
+        L().mlp_backward_dact(W1, W2, W3, G, D, H, S, A, B, h1.data_ptr(), h2.data_ptr(), dqd.data_ptr(), da.data_ptr(),
+                              ws.data_ptr(), impl, None)
+        torch.cuda.synchronize()
+        gu.assert_close(da.cpu().numpy(), want.numpy(), 1e-4, 1e-5 * float(want.abs().max()), f"da impl {impl}")
+    dxg = torch.empty((G, B, D), device=DEV)
+    _ops.mlp_backward(ar, 0, G, xd, B, h1, h2, dqd, want_dw=False, dx=dxg, lddx=D, impl=2)
+    gu.assert_close(da.cpu().numpy(), dxg.sum(0)[:, S:].cpu().numpy(), 1e-4, 1e-5 * float(want.abs().max()), "da vs dx path")
+
+
 # ------------------------------------------------------------------------------------------------ heads / TD / weights
 def test_policy_heads_match_oracle():
     gen = torch.Generator().manual_seed(4)
