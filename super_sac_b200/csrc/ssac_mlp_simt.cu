@@ -122,19 +122,28 @@ constexpr int kSmallO = 32;
 #define SSAC_LOG_SQRT_2PIF 0.9189385332046727f
 __device__ __forceinline__ float softplus_th(float z) { return z > 20.f ? z : log1pf(expf(z)); }
 
-__global__ void __launch_bounds__(256) head_forward_kernel(const float* __restrict__ h2, const float* __restrict__ W3,
+// Block = 8 or 16 warps, one batch row per warp (16 when the batch and W3 are large: the [O][H] weight block is then
+// staged once per 16 rows instead of once per 8).
+constexpr int kHeadMaxWarps = 16;
+__global__ void __launch_bounds__(512) head_forward_kernel(const float* __restrict__ h2, const float* __restrict__ W3,
                                                            const float* __restrict__ b3,
                                                            const int32_t* __restrict__ net_index, int G, int B, int H,
                                                            int O, float* __restrict__ y, HeadEpi epi) {
-  extern __shared__ float W3s[];   // [O][H]
-  __shared__ float red[2][8];
-  const int g = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  extern __shared__ __align__(16) float W3s[];   // [O][H]
+  __shared__ float red[2][kHeadMaxWarps];
+  const int g = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int wg = net_index ? net_index[g] : g;
   const float* W = W3 + (int64_t)wg * O * H;
-  for (int i = threadIdx.x; i < O * H; i += blockDim.x) W3s[i] = __ldg(W + i);   // parameters: before the PDL wait
+  // parameters: staged before the PDL wait
+  if (((O * H) & 3) == 0 && ((((uintptr_t)W) & 15) == 0)) {
+    for (int i = threadIdx.x; i < (O * H) >> 2; i += blockDim.x)
+      reinterpret_cast<float4*>(W3s)[i] = __ldg(reinterpret_cast<const float4*>(W) + i);
+  } else {
+    for (int i = threadIdx.x; i < O * H; i += blockDim.x) W3s[i] = __ldg(W + i);
+  }
   pdl_wait();
   pdl_trigger();
-  const int b = blockIdx.x * 8 + warp;
+  const int b = blockIdx.x * nwarps + warp;
   const bool row_ok = b < B;
   const float* hrow = h2 + ((int64_t)g * B + (row_ok ? b : 0)) * H;
   float hv[32];   // H <= 1024
@@ -193,7 +202,7 @@ __global__ void __launch_bounds__(256) head_forward_kernel(const float* __restri
     }
   } else if (epi.kind == 3) {
     // dq = -2 w imp (y - q') popw / (B E N_total);  loss += w imp (y - q')^2 / (B E N_total)
-    __shared__ float red_td[3][8];
+    __shared__ float red_td[3][kHeadMaxWarps];
     float l = 0.f, tdv = 0.f, s1 = 0.f, s2 = 0.f, se = 0.f;
     // TD target in place (same operation order as td_target_kernel: bit-identical y)
     float alpha = 0.f, y0 = 0.f;
@@ -236,15 +245,13 @@ __global__ void __launch_bounds__(256) head_forward_kernel(const float* __restri
     if (threadIdx.x == 0) {
       if (epi.loss) {
         float sl = 0.f, st = 0.f;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { sl += red[0][k]; st += red[1][k]; }
+        for (int k = 0; k < nwarps; ++k) { sl += red[0][k]; st += red[1][k]; }
         atomicAdd(&epi.loss[0], sl);
         if (g == G - 1) atomicAdd(&epi.loss[1], st / (float)B);
       }
       if (epi.qt && g == 0 && epi.td_logs) {
         float a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { a1 += red_td[0][k]; a2 += red_td[1][k]; a3 += red_td[2][k]; }
+        for (int k = 0; k < nwarps; ++k) { a1 += red_td[0][k]; a2 += red_td[1][k]; a3 += red_td[2][k]; }
         atomicAdd(&epi.td_logs[0], a1);
         atomicAdd(&epi.td_logs[1], a2);
         atomicAdd(&epi.td_logs[2], a3);
@@ -355,8 +362,9 @@ int head_forward(const float* h2, const float* W3, const float* b3, const int32_
     cudaFuncSetAttribute(head_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
     attr_set = true;
   }
-  dim3 grid((B + 7) / 8, G);
-  launch_pdl(head_forward_kernel, grid, dim3(256), smem, s, h2, W3, b3, net_index, G, B, H, O, y, e);
+  const int nwarps = (B >= 512 && (size_t)O * H >= 4096) ? kHeadMaxWarps : 8;
+  dim3 grid((B + nwarps - 1) / nwarps, G);
+  launch_pdl(head_forward_kernel, grid, dim3(32 * nwarps), smem, s, h2, W3, b3, net_index, G, B, H, O, y, e);
   SSAC_CHECK_LAUNCH("mlp head forward");
   return 0;
 }

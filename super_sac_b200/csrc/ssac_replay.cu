@@ -307,17 +307,29 @@ __global__ void __launch_bounds__(1024) tree_set_small_kernel(double* __restrict
                                                               double* __restrict__ min_tree, int64_t capacity,
                                                               const int64_t* __restrict__ idx,
                                                               const double* __restrict__ val, int n) {
-  __shared__ int64_t sidx[1024];
+  // "last write wins": the writer of a leaf is the highest position t that names it.  A 2048-slot open-addressing
+  // table in shared memory (key = leaf, value = max position) finds it in O(1) expected probes per element.
+  constexpr int kSlots = 2048;
+  constexpr unsigned long long kEmpty = ~0ull;
+  __shared__ unsigned long long hkey[kSlots];
+  __shared__ int hval[kSlots];
   const int t = threadIdx.x;
-  if (t < n) sidx[t] = idx[t];
+  for (int i = t; i < kSlots; i += blockDim.x) { hkey[i] = kEmpty; hval[i] = -1; }
+  __syncthreads();
+  const unsigned long long key = t < n ? (unsigned long long)idx[t] : 0ull;
+  int slot = (int)((key * 0x9E3779B97F4A7C15ull) >> 53);   // top 11 bits
+  if (t < n) {
+    while (true) {
+      const unsigned long long prev = atomicCAS(&hkey[slot], kEmpty, key);
+      if (prev == kEmpty || prev == key) { atomicMax(&hval[slot], t); break; }
+      slot = (slot + 1) & (kSlots - 1);
+    }
+  }
   __syncthreads();
   int64_t node = 0;
   if (t < n) {
-    bool last = true;
-    for (int j = t + 1; j < n; ++j)
-      if (sidx[j] == sidx[t]) { last = false; break; }
-    node = sidx[t] + capacity;
-    if (last) {
+    node = (int64_t)key + capacity;
+    if (hval[slot] == t) {   // slot still addresses this thread's key
       sum_tree[node] = val[t];
       min_tree[node] = val[t];
     }

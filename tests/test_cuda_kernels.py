@@ -213,6 +213,25 @@ def test_per_tree_large_matches_oracle():
         assert np.array_equal(sum_t.cpu().numpy(), orc.it_sum.value) and np.array_equal(min_t.cpu().numpy(), orc.it_min.value)
 
 
+def test_tree_set_last_write_wins_on_duplicates():
+    """numpy fancy assignment semantics (replay.py:263-277): with repeated leaves the LAST value sticks."""
+    rng = np.random.default_rng(3)
+    cap = 1 << 12
+    for n_leaves, n in ((7, 1024), (200, 1000), (4096, 1024), (1, 33)):
+        orc = ro.SegmentTree(cap, np.add, 0.0)
+        orc_min = ro.SegmentTree(cap, np.minimum, float("inf"))
+        sum_t = torch.zeros(2 * cap, dtype=torch.float64, device=DEV)
+        min_t = torch.full((2 * cap,), float("inf"), dtype=torch.float64, device=DEV)
+        idx = rng.integers(0, n_leaves, n)
+        val = rng.uniform(0.1, 3.0, n)
+        orc.set(idx, val)
+        orc_min.set(idx, val)
+        idx_d, val_d = dev(idx), dev(val)
+        L().tree_set(sum_t.data_ptr(), min_t.data_ptr(), cap, idx_d.data_ptr(), val_d.data_ptr(), n, S())
+        assert np.array_equal(sum_t.cpu().numpy(), orc.value), (n_leaves, n)
+        assert np.array_equal(min_t.cpu().numpy(), orc_min.value), (n_leaves, n)
+
+
 # ------------------------------------------------------------------------------------------------ pixels
 def _aug_call(src, idx, shift, B, C, H, W, pad, mode, aug_rows, noise=None):
     out = torch.empty((B, C, H, W), device=DEV)
