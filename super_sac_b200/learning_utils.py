@@ -570,13 +570,20 @@ def _advantage(agent, replay_dict, ensemble_idx, n=4, want_priority=False):
         s_rep = agent.encoder(o)
     XA = _first_layer_input(s_rep, a, packed["XA"] if packed else None, S, A)
     q_pi = torch.empty((n, B), dtype=torch.float32, device=dev)
-    Xp = torch.empty((B, S + A), dtype=torch.float32, device=dev)
-    Xp[:, :S].copy_(XA[:, :S])
     pptr = popart.state_ptr() if popart else None
-    for j in range(n):
-        _policy_sample(agent, i, Xp, B, S, A, None, None)
-        q = _critic_values(agent, i * N, N, Xp, B)
-        L.min_over_nets(q.data_ptr(), N, B, pptr, q_pi[j].data_ptr(), s)
+    # the n policy samples as ONE batch of n*B rows (sample-major): one actor forward, one critic forward and one
+    # min-over-nets instead of n of each.  The N(0,1) draws stay n separate fills, in the reference's order.
+    Xp = torch.empty((n, B, S + A), dtype=torch.float32, device=dev)
+    Xp[:, :, :S].copy_(XA[:, :S].unsqueeze(0).expand(n, B, S))
+    eps = None
+    if not agent.deterministic:
+        eps = torch.empty((n, B, A), dtype=torch.float32, device=dev)
+        for j in range(n):
+            _rng.source().normal(eps[j])
+    Xp2 = Xp.view(n * B, S + A)
+    _policy_sample(agent, i, Xp2, n * B, S, A, None, None, eps=None if eps is None else eps.view(n * B, A))
+    q = _critic_values(agent, i * N, N, Xp2, n * B)
+    L.min_over_nets(q.data_ptr(), N, n * B, pptr, q_pi.data_ptr(), s)
     q = _critic_values(agent, i * N, N, XA, B)
     q_data = torch.empty((B,), dtype=torch.float32, device=dev)
     L.min_over_nets(q.data_ptr(), N, B, pptr, q_data.data_ptr(), s)
