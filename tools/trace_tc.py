@@ -12,9 +12,11 @@ W1 = torch.randn(G, H, D, device=dev); b1 = torch.randn(G, H, device=dev); W2 = 
 W3 = torch.randn(G, O, H, device=dev); b3 = torch.randn(G, O, device=dev)
 x = torch.randn(B, D, device=dev); h1 = torch.empty(G, B, H, device=dev); h2 = torch.empty_like(h1); y = torch.empty(G, B, O, device=dev)
 f = lib.ssac_mlp_forward
-f.argtypes = [ctypes.c_void_p]*7 + [ctypes.c_int]*4 + [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int] + [ctypes.c_void_p]*3 + [ctypes.c_int, ctypes.c_void_p]
+f.argtypes = [ctypes.c_void_p]*7 + [ctypes.c_int]*4 + [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int] + [ctypes.c_void_p]*2 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+lib.ssac_set_fused_forward.argtypes = [ctypes.c_int]
+lib.ssac_set_fused_forward(0)   # this tool traces the layered GEMM kernel
 for it in range(3):
-    rc = f(W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr(), W3.data_ptr(), b3.data_ptr(), None, G, D, H, O, x.data_ptr(), D, 0, B, h1.data_ptr(), h2.data_ptr(), y.data_ptr(), 2, None)
+    rc = f(W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr(), W3.data_ptr(), b3.data_ptr(), None, G, D, H, O, x.data_ptr(), D, 0, B, h1.data_ptr(), h2.data_ptr(), 1, y.data_ptr(), 2, None)
     torch.cuda.synchronize()
 t = trace.cpu().tolist()
 print("rc", rc)
