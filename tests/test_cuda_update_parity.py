@@ -406,3 +406,39 @@ def test_auto_graph_replay_equals_eager():
     assert set(l0.keys()) == set(l1.keys()) and set(al0.keys()) == set(al1.keys())
     for k in l0:
         gu.assert_close(float(l1[k]), float(l0[k]), 1e-5, 1e-7, f"log {k}")
+
+
+def test_module_views_and_kernels_agree_on_the_acting_path():
+    """The nn.Modules the reference API exposes (Agent.forward / sample_action, critics[i](s, a)) are views into the
+    parameter arenas the kernels read: after a fused update both must see the same parameters, and the PyTorch forward of
+    the modules must equal the kernel forward (acting path)."""
+    import cuda_util as cu
+    import super_sac_b200 as ssb
+    from super_sac_b200 import learning_utils as lu, nets
+
+    torch.manual_seed(3)
+    S, A, H, N, B = 17, 6, 256, 10, 64
+    agent = ssb.Agent(act_space_size=A, encoder=cu.IdentityEncoder(S), actor_network_cls=nets.mlps.ContinuousStochasticActor,
+                      critic_network_cls=nets.mlps.ContinuousCritic, ensemble_size=1, num_critics=N, hidden_size=H,
+                      auto_rescale_targets=False, log_std_low=-5.0, log_std_high=2.0)
+    agent.to(ssb.device)
+    dev = agent._critic_arena.device
+    with torch.no_grad():   # perturb through the arena, read through the modules
+        agent._critic_arena.flat.mul_(1.5)
+        agent._actor_arena.flat.add_(0.01)
+    s = torch.randn(B, S, device=dev)
+    a = torch.rand(B, A, device=dev) * 2 - 1
+    with torch.no_grad():
+        q_mod = torch.stack([net(s, a) for net in agent.critics[0].nets], dim=0)          # PyTorch path, [N,B,1]
+        mu_mod = agent.actors[0](s).mean                                                   # tanh(mu)
+    X = torch.cat((s, a), dim=1).contiguous()
+    q_ker = lu._critic_values(agent, 0, N, X, B)
+    gu.assert_close(q_ker.cpu().numpy(), q_mod.cpu().numpy(), 1e-4, 2e-5, "critics: kernel vs nn.Module")
+    out, _, _ = lu._actor_forward(agent, 0, X, B, S, A)
+    gu.assert_close(torch.tanh(out[0, :, :A]).cpu().numpy(), mu_mod.cpu().numpy(), 1e-4, 2e-5, "actor mean: kernel vs nn.Module")
+    obs = {"obs": s[0].cpu().numpy()}
+    act = agent.forward(obs)
+    assert act.shape == (A,) and np.all(np.abs(act) <= 1.0)
+    gu.assert_close(act, mu_mod[0].cpu().numpy(), 1e-4, 2e-5, "Agent.forward")
+    smp = agent.sample_action(obs)
+    assert smp.shape == (A,) and np.all(np.abs(smp) <= 1.0)
