@@ -495,6 +495,35 @@ def test_action_gradient_through_critics(G, S, A, H, B):
     gu.assert_close(da.cpu().numpy(), dxg.sum(0)[:, S:].cpu().numpy(), 1e-4, 1e-5 * float(want.abs().max()), "da vs dx path")
 
 
+def test_3xtf32_accuracy_against_float64():
+    """The operand split assumes that kind::tf32 TRUNCATES an fp32 operand to its top 19 bits (lo = x - trunc(x) is then
+    exactly what the tensor core dropped).  If the hardware rounded instead, elements whose dropped bits exceed half an
+    ulp would be off by 2^-11 relative and the error below would be ~100x larger than the fp32-FFMA path's."""
+    from super_sac_b200 import _ops
+
+    gen = torch.Generator().manual_seed(21)
+    G, D, H, O, B = 4, 23, 256, 1, 256
+    st = uo.MLPStack(G, D, H, O).random_init(gen)
+    ar = _arena_from(st)
+    x = torch.randn(B, D, generator=gen)
+    xd = x.to(DEV)
+    ref = []
+    for g in range(G):   # float64 forward
+        W1, b1, W2, b2 = (getattr(st, n)[g].double() for n in ("W1", "b1", "W2", "b2"))
+        h1 = torch.relu(x.double() @ W1.T + b1)
+        ref.append(torch.relu(h1 @ W2.T + b2))
+    ref = torch.stack(ref)
+    errs = {}
+    for name, impl, fused in (("ffma", 1, 0), ("tcgen05-layered", 2, 0), ("tcgen05-fused", 2, 1)):
+        L().set_fused_forward(fused)
+        h1 = torch.empty((G, B, H), device=DEV); h2 = torch.empty_like(h1); y = torch.empty((G, B, O), device=DEV)
+        _ops.mlp_forward(ar, 0, G, xd, B, h1, h2, y, impl=impl, keep_hidden=True)
+        errs[name] = float((h2.double().cpu() - ref).abs().max() / ref.abs().max())
+    L().set_fused_forward(1)
+    assert errs["ffma"] < 2e-6, errs
+    assert errs["tcgen05-layered"] < 1e-5 and errs["tcgen05-fused"] < 1e-5, errs   # rounding hardware would give ~2e-4
+
+
 # ------------------------------------------------------------------------------------------------ heads / TD / weights
 def test_policy_heads_match_oracle():
     gen = torch.Generator().manual_seed(4)
