@@ -101,8 +101,10 @@ int ssac_push_row(const void* host_row_pinned, void* staging_dev, int64_t row_by
 int ssac_push_row_wait(int slot);
 /* Fused pixel gather + DrQ / DrQv2 random shift + uint8 -> fp32 + aug_mix: augmentations.py:165-269,
  * learning_utils.py:193-206.   src u8 [capacity, C, H, W] -> dst f32 [B, C, H, W].
- * pad_mode 0: no shift, 1: replicate (DrQv2 integer crop), 2: reflect (DrQ v1).
- * shift_dev int32 [B,2] = (x, y) with 0 <= shift <= 2*pad (v2) / < 2*pad (v1).  Rows b < aug_rows are
+ * pad_mode 0: no shift, 1: replicate (DrQv2 integer crop), 2: reflect (DrQ v1), 3: RAD (augmentations.py:129-162:
+ * cv2 bilinear upscale by `pad` (= crop) pixels per axis, then the H x W window at offset shift; same fp32
+ * arithmetic as cv2.resize(INTER_LINEAR) on float32 data, bit-exact on frame stacks of more than 4 channels).
+ * shift_dev int32 [B,2] = (x, y) with 0 <= shift <= 2*pad (v2) / < 2*pad (v1) / < crop (RAD).  Rows b < aug_rows are
  * augmented, the rest are a plain cast.  noise_dev (nullable) f32 [B,C,H,W] is added before the clamp to
  * [0,255] (DrqAug noise=True). */
 int ssac_gather_aug_u8(const uint8_t* src_dev, float* dst_dev, const int64_t* idx_dev, const int32_t* shift_dev,
@@ -277,10 +279,11 @@ int ssac_alpha_step(float* log_alpha_dev, const float* logp_dev, int B, float ta
                     int32_t* ctl_dev, double lr, double beta1, double beta2, double eps, float* logs_dev, void* stream);
 
 /* ---- advantage filter: adv_estimator.py:58-79, learning_utils.py:241-269,288-295 ------------------ */
-/* q_pi [n,B] = min-critic values of n policy samples, q_data [B]: adv = q_data - mean_n q_pi;
+/* q_pi [n,B] = min-critic values of n policy samples, q_data [B]: adv = q_data - V with V = mean_n q_pi (method 0,
+ * continuous_method "mean") or max_n q_pi (method 1, "max": adv_estimator.py:71-76);
  * mask = (adv >= 0); priority (float64) = relu(adv) + 1e-4.  Any output nullable. */
-int ssac_advantage(const float* q_pi_dev, int n, const float* q_data_dev, int B, float* adv_dev, float* mask_dev,
-                   double* priority_dev, void* stream);
+int ssac_advantage(const float* q_pi_dev, int n, const float* q_data_dev, int B, int method, float* adv_dev,
+                   float* mask_dev, double* priority_dev, void* stream);
 /* min over the N rows of q [N,B] with optional PopArt affine (agent.py:37-38, adv_estimator.py:30-35). */
 int ssac_min_over_nets(const float* q_dev, int N, int B, const float* popart_dev, float* out_dev, void* stream);
 

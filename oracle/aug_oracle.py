@@ -4,6 +4,7 @@ augmentations.py:165-211 (DrqAug: reflection pad + integer crop [+ N(0,1) noise]
 augmentations.py:214-269 (Drqv2Aug: replicate pad + shift; restated as the integer crop it encodes --
 the reference evaluates it with a bilinear grid_sample whose fp32 grid arithmetic lands ~1e-5 px off the
 pixel centres, so it differs from the integer crop by <= 4e-3 on the 0..255 scale),
+augmentations.py:129-162 (RadAug: cv2 bilinear upscale + integer crop),
 learning_utils.py:193-206 (uint8 -> float cast, first int(B*aug_mix) rows replaced by their augmentation).
 Byte/index work: the CUDA path must match this bit-for-bit.
 """
@@ -40,6 +41,47 @@ def drq_v2_crop(imgs, shift, pad=4):
     out = imgs[np.arange(B)[:, None, None, None], np.arange(C)[None, :, None, None],
                ys[:, None, :, None], xs[:, None, None, :]].astype(np.float32)
     return np.clip(out, 0.0, 255.0).astype(np.float32)
+
+
+def _cv2_linear_axis(n_src, n_dst, horizontal):
+    """Source taps and fp32 weights of cv2.resize(INTER_LINEAR) along one axis (OpenCV resize.cpp, resizeGeneric_ for
+    float32 images): fx = float((d + 0.5) * scale - 0.5) with scale = 1 / (n_dst / n_src) in double, tap = floor(fx),
+    weight = fx - tap in fp32.  Horizontally an out-of-range tap is moved onto the edge with weight 0; vertically the
+    two row indices are clamped and keep their weights."""
+    scale = 1.0 / (n_dst / n_src)
+    f = ((np.arange(n_dst, dtype=np.float64) + 0.5) * scale - 0.5).astype(np.float32)
+    s = np.floor(f).astype(np.int64)
+    f = (f - s.astype(np.float32)).astype(np.float32)
+    if horizontal:
+        lo, hi = s < 0, s >= n_src - 1
+        f[lo], s[lo] = 0.0, 0
+        f[hi], s[hi] = 0.0, n_src - 1
+        s0, s1 = s, np.minimum(s + 1, n_src - 1)
+    else:
+        s0, s1 = np.clip(s, 0, n_src - 1), np.clip(s + 1, 0, n_src - 1)
+    return s0, s1, (np.float32(1.0) - f).astype(np.float32), f
+
+
+def rad_crop(imgs, h_off, w_off, crop=16):
+    """RadAug.__call__ (augmentations.py:129-162): every image is upscaled to (H+crop, W+crop) with
+    cv2.resize(INTER_LINEAR) on float32 HWC data and the window [h:h+H, w:w+W] is cut out.  imgs [B,C,H,W] (any dtype)
+    -> float32.  Restates cv2's separable fp32 arithmetic -- horizontal pass S[x0]*a0 + S[x1]*a1, vertical pass
+    r0*b0 + r1*b1, each product and sum rounded to fp32 -- which reproduces cv2 4.x bit for bit on images with more
+    than 4 channels (frame stacks); cv2's <=4-channel path rounds differently (<= 1e-3 on the 0..255 scale)."""
+    imgs = np.asarray(imgs)
+    B, C, H, W = imgs.shape
+    S = imgs.astype(np.float32)
+    ys0, ys1, b0, b1 = _cv2_linear_axis(H, H + crop, False)
+    xs0, xs1, a0, a1 = _cv2_linear_axis(W, W + crop, True)
+    out = np.empty((B, C, H, W), dtype=np.float32)
+    for i in range(B):
+        Y, X = np.arange(H) + int(h_off[i]), np.arange(W) + int(w_off[i])
+        y0, y1, x0, x1 = ys0[Y], ys1[Y], xs0[X], xs1[X]
+        wa0, wa1, wb0, wb1 = a0[X], a1[X], b0[Y][None, :, None], b1[Y][None, :, None]
+        r0 = ((S[i][:, y0][:, :, x0] * wa0).astype(np.float32) + (S[i][:, y0][:, :, x1] * wa1).astype(np.float32)).astype(np.float32)
+        r1 = ((S[i][:, y1][:, :, x0] * wa0).astype(np.float32) + (S[i][:, y1][:, :, x1] * wa1).astype(np.float32)).astype(np.float32)
+        out[i] = ((r0 * wb0).astype(np.float32) + (r1 * wb1).astype(np.float32)).astype(np.float32)
+    return out
 
 
 def mix(original_f32, augmented_f32, aug_mix):

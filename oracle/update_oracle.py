@@ -506,6 +506,12 @@ def online_actor_update(agent, batches, rands, hp, log_alphas, actor_opt):
         pop_on = popart is not None and hp.get("pop", False)
         a, logp, cache = actor_sample(agent, i, s_rep, rands[i].get("eps"))
         a_pre = a
+        if agent.deterministic and rands[i].get("eps") is not None:
+            # ContinuousDeterministic is Normal(loc, 1e-4) (nets/distributions.py:107-114): rsample() (learning.py:392)
+            # returns loc + 1e-4*eps, and log_prob of that sample is const - eps^2/2 per dimension
+            eps = rands[i]["eps"]
+            a = a + 1e-4 * eps
+            logp = (-(eps**2) / 2 - math.log(1e-4) - LOG_SQRT_2PI).sum(-1, keepdim=True)
         if hp.get("noise_sigma") is not None:
             a = gaussian_noise_clamp(a, rands[i]["noise"], hp["noise_sigma"], hp.get("noise_clip"), -1.0, 1.0)
             entropy = torch.zeros(1)
@@ -566,8 +572,8 @@ def alpha_update(agent, batches, rands, log_alphas, alpha_opts, target_entropy):
     return logs
 
 
-def advantage(agent, i, o, a, eps_list):
-    """adv_estimator.py:58-79 continuous_forward, method 'mean' / n = len(eps_list) policy samples."""
+def advantage(agent, i, o, a, eps_list, method="mean"):
+    """adv_estimator.py:58-79 continuous_forward, method 'mean' | 'max' / n = len(eps_list) policy samples."""
     with torch.no_grad():
         s_rep = agent.encode(o)
         popart = agent.popart[i]
@@ -576,7 +582,7 @@ def advantage(agent, i, o, a, eps_list):
         for eps in eps_list:
             act, _, _ = actor_sample(agent, i, s_rep, eps)
             qs.append(pop(agent.critic_min(i, s_rep, act)))
-        value = torch.stack(qs, 0).mean(0)
+        value = torch.stack(qs, 0).mean(0) if method == "mean" else torch.stack(qs, 0).max(0).values
         q = pop(agent.critic_min(i, s_rep, a))
     return q - value
 

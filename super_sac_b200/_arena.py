@@ -167,7 +167,17 @@ class FlatAdam:
     @classmethod
     def attach(cls, optimizer, arena):
         cur = getattr(optimizer, "_ssac_flat_adam", None)
-        if cur is None or cur.arena is not arena or cur.m.device != arena.device:
+        if cur is not None and cur.arena is arena and cur.m.device == arena.device:
+            # optimizer.load_state_dict() replaces optimizer.state with fresh tensors: the fused step would keep using its
+            # private moments and silently ignore the loaded ones.  Probe one parameter: if its exp_avg no longer aliases
+            # the flat buffer, re-import the state (the constructor copies exp_avg / exp_avg_sq / step back in).
+            p0 = next(iter(arena.parameters()), None)
+            st = optimizer.state.get(p0) if p0 is not None else None
+            if st is None or "exp_avg" not in st or st["exp_avg"].data_ptr() != cur.m.data_ptr() + 4 * arena.offsets["W1"]:
+                cur = None
+        else:
+            cur = None
+        if cur is None:
             cur = cls(optimizer, arena)
             optimizer._ssac_flat_adam = cur
         return cur

@@ -13,8 +13,6 @@ class AdvantageEstimator(nn.Module):
         assert continuous_method in ["mean", "max"]
         if discrete:
             raise NotImplementedError("discrete actions are out of scope")
-        if continuous_method != "mean":
-            raise NotImplementedError("adv_method='max' is not implemented on the fused path")
         # plain attributes (not sub-modules): the Agent owns these objects
         object.__setattr__(self, "encoder", encoder)
         object.__setattr__(self, "actors", actors)

@@ -14,7 +14,7 @@ import torch
 
 from . import _rng
 
-PAD_NONE, PAD_REPLICATE, PAD_REFLECT = 0, 1, 2
+PAD_NONE, PAD_REPLICATE, PAD_REFLECT, PAD_RAD = 0, 1, 2, 3
 
 
 class _ShiftAug:
@@ -97,6 +97,49 @@ class Drqv2Aug(_ShiftAug):
 
     def __repr__(self):
         return "DrqV2"
+
+
+class RadAug(_ShiftAug):
+    """RAD (reference augmentations.py:129-162): bilinear upscale by ``crop`` pixels per axis (cv2.resize,
+    INTER_LINEAR, float32) followed by a random H x W window.  In the update path only the window is evaluated, inside
+    the gather kernel and straight from the uint8 ring (ssac_gather_aug_u8, pad_mode 3), with cv2's separable fp32
+    arithmetic: bit-exact with the reference on frame stacks (> 4 channels); cv2's <= 4-channel path rounds
+    differently (<= 1e-3 on the 0..255 scale).  ``shift`` = (w, h) window offsets in [0, crop)."""
+    pad_mode = PAD_RAD
+
+    def __init__(self, batch_size, crop=16, *_args, **_kwargs):
+        super().__init__(batch_size, pad=crop, noise=False)
+        self.crop = crop
+
+    def change_randomization_params(self, device=None):
+        if device is None:
+            from . import device as default_device
+
+            device = default_device
+        if self.shift is None or self.shift.device != torch.device(device):
+            self.shift = torch.zeros((self.batch_size, 2), dtype=torch.int32, device=device)
+        _rng.source().shifts(self.shift, self.crop)
+
+    def __call__(self, imgs):
+        """Standalone use on a float batch [B,C,H,W] (values 0..255 that are whole numbers, as the update path
+        produces them): routed through the same kernel via a uint8 view of the batch."""
+        from . import _lib
+
+        b, c, h, w = imgs.shape
+        assert b == self.batch_size
+        if self.shift is None or self.shift.device != imgs.device:
+            self.change_randomization_params(imgs.device)
+        src = imgs.round().clamp(0, 255).to(torch.uint8).contiguous()
+        if not torch.equal(src.float(), imgs):
+            raise NotImplementedError("RadAug on non-integer pixel values (the fused path reads the uint8 replay ring)")
+        out = torch.empty((b, c, h, w), dtype=torch.float32, device=imgs.device)
+        idx = torch.arange(b, dtype=torch.int64, device=imgs.device)
+        _lib.lib().gather_aug_u8(src.data_ptr(), out.data_ptr(), idx.data_ptr(), self.shift.data_ptr(), None, b, c, h, w,
+                                 self.crop, PAD_RAD, b, _lib.stream_ptr())
+        return out
+
+    def __repr__(self):
+        return "RAD"
 
 
 class IdentityAug:

@@ -586,12 +586,20 @@ __global__ void __launch_bounds__(1024) alpha_step_kernel(float* __restrict__ lo
 }
 
 __global__ void advantage_kernel(const float* __restrict__ q_pi, int n, const float* __restrict__ q_data, int B,
-                                 float* __restrict__ adv, float* __restrict__ mask, double* __restrict__ prio) {
+                                 int method, float* __restrict__ adv, float* __restrict__ mask,
+                                 double* __restrict__ prio) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  float s = 0.f;
-  for (int j = 0; j < n; ++j) s += q_pi[(int64_t)j * B + b];
-  const float a = q_data[b] - s / (float)n;
+  float v;
+  if (method == 1) {   // optimistic value: max over the n policy samples (adv_estimator.py:74-76)
+    v = q_pi[b];
+    for (int j = 1; j < n; ++j) v = fmaxf(v, q_pi[(int64_t)j * B + b]);
+  } else {             // V(s) = mean over the n policy samples (adv_estimator.py:71-73)
+    float s = 0.f;
+    for (int j = 0; j < n; ++j) s += q_pi[(int64_t)j * B + b];
+    v = s / (float)n;
+  }
+  const float a = q_data[b] - v;
   if (adv) adv[b] = a;
   if (mask) mask[b] = (a >= 0.f) ? 1.f : 0.f;
   if (prio) prio[b] = (double)(fmaxf(a, 0.f) + 1e-4f);
@@ -821,10 +829,10 @@ int ssac_alpha_step(float* log_alpha, const float* logp, int B, float target_ent
   return 0;
 }
 
-int ssac_advantage(const float* q_pi, int n, const float* q_data, int B, float* adv, float* mask, double* prio,
-                   void* stream) {
-  SSAC_REQUIRE(q_pi && q_data && n > 0 && B > 0, "ssac_advantage: bad args");
-  advantage_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(q_pi, n, q_data, B, adv, mask, prio);
+int ssac_advantage(const float* q_pi, int n, const float* q_data, int B, int method, float* adv, float* mask,
+                   double* prio, void* stream) {
+  SSAC_REQUIRE(q_pi && q_data && n > 0 && B > 0 && (method == 0 || method == 1), "ssac_advantage: bad args");
+  advantage_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(q_pi, n, q_data, B, method, adv, mask, prio);
   SSAC_CHECK_LAUNCH("ssac_advantage");
   return 0;
 }

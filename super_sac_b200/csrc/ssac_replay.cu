@@ -299,6 +299,85 @@ __global__ void __launch_bounds__(256) gather_aug_u8_kernel(const uint8_t* __res
 }
 
 // ------------------------------------------------------------------------------------------------
+// fused pixel gather + RAD crop + uint8->fp32: augmentations.py:129-162 (RadAug), learning_utils.py:193-206
+// The reference upscales every image to (H+crop, W+crop) with cv2.resize(INTER_LINEAR) on float32 data and cuts the
+// window [h:h+H, w:w+W]; here only the H x W window is ever evaluated, straight from the uint8 plane in shared memory,
+// with cv2's separable fp32 arithmetic (horizontal S[x0]*a0 + S[x1]*a1, vertical r0*b0 + r1*b1, every product and sum
+// rounded on its own: no FMA contraction), which reproduces cv2 bit for bit on frame stacks (> 4 channels).
+// One block per (sample, channel plane); the per-axis taps / weights of the block's window are built once in smem.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cv2_linear_tap(int d, int n_src, int n_dst, bool horizontal, int& s0, int& s1, float& w0,
+                                               float& w1) {
+  const double scale = 1.0 / ((double)n_dst / (double)n_src);
+  float f = (float)(((double)d + 0.5) * scale - 0.5);
+  int s = (int)floorf(f);
+  f = __fsub_rn(f, (float)s);
+  if (horizontal) {
+    if (s < 0) { f = 0.f; s = 0; }
+    if (s >= n_src - 1) { f = 0.f; s = n_src - 1; }
+    s0 = s;
+    s1 = min(s + 1, n_src - 1);
+  } else {
+    s0 = min(max(s, 0), n_src - 1);
+    s1 = min(max(s + 1, 0), n_src - 1);
+  }
+  w0 = __fsub_rn(1.0f, f);
+  w1 = f;
+}
+
+__global__ void __launch_bounds__(256) gather_rad_u8_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst,
+                                                            const int64_t* __restrict__ idx,
+                                                            const int32_t* __restrict__ shift, int C, int H, int W,
+                                                            int crop, int aug_rows) {
+  extern __shared__ __align__(16) uint8_t plane[];
+  const int b = blockIdx.x / C, c = blockIdx.x - b * C;
+  const int64_t plane_elems = (int64_t)H * W;
+  const size_t plane_pad = ((size_t)plane_elems + 15) & ~(size_t)15;
+  int* taps = (int*)(plane + plane_pad);            // [2*(H+W)]: y0[H] y1[H] x0[W] x1[W]
+  float* wts = (float*)(taps + 2 * (H + W));        // [2*(H+W)]: b0[H] b1[H] a0[W] a1[W]
+  const uint8_t* sp = src + (idx[b] * C + c) * plane_elems;
+  if ((plane_elems & 15) == 0 && (((uintptr_t)sp) & 15) == 0) {
+    const int4* sp4 = (const int4*)sp;
+    int4* pl4 = (int4*)plane;
+    for (int i = threadIdx.x; i < (int)(plane_elems >> 4); i += blockDim.x) pl4[i] = __ldg(sp4 + i);
+  } else {
+    for (int i = threadIdx.x; i < (int)plane_elems; i += blockDim.x) plane[i] = __ldg(sp + i);
+  }
+  const bool aug = b < aug_rows;
+  float* dp = dst + ((int64_t)b * C + c) * plane_elems;
+  if (aug) {
+    const int cw = shift[2 * b], ch = shift[2 * b + 1];
+    for (int i = threadIdx.x; i < H + W; i += blockDim.x) {
+      int s0, s1;
+      float w0, w1;
+      if (i < H) {
+        cv2_linear_tap(i + ch, H, H + crop, false, s0, s1, w0, w1);
+        taps[i] = s0; taps[H + i] = s1; wts[i] = w0; wts[H + i] = w1;
+      } else {
+        const int x = i - H;
+        cv2_linear_tap(x + cw, W, W + crop, true, s0, s1, w0, w1);
+        taps[2 * H + x] = s0; taps[2 * H + W + x] = s1; wts[2 * H + x] = w0; wts[2 * H + W + x] = w1;
+      }
+    }
+  }
+  __syncthreads();
+  if (!aug) {
+    for (int i = threadIdx.x; i < H * W; i += blockDim.x) dp[i] = (float)plane[i];
+    return;
+  }
+  for (int i = threadIdx.x; i < H * W; i += blockDim.x) {
+    const int y = i / W, x = i - y * W;
+    const uint8_t* r0 = plane + taps[y] * W;
+    const uint8_t* r1 = plane + taps[H + y] * W;
+    const int x0 = taps[2 * H + x], x1 = taps[2 * H + W + x];
+    const float a0 = wts[2 * H + x], a1 = wts[2 * H + W + x], b0 = wts[y], b1 = wts[H + y];
+    const float h0 = __fadd_rn(__fmul_rn((float)r0[x0], a0), __fmul_rn((float)r0[x1], a1));
+    const float h1 = __fadd_rn(__fmul_rn((float)r1[x0], a0), __fmul_rn((float)r1[x1], a1));
+    dp[i] = __fadd_rn(__fmul_rn(h0, b0), __fmul_rn(h1, b1));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // float64 segment trees: replay.py:207-353
 // ------------------------------------------------------------------------------------------------
 // small update (n <= 1024): one block, last write wins on duplicate indices (numpy fancy assignment),
@@ -540,11 +619,22 @@ int ssac_push_row(const void* host_row_pinned, void* staging_dev, int64_t row_by
 int ssac_gather_aug_u8(const uint8_t* src, float* dst, const int64_t* idx, const int32_t* shift, const float* noise,
                        int B, int C, int H, int W, int pad, int pad_mode, int aug_rows, void* stream) {
   SSAC_REQUIRE(src && dst && idx && B > 0 && C > 0 && H > 0 && W > 0, "ssac_gather_aug_u8: bad args");
-  SSAC_REQUIRE(pad_mode >= 0 && pad_mode <= 2, "ssac_gather_aug_u8: pad_mode must be 0, 1 or 2");
+  SSAC_REQUIRE(pad_mode >= 0 && pad_mode <= 3, "ssac_gather_aug_u8: pad_mode must be 0, 1, 2 or 3");
   SSAC_REQUIRE(pad_mode == 0 || shift, "ssac_gather_aug_u8: shift required when pad_mode != 0");
   SSAC_REQUIRE(pad_mode != 2 || (pad < H && pad < W), "ssac_gather_aug_u8: reflect pad must be < image size");
-  const size_t smem = ((size_t)H * W + 15) & ~(size_t)15;
+  SSAC_REQUIRE(pad_mode != 3 || (pad > 0 && !noise), "ssac_gather_aug_u8: RAD needs crop > 0 and takes no noise");
+  size_t smem = ((size_t)H * W + 15) & ~(size_t)15;
+  if (pad_mode == 3) smem += (size_t)4 * (H + W) * 4;   // taps + weights of the window
   SSAC_REQUIRE(smem <= 200 * 1024, "ssac_gather_aug_u8: image plane too large for shared memory");
+  if (pad_mode == 3) {
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(gather_rad_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) { set_error(std::string("ssac_gather_aug_u8 attr: ") + cudaGetErrorString(e)); return (int)e; }
+    }
+    gather_rad_u8_kernel<<<B * C, 256, smem, (cudaStream_t)stream>>>(src, dst, idx, shift, C, H, W, pad, aug_rows);
+    SSAC_CHECK_LAUNCH("ssac_gather_aug_u8 (rad)");
+    return 0;
+  }
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(gather_aug_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error(std::string("ssac_gather_aug_u8 attr: ") + cudaGetErrorString(e)); return (int)e; }

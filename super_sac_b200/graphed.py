@@ -69,18 +69,27 @@ def auto_graphs_enabled():
 
 
 class _Entry:
-    __slots__ = ("calls", "graph", "result", "on_replay")
+    __slots__ = ("calls", "graph", "result", "on_replay", "refs")
 
     def __init__(self):
-        self.calls, self.graph, self.result, self.on_replay = 0, None, None, None
+        self.calls, self.graph, self.result, self.on_replay, self.refs = 0, None, None, None, None
 
 
-def run_cached(key, fn, on_replay=None):
+def is_static(obj):
+    """True for objects (replay dicts) returned by a captured graph: the same buffers on every call."""
+    return getattr(obj, "_ssac_static", False)
+
+
+def run_cached(key, fn, on_replay=None, refs=None):
     """Eager for the first ``min_calls`` calls with this key (allocator and lazy state settle), then capture once
-    (capturing does not execute) and replay.  ``on_replay`` updates host-side mirrors (step counters)."""
+    (capturing does not execute) and replay.  ``on_replay`` updates host-side mirrors (step counters).  ``refs``: the
+    objects whose ``id()`` went into ``key`` -- the entry keeps them alive, so that CPython cannot hand one of those ids
+    to a new object while the entry exists (a key built from the ids of dead objects could otherwise match by accident).
+    The replay dicts a captured call returns are tagged static (``is_static``): they are the graph's own buffers."""
     e = _auto["cache"].get(key)
     if e is None:
         e = _auto["cache"][key] = _Entry()
+        e.refs = refs
     if e.graph is None:
         if e.calls < _auto["min_calls"]:
             e.calls += 1
@@ -91,6 +100,13 @@ def run_cached(key, fn, on_replay=None):
             with torch.cuda.graph(g):
                 e.result = fn()
         e.graph, e.on_replay = g, on_replay
+        if isinstance(e.result, tuple):
+            for part in e.result[1:]:
+                for rd in (part if isinstance(part, (list, tuple)) else [part]):
+                    try:
+                        rd._ssac_static = True
+                    except AttributeError:
+                        pass
     e.graph.replay()
     if e.on_replay is not None:
         e.on_replay()

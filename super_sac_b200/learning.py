@@ -57,7 +57,8 @@ def critic_update(buffer, agent, target_agent, critic_optimizer, encoder_optimiz
             opt.note_replayed_step()
             buffer.total_sample_calls += agent.ensemble_size
 
-        return graphed.run_cached(key, lambda: _critic_update_impl(*args), on_replay)
+        refs = (buffer, agent, target_agent, critic_optimizer, encoder_optimizer, tuple(log_alphas), augmenter)
+        return graphed.run_cached(key, lambda: _critic_update_impl(*args), on_replay, refs=refs)
     return _critic_update_impl(*args)
 
 
@@ -276,12 +277,17 @@ def online_actor_update(buffer, agent, pop, actor_optimizer, log_alphas, batch_s
     dicts come from a graph-replayed critic update, i.e. are the same static buffers on every call)."""
     args = (buffer, agent, pop, actor_optimizer, log_alphas, batch_size, clip, random_process, noise_clip, augmenter,
             aug_mix, premade_replay_dicts, per, discrete, use_baseline)
+    # Graph the actor update only over the STATIC buffers of a graph-captured critic update: eager critic updates hand
+    # out fresh replay dicts every step (whose ids CPython recycles), and a graph captured over those would replay on
+    # freed memory.
     if (not discrete and not use_baseline and premade_replay_dicts is not None
+            and all(graphed.is_static(rd) for rd in premade_replay_dicts)
             and _graphable(agent, random_process, per, False)):
         key = ("actor", id(agent), _opt_sig(actor_optimizer), tuple(id(l) for l in log_alphas), batch_size, clip, pop,
                tuple(id(rd) for rd in premade_replay_dicts), _lib.lib().default_mlp_impl())
         opt = _arena.FlatAdam.attach(actor_optimizer, agent._actor_arena)
-        return graphed.run_cached(key, lambda: _online_actor_update_impl(*args), opt.note_replayed_step)
+        refs = (agent, actor_optimizer, tuple(log_alphas), tuple(premade_replay_dicts))
+        return graphed.run_cached(key, lambda: _online_actor_update_impl(*args), opt.note_replayed_step, refs=refs)
     return _online_actor_update_impl(*args)
 
 
@@ -403,12 +409,20 @@ class _AlphaState:
         st = optimizer.state[log_alpha]
         self._step_tensor = torch.zeros((), dtype=torch.float32)
         self.steps = 0
+        if "exp_avg" in st:   # resuming from a loaded optimizer state (optimizer.load_state_dict)
+            self.state[0:1].copy_(st["exp_avg"].reshape(1))
+            self.state[1:2].copy_(st["exp_avg_sq"].reshape(1))
+            self.steps = int(st["step"])
+            self.ctl[0] = self.steps
+            self._step_tensor.fill_(self.steps)
         st["step"], st["exp_avg"], st["exp_avg_sq"] = self._step_tensor, self.state[0:1], self.state[1:2]
 
     @classmethod
     def attach(cls, optimizer, log_alpha):
         cur = getattr(optimizer, "_ssac_alpha_state", None)
-        if cur is None or cur.state.device != log_alpha.device:
+        st = optimizer.state.get(log_alpha)
+        aliased = st is not None and "exp_avg" in st and cur is not None and st["exp_avg"].data_ptr() == cur.state.data_ptr()
+        if cur is None or cur.state.device != log_alpha.device or not aliased:   # not aliased: load_state_dict replaced the state
             cur = cls(optimizer, log_alpha)
             optimizer._ssac_alpha_state = cur
         return cur

@@ -246,8 +246,11 @@ def sample_move_and_augment(buffer, batch_size, augmenter, aug_mix, per=True, _i
         keys = list(st.s_stack.keys())
         A = st.action_stack[0].numel()
         packed = None
+        shifting = getattr(aug, "pad_mode", augmentations.PAD_NONE) != augmentations.PAD_NONE
         if len(keys) == 1 and st.s_stack[keys[0]].dtype == torch.float32 and st.s_stack[keys[0]].dim() == 2 \
                 and st.action_stack.dim() == 2:
+            if shifting and keys[0] in aug_keys:   # as the general branch below: never skip an augmentation silently
+                raise NotImplementedError(f"shift augmentation of non-image key '{keys[0]}'")
             # state observations: gather s|a, s1|. and s|. straight into the [B, S+A] first-layer inputs
             k = keys[0]
             S = st.s_stack[k].shape[1]
@@ -406,7 +409,13 @@ def _policy_sample(agent, i, X, B, S, A, random_process, noise_clip, rsample=Fal
     res.update(eps=eps, logp=logp, tanh_out=tanh_out)
     if det and random_process is None:
         # Normal(loc, 1e-4).log_prob(loc) summed over A: a constant (nets/distributions.py:107-114)
-        res["logp"] = torch.full((B,), A * (0.0 - math.log(1e-4) - LOG_SQRT_2PI), dtype=torch.float32, device=dev)
+        const = A * (0.0 - math.log(1e-4) - LOG_SQRT_2PI)
+        if rsample and eps is not None:
+            # rsample() = loc + 1e-4*eps (learning.py:392): log_prob of that sample carries -eps^2/2 per dimension
+            # (no gradient: it does not depend on the parameters; the logged actor loss does)
+            res["logp"] = const - 0.5 * (eps * eps).sum(1)
+        else:
+            res["logp"] = torch.full((B,), const, dtype=torch.float32, device=dev)
     return res
 
 
@@ -590,7 +599,8 @@ def _advantage(agent, replay_dict, ensemble_idx, n=4, want_priority=False):
     adv = torch.empty((B,), dtype=torch.float32, device=dev)
     mask = torch.empty((B,), dtype=torch.float32, device=dev)
     prio = torch.empty((B,), dtype=torch.float64, device=dev) if want_priority else None
-    L.advantage(q_pi.data_ptr(), n, q_data.data_ptr(), B, adv.data_ptr(), mask.data_ptr(),
+    method = 1 if getattr(agent.adv_estimator, "cont_method", "mean") == "max" else 0
+    L.advantage(q_pi.data_ptr(), n, q_data.data_ptr(), B, method, adv.data_ptr(), mask.data_ptr(),
                 None if prio is None else prio.data_ptr(), s)
     return adv, mask, prio
 

@@ -382,6 +382,36 @@ def run_aug_case():
     print(f"wrote {path}  ({os.path.getsize(path)/1024:.1f} KiB)")
 
 
+def run_rad_case():
+    """RadAug (augmentations.py:129-162): cv2 bilinear upscale by ``crop`` pixels + random integer crop, through
+    sample_move_and_augment on uint8 frames.  Two layouts: a 9-channel frame stack (cv2's generic-channel path) and a
+    3-channel image (cv2's <=4-channel path, which rounds differently)."""
+    rng = np.random.default_rng(33)
+    out = {}
+    for tag, (B, C, HW, nbuf, crop, mix) in {"stack9": (4, 9, 36, 6, 16, 1.0), "rgb3": (4, 3, 20, 6, 5, 0.5)}.items():
+        A = 2
+        s = rng.integers(0, 256, (nbuf, C, HW, HW), dtype=np.uint8)
+        s1 = rng.integers(0, 256, (nbuf, C, HW, HW), dtype=np.uint8)
+        a = rng.uniform(-1, 1, (nbuf, A)).astype(np.float32)
+        r = rng.standard_normal(nbuf).astype(np.float32)
+        d = (rng.uniform(size=nbuf) < 0.1)
+        buf = rreplay.ReplayBuffer(size=nbuf)
+        buf.load_experience({"pixels": s}, a, r, {"pixels": s1}, d)
+        idx = rng.integers(0, nbuf, B)
+        h, w = rng.integers(0, crop, B), rng.integers(0, crop, B)
+        with rh.injected(randint=[h, w]):
+            augobj = raug.RadAug(B, crop=crop)   # constructor draws once
+        aug = raug.AugmentationSequence([augobj])
+        with rh.injected(randint=[idx, h, w]):
+            rd = lu.sample_move_and_augment(buf, B, aug, aug_mix=mix, per=False)
+        o, _, _, o1, _ = rd["primary_batch"]
+        put(out, tag, dict(s=s, s1=s1, a=a, r=r, d=d, idx=idx, h=h, w=w, crop=np.int64(crop), mix=np.float64(mix),
+                           o=o["pixels"].numpy(), o1=o1["pixels"].numpy()))
+    path = os.path.join(HERE, "aug_rad.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}  ({os.path.getsize(path)/1024:.1f} KiB)")
+
+
 def run_afbc_case():
     """Offline AFBC actor update with prioritised sampling and priority refresh (learning.py:144-219,
     learning_utils.py:241-295, adv_estimator.py:58-79, replay.py:163-190) -- BASELINE config 5's actor side."""
@@ -442,8 +472,10 @@ def run_afbc_case():
 
 
 if __name__ == "__main__":
+    only = set(sys.argv[1:])   # e.g. ``python make_golden.py rad`` regenerates one fixture
     for name, cfg in UPDATE_CASES.items():
-        run_update_case(name, cfg)
-    run_replay_case()
-    run_aug_case()
-    run_afbc_case()
+        if not only or name in only:
+            run_update_case(name, cfg)
+    for name, fn in (("replay", run_replay_case), ("aug", run_aug_case), ("rad", run_rad_case), ("afbc", run_afbc_case)):
+        if not only or name in only:
+            fn()

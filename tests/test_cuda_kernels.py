@@ -262,6 +262,62 @@ def test_pixel_gather_aug_matches_golden_reference():
     assert np.array_equal(_aug_call(s, idx, None, B, C, H, W, 4, 0, 0), g["oo"])
 
 
+def test_rad_crop_matches_golden_reference():
+    """RadAug (augmentations.py:129-162) fused into the gather (pad_mode 3) against the reference's own output
+    (tests/golden/aug_rad.npz): bit-exact on the 9-channel frame stack; on the 3-channel image cv2's small-channel
+    path rounds differently, so there the kernel is bit-exact with the oracle and within 1e-3 (0..255 scale) of cv2."""
+    fx = gu.load("aug_rad")
+    for tag in ("stack9", "rgb3"):
+        g = gu.sub(fx, tag)
+        idx, crop, mixv = g["idx"], int(g["crop"]), float(g["mix"])
+        B = len(idx)
+        _, C, H, W = g["s"].shape
+        sh = dev(np.stack([g["w"], g["h"]], 1), torch.int32)
+        for key, src in (("o", g["s"]), ("o1", g["s1"])):
+            got = _aug_call(dev(src), dev(idx), sh, B, C, H, W, crop, 3, int(B * mixv))
+            want = ao.mix(src[idx].astype(np.float32), ao.rad_crop(src[idx], g["h"], g["w"], crop), mixv)
+            assert np.array_equal(got, want), f"{tag}/{key}: kernel vs oracle"
+            if C > 4:
+                assert np.array_equal(got, g[key]), f"{tag}/{key}: kernel vs reference (cv2 generic-channel path)"
+            else:
+                assert np.abs(got - g[key]).max() <= 1e-3
+
+
+def test_rad_crop_full_size_and_drop_in():
+    """BASELINE config 4 shape (B=512, 9x84x84) through sample_move_and_augment with RadAug(512, crop=16): sampled rows
+    against the oracle, un-augmented rows are a pure cast, and the window of a constant image is that constant."""
+    import super_sac_b200 as ssb
+    from super_sac_b200 import _rng, augmentations, learning_utils as lu
+
+    rng = np.random.default_rng(8)
+    cap, B, C, H, W, crop = 1024, 512, 9, 84, 84, 16
+    s = rng.integers(0, 256, (cap, C, H, W), dtype=np.uint8)
+    s[7] = 131                                     # a constant frame: bilinear interpolation must return it unchanged
+    buf = ssb.replay.ReplayBuffer(cap, device=DEV)
+    buf.load_experience({"pixels": s}, np.zeros((cap, 2), np.float32), np.zeros(cap, np.float32), {"pixels": s[::-1].copy()},
+                        np.zeros(cap, bool))
+    idx = rng.integers(0, cap, B)
+    idx[3] = 7
+    shift = rng.integers(0, crop, (B, 2))
+    src = _rng.ScriptedSource()
+    old = _rng.set_source(src)
+    try:
+        src.push("indices", idx).push("shifts", shift.astype(np.int32))
+        rd = lu.sample_move_and_augment(buf, B, augmentations.AugmentationSequence([augmentations.RadAug(B, crop=crop)]), 0.75, per=False)
+        assert src.empty()
+    finally:
+        _rng.set_source(old)
+    o = rd["primary_batch"][0]["pixels"].cpu().numpy()
+    o1 = rd["primary_batch"][3]["pixels"].cpu().numpy()
+    k = int(B * 0.75)
+    rows = np.array([0, 1, 3, 200, k - 1])
+    assert np.array_equal(o[rows], ao.rad_crop(s[idx[rows]], shift[rows, 1], shift[rows, 0], crop))
+    assert np.array_equal(o1[rows], ao.rad_crop(s[::-1][idx[rows]], shift[rows, 1], shift[rows, 0], crop))
+    assert np.array_equal(o[k:], s[idx[k:]].astype(np.float32))
+    assert np.all(o[3] == 131.0)
+    assert o.min() >= 0.0 and o.max() <= 255.0
+
+
 @pytest.mark.parametrize("mode", [1, 2])
 def test_pixel_gather_aug_full_size(mode):
     """BASELINE config 4 shape: B=512 of 9x84x84 uint8 frames.  Oracle on a sample of rows + exact properties."""
@@ -643,3 +699,33 @@ def test_rng_fill_statistics_and_replay_advance():
     j = torch.empty(1 << 16, dtype=torch.int64, device=DEV)
     src2.fill(DEV, idx=j, n_filled=1000)
     assert torch.equal(j, i1)  # same seed, same first draw
+
+
+@pytest.mark.parametrize("method", ["mean", "max"])
+def test_advantage_estimator_mean_and_max(method):
+    """agent.adv_estimator(o, a, i) (adv_estimator.py:58-79): A = Q(s,a) - V(s) with V the mean or the max over n = 4
+    policy samples, min over the critics, PopArt affine -- against the oracle on the same N(0,1) draws."""
+    import twin_util as tw
+    from super_sac_b200 import _rng
+
+    E, N, S_, A, H, B = 2, 2, 17, 6, 256, 200
+    agent, _, o_agent, _ = tw.make_twins(E, N, S_, A, H, popart=True, seed=9)
+    agent.adv_estimator.cont_method = method
+    for i, p in enumerate(agent.popart):
+        p.w, p.b = 1.5 + i, -0.25
+        o_agent.popart[i].w, o_agent.popart[i].b = torch.tensor([1.5 + i]), torch.tensor([-0.25])
+    rng = np.random.default_rng(9)
+    s = rng.standard_normal((B, S_)).astype(np.float32)
+    a = rng.uniform(-1, 1, (B, A)).astype(np.float32)
+    eps = [rng.standard_normal((B, A)).astype(np.float32) for _ in range(4)]
+    src = _rng.ScriptedSource()
+    old = _rng.set_source(src)
+    try:
+        for e in eps:
+            src.push("normal", e)
+        got = agent.adv_estimator({"obs": dev(s)}, dev(a), 1)
+        assert src.empty()
+    finally:
+        _rng.set_source(old)
+    want = uo.advantage(o_agent, 1, {"obs": torch.as_tensor(s)}, torch.as_tensor(a), [torch.as_tensor(e) for e in eps], method=method)
+    gu.assert_close(got.cpu().numpy(), want.numpy(), 1e-4, 2e-5, f"advantage ({method})")

@@ -149,6 +149,23 @@ def test_aug_oracle_matches_reference():
     assert np.abs(aug1 - g["ao1"]).max() <= 4e-3
 
 
+def test_rad_oracle_matches_reference():
+    """RadAug (cv2 bilinear upscale + integer crop, augmentations.py:129-162) through sample_move_and_augment:
+    bit-exact on the 9-channel frame stack, <= 1e-3 (0..255 scale) on the 3-channel image (cv2's <=4-channel path)."""
+    fx = gu.load("aug_rad")
+    for tag in ("stack9", "rgb3"):
+        g = gu.sub(fx, tag)
+        idx, crop, mixv = g["idx"], int(g["crop"]), float(g["mix"])
+        for key, src in (("o", g["s"]), ("o1", g["s1"])):
+            got = ao.mix(src[idx].astype(np.float32), ao.rad_crop(src[idx], g["h"], g["w"], crop), mixv)
+            if src.shape[1] > 4:
+                assert np.array_equal(got, g[key]), f"{tag}/{key}"
+            else:
+                assert np.abs(got - g[key]).max() <= 1e-3, f"{tag}/{key}"
+            k = int(len(idx) * mixv)
+            assert np.array_equal(got[k:], g[key][k:])   # un-augmented rows: a pure uint8 -> float cast
+
+
 def _afbc_setup(fx):
     cfg = gu.cfg_of(fx)
     E, N, S, A, H = cfg["E"], cfg["N"], cfg["S"], cfg["A"], cfg["H"]
