@@ -45,6 +45,18 @@ def make_twins(E, N, S, A, H, det=False, popart=False, seed=0, encoder=None, dev
     return agent, target, o_agent, o_target
 
 
+def resync(agent, target, o_agent, o_target):
+    """Copy the oracle's parameters over the GPU twins' (after a step has been compared).  Per-step parity is judged
+    from identical starting points: the handful of entries that Adam moved by a different +-lr on the two sides (noise
+    gradients) would otherwise perturb the next step's gradients at the 1e-3 level.  The free-running case is the
+    100-step drift test."""
+    for ag, oa in ((agent, o_agent), (target, o_target)):
+        cu.load_stack(ag._actor_arena, oa.actors.named())
+        cu.load_stack(ag._critic_arena, oa.critics.named())
+        if oa.encoder is not None:
+            ag.encoder.load_state_dict({k: v.to(ag._critic_arena.device) for k, v in oa.encoder.state_dict().items()})
+
+
 def synthetic_state_buffer(n, S, A, seed=0):
     rng = np.random.default_rng(seed)
     return dict(s=rng.standard_normal((n, S), dtype=np.float32), a=rng.uniform(-1, 1, (n, A)).astype(np.float32),
@@ -64,22 +76,62 @@ def oracle_optimizers(o_agent, lr_c=3e-4, lr_a=3e-4, lr_alpha=1e-4, init_alpha=0
             [uo.Adam([la], lr=lr_alpha, betas=(0.5, 0.999)) for la in log_alphas])
 
 
-def cmp_stacks(arena, ostack, what, rtol=1e-4, atol_rel=1e-5, atol=0.0, grad=False, flip_lr=None):
+def rows_ambiguous(stack, g, x, tau=2e-6):
+    """Rows of ``x`` for which some hidden pre-activation of net ``g`` lies within fp32 rounding of zero:
+    |z| < tau * (sum of the magnitudes of its summands)  (fp32 / 3xTF32 dot products land within ~2e-7 of that scale).
+
+    Two correct fp32 forwards (different summation order) may put such a pre-activation on either side of the ReLU.  The
+    forward value moves by ~1e-6, but in the backward a whole term appears or vanishes, and because gradients are
+    random-sign sums that one term is worth ~1/sqrt(B*H) of EVERY first-layer gradient entry -- far above rtol 1e-4.
+    A gradient comparison at BASELINE sizes (millions of pre-activations per update) is therefore only well posed on
+    batches without such rows; the parity tests draw twice the rows they need and keep the unambiguous ones."""
+    with torch.no_grad():
+        W1, b1, W2, b2 = stack.W1[g], stack.b1[g], stack.W2[g], stack.b2[g]
+        z1 = x @ W1.t() + b1
+        s1 = x.abs() @ W1.abs().t() + b1.abs()
+        h1 = torch.relu(z1)
+        z2 = h1 @ W2.t() + b2
+        s2 = h1 @ W2.abs().t() + b2.abs()
+        return (z1.abs() < tau * s1).any(1) | (z2.abs() < tau * s2).any(1)
+
+
+def keep_rows(bad, B):
+    """Positions of the first B candidate rows that are not flagged."""
+    good = np.flatnonzero(~np.asarray(bad))
+    assert len(good) >= B, f"only {len(good)} unambiguous rows among {len(bad)} candidates"
+    return good[:B]
+
+
+def cmp_stacks(arena, ostack, what, rtol=1e-4, atol_rel=1e-5, atol=0.0, grad=False, noise_lr=None):
     """Every array of an MLP arena against the oracle stack.  atol = ``atol`` + ``atol_rel`` * max|want| per array.
-    ``flip_lr`` (post-Adam parameters only): Adam turns a gradient entry that is fp32 rounding noise around zero into a
-    step of +-lr, so at most 1e-4 of the entries of an array may miss the tolerance, and then by no more than 2.1*lr."""
+    ``noise_lr`` (post-Adam parameters only): Adam turns a gradient entry that is fp32 rounding noise around zero into a
+    step of up to +-lr, so at most 2e-4 of the entries of an array may miss the tolerance, and then by <= 2.1*noise_lr."""
     src = arena.g if grad else arena.p
     for n in uo.PARAM_NAMES:
         want = getattr(ostack, n).numpy().astype(np.float64)
         got = src[n].detach().cpu().numpy().astype(np.float64)
-        tol = atol + atol_rel * float(np.abs(want).max()) + rtol * np.abs(want)
-        err = np.abs(got - want)
-        bad = err > tol
-        if flip_lr is not None and bad.any():
-            assert bad.mean() <= 1e-4 and float(err[bad].max()) <= 2.1 * flip_lr + float(tol.max()), \
-                f"{what}.{n}: {int(bad.sum())} of {bad.size} entries off, worst {float(err[bad].max()):.3e}"
+        base = atol + atol_rel * float(np.abs(want).max())
+        if noise_lr is not None:
+            err = np.abs(got - want)
+            bad = err > base + rtol * np.abs(want)
+            if bad.any():
+                assert bad.mean() <= 2e-4 and float(err[bad].max()) <= 2.1 * noise_lr + base + rtol * float(np.abs(want).max()), \
+                    f"{what}.{n}: {int(bad.sum())} of {bad.size} entries off, worst {float(err[bad].max()):.3e}"
             continue
-        gu.assert_close(got, want, rtol, atol + atol_rel * float(np.abs(want).max()), f"{what}.{n}")
+        gu.assert_close(got, want, rtol, base, f"{what}.{n}")
+
+
+def frac_within(arena, ostack, rtol, atol):
+    """(fraction of parameter entries within rtol/atol of the oracle, largest absolute error) over a whole arena."""
+    ok = tot = 0
+    worst = 0.0
+    for n in uo.PARAM_NAMES:
+        want = getattr(ostack, n).numpy().astype(np.float64)
+        err = np.abs(arena.p[n].detach().cpu().numpy().astype(np.float64) - want)
+        ok += int((err <= atol + rtol * np.abs(want)).sum())
+        tot += err.size
+        worst = max(worst, float(err.max()))
+    return ok / tot, worst
 
 
 def max_err(arena, ostack, grad=False):
