@@ -1,218 +1,143 @@
 #!/usr/bin/env python
-"""bench.py -- SAC gradient updates/sec of the REDQ-10 update step (BASELINE.json configs[1]).
+"""bench.py -- SAC gradient updates/sec of the off-policy update step (BASELINE.json; headline: configs[1], REDQ-10).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config redq|sac|...]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config redq|sac|sunrise|drqv2|afbc]
 
-One "step" = one update = one ``critic_update`` + the conditional Polyak target update of main.py:380-414
-(target_delay 2), on synthetic HalfCheetah-shaped transitions (obs 17, act 6, batch 256, N=10 critics, subset M=2,
-2x256 MLPs).  Prints ONE JSON line (see the contract in the task statement):
+One "step" = one update = one ``critic_update`` + the conditional Polyak target update of main.py:380-414 (for the
+offline config also its ``offline_actor_update``), on synthetic batches of the config's shape.  ONE JSON line:
 
-  value     whole-job updates/s with everything resident in HBM: CUDA-graph replay of the update, no host reads
+  value     whole-job updates/s with everything resident in HBM: CUDA-graph replay of the update (eager launches for
+            the configs that cannot be captured yet), CUDA events, no host reads
   e2e       the same step through the drop-in Python API with HOST inputs: every step pushes one host transition
             into the device replay ring (H2D), calls learning.critic_update + learning_utils.soft_update, and reads
             the logged scalars back (D2H)
-  roofline  the dominant kernel group (ensemble-critic backward), CUDA-event timed inside this process
-  cpu_baseline  the CPU oracle port (oracle/update_oracle.py, per-net loops like the reference) on this box's cores
+  roofline  the dominant kernel of the config, CUDA-event timed inside this process against MEASURED_PEAKS.json
+  cpu_baseline  the reference's own CPU implementation on this box's cores (the UNMODIFIED reference from
+            baseline/_ref when it travelled, else the oracle port), best of a 1/8/16/all-thread sweep
+  secondary (default config only) the other BASELINE configs' step times, the HBM-bound kernels at C4/C5 sizes and the
+            unmodified reference on this GPU through stock PyTorch-CUDA (clearly labelled: a different arm)
 
---impl reference times that CPU oracle port alone (the reference itself is Python and cannot travel to the GPU box).
-Under torchrun (--gpus N > 1) every rank runs an independent learner replica (weak scaling, no data-path
-collective); rank 0 prints the aggregate.
+--impl reference times the reference's CPU implementation alone, on the same workload.  Under torchrun (--gpus N > 1)
+every rank runs an independent learner replica (weak scaling, no data-path collective); the ensemble-sharded single
+learner (critics / members partitioned over the ranks, exchange over NVLink) is checked for parity first
+("sharded_parity") and timed next to the replicas ("sharded_ensemble").
 """
 import argparse
 import json
 import os
-import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for p in (ROOT, os.path.join(ROOT, "tests")):
+for p in (ROOT, os.path.join(ROOT, "tools")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-import numpy as np  # noqa: E402
+import numpy as np  # noqa: E402,F401
 import torch  # noqa: E402
 
-CONFIGS = {
-    # BASELINE.json configs[1]: the configuration the metric is quoted on
-    "redq": dict(E=1, N=10, M=2, S=17, A=6, H=256, B=256, target_delay=2, tau=0.005, lr=3e-4, buffer=1_000_000, utd=20,
-                 workload="REDQ-10 critic_update+Polyak, obs17/act6, B=256, 2x256 MLP, M=2, target_delay=2"),
-    # BASELINE.json configs[0]
-    "sac": dict(E=1, N=2, M=2, S=3, A=1, H=256, B=256, target_delay=2, tau=0.005, lr=3e-4, buffer=100_000, utd=1,
-                workload="SAC (2 critics) critic_update+Polyak, obs3/act1, B=256, 2x256 MLP"),
-}
+import benchlib as bl  # noqa: E402
+from benchlib import CONFIGS  # noqa: E402
+
+METRIC = "sac_gradient_updates_per_sec"
 
 
-def synthetic_transitions(cfg, n, seed=0):
-    rng = np.random.default_rng(seed)
-    s = rng.standard_normal((n, cfg["S"]), dtype=np.float32)
-    a = rng.uniform(-1, 1, (n, cfg["A"])).astype(np.float32)
-    r = rng.standard_normal(n, dtype=np.float32)
-    s1 = rng.standard_normal((n, cfg["S"]), dtype=np.float32)
-    d = (rng.uniform(size=n) < 0.01)
-    return s, a, r, s1, d
+def base_line(args, cfg, world):
+    return {"metric": METRIC, "unit": "updates/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg["workload"], "name": args.config}}
 
 
-def measured_peaks():
-    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(path):
-        with open(path) as f:
-            d = json.load(f)
-        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"], source="MEASURED_PEAKS.json (measured)")
-    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, source="B200_PROFILING.md fallback")
-
-
-# ------------------------------------------------------------------------------------------------ clocks
-class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-
-    def __init__(self, gpu_index=0):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
-
-    def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except OSError:
-            self.proc = None
-            return
-        self.t = threading.Thread(target=self._read, daemon=True)
-        self.t.start()
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
-    def stop(self):
-        if self.proc is None:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) >= 9:
-                for nm, v in zip(names, r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
-        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=sorted(reasons), samples=len(sm))
-
-
-# ------------------------------------------------------------------------------------------------ CPU arm
-def build_oracle(cfg, seed=0):
-    from oracle import update_oracle as uo
-
-    gen = torch.Generator().manual_seed(seed)
-    agent = uo.OracleAgent(cfg["E"], cfg["N"], cfg["S"], cfg["A"], cfg["H"], log_std_low=-5.0, log_std_high=2.0)
-    agent.actors.random_init(gen)
-    agent.critics.random_init(gen)
-    target = agent.clone()
-    opt = uo.Adam(agent.critics.tensors(), lr=cfg["lr"])
-    return uo, agent, target, opt
-
-
-def oracle_step_fn(cfg, n_buf=100_000, seed=0):
-    """Returns step(k): one CPU critic update (+Polyak by the target_delay rule) of the oracle port, sampling its
-    batch from a host numpy buffer like the reference does (replay.py:121-126)."""
-    import math
-
-    uo, agent, target, opt = build_oracle(cfg, seed)
-    s, a, r, s1, d = synthetic_transitions(cfg, n_buf, seed)
-    rng = np.random.default_rng(seed + 1)
-    log_alphas = [torch.tensor([math.log(0.1)]) for _ in range(cfg["E"])]
-    hp = dict(gamma=0.99)
-    E, N, M, B, A = cfg["E"], cfg["N"], cfg["M"], cfg["B"], cfg["A"]
-
-    def step(k):
-        batches, rands = [], []
-        for _ in range(E):
-            idx = rng.integers(0, n_buf, B)
-            t = torch.from_numpy
-            batches.append(({"obs": t(s[idx])}, t(a[idx]), t(r[idx]).reshape(-1, 1), {"obs": t(s1[idx])},
-                            t(d[idx].astype(np.float32)).reshape(-1, 1)))
-            rands.append(dict(eps=torch.randn(B, A), subset=[int(x) for x in rng.permutation(N)[:M]]))
-        logs, _ = uo.critic_update(agent, target, batches, rands, hp, log_alphas, opt)
-        if k % cfg["target_delay"] == 0:
-            uo.soft_update(target.critics.tensors(), agent.critics.tensors(), cfg["tau"])
-        return logs
-
-    return step
-
-
-def time_cpu(cfg, steps, warmup):
-    torch.set_num_threads(os.cpu_count() or 1)
-    step = oracle_step_fn(cfg)
-    for k in range(warmup):
-        step(k)
-    t0 = time.perf_counter()
-    for k in range(steps):
-        step(k)
-    dt = time.perf_counter() - t0
-    return steps / dt, dt
-
-
+# ------------------------------------------------------------------------------------------------ reference arm
 def run_reference_arm(args, cfg, rank, world):
+    """The reference's own CPU implementation of the path on the box's host cores (rank 0 only)."""
     if rank != 0:
         return
-    ups, dt = time_cpu(cfg, args.steps, max(args.warmup, 3))
-    cores = torch.get_num_threads()
-    line = {
-        "impl": "reference", "metric": "sac_gradient_updates_per_sec", "value": ups, "unit": "updates/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": cfg["workload"], "arm": "CPU oracle port of the reference update (oracle/update_oracle.py), host numpy replay"},
-        "cpu_baseline": {"value": ups, "unit": "updates/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} updates after {max(args.warmup, 3)} warm-up, torch-CPU fp32, {cores} threads"},
+    warm = max(args.warmup, 3)
+    best, sweep = bl.cpu_thread_sweep(args.config, min(args.steps, 40), 2, budget_s=4.0)   # pick the thread count first
+    ups, dt, kind, threads, done = bl.time_cpu(args.config, args.steps, warm, threads=best["threads"], budget_s=150.0)
+    line = base_line(args, cfg, args.gpus)
+    line.update({
+        "impl": "reference", "value": ups, "ms_per_step": 1e3 * dt / done, "steps": done,
+        "arm": ("UNMODIFIED reference (baseline/_ref/super_sac, stub-imported) on the host CPU: learning.critic_update + soft_update, "
+                "host numpy replay" if kind == "reference" else "CPU oracle port of the reference update (oracle/update_oracle.py)"),
+        "cpu_baseline": {"value": ups, "unit": "updates/s", "cores": threads, "kind": kind, "host_cores": os.cpu_count(),
+                         "sample": f"{done} updates after {warm} warm-up, torch-CPU fp32, {threads} intra-op threads "
+                                   f"(best of the sweep {[(r['threads'], round(r['updates_per_s'], 1)) for r in sweep]})"},
         "e2e": {"value": ups, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }
+    })
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
-def build_gpu(cfg, device, seed=0):
-    import cuda_util as cu
-    import super_sac_b200 as ssb
-    from super_sac_b200 import nets
+def count_launches(fn, fused=False):
+    """Count kernel launches by wrapping the C-ABI entry points with their known launch multiplicities (fused: the
+    single-kernel forward applies, i.e. tcgen05 and a 2x256-class network)."""
+    from super_sac_b200 import _lib as L
 
-    ssb.manual_seed(seed)
-    torch.manual_seed(seed)
-    agent = ssb.Agent(act_space_size=cfg["A"], encoder=cu.IdentityEncoder(cfg["S"]),
-                      actor_network_cls=nets.mlps.ContinuousStochasticActor, critic_network_cls=nets.mlps.ContinuousCritic,
-                      ensemble_size=cfg["E"], num_critics=cfg["N"], hidden_size=cfg["H"], auto_rescale_targets=False,
-                      log_std_low=-5.0, log_std_high=2.0)
-    agent.to(device)
-    import copy
+    lib = L.lib()
+    per_call = {"mlp_forward": 1 if fused else 3, "actor_forward_sample": 1 if fused else 3, "scatter_fields": 1, "polyak": 1,
+                "polyak_multi": 1, "adam_step": 1, "adam_polyak_step": 1, "sumsq": 1, "rng_fill": 1, "gather_rows": 1,
+                "gather_aug_u8": 1, "tanh_normal_forward": 1, "tanh_normal_backward": 1, "tanh_normal_logprob": 1,
+                "det_head_forward": 1, "det_head_backward": 1, "td_target": 1, "critic_loss_seed": 1, "actor_loss_seed": 1,
+                "backup_weights": 1, "tree_set": 1, "tree_sample": 1, "dr3_dot": 1, "advantage": 1, "min_over_nets": 1,
+                "alpha_step": 1, "sum_groups": 1, "mlp_backward_dact": 2}
+    per_call = {k: v for k, v in per_call.items() if hasattr(lib, k)}
+    counter = {"n": 0}
+    saved = {}
 
-    target = copy.deepcopy(agent)
-    target.to(device)
-    c = dict(E=cfg["E"], critic_lr=cfg["lr"], actor_lr=cfg["lr"])
-    critic_opt, actor_opt, enc_opt, log_alphas, alpha_opts = cu.optimizers(agent, c)
-    agent.__dict__["_bench_actor_opts"] = (actor_opt, alpha_opts)   # for the full-SAC-step measurement
-    buf = ssb.replay.ReplayBuffer(cfg["buffer"], device=device)
-    s, a, r, s1, d = synthetic_transitions(cfg, cfg["buffer"], seed)
-    buf.load_experience({"obs": s}, a, r, {"obs": s1}, d)
-    return agent, target, critic_opt, enc_opt, log_alphas, buf
+    def wrap(name, f, mult):
+        def g(*a):
+            if name == "critic_forward_loss":
+                counter["n"] += ({0: 1, 1: 1, 2: 1} if fused else {0: 3, 1: 2, 2: 1})[a[24]]   # phase: all / hidden / output + loss
+            elif name == "mlp_backward":
+                want_dw = a[17] is not None   # dz2, gW3, gW2, dz1, gW1 (+dx): 5 launches with weight grads, 2 (+1) without
+                counter["n"] += (5 if want_dw else 2) + (1 if a[24] is not None else 0)
+            elif name in ("mlp_backward_pre", "mlp_backward_post"):
+                counter["n"] += 2
+            else:
+                counter["n"] += mult
+            return f(*a)
+        return g
+
+    for name, mult in list(per_call.items()) + [("critic_forward_loss", 0), ("mlp_backward", 0), ("mlp_backward_pre", 0), ("mlp_backward_post", 0)]:
+        saved[name] = getattr(lib, name)
+        setattr(lib, name, wrap(name, saved[name], mult))
+    try:
+        fn()
+    finally:
+        for name, f in saved.items():
+            setattr(lib, name, f)
+    return counter["n"]
 
 
-def critic_flops(cfg):
-    D, H, B, N, M, E = cfg["S"] + cfg["A"], cfg["H"], cfg["B"], cfg["N"], cfg["M"], cfg["E"]
-    fwd = 2 * B * (D * H + H * H + H)            # one critic net forward
-    bwd = 2 * B * (2 * H + 2 * H * H + D * H)    # dz2, gW3, gW2, dz1, gW1 (no dX: identity encoder)
-    actor = 2 * B * (cfg["S"] * H + H * H + 2 * cfg["A"] * H)
-    return dict(bwd_group=E * N * bwd, fwd_group=E * N * fwd, update=E * (actor + M * fwd + N * (fwd + bwd)))
+def graph_or_eager(fn):
+    from super_sac_b200 import graphed
+
+    try:
+        g = graphed.GraphedCall(fn)
+        return g.replay, "CUDA-graph replay", g
+    except Exception as e:  # noqa: BLE001  (configs with host-side decisions / autograd hand-off are not capturable yet)
+        torch.cuda.synchronize()
+        return fn, f"eager launches (not capturable: {type(e).__name__}: {str(e)[:80]})", None
+
+
+def time_config(W, steps, warmup):
+    """Device-resident ms/step of workload ``W``: graph replay where the update can be captured, else eager."""
+    delay = W.cfg["target_delay"]
+    with_pol, mode, g1 = graph_or_eager(lambda: W.step(0, with_polyak=True))
+    if delay > 1 and g1 is not None:
+        no_pol, _, _ = graph_or_eager(lambda: W.step(1, with_polyak=False))
+    else:
+        no_pol = (lambda: W.step(1, with_polyak=False)) if delay > 1 else with_pol
+    step = lambda k: (with_pol if k % delay == 0 else no_pol)()
+    ms = bl.timed_events(step, steps, warmup)
+    return ms, mode, g1
 
 
 def run_gpu_arm(args, cfg, rank, world, local_rank):
     import super_sac_b200 as ssb
-    from super_sac_b200 import _lib, _ops, augmentations, graphed, learning, learning_utils as lu
+    from super_sac_b200 import _lib, graphed, learning
 
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
@@ -222,195 +147,303 @@ def run_gpu_arm(args, cfg, rank, world, local_rank):
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=device)
+    sampler = bl.ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     ssb.set_mlp_impl(args.mlp_impl)
     ssb.set_overlap(not args.no_overlap)
     ssb.set_pdl(not args.no_pdl)
-    agent, target, critic_opt, enc_opt, log_alphas, buf = build_gpu(cfg, device, seed=rank)
-    B = cfg["B"]
-    augmenter = augmentations.AugmentationSequence([augmentations.IdentityAug(B)])
-    kw = dict(buffer=buf, agent=agent, target_agent=target, critic_optimizer=critic_opt, encoder_optimizer=enc_opt,
-              log_alphas=log_alphas, batch_size=B, gamma=0.99, critic_clip=None, encoder_clip=None,
-              target_critic_ensemble_n=cfg["M"], weighted_bellman_temp=None, weight_type=None, pop=False,
-              augmenter=augmenter, encoder_lambda=0.0, random_process=None, noise_clip=None, aug_mix=0.0)
 
-    launches = {"n": 0}
-    raw_cdll = _lib.lib().cdll
+    sharded_parity = None
+    if dist is not None:
+        sharded_parity = run_sharded_parity(rank, world, device, dist)
 
-    def polyak():
-        for ac, tc in zip(agent.critics, target.critics):
-            lu.soft_update(tc, ac, cfg["tau"])
-        lu.soft_update(target.encoder, agent.encoder, 0.01)
-
-    def update_only():
-        return learning.critic_update(**kw)
-
-    def update_and_polyak():
-        out = learning.critic_update(**kw)
-        polyak()
-        return out
+    W = bl.Workload(ssb, args.config, device, seed=rank, fill_on_device=True)
+    ring_mb = bl.buf_bytes(W.buffer) / 1e6
+    warm = max(args.warmup, 3)
 
     # ---- count our kernel launches per step (eager, via the C-ABI entry points) --------------------
     fused_fwd = cfg["H"] <= 256 and cfg["H"] % 16 == 0 and cfg["S"] + cfg["A"] <= 32 and args.mlp_impl == "tcgen05"
-    launch_count = count_launches(lambda: (update_and_polyak(), update_only()), _lib, fused_fwd) / 2.0
+    launch_count = count_launches(lambda: (W.step(0), W.step(1)), fused_fwd) / 2.0
 
-    # ---- device-resident timed region: graph replay ---------------------------------------------
-    g_upd = graphed.GraphedCall(update_only)
-    g_upd_pol = graphed.GraphedCall(update_and_polyak)
+    # ---- device-resident timed region ------------------------------------------------------------
+    delay = cfg["target_delay"]
+    with_pol, mode, g1 = graph_or_eager(lambda: W.step(0, with_polyak=True))
+    if delay > 1:
+        no_pol = graph_or_eager(lambda: W.step(1, with_polyak=False))[0] if g1 is not None else (lambda: W.step(1, with_polyak=False))
+    else:
+        no_pol = with_pol
 
     def gstep(k):
-        (g_upd_pol if k % cfg["target_delay"] == 0 else g_upd).replay()
+        (with_pol if k % delay == 0 else no_pol)()
 
-    for k in range(max(args.warmup, 3)):
+    for k in range(warm):
         gstep(k)
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
-    ev0.record()
-    for k in range(args.steps):
-        gstep(k)
-    ev1.record()
-    torch.cuda.synchronize()
+    with sampler.region():
+        ev0.record()
+        for k in range(args.steps):
+            gstep(k)
+        ev1.record()
+        torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
     ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
     if dist is not None:
         t = torch.tensor([ms], device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     value = world * args.steps / (ms * 1e-3)
-    glogs = g_upd.logs()
+    glogs = g1.logs() if g1 is not None else {}
 
     # ---- e2e through the drop-in API with host inputs ---------------------------------------------
     e2e_steps = min(args.steps, 2000)
-    hs, ha, hr, hs1, hd = synthetic_transitions(cfg, 4096, seed=123 + rank)
+    tr = W.host_transitions(256 if cfg.get("pixels") else 4096, seed=123 + rank)
+    n_tr = len(tr[1])
 
     def e2e_step(k):
-        j = k % 4096
-        buf.push({"obs": hs[j]}, ha[j], float(hr[j]), {"obs": hs1[j]}, bool(hd[j]))
-        logs, _ = learning.critic_update(**kw)
-        if k % cfg["target_delay"] == 0:
-            polyak()
+        W.push(tr, k % n_tr)
+        logs = W.step(k)[0]
+        if not isinstance(logs, dict) or not logs:
+            raise RuntimeError("e2e step returned no logs")
         return logs
 
     graphed.enable_auto_graphs(True)   # the drop-in calls below replay captured graphs from their third call on
-    eager_logs = learning._critic_update_impl(**kw)[0]
+    eager_logs = learning._critic_update_impl(**W.kw)[0]
     d2h = 4 * eager_logs._n
     for k in range(6):
-        logs = e2e_step(k)
-    # one pinned staging row per pushed transition: s, s1, a, r, d, tree index, priority, fill level (16-byte aligned)
-    h2d = buf._stage_bytes
+        e2e_step(k)
+    h2d = W.buffer._stage_bytes   # one pinned staging row per pushed transition (s, s1, a, r, d, tree index, priority, fill level)
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
-    t0 = time.perf_counter()
-    for k in range(e2e_steps):
-        e2e_step(k)
-    torch.cuda.synchronize()
-    e2e_dt = time.perf_counter() - t0
+    with sampler.region():
+        t0 = time.perf_counter()
+        for k in range(e2e_steps):
+            e2e_step(k)
+        torch.cuda.synchronize()
+        e2e_dt = time.perf_counter() - t0
     if dist is not None:
         t = torch.tensor([e2e_dt], device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_dt = float(t.item())
     e2e_value = world * e2e_steps / e2e_dt
+    graphed.enable_auto_graphs(False)
 
     sharded = None
-    if dist is not None and cfg["E"] == 1 and cfg["N"] >= world:
-        graphed.enable_auto_graphs(False)
-        sharded = time_sharded(cfg, args, device, rank, world, dist)
+    if dist is not None and cfg["E"] == 1 and cfg["N"] >= world and not cfg.get("pixels") and not cfg.get("offline"):
+        with sampler.region():
+            sharded = time_sharded(cfg, args, device, rank, world, dist)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
     # ---- the full SAC step, rank 0 --------------------------------------------------------
-    graphed.enable_auto_graphs(False)
-    try:
-        sac_step = time_full_sac_step(cfg, agent, target, kw, polyak, log_alphas)
-    except Exception as e:   # a secondary figure must not take the headline down with it
-        sac_step = {"unavailable": "%s: %s" % (type(e).__name__, e)}
+    sac_step = None
+    if not cfg.get("offline"):
+        try:
+            with sampler.region():
+                sac_step = time_full_sac_step(W)
+        except Exception as e:   # a secondary figure must not take the headline down with it
+            sac_step = {"unavailable": "%s: %s" % (type(e).__name__, e)}
 
     # ---- roofline of the dominant kernel (rank 0) -----------------------------------------------------
-    roof = time_dominant_kernel(cfg, agent, args)
-    peaks = measured_peaks()
-    fl = critic_flops(cfg)
-    achieved = fl["fwd_group"] / (roof["ms"] * 1e-3) / 1e12
-    fused = cfg["H"] <= 256 and cfg["H"] % 16 == 0 and cfg["S"] + cfg["A"] <= 32 and ssb.get_mlp_impl() == "tcgen05"
-    roofline = {"kernel": ("mlp3_forward_kernel<1> (fc1+fc2+fc3 of all %d critics in one launch, B=%d)" if fused else
-                           "ensemble critic forward (%d nets, B=%d; one launch per layer)") % (cfg["E"] * cfg["N"], cfg["B"]),
-                "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_tflops"],
-                "traffic": 3004416 if (fused and args.config == "redq") else None,
-                "us_per_launch": roof["ms"] * 1e3, "algorithmic_flops_per_launch": fl["fwd_group"],
-                "peak_source": peaks["source"],
-                "note": "fp32 parity needs 3xTF32 (three kind::tf32 MMAs per product at half the bf16 rate: the bf16 "
-                        "figure is 6x out of reach by construction); at 367 MFLOP per launch the kernel is bound by its "
-                        "serial chain (operand staging -> 8 k-chunks -> head), not by the tensor pipe "
-                        "(ncu: pipe_tc active 24%); traffic = dram bytes of one cold-cache ncu launch "
-                        "(profiles/r1_06_ncu_full_summary.json), operands are L2-resident inside the step"}
+    with sampler.region():
+        roofline = dominant_kernel_roofline(args, cfg, W)
 
-    cpu_steps = 300
-    cpu_ups, cpu_dt = time_cpu(cfg, cpu_steps, 10)
-    line = {
-        "metric": "sac_gradient_updates_per_sec", "value": value, "unit": "updates/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": cfg["workload"], "mode": "CUDA-graph replay of critic_update (+Polyak every 2nd step)",
-                   "parallelism": "1 learner" if world == 1 else f"{world} independent learner replicas (no data-path collective)",
-                   "l2": "replay ring %.0f MB > 126 MB L2 (random rows); parameters+moments (11.6 MB) are L2-resident by design"
-                         % (buf_bytes(buf) / 1e6),
-                   "impl": "ensemble MLP GEMMs: " + ssb.get_mlp_impl(),
-                   "overlap": "two-stream fork/join inside the update" if not args.no_overlap else "off",
-                   "pdl": "programmatic dependent launch along the critical path" if not args.no_pdl else "off"},
+    secondary = None
+    if args.config == "redq" and not args.skip_secondary:
+        del W
+        torch.cuda.empty_cache()
+        secondary = run_secondary(args, sampler)
+
+    best, sweep = bl.cpu_thread_sweep(args.config, 60 if not cfg.get("pixels") else 3, 3 if not cfg.get("pixels") else 1, budget_s=5.0)
+    clocks = sampler.stop()
+    line = base_line(args, cfg, world)
+    line.update({
+        "value": value, "ms_per_step": ms / args.steps,
+        "run": {"mode": mode + (" of critic_update (+Polyak every %d. step)" % delay if delay > 1 else " of the update"),
+                "parallelism": "1 learner" if world == 1 else f"{world} independent learner replicas (no data-path collective)",
+                "l2": "replay ring %.0f MB (random rows) vs 126 MB L2; parameters + moments are L2-resident by design" % ring_mb,
+                "impl": "ensemble MLP GEMMs: " + ssb.get_mlp_impl(),
+                "overlap": "two-stream fork/join inside the update" if not args.no_overlap else "off",
+                "pdl": "programmatic dependent launch along the critical path" if not args.no_pdl else "off"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "steps": e2e_steps, "path": "buffer.push(host transition, H2D) + learning.critic_update (auto CUDA graph) + "
-                                            "soft_update + logged scalars read back (D2H)"},
+                "steps": e2e_steps, "path": "buffer.push(host transition, H2D) + learning.critic_update (auto CUDA graph where "
+                                            "capturable) + soft_update + logged scalars read back (D2H)"},
         "gpu_launches": int(round(launch_count * args.steps)),
         "gpu_launches_per_step": launch_count,
         "roofline": roofline,
-        "cpu_baseline": {"value": cpu_ups, "unit": "updates/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"{cpu_steps} oracle updates (same workload) after 10 warm-up, torch-CPU fp32"},
-        "full_sac_step": sac_step, "flops_per_update": fl["update"],
-        "sharded_ensemble": sharded,
+        "cpu_baseline": {"value": best["updates_per_s"], "unit": "updates/s", "cores": best["threads"], "kind": best["kind"],
+                         "host_cores": os.cpu_count(),
+                         "sample": f"{best['steps']} updates of the same workload, torch-CPU fp32, best of the thread sweep "
+                                   f"{[(r['threads'], round(r['updates_per_s'], 1)) for r in sweep]}"},
+        "full_sac_step": sac_step, "flops_per_update": bl.critic_flops(cfg)["update"],
+        "sharded_parity": sharded_parity, "sharded_ensemble": sharded, "secondary": secondary,
         "sample_logs": {k: float(v) for k, v in list(glogs.items())[:4]},
-    }
+    })
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
 
+def run_secondary(args, sampler):
+    """The other BASELINE configs (device-resident ms/step, CPU reference on a bounded sample), the HBM-bound kernels at
+    C4 / C5 sizes, and the unmodified reference on this GPU through stock PyTorch-CUDA."""
+    import super_sac_b200 as ssb
+
+    out = {}
+    for name in ("sac", "sunrise", "afbc", "drqv2"):
+        try:
+            W = bl.Workload(ssb, name, torch.device("cuda", torch.cuda.current_device()), seed=0, fill_on_device=True)
+            steps = {"sac": 400, "sunrise": 200, "afbc": 60, "drqv2": 20}[name]
+            with sampler.region():
+                ms, mode, _ = time_config(W, steps, 5)
+            ent = {"workload": W.cfg["workload"], "ms_per_step": ms, "updates_per_s": 1e3 / ms, "mode": mode}
+            if name == "drqv2":
+                with sampler.region():
+                    ent["sample_move_and_augment"] = time_pixel_sampling(W)
+            del W
+            torch.cuda.empty_cache()
+            cpu_steps = {"sac": 40, "sunrise": 20, "afbc": 5, "drqv2": 2}[name]
+            ups, dt, kind, th, done = bl.time_cpu(name, cpu_steps, 1, threads=min(16, os.cpu_count() or 1), budget_s=8.0)
+            ent["cpu_baseline"] = {"value": ups, "unit": "updates/s", "cores": th, "kind": kind, "sample": f"{done} updates"}
+        except Exception as e:  # noqa: BLE001
+            ent = {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
+        out[name] = ent
+    try:
+        with sampler.region():
+            out["hbm_kernels"] = hbm_kernels()
+    except Exception as e:  # noqa: BLE001
+        out["hbm_kernels"] = {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
+    out["reference_on_this_gpu_pytorch_cuda"] = reference_on_gpu(args)
+    return out
+
+
+def reference_on_gpu(args):
+    """A DIFFERENT arm, for context only: the unmodified reference (baseline/_ref) running the REDQ-10 update on this B200
+    through stock PyTorch-CUDA -- what a user gets today on this GPU without this library."""
+    import subprocess
+
+    code = ("import sys,json,time,torch; sys.path.insert(0,%r); sys.path.insert(0,%r)\n"
+            "import benchlib as bl\n"
+            "from baseline import ref_import\n"
+            "ref=ref_import.import_reference(device='cuda')\n"
+            "W=bl.Workload(ref,'redq','cuda',seed=0,buffer_size=100000)\n"
+            "[W.step(k) for k in range(10)]\n"
+            "torch.cuda.synchronize(); t0=time.perf_counter()\n"
+            "[W.step(k) for k in range(100)]\n"
+            "torch.cuda.synchronize(); dt=time.perf_counter()-t0\n"
+            "print(json.dumps({'updates_per_s':100/dt,'ms_per_step':10*dt}))\n") % (os.path.join(ROOT, "tools"), ROOT)
+    try:
+        from baseline import ref_import
+
+        if not ref_import.available():
+            return {"unavailable": "baseline/_ref did not travel"}
+        res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+        if res.returncode != 0:
+            return {"unavailable": res.stderr[-300:]}
+        d = json.loads(res.stdout.strip().splitlines()[-1])
+        d["what"] = ("UNMODIFIED reference learning.critic_update + soft_update, REDQ-10 B=256, host numpy replay + H2D per batch, "
+                     "stock PyTorch-CUDA eager on this B200 (wall clock, 100 updates)")
+        return d
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
+
+
+def time_pixel_sampling(W):
+    from super_sac_b200 import learning_utils as lu
+
+    B = W.cfg["B"]
+    C, H, Wd = W.cfg["pixels"]
+    ms = bl.timed_events(lambda k: lu.sample_move_and_augment(W.buffer, B, W.augmenter, 1.0, per=False), 50, warmup=5)
+    nbytes = 2 * (B * C * H * Wd * 1 + B * C * H * Wd * 4)
+    peaks = bl.measured_peaks()
+    return {"ms": ms, "algorithmic_MB": nbytes / 1e6, "GBps": nbytes / ms / 1e6, "frac_of_hbm_peak": nbytes / ms / 1e6 / peaks["hbm_gbs"],
+            "note": "o and o1: u8 read + fp32 written; includes the index / shift draw and the small-array gather launches"}
+
+
+def hbm_kernels():
+    """Achieved GB/s of the HBM-bound kernels against the measured copy bandwidth (algorithmic bytes)."""
+    from super_sac_b200 import _lib
+
+    L, sp = _lib.lib(), _lib.stream_ptr()
+    peaks = bl.measured_peaks()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    rows = []
+    C, HW, B, cap = 9, 84, 512, 20_000
+    src = torch.empty((cap, C, HW, HW), dtype=torch.uint8, device=dev).random_(0, 256)
+    dst = torch.empty((B, C, HW, HW), device=dev)
+    idx = torch.randint(0, cap, (B,), device=dev)
+    shift = torch.randint(0, 9, (B, 2), device=dev, dtype=torch.int32)
+    ms = bl.timed_events(lambda k: L.gather_aug_u8(src.data_ptr(), dst.data_ptr(), idx.data_ptr(), shift.data_ptr(), None, B, C, HW, HW, 4, 1, B, sp), 100, 10)
+    rows.append(("ssac_gather_aug_u8 (C4: 512 x 9x84x84 u8 -> f32)", B * C * HW * HW * 5 + B * 8, ms, "ring and output larger than L2"))
+    del src, dst
+    for name, n, note in (("C5 2 150 402 params", 2_150_402, "L2-resident, as in the real step"), ("64 Mi params", 1 << 26, "larger than L2: HBM bound")):
+        p = torch.randn(n, device=dev); t = torch.randn(n, device=dev); g = torch.randn(n, device=dev)
+        m = torch.zeros(n, device=dev); v = torch.zeros(n, device=dev); ctl = torch.zeros(2, dtype=torch.int32, device=dev)
+        ms = bl.timed_events(lambda k: L.polyak(t.data_ptr(), p.data_ptr(), n, 0.005, sp), 50, 5)
+        rows.append((f"ssac_polyak ({name})", 12 * n, ms, note))
+        ms = bl.timed_events(lambda k: L.adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, ctl.data_ptr(), 3e-4, .9, .999, 1e-8, 0., None, 0., 0, sp), 50, 5)
+        rows.append((f"ssac_adam_step ({name})", 28 * n, ms, note))
+        del p, t, g, m, v
+    return [{"kernel": nm, "algorithmic_MB": nb / 1e6, "us": ms * 1e3, "GBps": nb / ms / 1e6, "frac_of_hbm_peak": nb / ms / 1e6 / peaks["hbm_gbs"],
+             "note": note} for nm, nb, ms, note in rows]
+
+
+def run_sharded_parity(rank, world, device, dist):
+    """Before any timing: the ensemble-sharded update (critics over the ranks, then SUNRISE members over the ranks) must
+    equal the single-GPU update on the same scripted draws (rtol 1e-4)."""
+    try:
+        import sharded_check
+
+        sharded_check.run_checks(rank, world, device)
+        ok = torch.ones(1, device=device)
+        msg = "ok"
+    except Exception as e:  # noqa: BLE001
+        ok = torch.zeros(1, device=device)
+        msg = "failed on rank %d: %s: %s" % (rank, type(e).__name__, str(e)[:300])
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    return "ok" if float(ok.item()) == 1.0 else (msg if msg != "ok" else "failed on another rank")
+
+
 def time_sharded(cfg, args, device, rank, world, dist):
-    """Secondary multi-GPU number: ONE learner whose N critics are sharded over the ranks, NCCL all-gather of
-    the target Q values inside every update.  Returns updates/s of that single learner (max over ranks)."""
+    """Multi-GPU single learner: ONE learner whose N critics are sharded over the ranks; the target-Q exchange
+    runs inside every update.  Returns updates/s of that single learner (max over ranks)."""
     import copy
 
-    import cuda_util as cu
     import super_sac_b200 as ssb
     from super_sac_b200 import augmentations, graphed, learning, learning_utils as lu, nets, parallel
 
+    IdentityEncoder, _ = bl._encoders(ssb)
     lo, hi = parallel.enable_critic_sharding(cfg["N"])
     try:
         ssb.manual_seed(1234)          # identical Philox stream on every rank: same indices / eps / subset
         torch.manual_seed(1234)        # identical actor replica
-        agent = ssb.Agent(act_space_size=cfg["A"], encoder=cu.IdentityEncoder(cfg["S"]),
+        agent = ssb.Agent(act_space_size=cfg["A"], encoder=IdentityEncoder(cfg["S"]),
                           actor_network_cls=nets.mlps.ContinuousStochasticActor, critic_network_cls=nets.mlps.ContinuousCritic,
                           ensemble_size=1, num_critics=hi - lo, hidden_size=cfg["H"], auto_rescale_targets=False,
                           log_std_low=-5.0, log_std_high=2.0)
         agent.to(device)
         target = copy.deepcopy(agent)
-        critic_opt, actor_opt, enc_opt, log_alphas, _ = cu.optimizers(agent, dict(E=1, critic_lr=cfg["lr"], actor_lr=cfg["lr"]))
+        from itertools import chain
+
+        critic_opt = torch.optim.Adam(chain(*(c.parameters() for c in agent.critics)), lr=cfg["lr"])
+        enc_opt = torch.optim.Adam(agent.encoder.parameters(), lr=1e-4)
+        la = torch.Tensor([-2.302585]).to(device)
+        la.requires_grad = True
         buf = ssb.replay.ReplayBuffer(200_000, device=device)
-        s, a, r, s1, d = synthetic_transitions(cfg, 200_000, 0)
+        s, a, r, s1, d = bl.synthetic_transitions(cfg, 200_000, 0)
         buf.load_experience({"obs": s}, a, r, {"obs": s1}, d)
         B = cfg["B"]
         kw = dict(buffer=buf, agent=agent, target_agent=target, critic_optimizer=critic_opt, encoder_optimizer=enc_opt,
-                  log_alphas=log_alphas, batch_size=B, gamma=0.99, critic_clip=None, encoder_clip=None,
+                  log_alphas=[la], batch_size=B, gamma=0.99, critic_clip=None, encoder_clip=None,
                   target_critic_ensemble_n=cfg["M"], weighted_bellman_temp=None, weight_type=None, pop=False,
                   augmenter=augmentations.AugmentationSequence([augmentations.IdentityAug(B)]), encoder_lambda=0.0,
                   random_process=None, noise_clip=None, aug_mix=0.0)
@@ -420,12 +453,12 @@ def time_sharded(cfg, args, device, rank, world, dist):
             lu.soft_update(target.critics[0], agent.critics[0], cfg["tau"])
             return out
 
-        mode = "cuda-graph replay (NCCL all-gather captured)"
+        mode = "cuda-graph replay (exchange captured)"
         try:
             g = graphed.GraphedCall(upd)
             step = g.replay
-        except Exception as e:  # noqa: BLE001  (capture of the collective is driver/NCCL dependent)
-            mode = "eager launches (graph capture of the collective unavailable: %s)" % type(e).__name__
+        except Exception as e:  # noqa: BLE001  (capture of the exchange is driver / NCCL dependent)
+            mode = "eager launches (graph capture of the exchange unavailable: %s)" % type(e).__name__
             step = upd
         steps = min(args.steps, 1000)
         for _ in range(10):
@@ -443,135 +476,70 @@ def time_sharded(cfg, args, device, rank, world, dist):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
         return {"value": steps / (ms * 1e-3), "unit": "updates/s of ONE learner", "ms_per_step": ms / steps, "mode": mode,
+                "exchange": parallel.exchange_name() if hasattr(parallel, "exchange_name") else "NCCL all-gather",
                 "critics_per_rank": [parallel.local_range(cfg["N"], world, r)[1] - parallel.local_range(cfg["N"], world, r)[0]
                                      for r in range(world)],
-                "collectives_per_update": "1 all-gather of Q_target [N,B] fp32 (%d B per rank)" % (4 * B * -(-cfg["N"] // world))}
+                "exchanged_per_update": "target Q [N,B] fp32 (%d B per rank)" % (4 * B * -(-cfg["N"] // world))}
     finally:
         parallel.disable()
 
 
-def buf_bytes(buf):
-    st = buf._storage
-    n = st.action_stack.numel() * 4 + st.reward_stack.numel() * 4 + st.done_stack.numel()
-    for d in (st.s_stack, st.s1_stack):
-        for v in d.values():
-            n += v.numel() * v.element_size()
-    return n
-
-
-def count_launches(fn, _lib, fused=False):
-    """Count kernel launches by wrapping the C-ABI entry points with their known launch multiplicities (fused: the
-    single-kernel forward applies, i.e. tcgen05 and a 2x256-class network)."""
-    from super_sac_b200 import _lib as L
-
-    lib = L.lib()
-    per_call = {"mlp_forward": 1 if fused else 3, "actor_forward_sample": 1 if fused else 3, "critic_forward_loss": 3, "scatter_fields": 1, "polyak": 1, "polyak_multi": 1, "adam_step": 1, "adam_polyak_step": 1, "sumsq": 1,
-                "rng_fill": 1, "gather_rows": 1, "gather_aug_u8": 1, "tanh_normal_forward": 1, "td_target": 1,
-                "critic_loss_seed": 1, "backup_weights": 1, "tree_set": 1, "tree_sample": 1}
-    counter = {"n": 0}
-    saved = {}
-
-    def wrap(name, f, mult):
-        def g(*a):
-            if name == "critic_forward_loss":
-                counter["n"] += ({0: 1, 1: 1, 2: 1} if fused else {0: 3, 1: 2, 2: 1})[a[24]]   # phase: all / hidden / output + loss
-            elif name == "mlp_backward":
-                # dz2, gW3, gW2, dz1, gW1 (+dx): 5 launches with weight grads, 2 (+1) without
-                want_dw = a[17] is not None
-                counter["n"] += (5 if want_dw else 2) + (1 if a[24] is not None else 0)
-            elif name == "mlp_backward_pre":
-                counter["n"] += 2    # v (unit dz2), u (GEMM)
-            elif name == "mlp_backward_post":
-                counter["n"] += 2    # gW2 GEMM, gW1 (+ gW3 in the same kernel)
-            else:
-                counter["n"] += mult
-            return f(*a)
-        return g
-
-    for name, mult in list(per_call.items()) + [("mlp_backward", 0), ("mlp_backward_pre", 0), ("mlp_backward_post", 0)]:
-        saved[name] = getattr(lib, name)
-        setattr(lib, name, wrap(name, saved[name], mult))
-    try:
-        fn()
-    finally:
-        for name, f in saved.items():
-            setattr(lib, name, f)
-    return counter["n"]
-
-
-def time_full_sac_step(cfg, agent, target, kw, polyak, log_alphas, iters=30):
+def time_full_sac_step(W, iters=30):
     """the full SAC step of main.py:380-543 -- UTD critic updates (+ their Polyak steps), then ONE actor
-    update and ONE temperature update on the last batch -- captured as a single CUDA graph."""
-    from super_sac_b200 import graphed, learning
+    update and ONE temperature update on the last batch -- captured as a single CUDA graph where possible."""
+    from super_sac_b200 import learning
 
-    actor_opt, alpha_opts = agent.__dict__["_bench_actor_opts"]
-    utd, B = cfg.get("utd", 1), cfg["B"]
+    cfg = W.cfg
+    utd = cfg.get("utd", 1)
 
     def full_step():
         rds = None
         for u in range(utd):
-            _, rds = learning._critic_update_impl(**kw)
+            _, rds = learning._critic_update_impl(**W.kw)
             if u % cfg["target_delay"] == 0:
-                polyak()
-        learning._online_actor_update_impl(buffer=kw["buffer"], agent=agent, pop=False, actor_optimizer=actor_opt,
-                                           log_alphas=log_alphas, batch_size=B, clip=None, random_process=None,
-                                           noise_clip=None, augmenter=kw["augmenter"], aug_mix=0.0,
-                                           premade_replay_dicts=rds)
-        return learning.alpha_update(buffer=kw["buffer"], agent=agent, optimizers=alpha_opts, batch_size=B,
-                                     log_alphas=log_alphas, augmenter=kw["augmenter"], aug_mix=0.0,
-                                     target_entropy=-float(cfg["A"]), premade_replay_dicts=rds, discrete=False)
+                W.polyak()
+        return W.actor_and_alpha(rds)
 
-    g = graphed.GraphedCall(full_step)
-    for _ in range(3):
-        g.replay()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(iters):
-        g.replay()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / iters
+    step, mode, _ = graph_or_eager(full_step)
+    ms = bl.timed_events(lambda k: step(), iters, 3)
     return {"value": 1e3 / ms, "unit": "SAC steps/s", "ms_per_step": ms, "critic_updates_per_step": utd,
-            "gradient_updates_per_sec": (utd + 1) * 1e3 / ms,
-            "what": "%d x (critic_update + Polyak every %d) + online_actor_update + alpha_update, one CUDA graph" %
-                    (utd, cfg["target_delay"])}
+            "gradient_updates_per_sec": (utd + 1) * 1e3 / ms, "mode": mode,
+            "what": "%d x (critic_update + Polyak every %d) + online_actor_update + alpha_update" % (utd, cfg["target_delay"])}
 
 
-def time_dominant_kernel(cfg, agent, args):
-    """CUDA-event time of ONE launch of the kernel with the most arithmetic in an update: the single-kernel ensemble
-    forward (all E*N critics on one batch), replayed back to back from a CUDA graph so that no launch gap is counted.
-    Operands are L2-warm, as they are inside the real step."""
+def dominant_kernel_roofline(args, cfg, W):
+    """CUDA-event time of ONE launch of the config's dominant kernel, replayed back to back from a CUDA graph so that no
+    launch gap is counted, against the measured peak.  MLP configs: the ensemble-critic forward (all E*N critics on one
+    batch; operands L2-warm, as they are inside the real step).  Pixel config: the fused gather + shift + cast."""
+    import super_sac_b200 as ssb
     from super_sac_b200 import _ops
 
-    ca = agent._critic_arena
+    peaks = bl.measured_peaks()
+    if cfg.get("pixels"):
+        r = hbm_kernels()[0]
+        return {"kernel": r["kernel"], "bound": "hbm", "achieved": r["GBps"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": r["frac_of_hbm_peak"], "traffic": None, "us_per_launch": r["us"],
+                "algorithmic_bytes_per_launch": r["algorithmic_MB"] * 1e6, "peak_source": peaks["source"]}
+    ca = W.agent._critic_arena
     G, B, H, D = cfg["E"] * cfg["N"], cfg["B"], cfg["H"], cfg["S"] + cfg["A"]
     dev = ca.device
     X = torch.randn(B, D, device=dev)
     h1 = torch.empty(G, B, H, device=dev)
     h2 = torch.empty_like(h1)
     q = torch.empty(G, B, 1, device=dev)
-    per_graph, iters = 20, 10
-    side = torch.cuda.Stream()
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        for _ in range(3):
-            _ops.mlp_forward(ca, 0, G, X, B, h1, h2, q, keep_hidden=True)
-    torch.cuda.current_stream().wait_stream(side)
-    torch.cuda.synchronize()
-    g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g):
-        for _ in range(per_graph):
-            _ops.mlp_forward(ca, 0, G, X, B, h1, h2, q, keep_hidden=True)
-    g.replay()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(iters):
-        g.replay()
-    e1.record()
-    torch.cuda.synchronize()
-    return dict(ms=e0.elapsed_time(e1) / (iters * per_graph), launches=1)
+    ms = bl.graph_time(lambda: _ops.mlp_forward(ca, 0, G, X, B, h1, h2, q, keep_hidden=True), per=20, iters=10)
+    fl = bl.critic_flops(cfg)
+    achieved = fl["fwd_group"] / (ms * 1e-3) / 1e12
+    fused = cfg["H"] <= 256 and cfg["H"] % 16 == 0 and D <= 32 and ssb.get_mlp_impl() == "tcgen05"
+    return {"kernel": ("mlp3_forward_kernel (fc1+fc2+fc3 of all %d critics in ONE launch, B=%d)" if fused else
+                       "ensemble critic forward (%d nets, B=%d; grouped tcgen05 GEMM, one launch per layer)") % (G, B),
+            "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+            "frac": achieved / peaks["bf16_tflops"], "frac_of_3xTF32_ceiling": achieved / (peaks["bf16_tflops"] / 6),
+            "traffic": 3004416 if (fused and args.config == "redq") else None,
+            "us_per_launch": ms * 1e3, "algorithmic_flops_per_launch": fl["fwd_group"], "peak_source": peaks["source"],
+            "note": "fp32 parity needs 3xTF32 (three kind::tf32 MMAs per product at half the bf16 rate: the bf16 figure is 6x "
+                    "out of reach by construction); traffic = dram bytes of one cold-cache ncu launch (profiles/), operands are "
+                    "L2-resident inside the step"}
 
 
 def main():
@@ -584,6 +552,7 @@ def main():
     ap.add_argument("--mlp-impl", default="tcgen05", choices=["tcgen05", "ffma"])
     ap.add_argument("--no-overlap", action="store_true", help="serialise the independent branches of the update (A/B switch)")
     ap.add_argument("--no-pdl", action="store_true", help="plain stream-ordered launches instead of programmatic dependent launch")
+    ap.add_argument("--skip-secondary", action="store_true", help="headline config only (no other configs / kernels / GPU-reference arm)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))
@@ -594,7 +563,7 @@ def main():
         return
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl ours needs a CUDA device (super_sac_b200 has no CPU path); "
-                         "use --impl reference for the CPU oracle arm")
+                         "use --impl reference for the CPU arm")
     run_gpu_arm(args, cfg, rank, world, local_rank)
 
 

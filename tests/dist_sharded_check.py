@@ -1,206 +1,11 @@
 #!/usr/bin/env python
-"""torchrun script (one rank per GPU): the ensemble-sharded REDQ update must equal the single-GPU update.
-
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-        tests/dist_sharded_check.py
-
-Every rank (a) runs the full N-critic agent on its own GPU and (b) runs its shard of the same agent with the NCCL
-exchange of super_sac_b200.parallel, on the same scripted draws, and compares post-update critics (its shard), actors,
-log_alpha-independent TD targets and the logged loss at rtol 1e-4.
-"""
-import copy
+"""torchrun entry point of the sharded-vs-single-GPU parity check (the logic lives in tools/sharded_check.py, which
+bench.py --gpus N > 1 also runs before timing)."""
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
-import numpy as np
-import torch
-import torch.distributed as dist
-
-import cuda_util as cu
-import golden_util as gu
-import super_sac_b200 as ssb
-from super_sac_b200 import _rng, augmentations, learning, learning_utils as lu, nets, parallel
-
-
-def build(N, S, A, H, device, seed):
-    torch.manual_seed(seed)
-    agent = ssb.Agent(act_space_size=A, encoder=cu.IdentityEncoder(S), actor_network_cls=nets.mlps.ContinuousStochasticActor,
-                      critic_network_cls=nets.mlps.ContinuousCritic, ensemble_size=1, num_critics=N, hidden_size=H,
-                      auto_rescale_targets=False, log_std_low=-5.0, log_std_high=2.0)
-    agent.to(device)
-    return agent
-
-
-def run(agent, target, buf, draws, B, M, cfg):
-    critic_opt, actor_opt, enc_opt, log_alphas, _ = cu.optimizers(agent, cfg)
-    aug = augmentations.AugmentationSequence([augmentations.IdentityAug(B)])
-    out = {}
-    old = _rng.set_source(_rng.ScriptedSource())
-    try:
-        for step, dr in enumerate(draws):
-            src = _rng.ScriptedSource()
-            _rng.set_source(src)
-            src.push("indices", dr["idx"]).push("normal", dr["eps"]).push("subsets", dr["subset"])
-            logs, rds = learning.critic_update(
-                buffer=buf, agent=agent, target_agent=target, critic_optimizer=critic_opt, encoder_optimizer=enc_opt,
-                log_alphas=log_alphas, batch_size=B, gamma=0.99, critic_clip=None, encoder_clip=None,
-                target_critic_ensemble_n=M, weighted_bellman_temp=None, weight_type=None, pop=False, augmenter=aug,
-                encoder_lambda=0.0, random_process=None, noise_clip=None, aug_mix=0.0)
-            for ac, tc in zip(agent.critics, target.critics):
-                lu.soft_update(tc, ac, 0.005)
-            out[f"loss{step}"] = logs["losses/critic_overall_loss"]
-        src = _rng.ScriptedSource()
-        _rng.set_source(src)
-        src.push("normal", draws[-1]["eps2"])
-        alogs = learning.online_actor_update(
-            buffer=buf, agent=agent, pop=False, actor_optimizer=actor_opt, log_alphas=log_alphas, batch_size=B, clip=None,
-            random_process=None, noise_clip=None, augmenter=aug, aug_mix=0.0, premade_replay_dicts=rds)
-        out["actor_loss"] = alogs["losses/actor_pg_loss"]
-    finally:
-        _rng.set_source(old)
-    return out
-
-
-def build_ensemble(E, N, S, A, H, device, seed):
-    torch.manual_seed(seed)
-    agent = ssb.Agent(act_space_size=A, encoder=cu.IdentityEncoder(S), actor_network_cls=nets.mlps.ContinuousStochasticActor,
-                      critic_network_cls=nets.mlps.ContinuousCritic, ensemble_size=E, num_critics=N, hidden_size=H,
-                      auto_rescale_targets=False, log_std_low=-5.0, log_std_high=2.0)
-    agent.to(device)
-    return agent
-
-
-def run_sunrise(agent, target, buf, draws, members, B, N, cfg):
-    """draws[step][member] for the GLOBAL member ids in ``members`` (this agent's members, in order)."""
-    critic_opt, actor_opt, enc_opt, log_alphas, _ = cu.optimizers(agent, dict(cfg, E=len(members)))
-    aug = augmentations.AugmentationSequence([augmentations.IdentityAug(B)])
-    out = {}
-    old = _rng.set_source(_rng.ScriptedSource())
-    try:
-        for step, dr in enumerate(draws):
-            src = _rng.ScriptedSource()
-            _rng.set_source(src)
-            for m in members:
-                src.push("indices", dr[m]["idx"]).push("normal", dr[m]["eps"]).push("subsets", dr[m]["subset"])
-            logs, rds = learning.critic_update(
-                buffer=buf, agent=agent, target_agent=target, critic_optimizer=critic_opt, encoder_optimizer=enc_opt,
-                log_alphas=log_alphas, batch_size=B, gamma=0.99, critic_clip=None, encoder_clip=None,
-                target_critic_ensemble_n=N, weighted_bellman_temp=20.0, weight_type="sunrise", pop=False, augmenter=aug,
-                encoder_lambda=0.0, random_process=None, noise_clip=None, aug_mix=0.0)
-            for ac, tc in zip(agent.critics, target.critics):
-                lu.soft_update(tc, ac, 0.005)
-            out[f"loss{step}"] = logs["losses/critic_overall_loss"]
-        src = _rng.ScriptedSource()
-        _rng.set_source(src)
-        for m in members:
-            src.push("normal", draws[-1][m]["eps2"])
-        learning.online_actor_update(
-            buffer=buf, agent=agent, pop=False, actor_optimizer=actor_opt, log_alphas=log_alphas, batch_size=B, clip=None,
-            random_process=None, noise_clip=None, augmenter=aug, aug_mix=0.0, premade_replay_dicts=rds)
-    finally:
-        _rng.set_source(old)
-    return out
-
-
-def sunrise_check(rank, world, dev):
-    """SUNRISE members sharded over the ranks == the single-GPU ensemble, member by member."""
-    E, N, S, A, H, B, nbuf = 3, 2, 17, 6, 64, 256, 4096
-    cfg = dict(critic_lr=3e-4, actor_lr=3e-4)
-    rng = np.random.default_rng(1)   # identical on every rank
-    s = rng.standard_normal((nbuf, S), dtype=np.float32); a = rng.uniform(-1, 1, (nbuf, A)).astype(np.float32)
-    r = rng.standard_normal(nbuf, dtype=np.float32); s1 = rng.standard_normal((nbuf, S), dtype=np.float32)
-    d = rng.uniform(size=nbuf) < 0.01
-    draws = [[dict(idx=rng.integers(0, nbuf, B), eps=rng.standard_normal((B, A)).astype(np.float32),
-                   subset=rng.permutation(N)[:N].astype(np.int32), eps2=rng.standard_normal((B, A)).astype(np.float32))
-              for _ in range(E)] for _ in range(2)]
-
-    def buffer():
-        b = ssb.replay.ReplayBuffer(nbuf, device=dev)
-        b.load_experience({"obs": s}, a, r, {"obs": s1}, d)
-        return b
-
-    names = ("W1", "b1", "W2", "b2", "W3", "b3")
-    full = build_ensemble(E, N, S, A, H, dev, seed=11)
-    full_t = copy.deepcopy(full)
-    init_c = {n: full._critic_arena.p[n].clone() for n in names}
-    init_a = {n: full._actor_arena.p[n].clone() for n in names}
-    ref = run_sunrise(full, full_t, buffer(), draws, list(range(E)), B, N, cfg)
-
-    lo, hi = parallel.enable_member_sharding(E)
-    shard = build_ensemble(hi - lo, N, S, A, H, dev, seed=11)
-    for n in names:
-        shard._critic_arena.p[n].copy_(init_c[n][lo * N:hi * N])
-        shard._actor_arena.p[n].copy_(init_a[n][lo:hi])
-    shard_t = copy.deepcopy(shard)
-    got = run_sunrise(shard, shard_t, buffer(), draws, list(range(lo, hi)), B, N, cfg)
-    parallel.disable_member_sharding()
-    for n in names:
-        gu.assert_close(shard._critic_arena.p[n].cpu().numpy(), full._critic_arena.p[n][lo * N:hi * N].cpu().numpy(), 1e-4, 1.5e-5,
-                        f"sunrise critics {n}")
-        gu.assert_close(shard._actor_arena.p[n].cpu().numpy(), full._actor_arena.p[n][lo:hi].cpu().numpy(), 1e-4, 1.5e-5,
-                        f"sunrise actors {n}")
-    for k in ref:
-        gu.assert_close(got[k], ref[k], 2e-4, 1e-6, f"sunrise {k}")
-    print(f"[rank {rank}] sharded members [{lo},{hi}) == single-GPU SUNRISE update; losses {got}", flush=True)
-
-
-def main():
-    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    local = int(os.environ.get("LOCAL_RANK", rank))
-    dev = torch.device("cuda", local)
-    torch.cuda.set_device(dev)
-    dist.init_process_group("nccl", device_id=dev)
-    sunrise_check(rank, world, dev)
-    N, M, S, A, H, B, nbuf = 10, 2, 17, 6, 256, 256, 4096
-    cfg = dict(E=1, critic_lr=3e-4, actor_lr=3e-4)
-    rng = np.random.default_rng(0)   # identical on every rank
-    s = rng.standard_normal((nbuf, S), dtype=np.float32); a = rng.uniform(-1, 1, (nbuf, A)).astype(np.float32)
-    r = rng.standard_normal(nbuf, dtype=np.float32); s1 = rng.standard_normal((nbuf, S), dtype=np.float32)
-    d = rng.uniform(size=nbuf) < 0.01
-    draws = [dict(idx=rng.integers(0, nbuf, B), eps=rng.standard_normal((B, A)).astype(np.float32),
-                  subset=rng.permutation(N)[:M].astype(np.int32), eps2=rng.standard_normal((B, A)).astype(np.float32))
-             for _ in range(3)]
-
-    def buffer():
-        b = ssb.replay.ReplayBuffer(nbuf, device=dev)
-        b.load_experience({"obs": s}, a, r, {"obs": s1}, d)
-        return b
-
-    # (a) single-GPU reference on this rank
-    full = build(N, S, A, H, dev, seed=7)
-    full_t = copy.deepcopy(full)
-    init_c = {n: full._critic_arena.p[n].clone() for n in ("W1", "b1", "W2", "b2", "W3", "b3")}
-    init_a = full._actor_arena.flat.clone()
-    ref = run(full, full_t, buffer(), draws, B, M, cfg)
-
-    # (b) this rank's shard with the NCCL exchange
-    lo, hi = parallel.enable_critic_sharding(N)
-    shard = build(hi - lo, S, A, H, dev, seed=7)
-    for n in init_c:
-        shard._critic_arena.p[n].copy_(init_c[n][lo:hi])
-    shard._actor_arena.flat.copy_(init_a)
-    shard_t = copy.deepcopy(shard)
-    got = run(shard, shard_t, buffer(), draws, B, M, cfg)
-    parallel.disable()
-
-    for n in init_c:
-        gu.assert_close(shard._critic_arena.p[n].cpu().numpy(), full._critic_arena.p[n][lo:hi].cpu().numpy(), 1e-4, 1.5e-5, f"critics {n}")
-        gu.assert_close(shard_t._critic_arena.p[n].cpu().numpy(), full_t._critic_arena.p[n][lo:hi].cpu().numpy(), 1e-4, 1.5e-5, f"targets {n}")
-    gu.assert_close(shard._actor_arena.flat.cpu().numpy(), full._actor_arena.flat.cpu().numpy(), 1e-4, 1.5e-5, "actor")
-    for k in ref:
-        gu.assert_close(got[k], ref[k], 2e-4, 1e-6, k)
-    # replicated state must be bit-identical across ranks (same all-reduced gradient everywhere)
-    chk = shard._actor_arena.flat.double().sum().reshape(1)
-    lst = [torch.zeros_like(chk) for _ in range(world)]
-    dist.all_gather(lst, chk)
-    assert all(torch.equal(x, lst[0]) for x in lst), "actor replicas diverged"
-    print(f"[rank {rank}] sharded critics [{lo},{hi}) == single-GPU update; losses {got}", flush=True)
-    dist.barrier()
-    dist.destroy_process_group()
-
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+import sharded_check
 
 if __name__ == "__main__":
-    main()
+    sharded_check.main()
