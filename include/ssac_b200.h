@@ -126,7 +126,8 @@ int ssac_tree_sample(const double* sum_tree_dev, const double* min_tree_dev, int
  * int32, e.g. the REDQ subset) or net g when NULL.  Input x_dev: row-major [.,B,D] with row stride ldx and
  * group stride x_gs (0 = every group reads the same batch).  Outputs h1/h2 [G,B,H] (nullable: not saved),
  * y [G,B,O].  impl: 0 = library default (ssac_set_default_mlp_impl), 1 = fp32 FFMA tiles, 2 = tcgen05 tensor cores
- * with 3xTF32 operand splitting (fp32-accurate: hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM). */
+ * with 3xTF32 operand splitting (fp32-accurate: hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM), 3 = the row-local
+ * CUDA-core kernel below (forward-only: keep_hidden == 0, shared input x_gs == 0, ssac_rows_supported shapes). */
 int ssac_default_mlp_impl(void);
 int ssac_set_default_mlp_impl(int impl);
 /* impl 2 stages operands with TMA (cp.async.bulk.tensor) when their pitch allows; 0 forces the register-staged path
@@ -209,6 +210,31 @@ int ssac_critic_forward_loss(const float* W1, const float* b1, const float* W2, 
  * ssac_td_target -- which takes one dependent launch off the update's critical path.  y_out_dev (nullable) receives y;
  * td_logs_dev[0..2] += {sum_b (y - c), sum_b (y - c)^2, sum_b alpha logp} and td_logs_dev[3] = c = y[0], from which the
  * caller forms the logged mean / unbiased std / entropy bonus (learning_utils.py:351-353). */
+
+/* ---- row-local forwards on the CUDA cores (exact fp32): the single-net, latency-bound pieces ------------------------
+ * One launch of ceil(B/8) clusters x 4 CTAs; every cluster walks the whole chain for 8 batch rows (layer slices per CTA,
+ * activations exchanged over distributed shared memory).  H in 32..256 (multiple of 8), first-layer width <= 64, O <= 16;
+ * ssac_rows_supported(D, H, O) tells.  No activations are kept (forward-only uses).
+ *
+ * ssac_target_chain: the TD-target path of one member (learning_utils.py:314-338, agent.py:22-40): a1, logp = pi(s1)
+ * (policy head as in ssac_actor_forward_sample) written into the action columns x1[:, S:], then the M critics
+ * net_index[m] (NULL: 0..M-1) of the given stack on (s1, a1): qt [M,B].  Replaces ssac_actor_forward_sample +
+ * ssac_mlp_forward(net_index), two tensor-core launches whose 8- and 16-CTA grids are pure latency.
+ * ssac_policy_rows: one actor with its head (acting path agent.py:204-327, forward-only policy samples); out_dev
+ * (nullable) receives the raw output layer [B, 2A | A]. */
+int ssac_rows_supported(int D, int H, int O);
+/* 0: ssac_rows_supported answers 0 for every shape, i.e. callers keep the tensor-core launches (A/B switch).  Default 1. */
+int ssac_set_rows_enabled(int on);
+int ssac_target_chain(const float* aW1, const float* ab1, const float* aW2, const float* ab2, const float* aW3,
+                      const float* ab3, int S, int H, int A, int deterministic, const float* cW1, const float* cb1,
+                      const float* cW2, const float* cb2, const float* cW3, const float* cb3,
+                      const int32_t* net_index_dev, int M, float* x1_dev, int64_t ldx, int B, const float* eps_dev,
+                      const float* noise_dev, float sigma, float clip, float log_std_lo, float log_std_hi,
+                      float* logp_dev, float* qt_dev, void* stream);
+int ssac_policy_rows(const float* W1, const float* b1, const float* W2, const float* b2, const float* W3, const float* b3,
+                     int D, int H, int A, int deterministic, const float* x_dev, int64_t ldx, int B, float* out_dev,
+                     const float* eps_dev, const float* noise_dev, float sigma, float clip, float log_std_lo,
+                     float log_std_hi, float* a_dev, int64_t lda, float* logp_dev, float* tanh_out_dev, void* stream);
 
 /* ---- policy heads: nets/distributions.py:9-15,64-114; learning_utils.py:48-59 --------------------- */
 /* out [B,2A] = [mu | raw_log_std], eps [B,A] -> a [B,A] (row stride lda: may be a column block of cat(s,a)),

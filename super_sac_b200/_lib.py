@@ -52,7 +52,7 @@ def parse_header(path=HEADER_PATH):
     return protos
 
 
-_NOT_STATUS = {"ssac_version", "ssac_default_mlp_impl", "ssac_get_overlap", "ssac_get_fused_forward", "ssac_get_pdl"}  # int-returning entry points whose value is not a status code
+_NOT_STATUS = {"ssac_version", "ssac_default_mlp_impl", "ssac_get_overlap", "ssac_get_fused_forward", "ssac_get_pdl", "ssac_rows_supported"}  # int-returning entry points whose value is not a status code
 
 
 class SsacError(RuntimeError):

@@ -258,22 +258,69 @@ class Agent:
     def _encode(self, obs, rolling):
         return self.encoder.forward_rolling(obs) if rolling else self.encoder(obs)
 
+    def _policy_rows(self, s_rep, i, eps):
+        """Actor ``i`` on the encoded observations [envs, S] through the kernels: a = tanh(mu + eps * std) (stochastic;
+        eps = 0 gives the mean action tanh(mu)) or tanh(out) (deterministic).  One launch (ssac_policy_rows for the
+        2 x 256-class networks, the tensor-core forward otherwise)."""
+        from . import learning_utils as lu
+
+        S, A = self._actor_arena.D, self.act_space_size
+        B = s_rep.shape[0]
+        X = torch.empty((B, S + A), dtype=torch.float32, device=s_rep.device)
+        X[:, :S].copy_(s_rep)
+        lu._policy_sample(self, i, X, B, S, A, None, None, rsample=False, eps=eps, keep=False)
+        return X[:, S:]
+
+    def _kernel_path(self, s_rep):
+        return torch.is_tensor(s_rep) and s_rep.is_cuda and s_rep.dim() == 2 and s_rep.shape[1] == self._actor_arena.D
+
     def forward(self, state, from_cpu=True, num_envs=1, rolling=False):
+        """Greedy action: the mean over the ensemble of each actor's mean action (reference agent.py:204-226)."""
         if from_cpu:
             state = self._process_obs(state, num_envs)
         self.eval()
         with torch.no_grad():
             s_rep = self._encode(state, rolling)
-            act = torch.stack([actor(s_rep).mean for actor in self.actors], dim=0).mean(0)
+            if self._kernel_path(s_rep):
+                zero = None if self.deterministic else torch.zeros((s_rep.shape[0], self.act_space_size), dtype=torch.float32,
+                                                                   device=s_rep.device)
+                acts = [self._policy_rows(s_rep, i, zero) for i in range(self.ensemble_size)]
+                act = acts[0] if len(acts) == 1 else torch.stack(acts, dim=0).mean(0)
+            else:
+                act = torch.stack([actor(s_rep).mean for actor in self.actors], dim=0).mean(0)
         self.train()
         return self._process_act(act, num_envs) if from_cpu else act
 
     def sample_action(self, obs, from_cpu=True, num_envs=1, return_dist=False, rolling=False):
+        """Exploration action (reference agent.py:228-327): a sample of a randomly chosen actor, or -- with
+        ``ucb_bonus > 0`` -- SUNRISE's UCB choice among every actor's proposal, scored by every member's critics.  On the
+        device both run through the grouped kernels at B = num_envs (one launch per actor proposal, ONE launch for all
+        E x N critics on all E x envs candidates); ``return_dist`` needs the torch distribution object and keeps the
+        nn.Module path."""
         if from_cpu:
             obs = self._process_obs(obs, num_envs)
         with torch.no_grad():
             s_rep = self._encode(obs, rolling)
-            if self.ucb_bonus > 0:
+            kernels = self._kernel_path(s_rep) and not return_dist
+            act_dist = None
+            if kernels:
+                from . import learning_utils as lu
+
+                E, N, A = self.ensemble_size, self.num_critics, self.act_space_size
+                envs = s_rep.shape[0]
+                if self.ucb_bonus > 0:
+                    random.choice(range(E))   # the reference draws its (unused here) act_dist member: keep the RNG stream
+                    cands = torch.stack([self._policy_rows(s_rep, i, None) for i in range(E)], dim=0)       # [E, envs, A]
+                    X = torch.cat((s_rep.unsqueeze(0).expand(E, envs, s_rep.shape[1]), cands), dim=-1)      # [E, envs, S+A]
+                    X = X.reshape(E * envs, -1).contiguous()
+                    q = lu._critic_values(self, 0, E * N, X, E * envs)                                      # [E*N, E*envs, 1]
+                    q = q.view(E, N, E, envs).min(1).values                                                 # [E_c, E, envs]
+                    ucb = q.mean(0) + self.ucb_bonus * q.std(0)                                             # [E, envs]
+                    best = ucb.argmax(0)
+                    act = cands[best, torch.arange(envs, device=cands.device)]
+                else:
+                    act = self._policy_rows(s_rep, random.choice(range(E)), None)
+            elif self.ucb_bonus > 0:
                 # SUNRISE UCB exploration: every actor proposes, every critic scores, pick argmax(mean + c*std)
                 dists = [actor(s_rep) for actor in self.actors]
                 cands = torch.stack([d.sample() for d in dists], dim=0)          # [E, envs, A]

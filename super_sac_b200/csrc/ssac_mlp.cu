@@ -8,6 +8,9 @@ int mlp_forward_simt(const float* W1, const float* b1, const float* W2, const fl
                      const float* b3, const int32_t* net_index, int G, int D, int H, int O, const float* x, int64_t ldx,
                      int64_t x_gs, int B, float* h1, float* h2, float* y, cudaStream_t s, int impl, const HeadEpi* epi,
                      int phase, int keep_hidden);
+int mlp_forward_rows(const float* W1, const float* b1, const float* W2, const float* b2, const float* W3, const float* b3,
+                     const int32_t* net_index, int G, int D, int H, int O, const float* x, int64_t ldx, int B, float* y,
+                     cudaStream_t s);
 void set_fused_forward(int on);
 int get_fused_forward();
 int mlp_backward_pre(const float* W2, const float* W3, int G, int H, int B, const float* h1, const float* h2, float* ws,
@@ -54,6 +57,10 @@ int ssac_mlp_forward(const float* W1, const float* b1, const float* W2, const fl
   if (impl == 1 || impl == 2)
     return mlp_forward_simt(W1, b1, W2, b2, W3, b3, net_index_dev, G, D, H, O, x_dev, ldx, x_gs, B, h1_dev, h2_dev,
                             y_dev, (cudaStream_t)stream, impl, nullptr, 0, keep_hidden);
+  if (impl == 3) {
+    SSAC_REQUIRE(!keep_hidden && x_gs == 0, "ssac_mlp_forward: impl 3 is forward-only on a shared batch");
+    return mlp_forward_rows(W1, b1, W2, b2, W3, b3, net_index_dev, G, D, H, O, x_dev, ldx, B, y_dev, (cudaStream_t)stream);
+  }
   return fail(SSAC_E_UNSUPPORTED, "ssac_mlp_forward: unknown impl");
 }
 

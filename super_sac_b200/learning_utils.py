@@ -362,20 +362,34 @@ def _actor_forward(agent, i, X, B, S, A, keep=False):
     return out, h1, h2
 
 
-def _policy_sample(agent, i, X, B, S, A, random_process, noise_clip, rsample=False, eps=None, noise=None, keep=None):
+def _rows_ok(D, H, O):
+    """The row-local CUDA-core kernel (ssac_mlp_rows.cu) covers this shape and is switched on."""
+    return bool(_lib.lib().rows_supported(int(D), int(H), int(O)))
+
+
+def _policy_sample(agent, i, X, B, S, A, random_process, noise_clip, rsample=False, eps=None, noise=None, keep=None,
+                   chain=None):
     """a ~ pi_i(.|s) written into X[:, S:], with log-prob [B] (None when a noise process replaces the entropy term):
     actor MLP + policy head in one entry point (the head is fused into the output-layer kernel).  ``eps`` / ``noise``:
     pre-drawn N(0,1) tensors (drawn here otherwise).  Returns dict(out, h1, h2, eps, logp, tanh_out); h1 / h2 are only
-    valid when ``keep`` (default: rsample, i.e. a backward pass follows)."""
+    valid when ``keep`` (default: rsample, i.e. a backward pass follows).
+
+    ``chain = (critic_arena, g0, net_index, M)`` (forward-only): the M critics net_index[m] of that arena (relative to
+    net g0) are evaluated on (s, a) in the SAME launch (ssac_target_chain); their values come back as ``qt`` [M,B,1]."""
     dev = X.device
     keep = rsample if keep is None else keep
     arena = agent._actor_arena
-    h1 = torch.empty((1, B, arena.H), dtype=torch.float32, device=dev)
-    h2 = torch.empty_like(h1)
-    out = torch.empty((1, B, arena.O), dtype=torch.float32, device=dev)
-    a_dst = X[:, S:]
-    res = dict(out=out, h1=h1, h2=h2, eps=None, logp=None, tanh_out=None)
     det = agent.deterministic
+    use_rows = not keep and _lib.lib().default_mlp_impl() == 2 and _rows_ok(S + A, arena.H, arena.O) and A <= 8
+    if chain is not None and not (use_rows and chain[0].H == arena.H and chain[0].O == 1 and chain[0].D == S + A):
+        chain = None
+    h1 = h2 = out = None
+    if not use_rows:
+        h1 = torch.empty((1, B, arena.H), dtype=torch.float32, device=dev)
+        h2 = torch.empty_like(h1)
+        out = torch.empty((1, B, arena.O), dtype=torch.float32, device=dev)
+    a_dst = X[:, S:]
+    res = dict(out=out, h1=h1, h2=h2, eps=None, logp=None, tanh_out=None, qt=None)
     sigma, clip, tanh_out, logp = 0.0, 0.0, None, None
     if det:
         if rsample and eps is None:  # Normal(loc, 1e-4).rsample() of the reference's deterministic "distribution"
@@ -401,11 +415,25 @@ def _policy_sample(agent, i, X, B, S, A, random_process, noise_clip, rsample=Fal
         noise = None
         logp = torch.empty((B,), dtype=torch.float32, device=dev)
     W1, b1, W2, b2, W3, b3 = arena.ptrs(i)
-    _lib.lib().actor_forward_sample(W1, b1, W2, b2, W3, b3, arena.D, arena.H, A, int(det), X.data_ptr(), S + A, B,
-                                    h1.data_ptr(), h2.data_ptr(), int(bool(keep)), out.data_ptr(), _ops._p(eps),
-                                    _ops._p(noise), sigma, clip,
-                                    float(agent.log_std_low), float(agent.log_std_high), a_dst.data_ptr(), S + A,
-                                    _ops._p(logp), _ops._p(tanh_out), 0, _lib.stream_ptr())
+    L = _lib.lib()
+    if chain is not None:
+        c_arena, g0, net_index, M = chain
+        qt = torch.empty((M, B, 1), dtype=torch.float32, device=dev)
+        cW1, cb1, cW2, cb2, cW3, cb3 = c_arena.ptrs(g0)
+        L.target_chain(W1, b1, W2, b2, W3, b3, S, arena.H, A, int(det), cW1, cb1, cW2, cb2, cW3, cb3, _ops._p(net_index), M,
+                       X.data_ptr(), S + A, B, _ops._p(eps), _ops._p(noise), sigma, clip, float(agent.log_std_low),
+                       float(agent.log_std_high), _ops._p(logp), qt.data_ptr(), _lib.stream_ptr())
+        res["qt"] = qt
+    elif use_rows:
+        L.policy_rows(W1, b1, W2, b2, W3, b3, arena.D, arena.H, A, int(det), X.data_ptr(), S + A, B, None, _ops._p(eps),
+                      _ops._p(noise), sigma, clip, float(agent.log_std_low), float(agent.log_std_high), a_dst.data_ptr(),
+                      S + A, _ops._p(logp), _ops._p(tanh_out), _lib.stream_ptr())
+    else:
+        L.actor_forward_sample(W1, b1, W2, b2, W3, b3, arena.D, arena.H, A, int(det), X.data_ptr(), S + A, B,
+                               h1.data_ptr(), h2.data_ptr(), int(bool(keep)), out.data_ptr(), _ops._p(eps),
+                               _ops._p(noise), sigma, clip,
+                               float(agent.log_std_low), float(agent.log_std_high), a_dst.data_ptr(), S + A,
+                               _ops._p(logp), _ops._p(tanh_out), 0, _lib.stream_ptr())
     res.update(eps=eps, logp=logp, tanh_out=tanh_out)
     if det and random_process is None:
         # Normal(loc, 1e-4).log_prob(loc) summed over A: a constant (nets/distributions.py:107-114)
@@ -475,16 +503,27 @@ def compute_td_targets(logs, replay_dict, agent, target_agent, ensemble_idx, ens
     # REDQ subset: drawn over the GLOBAL ensemble when the critics are sharded over ranks (replicated Philox state)
     pool = parallel.n_global() if parallel.is_sharded() else N
     assert 0 < ensemble_n <= pool
+    # unsharded: actor + target-critic subset + action write-back are ONE row-local launch (ssac_target_chain)
+    want_chain = not parallel.is_sharded()
     if _draws is not None:   # critic_update drew indices, policy noise and the subset in ONE launch
+        net_index = _draws["subset"]
         pol = _policy_sample(agent, i, X1, B, S, A, random_process, noise_clip,
                              eps=None if agent.deterministic else _draws["normal"],
-                             noise=_draws["normal"] if agent.deterministic else None)
-        net_index = _draws["subset"]
+                             noise=_draws["normal"] if agent.deterministic else None,
+                             chain=(target_agent._critic_arena, i * N, net_index, ensemble_n) if want_chain else None)
     else:
-        pol = _policy_sample(agent, i, X1, B, S, A, random_process, noise_clip)
         net_index = torch.empty(ensemble_n, dtype=torch.int32, device=X1.device)
-        _rng.source().subsets(net_index, pool, ensemble_n)
-    if parallel.is_sharded():
+        # (the reference draws the policy sample first, the subset second: learning_utils.py:321, agent.py:29)
+        if want_chain and isinstance(_rng.source(), _rng.PhiloxSource):
+            _rng.source().subsets(net_index, pool, ensemble_n)   # independent Philox draws: the order is immaterial
+            pol = _policy_sample(agent, i, X1, B, S, A, random_process, noise_clip,
+                                 chain=(target_agent._critic_arena, i * N, net_index, ensemble_n))
+        else:
+            pol = _policy_sample(agent, i, X1, B, S, A, random_process, noise_clip)
+            _rng.source().subsets(net_index, pool, ensemble_n)
+    if pol.get("qt") is not None:
+        q_t = pol["qt"]
+    elif parallel.is_sharded():
         # every rank evaluates its own target critics and all-gathers the [N_global, B] values; the subset-min is then
         # identical on every rank
         q_all = parallel.all_gather_q(_critic_values(target_agent, i * N, N, X1, B))

@@ -729,3 +729,99 @@ def test_advantage_estimator_mean_and_max(method):
         _rng.set_source(old)
     want = uo.advantage(o_agent, 1, {"obs": torch.as_tensor(s)}, torch.as_tensor(a), [torch.as_tensor(e) for e in eps], method=method)
     gu.assert_close(got.cpu().numpy(), want.numpy(), 1e-4, 2e-5, f"advantage ({method})")
+
+
+# ------------------------------------------------------------------------------------------------ row-local CUDA-core chains
+def _rand_stack(G, D, H, O, seed):
+    return uo.MLPStack(G, D, H, O).random_init(torch.Generator().manual_seed(seed))
+
+
+@pytest.mark.parametrize("G,D,H,O,B", [(2, 23, 256, 1, 256), (3, 9, 48, 5, 37), (1, 56, 128, 16, 8), (10, 23, 256, 1, 5),
+                                        (1, 17, 256, 12, 256), (2, 64, 40, 3, 19)])
+def test_rows_forward_matches_oracle(G, D, H, O, B):
+    """ssac_mlp_forward impl 3 (ssac_mlp_rows.cu: clusters of 4 CTAs, 8 rows each, exact fp32 on the CUDA cores)."""
+    st = _rand_stack(G, D, H, O, seed=G * 1000 + H)
+    x = torch.randn(B, D + 3, generator=torch.Generator().manual_seed(B))   # wider rows than D: exercises ldx
+    y = torch.empty(G, B, O, device=DEV)
+    xd = x.to(DEV)
+    p = {n: getattr(st, n).to(DEV).contiguous() for n in uo.PARAM_NAMES}
+    L().mlp_forward(p["W1"].data_ptr(), p["b1"].data_ptr(), p["W2"].data_ptr(), p["b2"].data_ptr(), p["W3"].data_ptr(),
+                    p["b3"].data_ptr(), None, G, D, H, O, xd.data_ptr(), D + 3, 0, B, None, None, 0, y.data_ptr(), 3, S())
+    want = torch.stack([uo.mlp_forward(st, g, x[:, :D])[0] for g in range(G)], 0)
+    gu.assert_close(y.cpu().numpy(), want.numpy(), 1e-5, 2e-6, "rows forward")
+
+
+@pytest.mark.parametrize("det", [False, True])
+@pytest.mark.parametrize("B", [256, 13])
+def test_target_chain_matches_oracle(det, B):
+    """ssac_target_chain: a1, logp = pi(s1) (tanh-Normal sample / deterministic head + TD3 noise), written into the action
+    columns, then the REDQ subset of target critics on (s1, a1) -- one launch -- against the oracle's per-net loops."""
+    S_, A, H, N, M = 17, 6, 256, 10, 2
+    actor = _rand_stack(1, S_, H, A if det else 2 * A, seed=1)
+    critics = _rand_stack(N, S_ + A, H, 1, seed=2)
+    g = torch.Generator().manual_seed(B)
+    s1 = torch.randn(B, S_, generator=g)
+    eps, noise = torch.randn(B, A, generator=g), torch.randn(B, A, generator=g)
+    subset = [7, 2]
+    X1 = torch.zeros(B, S_ + A)
+    X1[:, :S_] = s1
+    xd = X1.to(DEV)
+    pa = {n: getattr(actor, n).to(DEV).contiguous() for n in uo.PARAM_NAMES}
+    pc = {n: getattr(critics, n).to(DEV).contiguous() for n in uo.PARAM_NAMES}
+    ni = dev(np.array(subset, dtype=np.int32))
+    logp = torch.empty(B, device=DEV)
+    qt = torch.empty(M, B, 1, device=DEV)
+    ed, nd = eps.to(DEV), noise.to(DEV)
+    L().target_chain(*(pa[n].data_ptr() for n in uo.PARAM_NAMES), S_, H, A, int(det), *(pc[n].data_ptr() for n in uo.PARAM_NAMES),
+                     ni.data_ptr(), M, xd.data_ptr(), S_ + A, B, None if det else ed.data_ptr(), nd.data_ptr() if det else None,
+                     0.6, 0.3, -5.0, 2.0, None if det else logp.data_ptr(), qt.data_ptr(), S())
+    out = uo.mlp_forward(actor, 0, s1)[0]
+    if det:
+        a1 = uo.gaussian_noise_clamp(torch.tanh(out), noise, 0.6, 0.3, -1.0, 1.0)
+    else:
+        a1, lp, _ = uo.tanh_normal_sample(out, eps, -5.0, 2.0)
+        gu.assert_close(logp.cpu().numpy(), lp.squeeze(1).numpy(), 1e-4, 1e-4, "chain logp")
+    gu.assert_close(xd[:, S_:].cpu().numpy(), a1.numpy(), 1e-5, 1e-6, "chain action")
+    assert torch.equal(xd[:, :S_].cpu(), s1)
+    want = torch.stack([uo.mlp_forward(critics, k, torch.cat((s1, a1), -1))[0] for k in subset], 0)
+    gu.assert_close(qt.cpu().numpy(), want.numpy(), 1e-4, 1e-5, "chain target Q")
+
+
+@pytest.mark.parametrize("envs", [1, 5])
+def test_acting_path_kernels_match_oracle(envs):
+    """Agent.forward / sample_action (agent.py:204-327) through the kernels at B = num_envs, incl. SUNRISE's
+    UCB choice (every actor proposes, every member's critics score every proposal) -- against the oracle on the same draws."""
+    import twin_util as tw
+    from super_sac_b200 import _rng
+
+    E, N, S_, A, H = 3, 2, 17, 6, 256
+    agent, _, o_agent, _ = tw.make_twins(E, N, S_, A, H, seed=21)
+    rng = np.random.default_rng(envs)
+    s = rng.standard_normal((envs, S_)).astype(np.float32)
+    obs = {"obs": s[0] if envs == 1 else s}
+    st = torch.as_tensor(s)
+    # greedy action: mean over the actors of tanh(mu)
+    want = torch.stack([torch.tanh(uo.mlp_forward(o_agent.actors, i, st)[0][:, :A]) for i in range(E)], 0).mean(0).numpy()
+    got = agent.forward(obs, num_envs=envs)
+    gu.assert_close(got, want[0] if envs == 1 else want, 1e-5, 2e-6, "Agent.forward")
+    # UCB exploration
+    agent.ucb_bonus = 2.5
+    eps = [rng.standard_normal((envs, A)).astype(np.float32) for _ in range(E)]
+    src = _rng.ScriptedSource()
+    old = _rng.set_source(src)
+    try:
+        for e in eps:
+            src.push("normal", e)
+        got = agent.sample_action(obs, num_envs=envs)
+        assert src.empty()
+    finally:
+        _rng.set_source(old)
+        agent.ucb_bonus = 0.0
+    cands = torch.stack([uo.actor_sample(o_agent, i, st, torch.as_tensor(eps[i]))[0] for i in range(E)], 0)       # [E, envs, A]
+    q = torch.stack([torch.stack([o_agent.critic_min(c, st, cands[e]) for e in range(E)], 0) for c in range(E)], 0)  # [Ec, E, envs, 1]
+    ucb = (q.mean(0) + 2.5 * q.std(0)).squeeze(-1)
+    best = ucb.argmax(0)
+    srt = ucb.sort(0, descending=True).values
+    assert float((srt[0] - srt[1]).min()) > 1e-4, "test data: UCB scores too close to call"
+    want = cands[best, torch.arange(envs)].numpy()
+    gu.assert_close(got, want[0] if envs == 1 else want, 1e-5, 2e-6, "UCB sample_action")
