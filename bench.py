@@ -204,35 +204,50 @@ def run_gpu_arm(args, cfg, rank, world, local_rank):
     e2e_steps = min(args.steps, 2000)
     tr = W.host_transitions(256 if cfg.get("pixels") else 4096, seed=123 + rank)
     n_tr = len(tr[1])
-
-    def e2e_step(k):
-        W.push(tr, k % n_tr)
-        logs = W.step(k)[0]
-        if not isinstance(logs, dict) or not logs:
-            raise RuntimeError("e2e step returned no logs")
-        return logs
-
-    graphed.enable_auto_graphs(True)   # the drop-in calls below replay captured graphs from their third call on
     eager_logs = learning._critic_update_impl(**W.kw)[0]
     d2h = 4 * eager_logs._n
-    for k in range(6):
-        e2e_step(k)
-    h2d = W.buffer._stage_bytes   # one pinned staging row per pushed transition (s, s1, a, r, d, tree index, priority, fill level)
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    with sampler.region():
-        t0 = time.perf_counter()
-        for k in range(e2e_steps):
+
+    def time_e2e(lazy):
+        """push (H2D) + update + Polyak + logged scalars read on the host, every step.  lazy: the drop-in call returns
+        after cudaGraphLaunch and step k's scalars are read while step k+1 runs (one step late, every step); strict: the
+        call itself waits for them."""
+        graphed.enable_auto_graphs(True, lazy_logs=lazy)   # the drop-in calls replay captured graphs from their third call on
+        prev = {"logs": None, "sum": 0.0}
+
+        def e2e_step(k):
+            W.push(tr, k % n_tr)
+            logs = W.step(k)[0]
+            if prev["logs"] is not None:
+                prev["sum"] += float(prev["logs"]["losses/critic_overall_loss"])   # the D2H read of the previous step's result
+            prev["logs"] = logs if lazy else None
+            if not lazy:
+                prev["sum"] += float(logs["losses/critic_overall_loss"])
+
+        for k in range(6):
             e2e_step(k)
         torch.cuda.synchronize()
-        e2e_dt = time.perf_counter() - t0
-    if dist is not None:
-        t = torch.tensor([e2e_dt], device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_dt = float(t.item())
-    e2e_value = world * e2e_steps / e2e_dt
-    graphed.enable_auto_graphs(False)
+        if dist is not None:
+            dist.barrier()
+        with sampler.region():
+            t0 = time.perf_counter()
+            for k in range(e2e_steps):
+                e2e_step(k)
+            if prev["logs"] is not None:
+                prev["sum"] += float(prev["logs"]["losses/critic_overall_loss"])
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        graphed.enable_auto_graphs(False)
+        if not np.isfinite(prev["sum"]):
+            raise RuntimeError("e2e: non-finite loss")
+        if dist is not None:
+            t = torch.tensor([dt], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return world * e2e_steps / dt
+
+    e2e_strict = time_e2e(False)
+    e2e_value = time_e2e(True)
+    h2d = W.buffer._stage_bytes   # one pinned staging row per pushed transition (s, s1, a, r, d, tree index, priority, fill level)
 
     sharded = None
     if dist is not None and cfg["E"] == 1 and cfg["N"] >= world and not cfg.get("pixels") and not cfg.get("offline"):
@@ -276,7 +291,10 @@ def run_gpu_arm(args, cfg, rank, world, local_rank):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_steps, "path": "buffer.push(host transition, H2D) + learning.critic_update (auto CUDA graph where "
-                                            "capturable) + soft_update + logged scalars read back (D2H)"},
+                                            "capturable) + soft_update + logged scalars read back (D2H) on every step",
+                "logs_read": "every step, one step late: graphed.enable_auto_graphs(lazy_logs=True) returns after cudaGraphLaunch and "
+                             "the host reads step k's loss while step k+1 runs",
+                "strict_value": e2e_strict, "strict_logs_read": "the drop-in call itself waits for its scalars (lazy_logs=False)"},
         "gpu_launches": int(round(launch_count * args.steps)),
         "gpu_launches_per_step": launch_count,
         "roofline": roofline,

@@ -100,12 +100,14 @@ class DeviceLogs(dict):
             return self
         return self.fetch()
 
-    def fetch(self, keep=False):
+    def fetch(self, keep=False, synced=False):
         """Resolve pending entries with one device->host copy.  keep=True leaves them registered so the same
-        buffer can be read again after the next graph replay."""
+        buffer can be read again after the next graph replay.  synced: the caller already waited for the replay whose
+        embedded copy filled the pinned buffer (an event recorded behind it)."""
         if self._pending:
             if self._host is not None:
-                torch.cuda.current_stream(self._buf.device).synchronize()   # the copy is part of the replayed graph
+                if not synced:
+                    torch.cuda.current_stream(self._buf.device).synchronize()   # the copy is part of the replayed graph
                 host = self._host[: self._n].tolist()
             else:
                 _reserve_pinned(self._buf.numel())
@@ -131,3 +133,71 @@ def as_device_logs(logs, device):
     if isinstance(logs, DeviceLogs):
         return logs, None
     return DeviceLogs(device), logs
+
+
+class LazyLogs(dict):
+    """The logged scalars of a graph-replayed update whose device->host copy is still in flight.
+
+    ``graphed.enable_auto_graphs(lazy_logs=True)``: ``learning.critic_update`` returns right after ``cudaGraphLaunch``; the
+    values (plain floats under the reference's keys) materialise on first access -- one event wait -- or, at the latest,
+    when the same update is launched again (its pinned read-back buffer is about to be overwritten).  A training loop that
+    only looks at its logs every few hundred steps (main.py:552-572) never stalls on them, and the host prepares the
+    next transition (``buffer.push``) while the GPU is still inside the update."""
+
+    def __init__(self, logs, event):
+        super().__init__()
+        self._src, self._event = logs, event
+
+    def resolve(self):
+        if self._src is not None:
+            src, self._src = self._src, None
+            self._event.synchronize()
+            dict.update(self, src.fetch(keep=True, synced=True))
+        return self
+
+    def __getitem__(self, k):
+        return dict.__getitem__(self.resolve(), k)
+
+    def __iter__(self):
+        return dict.__iter__(self.resolve())
+
+    def __len__(self):
+        return dict.__len__(self.resolve())
+
+    def __contains__(self, k):
+        return dict.__contains__(self.resolve(), k)
+
+    def __repr__(self):
+        return dict.__repr__(self.resolve())
+
+    def __eq__(self, other):
+        return dict.__eq__(self.resolve(), other)
+
+    __hash__ = None
+
+    def get(self, k, default=None):
+        return dict.get(self.resolve(), k, default)
+
+    def keys(self):
+        return dict.keys(self.resolve())
+
+    def values(self):
+        return dict.values(self.resolve())
+
+    def items(self):
+        return dict.items(self.resolve())
+
+    def copy(self):
+        return dict(self.resolve())
+
+    def update(self, *a, **k):
+        return dict.update(self.resolve(), *a, **k)
+
+    def __setitem__(self, k, v):
+        return dict.__setitem__(self.resolve(), k, v)
+
+    def pop(self, *a):
+        return dict.pop(self.resolve(), *a)
+
+    def setdefault(self, *a):
+        return dict.setdefault(self.resolve(), *a)

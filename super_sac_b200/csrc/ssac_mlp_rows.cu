@@ -3,8 +3,8 @@
 // The TD-target path of one member -- a1, logp = pi(s1), then the M target critics of the REDQ subset on (s1, a1)
 // (learning_utils.py:314-338, agent.py:22-40) -- is 0.11 GFLOP on B = 256 rows: as two tensor-core launches its grids are
 // 8 and 16 CTAs and each launch pays ~15 us of serial latency (TMEM allocation, a K = 256 pipeline of eight chunks,
-// epilogue).  Every step of that chain is ROW-LOCAL, so here ONE launch of ceil(B/8) clusters x 4 CTAs (128 CTAs for
-// B = 256) walks the whole chain for 8 batch rows per cluster:
+// epilogue).  Every step of that chain is ROW-LOCAL, so here ONE launch of ceil(B/16) clusters x 4 CTAs (64 CTAs for
+// B = 256) walks the whole chain for 16 batch rows per cluster:
 //
 //   per net  : CTA r of the cluster owns hidden units [r*H/4, (r+1)*H/4) of both hidden layers
 //     layer 1: K = D <= 64, weights slice staged in shared memory, thread = (unit, row group)
@@ -25,7 +25,8 @@
 namespace ssac {
 namespace rows {
 
-constexpr int R = 8;        // batch rows per cluster
+constexpr int R = 16;       // batch rows per cluster (B = 256: 16 clusters x 4 = 64 CTAs, the other SMs stay free for the
+                            // online critics' tensor-core launches that run next to this kernel)
 constexpr int CS = 4;       // CTAs per cluster = slices of the hidden layers
 constexpr int T = 256;      // threads per CTA
 constexpr int kMaxH = 256, kMaxO = 16, kMaxD = 64;
@@ -45,6 +46,14 @@ struct Args {
   float* y;                             // [M,B,O] critic outputs
   const float* x; int64_t ldx; int B, H;
 };
+
+#ifdef SSAC_TRACE
+__device__ long long* g_trace_rows = nullptr;
+__device__ int g_trace_slot = 0;
+#define RT(slot) do { if (g_trace_rows && blockIdx.x == 0 && threadIdx.x == 0) g_trace_rows[slot] = clock64(); } while (0)
+#else
+#define RT(slot) do {} while (0)
+#endif
 
 #define SSAC_LOG2F 0.6931471805599453f
 #define SSAC_LOG_SQRT_2PIF 0.9189385332046727f
@@ -71,133 +80,210 @@ __device__ __forceinline__ void st_remote_f1(const float* local_ptr, uint32_t ct
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
 }
 
-struct Smem {
-  float xs[R][kXP];               // input rows of the current net: [s | a]
-  float hfull[R][kMaxH];          // layer-1 activations of all units (every CTA's slice, via DSMEM)
-  float hloc[R][kMaxH / CS + 1];  // this CTA's layer-1 slice (before the broadcast) / layer-2 slice
-  float red[2 * R * T];           // layer-2 k-split partials: [j][r][ks][pair]
-  float W1s[kMaxH / CS][kXP];     // this CTA's rows of W1
+struct Ops {                        // the small operands of one net, this CTA's slice
+  float W1s[kMaxH / CS][kXP];       // rows of W1
   float W3s[kMaxO][kMaxH / CS + 1];
   float b1s[kMaxH / CS], b2s[kMaxH / CS], b3s[kMaxO];
-  float yp[CS][R][kMaxO];         // output-layer partials of the four CTAs
-  float out[R][kMaxO];            // the net's outputs (identical in all four CTAs)
 };
 
-// One 3-Linear ReLU MLP on the R rows in sm.xs -> sm.out.  Every thread of all four CTAs calls it.
-__device__ void run_net(Smem& sm, const Net& n, int g, int H, int rank, int t) {
-  const int D = n.D, O = n.O;
-  const int HC = H / CS;                 // units per CTA (H is a multiple of 8: HC is even)
-  const int n_lo = rank * HC;
-  const int NP = HC / 2;                 // unit pairs
-  const int KS = T / NP;                 // k splits (threads beyond NP*KS idle in layer 2)
-  const int klen = ((H + KS - 1) / KS + 3) & ~3;   // k per split, multiple of 4, <= 32
-  const float* W1 = n.W1 + (int64_t)g * H * D;
-  const float* W2 = n.W2 + (int64_t)g * H * H;
-  const float* W3 = n.W3 + (int64_t)g * O * H;
-  // ---- layer-2 weights of this thread: issued first, consumed after the layer-1 exchange -----------------------------
-  const int pair = t % NP, ks = t / NP;
-  const bool l2_active = ks < KS;
-  const int k0 = ks * klen;
-  float4 w[2][8];
+struct Smem {
+  float xs[R][kXP];                 // input rows of the current net: [s | a]
+  float hfull[R][kMaxH];            // layer-1 activations of all units (every CTA's slice, via DSMEM)
+  float hloc[R][kMaxH / CS + 4];    // this CTA's layer-1 slice (before the broadcast) / layer-2 slice
+  float red[2 * R * T];             // layer-2 k-split partials: [j][r][ks][pair]
+  Ops ops[2];                       // double buffered: the next net's operands land while the current net computes
+  float yp[CS][R][kMaxO];           // output-layer partials of the four CTAs
+  float out[R][kMaxO];              // the net's outputs (identical in all four CTAs)
+};
+
+struct Geo {   // how a hidden layer of H units is cut up
+  int H, HC, n_lo, NP, KS, klen, pair, ks, k0;
+  bool l2_active;
+  __device__ Geo(int H_, int rank, int t) {
+    H = H_;
+    HC = H / CS;                 // units per CTA (H is a multiple of 8: HC is even)
+    n_lo = rank * HC;
+    NP = HC / 2;                 // unit pairs
+    KS = T / NP;                 // k splits (threads beyond NP*KS idle in layer 2)
+    klen = ((H + KS - 1) / KS + 3) & ~3;   // k per split, multiple of 4, <= 32
+    pair = t % NP;
+    ks = t / NP;
+    l2_active = ks < KS;
+    k0 = ks * klen;
+  }
+};
+
+// this thread's layer-2 weights (2 units x klen k) straight from L2 into registers: sixteen 16-byte loads in flight
+__device__ __forceinline__ void load_w2(float4 (&w)[2][8], const Net& n, int g, const Geo& G) {
+  const float* W2 = n.W2 + (int64_t)g * G.H * G.H;
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
-    const float* wr = W2 + (int64_t)(n_lo + 2 * pair + j) * H + k0;
+    const float* wr = W2 + (int64_t)(G.n_lo + 2 * G.pair + j) * G.H + G.k0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const bool ok = l2_active && 4 * i < klen && k0 + 4 * i < H;
+      const bool ok = G.l2_active && 4 * i < G.klen && G.k0 + 4 * i < G.H;
       w[j][i] = ok ? __ldg(reinterpret_cast<const float4*>(wr + 4 * i)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
-  // ---- small operands -> shared memory ---------------------------------------------------------------------------
-  for (int i = t; i < HC * D; i += T) {
-    const int c = i / D, k = i - c * D;
-    sm.W1s[c][k] = __ldg(W1 + (int64_t)(n_lo + c) * D + k);
+}
+
+// the net's small operands -> shared memory; all global loads of a thread are issued before its first store
+__device__ __forceinline__ void load_ops(Ops& op, const Net& n, int g, const Geo& G, int t) {
+  const int D = n.D, O = n.O, HC = G.HC;
+  const float* W1 = n.W1 + ((int64_t)g * G.H + G.n_lo) * D;   // the slice's rows are contiguous: HC * D floats
+  const float* W3 = n.W3 + (int64_t)g * O * G.H;
+  constexpr int U1 = (kMaxH / CS) * kMaxD / T;   // 16
+  constexpr int U3 = (kMaxH / CS) * kMaxO / T;   // 4
+  float v1[U1], v3[U3];
+#pragma unroll
+  for (int u = 0; u < U1; ++u) {
+    const int i = t + u * T;
+    v1[u] = i < HC * D ? __ldg(W1 + i) : 0.f;
   }
-  for (int i = t; i < O * HC; i += T) {
-    const int o = i / HC, c = i - o * HC;
-    sm.W3s[o][c] = __ldg(W3 + (int64_t)o * H + n_lo + c);
+#pragma unroll
+  for (int u = 0; u < U3; ++u) {
+    const int i = t + u * T;
+    v3[u] = i < O * HC ? __ldg(W3 + (int64_t)(i / HC) * G.H + G.n_lo + (i % HC)) : 0.f;
   }
+  float vb1 = 0.f, vb2 = 0.f, vb3 = 0.f;
   if (t < HC) {
-    sm.b1s[t] = __ldg(n.b1 + (int64_t)g * H + n_lo + t);
-    sm.b2s[t] = __ldg(n.b2 + (int64_t)g * H + n_lo + t);
+    vb1 = __ldg(n.b1 + (int64_t)g * G.H + G.n_lo + t);
+    vb2 = __ldg(n.b2 + (int64_t)g * G.H + G.n_lo + t);
   }
-  if (t < O) sm.b3s[t] = __ldg(n.b3 + (int64_t)g * O + t);
-  __syncthreads();
-  // ---- layer 1: thread = (unit c, row group) ----------------------------------------------------------------------
-  for (int o = t; o < R * HC; o += T) {
-    const int c = o % HC, r = o / HC;
-    float acc = sm.b1s[c];
-    for (int k = 0; k < D; ++k) acc = fmaf(sm.xs[r][k], sm.W1s[c][k], acc);
-    sm.hloc[r][c] = fmaxf(acc, 0.f);
+  if (t < O) vb3 = __ldg(n.b3 + (int64_t)g * O + t);
+#pragma unroll
+  for (int u = 0; u < U1; ++u) {
+    const int i = t + u * T;
+    if (i < HC * D) op.W1s[i / D][i % D] = v1[u];
+  }
+#pragma unroll
+  for (int u = 0; u < U3; ++u) {
+    const int i = t + u * T;
+    if (i < O * HC) op.W3s[i / HC][i % HC] = v3[u];
+  }
+  if (t < HC) { op.b1s[t] = vb1; op.b2s[t] = vb2; }
+  if (t < O) op.b3s[t] = vb3;
+}
+
+// One 3-Linear ReLU MLP on the R rows in sm.xs -> sm.out.  Every thread of all four CTAs calls it.  On entry ``w`` and
+// ``op`` hold this net's layer-2 weights / small operands (visible: a barrier separates the load from this call); on exit
+// they hold those of (next, next_g) when ``next`` is given, loaded behind this net's layer-2 arithmetic.
+__device__ void run_net(Smem& sm, int buf, float4 (&w)[2][8], const Net& n, const Net* next, int next_g, const Geo& G, int rank,
+                        int t, int tb = 0) {
+  RT(tb + 0);
+  const int D = n.D, O = n.O, HC = G.HC, NP = G.NP, KS = G.KS;
+  const Ops& op = sm.ops[buf];
+  // ---- layer 1: thread = (unit c, row group of R / (T / HC) rows); one weight read feeds all rows of the group ------
+  {
+    const int groups = T / HC > 0 ? T / HC : 1;            // 4 for H = 256
+    const int rpg = (R + groups - 1) / groups;             // rows per group
+    const int c = t % HC, gr = t / HC;
+    if (gr < groups) {
+      for (int r0 = gr * rpg; r0 < min(R, (gr + 1) * rpg); r0 += 4) {
+        float acc[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] = op.b1s[c];
+#pragma unroll 4
+        for (int k = 0; k < D; ++k) {
+          const float wv = op.W1s[c][k];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) acc[u] = fmaf(sm.xs[min(r0 + u, R - 1)][k], wv, acc[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (r0 + u < min(R, (gr + 1) * rpg)) sm.hloc[r0 + u][c] = fmaxf(acc[u], 0.f);
+      }
+    }
   }
   __syncthreads();
-  // broadcast the slice into every CTA's hfull (16-byte stores; HC is a multiple of 2: pairs as 8-byte halves are
-  // avoided by requiring HC % 4 == 0 on this path, else scalar stores)
+  RT(tb + 2);
+  // broadcast the slice into every CTA's hfull (16-byte remote stores when the slice is a multiple of 4 units wide)
   if ((HC & 3) == 0) {
     const int q = HC / 4;
     for (int i = t; i < R * q; i += T) {
       const int r = i / q, c4 = (i - r * q) * 4;
-      const float4 v = make_float4(sm.hloc[r][c4], sm.hloc[r][c4 + 1], sm.hloc[r][c4 + 2], sm.hloc[r][c4 + 3]);
+      const float4 v = *reinterpret_cast<const float4*>(&sm.hloc[r][c4]);
 #pragma unroll
-      for (int d = 0; d < CS; ++d) st_remote_f4(&sm.hfull[r][n_lo + c4], (uint32_t)d, v);
+      for (int d = 0; d < CS; ++d) st_remote_f4(&sm.hfull[r][G.n_lo + c4], (uint32_t)d, v);
     }
   } else {
     for (int i = t; i < R * HC; i += T) {
       const int r = i / HC, c = i - r * HC;
 #pragma unroll
-      for (int d = 0; d < CS; ++d) st_remote_f1(&sm.hfull[r][n_lo + c], (uint32_t)d, sm.hloc[r][c]);
+      for (int d = 0; d < CS; ++d) st_remote_f1(&sm.hfull[r][G.n_lo + c], (uint32_t)d, sm.hloc[r][c]);
     }
   }
+  RT(tb + 3);
   cluster_sync_all();
+  RT(tb + 4);
   // ---- layer 2: thread = (unit pair, k split) ----------------------------------------------------------------------
-  if (l2_active) {
-    float acc[2][R];
+  if (G.l2_active) {
 #pragma unroll
-    for (int r = 0; r < R; ++r) acc[0][r] = acc[1][r] = 0.f;
+    for (int rb = 0; rb < R; rb += 8) {
+      float acc[2][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (4 * i < klen && k0 + 4 * i < H) {
+      for (int r = 0; r < 8; ++r) acc[0][r] = acc[1][r] = 0.f;
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const float4 h = *reinterpret_cast<const float4*>(&sm.hfull[r][k0 + 4 * i]);
-          acc[0][r] = fmaf(h.x, w[0][i].x, acc[0][r]); acc[0][r] = fmaf(h.y, w[0][i].y, acc[0][r]);
-          acc[0][r] = fmaf(h.z, w[0][i].z, acc[0][r]); acc[0][r] = fmaf(h.w, w[0][i].w, acc[0][r]);
-          acc[1][r] = fmaf(h.x, w[1][i].x, acc[1][r]); acc[1][r] = fmaf(h.y, w[1][i].y, acc[1][r]);
-          acc[1][r] = fmaf(h.z, w[1][i].z, acc[1][r]); acc[1][r] = fmaf(h.w, w[1][i].w, acc[1][r]);
+      for (int i = 0; i < 8; ++i) {
+        if (4 * i < G.klen && G.k0 + 4 * i < G.H) {
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const float4 h = *reinterpret_cast<const float4*>(&sm.hfull[rb + r][G.k0 + 4 * i]);
+            acc[0][r] = fmaf(h.x, w[0][i].x, acc[0][r]); acc[0][r] = fmaf(h.y, w[0][i].y, acc[0][r]);
+            acc[0][r] = fmaf(h.z, w[0][i].z, acc[0][r]); acc[0][r] = fmaf(h.w, w[0][i].w, acc[0][r]);
+            acc[1][r] = fmaf(h.x, w[1][i].x, acc[1][r]); acc[1][r] = fmaf(h.y, w[1][i].y, acc[1][r]);
+            acc[1][r] = fmaf(h.z, w[1][i].z, acc[1][r]); acc[1][r] = fmaf(h.w, w[1][i].w, acc[1][r]);
+          }
         }
       }
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int r = 0; r < 8; ++r) sm.red[((j * R + rb + r) * KS + G.ks) * NP + G.pair] = acc[j][r];
     }
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-#pragma unroll
-      for (int r = 0; r < R; ++r) sm.red[((j * R + r) * KS + ks) * NP + pair] = acc[j][r];
   }
   __syncthreads();
+  RT(tb + 5);
+  // the registers are free again: the next net's layer-2 weights fly behind the rest of this net
+  if (next) load_w2(w, *next, next_g, G);
   for (int o = t; o < R * HC; o += T) {
     const int c = o % HC, r = o / HC;
     const int j = c & 1, pr = c >> 1;
-    float s = sm.b2s[c];
-    for (int q = 0; q < KS; ++q) s += sm.red[((j * R + r) * KS + q) * NP + pr];   // fixed order
+    const float* rp = &sm.red[((j * R + r) * KS) * NP + pr];
+    float s = op.b2s[c];
+#pragma unroll 8
+    for (int q = 0; q < KS; ++q) s += rp[q * NP];   // fixed order
     sm.hloc[r][c] = fmaxf(s, 0.f);
   }
   __syncthreads();
-  // ---- layer 3: partial outputs over this CTA's units, exchanged over DSMEM ------------------------------------------
+  RT(tb + 6);
+  // ---- layer 3: partial outputs over this CTA's units (thread = output), exchanged over DSMEM ------------------------
   for (int o = t; o < R * O; o += T) {
     const int oo = o % O, r = o / O;
-    float acc = 0.f;
-    for (int c = 0; c < HC; ++c) acc = fmaf(sm.hloc[r][c], sm.W3s[oo][c], acc);
+    float a0 = 0.f, a1 = 0.f;
+    int c = 0;
+#pragma unroll 8
+    for (; c + 1 < HC; c += 2) {
+      a0 = fmaf(sm.hloc[r][c], op.W3s[oo][c], a0);
+      a1 = fmaf(sm.hloc[r][c + 1], op.W3s[oo][c + 1], a1);
+    }
+    const float acc = a0 + a1;
 #pragma unroll
     for (int d = 0; d < CS; ++d) st_remote_f1(&sm.yp[rank][r][oo], (uint32_t)d, acc);
   }
+  RT(tb + 7);
   cluster_sync_all();
+  RT(tb + 8);
   for (int o = t; o < R * O; o += T) {
     const int oo = o % O, r = o / O;
-    float s = sm.b3s[oo];
+    float s = op.b3s[oo];
 #pragma unroll
     for (int d = 0; d < CS; ++d) s += sm.yp[d][r][oo];   // rank order: identical in all four CTAs
     sm.out[r][oo] = s;
   }
+  if (next) load_ops(sm.ops[buf ^ 1], *next, next_g, G, t);
   __syncthreads();
+  RT(tb + 9);
 }
 
 __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(T, 1) mlp_rows_kernel(const __grid_constant__ Args q) {
@@ -206,22 +292,33 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(T, 1) mlp_rows_kern
   const int t = threadIdx.x;
   const int rank = (int)cluster_rank();
   const int m0 = ((int)blockIdx.x / CS) * R;
-  const int H = q.H, B = q.B;
-  const int Din = q.has_actor ? q.S : q.critic.D;   // columns of x that are inputs (the actor reads the state columns)
-  // the batch (x, eps, noise) is the previous kernels' business: everything else above was parameter-free set-up
-  pdl_wait();
-  pdl_trigger();
+  const int B = q.B;
+  const Geo G(q.H, rank, t);
+  RT(0);
+  // parameters first (nobody upstream writes them: Adam / Polyak never trigger early), so that under PDL their latency
+  // overlaps the tail of the previous kernel; the REDQ subset was drawn at least two launches ago
+  float4 w[2][8];
+  const Net& first = q.has_actor ? q.actor : q.critic;
+  const int g_first = q.has_actor ? 0 : (q.net_index ? q.net_index[0] : 0);
+  load_w2(w, first, g_first, G);
+  load_ops(sm.ops[0], first, g_first, G, t);
   for (int i = t; i < R * kXP; i += T) (&sm.xs[0][0])[i] = 0.f;
+  pdl_wait();      // the batch (x, eps, noise) is the previous kernels' business
+  pdl_trigger();
+  RT(1);
   __syncthreads();
-  const int Dload = q.has_actor ? ((q.M > 0) ? q.S : q.actor.D) : Din;
+  const int Dload = q.has_actor ? q.S : q.critic.D;
   for (int i = t; i < R * Dload; i += T) {
     const int r = i / Dload, k = i - r * Dload;
     if (m0 + r < B) sm.xs[r][k] = q.x[(int64_t)(m0 + r) * q.ldx + k];
   }
   __syncthreads();
 
+  int buf = 0;
   if (q.has_actor) {
-    run_net(sm, q.actor, 0, H, rank, t);
+    const int g_next = q.M > 0 ? (q.net_index ? q.net_index[0] : 0) : 0;
+    run_net(sm, buf, w, q.actor, q.M > 0 ? &q.critic : nullptr, g_next, G, rank, t, 10);
+    buf ^= 1;
     // ---- policy head: thread = row (all four CTAs compute it, rank 0 writes the global outputs) -----------------------
     if (t < R) {
       const int r = t, b = m0 + r;
@@ -269,8 +366,9 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(T, 1) mlp_rows_kern
     __syncthreads();
   }
   for (int m = 0; m < q.M; ++m) {
-    const int g = q.net_index ? q.net_index[m] : m;
-    run_net(sm, q.critic, g, H, rank, t);
+    const int g_next = m + 1 < q.M ? (q.net_index ? q.net_index[m + 1] : m + 1) : 0;
+    run_net(sm, buf, w, q.critic, m + 1 < q.M ? &q.critic : nullptr, g_next, G, rank, t, 20 + 10 * m);
+    buf ^= 1;
     const int O = q.critic.O;
     if (rank == 0)
       for (int o = t; o < R * O; o += T) {
@@ -280,6 +378,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(T, 1) mlp_rows_kern
     __syncthreads();
   }
   cluster_sync_all();   // nobody leaves while a neighbour may still write into its shared memory
+  RT(2);
 }
 
 static int launch(const Args& a, cudaStream_t s) {
@@ -320,6 +419,10 @@ int mlp_forward_rows(const float* W1, const float* b1, const float* W2, const fl
 using namespace ssac;
 
 extern "C" {
+
+#ifdef SSAC_TRACE
+int ssac_debug_set_trace_rows(long long* dev_ptr) { return (int)cudaMemcpyToSymbol(rows::g_trace_rows, &dev_ptr, sizeof(dev_ptr)); }
+#endif
 
 int ssac_policy_rows(const float* W1, const float* b1, const float* W2, const float* b2, const float* W3, const float* b3,
                      int D, int H, int A, int deterministic, const float* x_dev, int64_t ldx, int B, float* out_dev,

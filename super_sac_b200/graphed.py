@@ -51,15 +51,17 @@ class GraphedCall:
 # ------------------------------------------------------------------------------------------------
 # transparent graph replay behind the drop-in entry points
 # ------------------------------------------------------------------------------------------------
-_auto = {"on": False, "cache": {}, "min_calls": 2}
+_auto = {"on": False, "cache": {}, "min_calls": 2, "lazy": False}
 
 
-def enable_auto_graphs(on=True):
+def enable_auto_graphs(on=True, lazy_logs=False):
     """After ``enable_auto_graphs()``, ``learning.critic_update`` / ``online_actor_update`` / ``alpha_update`` replay a
     captured CUDA graph from the third call with identical arguments on (same objects, same hyper-parameters): the call
     a user makes stays ``learning.critic_update(...)``, the ~20 launches and their Python marshalling collapse into one
-    ``cudaGraphLaunch`` + one device->host copy of the logged scalars."""
+    ``cudaGraphLaunch`` + one device->host copy of the logged scalars.  ``lazy_logs``: the returned dict materialises its
+    values on first access instead of synchronising inside the call (``_logs.LazyLogs``)."""
     _auto["on"] = bool(on)
+    _auto["lazy"] = bool(lazy_logs) and bool(on)
     if not on:
         _auto["cache"].clear()
 
@@ -69,10 +71,11 @@ def auto_graphs_enabled():
 
 
 class _Entry:
-    __slots__ = ("calls", "graph", "result", "on_replay", "refs")
+    __slots__ = ("calls", "graph", "result", "on_replay", "refs", "pending", "event")
 
     def __init__(self):
         self.calls, self.graph, self.result, self.on_replay, self.refs = 0, None, None, None, None
+        self.pending, self.event = None, None
 
 
 def is_static(obj):
@@ -107,10 +110,19 @@ def run_cached(key, fn, on_replay=None, refs=None):
                         rd._ssac_static = True
                     except AttributeError:
                         pass
+    if e.pending is not None:    # the previous replay's logs live in the pinned buffer this replay overwrites
+        e.pending.resolve()
+        e.pending = None
     e.graph.replay()
     if e.on_replay is not None:
         e.on_replay()
     res = e.result
     logs = res[0] if isinstance(res, tuple) else res
-    out = dict(logs.fetch(keep=True))
+    if _auto["lazy"] and logs._host is not None:
+        if e.event is None:
+            e.event = torch.cuda.Event()
+        e.event.record()
+        out = e.pending = _logs.LazyLogs(logs, e.event)
+    else:
+        out = dict(logs.fetch(keep=True))
     return (out,) + tuple(res[1:]) if isinstance(res, tuple) else out

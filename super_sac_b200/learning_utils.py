@@ -362,6 +362,9 @@ def _actor_forward(agent, i, X, B, S, A, keep=False):
     return out, h1, h2
 
 
+TARGET_CHAIN = False
+
+
 def _rows_ok(D, H, O):
     """The row-local CUDA-core kernel (ssac_mlp_rows.cu) covers this shape and is switched on."""
     return bool(_lib.lib().rows_supported(int(D), int(H), int(O)))
@@ -380,7 +383,8 @@ def _policy_sample(agent, i, X, B, S, A, random_process, noise_clip, rsample=Fal
     keep = rsample if keep is None else keep
     arena = agent._actor_arena
     det = agent.deterministic
-    use_rows = not keep and _lib.lib().default_mlp_impl() == 2 and _rows_ok(S + A, arena.H, arena.O) and A <= 8
+    use_rows = (not keep and _lib.lib().default_mlp_impl() == 2 and _rows_ok(S + A, arena.H, arena.O) and A <= 8
+                and (B <= 64 or chain is not None))   # the acting path (B = num_envs); large batches keep the tensor cores
     if chain is not None and not (use_rows and chain[0].H == arena.H and chain[0].O == 1 and chain[0].D == S + A):
         chain = None
     h1 = h2 = out = None
@@ -503,8 +507,10 @@ def compute_td_targets(logs, replay_dict, agent, target_agent, ensemble_idx, ens
     # REDQ subset: drawn over the GLOBAL ensemble when the critics are sharded over ranks (replicated Philox state)
     pool = parallel.n_global() if parallel.is_sharded() else N
     assert 0 < ensemble_n <= pool
-    # unsharded: actor + target-critic subset + action write-back are ONE row-local launch (ssac_target_chain)
-    want_chain = not parallel.is_sharded()
+    # ssac_target_chain (actor + target-critic subset + action write-back in ONE row-local CUDA-core launch) is exact fp32
+    # but measured SLOWER than the two tensor-core launches it replaces at B = 256 (35 vs 31 us back to back, and it takes
+    # SMs away from the online critics' branch): off unless TARGET_CHAIN is set (kept for small batches / A-B runs)
+    want_chain = TARGET_CHAIN and not parallel.is_sharded()
     if _draws is not None:   # critic_update drew indices, policy noise and the subset in ONE launch
         net_index = _draws["subset"]
         pol = _policy_sample(agent, i, X1, B, S, A, random_process, noise_clip,
