@@ -60,7 +60,9 @@ def import_reference(root=None, device="cpu"):
     import torch
 
     dev = torch.device(device) if device != "cpu" else "cpu"
-    # every module did ``from . import device`` at import time (learning.py:13, learning_utils.py:10, agent.py:10)
-    for mod in (cur, cur.learning, cur.learning_utils, cur.agent):
-        mod.device = dev
+    # every module did ``from . import device`` at import time (learning.py:13, learning_utils.py:10, agent.py:10,
+    # main.py:18, ...): re-point all of them
+    for name, mod in list(sys.modules.items()):
+        if (name == "super_sac" or name.startswith("super_sac.")) and mod is not None and hasattr(mod, "device"):
+            mod.device = dev
     return cur

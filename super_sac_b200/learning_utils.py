@@ -656,3 +656,77 @@ def adjust_priorities(logs, replay_dict, agent, buffer):
     member = random.choice(range(agent.ensemble_size))
     _, _, prio = _advantage(agent, replay_dict, member, want_priority=True)
     buffer.update_priorities(replay_dict["priority_idxs"], prio)
+
+
+# ------------------------------------------------------------------------------------------------
+# caller-side helpers the reference training loop imports from learning_utils (main.py:249-275, :587)
+# ------------------------------------------------------------------------------------------------
+class EpsilonGreedyExplorationNoise:
+    """Discrete-action counterpart of GaussianExplorationNoise (reference learning_utils.py:69-93): with probability
+    ``current_scale`` the whole action array is replaced by uniform random actions; epsilon anneals linearly."""
+
+    def __init__(self, action_space, eps_start=1.0, eps_final=1e-5, steps_annealed=1000):
+        assert eps_start >= eps_final
+        self.action_space = action_space
+        self.eps_start, self.eps_final, self.steps_annealed = eps_start, eps_final, steps_annealed
+        self.current_scale = eps_start
+        self._eps_slope = (eps_start - eps_final) / steps_annealed
+
+    def sample(self, action, clip=None, update_schedule=False):
+        if random.random() < self.current_scale:
+            action = np.random.randint(0, self.action_space.n, size=action.shape, dtype=action.dtype)
+        if update_schedule:
+            self.current_scale = max(self.current_scale - self._eps_slope, self.eps_final)
+        return action
+
+
+def n_step_push(buffer, window, gamma, terminate_traj):
+    """Fold a full n-step window [(s, a, r, s1, d), ...] into one transition (s_0, a_0, sum_i gamma^i r_i, s1_last,
+    d_last) and push it (main.py:353-365, learning_utils.py:139-151)."""
+    s, a, r, s1, d = window.popleft()
+    for i, (*_, r_i, s1_i, d_i) in enumerate(window):
+        r = r + (gamma ** (i + 1)) * r_i
+        s1, d = s1_i, d_i
+    buffer.push(s, a, r, s1, d, terminate_traj=terminate_traj)
+    return d
+
+
+def warmup_buffer(buffer, env, warmup_steps, max_episode_steps, n_step, gamma, num_envs=1):
+    """Fill the buffer with ``warmup_steps`` random-action transitions (reference learning_utils.py:108-157)."""
+    from collections import deque
+
+    state, _ = env.reset()
+    done, steps_this_ep = False, 0
+    window = deque([], maxlen=n_step)
+    for step_num in range(warmup_steps):
+        if done:
+            state, _ = env.reset()
+            done, steps_this_ep = False, 0
+            window.clear()
+        act = env.action_space.sample()
+        if not isinstance(act, np.ndarray):
+            act = np.array(act)
+            if act.ndim == 0:
+                act = np.expand_dims(act, 0)
+        if num_envs > 1:
+            act = np.array([act for _ in range(num_envs)])
+        next_state, reward, terminated, truncated, _ = env.step(act)
+        window.append((state, act, reward, next_state, terminated))   # "terminated", not "truncated", is what is stored
+        if len(window) == window.maxlen:
+            last_d = window[-1][4]
+            over = last_d.any() if num_envs > 1 else last_d
+            n_step_push(buffer, window, gamma, terminate_traj=over or step_num >= warmup_steps - 1)
+        if num_envs > 1:
+            done = terminated.any() or truncated.any()
+        state = next_state
+        steps_this_ep += 1
+        if steps_this_ep >= max_episode_steps:
+            done = True
+
+
+def compute_filter_stats(buffer, agent, augmenter, batch_size):
+    """Percentage of a uniformly sampled batch that the binary advantage filter accepts (reference
+    learning_utils.py:217-238), through the kernel advantage estimator; one scalar read-back."""
+    rd = sample_move_and_augment(buffer=buffer, batch_size=batch_size, augmenter=augmenter, aug_mix=0.0, per=False)
+    _, mask, _ = _advantage(agent, rd, random.choice(range(agent.ensemble_size)))
+    return float(mask.mean().item()) * 100.0
