@@ -250,7 +250,8 @@ def run_gpu_arm(args, cfg, rank, world, local_rank):
     h2d = W.buffer._stage_bytes   # one pinned staging row per pushed transition (s, s1, a, r, d, tree index, priority, fill level)
 
     sharded = None
-    if dist is not None and cfg["E"] == 1 and cfg["N"] >= world and not cfg.get("pixels") and not cfg.get("offline"):
+    can_shard = (cfg["N"] >= world) if cfg["E"] == 1 else (cfg["E"] >= world)
+    if dist is not None and can_shard and not cfg.get("pixels") and not cfg.get("offline"):
         with sampler.region():
             sharded = time_sharded(cfg, args, device, rank, world, dist)
     if rank != 0:
@@ -432,43 +433,27 @@ def run_sharded_parity(rank, world, device, dist):
 
 
 def time_sharded(cfg, args, device, rank, world, dist):
-    """Multi-GPU single learner: ONE learner whose N critics are sharded over the ranks; the target-Q exchange
-    runs inside every update.  Returns updates/s of that single learner (max over ranks)."""
-    import copy
-
+    """Multi-GPU single learner: ONE learner whose ensemble is partitioned over the ranks -- the N critics of
+    a REDQ-style agent, or the E members of a SUNRISE-style ensemble -- with the exchange (target Q rows / member batches
+    and values) inside every update.  Returns updates/s of that single learner (max over ranks)."""
     import super_sac_b200 as ssb
-    from super_sac_b200 import augmentations, graphed, learning, learning_utils as lu, nets, parallel
+    from super_sac_b200 import graphed, parallel
 
-    IdentityEncoder, _ = bl._encoders(ssb)
-    lo, hi = parallel.enable_critic_sharding(cfg["N"])
+    members = cfg["E"] > 1
+    if members:
+        lo, hi = parallel.enable_member_sharding(cfg["E"])
+        over, seed, tseed = dict(E=hi - lo), 100 + rank, 0      # every rank samples its own members' batches
+    else:
+        lo, hi = parallel.enable_critic_sharding(cfg["N"])
+        over, seed, tseed = dict(N=hi - lo), 1234, 1234         # identical Philox stream and actor replica on every rank
     try:
-        ssb.manual_seed(1234)          # identical Philox stream on every rank: same indices / eps / subset
-        torch.manual_seed(1234)        # identical actor replica
-        agent = ssb.Agent(act_space_size=cfg["A"], encoder=IdentityEncoder(cfg["S"]),
-                          actor_network_cls=nets.mlps.ContinuousStochasticActor, critic_network_cls=nets.mlps.ContinuousCritic,
-                          ensemble_size=1, num_critics=hi - lo, hidden_size=cfg["H"], auto_rescale_targets=False,
-                          log_std_low=-5.0, log_std_high=2.0)
-        agent.to(device)
-        target = copy.deepcopy(agent)
-        from itertools import chain
-
-        critic_opt = torch.optim.Adam(chain(*(c.parameters() for c in agent.critics)), lr=cfg["lr"])
-        enc_opt = torch.optim.Adam(agent.encoder.parameters(), lr=1e-4)
-        la = torch.Tensor([-2.302585]).to(device)
-        la.requires_grad = True
-        buf = ssb.replay.ReplayBuffer(200_000, device=device)
-        s, a, r, s1, d = bl.synthetic_transitions(cfg, 200_000, 0)
-        buf.load_experience({"obs": s}, a, r, {"obs": s1}, d)
-        B = cfg["B"]
-        kw = dict(buffer=buf, agent=agent, target_agent=target, critic_optimizer=critic_opt, encoder_optimizer=enc_opt,
-                  log_alphas=[la], batch_size=B, gamma=0.99, critic_clip=None, encoder_clip=None,
-                  target_critic_ensemble_n=cfg["M"], weighted_bellman_temp=None, weight_type=None, pop=False,
-                  augmenter=augmentations.AugmentationSequence([augmentations.IdentityAug(B)]), encoder_lambda=0.0,
-                  random_process=None, noise_clip=None, aug_mix=0.0)
+        W = bl.Workload(ssb, args.config, device, seed=seed, buffer_size=200_000, overrides=over, torch_seed=tseed)
+        if not members:
+            W.kw["target_critic_ensemble_n"] = cfg["M"]
 
         def upd():
-            out = learning.critic_update(**kw)
-            lu.soft_update(target.critics[0], agent.critics[0], cfg["tau"])
+            out = W.critic_update()
+            W.polyak()
             return out
 
         mode = "cuda-graph replay (exchange captured)"
@@ -493,11 +478,12 @@ def time_sharded(cfg, args, device, rank, world, dist):
         t = torch.tensor([e0.elapsed_time(e1)], device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+        n_units = cfg["E"] if members else cfg["N"]
         return {"value": steps / (ms * 1e-3), "unit": "updates/s of ONE learner", "ms_per_step": ms / steps, "mode": mode,
-                "exchange": parallel.exchange_name() if hasattr(parallel, "exchange_name") else "NCCL all-gather",
-                "critics_per_rank": [parallel.local_range(cfg["N"], world, r)[1] - parallel.local_range(cfg["N"], world, r)[0]
-                                     for r in range(world)],
-                "exchanged_per_update": "target Q [N,B] fp32 (%d B per rank)" % (4 * B * -(-cfg["N"] // world))}
+                "partitioned": "members" if members else "critics", "exchange": parallel.exchange_name(),
+                "per_rank": [parallel.local_range(n_units, world, r)[1] - parallel.local_range(n_units, world, r)[0] for r in range(world)],
+                "exchanged_per_update": ("member batches [E,B,S+A] + target values [E*N,E,B] fp32" if members else
+                                         "target Q rows [N,B] fp32 (%d B per critic)" % (4 * cfg["B"]))}
     finally:
         parallel.disable()
 

@@ -313,6 +313,24 @@ int ssac_advantage(const float* q_pi_dev, int n, const float* q_data_dev, int B,
 /* min over the N rows of q [N,B] with optional PopArt affine (agent.py:37-38, adv_estimator.py:30-35). */
 int ssac_min_over_nets(const float* q_dev, int N, int B, const float* popart_dev, float* out_dev, void* stream);
 
+/* ---- ensemble sharding over NVLink peer memory: SURVEY 8e (no counterpart in the reference: it is single-device) ---- */
+/* The exchanges of the sharded learner (target Q rows, Q(s,pi(s)) rows, dL/da partials, SUNRISE batches / values) as two
+ * small kernels over SYMMETRIC buffers (one allocation of 2 x half_bytes per rank, mapped into every peer; the mappings
+ * come from torch.distributed._symmetric_memory.rendezvous): no NCCL launch on the update's critical path.
+ *   ssac_peer_put : copy nbytes from src_dev to offset dst_off of the current half (epoch parity) of EVERY rank's buffer
+ *                   (peer_bufs_dev: device array of `world` mapped pointers, own rank included) with 16-byte peer stores,
+ *                   fence at system scope, then raise this rank's signal on every rank: sigs[p][rank] = ++epoch.
+ *   ssac_peer_wait: spin until every rank's signal reached the epoch of the preceding put, then copy the first nbytes of
+ *                   the current half into out_dev (an address that is stable across CUDA-graph replays) -- or, with
+ *                   row_index_dev (device int32[n_rows]), only rows row_index[m] of row_bytes each (the REDQ subset).
+ * epoch_dev: device uint32 owned by the exchange site (one per site: sites never share signals).  Both calls are
+ * CUDA-graph capturable; ranks run the same sequence of exchanges (lock-step by construction of the sharded update). */
+int ssac_peer_put(const void* src_dev, int64_t nbytes, int64_t dst_off, int64_t half_bytes, void* const* peer_bufs_dev,
+                  uint32_t* const* peer_sigs_dev, int rank, int world, uint32_t* epoch_dev, void* stream);
+int ssac_peer_wait(const void* my_buf_dev, int64_t half_bytes, int64_t nbytes, const uint32_t* my_sigs_dev, int world,
+                   const uint32_t* epoch_dev, void* out_dev, const int32_t* row_index_dev, int n_rows, int64_t row_bytes,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

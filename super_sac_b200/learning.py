@@ -153,7 +153,7 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
         td_target, (s1, a1) = lu.compute_td_targets(
             logs=logs, replay_dict=rd, agent=agent, target_agent=target_agent, log_alphas=log_alphas, ensemble_idx=i,
             ensemble_n=target_critic_ensemble_n, pop=pop, gamma=gamma, random_process=random_process,
-            noise_clip=noise_clip, _draws=draws, _fuse_into_loss=side is not None and not parallel.is_sharded())
+            noise_clip=noise_clip, _draws=draws, _fuse_into_loss=side is not None)
         tdp = getattr(td_target, "_ssac_pending", None)   # TD target evaluated inside the loss kernel
         w = lu.compute_backup_weights(logs=logs, replay_dict=rd, agent=agent, target_agent=target_agent,
                                       weight_type=weight_type, weight_temp=weighted_bellman_temp, batch_size=B,
@@ -244,15 +244,20 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
         main = torch.cuda.current_stream(dev)
         side.wait_stream(main)
         gslot = lu._member_grad_norm_slot(logs, ca, member * N, (member + 1) * N, stream=side)
+    if parallel.is_sharded() and side is not None:
+        # each rank summed its own critics: the logged loss is the global sum -- a log value, so its exchange runs next to
+        # Adam on the second stream instead of behind it
+        with torch.cuda.stream(side):
+            parallel.all_reduce_sum_(loss_all[0:1], site="critic_loss")
     opt.step(stream, max_norm=critic_clip if critic_clip else None)
     if side is not None:
         main.wait_stream(side)
     else:
         gslot = lu._member_grad_norm_slot(logs, ca, member * N, (member + 1) * N)
+        if parallel.is_sharded():
+            parallel.all_reduce_sum_(loss_all[0:1], site="critic_loss")
     lu._mark("Adam (+ logged grad norm)")
 
-    if parallel.is_sharded():
-        parallel.all_reduce_sum_(loss_all[0:1])   # each rank summed its own critics
     if parallel.members_sharded():                # ... or its own members: the logged loss is the global sum
         tot = loss_all[0:2 * E:2].sum().reshape(1)
         parallel.all_reduce_members_(tot)
@@ -336,7 +341,7 @@ def _online_actor_update_impl(buffer, agent, pop, actor_optimizer, log_alphas, b
         if parallel.is_sharded():
             # every rank sees all N_global values, picks the arg-min net per row, and back-propagates only the rows
             # whose arg-min critic it owns; the partial dL/da are summed below
-            q_all = parallel.all_gather_q(q)
+            q_all = parallel.all_gather_q(q, site="actor_q")
             Ng = q_all.shape[0]
             dq_all = torch.empty((Ng, B, 1), dtype=torch.float32, device=dev)
             L.actor_loss_seed(q_all.data_ptr(), Ng, B, pol["logp"].data_ptr() if entropy_on else None,
@@ -361,7 +366,7 @@ def _online_actor_update_impl(buffer, agent, pop, actor_optimizer, log_alphas, b
             _ops.mlp_backward(ca, i * N, N, XPI, B, h1c, h2c, dq, ldx=S + A, want_dw=False, dx=dxg, lddx=S + A)
             L.sum_groups(dxg.data_ptr(), N, B, S + A, S, A, da.data_ptr(), _lib.stream_ptr())
         if parallel.is_sharded():
-            parallel.all_reduce_sum_(da)
+            parallel.all_reduce_sum_(da, site="actor_da")
         O = aa.O
         dout = torch.empty((1, B, O), dtype=torch.float32, device=dev)
         if agent.deterministic:

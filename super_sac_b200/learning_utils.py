@@ -532,8 +532,7 @@ def compute_td_targets(logs, replay_dict, agent, target_agent, ensemble_idx, ens
     elif parallel.is_sharded():
         # every rank evaluates its own target critics and all-gathers the [N_global, B] values; the subset-min is then
         # identical on every rank
-        q_all = parallel.all_gather_q(_critic_values(target_agent, i * N, N, X1, B))
-        q_t = q_all.index_select(0, net_index.long())
+        q_t = parallel.all_gather_q(_critic_values(target_agent, i * N, N, X1, B), site="target_q", select=net_index)
     else:
         q_t = _critic_values(target_agent, i * N, ensemble_n, X1, B, net_index=net_index)
     _mark("target critics Q(s1, a1)")

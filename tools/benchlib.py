@@ -162,15 +162,16 @@ class Workload:
     constructor calls main.py:188-244 / :321 makes, then ``step(k)`` = one update of that config as the reference's
     training loop runs it (main.py:380-414 online, :456-477 offline)."""
 
-    def __init__(self, pkg, name, device, seed=0, buffer_size=None, fill_on_device=False):
+    def __init__(self, pkg, name, device, seed=0, buffer_size=None, fill_on_device=False, overrides=None, torch_seed=None):
         import copy
 
         cfg = self.cfg = dict(CONFIGS[name])
+        cfg.update(overrides or {})   # e.g. this rank's share of the ensemble when it is sharded over the GPUs
         self.name, self.pkg, self.device = name, pkg, torch.device(device)
         ours = pkg.__name__ == "super_sac_b200"
         if ours:
             pkg.manual_seed(seed)
-        torch.manual_seed(seed)
+        torch.manual_seed(seed if torch_seed is None else torch_seed)
         IdentityEncoder, PixelEncoder = _encoders(pkg)
         E, N, S, A, H, B = cfg["E"], cfg["N"], cfg["S"], cfg["A"], cfg["H"], cfg["B"]
         pixels = cfg.get("pixels")

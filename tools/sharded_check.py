@@ -135,7 +135,7 @@ def run_sunrise(agent, target, buf, draws, members, B, N, cfg):
 
 def sunrise_check(rank, world, dev):
     """SUNRISE members sharded over the ranks == the single-GPU ensemble, member by member."""
-    E, N, S, A, H, B, nbuf = 3, 2, 17, 6, 64, 256, 4096
+    E, N, S, A, H, B, nbuf = max(3, world), 2, 17, 6, 64, 256, 4096
     cfg = dict(critic_lr=3e-4, actor_lr=3e-4)
     rng = np.random.default_rng(1)   # identical on every rank
     s = rng.standard_normal((nbuf, S), dtype=np.float32); a = rng.uniform(-1, 1, (nbuf, A)).astype(np.float32)
