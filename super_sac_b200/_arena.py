@@ -48,10 +48,20 @@ class MLPArena:
             off += G * per_net[n]
             off = (off + _ALIGN - 1) // _ALIGN * _ALIGN
         self.numel = off
-        self.flat = torch.zeros(off, dtype=torch.float32, device=device)
-        self.grad = torch.zeros(off, dtype=torch.float32, device=device)
+        # Tail padding (never part of `numel`): keeps the TMA boxes of the last net's matrices inside the allocation even
+        # when the arena is the last thing in its cudaMalloc block (csrc/ssac_mlp_tc.cu make_map explains what was
+        # measured: a tensor map must not declare an extent that leaves mapped memory).
+        self._pad = 128 * max(H, D) + 1024
+        self.flat = self._alloc(device)
+        self.grad = self._alloc(device)
         self.modules = []
         self._make_views()
+
+    def _alloc(self, device, like=None):
+        store = torch.zeros(self.numel + self._pad, dtype=torch.float32, device=device)
+        if like is not None:
+            store[: self.numel].copy_(like)
+        return store[: self.numel]
 
     def _make_views(self):
         self.p = {}
@@ -90,8 +100,8 @@ class MLPArena:
 
     def to(self, device):
         if torch.device(device) != self.flat.device:
-            self.flat = self.flat.to(device)
-            self.grad = self.grad.to(device)
+            self.flat = self._alloc(device, like=self.flat)
+            self.grad = self._alloc(device, like=self.grad)
             self._make_views()
             self._rebind()
         return self

@@ -84,6 +84,17 @@ class _Lib:
                 setattr(self, name[len("ssac_"):], fn)
         if missing:
             raise SsacError(f"libssac_b200.so does not export: {missing}")
+        # debugging switches (results never depend on them)
+        if os.environ.get("SSAC_NO_PDL"):
+            self.cdll.ssac_set_pdl(0)
+        if os.environ.get("SSAC_NO_OVERLAP"):
+            self.cdll.ssac_set_overlap(0)
+        if os.environ.get("SSAC_NO_ROWS"):
+            self.cdll.ssac_set_rows_enabled(0)
+        if os.environ.get("SSAC_NO_TMA"):
+            self.cdll.ssac_set_tma_enabled(0)
+        if os.environ.get("SSAC_NO_FUSED"):
+            self.cdll.ssac_set_fused_forward(0)
 
     def _checked(self, fn, name):
         last_error = self.cdll.ssac_last_error

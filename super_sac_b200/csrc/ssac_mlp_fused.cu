@@ -554,10 +554,10 @@ int launch_mlp3_fused(const float* W1, const float* b1, const float* W2, const f
   if (keep_hidden && (!h1 || !h2)) return -1;
   fz::FusedFwd q;
   memset(&q, 0, sizeof(q));
-  if (!tc::make_map(W2, H, (int64_t)H * H, H, H, false, &q.tmW2)) return -1;
+  if (!tc::make_map(W2, H, (int64_t)H * H, H, H, false, &q.tmW2, G)) return -1;
   if (keep_hidden) {
-    if (!tc::make_map(h1, H, (int64_t)B * H, H, B, false, &q.tmH1)) return -1;
-    if (!tc::make_map(h2, H, (int64_t)B * H, H, B, false, &q.tmH2)) return -1;
+    if (!tc::make_map(h1, H, (int64_t)B * H, H, B, false, &q.tmH1, G)) return -1;
+    if (!tc::make_map(h2, H, (int64_t)B * H, H, B, false, &q.tmH2, G)) return -1;
   }
   // column slices per 128-row tile: 4 while the grid fits the SMs (and the DSMEM landing zone fits: O <= 12), else 2
   const int tiles = (B + fz::FM - 1) / fz::FM;

@@ -22,6 +22,7 @@
 //            (the only MN-major layout for 32-bit operands)                  + ((((m%32)/8) ^ (k%4))*32) + (m%8)*4
 #include <cuda.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "ssac_tc_prims.cuh"
@@ -439,10 +440,26 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
+// cuMemGetAddressRange: the [base, base + size) of the allocation (cudaMalloc block / torch allocator segment) holding p
+typedef CUresult (*AddrRangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
+AddrRangeFn addr_range_fn() {
+  static AddrRangeFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<AddrRangeFn>(ptr);
+  }
+  return fn;
+}
+
 struct MapKey {
-  const void* base; int64_t ld, gs; int inner, outer; bool mn;
+  const void* base; int64_t ld, gs; int inner, outer; bool mn; int64_t ngroups;
   bool operator==(const MapKey& o) const {
-    return base == o.base && ld == o.ld && gs == o.gs && inner == o.inner && outer == o.outer && mn == o.mn;
+    return base == o.base && ld == o.ld && gs == o.gs && inner == o.inner && outer == o.outer && mn == o.mn && ngroups == o.ngroups;
   }
 };
 struct MapEntry { MapKey key; CUtensorMap map; };
@@ -456,17 +473,48 @@ std::vector<MapEntry>& map_cache() {
 namespace tc {
 // 3-D map (inner, outer, group) over a row-major fp32 matrix stack.  K-major operands: inner = k, outer = rows,
 // box 32 x 128, SWIZZLE_128B.  MN-major operands: inner = cols, outer = k, box 32 x 32, SWIZZLE_128B_ATOM_32B.
-bool make_map(const float* base, int64_t ld, int64_t gs, int inner, int outer, bool mn, CUtensorMap* out) {
+//
+// MEASURED on B200 (tools/probes/tma_tail_probe.cu, profiles/r2_03_tma_tail_probe.log): when a box hangs over the
+// tensor's bounds (rows >= outer or columns >= inner, zero-filled as they should be) the TMA unit still touches global
+// addresses up to ~64 KB behind the box -- and FAULTS if they are unmapped -- whenever the tensor map DECLARES an extent
+// that reaches there.  A group dimension declared "large enough" (this code used 65536) over a stack that ends at the
+// tail of its allocation did exactly that.  With the declared extent inside mapped memory no configuration faulted, at
+// any distance from the end of the mapping; boxes that do not hang over never fault either.  Hence:
+//   * the group count of a map is clamped to the groups that fit the allocation holding `base` (cuMemGetAddressRange),
+//     so the declared extent never leaves it; `groups` (the groups this launch addresses without a net subset) must fit;
+//   * if the allocation cannot be queried the map is only handed out for boxes that cannot hang over.
+// Every TMA operand has a register-staged path for a refused map.
+bool make_map(const float* base, int64_t ld, int64_t gs, int inner, int outer, bool mn, CUtensorMap* out, int groups) {
   if (!encode_fn()) return false;
   if ((((uintptr_t)base) & 15) != 0 || (ld & 3) != 0 || ld <= 0 || (gs & 3) != 0 || inner <= 0 || outer <= 0) return false;
-  MapKey key{base, ld, gs, inner, outer, mn};
+  const int64_t box_rows = mn ? 32 : 128;
+  int64_t ngroups = gs > 0 ? 65536 : 1;
+  bool known = false;
+  if (AddrRangeFn range = addr_range_fn()) {
+    CUdeviceptr abase = 0;
+    size_t asize = 0;
+    if (range(&abase, &asize, (CUdeviceptr)(uintptr_t)base) == CUDA_SUCCESS && asize > 0) {
+      const int64_t room = (int64_t)((uintptr_t)abase + asize - (uintptr_t)base) / 4;      // floats from base to the end
+      const int64_t one = (int64_t)(outer - 1) * ld + inner;                                // footprint of one group
+      if (room < one) return false;
+      if (gs > 0) ngroups = std::min<int64_t>(ngroups, (room - one) / gs + 1);
+      known = true;
+    }
+  }
+  static const bool dbg = getenv("SSAC_DEBUG_MAPS") != nullptr;
+  if (dbg)
+    fprintf(stderr, "[make_map] base %p ld %lld gs %lld inner %d outer %d mn %d groups %d: declared groups %lld (%s)\n",
+            (const void*)base, (long long)ld, (long long)gs, inner, outer, (int)mn, groups, (long long)ngroups,
+            known ? "allocation known" : "allocation unknown");
+  if (!known && (inner % 32 != 0 || outer % box_rows != 0)) return false;
+  if (gs > 0 && ngroups < groups) return false;
+  MapKey key{base, ld, gs, inner, outer, mn, ngroups};
   auto& cache = map_cache();
   for (auto& e : cache)
     if (e.key == key) { *out = e.map; return true; }
-  const cuuint64_t ngroups = gs > 0 ? 65536 : 1;
-  cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)outer, ngroups};
+  cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)outer, (cuuint64_t)ngroups};
   cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)(gs > 0 ? gs : (int64_t)outer * ld) * 4};
-  cuuint32_t box[3] = {32, (cuuint32_t)(mn ? 32 : 128), 1};
+  cuuint32_t box[3] = {32, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = encode_fn()(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -510,11 +558,11 @@ int launch_gemm_tc(int layout, const GemmP& p, int G, cudaStream_t s, const char
   if (g_tma_enabled && p.K > 0) {
     const bool a_mn = layout == L_TN, b_mn = layout != L_NT;
     // group strides are baked into the maps; base pointers are the group-0 matrices
-    if (a_mn) q.a_tma = make_map(p.A, p.lda, p.a_gs, p.M, p.K, true, &q.tmA);
-    else q.a_tma = make_map(p.A, p.lda, p.a_gs, p.K, p.M, false, &q.tmA);
-    if (b_mn) q.b_tma = make_map(p.Bm, p.ldb, p.b_gs, p.N, p.K, true, &q.tmB);
-    else q.b_tma = make_map(p.Bm, p.ldb, p.b_gs, p.K, p.N, false, &q.tmB);
-    if (!p.mask && !p.extra && !p.accumulate) q.c_tma = make_map(p.C, p.ldc, p.c_gs, p.N, p.M, false, &q.tmC);
+    if (a_mn) q.a_tma = make_map(p.A, p.lda, p.a_gs, p.M, p.K, true, &q.tmA, G);
+    else q.a_tma = make_map(p.A, p.lda, p.a_gs, p.K, p.M, false, &q.tmA, G);
+    if (b_mn) q.b_tma = make_map(p.Bm, p.ldb, p.b_gs, p.N, p.K, true, &q.tmB, G);
+    else q.b_tma = make_map(p.Bm, p.ldb, p.b_gs, p.K, p.N, false, &q.tmB, G);
+    if (!p.mask && !p.extra && !p.accumulate) q.c_tma = make_map(p.C, p.ldc, p.c_gs, p.N, p.M, false, &q.tmC, G);
   }
   if (p.a_kscale && !(layout == L_TN && q.a_tma))
     return fail(SSAC_E_UNSUPPORTED, "tcgen05 GEMM: a per-k scale needs a TMA-addressable transposed A operand");

@@ -240,7 +240,7 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t* r) {
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // host side (ssac_mlp_tc.cu): cached 3-D tensor maps (inner, outer, group) over row-major fp32 matrix stacks
-bool make_map(const float* base, int64_t ld, int64_t gs, int inner, int outer, bool mn, CUtensorMap* out);
+bool make_map(const float* base, int64_t ld, int64_t gs, int inner, int outer, bool mn, CUtensorMap* out, int groups = 1);
 bool tma_enabled();
 
 }  // namespace tc

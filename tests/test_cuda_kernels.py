@@ -825,3 +825,18 @@ def test_acting_path_kernels_match_oracle(envs):
     assert float((srt[0] - srt[1]).min()) > 1e-4, "test data: UCB scores too close to call"
     want = cands[best, torch.arange(envs)].numpy()
     gu.assert_close(got, want[0] if envs == 1 else want, 1e-5, 2e-6, "UCB sample_action")
+
+
+@pytest.mark.parametrize("which", ["arena_tail", "h_tail"])
+def test_tma_operands_at_allocation_tail(which):
+    """TMA operands that end exactly at the end of their cudaMalloc block (regression: the box hanging over the tensor's
+    end faulted on B200 although those rows are out of bounds for the tensor map) -- tests/tail_alloc_check.py."""
+    import os
+    import subprocess
+    import sys
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, PYTORCH_NO_CUDA_MEMORY_CACHING="1")
+    out = subprocess.run([sys.executable, os.path.join(here, "tail_alloc_check.py"), which], env=env, capture_output=True,
+                         text=True, timeout=300)
+    assert out.returncode == 0 and f"ok {which}" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
