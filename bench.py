@@ -177,8 +177,38 @@ def run_gpu_arm(args, cfg, rank, world, local_rank):
     def gstep(k):
         (with_pol if k % delay == 0 else no_pol)()
 
-    for k in range(warm):
-        gstep(k)
+    # The reference's training loop runs UTD updates back to back per environment step (main.py:380-414; REDQ: 20).  Such
+    # a block is captured as ONE graph in which the target side of update k+1 overlaps update k's backward / Adam
+    # (learning_utils.pipelined_updates: bit-identical to the sequential schedule, tests/test_cuda_update_parity.py).
+    utd = cfg.get("utd", 1)
+    block = None
+    if utd > 1 and utd % delay == 0 and g1 is not None and not args.no_pipeline:
+        from super_sac_b200 import learning_utils as lu
+
+        def utd_block():
+            with lu.pipelined_updates():
+                for u in range(utd):
+                    out = W.step(u)
+            return out
+
+        try:
+            block = graphed.GraphedCall(utd_block, warmup=1)
+            mode = "CUDA-graph replay of the UTD block (%d updates per graph, target side of update k+1 next to update k)" % utd
+        except Exception as e:  # noqa: BLE001
+            torch.cuda.synchronize()
+            block = None
+            mode += " (UTD block not capturable: %s)" % type(e).__name__
+
+    def run_steps(n):
+        k = 0
+        if block is not None:
+            for _ in range(n // utd):
+                block.replay()
+            k = n - n % utd
+        for j in range(k, n):
+            gstep(j)
+
+    run_steps(max(warm, utd if block is not None else 0))
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
@@ -186,8 +216,7 @@ def run_gpu_arm(args, cfg, rank, world, local_rank):
     torch.cuda.synchronize()
     with sampler.region():
         ev0.record()
-        for k in range(args.steps):
-            gstep(k)
+        run_steps(args.steps)
         ev1.record()
         torch.cuda.synchronize()
     if dist is not None:
@@ -198,7 +227,7 @@ def run_gpu_arm(args, cfg, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     value = world * args.steps / (ms * 1e-3)
-    glogs = g1.logs() if g1 is not None else {}
+    glogs = (block or g1).logs() if g1 is not None else {}
 
     # ---- e2e through the drop-in API with host inputs ---------------------------------------------
     e2e_steps = min(args.steps, 2000)
@@ -283,7 +312,7 @@ def run_gpu_arm(args, cfg, rank, world, local_rank):
     line = base_line(args, cfg, world)
     line.update({
         "value": value, "ms_per_step": ms / args.steps,
-        "run": {"mode": mode + (" of critic_update (+Polyak every %d. step)" % delay if delay > 1 else " of the update"),
+        "run": {"mode": mode + ("; update = critic_update (+Polyak every %d. step)" % delay if delay > 1 else " of the update"),
                 "parallelism": "1 learner" if world == 1 else f"{world} independent learner replicas (no data-path collective)",
                 "l2": "replay ring %.0f MB (random rows) vs 126 MB L2; parameters + moments are L2-resident by design" % ring_mb,
                 "impl": "ensemble MLP GEMMs: " + ssb.get_mlp_impl(),
@@ -491,18 +520,21 @@ def time_sharded(cfg, args, device, rank, world, dist):
 def time_full_sac_step(W, iters=30):
     """the full SAC step of main.py:380-543 -- UTD critic updates (+ their Polyak steps), then ONE actor
     update and ONE temperature update on the last batch -- captured as a single CUDA graph where possible."""
-    from super_sac_b200 import learning
+    import contextlib
+
+    from super_sac_b200 import learning, learning_utils as lu
 
     cfg = W.cfg
     utd = cfg.get("utd", 1)
 
     def full_step():
         rds = None
-        for u in range(utd):
-            _, rds = learning._critic_update_impl(**W.kw)
-            if u % cfg["target_delay"] == 0:
-                W.polyak()
-        return W.actor_and_alpha(rds)
+        with lu.pipelined_updates() if utd > 1 else contextlib.nullcontext():
+            for u in range(utd):
+                _, rds = learning._critic_update_impl(**W.kw)
+                if u % cfg["target_delay"] == 0:
+                    W.polyak()
+            return W.actor_and_alpha(rds)
 
     step, mode, _ = graph_or_eager(full_step)
     ms = bl.timed_events(lambda k: step(), iters, 3)
@@ -556,6 +588,7 @@ def main():
     ap.add_argument("--mlp-impl", default="tcgen05", choices=["tcgen05", "ffma"])
     ap.add_argument("--no-overlap", action="store_true", help="serialise the independent branches of the update (A/B switch)")
     ap.add_argument("--no-pdl", action="store_true", help="plain stream-ordered launches instead of programmatic dependent launch")
+    ap.add_argument("--no-pipeline", action="store_true", help="one graph per update instead of the pipelined UTD block (A/B switch)")
     ap.add_argument("--skip-secondary", action="store_true", help="headline config only (no other configs / kernels / GPU-reference arm)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]

@@ -6,6 +6,7 @@ launch, the backward is explicit (no autograd tape on the ensemble), Adam is one
 arena, and the logged scalars come back with a single device->host copy.  The caller still owns the optimizer
 objects, ``log_alphas`` and the target agent exactly as main.py:188-244 / :321 builds them.
 """
+import contextlib
 import random
 
 import torch
@@ -76,7 +77,22 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
     L, stream = _lib.lib(), _lib.stream_ptr()
     E, N, B = agent.ensemble_size, agent.num_critics, batch_size
     S, A = lu._dims(agent)
-    logs = _logs.DeviceLogs(dev, zeroed=False)   # cleared by the first member's draw kernel
+    # Software pipelining across consecutive updates (lu.pipelined_updates): the target side of this update runs on the
+    # front stream, which is NOT joined at the end of the update -- the next update's target side starts next to this
+    # update's backward / Adam.  One member, plain Bellman weights, uniform sampling, no trainable encoder.
+    pipe = lu.pipeline()
+    if pipe is not None and (E != 1 or per or update_priorities or weight_type is not None or _encoder_trainable(agent) or
+                             parallel.is_sharded() or parallel.members_sharded() or lu.side_stream(dev) is None or
+                             pipe.device != dev):
+        lu.pipeline_barrier()
+        pipe = None
+    # (the log buffer is cleared by the first member's draw kernel, i.e. on the front stream when pipelined: it then has to
+    # come from that stream's allocator pool -- a block recycled from the caller's stream could still be in use by the
+    # previous update's backward -- and must not be recycled before the block ends)
+    with (torch.cuda.stream(pipe.front) if pipe is not None else contextlib.nullcontext()):
+        logs = _logs.DeviceLogs(dev, zeroed=False)
+    if pipe is not None:
+        pipe.keep.append(logs)
     loss_all, loss_slot = logs.slots(2 * E)   # per member: {loss contribution, mean td error of its last net}
     opt = _arena.FlatAdam.attach(critic_optimizer, ca)
     if parallel.is_sharded() and (E != 1 or dr3_coeff > 0 or critic_clip):
@@ -121,7 +137,7 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
             presampled.append((draws, rd))
     replay_dicts = [None] * E
 
-    def member_step(i, draws, rd, lane):
+    def member_step(i, draws, rd, lane, batch_ready=None):
         loss_v = loss_all[2 * i:2 * i + 2]
         lu._mark("replay gather")
         o, a, *_ = rd["primary_batch"]
@@ -137,6 +153,9 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
         # The online critics' hidden layers do not depend on the TD target: run them on a second stream next to the
         # target actor -> target critics chain (their grids leave most SMs idle), join before the output layer + loss.
         side = None if need_ds else lu.side_stream(dev, lane)
+        piped = pipe is not None and side is not None
+        if pipe is not None and not piped:
+            lu.pipeline_barrier()
         # With scalar-output critics the TD-error seed factors out of the data-gradient chain (ssac_mlp_backward_pre /
         # _post), so that chain runs on the second stream as well, before the TD target exists; after the loss only the
         # three weight-gradient reductions remain.
@@ -144,16 +163,28 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
         bws = _ops._bwd_ws(N, B, ca.H, dev) if split_bwd else None
         if side is not None:
             main = torch.cuda.current_stream(dev)
-            side.wait_stream(main)
+            if piped:
+                # the online branch stays on the caller's stream (nothing else runs there before the loss); it needs the
+                # batch, which the front stream gathered
+                online = main
+                main.wait_event(batch_ready)
+            else:
+                online = side
+                side.wait_stream(main)
             L.critic_forward_loss(W1, b1, W2, b2, W3, b3, N, ca.D, ca.H, X.data_ptr(), S + A, B, h1.data_ptr(),
                                   h2.data_ptr(), None, None, None, None, None, 0, En, 0, None, None, 1,
-                                  None, 0, None, None, None, None, 0.0, None, None, 0, side.cuda_stream)
+                                  None, 0, None, None, None, None, 0.0, None, None, 0, online.cuda_stream)
             if split_bwd:
-                L.mlp_backward_pre(W2, W3, N, ca.H, B, h1.data_ptr(), h2.data_ptr(), bws.data_ptr(), 0, side.cuda_stream)
-        td_target, (s1, a1) = lu.compute_td_targets(
-            logs=logs, replay_dict=rd, agent=agent, target_agent=target_agent, log_alphas=log_alphas, ensemble_idx=i,
-            ensemble_n=target_critic_ensemble_n, pop=pop, gamma=gamma, random_process=random_process,
-            noise_clip=noise_clip, _draws=draws, _fuse_into_loss=side is not None)
+                L.mlp_backward_pre(W2, W3, N, ca.H, B, h1.data_ptr(), h2.data_ptr(), bws.data_ptr(), 0, online.cuda_stream)
+        with (torch.cuda.stream(pipe.front) if piped else contextlib.nullcontext()):
+            td_target, (s1, a1) = lu.compute_td_targets(
+                logs=logs, replay_dict=rd, agent=agent, target_agent=target_agent, log_alphas=log_alphas, ensemble_idx=i,
+                ensemble_n=target_critic_ensemble_n, pop=pop, gamma=gamma, random_process=random_process,
+                noise_clip=noise_clip, _draws=draws, _fuse_into_loss=side is not None)
+            if piped:
+                target_ready = torch.cuda.Event()
+                target_ready.record(pipe.front)
+                pipe.keep.append((draws, rd, td_target, getattr(td_target, "_ssac_pending", None), s1, a1))
         tdp = getattr(td_target, "_ssac_pending", None)   # TD target evaluated inside the loss kernel
         w = lu.compute_backup_weights(logs=logs, replay_dict=rd, agent=agent, target_agent=target_agent,
                                       weight_type=weight_type, weight_temp=weighted_bellman_temp, batch_size=B,
@@ -163,7 +194,9 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
         imp = rd["imp_weights"]
         imp_ptr = imp.float().contiguous() if per else None  # per=False: ones(1), i.e. no weighting (main.py:401)
         n_total = parallel.n_global() if parallel.is_sharded() else 0   # sharded critics: normalise by the global N
-        if side is not None:
+        if piped:
+            main.wait_event(target_ready)
+        elif side is not None:
             main.wait_stream(side)
         # N critic forwards + loss value + seed gradient dL/dq in one entry point (loss seed fused into the head kernel)
         L.critic_forward_loss(W1, b1, W2, b2, W3, b3, N, ca.D, ca.H, X.data_ptr(), S + A, B, h1.data_ptr(), h2.data_ptr(),
@@ -209,6 +242,17 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
     for i in range(E):
         if presampled is not None:
             draws, rd = presampled[i]
+        elif pipe is not None:
+            pipe.front_wait_dep(caller)
+            with torch.cuda.stream(pipe.front):
+                draws = lu.draw_for_critic_member(buffer, agent, B, target_critic_ensemble_n, random_process, per,
+                                                  zero=logs.take_unzeroed())
+                rd = lu.sample_move_and_augment(buffer=buffer, batch_size=B, augmenter=augmenter, aug_mix=aug_mix, per=per,
+                                                _idx=draws["idx"])
+                batch_ready = torch.cuda.Event()
+                batch_ready.record(pipe.front)
+            member_step(i, draws, rd, 0, batch_ready)
+            continue
         else:
             draws = lu.draw_for_critic_member(buffer, agent, B, target_critic_ensemble_n, random_process, per,
                                               zero=logs.take_unzeroed())
@@ -301,6 +345,7 @@ def _online_actor_update_impl(buffer, agent, pop, actor_optimizer, log_alphas, b
                               use_baseline=False):
     if discrete or use_baseline:
         raise NotImplementedError("discrete actions / advantage baselines are out of scope")
+    lu.pipeline_barrier()
     aa, ca = agent._actor_arena, agent._critic_arena
     dev = aa.device
     _ops.check_cuda(aa.flat)
@@ -437,6 +482,7 @@ def alpha_update(buffer, agent, optimizers, batch_size, log_alphas, augmenter, a
                  premade_replay_dicts, discrete):
     if discrete:
         raise NotImplementedError("discrete actions are out of scope")
+    lu.pipeline_barrier()
     dev = agent._actor_arena.device
     L, stream = _lib.lib(), _lib.stream_ptr()
     E, B = agent.ensemble_size, batch_size
@@ -501,6 +547,7 @@ def offline_actor_update(buffer, agent, actor_optimizer, encoder_optimizer, batc
         raise NotImplementedError("action invariance regulariser (lambda = 0 in every shipped config) is out of scope")
     if agent.deterministic:
         raise NotImplementedError("filtered behaviour cloning needs a stochastic actor")
+    lu.pipeline_barrier()
     aa = agent._actor_arena
     dev = aa.device
     _ops.check_cuda(aa.flat)

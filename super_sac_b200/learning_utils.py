@@ -5,6 +5,7 @@ compute_backup_weights (:357-398), filtered_bc_loss (:241-269), adjust_prioritie
 (:95-106) and GaussianExplorationNoise (:18-66).  Every tensor stays in HBM; each function enqueues a handful of
 kernels from libssac_b200 on the current stream and never synchronises (logged scalars go through _logs.DeviceLogs).
 """
+import contextlib
 import math
 import random
 
@@ -98,12 +99,16 @@ def soft_update(target, source, tau):
         g0, g1 = target._g0, target._g0 + target.num_critics
         assert (source._g0, source.num_critics) == (target._g0, target.num_critics)
         _ops.polyak_ranges(ta.flat, sa.flat, ta.range_table(g0, g1), tau)
+        if _pipeline is not None:
+            _pipeline.note_polyak(torch.cuda.current_stream(_pipeline.device))
         return
     sig, table, max_numel = _multi_table(target, source)
     if table is None:
         return
     _ops.check_cuda(table)
     _lib.lib().polyak_multi(table.data_ptr(), len(sig), max_numel, float(tau), _lib.stream_ptr())
+    if _pipeline is not None:
+        _pipeline.note_polyak(torch.cuda.current_stream(_pipeline.device))
 
 
 def hard_update(target, source):
@@ -170,6 +175,94 @@ def member_stream(device, lane):
     if st is None:
         st = _member_streams[(device, lane)] = torch.cuda.Stream(device=device)
     return st
+
+
+# ---- software pipelining of consecutive critic updates ---------------------------------------------------------------
+# The only true recurrence between two critic updates runs through the ONLINE critics' parameters (forward -> loss ->
+# backward -> Adam -> next forward).  The target side of update k+1 -- index / noise / subset draws, replay gather,
+# target actor, target critics -- reads the replay ring, the actor and the TARGET critics only, so inside a
+# ``pipelined_updates()`` block it runs on its own stream ("front") next to update k's backward and Adam, ordered by
+# events exactly where data flows: the batch before the online forward, the target values before the loss, a Polyak step
+# before the next target-critic forward.  Same kernels, same draw order, same numbers as the sequential schedule; it is
+# the UTD loop of main.py:380-414 (20 back-to-back updates for REDQ) that offers the overlap.
+class _Pipeline:
+    def __init__(self, device):
+        self.device = device
+        self.front = _front_stream(device)
+        self.dep = None          # main-stream event the front has to wait for before it reads actor / ring again
+        self.polyak = None       # main-stream event of the latest Polyak step (the target critics' parameters)
+        self.keep = []           # front-allocated tensors that main-stream kernels read: alive until the block ends
+        self.needs_order = False  # a barrier happened: the front's next work goes behind the caller's stream as it is then
+
+    def order_front_after_main(self, main):
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self.dep = ev
+
+    def front_wait_dep(self, main):
+        if self.needs_order:
+            self.order_front_after_main(main)
+            self.needs_order = False
+        if self.dep is not None:
+            self.front.wait_event(self.dep)
+            self.dep = None
+
+    def front_wait_polyak(self):
+        if self.polyak is not None:
+            self.front.wait_event(self.polyak)
+            self.polyak = None
+
+    def note_polyak(self, main):
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self.polyak = ev
+
+
+_pipeline = None
+_front_streams = {}
+
+
+def _front_stream(device):
+    device = torch.device(device)
+    st = _front_streams.get(device)
+    if st is None:
+        st = _front_streams[device] = torch.cuda.Stream(device=device)
+    return st
+
+
+def pipeline():
+    return _pipeline
+
+
+@contextlib.contextmanager
+def pipelined_updates(device=None):
+    """Consecutive ``learning.critic_update`` (+ ``soft_update``) calls inside this block overlap as described above.
+    Meant to be captured as ONE CUDA graph (graphed.GraphedCall) or run eagerly; every other update entry point joins the
+    two streams first (``pipeline_barrier``).  Do not push to / re-prioritise the buffer inside the block."""
+    global _pipeline
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if _pipeline is not None or not _lib.lib().get_overlap():
+        yield None
+        return
+    p = _Pipeline(device)
+    p.order_front_after_main(torch.cuda.current_stream(device))
+    _pipeline = p
+    try:
+        yield p
+    finally:
+        _pipeline = None
+        torch.cuda.current_stream(device).wait_stream(p.front)
+        p.keep.clear()
+
+
+def pipeline_barrier():
+    """Join the front stream into the caller's stream and order its next work after the caller's (an entry point that
+    changes what the front reads -- actor update, buffer writes -- or draws random numbers on the caller's stream)."""
+    p = _pipeline
+    if p is not None:
+        main = torch.cuda.current_stream(p.device)
+        main.wait_stream(p.front)
+        p.needs_order = True
 
 
 # ------------------------------------------------------------------------------------------------
@@ -511,6 +604,8 @@ def compute_td_targets(logs, replay_dict, agent, target_agent, ensemble_idx, ens
     # but measured SLOWER than the two tensor-core launches it replaces at B = 256 (35 vs 31 us back to back, and it takes
     # SMs away from the online critics' branch): off unless TARGET_CHAIN is set (kept for small batches / A-B runs)
     want_chain = TARGET_CHAIN and not parallel.is_sharded()
+    if want_chain and _pipeline is not None:
+        _pipeline.front_wait_polyak()
     if _draws is not None:   # critic_update drew indices, policy noise and the subset in ONE launch
         net_index = _draws["subset"]
         pol = _policy_sample(agent, i, X1, B, S, A, random_process, noise_clip,
@@ -527,6 +622,8 @@ def compute_td_targets(logs, replay_dict, agent, target_agent, ensemble_idx, ens
         else:
             pol = _policy_sample(agent, i, X1, B, S, A, random_process, noise_clip)
             _rng.source().subsets(net_index, pool, ensemble_n)
+    if _pipeline is not None:
+        _pipeline.front_wait_polyak()   # the target critics' parameters: the only thing this side reads that Polyak writes
     if pol.get("qt") is not None:
         q_t = pol["qt"]
     elif parallel.is_sharded():

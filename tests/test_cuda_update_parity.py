@@ -408,6 +408,86 @@ def test_auto_graph_replay_equals_eager():
         gu.assert_close(float(l1[k]), float(l0[k]), 1e-5, 1e-7, f"log {k}")
 
 
+@pytest.mark.parametrize("captured", [False, True], ids=["eager", "graph"])
+def test_pipelined_update_block_equals_sequential(captured):
+    """lu.pipelined_updates(): the target side of update k+1 runs next to update k's backward / Adam on its own stream.
+    Same kernels, same draw order, event-ordered where data flows => a block of UTD updates (+ Polyak every 2nd, + one
+    actor and one temperature update, as main.py:380-543 runs them) must reproduce the sequential schedule bit for bit."""
+    import copy
+    from itertools import chain
+
+    import cuda_util as cu
+    import super_sac_b200 as ssb
+    from super_sac_b200 import augmentations, graphed, learning, learning_utils as lu, nets
+
+    def build():
+        ssb.manual_seed(5)
+        torch.manual_seed(5)
+        agent = ssb.Agent(act_space_size=6, encoder=cu.IdentityEncoder(17), actor_network_cls=nets.mlps.ContinuousStochasticActor,
+                          critic_network_cls=nets.mlps.ContinuousCritic, ensemble_size=1, num_critics=10, hidden_size=256,
+                          auto_rescale_targets=False, log_std_low=-5.0, log_std_high=2.0)
+        agent.to("cuda")
+        target = copy.deepcopy(agent)
+        rng = np.random.default_rng(0)
+        n = 4096
+        buf = ssb.replay.ReplayBuffer(n, device="cuda")
+        buf.load_experience({"obs": rng.standard_normal((n, 17), dtype=np.float32)}, rng.uniform(-1, 1, (n, 6)).astype(np.float32),
+                            rng.standard_normal(n, dtype=np.float32), {"obs": rng.standard_normal((n, 17), dtype=np.float32)},
+                            rng.uniform(size=n) < 0.05)
+        c_opt = torch.optim.Adam(chain(*(c.parameters() for c in agent.critics)), lr=3e-4)
+        a_opt = torch.optim.Adam(chain(*(a.parameters() for a in agent.actors)), lr=3e-4)
+        e_opt = torch.optim.Adam(agent.encoder.parameters(), lr=1e-4)
+        la = [torch.tensor([-2.3], device="cuda", requires_grad=True)]
+        al_opt = [torch.optim.Adam([la[0]], lr=1e-4, betas=(0.5, 0.999))]
+        aug = augmentations.AugmentationSequence([augmentations.IdentityAug(256)])
+
+        def block(pipelined):
+            ctx = lu.pipelined_updates() if pipelined else contextlib.nullcontext()
+            with ctx:
+                for k in range(6):
+                    logs, rds = learning._critic_update_impl(
+                        buffer=buf, agent=agent, target_agent=target, critic_optimizer=c_opt, encoder_optimizer=e_opt,
+                        log_alphas=la, batch_size=256, gamma=0.99, critic_clip=None, encoder_clip=None,
+                        target_critic_ensemble_n=2, weighted_bellman_temp=None, weight_type=None, pop=False, augmenter=aug,
+                        encoder_lambda=0.0, random_process=None, noise_clip=None, aug_mix=0.0)
+                    if k % 2 == 0:
+                        lu.soft_update(target.critics[0], agent.critics[0], 0.005)
+                learning._online_actor_update_impl(
+                    buffer=buf, agent=agent, pop=False, actor_optimizer=a_opt, log_alphas=la, batch_size=256, clip=None,
+                    random_process=None, noise_clip=None, augmenter=aug, aug_mix=0.0, premade_replay_dicts=rds)
+                learning.alpha_update(buffer=buf, agent=agent, optimizers=al_opt, batch_size=256, log_alphas=la, augmenter=aug,
+                                      aug_mix=0.0, target_entropy=-6.0, premade_replay_dicts=rds, discrete=False)
+            return logs
+
+        return agent, target, la, block
+
+    import contextlib
+
+    a0, t0, la0, block0 = build()
+    for _ in range(5):
+        l0 = block0(False)
+    l0 = dict(l0.fetch(keep=True)) if hasattr(l0, "fetch") else dict(l0)
+    a1, t1, la1, block1 = build()
+    if captured:
+        g = graphed.GraphedCall(lambda: block1(True), warmup=2)   # two eager pipelined blocks, then three replays
+        for _ in range(3):
+            g.replay()
+        l1 = g.logs()
+    else:
+        for _ in range(5):
+            l1 = block1(True)
+        l1 = dict(l1.fetch(keep=True)) if hasattr(l1, "fetch") else dict(l1)
+    torch.cuda.synchronize()
+    assert lu.pipeline() is None
+    assert torch.equal(a0._critic_arena.flat, a1._critic_arena.flat)
+    assert torch.equal(t0._critic_arena.flat, t1._critic_arena.flat)
+    assert torch.equal(a0._actor_arena.flat, a1._actor_arena.flat)
+    assert torch.equal(la0[0], la1[0])
+    assert set(l0.keys()) == set(l1.keys())
+    for k in l0:
+        gu.assert_close(float(l1[k]), float(l0[k]), 1e-5, 1e-7, f"log {k}")
+
+
 def test_module_views_and_kernels_agree_on_the_acting_path():
     """The nn.Modules the reference API exposes (Agent.forward / sample_action, critics[i](s, a)) are views into the
     parameter arenas the kernels read: after a fused update both must see the same parameters, and the PyTorch forward of
