@@ -93,8 +93,10 @@ def count_launches(fn, fused=False):
             elif name == "mlp_backward":
                 want_dw = a[17] is not None   # dz2, gW3, gW2, dz1, gW1 (+dx): 5 launches with weight grads, 2 (+1) without
                 counter["n"] += (5 if want_dw else 2) + (1 if a[24] is not None else 0)
-            elif name in ("mlp_backward_pre", "mlp_backward_post"):
-                counter["n"] += 2
+            elif name == "mlp_backward_pre":
+                counter["n"] += 1    # u GEMM (v = W3 .* (h2 > 0) is generated while its A tiles are staged)
+            elif name == "mlp_backward_post":
+                counter["n"] += 2    # gW2 GEMM, gW1 / gb1 / gW3 / gb3 reduction
             else:
                 counter["n"] += mult
             return f(*a)
@@ -197,6 +199,7 @@ def run_gpu_arm(args, cfg, rank, world, local_rank):
         except Exception as e:  # noqa: BLE001
             torch.cuda.synchronize()
             block = None
+            print("[bench] UTD block not capturable: %s: %s" % (type(e).__name__, str(e)[:300]), file=sys.stderr, flush=True)
             mode += " (UTD block not capturable: %s)" % type(e).__name__
 
     def run_steps(n):

@@ -46,7 +46,7 @@ int ssac_polyak(float* target_dev, const float* source_dev, int64_t n, double ta
 int ssac_polyak_multi(const uint64_t* table_dev, int n_tensors, int64_t max_numel, double tau, void* stream);
 
 /* ---- optimiser: torch.optim.Adam as configured in main.py:188-239 (coupled L2, no amsgrad) -------- */
-/* ctl_dev: int32[2] = {step, blocks_done}; the kernel reads step, uses t = step+1 for the bias
+/* ctl_dev: int32[2] (int32[8] when shared with ssac_mlp_backward_post_adam) = {step, blocks_done}; the kernel reads step, uses t = step+1 for the bias
  * corrections and the last block to finish stores step+1 (graph replays advance it).
  * gnorm_sq_dev (nullable): if given with max_norm > 0, grads are scaled by
  * min(1, max_norm/(sqrt(*gnorm_sq_dev)+1e-6)) (torch.nn.utils.clip_grad_norm_, learning.py:122-128) and,
@@ -168,15 +168,33 @@ int ssac_mlp_backward(const float* W1, const float* W2, const float* W3, const i
 
 /* Split backward of a scalar-output (critic) ensemble, impl 2, D <= 32.  With O == 1 the seed dq[g,b] = dL/dq factors
  * out of the data-gradient chain: dz2 = dq (x) v, dz1 = dq (x) u with v = W3 .* (h2 > 0), u = (v W2) .* (h1 > 0), neither
- * of which depends on the TD target.  _pre computes v and u into ws_dev (ssac_mlp_backward_ws floats: v then u) and can
- * run next to the target networks; _post needs dq and leaves only the three weight-gradient reductions
+ * of which depends on the TD target.  _pre computes u into ws_dev (ssac_mlp_backward_ws floats: v then u; v itself is
+ * generated from h2 and W3 inside the GEMMs that consume it and only materialised when an operand is not TMA-addressable)
+ * and can run next to the target networks; _post needs dq and leaves only the three weight-gradient reductions
  * gW1 = (dq.*u)^T x, gW2 = (dq.*v)^T h1, gW3 = dq^T h2 (+ bias gradients), overwriting the gradient arrays.  Same
- * results as ssac_mlp_backward up to fp32 rounding of dz1 (dq is applied after, not before, the W2 product). */
+ * results as ssac_mlp_backward up to fp32 rounding of dz1 (dq is applied after, not before, the W2 product).
+ * u_async != 0 (and ssac_set_overlap on): the u GEMM is forked onto the library's own second stream and joined by the
+ * matching _post call (which must follow on a stream ordered after `stream`) -- the output layer, the loss and the gW2
+ * reduction do not read u, so it leaves the caller's chain. */
 int ssac_mlp_backward_pre(const float* W2, const float* W3, int G, int H, int B, const float* h1_dev, const float* h2_dev,
-                          float* ws_dev, int impl, void* stream);
-int ssac_mlp_backward_post(int G, int D, int H, const float* x_dev, int64_t ldx, int64_t x_gs, int B,
-                           const float* h1_dev, const float* h2_dev, const float* dq_dev, const float* ws_dev, float* gW1,
+                          float* ws_dev, int u_async, int impl, void* stream);
+int ssac_mlp_backward_post(const float* W3, int G, int D, int H, const float* x_dev, int64_t ldx, int64_t x_gs, int B,
+                           const float* h1_dev, const float* h2_dev, const float* dq_dev, float* ws_dev, float* gW1,
                            float* gb1, float* gW2, float* gb2, float* gW3, float* gb3, int impl, void* stream);
+
+/* _post with the optimiser step folded into its two branches: the gW1 / gb1 / gW3 / gb3 reduction applies Adam to the
+ * elements it has just produced (behind the gW2 GEMM, the last reader of W3), an Adam launch over W2 / b2 follows the gW2
+ * GEMM on `stream` (behind the u GEMM of an asynchronous _pre, the last reader of W2); no separate pass over the arena
+ * after the join, gradients still written.  The parameter / exp_avg / exp_avg_sq of a gradient element sit at float
+ * offsets param_off / exp_avg_off / exp_avg_sq_off from the gradient's own address (twin arenas with one layout; W2 and
+ * b2 adjacent).  ctl_dev: int32[8], [0] = step as in ssac_adam_step (the same counter; it advances once per call, when
+ * both branches are done), [2..4] scratch counters, zero-initialised.  No gradient clipping (that needs the global norm
+ * first: use _post + ssac_adam_step).  Same arithmetic per element as ssac_adam_step. */
+int ssac_mlp_backward_post_adam(const float* W3, int G, int D, int H, const float* x_dev, int64_t ldx, int64_t x_gs, int B,
+                                const float* h1_dev, const float* h2_dev, const float* dq_dev, float* ws_dev, float* gW1,
+                                float* gb1, float* gW2, float* gb2, float* gW3, float* gb3, int64_t param_off,
+                                int64_t exp_avg_off, int64_t exp_avg_sq_off, int32_t* ctl_dev, double lr, double beta1,
+                                double beta2, double eps, double weight_decay, int impl, void* stream);
 
 /* The actor update's pass through an ensemble of scalar-output critics (learning.py:400-418): from the seed dq [G,B]
  * (ssac_actor_loss_seed: non-zero on each row's arg-min net only) straight to the action gradient summed over the nets,

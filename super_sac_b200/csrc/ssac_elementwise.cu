@@ -83,28 +83,12 @@ __global__ void __launch_bounds__(256) polyak_multi_kernel(const uint64_t* __res
 // ------------------------------------------------------------------------------------------------
 // Adam (torch/optim/adam.py _single_tensor_adam as configured at main.py:188-239) [+ fused Polyak]
 // ------------------------------------------------------------------------------------------------
-struct AdamScalars {
-  float step_size, bc2_sqrt, clip_coef;
-};
-
-__device__ __forceinline__ void adam1(float& p, float& g, float& m, float& v, const AdamScalars& sc, float one_m_b1,
-                                      float b2, float one_m_b2, float eps, float wd, bool clip) {
-  if (clip) g = g * sc.clip_coef;
-  float ge = g;
-  if (wd != 0.f) ge = ge + wd * p;
-  m = m + one_m_b1 * (ge - m);          // exp_avg.lerp_(grad, 1-beta1)
-  v = v * b2;                           // exp_avg_sq.mul_(beta2)
-  v = v + one_m_b2 * ge * ge;           //   .addcmul_(grad, grad, value=1-beta2)
-  float denom = sqrtf(v) / sc.bc2_sqrt + eps;
-  p = p - sc.step_size * (m / denom);   // param.addcdiv_(exp_avg, denom, value=-step_size)
-}
-
 template <bool POLYAK>
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, float* __restrict__ tgt, int64_t n,
                                                    int32_t* __restrict__ ctl, double lr, double b1d, double b2d, float eps,
                                                    float wd, const float* __restrict__ gnorm_sq, float max_norm,
-                                                   int write_back, float c1, float c2) {
+                                                   int write_back, float c1, float c2, int fuse_slot, int fuse_n) {
   __shared__ AdamScalars sc;
   if (threadIdx.x == 0) {
     // the step counter is only ever written by this optimiser's own previous launch: the (double-precision) bias
@@ -174,11 +158,18 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float*
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
-    const int prev = atomicAdd(&ctl[1], 1);
-    if (prev == (int)gridDim.x - 1) {
-      ctl[0] = ctl[0] + 1;
-      ctl[1] = 0;
-      __threadfence();
+    if (fuse_n > 0) {
+      // one of several kernels that share this step (ssac_mlp_backward_post_adam): the last of them advances it
+      AdamFuse a;
+      a.ctl = ctl; a.slot = fuse_slot; a.n_kernels = fuse_n;
+      adam_fuse_block_done(a, (int)gridDim.x);
+    } else {
+      const int prev = atomicAdd(&ctl[1], 1);
+      if (prev == (int)gridDim.x - 1) {
+        ctl[0] = ctl[0] + 1;
+        ctl[1] = 0;
+        __threadfence();
+      }
     }
   }
 }
@@ -674,9 +665,9 @@ int ssac_polyak_multi(const uint64_t* table_dev, int n_tensors, int64_t max_nume
   return 0;
 }
 
-static int adam_launch(bool polyak, float* p, float* g, float* m, float* v, float* tgt, int64_t n, int32_t* ctl,
-                       double lr, double b1, double b2, double eps, double wd, const float* gnorm_sq, double max_norm,
-                       int wb, double tau, void* stream) {
+int ssac_internal_adam_launch(int polyak, float* p, float* g, float* m, float* v, float* tgt, int64_t n, int32_t* ctl,
+                double lr, double b1, double b2, double eps, double wd, const float* gnorm_sq, double max_norm,
+                int wb, double tau, void* stream, int fuse_slot, int fuse_n) {
   if (n <= 0) return 0;
   SSAC_REQUIRE(p && g && m && v && ctl, "ssac_adam_step: null pointer");
   const int grid = grid_for((n + 3) / 4, 256, 8);
@@ -684,10 +675,10 @@ static int adam_launch(bool polyak, float* p, float* g, float* m, float* v, floa
   if (polyak) {
     SSAC_REQUIRE(tgt, "ssac_adam_polyak_step: null target");
     launch_pdl(adam_kernel<true>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, tgt, n, ctl, lr, b1, b2, (float)eps,
-               (float)wd, gnorm_sq, (float)max_norm, wb, c1, c2);
+               (float)wd, gnorm_sq, (float)max_norm, wb, c1, c2, fuse_slot, fuse_n);
   } else {
     launch_pdl(adam_kernel<false>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, (float*)nullptr, n, ctl, lr, b1, b2,
-               (float)eps, (float)wd, gnorm_sq, (float)max_norm, wb, 0.f, 0.f);
+               (float)eps, (float)wd, gnorm_sq, (float)max_norm, wb, 0.f, 0.f, fuse_slot, fuse_n);
   }
   SSAC_CHECK_LAUNCH("ssac_adam_step");
   return 0;
@@ -696,15 +687,15 @@ static int adam_launch(bool polyak, float* p, float* g, float* m, float* v, floa
 int ssac_adam_step(float* p, float* g, float* m, float* v, int64_t n, int32_t* ctl, double lr, double beta1,
                    double beta2, double eps, double weight_decay, const float* gnorm_sq_dev, double max_norm,
                    int write_back_grad, void* stream) {
-  return adam_launch(false, p, g, m, v, nullptr, n, ctl, lr, beta1, beta2, eps, weight_decay, gnorm_sq_dev, max_norm,
-                     write_back_grad, 0.0, stream);
+  return ssac_internal_adam_launch(0, p, g, m, v, nullptr, n, ctl, lr, beta1, beta2, eps, weight_decay, gnorm_sq_dev, max_norm,
+                     write_back_grad, 0.0, stream, 0, 0);
 }
 
 int ssac_adam_polyak_step(float* p, float* g, float* m, float* v, float* target, int64_t n, int32_t* ctl, double lr,
                           double beta1, double beta2, double eps, double weight_decay, const float* gnorm_sq_dev,
                           double max_norm, int write_back_grad, double tau, void* stream) {
-  return adam_launch(true, p, g, m, v, target, n, ctl, lr, beta1, beta2, eps, weight_decay, gnorm_sq_dev, max_norm,
-                     write_back_grad, tau, stream);
+  return ssac_internal_adam_launch(1, p, g, m, v, target, n, ctl, lr, beta1, beta2, eps, weight_decay, gnorm_sq_dev, max_norm,
+                     write_back_grad, tau, stream, 0, 0);
 }
 
 int ssac_sumsq(const float* x, int64_t n, float* out, int accumulate, void* stream) {

@@ -20,6 +20,10 @@ struct GemmP {
   const float* extra; int64_t ldextra, extra_gs; float extra_scale;   // + s * extra[m][n] (before the mask)
   float* colsum; int64_t colsum_gs;                                    // L_TN: colsum[m] = sum_k A[k][m]  (bias grads)
   const float* a_kscale; int64_t a_kscale_gs;                          // L_TN (TMA-fed A only): A[k][m] *= a_kscale[g][k] while staging
+  // TMA-fed A only: the operand is GENERATED from the loaded tile while it is staged, A' = A > 0 ? a_gate[g][j] : 0 with j
+  // the index along A's contiguous dimension (k for L_NN / L_NT, m for L_TN).  With A = h2 and a_gate = W3 this is
+  // v = W3 .* (h2 > 0) of the split critic backward, which therefore never exists in memory.
+  const float* a_gate; int64_t a_gate_gs;
   int M, N, K;
   int relu, accumulate;
   int pdl;   // host side: launch with programmatic stream serialization (the predecessor in the stream is PDL-aware)

@@ -390,30 +390,37 @@ int head_backward_weight(const float* dy, const float* h2, int G, int B, int H, 
 // First-layer weight gradients for narrow inputs (D <= 32: cat(s, a) of the state-based configs):
 //   gW1[g][h][d] (+)= sum_b dz1[g][b][h] * x[g][b][d],   gb1[g][h] (+)= sum_b dz1[g][b][h]
 // A 256 x 23 output with K = 256 is far too small for a tensor-core tile pipeline to amortise its set-up, so this is
-// a plain FFMA kernel: block = (net, 32-wide h slab), lane = h, warp w owns batch rows b = w, w+8, ...; every thread
-// keeps all DP outputs of its h in registers, x rows are broadcast from shared memory, and the eight per-warp
-// partials are summed in a fixed order (bit-reproducible).
+// a plain FFMA kernel: block = (net, 32-wide h slab), lane = h, warp w of 16 owns batch rows b = w, w+16, ...; every
+// thread keeps all DP outputs of its h in registers, x rows are broadcast from shared memory, and the sixteen per-warp
+// partials are summed in a fixed order (bit-reproducible): warps 8-15 hand theirs to warps 0-7, which add them to their
+// own, then the eight sums are added in index order.  16 warps (4 per scheduler) because the kernel is latency bound: with 8
+// the two warps of a scheduler could not cover the FMA / shared-memory latencies (ncu: 1.5 of 4 issue slots used).
+constexpr int kWgWarps = 16, kWgThreads = 32 * kWgWarps;
 template <int DP>
-__global__ void __launch_bounds__(256) first_layer_wgrad_kernel(const float* __restrict__ dz1, const float* __restrict__ x,
-                                                                int64_t ldx, int64_t x_gs, int B, int H, int D,
-                                                                float* __restrict__ gW1, float* __restrict__ gb1,
-                                                                int accumulate, const float* __restrict__ row_scale,
-                                                                const float* __restrict__ h2, float* __restrict__ gW3,
-                                                                float* __restrict__ gb3) {
+__global__ void __launch_bounds__(kWgThreads) first_layer_wgrad_kernel(const float* __restrict__ dz1, const float* __restrict__ x,
+                                                                      int64_t ldx, int64_t x_gs, int B, int H, int D,
+                                                                      float* __restrict__ gW1, float* __restrict__ gb1,
+                                                                      int accumulate, const float* __restrict__ row_scale,
+                                                                      const float* __restrict__ h2, float* __restrict__ gW3,
+                                                                      float* __restrict__ gb3, const AdamFuse adam) {
   constexpr int kRows = 256;                    // batch rows staged per pass
   // h2 / gW3 / gb3 (optional, scalar-output critics with row_scale = dq): the output-layer weight gradients
-  // gW3[g][h] = sum_b dq[b] h2[b][h], gb3[g] = sum_b dq[b] ride along (same rows, same lanes: one more load and FMA per
-  // row), in exactly the summation order of head_backward_weight_kernel
+  // gW3[g][h] = sum_b dq[b] h2[b][h], gb3[g] = sum_b dq[b] ride along (same rows, same lanes: one more load and FMA per row)
   constexpr int kPartFloats = 8 * 32 * (DP + 3), kXFloats = kRows * DP;
   __shared__ __align__(16) float shbuf[kPartFloats > kXFloats ? kPartFloats : kXFloats];   // x rows, then the partials
   float (*xs)[DP] = reinterpret_cast<float (*)[DP]>(shbuf);
   float (*part)[32][DP + 3] = reinterpret_cast<float (*)[32][DP + 3]>(shbuf);
+  __shared__ AdamFuseConsts adam_sh;
+  // (the step counter is only written by this optimiser's own previous kernels: the double-precision bias corrections can
+  // be evaluated while the producer of the operands is still running)
+  if (adam.on && threadIdx.x == 0) adam_sh = adam_fuse_consts(adam);
   pdl_wait();
-  pdl_trigger();
+  if (!adam.on) pdl_trigger();   // a kernel that writes parameters never triggers early: later kernels prefetch them
   const int g = blockIdx.y, h0 = blockIdx.x * 32, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int h = h0 + lane;
   const float* dz = dz1 + (int64_t)g * B * H + (h < H ? h : 0);
   const float* xg = x + (int64_t)g * x_gs;
+  const float* rs = row_scale ? row_scale + (int64_t)g * B : nullptr;
   float acc[DP], bsum = 0.f, acc3 = 0.f, bsum3 = 0.f;
   const float* h2p = h2 ? h2 + (int64_t)g * B * H + (h < H ? h : 0) : nullptr;
 #pragma unroll
@@ -422,55 +429,73 @@ __global__ void __launch_bounds__(256) first_layer_wgrad_kernel(const float* __r
     const int nb = min(kRows, B - b0);
     __syncthreads();
     {
-      // kRows * DP / 256 = DP elements per thread, all loads issued before the first store
-      float xv[DP];
+      // kRows * DP / 512 = DP / 2 elements per thread, all loads issued before the first store
+      float xv[DP / 2];
 #pragma unroll
-      for (int u = 0; u < DP; ++u) {
-        const int i = threadIdx.x + 256 * u, r = i / DP, d = i - r * DP;
+      for (int u = 0; u < DP / 2; ++u) {
+        const int i = threadIdx.x + kWgThreads * u, r = i / DP, d = i - r * DP;
         xv[u] = (r < nb && d < D) ? __ldg(xg + (int64_t)(b0 + r) * ldx + d) : 0.f;
       }
 #pragma unroll
-      for (int u = 0; u < DP; ++u) {
-        const int i = threadIdx.x + 256 * u, r = i / DP, d = i - r * DP;
+      for (int u = 0; u < DP / 2; ++u) {
+        const int i = threadIdx.x + kWgThreads * u, r = i / DP, d = i - r * DP;
         xs[r][d] = xv[u];
       }
     }
+    // every row a warp owns in this pass (kRows / 16 = 16) is requested before the first FMA: the L2 latency is paid once
+    constexpr int kFly = kRows / kWgWarps;
+    float dv[kFly], sc[kFly], hv[kFly];
+    const float* dzb = dz + (int64_t)b0 * H;
+    const float* h2b = h2p ? h2p + (int64_t)b0 * H : nullptr;
+#pragma unroll
+    for (int u = 0; u < kFly; ++u) {
+      const int r = warp + kWgWarps * u;
+      const bool ok = r < nb && h < H;
+      dv[u] = ok ? __ldg(dzb + r * H) : 0.f;
+      sc[u] = (rs && r < nb) ? __ldg(rs + b0 + r) : 1.f;
+      hv[u] = (h2b && ok) ? __ldg(h2b + r * H) : 0.f;
+    }
     __syncthreads();
-    for (int r0 = warp; r0 < nb; r0 += 64) {
-      float dv[8], sc[8], hv[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {             // eight independent loads (per array) in flight per thread
-        const int r = r0 + 8 * u;
-        dv[u] = (r < nb && h < H) ? __ldg(dz + (int64_t)(b0 + r) * H) : 0.f;
-        sc[u] = (row_scale && r < nb) ? __ldg(row_scale + (int64_t)g * B + b0 + r) : 1.f;
-        hv[u] = (h2p && r < nb && h < H) ? __ldg(h2p + (int64_t)(b0 + r) * H) : 0.f;
-      }
+    for (int u = 0; u < kFly; ++u) {
+      const int r = warp + kWgWarps * u;
+      if (r < nb) {
+        if (rs) dv[u] *= sc[u];        // dz1 = dq (x) u, split backward
+        if (h2p) { acc3 = fmaf(sc[u], hv[u], acc3); bsum3 += sc[u]; }
+        bsum += dv[u];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int r = r0 + 8 * u;
-        if (r < nb) {
-          if (row_scale) dv[u] *= sc[u];        // dz1 = dq (x) u, split backward
-          if (h2p) { acc3 = fmaf(sc[u], hv[u], acc3); bsum3 += sc[u]; }
-          bsum += dv[u];
-#pragma unroll
-          for (int d = 0; d < DP; d += 4) {
-            const float4 xv = *reinterpret_cast<const float4*>(&xs[r][d]);
-            acc[d + 0] = fmaf(dv[u], xv.x, acc[d + 0]); acc[d + 1] = fmaf(dv[u], xv.y, acc[d + 1]);
-            acc[d + 2] = fmaf(dv[u], xv.z, acc[d + 2]); acc[d + 3] = fmaf(dv[u], xv.w, acc[d + 3]);
-          }
+        for (int d = 0; d < DP; d += 4) {
+          const float4 xv = *reinterpret_cast<const float4*>(&xs[r][d]);
+          acc[d + 0] = fmaf(dv[u], xv.x, acc[d + 0]); acc[d + 1] = fmaf(dv[u], xv.y, acc[d + 1]);
+          acc[d + 2] = fmaf(dv[u], xv.z, acc[d + 2]); acc[d + 3] = fmaf(dv[u], xv.w, acc[d + 3]);
         }
       }
     }
   }
   __syncthreads();   // every warp is done with the x rows: the buffer becomes the partials
+  if (warp >= 8) {
 #pragma unroll
-  for (int d = 0; d < DP; ++d) part[warp][lane][d] = acc[d];
-  part[warp][lane][DP] = bsum;
-  part[warp][lane][DP + 1] = acc3;
-  part[warp][lane][DP + 2] = bsum3;
+    for (int d = 0; d < DP; ++d) part[warp - 8][lane][d] = acc[d];
+    part[warp - 8][lane][DP] = bsum;
+    part[warp - 8][lane][DP + 1] = acc3;
+    part[warp - 8][lane][DP + 2] = bsum3;
+  }
   __syncthreads();
-  // 32 x (D + 1 [+ 2]) results, summed over the eight warps in index order
-  for (int i = threadIdx.x; i < 32 * (DP + 3); i += 256) {
+  if (warp < 8) {
+#pragma unroll
+    for (int d = 0; d < DP; ++d) acc[d] += part[warp][lane][d];
+    bsum += part[warp][lane][DP];
+    acc3 += part[warp][lane][DP + 1];
+    bsum3 += part[warp][lane][DP + 2];
+#pragma unroll
+    for (int d = 0; d < DP; ++d) part[warp][lane][d] = acc[d];   // (own slot: read and written by this thread only)
+    part[warp][lane][DP] = bsum;
+    part[warp][lane][DP + 1] = acc3;
+    part[warp][lane][DP + 2] = bsum3;
+  }
+  __syncthreads();
+  // 32 x (D + 1 [+ 2]) results, summed over the eight pair sums in index order
+  for (int i = threadIdx.x; i < 32 * (DP + 3); i += kWgThreads) {
     const int hl = i / (DP + 3), d = i - hl * (DP + 3);
     if (h0 + hl >= H || (d < DP && d >= D)) continue;
     if (d > DP && !h2p) continue;
@@ -481,22 +506,33 @@ __global__ void __launch_bounds__(256) first_layer_wgrad_kernel(const float* __r
     float* out = d < DP ? gW1 + ((int64_t)g * H + h0 + hl) * D + d
                  : d == DP ? gb1 + (int64_t)g * H + h0 + hl
                  : d == DP + 1 ? gW3 + (int64_t)g * H + h0 + hl : gb3 + g;
-    *out = accumulate ? *out + tot : tot;
+    const float val = accumulate ? *out + tot : tot;
+    *out = val;
+    if (adam.on) adam_fuse1(out, val, adam, adam_sh);
+  }
+  if (adam.on) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) adam_fuse_block_done(adam, (int)(gridDim.x * gridDim.y));
   }
 }
 
 static int first_layer_wgrad(const float* dz1, const float* x, int64_t ldx, int64_t x_gs, int G, int B, int H, int D,
                              float* gW1, float* gb1, int accumulate, cudaStream_t s, const float* row_scale = nullptr,
-                             const float* h2 = nullptr, float* gW3 = nullptr, float* gb3 = nullptr) {
+                             const float* h2 = nullptr, float* gW3 = nullptr, float* gb3 = nullptr,
+                             const AdamFuse* adam = nullptr) {
   dim3 grid((H + 31) / 32, G);
-  if (D <= 8) launch_pdl(first_layer_wgrad_kernel<8>, grid, dim3(256), 0, s, dz1, x, ldx, x_gs, B, H, D, gW1, gb1, accumulate, row_scale, h2, gW3,
-             gb3);
-  else if (D <= 16) launch_pdl(first_layer_wgrad_kernel<16>, grid, dim3(256), 0, s, dz1, x, ldx, x_gs, B, H, D, gW1, gb1, accumulate, row_scale, h2, gW3,
-             gb3);
-  else if (D <= 24) launch_pdl(first_layer_wgrad_kernel<24>, grid, dim3(256), 0, s, dz1, x, ldx, x_gs, B, H, D, gW1, gb1, accumulate, row_scale, h2, gW3,
-             gb3);
-  else launch_pdl(first_layer_wgrad_kernel<32>, grid, dim3(256), 0, s, dz1, x, ldx, x_gs, B, H, D, gW1, gb1, accumulate, row_scale, h2, gW3,
-             gb3);
+  AdamFuse af;
+  memset(&af, 0, sizeof(af));
+  if (adam) af = *adam;
+#define SSAC_FLW(DP)                                                                                                   \
+  launch_pdl(first_layer_wgrad_kernel<DP>, grid, dim3(kWgThreads), 0, s, dz1, x, ldx, x_gs, B, H, D, gW1, gb1, accumulate, row_scale, \
+             h2, gW3, gb3, af)
+  if (D <= 8) SSAC_FLW(8);
+  else if (D <= 16) SSAC_FLW(16);
+  else if (D <= 24) SSAC_FLW(24);
+  else SSAC_FLW(32);
+#undef SSAC_FLW
   SSAC_CHECK_LAUNCH("mlp backward gW1 (narrow input)");
   return 0;
 }
@@ -520,7 +556,9 @@ static int launch_gemm(int layout, const GemmP& p, int G, cudaStream_t s, const 
 static int g_overlap = 1;
 struct Side {
   cudaStream_t s = nullptr;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int u_pending = 0;   // asynchronous mlp_backward_pre calls whose _post is still to come (ev[5] sits behind their u GEMM; on the
+                       // in-order second stream its latest record covers the earlier ones)
 };
 static Side* side_of_current_device() {
   static Side sides[64];
@@ -557,7 +595,7 @@ static GemmP blank() {
   p.A = nullptr; p.lda = 0; p.a_gs = 0; p.Bm = nullptr; p.ldb = 0; p.b_gs = 0; p.b_index = nullptr;
   p.C = nullptr; p.ldc = 0; p.c_gs = 0; p.bias = nullptr; p.bias_gs = 0; p.mask = nullptr; p.ldmask = 0; p.mask_gs = 0;
   p.extra = nullptr; p.ldextra = 0; p.extra_gs = 0; p.extra_scale = 0.f; p.colsum = nullptr; p.colsum_gs = 0;
-  p.a_kscale = nullptr; p.a_kscale_gs = 0;
+  p.a_kscale = nullptr; p.a_kscale_gs = 0; p.a_gate = nullptr; p.a_gate_gs = 0;
   p.M = p.N = p.K = 0; p.relu = 0; p.accumulate = 0; p.pdl = 0;
   return p;
 }
@@ -753,40 +791,97 @@ int mlp_backward_dact(const float* W1, const float* W2, const float* W3, int G, 
 // stream) and mlp_backward_post only has the three weight-gradient reductions left once dq is known:
 //   gW1 = (dq .* u)^T x   gW2 = (dq .* v)^T h1   gW3 = dq^T h2     (+ the bias gradients as their column sums)
 int mlp_backward_pre(const float* W2, const float* W3, int G, int H, int B, const float* h1, const float* h2, float* ws,
-                     cudaStream_t s, int impl) {
+                     int u_async, cudaStream_t s, int impl) {
   g_impl = impl;
   float* v = ws;
   float* u = ws + (int64_t)G * B * H;
-  int rc = head_backward_data(nullptr, W3, nullptr, nullptr, 0.f, h2, G, B, H, 1, v, s, 1);
-  if (rc) return rc;
+  int rc;
+  // Neither the output layer nor the loss reads u: with u_async it is computed on the second stream, next to the caller's
+  // fwd -> loss chain; _post runs the gW1 reduction, the only reader of u, on that second stream behind this GEMM.
+  Side* sd = (u_async && g_overlap) ? side_of_current_device() : nullptr;
+  if (sd) {
+    if ((rc = order_after(s, sd->s, sd->ev[4]))) return rc;
+    s = sd->s;
+  }
+  // u = (v W2) .* (h1 > 0) with v = W3 .* (h2 > 0) generated from h2 while the A tiles are staged (GemmP::a_gate)
   GemmP p = blank();
-  p.A = v; p.lda = H; p.a_gs = (int64_t)B * H; p.Bm = W2; p.ldb = H; p.b_gs = (int64_t)H * H;
+  p.A = h2; p.lda = H; p.a_gs = (int64_t)B * H; p.a_gate = W3; p.a_gate_gs = H;
+  p.Bm = W2; p.ldb = H; p.b_gs = (int64_t)H * H;
   p.C = u; p.ldc = H; p.c_gs = (int64_t)B * H; p.mask = h1; p.ldmask = H; p.mask_gs = (int64_t)B * H;
   p.M = B; p.N = H; p.K = H; p.pdl = 1;
-  return launch_gemm(L_NN, p, G, s, "mlp_backward_pre u");
+  rc = launch_gemm(L_NN, p, G, s, "mlp_backward_pre u");
+  if (rc == SSAC_E_UNSUPPORTED) {
+    // operand not TMA-addressable: materialise v first
+    rc = head_backward_data(nullptr, W3, nullptr, nullptr, 0.f, h2, G, B, H, 1, v, s, 1);
+    if (rc) return rc;
+    p.A = v; p.a_gate = nullptr;
+    rc = launch_gemm(L_NN, p, G, s, "mlp_backward_pre u");
+  }
+  if (rc) return rc;
+  if (sd) {   // the last reader of W2 in this update: a fused optimiser step of _post waits for it
+    if (cudaEventRecord(sd->ev[5], s) != cudaSuccess) return fail((int)cudaErrorUnknown, "mlp_backward_pre: event record");
+    sd->u_pending++;
+  }
+  return 0;
 }
 
-int mlp_backward_post(int G, int D, int H, const float* x, int64_t ldx, int64_t x_gs, int B, const float* h1,
-                      const float* h2, const float* dq, const float* ws, float* gW1, float* gb1, float* gW2, float* gb2,
-                      float* gW3, float* gb3, cudaStream_t s, int impl) {
+int mlp_backward_post(const float* W3, int G, int D, int H, const float* x, int64_t ldx, int64_t x_gs, int B, const float* h1,
+                      const float* h2, const float* dq, float* ws, float* gW1, float* gb1, float* gW2, float* gb2,
+                      float* gW3, float* gb3, cudaStream_t s, int impl, const AdamFuse* adam) {
   g_impl = impl;
   SSAC_REQUIRE(D <= 32, "ssac_mlp_backward_post: first-layer width must be <= 32");
-  const float* v = ws;
+  float* v = ws;
   const float* u = ws + (int64_t)G * B * H;
   int rc;
   Side* sd = g_overlap ? side_of_current_device() : nullptr;
   cudaStream_t w = sd ? sd->s : s;
   if (sd && (rc = order_after(s, w, sd->ev[0]))) return rc;   // fork
-  // the short reductions go to the side stream; the GEMM (the longer branch) stays on the caller's stream, where its
-  // set-up overlaps the loss kernel (programmatic dependent launch)
-  rc = first_layer_wgrad(u, x, ldx, x_gs, G, B, H, D, gW1, gb1, 0, w, dq, h2, gW3, gb3);   // gW1, gb1, gW3, gb3
-  if (rc) return rc;
+  // the short reductions go to the side stream (behind the u GEMM of an asynchronous _pre); the gW2 GEMM stays on the
+  // caller's stream, where its set-up overlaps the loss kernel (programmatic dependent launch)
+  if (!adam) {
+    rc = first_layer_wgrad(u, x, ldx, x_gs, G, B, H, D, gW1, gb1, 0, w, dq, h2, gW3, gb3);   // gW1, gb1, gW3, gb3
+    if (rc) return rc;
+  }
+  // gW2 = (dq .* v)^T h1 with v generated from h2 while the A tiles are staged
   GemmP q = blank();
-  q.A = v; q.lda = H; q.a_gs = (int64_t)B * H; q.Bm = h1; q.ldb = H; q.b_gs = (int64_t)B * H;
+  q.A = h2; q.lda = H; q.a_gs = (int64_t)B * H; q.a_gate = W3; q.a_gate_gs = H;
+  q.Bm = h1; q.ldb = H; q.b_gs = (int64_t)B * H;
   q.C = gW2; q.ldc = H; q.c_gs = (int64_t)H * H; q.colsum = gb2; q.colsum_gs = H; q.M = H; q.N = H; q.K = B;
   q.a_kscale = dq; q.a_kscale_gs = B; q.pdl = 1;
   rc = launch_gemm(L_TN, q, G, s, "mlp_backward_post gW2");
+  if (rc == SSAC_E_UNSUPPORTED) {
+    rc = head_backward_data(nullptr, W3, nullptr, nullptr, 0.f, h2, G, B, H, 1, v, s, 1);
+    if (rc) return rc;
+    q.A = v; q.a_gate = nullptr;
+    rc = launch_gemm(L_TN, q, G, s, "mlp_backward_post gW2");
+  }
   if (rc) return rc;
+  // Fused optimiser step (ssac_mlp_backward_post_adam).  Who may write what, and when:
+  //   W1, b1, W3, b3  by the gW1 reduction itself, element by element as it produces their gradients -- once the gW2 GEMM,
+  //                   the last reader of W3 (its gate), is done: the second stream waits for it first;
+  //   W2, b2          by an Adam launch over that range behind the gW2 GEMM on the caller's stream -- once the u GEMM of an
+  //                   asynchronous _pre, the last reader of W2, is done.
+  // The two share the step counter (AdamFuse): it advances when both have finished.
+  AdamFuse a1;
+  if (adam) {
+    a1 = *adam; a1.slot = 0; a1.n_kernels = 2; a1.on = 1;
+    if (sd && (rc = order_after(s, w, sd->ev[1]))) return rc;
+  }
+  if (adam) {
+    rc = first_layer_wgrad(u, x, ldx, x_gs, G, B, H, D, gW1, gb1, 0, w, dq, h2, gW3, gb3, &a1);   // gW1, gb1, gW3, gb3 + Adam
+    if (rc) return rc;
+  }
+  if (sd && sd->u_pending > 0) {
+    if (adam && cudaStreamWaitEvent(s, sd->ev[5], 0) != cudaSuccess) return fail((int)cudaErrorUnknown, "mlp_backward_post: event wait");
+    sd->u_pending--;
+  }
+  if (adam) {
+    SSAC_REQUIRE(gb2 > gW2 && (gb2 - gW2) < (int64_t)G * H * H + 1024, "ssac_mlp_backward_post_adam: W2 / b2 gradients must be adjacent arrays of one arena");
+    const int64_t n = (gb2 - gW2) + (int64_t)G * H;
+    rc = ssac_internal_adam_launch(0, gW2 + adam->dp, gW2, gW2 + adam->dm, gW2 + adam->dv, nullptr, n, adam->ctl, adam->lr, adam->b1,
+                                   adam->b2, (double)adam->eps, (double)adam->wd, nullptr, 0.0, 0, 0.0, (void*)s, 1, 2);
+    if (rc) return rc;
+  }
   if (sd && (rc = order_after(w, s, sd->ev[3]))) return rc;   // join
   return 0;
 }

@@ -177,6 +177,36 @@ __global__ void __launch_bounds__(kThreads, 1) grouped_gemm_tc_kernel(const __gr
       for (int e = 0; e < 4; ++e)
         if (nc + e < p.N) bv[e] = __ldg(bias + nc + e);
     }
+    // gate (see GemmP::a_gate): the four floats of a 16-byte chunk are consecutive along A's contiguous dimension; the
+    // chunk's position follows from the swizzle formulas at the top of this file.  MN-major A: the gate index is the m
+    // coordinate, the same for every stage (loaded once); K-major A: it is the k coordinate -- the values of stage kc + 1
+    // are requested while stage kc is converted, so their latency stays off the stage's critical path.
+    const float* gate = (a_tma && p.a_gate) ? p.a_gate + (int64_t)wg * p.a_gate_gs : nullptr;
+    float4 gv[4];
+    auto load_gate = [&](int kc) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t off = (uint32_t)(t + kWorkerThreads * i) * 16u;
+        int j0, lim;
+        if (A_MN) {   // (m/32)*4096 + k*128 + (((m%32)/8 ^ k%4)*32) + (m%8)*4
+          const uint32_t kk = (off >> 7) & 31u;
+          j0 = m0 + (int)(32u * (off >> 12) + 8u * (((off >> 5) & 3u) ^ (kk & 3u)) + 4u * ((off >> 4) & 1u));
+          lim = p.M;
+        } else {      // r*128 + ((k/4 ^ r%8)*16) + (k%4)*4
+          const uint32_t r = off >> 7;
+          j0 = kc * TK + (int)(4u * (((off >> 4) & 7u) ^ (r & 7u)));
+          lim = p.K;
+        }
+        gv[i] = (j0 + 3 < lim) ? __ldg(reinterpret_cast<const float4*>(gate + j0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    if (gate && nk > 0) load_gate(0);
+    const bool kscale = (LAYOUT == L_TN) && a_tma && p.a_kscale != nullptr;
+    auto load_ksc = [&](int kc) {
+      const int kk = kc * TK + (t >> 3);
+      return kk < p.K ? __ldg(p.a_kscale + (int64_t)g * p.a_kscale_gs + kk) : 0.f;
+    };
+    float ksc_next = (kscale && nk > 0) ? load_ksc(0) : 1.f;
     for (int kc = 0; kc < nk; ++kc) {
       const int s = kc % kStages, use = kc / kStages;
       uint8_t* st = smem + s * kStageBytes;
@@ -189,23 +219,22 @@ __global__ void __launch_bounds__(kThreads, 1) grouped_gemm_tc_kernel(const __gr
         // lo pass: same (swizzled) offsets in and out, 4 x 16 bytes per thread.  In the MN-major layout all four
         // chunks of a thread sit on k row t/8 of the stage, so an optional per-k scale (the TD-error seed of the
         // split critic backward, mlp_backward_post) is one load per thread and stage.
-        float ksc = 1.f;
-        const bool kscale = (LAYOUT == L_TN) && p.a_kscale != nullptr;
-        if (kscale) {
-          const int kk = kc * TK + (t >> 3);
-          ksc = kk < p.K ? __ldg(p.a_kscale + (int64_t)g * p.a_kscale_gs + kk) : 0.f;
-        }
+        const float ksc = ksc_next;
+        if (kscale && kc + 1 < nk) ksc_next = load_ksc(kc + 1);   // (requested a stage ahead, like the gate values)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const uint32_t off = (uint32_t)(t + kWorkerThreads * i) * 16u;
           float4 v = *reinterpret_cast<const float4*>(a_hi + off);
-          if (kscale) {
-            v.x *= ksc; v.y *= ksc; v.z *= ksc; v.w *= ksc;
-            *reinterpret_cast<float4*>(a_hi + off) = v;
+          if (gate) {
+            v.x = v.x > 0.f ? gv[i].x : 0.f; v.y = v.y > 0.f ? gv[i].y : 0.f;
+            v.z = v.z > 0.f ? gv[i].z : 0.f; v.w = v.w > 0.f ? gv[i].w : 0.f;
           }
+          if (kscale) { v.x *= ksc; v.y *= ksc; v.z *= ksc; v.w *= ksc; }
+          if (kscale || gate) *reinterpret_cast<float4*>(a_hi + off) = v;
           *reinterpret_cast<float4*>(a_lo + off) = lo4(v);
           if (do_colsum) { cs[4 * i + 0] += v.x; cs[4 * i + 1] += v.y; cs[4 * i + 2] += v.z; cs[4 * i + 3] += v.w; }
         }
+        if (gate && !A_MN && kc + 1 < nk) load_gate(kc + 1);
       } else {
         if (do_colsum) {
 #pragma unroll
@@ -566,6 +595,8 @@ int launch_gemm_tc(int layout, const GemmP& p, int G, cudaStream_t s, const char
   }
   if (p.a_kscale && !(layout == L_TN && q.a_tma))
     return fail(SSAC_E_UNSUPPORTED, "tcgen05 GEMM: a per-k scale needs a TMA-addressable transposed A operand");
+  if (p.a_gate && !(q.a_tma && (layout == L_TN ? p.M : p.K) % 4 == 0 && (((uintptr_t)p.a_gate | (uintptr_t)(p.a_gate_gs * 4)) & 15) == 0))
+    return fail(SSAC_E_UNSUPPORTED, "tcgen05 GEMM: a gated A operand needs a TMA-addressable A and 16-byte aligned gate rows");
   dim3 grid((p.N + tc::TN - 1) / tc::TN, (p.M + tc::TM - 1) / tc::TM, G);
   if (p.pdl) {
     if (layout == L_NT) launch_pdl(tc::grouped_gemm_tc_kernel<L_NT>, grid, dim3(tc::kThreads), tc::kSmemBytes, s, q);

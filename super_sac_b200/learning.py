@@ -7,12 +7,20 @@ arena, and the logged scalars come back with a single device->host copy.  The ca
 objects, ``log_alphas`` and the target agent exactly as main.py:188-244 / :321 builds them.
 """
 import contextlib
+import os
 import random
 
 import torch
 
 from . import _arena, _lib, _logs, _ops, _rng, graphed, parallel
 from . import learning_utils as lu
+
+
+# Adam folded into the branches of the split backward (ssac_mlp_backward_post_adam): correct and tested, but MEASURED slower
+# inside the pipelined REDQ block (55.6 vs 49.4 us per update on B200): the gW1 reduction then has to wait for the gW2
+# GEMM (the last reader of W3) and the extra optimiser launch competes with the next update's forward.  Opt-in.
+_FUSE_ADAM = bool(os.environ.get("SSAC_FUSED_ADAM"))
+_U_ASYNC = 0 if os.environ.get("SSAC_NO_UASYNC") else 1   # A/B switch: v / u of the split backward on the second stream
 
 
 def _encoder_has_grad_path(s_rep):
@@ -89,6 +97,10 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
     # (the log buffer is cleared by the first member's draw kernel, i.e. on the front stream when pipelined: it then has to
     # come from that stream's allocator pool -- a block recycled from the caller's stream could still be in use by the
     # previous update's backward -- and must not be recycled before the block ends)
+    if pipe is not None:
+        # (first: order the front stream behind whatever it depends on -- under graph capture this is also what makes it
+        # part of the capture, and an allocation on a stream outside the capture would invalidate it)
+        pipe.front_wait_dep(torch.cuda.current_stream(dev))
     with (torch.cuda.stream(pipe.front) if pipe is not None else contextlib.nullcontext()):
         logs = _logs.DeviceLogs(dev, zeroed=False)
     if pipe is not None:
@@ -136,6 +148,7 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
                                             _idx=draws["idx"])
             presampled.append((draws, rd))
     replay_dicts = [None] * E
+    adam_done = []
 
     def member_step(i, draws, rd, lane, batch_ready=None):
         loss_v = loss_all[2 * i:2 * i + 2]
@@ -161,6 +174,9 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
         # three weight-gradient reductions remain.
         split_bwd = side is not None and ca.O == 1 and ca.D <= 32 and not dr3_coeff and L.default_mlp_impl() == 2
         bws = _ops._bwd_ws(N, B, ca.H, dev) if split_bwd else None
+        # one member, no global-norm clipping (that needs every gradient first): the optimiser step rides in the epilogues
+        fuse_adam = (split_bwd and _FUSE_ADAM and E == 1 and not critic_clip and not parallel.is_sharded()
+                     and not parallel.members_sharded())
         if side is not None:
             main = torch.cuda.current_stream(dev)
             if piped:
@@ -175,7 +191,7 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
                                   h2.data_ptr(), None, None, None, None, None, 0, En, 0, None, None, 1,
                                   None, 0, None, None, None, None, 0.0, None, None, 0, online.cuda_stream)
             if split_bwd:
-                L.mlp_backward_pre(W2, W3, N, ca.H, B, h1.data_ptr(), h2.data_ptr(), bws.data_ptr(), 0, online.cuda_stream)
+                L.mlp_backward_pre(W2, W3, N, ca.H, B, h1.data_ptr(), h2.data_ptr(), bws.data_ptr(), _U_ASYNC, 0, online.cuda_stream)
         with (torch.cuda.stream(pipe.front) if piped else contextlib.nullcontext()):
             td_target, (s1, a1) = lu.compute_td_targets(
                 logs=logs, replay_dict=rd, agent=agent, target_agent=target_agent, log_alphas=log_alphas, ensemble_idx=i,
@@ -220,9 +236,21 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
             loss_v[0:1].add_(dv, alpha=dr3_coeff / (E * N))
             extra, extra_scale, f1 = h2b, dr3_coeff / (E * N) / (N * B), (X1, h1b, h2b)
         dxg = torch.empty((N, B, S + A), dtype=torch.float32, device=dev) if need_ds else None
-        if split_bwd:
+        if pipe is not None:
+            pipe.join_deferred(torch.cuda.current_stream(dev))   # the previous update's logged gradient norm reads what follows overwrites
+        if split_bwd and fuse_adam:
+            # Adam applied by the two weight-gradient reductions themselves (no optimiser pass on the chain)
+            if pipe is not None:
+                pipe.main_wait_polyak(torch.cuda.current_stream(dev))   # a Polyak step still reads the online parameters
             gW1, gb1, gW2, gb2, gW3, gb3 = ca.ptrs(i * N, grad=True)
-            L.mlp_backward_post(N, ca.D, ca.H, X.data_ptr(), S + A, 0, B, h1.data_ptr(), h2.data_ptr(), dq.data_ptr(),
+            lr, b1, b2, eps, wd = opt.hyper()
+            L.mlp_backward_post_adam(W3, N, ca.D, ca.H, X.data_ptr(), S + A, 0, B, h1.data_ptr(), h2.data_ptr(),
+                                     dq.data_ptr(), bws.data_ptr(), gW1, gb1, gW2, gb2, gW3, gb3, *opt.fused_offsets(),
+                                     opt.ctl.data_ptr(), lr, b1, b2, eps, wd, 0, _lib.stream_ptr())
+            adam_done.append(True)
+        elif split_bwd:
+            gW1, gb1, gW2, gb2, gW3, gb3 = ca.ptrs(i * N, grad=True)
+            L.mlp_backward_post(W3, N, ca.D, ca.H, X.data_ptr(), S + A, 0, B, h1.data_ptr(), h2.data_ptr(), dq.data_ptr(),
                                 bws.data_ptr(), gW1, gb1, gW2, gb2, gW3, gb3, 0, _lib.stream_ptr())
         else:
             _ops.mlp_backward(ca, i * N, N, X, B, h1, h2, dq, ldx=S + A, dh2_extra=extra, extra_scale=extra_scale,
@@ -243,7 +271,6 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
         if presampled is not None:
             draws, rd = presampled[i]
         elif pipe is not None:
-            pipe.front_wait_dep(caller)
             with torch.cuda.stream(pipe.front):
                 draws = lu.draw_for_critic_member(buffer, agent, B, target_critic_ensemble_n, random_process, per,
                                                   zero=logs.take_unzeroed())
@@ -293,9 +320,17 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
         # Adam on the second stream instead of behind it
         with torch.cuda.stream(side):
             parallel.all_reduce_sum_(loss_all[0:1], site="critic_loss")
-    opt.step(stream, max_norm=critic_clip if critic_clip else None)
+    if adam_done:
+        opt.note_fused_step()
+    else:
+        if pipe is not None:
+            pipe.main_wait_polyak(torch.cuda.current_stream(dev))   # a Polyak step on the auxiliary stream still reads these
+        opt.step(stream, max_norm=critic_clip if critic_clip else None)
     if side is not None:
-        main.wait_stream(side)
+        if pipe is not None and adam_done:
+            pipe.defer_join(side)   # nothing on the caller's stream needs the logged norm before the next backward
+        else:
+            main.wait_stream(side)
     else:
         gslot = lu._member_grad_norm_slot(logs, ca, member * N, (member + 1) * N)
         if parallel.is_sharded():

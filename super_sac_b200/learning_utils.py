@@ -91,6 +91,18 @@ def _multi_table(target, source):
     return cur
 
 
+@contextlib.contextmanager
+def _polyak_context():
+    """Inside a pipelined_updates() block a Polyak step runs on the block's auxiliary stream (see _Pipeline)."""
+    p = _pipeline
+    if p is None:
+        yield lambda: None
+        return
+    aux = p.polyak_stream(torch.cuda.current_stream(p.device))
+    with torch.cuda.stream(aux):
+        yield lambda: p.note_polyak(aux)
+
+
 def soft_update(target, source, tau):
     """target <- target*(1-tau) + source*tau, bit-exact with the reference (learning_utils.py:160-162)."""
     ta, sa = _arena_of(target), _arena_of(source)
@@ -98,17 +110,17 @@ def soft_update(target, source, tau):
         _ops.check_cuda(ta.flat, sa.flat)
         g0, g1 = target._g0, target._g0 + target.num_critics
         assert (source._g0, source.num_critics) == (target._g0, target.num_critics)
-        _ops.polyak_ranges(ta.flat, sa.flat, ta.range_table(g0, g1), tau)
-        if _pipeline is not None:
-            _pipeline.note_polyak(torch.cuda.current_stream(_pipeline.device))
+        with _polyak_context() as note:
+            _ops.polyak_ranges(ta.flat, sa.flat, ta.range_table(g0, g1), tau)
+            note()
         return
     sig, table, max_numel = _multi_table(target, source)
     if table is None:
         return
     _ops.check_cuda(table)
-    _lib.lib().polyak_multi(table.data_ptr(), len(sig), max_numel, float(tau), _lib.stream_ptr())
-    if _pipeline is not None:
-        _pipeline.note_polyak(torch.cuda.current_stream(_pipeline.device))
+    with _polyak_context() as note:
+        _lib.lib().polyak_multi(table.data_ptr(), len(sig), max_numel, float(tau), _lib.stream_ptr())
+        note()
 
 
 def hard_update(target, source):
@@ -190,7 +202,10 @@ class _Pipeline:
         self.device = device
         self.front = _front_stream(device)
         self.dep = None          # main-stream event the front has to wait for before it reads actor / ring again
-        self.polyak = None       # main-stream event of the latest Polyak step (the target critics' parameters)
+        self.polyak = None       # event of the latest Polyak step (the target critics' parameters), for the front stream
+        self.polyak_main = None  # the same event, for the caller's stream (its next Adam step)
+        self.aux = None          # stream the Polyak steps run on
+        self.deferred = []       # streams with log-only work the caller's stream has not joined yet
         self.keep = []           # front-allocated tensors that main-stream kernels read: alive until the block ends
         self.needs_order = False  # a barrier happened: the front's next work goes behind the caller's stream as it is then
 
@@ -212,14 +227,48 @@ class _Pipeline:
             self.front.wait_event(self.polyak)
             self.polyak = None
 
-    def note_polyak(self, main):
+    def polyak_stream(self, main):
+        """Polyak steps run on a stream of their own: they follow the Adam step at the caller's tail, but the caller's next
+        online forward does not wait for them (only the next target-critic forward and the next Adam step do)."""
+        if self.aux is None:
+            self.aux = _aux_stream(self.device)
+        self.aux.wait_stream(main)
+        return self.aux
+
+    def note_polyak(self, stream):
         ev = torch.cuda.Event()
-        ev.record(main)
+        ev.record(stream)
         self.polyak = ev
+        self.polyak_main = ev
+
+    def defer_join(self, stream):
+        """A log-only reduction over the gradients runs on `stream`: the caller's stream joins it only before the next
+        backward overwrites the gradient arrays (or when the block ends), not before the next forward."""
+        self.deferred.append(stream)
+
+    def join_deferred(self, main):
+        for st in self.deferred:
+            main.wait_stream(st)
+        self.deferred.clear()
+
+    def main_wait_polyak(self, main):
+        """Before the caller's stream overwrites the online parameters (Adam) a Polyak step still reads."""
+        if self.polyak_main is not None:
+            main.wait_event(self.polyak_main)
+            self.polyak_main = None
 
 
 _pipeline = None
 _front_streams = {}
+_aux_streams = {}
+
+
+def _aux_stream(device):
+    device = torch.device(device)
+    st = _aux_streams.get(device)
+    if st is None:
+        st = _aux_streams[device] = torch.cuda.Stream(device=device)
+    return st
 
 
 def _front_stream(device):
@@ -251,7 +300,11 @@ def pipelined_updates(device=None):
         yield p
     finally:
         _pipeline = None
-        torch.cuda.current_stream(device).wait_stream(p.front)
+        main = torch.cuda.current_stream(device)
+        main.wait_stream(p.front)
+        if p.aux is not None:
+            main.wait_stream(p.aux)
+        p.join_deferred(main)
         p.keep.clear()
 
 
@@ -262,6 +315,10 @@ def pipeline_barrier():
     if p is not None:
         main = torch.cuda.current_stream(p.device)
         main.wait_stream(p.front)
+        if p.aux is not None:
+            main.wait_stream(p.aux)
+            p.polyak_main = None
+        p.join_deferred(main)
         p.needs_order = True
 
 
@@ -593,6 +650,8 @@ def compute_td_targets(logs, replay_dict, agent, target_agent, ensemble_idx, ens
     B = a.shape[0]
     packed = _packed_of(replay_dict)
     popart = agent.popart[i]
+    if _pipeline is not None and any(p.numel() > 2 for p in target_agent.encoder.parameters()):
+        _pipeline.front_wait_polyak()   # a target encoder with parameters is Polyak-updated as well
     with torch.no_grad():
         s1_rep = target_agent.encoder(o1)
     X1 = _first_layer_input(s1_rep, None, packed["X1"] if packed else None, S, A)

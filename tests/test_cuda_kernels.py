@@ -479,8 +479,9 @@ def test_fused_forward_matches_oracle_and_layered(G, D, H, O, B):
             gu.assert_close(h2[g].numpy(), h2w.numpy(), 1e-4, 2e-5 * float(h2w.abs().max()), f"{mode} h2[{g}]")
 
 
+@pytest.mark.parametrize("u_async", [False, True], ids=["u-in-order", "u-on-second-stream"])
 @pytest.mark.parametrize("G,D,H,B", [(10, 23, 256, 256), (2, 4, 64, 200), (3, 32, 128, 300)])
-def test_split_critic_backward_matches_oracle(G, D, H, B):
+def test_split_critic_backward_matches_oracle(G, D, H, B, u_async):
     """ssac_mlp_backward_pre / _post (TD-independent chain first, seed applied afterwards) against the oracle's backward
     and against the one-call ssac_mlp_backward."""
     from super_sac_b200 import _ops
@@ -501,8 +502,8 @@ def test_split_critic_backward_matches_oracle(G, D, H, B):
     W1, _, W2, _, W3, _ = ar.ptrs(0)
     gW1, gb1, gW2, gb2, gW3, gb3 = ar.ptrs(0, grad=True)
     ar.grad.fill_(float("nan"))
-    L().mlp_backward_pre(W2, W3, G, H, B, h1.data_ptr(), h2.data_ptr(), ws.data_ptr(), 2, None)
-    L().mlp_backward_post(G, D, H, xd.data_ptr(), D, 0, B, h1.data_ptr(), h2.data_ptr(), dqd.data_ptr(), ws.data_ptr(), gW1, gb1,
+    L().mlp_backward_pre(W2, W3, G, H, B, h1.data_ptr(), h2.data_ptr(), ws.data_ptr(), int(u_async), 2, None)
+    L().mlp_backward_post(W3, G, D, H, xd.data_ptr(), D, 0, B, h1.data_ptr(), h2.data_ptr(), dqd.data_ptr(), ws.data_ptr(), gW1, gb1,
                           gW2, gb2, gW3, gb3, 2, None)
     torch.cuda.synchronize()
     split = {n: ar.g[n].cpu().clone() for n in uo.PARAM_NAMES}
@@ -511,10 +512,63 @@ def test_split_critic_backward_matches_oracle(G, D, H, B):
         gu.assert_close(split[n].numpy(), want.numpy(), 1e-4, 1e-5 * float(want.abs().max()), f"split grad {n}")
     _ops.mlp_backward(ar, 0, G, xd, B, h1, h2, dqd, want_dw=True, accumulate=False, impl=2)
     torch.cuda.synchronize()
-    for n in ("W2", "b2", "W3", "b3"):   # identical operands and summation order: bit-identical
+    for n in ("W2", "b2"):               # identical operands and summation order: bit-identical
         assert torch.equal(ar.g[n].cpu(), split[n]), f"split vs one-call {n}"
-    for n in ("W1", "b1"):               # dq applied after instead of before the W2 product: rounding only
+    for n in ("W1", "b1", "W3", "b3"):   # dq applied after instead of before the W2 product / another (fixed) summation order
         gu.assert_close(ar.g[n].cpu().numpy(), split[n].numpy(), 1e-4, 2e-6 * float(split[n].abs().max()), f"split vs one-call {n}")
+
+
+@pytest.mark.parametrize("wd", [0.0, 1e-3])
+@pytest.mark.parametrize("G,D,H,B", [(10, 23, 256, 256), (2, 4, 64, 200), (3, 32, 128, 300)])
+def test_split_backward_with_fused_adam_equals_separate_adam(G, D, H, B, wd):
+    """ssac_mlp_backward_post_adam (Adam applied by the two weight-gradient kernels to the elements they produce) ==
+    ssac_mlp_backward_post followed by ssac_adam_step over the arena: same gradients, bit-identical parameters and
+    moments over three steps, step counter advanced once per call."""
+    gen = torch.Generator().manual_seed(G * 7 + H + B)
+    st = uo.MLPStack(G, D, H, 1).random_init(gen)
+    ars = [_arena_from(st), _arena_from(st)]
+    ms = [torch.zeros_like(a.flat) for a in ars]
+    vs = [torch.zeros_like(a.flat) for a in ars]
+    ctls = [torch.zeros(8, dtype=torch.int32, device=DEV) for _ in ars]
+    ws = torch.empty(L().mlp_backward_ws(G, B, H), dtype=torch.float32, device=DEV)
+    lr, b1, b2, eps = 3e-4, 0.9, 0.999, 1e-8
+    for step in range(3):
+        x = torch.randn(B, D, generator=gen).to(DEV)
+        dq = (torch.randn(G, B, 1, generator=gen) / B).to(DEV)
+        h1 = torch.empty(G, B, H, device=DEV)
+        h2 = torch.empty(G, B, H, device=DEV)
+        q = torch.empty(G, B, 1, device=DEV)
+        for k, ar in enumerate(ars):
+            from super_sac_b200 import _ops
+            _ops.mlp_forward(ar, 0, G, x, B, h1, h2, q, keep_hidden=True)
+            W1, _, W2, _, W3, _ = ar.ptrs(0)
+            gW1, gb1, gW2, gb2, gW3, gb3 = ar.ptrs(0, grad=True)
+            ar.grad.zero_()
+            L().mlp_backward_pre(W2, W3, G, H, B, h1.data_ptr(), h2.data_ptr(), ws.data_ptr(), 1, 2, None)
+            if k == 0:
+                L().mlp_backward_post(W3, G, D, H, x.data_ptr(), D, 0, B, h1.data_ptr(), h2.data_ptr(), dq.data_ptr(), ws.data_ptr(),
+                                      gW1, gb1, gW2, gb2, gW3, gb3, 2, None)
+                # Adam over every array of the arena (the alignment gaps between the arrays hold no parameters)
+                for off, n in ar.range_table(0, G):
+                    c = torch.zeros(8, dtype=torch.int32, device=DEV)
+                    c[0] = step
+                    L().adam_step(ar.flat.data_ptr() + 4 * off, ar.grad.data_ptr() + 4 * off, ms[k].data_ptr() + 4 * off,
+                                  vs[k].data_ptr() + 4 * off, n, c.data_ptr(), lr, b1, b2, eps, wd, None, 0.0, 0, None)
+            else:
+                g0 = ar.grad.data_ptr()
+                offs = [(t.data_ptr() - g0) // 4 for t in (ar.flat, ms[k], vs[k])]
+                L().mlp_backward_post_adam(W3, G, D, H, x.data_ptr(), D, 0, B, h1.data_ptr(), h2.data_ptr(), dq.data_ptr(),
+                                           ws.data_ptr(), gW1, gb1, gW2, gb2, gW3, gb3, *offs, ctls[k].data_ptr(), lr, b1, b2, eps,
+                                           wd, 2, None)
+        torch.cuda.synchronize()
+        assert ctls[1].tolist()[:5] == [step + 1, 0, 0, 0, 0]
+        for n in uo.PARAM_NAMES:
+            assert torch.equal(ars[0].g[n], ars[1].g[n]), f"step {step}: grad {n}"
+            assert torch.equal(ars[0].p[n], ars[1].p[n]), f"step {step}: param {n}"
+        for name in uo.PARAM_NAMES:
+            off, n = ars[0].offsets[name], G * ars[0].net_stride[name]
+            assert torch.equal(ms[0][off:off + n], ms[1][off:off + n]), f"step {step}: exp_avg {name}"
+            assert torch.equal(vs[0][off:off + n], vs[1][off:off + n]), f"step {step}: exp_avg_sq {name}"
 
 
 @pytest.mark.parametrize("G,S,A,H,B", [(10, 17, 6, 256, 256), (2, 3, 1, 64, 100), (3, 11, 12, 128, 130)])
