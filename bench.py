@@ -243,7 +243,8 @@ def run_gpu_arm(args, cfg, rank, world, local_rank):
         """push (H2D) + update + Polyak + logged scalars read on the host, every step.  lazy: the drop-in call returns
         after cudaGraphLaunch and step k's scalars are read while step k+1 runs (one step late, every step); strict: the
         call itself waits for them."""
-        graphed.enable_auto_graphs(True, lazy_logs=lazy)   # the drop-in calls replay captured graphs from their third call on
+        # the drop-in calls replay captured graphs from their third call on; lazy: consecutive updates also overlap on the device
+        graphed.enable_auto_graphs(True, lazy_logs=lazy, pipeline=lazy and not args.no_pipeline)
         prev = {"logs": None, "sum": 0.0}
 
         def e2e_step(k):

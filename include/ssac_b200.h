@@ -349,6 +349,19 @@ int ssac_peer_wait(const void* my_buf_dev, int64_t half_bytes, int64_t nbytes, c
                    const uint32_t* epoch_dev, void* out_dev, const int32_t* row_index_dev, int n_rows, int64_t row_bytes,
                    void* stream);
 
+/* ---- host-side helpers of the graph-replayed path (graphed.py) ---------------------------------------------------- */
+/* Raw runtime calls behind one C call each (handles: cudaEvent_t / cudaStream_t / cudaGraphExec_t as void*): what a
+ * training loop does per update on the host is a graph launch plus a few event operations.
+ * ssac_graph_launch: cudaGraphLaunch on `stream` [+ record done_event behind it].
+ * ssac_pipelined_launch: record caller_ready_event on caller_stream, make launch_stream wait for it, launch the graph on
+ * launch_stream [+ record done_event]: an update that follows everything the caller has issued so far without the
+ * caller's stream having to wait for the update (graphed._Cross). */
+int ssac_event_record(void* event, void* stream);
+int ssac_stream_wait_event(void* stream, void* event);
+int ssac_graph_launch(void* graph_exec, void* stream, void* done_event);
+int ssac_pipelined_launch(void* graph_exec, void* launch_stream, void* caller_stream, void* caller_ready_event,
+                          void* done_event);
+
 #ifdef __cplusplus
 }
 #endif

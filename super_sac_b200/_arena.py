@@ -181,7 +181,9 @@ class FlatAdam:
             # optimizer.load_state_dict() replaces optimizer.state with fresh tensors: the fused step would keep using its
             # private moments and silently ignore the loaded ones.  Probe one parameter: if its exp_avg no longer aliases
             # the flat buffer, re-import the state (the constructor copies exp_avg / exp_avg_sq / step back in).
-            p0 = next(iter(arena.parameters()), None)
+            p0 = cur.__dict__.get("_probe")
+            if p0 is None:   # (walking the module tree on every update call costs more than the probe itself)
+                p0 = cur._probe = next(iter(arena.parameters()), None)
             st = optimizer.state.get(p0) if p0 is not None else None
             if st is None or "exp_avg" not in st or st["exp_avg"].data_ptr() != cur.m.data_ptr() + 4 * arena.offsets["W1"]:
                 cur = None

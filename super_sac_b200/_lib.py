@@ -128,9 +128,30 @@ def require_device(index):
         _device_ok.add(index)
 
 
+_forced_stream = None
+
+
+class on_stream:
+    """Route every entry-point call inside the block to the raw stream ``ptr`` (cheaper than torch.cuda.stream(...) when
+    the callee only needs the handle)."""
+
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+    def __enter__(self):
+        global _forced_stream
+        self.prev, _forced_stream = _forced_stream, self.ptr
+
+    def __exit__(self, *a):
+        global _forced_stream
+        _forced_stream = self.prev
+
+
 def stream_ptr():
     """Raw handle of torch's current CUDA stream on the current device (the private C accessor is an order of
     magnitude cheaper than building a torch.cuda.Stream object on every entry-point call)."""
+    if _forced_stream is not None:
+        return _forced_stream
     import torch
 
     try:

@@ -14,7 +14,7 @@ import random
 import torch
 from torch import nn
 
-from . import _arena, _ops, _rng, adv_estimator, nets, popart
+from . import _arena, _ops, _rng, adv_estimator, graphed, nets, popart
 
 
 class _EnsembleMLPFn(torch.autograd.Function):
@@ -234,10 +234,12 @@ class Agent:
         yield "contrastive.pt", self.contrastive_model
 
     def save(self, path):
+        graphed.join()
         for name, module in self._files():
             torch.save(module.state_dict(), os.path.join(path, name))
 
     def load(self, path):
+        graphed.join()
         dev = self._critic_arena.device
         for name, module in self._files():
             module.load_state_dict(torch.load(os.path.join(path, name), map_location=dev))
@@ -276,6 +278,7 @@ class Agent:
 
     def forward(self, state, from_cpu=True, num_envs=1, rolling=False):
         """Greedy action: the mean over the ensemble of each actor's mean action (reference agent.py:204-226)."""
+        graphed.join()
         if from_cpu:
             state = self._process_obs(state, num_envs)
         self.eval()
@@ -297,6 +300,7 @@ class Agent:
         device both run through the grouped kernels at B = num_envs (one launch per actor proposal, ONE launch for all
         E x N critics on all E x envs candidates); ``return_dist`` needs the torch distribution object and keeps the
         nn.Module path."""
+        graphed.join()
         if from_cpu:
             obs = self._process_obs(obs, num_envs)
         with torch.no_grad():

@@ -67,7 +67,12 @@ def critic_update(buffer, agent, target_agent, critic_optimizer, encoder_optimiz
             buffer.total_sample_calls += agent.ensemble_size
 
         refs = (buffer, agent, target_agent, critic_optimizer, encoder_optimizer, tuple(log_alphas), augmenter)
-        return graphed.run_cached(key, lambda: _critic_update_impl(*args), on_replay, refs=refs)
+        # cross-call pipelining (graphed._Cross) covers what lu.pipelined_updates covers, minus PopArt (device state that
+        # both sides of an update touch)
+        cross_ok = (agent.ensemble_size == 1 and weight_type is None and not any(bool(p) for p in agent.popart)
+                    and lu.side_stream(agent._critic_arena.device) is not None)
+        return graphed.run_cached(key, lambda: _critic_update_impl(*args), on_replay, refs=refs, cross_ok=cross_ok)
+    graphed.join()
     return _critic_update_impl(*args)
 
 
@@ -184,6 +189,7 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
                 # batch, which the front stream gathered
                 online = main
                 main.wait_event(batch_ready)
+                pipe.cross_before_online(main)
             else:
                 online = side
                 side.wait_stream(main)
@@ -238,6 +244,7 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
         dxg = torch.empty((N, B, S + A), dtype=torch.float32, device=dev) if need_ds else None
         if pipe is not None:
             pipe.join_deferred(torch.cuda.current_stream(dev))   # the previous update's logged gradient norm reads what follows overwrites
+            pipe.cross_before_grads(torch.cuda.current_stream(dev))
         if split_bwd and fuse_adam:
             # Adam applied by the two weight-gradient reductions themselves (no optimiser pass on the chain)
             if pipe is not None:
@@ -276,6 +283,7 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
                                                   zero=logs.take_unzeroed())
                 rd = lu.sample_move_and_augment(buffer=buffer, batch_size=B, augmenter=augmenter, aug_mix=aug_mix, per=per,
                                                 _idx=draws["idx"])
+                pipe.cross_after_gather()
                 batch_ready = torch.cuda.Event()
                 batch_ready.record(pipe.front)
             member_step(i, draws, rd, 0, batch_ready)
@@ -326,6 +334,8 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
         if pipe is not None:
             pipe.main_wait_polyak(torch.cuda.current_stream(dev))   # a Polyak step on the auxiliary stream still reads these
         opt.step(stream, max_norm=critic_clip if critic_clip else None)
+    if pipe is not None:
+        pipe.cross_after_adam(torch.cuda.current_stream(dev))
     if side is not None:
         if pipe is not None and adam_done:
             pipe.defer_join(side)   # nothing on the caller's stream needs the logged norm before the next backward

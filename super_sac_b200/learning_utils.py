@@ -12,7 +12,7 @@ import random
 import numpy as np
 import torch
 
-from . import _lib, _logs, _ops, _rng, augmentations, parallel
+from . import _lib, _logs, _ops, _rng, augmentations, graphed, parallel
 from ._arena import MLPArena
 
 LOG_SQRT_2PI = math.log(math.sqrt(2 * math.pi))
@@ -72,23 +72,31 @@ def _arena_of(module):
 
 
 def _multi_table(target, source):
-    """Device pointer table for arbitrary module pairs (user encoders); cached per pair, rebuilt if storage moved."""
-    tp, sp = list(target.parameters()), list(source.parameters())
-    sig = tuple((t.data_ptr(), s.data_ptr(), t.numel()) for t, s in zip(tp, sp))
+    """Device pointer table for arbitrary module pairs (user encoders); cached per pair, rebuilt if storage moved.
+    (The cache keeps the parameter tensors themselves: re-validating is a data_ptr() per tensor, not a walk over the
+    module tree on every Polyak step.)"""
     key = (id(target), id(source))
     cur = _polyak_tables.get(key)
-    if cur is None or cur[0] != sig:
-        if not sig:
-            cur = (sig, None, 0)
-        else:
-            for t, s in zip(tp, sp):
-                if t.dtype != torch.float32 or s.dtype != torch.float32 or not t.is_contiguous() or not s.is_contiguous():
-                    raise NotImplementedError("soft_update: parameters must be contiguous fp32")
-            flat = [v for e in sig for v in e]
-            table = torch.tensor(flat, dtype=torch.int64, device=tp[0].device)
-            cur = (sig, table, max(e[2] for e in sig))
-        _polyak_tables[key] = cur
-    return cur
+    if cur is not None:
+        sig, table, max_numel, tp, sp, owners = cur
+        if owners[0]() is target and owners[1]() is source and all(
+                t.data_ptr() == e[0] and q.data_ptr() == e[1] for t, q, e in zip(tp, sp, sig)):
+            return sig, table, max_numel
+    tp, sp = list(target.parameters()), list(source.parameters())
+    sig = tuple((t.data_ptr(), q.data_ptr(), t.numel()) for t, q in zip(tp, sp))
+    if not sig:
+        table, max_numel = None, 0
+    else:
+        for t, q in zip(tp, sp):
+            if t.dtype != torch.float32 or q.dtype != torch.float32 or not t.is_contiguous() or not q.is_contiguous():
+                raise NotImplementedError("soft_update: parameters must be contiguous fp32")
+        flat = [v for e in sig for v in e]
+        table = torch.tensor(flat, dtype=torch.int64, device=tp[0].device)
+        max_numel = max(e[2] for e in sig)
+    import weakref
+
+    _polyak_tables[key] = (sig, table, max_numel, tp, sp, (weakref.ref(target), weakref.ref(source)))
+    return sig, table, max_numel
 
 
 @contextlib.contextmanager
@@ -96,7 +104,13 @@ def _polyak_context():
     """Inside a pipelined_updates() block a Polyak step runs on the block's auxiliary stream (see _Pipeline)."""
     p = _pipeline
     if p is None:
-        yield lambda: None
+        X = graphed.cross_active()
+        if X is None:
+            yield lambda: None
+        else:   # behind the update it follows (its Adam step), on that update's stream; the next update waits for the event
+            sp = X.stream_ptrs[X.last]
+            with _lib.on_stream(sp):
+                yield lambda: _lib.lib().event_record(X.polyak_ptr, sp)
         return
     aux = p.polyak_stream(torch.cuda.current_stream(p.device))
     with torch.cuda.stream(aux):
@@ -206,6 +220,7 @@ class _Pipeline:
         self.polyak_main = None  # the same event, for the caller's stream (its next Adam step)
         self.aux = None          # stream the Polyak steps run on
         self.deferred = []       # streams with log-only work the caller's stream has not joined yet
+        self.cross = graphed.cross_capturing()   # (state, slot): this block is ONE update captured for cross-call pipelining
         self.keep = []           # front-allocated tensors that main-stream kernels read: alive until the block ends
         self.needs_order = False  # a barrier happened: the front's next work goes behind the caller's stream as it is then
 
@@ -221,11 +236,37 @@ class _Pipeline:
         if self.dep is not None:
             self.front.wait_event(self.dep)
             self.dep = None
+            if self.cross is not None:   # one Philox stream, one set of ring readers: behind the other capture's target side
+                X, i = self.cross
+                self.front.wait_event(X.gather_done[1 - i])
 
     def front_wait_polyak(self):
         if self.polyak is not None:
             self.front.wait_event(self.polyak)
             self.polyak = None
+        if self.cross is not None:
+            self.front.wait_event(self.cross[0].polyak_done)
+
+    # ---- cross-call pipelining (graphed._Cross): external event nodes of the captured update -------------------------
+    def cross_after_gather(self):
+        if self.cross is not None:
+            X, i = self.cross
+            X.gather_done[i].record(self.front)
+
+    def cross_before_online(self, main):
+        if self.cross is not None:   # the online parameters: behind the other capture's Adam step
+            X, i = self.cross
+            main.wait_event(X.adam_done[1 - i])
+
+    def cross_before_grads(self, main):
+        if self.cross is not None:   # the gradient arrays / backward workspace: behind everything of the other capture
+            X, i = self.cross
+            main.wait_event(X.tail_done[1 - i])
+
+    def cross_after_adam(self, main):
+        if self.cross is not None:
+            X, i = self.cross
+            X.adam_done[i].record(main)
 
     def polyak_stream(self, main):
         """Polyak steps run on a stream of their own: they follow the Adam step at the caller's tail, but the caller's next
@@ -256,6 +297,8 @@ class _Pipeline:
         if self.polyak_main is not None:
             main.wait_event(self.polyak_main)
             self.polyak_main = None
+        if self.cross is not None:
+            main.wait_event(self.cross[0].polyak_done)
 
 
 _pipeline = None
@@ -312,6 +355,8 @@ def pipeline_barrier():
     """Join the front stream into the caller's stream and order its next work after the caller's (an entry point that
     changes what the front reads -- actor update, buffer writes -- or draws random numbers on the caller's stream)."""
     p = _pipeline
+    if p is None:
+        graphed.join()
     if p is not None:
         main = torch.cuda.current_stream(p.device)
         main.wait_stream(p.front)

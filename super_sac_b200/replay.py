@@ -13,7 +13,7 @@ transition -- size the capacity for the 180 GB of a B200 (1.4 M pixel transition
 import numpy as np
 import torch
 
-from . import _lib, _ops, _rng
+from . import _lib, _ops, _rng, graphed
 
 
 def _default_device():
@@ -248,6 +248,7 @@ class ReplayBuffer:
         return np.array([pos])
 
     def push(self, state, action, reward, next_state, done, priorities=None, **kwargs):
+        graphed.before_push()   # (cross-call pipelined updates: the latest gather may still read the slot this overwrites)
         self._ensure_storage(state, action)
         if np.asarray(action).ndim == 1 and (priorities is None or np.ndim(priorities) == 0):
             p = self._max_priority if priorities is None else float(priorities)
@@ -291,11 +292,13 @@ class ReplayBuffer:
 
     # --- reference API ---------------------------------------------------------------------------------
     def sample(self, batch_size):
+        graphed.join()
         self.total_sample_calls += 1
         idx, w = self.sample_indices_per(batch_size)
         return self._storage.gather(idx), w, idx.cpu().numpy()
 
     def sample_uniform(self, batch_size):
+        graphed.join()
         self.total_sample_calls += 1
         idx = self.sample_indices_uniform(batch_size)
         return self._storage.gather(idx), idx.cpu().numpy()
@@ -303,6 +306,8 @@ class ReplayBuffer:
     def update_priorities(self, idxes, priorities):
         """idxes / priorities: numpy arrays (reference signature) or device tensors (no host round trip)."""
         assert len(idxes) == len(priorities)
+        if not torch.cuda.is_current_stream_capturing():
+            graphed.join()
         if torch.is_tensor(priorities):
             idx_dev = idxes if torch.is_tensor(idxes) else torch.from_numpy(np.asarray(idxes, dtype=np.int64)).to(self.device)
             pr = priorities.to(torch.float64)

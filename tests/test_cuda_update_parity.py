@@ -408,6 +408,86 @@ def test_auto_graph_replay_equals_eager():
         gu.assert_close(float(l1[k]), float(l0[k]), 1e-5, 1e-7, f"log {k}")
 
 
+@pytest.mark.parametrize("shape", [(4, 64, 64), (10, 256, 256)], ids=["small", "redq"])
+def test_cross_call_pipelined_updates_equal_eager(shape):
+    """graphed.enable_auto_graphs(pipeline=True): consecutive critic_update calls overlap on the device (two alternating
+    captures on two streams, ordered by external event nodes), with a buffer.push before every update, a Polyak step after
+    every second one and an actor + temperature update every fifth -- exactly the calls a training loop makes.  Same Philox
+    seed => bit-identical parameters and replay ring, same logged scalars as the eager run."""
+    import copy
+    from itertools import chain
+
+    import cuda_util as cu
+    import super_sac_b200 as ssb
+    from super_sac_b200 import augmentations, graphed, learning, learning_utils as lu, nets
+
+    N, H, B = shape
+    steps = 23
+
+    def run(mode):
+        ssb.manual_seed(13)
+        torch.manual_seed(13)
+        agent = ssb.Agent(act_space_size=6, encoder=cu.IdentityEncoder(17), actor_network_cls=nets.mlps.ContinuousStochasticActor,
+                          critic_network_cls=nets.mlps.ContinuousCritic, ensemble_size=1, num_critics=N, hidden_size=H,
+                          auto_rescale_targets=False, log_std_low=-5.0, log_std_high=2.0)
+        agent.to("cuda")
+        target = copy.deepcopy(agent)
+        rng = np.random.default_rng(0)
+        n = 512   # small ring: pushes wrap around and overwrite rows that are being sampled
+        buf = ssb.replay.ReplayBuffer(n, device="cuda")
+        buf.load_experience({"obs": rng.standard_normal((n - 7, 17), dtype=np.float32)}, rng.uniform(-1, 1, (n - 7, 6)).astype(np.float32),
+                            rng.standard_normal(n - 7, dtype=np.float32), {"obs": rng.standard_normal((n - 7, 17), dtype=np.float32)},
+                            rng.uniform(size=n - 7) < 0.05)
+        c_opt = torch.optim.Adam(chain(*(c.parameters() for c in agent.critics)), lr=3e-4)
+        a_opt = torch.optim.Adam(chain(*(a.parameters() for a in agent.actors)), lr=3e-4)
+        e_opt = torch.optim.Adam(agent.encoder.parameters(), lr=1e-4)
+        la = [torch.tensor([-2.3], device="cuda", requires_grad=True)]
+        al_opt = [torch.optim.Adam([la[0]], lr=1e-4, betas=(0.5, 0.999))]
+        aug = augmentations.AugmentationSequence([augmentations.IdentityAug(B)])
+        tr = np.random.default_rng(1)
+        graphed.enable_auto_graphs(mode != "eager", pipeline=(mode == "pipeline"))
+        all_logs = []
+        try:
+            for k in range(steps):
+                buf.push({"obs": tr.standard_normal(17, dtype=np.float32)}, tr.uniform(-1, 1, 6).astype(np.float32), float(tr.standard_normal()),
+                         {"obs": tr.standard_normal(17, dtype=np.float32)}, bool(tr.uniform() < 0.1))
+                logs, rds = learning.critic_update(
+                    buffer=buf, agent=agent, target_agent=target, critic_optimizer=c_opt, encoder_optimizer=e_opt, log_alphas=la,
+                    batch_size=B, gamma=0.99, critic_clip=None, encoder_clip=None, target_critic_ensemble_n=2,
+                    weighted_bellman_temp=None, weight_type=None, pop=False, augmenter=aug, encoder_lambda=0.0,
+                    random_process=None, noise_clip=None, aug_mix=0.0)
+                all_logs.append(logs)
+                if k % 2 == 0:
+                    lu.soft_update(target.critics[0], agent.critics[0], 0.005)
+                if k % 5 == 4:
+                    learning.online_actor_update(
+                        buffer=buf, agent=agent, pop=False, actor_optimizer=a_opt, log_alphas=la, batch_size=B, clip=None,
+                        random_process=None, noise_clip=None, augmenter=aug, aug_mix=0.0, premade_replay_dicts=rds)
+                    learning.alpha_update(buffer=buf, agent=agent, optimizers=al_opt, batch_size=B, log_alphas=la, augmenter=aug,
+                                          aug_mix=0.0, target_entropy=-6.0, premade_replay_dicts=rds, discrete=False)
+            all_logs = [dict(l) for l in all_logs]   # (lazy logs resolve here)
+            graphed.join()
+            torch.cuda.synchronize()
+        finally:
+            graphed.enable_auto_graphs(False)
+        assert c_opt._ssac_flat_adam.steps == steps and int(c_opt._ssac_flat_adam.ctl[0]) == steps
+        return agent, target, la, buf, all_logs
+
+    a0, t0, la0, b0, l0 = run("eager")
+    a1, t1, la1, b1, l1 = run("pipeline")
+    assert torch.equal(a0._critic_arena.flat, a1._critic_arena.flat)
+    assert torch.equal(t0._critic_arena.flat, t1._critic_arena.flat)
+    assert torch.equal(a0._actor_arena.flat, a1._actor_arena.flat)
+    assert torch.equal(la0[0], la1[0])
+    assert torch.equal(b0._storage.s_stack["obs"], b1._storage.s_stack["obs"])
+    for k, (x, y) in enumerate(zip(l0, l1)):
+        assert set(x.keys()) == set(y.keys())
+        for key in x:
+            if key.startswith("gradients/"):
+                continue   # the logged member is a host-side random.choice (frozen at capture)
+            gu.assert_close(float(y[key]), float(x[key]), 1e-5, 1e-7, f"step {k} log {key}")
+
+
 @pytest.mark.parametrize("captured", [False, True], ids=["eager", "graph"])
 def test_pipelined_update_block_equals_sequential(captured):
     """lu.pipelined_updates(): the target side of update k+1 runs next to update k's backward / Adam on its own stream.

@@ -45,3 +45,18 @@ if __name__ == "__main__":
     L = _lib.lib()
     print(f"polyak C2 (8.7 MB)   {timeit(lambda: L.polyak(t.data_ptr(), p.data_ptr(), n, 0.005, _lib.stream_ptr())):6.1f} us")
     print(f"adam   C2 (20 MB)    {timeit(lambda: L.adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, ctl.data_ptr(), 3e-4, .9, .999, 1e-8, 0., None, 0., 0, _lib.stream_ptr())):6.1f} us")
+    # split critic backward at the REDQ shape: u GEMM (_pre) and the two branches of _post
+    G, D, H, B = 10, 23, 256, 256
+    ar = MLPArena(G, D, H, 1, DEV); ar.flat.normal_(0, 0.05)
+    x = torch.randn(B, D, device=DEV); h1 = torch.rand(G, B, H, device=DEV); h2 = torch.rand(G, B, H, device=DEV)
+    dq = torch.randn(G, B, 1, device=DEV) / B
+    ws = torch.empty(L.mlp_backward_ws(G, B, H), dtype=torch.float32, device=DEV)
+    W1, _, W2, _, W3, _ = ar.ptrs(0)
+    gr = ar.ptrs(0, grad=True)
+    pre = lambda a: L.mlp_backward_pre(W2, W3, G, H, B, h1.data_ptr(), h2.data_ptr(), ws.data_ptr(), a, 2, _lib.stream_ptr())
+    post = lambda: L.mlp_backward_post(W3, G, D, H, x.data_ptr(), D, 0, B, h1.data_ptr(), h2.data_ptr(), dq.data_ptr(), ws.data_ptr(), *gr, 2, _lib.stream_ptr())
+    print(f"split bwd C2: _pre (u GEMM, gated A)            {timeit(lambda: pre(0)):6.1f} us")
+    print(f"split bwd C2: _post, branches side by side      {timeit(post):6.1f} us")
+    L.set_overlap(0)
+    print(f"split bwd C2: _post, branches in series         {timeit(post):6.1f} us   (gW1 reduction = series - gW2 GEMM)")
+    L.set_overlap(1)

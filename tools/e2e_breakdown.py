@@ -1,46 +1,44 @@
 #!/usr/bin/env python
-"""Host-side breakdown of one end-to-end step (the `e2e` leg of bench.py): push, update call, Polyak, log fetch."""
+"""Host-side breakdown of one end-to-end step (the `e2e` leg of bench.py): push, update call, Polyak, log read."""
 import os
 import sys
 import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 import torch  # noqa: E402
 
-import bench  # noqa: E402
-from super_sac_b200 import augmentations, graphed, learning, learning_utils as lu  # noqa: E402
+import benchlib as bl  # noqa: E402
+import super_sac_b200 as ssb  # noqa: E402
+from super_sac_b200 import graphed  # noqa: E402
 
-cfg = dict(bench.CONFIGS["redq"])
-cfg["buffer"] = 200_000
-agent, target, critic_opt, enc_opt, log_alphas, buf = bench.build_gpu(cfg, torch.device("cuda", 0))
-B = cfg["B"]
-kw = dict(buffer=buf, agent=agent, target_agent=target, critic_optimizer=critic_opt, encoder_optimizer=enc_opt,
-          log_alphas=log_alphas, batch_size=B, gamma=0.99, critic_clip=None, encoder_clip=None,
-          target_critic_ensemble_n=cfg["M"], weighted_bellman_temp=None, weight_type=None, pop=False,
-          augmenter=augmentations.AugmentationSequence([augmentations.IdentityAug(B)]), encoder_lambda=0.0,
-          random_process=None, noise_clip=None, aug_mix=0.0)
-hs, ha, hr, hs1, hd = bench.synthetic_transitions(cfg, 4096, seed=1)
-graphed.enable_auto_graphs(True)
-acc = {"push": 0.0, "update call (graph launch + log fetch)": 0.0, "polyak": 0.0}
-N = 2000
+W = bl.Workload(ssb, "redq", torch.device("cuda", 0), buffer_size=200_000, fill_on_device=True)
+tr = W.host_transitions(4096, seed=1)
+graphed.enable_auto_graphs(True, lazy_logs=True, pipeline="--pipeline" in sys.argv)
+acc = {"push": 0.0, "critic_update call": 0.0, "polyak": 0.0, "read previous logs": 0.0}
+N = 3000
+prev = {"logs": None}
 
 
 def step(k, rec):
-    j = k % 4096
     t0 = time.perf_counter()
-    buf.push({"obs": hs[j]}, ha[j], float(hr[j]), {"obs": hs1[j]}, bool(hd[j]))
+    W.push(tr, k % 4096)
     t1 = time.perf_counter()
-    logs, _ = learning.critic_update(**kw)
+    logs = W.critic_update()[0]
     t2 = time.perf_counter()
-    if k % cfg["target_delay"] == 0:
-        for ac, tc in zip(agent.critics, target.critics):
-            lu.soft_update(tc, ac, cfg["tau"])
+    if k % W.cfg["target_delay"] == 0:
+        W.polyak()
     t3 = time.perf_counter()
+    if prev["logs"] is not None:
+        float(prev["logs"]["losses/critic_overall_loss"])
+    prev["logs"] = logs
+    t4 = time.perf_counter()
     if rec:
         acc["push"] += t1 - t0
-        acc["update call (graph launch + log fetch)"] += t2 - t1
+        acc["critic_update call"] += t2 - t1
         acc["polyak"] += t3 - t2
+        acc["read previous logs"] += t4 - t3
 
 
 for k in range(10):
@@ -57,7 +55,7 @@ for k, v in acc.items():
 import cProfile, pstats
 pr = cProfile.Profile()
 pr.enable()
-for k in range(500):
+for k in range(1000):
     step(k, False)
 pr.disable()
-pstats.Stats(pr).sort_stats("cumulative").print_stats(28)
+pstats.Stats(pr).sort_stats("tottime").print_stats(30)
