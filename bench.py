@@ -40,6 +40,7 @@ import benchlib as bl  # noqa: E402
 from benchlib import CONFIGS  # noqa: E402
 
 METRIC = "sac_gradient_updates_per_sec"
+_emit = lambda line: print(line, flush=True)   # noqa: E731  (replaced in main)
 
 
 def base_line(args, cfg, world):
@@ -66,7 +67,7 @@ def run_reference_arm(args, cfg, rank, world):
                                    f"(best of the sweep {[(r['threads'], round(r['updates_per_s'], 1)) for r in sweep]})"},
         "e2e": {"value": ups, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
-    print(json.dumps(line), flush=True)
+    _emit(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -340,7 +341,7 @@ def run_gpu_arm(args, cfg, rank, world, local_rank):
         "sharded_parity": sharded_parity, "sharded_ensemble": sharded, "secondary": secondary,
         "sample_logs": {k: float(v) for k, v in list(glogs.items())[:4]},
     })
-    print(json.dumps(line), flush=True)
+    _emit(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
 
@@ -582,6 +583,22 @@ def dominant_kernel_roofline(args, cfg, W):
                     "L2-resident inside the step"}
 
 
+def _keep_stdout_for_the_json_line():
+    """Everything that writes to fd 1 during the run (NCCL's version banner, diagnostics of the parity check) goes to
+    stderr; the ONE JSON line is written to the original stdout."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    out = os.fdopen(saved, "w")
+    real_print = print
+
+    def emit(line):
+        out.write(line + "\n")
+        out.flush()
+
+    return emit
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -599,6 +616,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    global _emit
+    _emit = _keep_stdout_for_the_json_line()
     if args.impl == "reference":
         run_reference_arm(args, cfg, rank, world)
         return
