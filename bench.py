@@ -362,6 +362,10 @@ def run_secondary(args, sampler):
             if name == "drqv2":
                 with sampler.region():
                     ent["sample_move_and_augment"] = time_pixel_sampling(W)
+                    try:
+                        ent["nstep_frame_ring"] = time_nstep_ring_sampling(W)
+                    except Exception as e:  # noqa: BLE001  (a secondary figure)
+                        ent["nstep_frame_ring"] = {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
             del W
             torch.cuda.empty_cache()
             cpu_steps = {"sac": 40, "sunrise": 20, "afbc": 5, "drqv2": 2}[name]
@@ -420,6 +424,41 @@ def time_pixel_sampling(W):
     peaks = bl.measured_peaks()
     return {"ms": ms, "algorithmic_MB": nbytes / 1e6, "GBps": nbytes / ms / 1e6, "frac_of_hbm_peak": nbytes / ms / 1e6 / peaks["hbm_gbs"],
             "note": "o and o1: u8 read + fp32 written; includes the index / shift draw and the small-array gather launches"}
+
+
+def time_nstep_ring_sampling(W, n_frames=12_000):
+    """the same DrQv2 batch drawn from the frame-deduplicated one-step ring (NStepReplayBuffer, n_step 3,
+    3 stacked RGB frames): device bytes per stored transition and the time of sample_move_and_augment, next to the classic
+    ring (two copies of the whole stack per transition, n-step returns built on the host)."""
+    import super_sac_b200 as ssb
+    from super_sac_b200 import learning_utils as lu
+
+    B = W.cfg["B"]
+    C, H, Wd = W.cfg["pixels"]
+    k, cf = 3, C // 3
+    rng = np.random.default_rng(5)
+    nb = ssb.replay.NStepReplayBuffer(n_frames, n_step=3, gamma=0.99, frame_stack=k, device=W.device, validate=False)
+    A = W.cfg["A"]
+    t, frames = 0, None
+    t0 = time.perf_counter()
+    while t < n_frames:
+        T = 500
+        frames = rng.integers(0, 256, (T + 1, cf, H, Wd), dtype=np.uint8)
+        stack = lambda i: {"pixels": np.concatenate([frames[max(i - j, 0)] for j in range(k - 1, -1, -1)], 0)}   # noqa: E731
+        for i in range(T):
+            nb.push(stack(i), rng.uniform(-1, 1, A).astype(np.float32), float(rng.standard_normal()), stack(i + 1), False,
+                    terminate_traj=(i == T - 1))
+        t += T
+    torch.cuda.synchronize()
+    push_us = (time.perf_counter() - t0) / t * 1e6
+    ms = bl.timed_events(lambda k_: lu.sample_move_and_augment(nb, B, W.augmenter, 1.0, per=False), 50, warmup=5)
+    nbytes = 2 * (B * C * H * Wd * 1 + B * C * H * Wd * 4)
+    peaks = bl.measured_peaks()
+    classic = 2 * C * H * Wd + 4 * A + 5
+    return {"ms": ms, "algorithmic_MB": nbytes / 1e6, "GBps": nbytes / ms / 1e6, "frac_of_hbm_peak": nbytes / ms / 1e6 / peaks["hbm_gbs"],
+            "bytes_per_transition": nb.bytes_per_transition(), "classic_ring_bytes_per_transition": classic,
+            "host_push_us_incl_frame_generation": push_us, "ring_frames": n_frames,
+            "note": "one-step ring, every frame stored once; n-step return, next-state stack and done flag assembled by the sampler"}
 
 
 def hbm_kernels():

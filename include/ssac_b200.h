@@ -111,6 +111,26 @@ int ssac_gather_aug_u8(const uint8_t* src_dev, float* dst_dev, const int64_t* id
                        const float* noise_dev, int B, int C, int H, int W, int pad, int pad_mode, int aug_rows,
                        void* stream);
 
+/* The same gather over a ring of SINGLE FRAMES (frame-deduplicated layout): an observation is C consecutive
+ * planes starting at frame first_frame_dev[b] (a monotonically increasing frame counter; taken modulo ring_frames), so a
+ * frame stack s_t = [f_{t-k+1} .. f_t] and its successor s_{t+1} share k-1 stored frames and every frame is stored once
+ * (reference layout: s and s1 stacks side by side, replay.py:10-61: 2k copies).  pad_mode 0..2. */
+int ssac_gather_aug_u8_ring(const uint8_t* frames_dev, float* dst_dev, const int64_t* first_frame_dev,
+                            int64_t planes_per_frame, int64_t ring_frames, const int32_t* shift_dev, const float* noise_dev,
+                            int B, int C, int H, int W, int pad, int pad_mode, int aug_rows, void* stream);
+/* On-the-fly n-step transitions (main.py:353-365, learning_utils.py:139-151 moved into the sampler).  The ring holds
+ * one-step transitions in time order; valid_ring_dev (int64[cap], a FIFO whose oldest entry sits at scalars_dev[1] =
+ * v_tail; scalars_dev[0] = number of entries, the `n_filled` the index draw uses) lists the slots whose n-step window
+ * lies inside one episode.  For position j_dev[b]: idx_start = that slot, idx_last = slot of step t+n-1 (its next state
+ * and done flag are the transition's), R = r_t + gamma r_{t+1} + ... accumulated left to right like the reference's loop:
+ * in float64 over reward64_dev, or in float32 over reward32_dev (float32(gamma^i) * r_i: what NumPy does with np.float32
+ * rewards); gamma_pows_dev float64[n_step] = gamma**i.  first_frame_dev (nullable, frame-deduplicated layout): frame
+ * counter of each step's state stack -> frame_s / frame_s1 for ssac_gather_aug_u8_ring. */
+int ssac_nstep_resolve(const int64_t* j_dev, int B, const int64_t* valid_ring_dev, const int64_t* scalars_dev, int64_t cap,
+                       int n_step, const double* reward64_dev, const float* reward32_dev, const double* gamma_pows_dev,
+                       const int64_t* first_frame_dev, int64_t* idx_start_dev, int64_t* idx_last_dev, float* R_dev,
+                       int64_t* frame_s_dev, int64_t* frame_s1_dev, void* stream);
+
 /* ---- prioritised replay: replay.py:163-190, :207-353 (float64 sum / min segment trees) ------------ */
 /* tree layout identical to the reference: value[2*capacity], root at 1, leaves at capacity + i. */
 int ssac_tree_set(double* sum_tree_dev, double* min_tree_dev, int64_t capacity, const int64_t* idx_dev,

@@ -234,11 +234,16 @@ __global__ void __launch_bounds__(256) gather_aug_u8_kernel(const uint8_t* __res
                                                             const int64_t* __restrict__ idx,
                                                             const int32_t* __restrict__ shift,
                                                             const float* __restrict__ noise, int C, int H, int W,
-                                                            int pad, int pad_mode, int aug_rows) {
+                                                            int pad, int pad_mode, int aug_rows, int64_t idx_mul,
+                                                            int64_t ring_planes) {
   extern __shared__ __align__(16) uint8_t plane[];
   const int b = blockIdx.x / C, c = blockIdx.x - b * C;
   const int64_t plane_elems = (int64_t)H * W;
-  const uint8_t* sp = src + (idx[b] * C + c) * plane_elems;
+  // classic ring of whole observations: plane idx[b] * C + c.  Frame ring (ssac_gather_aug_u8_ring): an observation is C
+  // CONSECUTIVE planes of a ring of single frames, starting at frame idx[b] (idx_mul = planes per frame), modulo the ring.
+  int64_t pl = idx[b] * idx_mul + c;
+  if (ring_planes > 0) pl %= ring_planes;
+  const uint8_t* sp = src + pl * plane_elems;
   if ((plane_elems & 15) == 0 && (((uintptr_t)sp) & 15) == 0) {
     const int4* sp4 = (const int4*)sp;
     int4* pl4 = (int4*)plane;
@@ -640,8 +645,86 @@ int ssac_gather_aug_u8(const uint8_t* src, float* dst, const int64_t* idx, const
     if (e != cudaSuccess) { set_error(std::string("ssac_gather_aug_u8 attr: ") + cudaGetErrorString(e)); return (int)e; }
   }
   gather_aug_u8_kernel<<<B * C, 256, smem, (cudaStream_t)stream>>>(src, dst, idx, shift, noise, C, H, W, pad, pad_mode,
-                                                                   aug_rows);
+                                                                   aug_rows, (int64_t)C, (int64_t)0);
   SSAC_CHECK_LAUNCH("ssac_gather_aug_u8");
+  return 0;
+}
+
+int ssac_gather_aug_u8_ring(const uint8_t* frames, float* dst, const int64_t* first_frame, int64_t planes_per_frame,
+                            int64_t ring_frames, const int32_t* shift, const float* noise, int B, int C, int H, int W, int pad,
+                            int pad_mode, int aug_rows, void* stream) {
+  SSAC_REQUIRE(frames && dst && first_frame && B > 0 && C > 0 && H > 0 && W > 0, "ssac_gather_aug_u8_ring: bad args");
+  SSAC_REQUIRE(planes_per_frame > 0 && C % planes_per_frame == 0 && ring_frames * planes_per_frame >= C,
+               "ssac_gather_aug_u8_ring: an observation is a whole number of frames of the ring");
+  SSAC_REQUIRE(pad_mode >= 0 && pad_mode <= 2, "ssac_gather_aug_u8_ring: pad_mode must be 0, 1 or 2");
+  SSAC_REQUIRE(pad_mode == 0 || shift, "ssac_gather_aug_u8_ring: shift required when pad_mode != 0");
+  SSAC_REQUIRE(pad_mode != 2 || (pad < H && pad < W), "ssac_gather_aug_u8_ring: reflect pad must be < image size");
+  const size_t smem = ((size_t)H * W + 15) & ~(size_t)15;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(gather_aug_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error(std::string("ssac_gather_aug_u8_ring attr: ") + cudaGetErrorString(e)); return (int)e; }
+  }
+  gather_aug_u8_kernel<<<B * C, 256, smem, (cudaStream_t)stream>>>(frames, dst, first_frame, shift, noise, C, H, W, pad, pad_mode,
+                                                                   aug_rows, planes_per_frame, ring_frames * planes_per_frame);
+  SSAC_CHECK_LAUNCH("ssac_gather_aug_u8_ring");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// on-the-fly n-step transitions (main.py:353-365 moved into the sampler): the ring stores ONE-step transitions in time
+// order; valid_ring lists, oldest first, the slots t whose n-step window [t, t+n-1] lies inside one episode.  For the
+// drawn position j: start slot s = valid_ring[(v_tail + j) % cap], last slot l = (s + n - 1) % cap,
+//   R = r_s + gamma^1 r_{s+1} + ... accumulated left to right exactly as the reference's Python loop does -- in float64
+//   when the environment hands out Python / float64 rewards, in float32 (float32(gamma^i) * r_i, NumPy's weak-scalar rule)
+//   when it hands out np.float32 -- and the frame indices of the two observation stacks.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) nstep_resolve_kernel(const int64_t* __restrict__ j, int B,
+                                                            const int64_t* __restrict__ valid_ring,
+                                                            const int64_t* __restrict__ scalars, int64_t cap, int n_step,
+                                                            const double* __restrict__ reward64,
+                                                            const float* __restrict__ reward32,
+                                                            const double* __restrict__ gamma_pows,
+                                                            const int64_t* __restrict__ first_frame,
+                                                            int64_t* __restrict__ idx_start, int64_t* __restrict__ idx_last,
+                                                            float* __restrict__ R, int64_t* __restrict__ frame_s,
+                                                            int64_t* __restrict__ frame_s1) {
+  pdl_wait();
+  pdl_trigger();
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int64_t v_tail = scalars[1];
+  const int64_t s = valid_ring[(v_tail + j[b]) % cap];
+  const int64_t l = (s + n_step - 1) % cap;
+  idx_start[b] = s;
+  idx_last[b] = l;
+  if (reward64) {
+    double r = reward64[s];
+    for (int i = 1; i < n_step; ++i) r = __dadd_rn(r, __dmul_rn(gamma_pows[i], reward64[(s + i) % cap]));
+    R[b] = (float)r;
+  } else {
+    float r = reward32[s];
+    for (int i = 1; i < n_step; ++i) r = __fadd_rn(r, __fmul_rn((float)gamma_pows[i], reward32[(s + i) % cap]));
+    R[b] = r;
+  }
+  if (first_frame) {
+    frame_s[b] = first_frame[s];
+    frame_s1[b] = first_frame[l] + 1;   // the next state's stack starts one frame later
+  }
+}
+
+int ssac_nstep_resolve(const int64_t* j_dev, int B, const int64_t* valid_ring_dev, const int64_t* scalars_dev, int64_t cap,
+                       int n_step, const double* reward64_dev, const float* reward32_dev, const double* gamma_pows_dev,
+                       const int64_t* first_frame_dev, int64_t* idx_start_dev, int64_t* idx_last_dev, float* R_dev,
+                       int64_t* frame_s_dev, int64_t* frame_s1_dev, void* stream) {
+  SSAC_REQUIRE(j_dev && valid_ring_dev && scalars_dev && gamma_pows_dev && idx_start_dev && idx_last_dev && R_dev,
+               "ssac_nstep_resolve: null pointer");
+  SSAC_REQUIRE((reward64_dev != nullptr) != (reward32_dev != nullptr), "ssac_nstep_resolve: exactly one reward array");
+  SSAC_REQUIRE(B > 0 && cap > 0 && n_step >= 1 && n_step <= cap, "ssac_nstep_resolve: bad sizes");
+  SSAC_REQUIRE(!first_frame_dev || (frame_s_dev && frame_s1_dev), "ssac_nstep_resolve: frame outputs missing");
+  launch_pdl(nstep_resolve_kernel, dim3((B + 255) / 256), dim3(256), 0, (cudaStream_t)stream, j_dev, B, valid_ring_dev, scalars_dev,
+             cap, n_step, reward64_dev, reward32_dev, gamma_pows_dev, first_frame_dev, idx_start_dev, idx_last_dev, R_dev,
+             frame_s_dev, frame_s1_dev);
+  SSAC_CHECK_LAUNCH("ssac_nstep_resolve");
   return 0;
 }
 

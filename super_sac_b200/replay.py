@@ -322,3 +322,6 @@ class ReplayBuffer:
         self._tree_set(torch.from_numpy(idxes.astype(np.int64)).to(self.device),
                        torch.from_numpy(priorities**self.alpha).to(self.device))
         self._max_priority = max(self._max_priority, float(np.max(priorities)))
+
+
+from .nstep_replay import NStepReplayBuffer  # noqa: E402,F401  (on-the-fly n-step + frame-deduplicated layout)
