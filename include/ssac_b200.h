@@ -369,6 +369,29 @@ int ssac_peer_wait(const void* my_buf_dev, int64_t half_bytes, int64_t nbytes, c
                    const uint32_t* epoch_dev, void* out_dev, const int32_t* row_index_dev, int n_rows, int64_t row_bytes,
                    void* stream);
 
+/* ---- DrQ pixel encoder: nets/cnns.py:37-69 (BigPixelEncoder), SURVEY 8f N3 ------------------------------------------ */
+/* obs [B,C,H,W] fp32 in 0..255 -> obs/255 - 0.5 -> conv3x3 stride 2 (C -> 32) -> 3 x conv3x3 stride 1 (32 -> 32), each + ReLU
+ * -> flatten (NCHW order, cnns.py:63) -> Linear(32*h*w, out_dim) -> LayerNorm(eps 1e-5) -> tanh, forward and backward, as
+ * implicit GEMMs on the tcgen05 tensor cores (3xTF32, fp32 accumulate) over NHWC activations; replaces the cuDNN / ATen call
+ * sequence of BigPixelEncoder.forward and its autograd.  C <= 16, H and W even, out_dim <= 64.
+ * params / grads: HOST arrays of 12 device pointers in the module's parameter order: conv1.weight [32,C,3,3], conv1.bias,
+ * conv2.weight [32,32,3,3], conv2.bias, conv3.*, conv4.*, fc.weight [out_dim, 32*h*w], fc.bias, ln.weight, ln.bias.
+ * ws_dev: caller-owned workspace of ssac_conv_encoder_ws_floats floats, ZERO-INITIALISED once by the caller (padding
+ * channels / pixels are never written); it carries the activations from a forward with save = 1 to its backward.
+ * save = 0: no backward will follow (target encoder, acting path): activations ping-pong between two buffers.
+ * out_dev f32 [B,out_dim].  backward: dout_dev = dL/dout, out_dev = the forward's output; every gradient is WRITTEN
+ * (not accumulated).  ssac_conv_encoder_ws_offsets (tests / tools): int64[24] = float offsets of {x0, y1..y4, d0, d1, wfc,
+ * gwfc, fc partials, xhat, rstd, dfc, dl} followed by {pixels per image, pitch, pixels, kf, kf padded, split size, splits,
+ * total}. */
+/* debugging switch (results do not depend on it): 0 = one TMA box per filter tap, 1 = one halo box per tile (default) */
+int ssac_set_conv_halo(int mode);
+int ssac_conv_encoder_ws_floats(int B, int C, int H, int W, int out_dim, int save, int64_t* n_floats_out);
+int ssac_conv_encoder_ws_offsets(int B, int C, int H, int W, int out_dim, int save, int64_t* offsets_out);
+int ssac_conv_encoder_forward(const float* obs_dev, int B, int C, int H, int W, int out_dim, const float* const* params,
+                              float* ws_dev, int save, float* out_dev, void* stream);
+int ssac_conv_encoder_backward(const float* dout_dev, const float* out_dev, int B, int C, int H, int W, int out_dim,
+                               const float* const* params, float* ws_dev, float* const* grads, void* stream);
+
 /* ---- host-side helpers of the graph-replayed path (graphed.py) ---------------------------------------------------- */
 /* Raw runtime calls behind one C call each (handles: cudaEvent_t / cudaStream_t / cudaGraphExec_t as void*): what a
  * training loop does per update on the host is a graph launch plus a few event operations.

@@ -1,0 +1,867 @@
+// DrQ pixel encoder (reference nets/cnns.py:37-69 BigPixelEncoder) on the 5th-generation tensor cores.
+// sm_100a only.
+//
+//   obs [B,C,H,W] (0..255)  ->  x/255 - 0.5  ->  conv3x3 s2 (32) ReLU -> 3 x [conv3x3 s1 (32) ReLU]  ->  FC  ->  LayerNorm -> tanh
+//
+// Layout.  Activations are NHWC fp32 with 32 channels = one 128-byte row per pixel, which is exactly one SWIZZLE_128B row
+// of a K-major UMMA operand: a tile of 128 consecutive pixels IS a [128 x 32] A operand and TMA drops it into shared memory
+// ready for tcgen05.mma.  Every layer keeps the SAME pixel grid -- gh x gw = H/2 x W/2 per image (42 x 42 for 84 x 84) --
+// and only the valid region shrinks (41, 39, 37, 35): with one pitch for input and output, tap (kh,kw) of a 3x3
+// convolution is a constant shift of the flat pixel index,  out[q] = sum_taps W_tap . in[q + kh*gw + kw],  so the implicit
+// GEMM needs no im2col at all: tap t of output tile q0 is the TMA box at pixel q0 + shift_t (zero-filled outside the
+// tensor).  Outputs outside the valid region are finite garbage that no valid output ever reads; the backward zeroes them.
+// The stride-2 first layer becomes a stride-1 2x2 convolution over the space-to-depth(2) image (4C channels padded to 64 =
+// two 32-channel k-blocks per tap), so it runs through the same kernel.
+//
+// Arithmetic: 3xTF32 like the MLP GEMMs: x = hi + lo, D = A_hi.[B_hi | B_lo] + A_lo.B_hi with the two B planes
+// concatenated along N (one N = 64 MMA instead of two N = 32 ones; the epilogue adds the halves).
+//
+//   conv_tc_kernel       forward (bias + ReLU) and data gradient (transposed taps, negative shifts, ReLU / valid mask):
+//                        persistent CTAs over 128-pixel tiles, warp 9 = TMA producer (one 16 KB box per tap-block),
+//                        warps 4-7 = lo planes, warp 8 = MMA issuer, warps 0-3 = epilogue out of a double-buffered TMEM
+//                        accumulator (tile i+1's MMAs run under tile i's epilogue) -> swizzled smem -> TMA store.
+//   conv_wgrad_tc_kernel weight gradient: K = pixels; A = 4 tap-blocks of the layer input side by side as the four
+//                        32-column groups of an MN-major M = 128 operand, B = dZ [pixels x 32]; each CTA reduces a
+//                        contiguous pixel range into TMEM and writes one partial; bias gradients ride on the lo pass.
+//   the FC layer         three launches of the grouped tcgen05 GEMM (split-K forward as groups; dX with the ReLU mask fused;
+//                        dW) over a zero-padded copy of the weight in the pitch layout.
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "ssac_tc_prims.cuh"
+
+namespace ssac {
+namespace cv {
+using namespace tc;
+
+constexpr int kMaxTB = 12;          // tap-blocks: 9 (3x3, 32 ch) or 8 (2x2 over the 64-channel space-to-depth image)
+constexpr int kConvStages = 4;
+constexpr int kConvThreads = 320;
+constexpr int kWBytes = 9 * 8192;   // resident weights: per tap-block 64 rows (32 hi + 32 lo) x 128 bytes
+constexpr int kConvStageBytes = 32768;   // A_hi + A_lo
+constexpr int kConvSmem = kWBytes + kConvStages * kConvStageBytes + 16384 + 1024;
+
+struct ConvP {
+  CUtensorMap tmIn;    // (channels, pixels), box 32 x 128, SWIZZLE_128B
+  CUtensorMap tmOut;   // (32, pixels), box 32 x 128, SWIZZLE_128B
+  const float* wpack;  // ntb x 8 KB shared-memory images (conv_pack_kernel)
+  const float* bias;   // mode 0
+  const float* yprev;  // mode 1: the activations whose ReLU the gradient passes through [pixels][32]
+  int ntb;
+  int shift[kMaxTB], cb[kMaxTB];
+  int ntiles, mode;
+  int64_t np;
+  int pp, pw, vh, vw;  // mode 1: pixels per image, pitch, valid rows / cols of yprev
+  // halo > 0 (32-channel layers): ONE box of hr rows per tile -- pixels base .. base + hr - 1, base = q0 + halo_base --
+  // and tap t reads it at row offset toff[t] through the start address of its UMMA descriptor, so every input pixel
+  // crosses shared memory once instead of nine times.  MEASURED on B200: the 128-byte swizzle is a function of the
+  // absolute shared-memory address, so a descriptor whose start address is offset by whole rows inside a 1024-byte
+  // aligned tile reads exactly the rows TMA wrote there -- with the descriptor's base-offset field left at 0 (setting it
+  // to (start >> 7) & 7 gives wrong results).
+  int halo, hr, halo_base;
+  int toff[kMaxTB];
+};
+constexpr int kHaloStages = 2;
+
+__global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_constant__ ConvP q) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_raw[kConvStages], bar_full[kConvStages], bar_empty[kConvStages];
+  __shared__ __align__(8) uint64_t bar_accf[2], bar_acce[2];
+  __shared__ uint32_t tmem_base_sh;
+  __shared__ float bias_sh[32];
+
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* wsm = smem;
+  uint8_t* stg = smem + kWBytes;
+  uint8_t* osm = stg + (q.halo ? kHaloStages * 2 * q.hr * 128 : kConvStages * kConvStageBytes);
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+
+  if (warp == 0) tmem_alloc(&tmem_base_sh, 128);
+  if (t == 0) {
+    for (int s = 0; s < kConvStages; ++s) {
+      mbar_init(&bar_raw[s], 1);
+      mbar_init(&bar_full[s], 128);
+      mbar_init(&bar_empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bar_accf[b], 1);
+      mbar_init(&bar_acce[b], 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  pdl_wait();
+  pdl_trigger();
+  {
+    const float4* src = reinterpret_cast<const float4*>(q.wpack);
+    float4* dst = reinterpret_cast<float4*>(wsm);
+    for (int i = t; i < q.ntb * 512; i += kConvThreads) dst[i] = __ldg(src + i);
+  }
+  if (t < 32) bias_sh[t] = q.bias ? __ldg(q.bias + t) : 0.f;
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_d = tmem_base_sh;
+  const int ntl = ((int)blockIdx.x < q.ntiles) ? (q.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int ntb = q.ntb;
+
+  if (warp == 9) {
+    // ===== TMA producer: one 16 KB box (128 pixels x 32 channels) per tap-block ====================================
+    if (lane == 0 && q.halo) {
+      const uint32_t hrb = (uint32_t)q.hr * 128u;
+      for (int i = 0; i < ntl; ++i) {
+        const int q0 = ((int)blockIdx.x + i * (int)gridDim.x) * 128;
+        const int s = i % kHaloStages, use = i / kHaloStages;
+        if (i >= kHaloStages) mbar_wait(&bar_empty[s], (uint32_t)((use - 1) & 1));
+        mbar_arrive_expect_tx(&bar_raw[s], hrb);
+        tma_load_2d(smem_u32(stg) + (uint32_t)s * 2u * hrb, &q.tmIn, &bar_raw[s], 0, q0 + q.halo_base);
+      }
+    } else if (lane == 0) {
+      int it = 0;
+      for (int i = 0; i < ntl; ++i) {
+        const int q0 = ((int)blockIdx.x + i * (int)gridDim.x) * 128;
+        for (int tb = 0; tb < ntb; ++tb, ++it) {
+          const int s = it % kConvStages, use = it / kConvStages;
+          if (it >= kConvStages) mbar_wait(&bar_empty[s], (uint32_t)((use - 1) & 1));
+          mbar_arrive_expect_tx(&bar_raw[s], 16384u);
+          tma_load_2d(smem_u32(stg + s * kConvStageBytes), &q.tmIn, &bar_raw[s], q.cb[tb] * 32, q0 + q.shift[tb]);
+        }
+      }
+    }
+  } else if (warp == 8) {
+    // ===== MMA issuer ==============================================================================================
+    const uint32_t idesc64 = instr_desc(64, 0, 0), idesc32 = instr_desc(32, 0, 0);
+    int it = 0;
+    for (int i = 0; i < ntl; ++i) {
+      const int buf = i & 1;
+      const uint32_t d = tmem_d + (uint32_t)(buf * 64);
+      if (i >= 2) {
+        mbar_wait(&bar_acce[buf], (uint32_t)(((i >> 1) - 1) & 1));   // the epilogue has drained this accumulator
+        fence_after_sync();
+      }
+      if (q.halo) {
+        const uint32_t hrb = (uint32_t)q.hr * 128u;
+        const int s = i % kHaloStages, use = i / kHaloStages;
+        mbar_wait(&bar_full[s], (uint32_t)(use & 1));
+        fence_after_sync();
+        if (lane == 0) {
+          const uint32_t h_hi = smem_u32(stg) + (uint32_t)s * 2u * hrb, h_lo = h_hi + hrb;
+          for (int tb = 0; tb < ntb; ++tb) {
+            const uint32_t roff = (uint32_t)q.toff[tb] * 128u;
+            const uint32_t b = smem_u32(wsm) + (uint32_t)tb * 8192u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint64_t dah = smem_desc(h_hi + roff + j * 32, 16u, 1024u, 2u);
+              const uint64_t dal = smem_desc(h_lo + roff + j * 32, 16u, 1024u, 2u);
+              const uint64_t db = smem_desc(b + j * 32, 16u, 1024u, 2u);
+              mma_tf32(d, dah, db, idesc64, (tb | j) != 0);
+              mma_tf32(d, dal, db, idesc32, 1u);
+            }
+          }
+          mma_commit(&bar_empty[s]);
+          mma_commit(&bar_accf[buf]);
+        }
+        __syncwarp();
+        continue;
+      }
+      for (int tb = 0; tb < ntb; ++tb, ++it) {
+        const int s = it % kConvStages, use = it / kConvStages;
+        mbar_wait(&bar_full[s], (uint32_t)(use & 1));
+        fence_after_sync();
+        if (lane == 0) {
+          const uint32_t a_hi = smem_u32(stg + s * kConvStageBytes), a_lo = a_hi + 16384u;
+          const uint32_t b = smem_u32(wsm) + (uint32_t)tb * 8192u;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint64_t dah = smem_desc(a_hi + j * 32, 16u, 1024u, 2u);
+            const uint64_t dal = smem_desc(a_lo + j * 32, 16u, 1024u, 2u);
+            const uint64_t db = smem_desc(b + j * 32, 16u, 1024u, 2u);
+            mma_tf32(d, dah, db, idesc64, (tb | j) != 0);   // A_hi . [B_hi | B_lo] -> columns 0..63
+            mma_tf32(d, dal, db, idesc32, 1u);              // A_lo . B_hi          -> columns 0..31
+          }
+          mma_commit(&bar_empty[s]);
+          if (tb == ntb - 1) mma_commit(&bar_accf[buf]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== lo planes ===============================================================================================
+    const int tl = t - 128;
+    if (q.halo) {
+      const uint32_t hrb = (uint32_t)q.hr * 128u;
+      const int n16 = q.hr * 8;
+      for (int i = 0; i < ntl; ++i) {
+        const int s = i % kHaloStages, use = i / kHaloStages;
+        mbar_wait(&bar_raw[s], (uint32_t)(use & 1));
+        uint8_t* hi = stg + (size_t)s * 2u * hrb;
+        uint8_t* lo = hi + hrb;
+        for (int k = tl; k < n16; k += 128)
+          *reinterpret_cast<float4*>(lo + k * 16) = lo4(*reinterpret_cast<const float4*>(hi + k * 16));
+        fence_async_smem();
+        mbar_arrive(&bar_full[s]);
+      }
+    }
+    const int nit = q.halo ? 0 : ntl * ntb;
+    for (int it = 0; it < nit; ++it) {
+      const int s = it % kConvStages, use = it / kConvStages;
+      mbar_wait(&bar_raw[s], (uint32_t)(use & 1));
+      uint8_t* hi = stg + s * kConvStageBytes;
+      uint8_t* lo = hi + 16384;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t off = (uint32_t)(tl + 128 * i) * 16u;
+        *reinterpret_cast<float4*>(lo + off) = lo4(*reinterpret_cast<const float4*>(hi + off));
+      }
+      fence_async_smem();
+      mbar_arrive(&bar_full[s]);
+    }
+  } else {
+    // ===== epilogue: thread = pixel = TMEM lane ====================================================================
+    const int row = t;
+    const uint32_t r7 = (uint32_t)(row & 7);
+    uint8_t* orow = osm + (uint32_t)(row >> 3) * 1024u + r7 * 128u;
+    for (int i = 0; i < ntl; ++i) {
+      const int buf = i & 1;
+      const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+      const int64_t pix = (int64_t)tile * 128 + row;
+      float4 mk[8];
+      bool valid = true;
+      if (q.mode == 1) {
+        valid = pix < q.np;
+        if (valid) {
+          const int r = (int)(pix % q.pp);
+          valid = (r / q.pw) < q.vh && (r % q.pw) < q.vw;
+        }
+        if (valid) {
+          const float4* yp = reinterpret_cast<const float4*>(q.yprev + pix * 32);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) mk[c] = __ldg(yp + c);
+        }
+      }
+      mbar_wait(&bar_accf[buf], (uint32_t)((i >> 1) & 1));
+      fence_after_sync();
+      uint32_t r0[32], r1[32];
+      const uint32_t ta = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * 64);
+      tmem_ld32_issue(ta, r0);
+      tmem_ld32_issue(ta + 32u, r1);
+      tmem_wait_ld();
+      fence_before_sync();
+      mbar_arrive(&bar_acce[buf]);
+      if (t == 0) tma_store_wait_read();                 // the previous tile's store has read the staging tile
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float4 o;
+        o.x = __uint_as_float(r0[4 * c + 0]) + __uint_as_float(r1[4 * c + 0]);
+        o.y = __uint_as_float(r0[4 * c + 1]) + __uint_as_float(r1[4 * c + 1]);
+        o.z = __uint_as_float(r0[4 * c + 2]) + __uint_as_float(r1[4 * c + 2]);
+        o.w = __uint_as_float(r0[4 * c + 3]) + __uint_as_float(r1[4 * c + 3]);
+        if (q.mode == 0) {
+          o.x = fmaxf(o.x + bias_sh[4 * c + 0], 0.f); o.y = fmaxf(o.y + bias_sh[4 * c + 1], 0.f);
+          o.z = fmaxf(o.z + bias_sh[4 * c + 2], 0.f); o.w = fmaxf(o.w + bias_sh[4 * c + 3], 0.f);
+        } else {
+          if (valid) {
+            o.x = mk[c].x > 0.f ? o.x : 0.f; o.y = mk[c].y > 0.f ? o.y : 0.f;
+            o.z = mk[c].z > 0.f ? o.z : 0.f; o.w = mk[c].w > 0.f ? o.w : 0.f;
+          } else {
+            o = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        *reinterpret_cast<float4*>(orow + (((uint32_t)c ^ r7) << 4)) = o;
+      }
+      fence_async_smem();
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (t == 0) {
+        tma_store_2d(&q.tmOut, smem_u32(osm), 0, tile * 128);
+        tma_store_commit();
+      }
+    }
+    if (t == 0) tma_store_wait_all();
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_d, 128);
+}
+
+// ---- weight gradient ---------------------------------------------------------------------------------------------
+constexpr int kWgThreads = 320;
+struct WgradP {
+  CUtensorMap tmX;   // (channels, pixels), box 32 x 32, SWIZZLE_128B_ATOM_32B
+  CUtensorMap tmD;   // (32, pixels), same box
+  float* part;       // [grid][kMaxTB][32 ci][32 co]
+  float* bpart;      // [grid][32]
+  int ntb, ng;
+  int shift[kMaxTB], cb[kMaxTB];
+  int nstages, spc;  // 32-pixel stages in total / per CTA
+};
+
+template <int NG>
+__global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_tc_kernel(const __grid_constant__ WgradP q) {
+  constexpr int kABytes = NG * 16384;             // one plane of the A operands of a stage
+  constexpr int kStage = 2 * kABytes + 8192;      // A_hi, A_lo, B_hi, B_lo
+  constexpr int kNS = (NG == 3) ? 2 : 3;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_raw[kNS], bar_full[kNS], bar_empty[kNS], bar_done;
+  __shared__ uint32_t tmem_base_sh;
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+
+  if (warp == 0) tmem_alloc(&tmem_base_sh, 256);
+  if (t == 0) {
+    for (int s = 0; s < kNS; ++s) {
+      mbar_init(&bar_raw[s], 1);
+      mbar_init(&bar_full[s], 256);
+      mbar_init(&bar_empty[s], 1);
+    }
+    mbar_init(&bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  pdl_wait();
+  pdl_trigger();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_d = tmem_base_sh;
+  const int st0 = (int)blockIdx.x * q.spc;
+  const int nst = max(0, min(q.spc, q.nstages - st0));
+
+  if (warp == 9) {
+    if (lane == 0) {
+      for (int i = 0; i < nst; ++i) {
+        const int s = i % kNS, use = i / kNS;
+        if (i >= kNS) mbar_wait(&bar_empty[s], (uint32_t)((use - 1) & 1));
+        mbar_arrive_expect_tx(&bar_raw[s], (uint32_t)(kABytes + 4096));
+        const uint32_t base = smem_u32(smem + s * kStage);
+        const int p0 = (st0 + i) * 32;
+#pragma unroll
+        for (int j = 0; j < NG * 4; ++j) {
+          const int tb = j < q.ntb ? j : 0;
+          tma_load_2d(base + (uint32_t)j * 4096u, &q.tmX, &bar_raw[s], q.cb[tb] * 32, p0 + q.shift[tb]);
+        }
+        tma_load_2d(base + 2u * kABytes, &q.tmD, &bar_raw[s], 0, p0);
+      }
+    }
+  } else if (warp == 8) {
+    const uint32_t idesc64 = instr_desc(64, 1, 1), idesc32 = instr_desc(32, 1, 1);
+    for (int i = 0; i < nst; ++i) {
+      const int s = i % kNS, use = i / kNS;
+      mbar_wait(&bar_full[s], (uint32_t)(use & 1));
+      fence_after_sync();
+      if (lane == 0) {
+        const uint32_t base = smem_u32(smem + s * kStage);
+        const uint32_t b_hi = base + 2u * kABytes;     // B_lo follows at + 4096 = the second 32-column group
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          const uint32_t a_hi = base + (uint32_t)g * 16384u, a_lo = a_hi + (uint32_t)kABytes;
+          const uint32_t d = tmem_d + (uint32_t)(g * 64);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint64_t dah = smem_desc(a_hi + j * 1024, 4096u, 512u, 1u);
+            const uint64_t dal = smem_desc(a_lo + j * 1024, 4096u, 512u, 1u);
+            const uint64_t db = smem_desc(b_hi + j * 1024, 4096u, 512u, 1u);
+            mma_tf32(d, dah, db, idesc64, (i | j) != 0);
+            mma_tf32(d, dal, db, idesc32, 1u);
+          }
+        }
+        mma_commit(&bar_empty[s]);
+        if (i == nst - 1) mma_commit(&bar_done);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== workers: lo planes + column sums of dZ (bias gradient), then the epilogue ===============================
+    float cs[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int i = 0; i < nst; ++i) {
+      const int s = i % kNS, use = i / kNS;
+      mbar_wait(&bar_raw[s], (uint32_t)(use & 1));
+      uint8_t* a_hi = smem + s * kStage;
+      uint8_t* a_lo = a_hi + kABytes;
+      uint8_t* b_hi = a_hi + 2 * kABytes;
+#pragma unroll
+      for (int k = 0; k < NG * 4; ++k) {
+        const uint32_t off = (uint32_t)(t + 256 * k) * 16u;
+        *reinterpret_cast<float4*>(a_lo + off) = lo4(*reinterpret_cast<const float4*>(a_hi + off));
+      }
+      {
+        const float4 v = *reinterpret_cast<const float4*>(b_hi + t * 16);
+        *reinterpret_cast<float4*>(b_hi + 4096 + t * 16) = lo4(v);
+        cs[0] += v.x; cs[1] += v.y; cs[2] += v.z; cs[3] += v.w;
+      }
+      fence_async_smem();
+      mbar_arrive(&bar_full[s]);
+    }
+    if (nst > 0) mbar_wait(&bar_done, 0);
+    fence_after_sync();
+    // bias gradient: chunk t of the B tile = k row t/8, physical 32-byte chunk (t/2)%4, half t%2
+    float* scr = reinterpret_cast<float*>(smem);   // every MMA has completed: the stages are free
+    {
+      const int krow = t >> 3;
+      const int col = 8 * (((t >> 1) & 3) ^ (krow & 3)) + 4 * (t & 1);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) scr[krow * 32 + col + e] = cs[e];
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (t < 32) {
+      float tot = 0.f;
+      for (int k = 0; k < 32; ++k) tot += scr[k * 32 + t];
+      q.bpart[(int64_t)blockIdx.x * 32 + t] = tot;
+    }
+    if (warp < 4) {
+      // TMEM lane m = 32 * (tap-block within the group) + ci; columns = co (hi.hi+lo.hi | hi.lo)
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        const int tb = g * 4 + warp;
+        float4 o[8];
+        if (nst > 0) {
+          uint32_t r0[32], r1[32];
+          const uint32_t ta = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g * 64);
+          tmem_ld32_issue(ta, r0);
+          tmem_ld32_issue(ta + 32u, r1);
+          tmem_wait_ld();
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            o[c].x = __uint_as_float(r0[4 * c + 0]) + __uint_as_float(r1[4 * c + 0]);
+            o[c].y = __uint_as_float(r0[4 * c + 1]) + __uint_as_float(r1[4 * c + 1]);
+            o[c].z = __uint_as_float(r0[4 * c + 2]) + __uint_as_float(r1[4 * c + 2]);
+            o[c].w = __uint_as_float(r0[4 * c + 3]) + __uint_as_float(r1[4 * c + 3]);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) o[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (tb < q.ntb) {
+          float4* dst = reinterpret_cast<float4*>(q.part + (((int64_t)blockIdx.x * kMaxTB + tb) * 32 + lane) * 32);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) dst[c] = o[c];
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_d, 256);
+}
+
+// ---- small kernels -----------------------------------------------------------------------------------------------
+// Shared-memory images of the per-tap weight matrices: rows n = 0..31 hold B[n][k] as the tensor core sees it, rows
+// 32..63 the lo parts; K-major SWIZZLE_128B.
+//   mode 0 (forward 3x3, 32 in):  tb = kh*3+kw,           B[n=co][k=ci] = W[co][ci][kh][kw]
+//   mode 1 (data gradient):       tb = kh*3+kw,           B[n=ci][k=co] = W[co][ci][kh][kw]
+//   mode 2 (first layer, s2d):    tb = (dh*2+dw)*2 + cb,  B[n=co][k] = W[co][c][2dh+ph][2dw+pw], s2d channel cb*32+k = (ph*2+pw)*C + c
+__global__ void conv_pack_kernel(const float* __restrict__ W, float* __restrict__ pack, int mode, int C, int ntb) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= ntb * 2048) return;
+  const int k = idx & 31, n = (idx >> 5) & 63, tb = idx >> 11, nn = n & 31;
+  float w = 0.f;
+  if (mode == 0) {
+    w = W[(nn * 32 + k) * 9 + tb];
+  } else if (mode == 1) {
+    w = W[(k * 32 + nn) * 9 + tb];
+  } else {
+    const int cb = tb & 1, tap = tb >> 1, dh = tap >> 1, dw = tap & 1, sc = cb * 32 + k;
+    if (sc < 4 * C) {
+      const int ph = sc / (2 * C), pw = (sc / C) & 1, c = sc % C, kh = 2 * dh + ph, kw = 2 * dw + pw;
+      if (kh < 3 && kw < 3) w = W[((nn * C + c) * 3 + kh) * 3 + kw];
+    }
+  }
+  const float val = n < 32 ? w : tf32_lo(w);
+  const uint32_t off = (uint32_t)tb * 8192u + (uint32_t)(n >> 3) * 1024u + (uint32_t)(n & 7) * 128u +
+                       ((((uint32_t)k >> 2) ^ (uint32_t)(n & 7)) << 4) + (uint32_t)(k & 3) * 4u;
+  pack[off >> 2] = val;
+}
+
+// obs [B,C,H,W] fp32 (0..255) -> X0[(b*pp + gy*gw + gx)*64 + (ph*2+pw)*C + c] = obs[b][c][2gy+ph][2gx+pw] / 255 - 0.5
+// (nets/cnns.py:58: two separately rounded fp32 operations).  One block per (image, row pair).
+__global__ void s2d_norm_kernel(const float* __restrict__ obs, float* __restrict__ x0, int C, int H, int W) {
+  extern __shared__ float sh[];
+  const int gw = W / 2, gh = H / 2;
+  const int b = blockIdx.x / gh, gy = blockIdx.x % gh;
+  const int c4 = 4 * C;
+  for (int idx = threadIdx.x; idx < C * 2 * W; idx += blockDim.x) {
+    const int c = idx / (2 * W), rem = idx % (2 * W), ph = rem / W, x = rem % W;
+    const float v = __ldg(obs + (((int64_t)b * C + c) * H + 2 * gy + ph) * W + x);
+    sh[(x >> 1) * c4 + (ph * 2 + (x & 1)) * C + c] = __fsub_rn(__fdiv_rn(v, 255.0f), 0.5f);
+  }
+  __syncthreads();
+  float* dst = x0 + ((int64_t)b * gh * gw + (int64_t)gy * gw) * 64;
+  for (int idx = threadIdx.x; idx < gw * c4; idx += blockDim.x) dst[(idx / c4) * 64 + idx % c4] = sh[idx];
+}
+
+// gW[co][ci][kh][kw] (mode 0) or the first layer's gW[co][c][kh][kw] (mode 2) = sum over CTAs of the partial tap-block
+// products, in a fixed order; bias gradient likewise.  `accumulate` adds to what is there (autograd hands out fresh tensors).
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, const float* __restrict__ bpart, int nparts, int mode,
+                                    int C, float* __restrict__ gW, float* __restrict__ gb) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nW = mode == 0 ? 9 * 1024 : 9 * 32 * C;
+  if (idx < nW) {
+    int co, tb, k, out;
+    if (mode == 0) {
+      co = idx & 31; k = (idx >> 5) & 31; tb = idx >> 10;   // k = ci
+      out = (co * 32 + k) * 9 + tb;
+    } else {
+      co = idx & 31;
+      const int r = idx >> 5;              // (c, kh, kw)
+      const int kw = r % 3, kh = (r / 3) % 3, c = r / 9;
+      const int dh = kh >> 1, ph = kh & 1, dw = kw >> 1, pw = kw & 1;
+      const int sc = (ph * 2 + pw) * C + c;
+      tb = (dh * 2 + dw) * 2 + (sc >> 5);
+      k = sc & 31;
+      out = ((co * C + c) * 3 + kh) * 3 + kw;
+    }
+    float tot = 0.f;
+    for (int p = 0; p < nparts; ++p) tot += part[(((int64_t)p * kMaxTB + tb) * 32 + k) * 32 + co];
+    gW[out] = tot;
+  } else if (idx < nW + 32) {
+    const int co = idx - nW;
+    float tot = 0.f;
+    for (int p = 0; p < nparts; ++p) tot += bpart[p * 32 + co];
+    gb[co] = tot;
+  }
+}
+
+// FC weight [O][32*vh*vw] (NCHW flatten, nets/cnns.py:63) <-> zero-padded pitch layout Wp[64][kfp], column (h*gw+w)*32 + c
+__global__ void fc_pack_kernel(const float* __restrict__ fcw, float* __restrict__ wp, int O, int vh, int vw, int gw, int64_t kfp,
+                               int unpack) {
+  const int64_t n = (int64_t)O * 32 * vh * vw;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  // thread order (o, h, w, c): the pitch-layout side is contiguous
+  const int c = (int)(idx & 31);
+  const int64_t r = idx >> 5;
+  const int w = (int)(r % vw), h = (int)((r / vw) % vh), o = (int)(r / ((int64_t)vw * vh));
+  const int64_t a = (int64_t)o * 32 * vh * vw + (int64_t)c * vh * vw + h * vw + w;
+  const int64_t b = (int64_t)o * kfp + ((int64_t)h * gw + w) * 32 + c;
+  if (unpack) const_cast<float*>(fcw)[a] = wp[b];
+  else wp[b] = __ldg(fcw + a);
+}
+
+// z = fc bias + split-K partials (fixed order) -> LayerNorm (biased variance, eps 1e-5) -> tanh.  One block of 64 threads per row.
+__global__ void fc_ln_tanh_kernel(const float* __restrict__ part, int nsplit, int B, int O, const float* __restrict__ fcb,
+                                  const float* __restrict__ gam, const float* __restrict__ bet, float* __restrict__ xhat,
+                                  float* __restrict__ rstd, float* __restrict__ out) {
+  __shared__ float sh[64];
+  const int b = blockIdx.x, o = threadIdx.x;
+  float z = 0.f;
+  if (o < O) {
+    z = __ldg(fcb + o);
+    for (int s = 0; s < nsplit; ++s) z += part[((int64_t)s * B + b) * 64 + o];
+  }
+  sh[o] = z;
+  __syncthreads();
+  float mean = 0.f;
+  for (int j = 0; j < O; ++j) mean += sh[j];
+  mean /= (float)O;
+  const float dz = o < O ? z - mean : 0.f;
+  __syncthreads();
+  sh[o] = dz * dz;
+  __syncthreads();
+  float var = 0.f;
+  for (int j = 0; j < O; ++j) var += sh[j];
+  var /= (float)O;
+  const float rs = rsqrtf(var + 1e-5f);
+  if (o < O) {
+    const float xh = dz * rs;
+    if (xhat) xhat[(int64_t)b * 64 + o] = xh;
+    out[(int64_t)b * O + o] = tanhf(xh * __ldg(gam + o) + __ldg(bet + o));
+  }
+  if (o == 0 && rstd) rstd[b] = rs;
+}
+
+// tanh / LayerNorm backward per row: dl = dout (1 - out^2); dz = rstd (dl g - mean(dl g) - xhat mean(dl g xhat))
+__global__ void fc_ln_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out, const float* __restrict__ xhat,
+                                 const float* __restrict__ rstd, const float* __restrict__ gam, int O, float* __restrict__ dl,
+                                 float* __restrict__ dfc) {
+  __shared__ float s1[64], s2[64];
+  const int b = blockIdx.x, o = threadIdx.x;
+  float d = 0.f, xh = 0.f, dxh = 0.f;
+  if (o < O) {
+    const float y = out[(int64_t)b * O + o];
+    d = dout[(int64_t)b * O + o] * (1.f - y * y);
+    xh = xhat[(int64_t)b * 64 + o];
+    dxh = d * __ldg(gam + o);
+  }
+  s1[o] = dxh;
+  s2[o] = dxh * xh;
+  __syncthreads();
+  float m1 = 0.f, m2 = 0.f;
+  for (int j = 0; j < O; ++j) { m1 += s1[j]; m2 += s2[j]; }
+  m1 /= (float)O;
+  m2 /= (float)O;
+  dl[(int64_t)b * 64 + o] = d;
+  dfc[(int64_t)b * 64 + o] = o < O ? rstd[b] * (dxh - m1 - xh * m2) : 0.f;
+}
+
+// column reductions over the batch: LayerNorm weight / bias gradients and the FC bias gradient (one block, 4 x 64 threads)
+__global__ void fc_colred_kernel(const float* __restrict__ dl, const float* __restrict__ xhat, const float* __restrict__ dfc,
+                                 int B, int O, float* __restrict__ g_gam, float* __restrict__ g_bet, float* __restrict__ g_fcb) {
+  __shared__ float sh[3][4][64];
+  const int o = threadIdx.x & 63, part = threadIdx.x >> 6;
+  float a = 0.f, c = 0.f, e = 0.f;
+  for (int b = part; b < B; b += 4) {
+    const float d = dl[(int64_t)b * 64 + o];
+    a += d * xhat[(int64_t)b * 64 + o];
+    c += d;
+    e += dfc[(int64_t)b * 64 + o];
+  }
+  sh[0][part][o] = a; sh[1][part][o] = c; sh[2][part][o] = e;
+  __syncthreads();
+  if (part == 0 && o < O) {
+    g_gam[o] = (sh[0][0][o] + sh[0][1][o]) + (sh[0][2][o] + sh[0][3][o]);
+    g_bet[o] = (sh[1][0][o] + sh[1][1][o]) + (sh[1][2][o] + sh[1][3][o]);
+    g_fcb[o] = (sh[2][0][o] + sh[2][1][o]) + (sh[2][2][o] + sh[2][3][o]);
+  }
+}
+
+}  // namespace cv
+
+// ---- host ----------------------------------------------------------------------------------------------------------
+namespace {
+
+struct EncPlan {
+  int B, C, H, W, O, save;
+  int gh, gw, pp;
+  int64_t np;
+  int vh[5], vw[5];
+  int64_t kf, kfp;
+  int ks, nsplit;
+  int64_t x0, y[5], d[2], wfc, gwfc, part_fc, xhat, rstd, dfc, dl, pack_f[5], pack_d[5], wpart, bpart, total;
+};
+
+inline int64_t up256(int64_t v) { return (v + 255) & ~(int64_t)255; }
+
+int make_plan(int B, int C, int H, int W, int O, int save, EncPlan* p) {
+  SSAC_REQUIRE(B > 0 && C > 0 && 4 * C <= 64, "conv encoder: 1 <= channels <= 16");
+  SSAC_REQUIRE(H >= 16 && W >= 16 && (H % 2) == 0 && (W % 2) == 0, "conv encoder: even image sides >= 16");
+  SSAC_REQUIRE(O > 0 && O <= 64, "conv encoder: 1 <= out_dim <= 64");
+  p->B = B; p->C = C; p->H = H; p->W = W; p->O = O; p->save = save;
+  p->gh = H / 2; p->gw = W / 2; p->pp = p->gh * p->gw;
+  p->np = (int64_t)B * p->pp;
+  SSAC_REQUIRE(p->np + 4 * p->gw < (int64_t)1 << 30, "conv encoder: too many pixels for 32-bit TMA coordinates");
+  for (int l = 1; l <= 4; ++l) { p->vh[l] = p->gh - 1 - 2 * (l - 1); p->vw[l] = p->gw - 1 - 2 * (l - 1); }
+  SSAC_REQUIRE(p->vh[4] > 0 && p->vw[4] > 0, "conv encoder: image too small");
+  p->kf = (int64_t)p->pp * 32;
+  const int64_t k32 = p->kf / 32;
+  p->ks = (int)(32 * ((k32 + 63) / 64));
+  p->nsplit = (int)((p->kf + p->ks - 1) / p->ks);
+  p->kfp = (int64_t)p->nsplit * p->ks;
+  const int64_t pad = p->ks + 256;     // zero tail behind every activation buffer (the last split-K group reads past kf)
+  int64_t o = 0;
+  auto take = [&](int64_t n) { const int64_t at = o; o += up256(n); return at; };
+  p->x0 = take(p->np * 64 + pad);
+  const int64_t ybytes = p->np * 32 + pad;
+  if (save) {
+    for (int l = 1; l <= 4; ++l) p->y[l] = take(ybytes);
+    p->d[0] = take(ybytes); p->d[1] = take(ybytes);
+  } else {
+    p->y[1] = p->y[3] = take(ybytes);
+    p->y[2] = p->y[4] = take(ybytes);
+    p->d[0] = p->d[1] = -1;
+  }
+  p->wfc = take(64 * p->kfp);
+  p->gwfc = save ? take(64 * p->kfp) : -1;
+  p->part_fc = take((int64_t)p->nsplit * B * 64);
+  p->xhat = take((int64_t)B * 64);
+  p->rstd = take(B);
+  p->dfc = take((int64_t)B * 64);
+  p->dl = take((int64_t)B * 64);
+  for (int l = 1; l <= 4; ++l) { p->pack_f[l] = take(cv::kMaxTB * 2048); p->pack_d[l] = take(cv::kMaxTB * 2048); }
+  p->wpart = save ? take((int64_t)kNumSMs * cv::kMaxTB * 1024) : -1;
+  p->bpart = save ? take((int64_t)kNumSMs * 32) : -1;
+  p->total = o;
+  return 0;
+}
+
+int g_conv_halo = 1;
+bool g_conv_attr = false;
+int conv_attrs() {
+  if (g_conv_attr) return 0;
+  cudaError_t e = cudaFuncSetAttribute(cv::conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cv::kConvSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(cv::conv_wgrad_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (6 * 16384 + 8192) + 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(cv::conv_wgrad_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (4 * 16384 + 8192) + 1024);
+  if (e != cudaSuccess) {
+    set_error(std::string("conv encoder (smem attribute): ") + cudaGetErrorString(e));
+    return (int)e;
+  }
+  g_conv_attr = true;
+  return 0;
+}
+
+// layer 1: 2x2 taps over the 64-channel space-to-depth image; layers 2-4: 3x3 taps over 32 channels
+void taps_of(int layer, int gw, bool dgrad, int* ntb, int* shift, int* cb) {
+  int n = 0;
+  if (layer == 1) {
+    for (int dh = 0; dh < 2; ++dh)
+      for (int dw = 0; dw < 2; ++dw)
+        for (int b = 0; b < 2; ++b) { shift[n] = dh * gw + dw; cb[n] = b; ++n; }
+  } else {
+    for (int kh = 0; kh < 3; ++kh)
+      for (int kw = 0; kw < 3; ++kw) { shift[n] = (dgrad ? -1 : 1) * (kh * gw + kw); cb[n] = 0; ++n; }
+  }
+  *ntb = n;
+}
+
+int launch_conv(const EncPlan& pl, int layer, bool dgrad, const float* in, int in_ch, float* out, const float* wpack,
+                const float* bias, const float* yprev, int vh, int vw, cudaStream_t s) {
+  cv::ConvP q;
+  memset(&q, 0, sizeof(q));
+  if (!tc::make_map2d(in, in_ch, in_ch, pl.np, 128, false, &q.tmIn) || !tc::make_map2d(out, 32, 32, pl.np, 128, false, &q.tmOut))
+    return fail(SSAC_E_UNSUPPORTED, "conv encoder: tensor map");
+  q.wpack = wpack; q.bias = bias; q.yprev = yprev;
+  taps_of(layer, pl.gw, dgrad, &q.ntb, q.shift, q.cb);
+  const int reach = 2 * pl.gw + 2;                       // largest tap shift
+  const int hr = (128 + reach + 7) & ~7;
+  if (g_conv_halo && in_ch == 32 && hr <= 256) {
+    q.halo = g_conv_halo; q.hr = hr;
+    q.halo_base = dgrad ? -reach : 0;
+    for (int t = 0; t < q.ntb; ++t) q.toff[t] = dgrad ? reach + q.shift[t] : q.shift[t];   // dgrad shifts are negative
+    if (!tc::make_map2d(in, 32, 32, pl.np, hr, false, &q.tmIn)) return fail(SSAC_E_UNSUPPORTED, "conv encoder: tensor map");
+  }
+  q.ntiles = (int)((pl.np + 127) / 128);
+  q.mode = dgrad ? 1 : 0;
+  q.np = pl.np; q.pp = pl.pp; q.pw = pl.gw; q.vh = vh; q.vw = vw;
+  const int grid = std::min(q.ntiles, kNumSMs);
+  cv::conv_tc_kernel<<<grid, cv::kConvThreads, cv::kConvSmem, s>>>(q);
+  SSAC_CHECK_LAUNCH("conv_tc_kernel");
+  return 0;
+}
+
+int launch_wgrad(const EncPlan& pl, int layer, const float* x, int x_ch, const float* dz, float* ws, float* gW, float* gb,
+                 cudaStream_t s) {
+  cv::WgradP q;
+  memset(&q, 0, sizeof(q));
+  if (!tc::make_map2d(x, x_ch, x_ch, pl.np, 32, true, &q.tmX) || !tc::make_map2d(dz, 32, 32, pl.np, 32, true, &q.tmD))
+    return fail(SSAC_E_UNSUPPORTED, "conv encoder: tensor map");
+  taps_of(layer, pl.gw, false, &q.ntb, q.shift, q.cb);
+  q.ng = (q.ntb + 3) / 4;
+  q.part = ws + pl.wpart; q.bpart = ws + pl.bpart;
+  q.nstages = (int)((pl.np + 31) / 32);
+  const int grid = std::min(q.nstages, kNumSMs);
+  q.spc = (q.nstages + grid - 1) / grid;
+  if (q.ng == 3) cv::conv_wgrad_tc_kernel<3><<<grid, cv::kWgThreads, 2 * (6 * 16384 + 8192) + 1024, s>>>(q);
+  else cv::conv_wgrad_tc_kernel<2><<<grid, cv::kWgThreads, 3 * (4 * 16384 + 8192) + 1024, s>>>(q);
+  SSAC_CHECK_LAUNCH("conv_wgrad_tc_kernel");
+  const int mode = layer == 1 ? 2 : 0;
+  const int nW = mode == 0 ? 9 * 1024 : 9 * 32 * pl.C;
+  cv::wgrad_reduce_kernel<<<(nW + 32 + 255) / 256, 256, 0, s>>>(q.part, q.bpart, grid, mode, pl.C, gW, gb);
+  SSAC_CHECK_LAUNCH("wgrad_reduce_kernel");
+  return 0;
+}
+
+GemmP zero_gemm() {
+  GemmP g;
+  memset(&g, 0, sizeof(g));
+  return g;
+}
+
+}  // namespace
+}  // namespace ssac
+
+using namespace ssac;
+
+extern "C" int ssac_set_conv_halo(int mode) {
+  g_conv_halo = mode;
+  return 0;
+}
+
+// params / grads: host arrays of 12 device pointers in the order conv1.weight, conv1.bias, ..., conv4.bias, fc.weight,
+// fc.bias, ln.weight, ln.bias (the module's parameter order, nets/cnns.py:40-54).
+extern "C" int ssac_conv_encoder_ws_floats(int B, int C, int H, int W, int out_dim, int save, int64_t* n_floats_out) {
+  EncPlan pl;
+  if (int rc = make_plan(B, C, H, W, out_dim, save, &pl)) return rc;
+  *n_floats_out = pl.total;
+  return 0;
+}
+
+extern "C" int ssac_conv_encoder_ws_offsets(int B, int C, int H, int W, int out_dim, int save, int64_t* offsets_out) {
+  EncPlan pl;
+  if (int rc = make_plan(B, C, H, W, out_dim, save, &pl)) return rc;
+  const int64_t v[24] = {pl.x0, pl.y[1], pl.y[2], pl.y[3], pl.y[4], pl.d[0], pl.d[1], pl.wfc, pl.gwfc, pl.part_fc, pl.xhat,
+                         pl.rstd, pl.dfc, pl.dl, pl.pp, pl.gw, pl.np, pl.kf, pl.kfp, pl.ks, pl.nsplit, pl.total, 0, 0};
+  for (int i = 0; i < 24; ++i) offsets_out[i] = v[i];
+  return 0;
+}
+
+extern "C" int ssac_conv_encoder_forward(const float* obs_dev, int B, int C, int H, int W, int out_dim,
+                                         const float* const* params, float* ws_dev, int save, float* out_dev, void* stream) {
+  EncPlan pl;
+  if (int rc = make_plan(B, C, H, W, out_dim, save, &pl)) return rc;
+  if (int rc = conv_attrs()) return rc;
+  SSAC_REQUIRE(obs_dev && params && ws_dev && out_dev, "conv encoder: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  float* ws = ws_dev;
+  cv::s2d_norm_kernel<<<B * pl.gh, 256, (size_t)pl.gw * 4 * C * sizeof(float), s>>>(obs_dev, ws + pl.x0, C, H, W);
+  SSAC_CHECK_LAUNCH("s2d_norm_kernel");
+  cv::conv_pack_kernel<<<(8 * 2048 + 255) / 256, 256, 0, s>>>(params[0], ws + pl.pack_f[1], 2, C, 8);
+  SSAC_CHECK_LAUNCH("conv_pack_kernel");
+  for (int l = 2; l <= 4; ++l) {
+    cv::conv_pack_kernel<<<(9 * 2048 + 255) / 256, 256, 0, s>>>(params[2 * (l - 1)], ws + pl.pack_f[l], 0, C, 9);
+    SSAC_CHECK_LAUNCH("conv_pack_kernel");
+  }
+  {
+    const int64_t n = (int64_t)out_dim * 32 * pl.vh[4] * pl.vw[4];
+    cv::fc_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(params[8], ws + pl.wfc, out_dim, pl.vh[4], pl.vw[4], pl.gw, pl.kfp, 0);
+    SSAC_CHECK_LAUNCH("fc_pack_kernel");
+  }
+  if (int rc = launch_conv(pl, 1, false, ws + pl.x0, 64, ws + pl.y[1], ws + pl.pack_f[1], params[1], nullptr, 0, 0, s)) return rc;
+  for (int l = 2; l <= 4; ++l)
+    if (int rc = launch_conv(pl, l, false, ws + pl.y[l - 1], 32, ws + pl.y[l], ws + pl.pack_f[l], params[2 * (l - 1) + 1], nullptr, 0, 0, s)) return rc;
+  // FC: split-K as groups of the grouped GEMM
+  GemmP g = zero_gemm();
+  g.A = ws + pl.y[4]; g.lda = pl.kf; g.a_gs = pl.ks;
+  g.Bm = ws + pl.wfc; g.ldb = pl.kfp; g.b_gs = pl.ks;
+  g.C = ws + pl.part_fc; g.ldc = 64; g.c_gs = (int64_t)B * 64;
+  g.M = B; g.N = 64; g.K = pl.ks;
+  if (int rc = launch_gemm_tc(L_NT, g, pl.nsplit, s, "conv encoder fc forward")) return rc;
+  cv::fc_ln_tanh_kernel<<<B, 64, 0, s>>>(ws + pl.part_fc, pl.nsplit, B, out_dim, params[9], params[10], params[11],
+                                         ws + pl.xhat, ws + pl.rstd, out_dev);
+  SSAC_CHECK_LAUNCH("fc_ln_tanh_kernel");
+  return 0;
+}
+
+extern "C" int ssac_conv_encoder_backward(const float* dout_dev, const float* out_dev, int B, int C, int H, int W, int out_dim,
+                                          const float* const* params, float* ws_dev, float* const* grads, void* stream) {
+  EncPlan pl;
+  if (int rc = make_plan(B, C, H, W, out_dim, 1, &pl)) return rc;
+  if (int rc = conv_attrs()) return rc;
+  SSAC_REQUIRE(dout_dev && out_dev && params && ws_dev && grads, "conv encoder: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  float* ws = ws_dev;
+  cv::fc_ln_bwd_kernel<<<B, 64, 0, s>>>(dout_dev, out_dev, ws + pl.xhat, ws + pl.rstd, params[10], out_dim, ws + pl.dl, ws + pl.dfc);
+  SSAC_CHECK_LAUNCH("fc_ln_bwd_kernel");
+  cv::fc_colred_kernel<<<1, 256, 0, s>>>(ws + pl.dl, ws + pl.xhat, ws + pl.dfc, B, out_dim, grads[10], grads[11], grads[9]);
+  SSAC_CHECK_LAUNCH("fc_colred_kernel");
+  {  // gW' = dfc^T . Y4
+    GemmP g = zero_gemm();
+    g.A = ws + pl.dfc; g.lda = 64;
+    g.Bm = ws + pl.y[4]; g.ldb = pl.kf;
+    g.C = ws + pl.gwfc; g.ldc = pl.kfp;
+    g.M = 64; g.N = (int)pl.kf; g.K = B;
+    if (int rc = launch_gemm_tc(L_TN, g, 1, s, "conv encoder fc wgrad")) return rc;
+    const int64_t n = (int64_t)out_dim * 32 * pl.vh[4] * pl.vw[4];
+    cv::fc_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(grads[8], ws + pl.gwfc, out_dim, pl.vh[4], pl.vw[4], pl.gw, pl.kfp, 1);
+    SSAC_CHECK_LAUNCH("fc_pack_kernel (unpack)");
+  }
+  {  // dZ4 = (dfc . W') .* (Y4 > 0)   (W' is zero outside the valid region)
+    GemmP g = zero_gemm();
+    g.A = ws + pl.dfc; g.lda = 64;
+    g.Bm = ws + pl.wfc; g.ldb = pl.kfp;
+    g.C = ws + pl.d[0]; g.ldc = pl.kf;
+    g.mask = ws + pl.y[4]; g.ldmask = pl.kf;
+    g.M = B; g.N = (int)pl.kf; g.K = 64;
+    if (int rc = launch_gemm_tc(L_NN, g, 1, s, "conv encoder fc dgrad")) return rc;
+  }
+  int cur = 0;
+  for (int l = 4; l >= 2; --l) {
+    if (int rc = launch_wgrad(pl, l, ws + pl.y[l - 1], 32, ws + pl.d[cur], ws, grads[2 * (l - 1)], grads[2 * (l - 1) + 1], s)) return rc;
+    cv::conv_pack_kernel<<<(9 * 2048 + 255) / 256, 256, 0, s>>>(params[2 * (l - 1)], ws + pl.pack_d[l], 1, C, 9);
+    SSAC_CHECK_LAUNCH("conv_pack_kernel");
+    if (int rc = launch_conv(pl, l, true, ws + pl.d[cur], 32, ws + pl.d[cur ^ 1], ws + pl.pack_d[l], nullptr, ws + pl.y[l - 1],
+                             pl.vh[l - 1], pl.vw[l - 1], s)) return rc;
+    cur ^= 1;
+  }
+  return launch_wgrad(pl, 1, ws + pl.x0, 64, ws + pl.d[cur], ws, grads[0], grads[1], s);
+}

@@ -554,6 +554,19 @@ bool make_map(const float* base, int64_t ld, int64_t gs, int inner, int outer, b
   cache.push_back(MapEntry{key, *out});
   return true;
 }
+bool make_map2d(const float* base, int64_t ld, int inner, int64_t rows, int box_rows, bool mn, CUtensorMap* out) {
+  if (!encode_fn()) return false;
+  if ((((uintptr_t)base) & 15) != 0 || (ld & 3) != 0 || ld < inner || inner <= 0 || rows <= 0 || box_rows <= 0 || box_rows > 256) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode_fn()(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           mn ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
 }  // namespace tc
 using tc::make_map;
 

@@ -65,6 +65,21 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t sr
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+// 2-D variants (conv encoder: (channels, pixels) views of NHWC activations)
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src_smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src_smem), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_commit_and_wait_read() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -242,6 +257,10 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 // host side (ssac_mlp_tc.cu): cached 3-D tensor maps (inner, outer, group) over row-major fp32 matrix stacks
 bool make_map(const float* base, int64_t ld, int64_t gs, int inner, int outer, bool mn, CUtensorMap* out, int groups = 1);
 bool tma_enabled();
+// 2-D map (inner, rows) over a dense row-major fp32 matrix whose rows are `ld` floats apart; box = 32 x box_rows;
+// mn = false: SWIZZLE_128B (K-major operand / plain tile), true: SWIZZLE_128B_ATOM_32B (MN-major operand).  The declared
+// extent is exactly inner x rows (boxes hanging over it are zero-filled / clipped; see make_map for why it must not be more).
+bool make_map2d(const float* base, int64_t ld, int inner, int64_t rows, int box_rows, bool mn, CUtensorMap* out);
 
 }  // namespace tc
 }  // namespace ssac

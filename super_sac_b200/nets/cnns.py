@@ -1,5 +1,15 @@
-"""Pixel encoders (reference nets/cnns.py:37-103).  User-pluggable ``nn.Module``s: they stay PyTorch / cuDNN
-and feed ``s_rep`` to the CUDA update path (a native conv encoder is SURVEY 8f row N3)."""
+"""Pixel encoders (reference nets/cnns.py:37-103).
+
+``BigPixelEncoder`` -- the DrQ / DrQv2 encoder of the pixel configs -- keeps the reference's ``nn.Module`` shell
+(parameter names and shapes, so ``state_dict`` / optimisers / ``deepcopy`` / Polyak keep working) but on a CUDA tensor its
+forward and backward are the library's tcgen05 implicit-GEMM kernels (``ssac_conv_encoder_forward / _backward``,
+csrc/ssac_conv.cu), handed to autograd as one ``torch.autograd.Function``.  There is no cuDNN or ATen
+fallback on the GPU: a missing library raises.  On CPU tensors the module is the plain PyTorch definition (state-dict
+round trips and host-side tests).
+"""
+import ctypes
+import os
+
 import torch
 import torch.nn.functional as F
 from torch import nn
@@ -11,8 +21,65 @@ def _conv_out(size, kernel, stride):
     return (size - (kernel - 1) - 1) // stride + 1
 
 
+class _Workspace:
+    """Zero-initialised device workspaces of the native encoder, one per (batch, save) and recycled once the backward
+    that needs the saved activations has run."""
+
+    def __init__(self):
+        self.free = {}
+
+    def take(self, key, n_floats, device):
+        pool = self.free.setdefault(key, [])
+        if pool:
+            return pool.pop()
+        return torch.zeros(n_floats, dtype=torch.float32, device=device)
+
+    def give(self, key, ws):
+        self.free.setdefault(key, []).append(ws)
+
+
+class _EncoderFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module, obs, *params):
+        from .. import _lib
+
+        lib = _lib.lib()
+        B, C, H, W = obs.shape
+        O = module.embedding_dim
+        save = 1 if any(ctx.needs_input_grad[2:]) else 0
+        key = (B, save, obs.device)
+        n = ctypes.c_int64()
+        lib.conv_encoder_ws_floats(B, C, H, W, O, save, ctypes.byref(n))
+        ws = module._ws.take(key, n.value, obs.device)
+        out = torch.empty(B, O, dtype=torch.float32, device=obs.device)
+        pp = _lib.host_array(ctypes.c_void_p, [p.data_ptr() for p in params])
+        lib.conv_encoder_forward(obs.data_ptr(), B, C, H, W, O, pp, ws.data_ptr(), save, out.data_ptr(), _lib.stream_ptr())
+        if save:
+            ctx.module, ctx.key, ctx.ws, ctx.dims = module, key, ws, (B, C, H, W, O)
+            ctx.save_for_backward(out, *params)
+        else:
+            module._ws.give(key, ws)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        from .. import _lib
+
+        lib = _lib.lib()
+        out, *params = ctx.saved_tensors
+        B, C, H, W, O = ctx.dims
+        dout = dout.contiguous()
+        grads = [torch.empty_like(p) for p in params]
+        pp = _lib.host_array(ctypes.c_void_p, [p.data_ptr() for p in params])
+        gp = _lib.host_array(ctypes.c_void_p, [g.data_ptr() for g in grads])
+        lib.conv_encoder_backward(dout.data_ptr(), out.data_ptr(), B, C, H, W, O, pp, ctx.ws.data_ptr(), gp, _lib.stream_ptr())
+        ctx.module._ws.give(ctx.key, ctx.ws)
+        ctx.ws = None
+        return (None, None, *grads)
+
+
 class BigPixelEncoder(nn.Module):
-    """DrQ encoder: conv3x3(32) s2,1,1,1 -> FC -> LayerNorm -> tanh on obs/255 - 0.5."""
+    """DrQ encoder: conv3x3(32) s2,1,1,1 -> FC -> LayerNorm -> tanh on obs/255 - 0.5 (nets/cnns.py:37-69)."""
 
     def __init__(self, obs_shape, out_dim=50):
         super().__init__()
@@ -28,8 +95,36 @@ class BigPixelEncoder(nn.Module):
         self.ln = nn.LayerNorm(out_dim)
         self.apply(weight_init)
         self.embedding_dim = out_dim
+        self._ws = _Workspace()
+
+    def __deepcopy__(self, memo):
+        # target_agent = deepcopy(agent) (main.py:321): parameters are copied, workspaces are not shared
+        import copy
+
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = _Workspace() if k == "_ws" else copy.deepcopy(v, memo)
+        return new
+
+    def _native_params(self):
+        return (self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias, self.conv3.weight, self.conv3.bias,
+                self.conv4.weight, self.conv4.bias, self.fc.weight, self.fc.bias, self.ln.weight, self.ln.bias)
+
+    def native_supported(self, obs):
+        return (obs.dim() == 4 and obs.shape[1] <= 16 and obs.shape[2] % 2 == 0 and obs.shape[3] % 2 == 0
+                and min(obs.shape[2], obs.shape[3]) >= 16 and self.embedding_dim <= 64)
 
     def forward(self, obs):
+        if obs.is_cuda and os.environ.get("SSAC_ENCODER_IMPL", "native") != "torch":
+            if not self.native_supported(obs):
+                raise NotImplementedError("BigPixelEncoder on CUDA: <= 16 channels, even sides >= 16, out_dim <= 64")
+            x = obs if obs.dtype == torch.float32 else obs.float()
+            params = self._native_params()
+            if not torch.is_grad_enabled():
+                params = tuple(p.detach() for p in params)
+            return _EncoderFn.apply(self, x.contiguous(), *params)
         x = (obs / 255.0) - 0.5
         x = F.relu(self.conv1(x))
         x = F.relu(self.conv2(x))

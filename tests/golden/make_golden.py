@@ -471,11 +471,36 @@ def run_afbc_case():
     print(f"wrote {path}  ({os.path.getsize(path)/1024:.1f} KiB)")
 
 
+def run_encoder_case():
+    """BigPixelEncoder (nets/cnns.py:37-69): forward output and autograd gradients of every parameter, from the
+    unmodified reference module, on two small image geometries (one odd valid size, one with 9 channels)."""
+    out = {}
+    for tag, (B, C, HW, O, seed) in {"rgb20": (5, 3, 20, 10, 41), "stack24": (3, 9, 24, 50, 42)}.items():
+        rng = np.random.default_rng(seed)
+        torch.manual_seed(seed)
+        enc = rnets.cnns.BigPixelEncoder((C, HW, HW), out_dim=O)
+        with torch.no_grad():   # the delta-orthogonal init leaves 8 of 9 taps and every bias at zero: fill them
+            for p_ in enc.parameters():
+                p_.add_(0.05 * torch.randn_like(p_))
+        obs = rng.integers(0, 256, (B, C, HW, HW)).astype(np.float32)
+        dout = rng.standard_normal((B, O)).astype(np.float32)
+        y = enc(torch.as_tensor(obs))
+        params = dict(enc.named_parameters())
+        grads = torch.autograd.grad(y, list(params.values()), grad_outputs=torch.as_tensor(dout))
+        put(out, tag, dict(obs=obs.astype(np.uint8), dout=dout, out=y.detach().numpy()))
+        put(out, f"{tag}/params", {k: v.detach().numpy() for k, v in params.items()})
+        put(out, f"{tag}/grads", {k: g.numpy() for k, g in zip(params.keys(), grads)})
+    path = os.path.join(HERE, "encoder.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}  ({os.path.getsize(path)/1024:.1f} KiB)")
+
+
 if __name__ == "__main__":
     only = set(sys.argv[1:])   # e.g. ``python make_golden.py rad`` regenerates one fixture
     for name, cfg in UPDATE_CASES.items():
         if not only or name in only:
             run_update_case(name, cfg)
-    for name, fn in (("replay", run_replay_case), ("aug", run_aug_case), ("rad", run_rad_case), ("afbc", run_afbc_case)):
+    for name, fn in (("replay", run_replay_case), ("aug", run_aug_case), ("rad", run_rad_case), ("afbc", run_afbc_case),
+                     ("encoder", run_encoder_case)):
         if not only or name in only:
             fn()

@@ -1,0 +1,219 @@
+"""N3: the native DrQ pixel encoder (csrc/ssac_conv.cu behind nets.cnns.BigPixelEncoder) against
+
+* the golden vectors of the unmodified reference module (tests/golden/encoder.npz), through the C ABI, layer by layer
+  (every activation and every per-layer gradient is compared with oracle/encoder_oracle.py, which test_oracle_golden.py
+  pins against the same fixture), and through the drop-in module + autograd;
+* the oracle at the BASELINE geometry (9 x 84 x 84, out_dim 50).
+
+Tolerance: north_star's rtol 1e-4 (+ atol 1e-4 of the tensor's largest magnitude: sums of thousands of 3xTF32 products of
+either sign).  CPU part: the library exports the entry points and plans its workspace.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import golden_util as gu
+from oracle import encoder_oracle as eo
+
+RTOL = 1e-4
+
+
+def _close(got, want, what, rtol=RTOL, rel_atol=1e-4, flip_frac=0.0):
+    """flip_frac: fraction of elements allowed to disagree -- a pre-activation within rounding of zero lands on either
+    side of the ReLU in two correct fp32 forwards, which switches single elements of dL/dz on or off."""
+    want = np.asarray(want, dtype=np.float64)
+    atol = rel_atol * max(float(np.abs(want).max()), 1e-30)
+    if flip_frac:
+        bad = np.abs(np.asarray(got, dtype=np.float64) - want) > atol + rtol * np.abs(want)
+        assert bad.sum() <= flip_frac * bad.size, f"{what}: {int(bad.sum())} of {bad.size} elements disagree"
+        return
+    gu.assert_close(got, want, rtol, atol, what)
+
+
+def test_workspace_plan_cpu():
+    """No GPU needed: the plan is host arithmetic (and the symbols exist)."""
+    from super_sac_b200 import _lib
+
+    lib = _lib.lib()
+    n = ctypes.c_int64()
+    lib.conv_encoder_ws_floats(512, 9, 84, 84, 50, 1, ctypes.byref(n))
+    off = (ctypes.c_int64 * 24)()
+    lib.conv_encoder_ws_offsets(512, 9, 84, 84, 50, 1, off)
+    pp, gw, npx, kf, kfp, ks, nsplit, total = [off[i] for i in range(14, 22)]
+    assert (pp, gw, npx) == (42 * 42, 42, 512 * 42 * 42)
+    assert kf == 42 * 42 * 32 and kfp == ks * nsplit >= kf and ks % 32 == 0
+    assert total == n.value and all(off[i] % 256 == 0 for i in range(14))
+    with pytest.raises(_lib.SsacError):
+        lib.conv_encoder_ws_floats(4, 17, 84, 84, 50, 1, ctypes.byref(n))   # 4C must fit 64 channels
+    with pytest.raises(_lib.SsacError):
+        lib.conv_encoder_ws_floats(4, 9, 83, 84, 50, 1, ctypes.byref(n))
+
+
+class _Native:
+    """The encoder through the C ABI with a test-owned workspace (so intermediates can be inspected)."""
+
+    def __init__(self, params, B, C, H, W, O, save=1):
+        from super_sac_b200 import _lib
+
+        self.lib, self._lib = _lib.lib(), _lib
+        self.dims = (B, C, H, W, O)
+        self.save = save
+        self.params = [torch.as_tensor(np.asarray(params[n])).float().cuda().contiguous() for n in eo.PARAM_NAMES]
+        n = ctypes.c_int64()
+        self.lib.conv_encoder_ws_floats(B, C, H, W, O, save, ctypes.byref(n))
+        self.ws = torch.zeros(n.value, device="cuda")
+        off = (ctypes.c_int64 * 24)()
+        self.lib.conv_encoder_ws_offsets(B, C, H, W, O, save, off)
+        self.off = list(off)
+        self.pp, self.gw = self.off[14], self.off[15]
+        self.out = torch.empty(B, O, device="cuda")
+        self.grads = [torch.full_like(p, float("nan")) for p in self.params]
+
+    def _ptrs(self, ts):
+        return self._lib.host_array(ctypes.c_void_p, [t.data_ptr() for t in ts])
+
+    def forward(self, obs):
+        B, C, H, W, O = self.dims
+        self.obs = torch.as_tensor(np.asarray(obs)).float().cuda().contiguous()
+        self.lib.conv_encoder_forward(self.obs.data_ptr(), B, C, H, W, O, self._ptrs(self.params), self.ws.data_ptr(),
+                                      self.save, self.out.data_ptr(), self._lib.stream_ptr())
+        torch.cuda.synchronize()
+        return self.out.cpu().numpy()
+
+    def backward(self, dout):
+        B, C, H, W, O = self.dims
+        d = torch.as_tensor(np.asarray(dout)).float().cuda().contiguous()
+        self.lib.conv_encoder_backward(d.data_ptr(), self.out.data_ptr(), B, C, H, W, O, self._ptrs(self.params),
+                                       self.ws.data_ptr(), self._ptrs(self.grads), self._lib.stream_ptr())
+        torch.cuda.synchronize()
+        return {n: g.cpu().numpy() for n, g in zip(eo.PARAM_NAMES, self.grads)}
+
+    def act(self, slot, layer):
+        """Valid region of pitch-layout buffer `slot` (ws offset index) as NCHW, for conv layer `layer`'s output size."""
+        B = self.dims[0]
+        gh = self.pp // self.gw
+        v_h, v_w = gh - 1 - 2 * (layer - 1), self.gw - 1 - 2 * (layer - 1)
+        o = self.off[slot]
+        x = self.ws[o:o + B * self.pp * 32].view(B, gh, self.gw, 32)
+        return x[:, :v_h, :v_w, :].permute(0, 3, 1, 2).contiguous().cpu().numpy(), x
+
+
+def _native_masks(nat, cache, tag):
+    """The ReLU patterns of the native forward; where they differ from the oracle's, the oracle's activation is within
+    rounding of zero -- and that happens for a handful of elements only."""
+    masks = {}
+    for l in range(1, 5):
+        got, _ = nat.act(l, l)
+        want = cache["acts"][l].numpy()
+        _close(got, want, f"{tag} y{l}")
+        masks[l] = got > 0
+        diff = masks[l] != (want > 0)
+        assert diff.sum() <= 1e-5 * diff.size + 2, f"{tag} y{l}: {int(diff.sum())} ReLU decisions differ"
+        if diff.any():
+            assert np.abs(want[diff]).max() <= 1e-4 * np.abs(want).max() and np.abs(got[diff]).max() <= 1e-4 * np.abs(want).max()
+    return masks
+
+
+def _check_layers(nat, cache, g, tag):
+    # d0 / d1 hold dz4, dz3, dz2, dz1 alternately; after the backward dz1 and dz2 are still there: 4 -> d0, 3 -> d1, 2 -> d0, 1 -> d1
+    for l, slot in ((2, 5), (1, 6)):
+        got, full = nat.act(slot, l)
+        _close(got, g[f"dz{l}"].numpy(), f"{tag} dz{l}")
+        gh = nat.pp // nat.gw
+        v_h, v_w = gh - 1 - 2 * (l - 1), nat.gw - 1 - 2 * (l - 1)
+        assert float(full[:, v_h:, :, :].abs().max()) == 0.0 and float(full[:, :, v_w:, :].abs().max()) == 0.0, \
+            f"{tag} dz{l}: gradient outside the valid region"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["rgb20", "stack24"])
+def test_encoder_golden_through_c_abi(tag):
+    fx = gu.load("encoder")
+    params = gu.sub(fx, f"{tag}/params")
+    obs = fx[f"{tag}/obs"].astype(np.float32)
+    B, C, H, W = obs.shape
+    O = fx[f"{tag}/out"].shape[1]
+    nat = _Native(params, B, C, H, W, O)
+    out = nat.forward(obs)
+    ref_out, cache = eo.forward(params, obs)
+    # layer by layer against the oracle first (localises a failure), then the reference's own numbers
+    masks = _native_masks(nat, cache, tag)
+    g_or = eo.backward(cache, fx[f"{tag}/dout"], masks)
+    _close(out, fx[f"{tag}/out"], f"{tag} out")
+    grads = nat.backward(fx[f"{tag}/dout"])
+    _check_layers(nat, cache, g_or, tag)
+    want = gu.sub(fx, f"{tag}/grads")
+    for n in reversed(eo.PARAM_NAMES):
+        _close(grads[n], want[n], f"{tag} grad {n}")
+    # a second pass over the same (now dirty) workspace gives the same bits: nothing leaks through the padding
+    out2 = nat.forward(obs)
+    grads2 = nat.backward(fx[f"{tag}/dout"])
+    assert np.array_equal(out, out2)
+    for n in eo.PARAM_NAMES:
+        assert np.array_equal(grads[n], grads2[n]), n
+    # the no-grad variant (ping-pong buffers) computes the same forward
+    nat0 = _Native(params, B, C, H, W, O, save=0)
+    assert np.array_equal(nat0.forward(obs), out)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["rgb20", "stack24"])
+def test_encoder_module_autograd_matches_reference(tag):
+    """The drop-in module: forward + loss.backward() fill .grad like the reference's autograd does; a deepcopy (the target
+    encoder, main.py:321) runs without grad on its own workspace."""
+    import copy
+
+    from super_sac_b200.nets import cnns
+
+    fx = gu.load("encoder")
+    obs = fx[f"{tag}/obs"]
+    B, C, H, W = obs.shape
+    O = fx[f"{tag}/out"].shape[1]
+    enc = cnns.BigPixelEncoder((C, H, W), out_dim=O)
+    enc.load_state_dict({k: torch.as_tensor(v) for k, v in gu.sub(fx, f"{tag}/params").items()})
+    enc.cuda()
+    x = torch.as_tensor(obs).cuda().float()
+    y = enc(x)
+    _close(y.detach().cpu().numpy(), fx[f"{tag}/out"], f"{tag} module out")
+    (y * torch.as_tensor(fx[f"{tag}/dout"]).cuda()).sum().backward()
+    want = gu.sub(fx, f"{tag}/grads")
+    for n, p in enc.named_parameters():
+        _close(p.grad.cpu().numpy(), want[n], f"{tag} module grad {n}")
+    tgt = copy.deepcopy(enc)
+    with torch.no_grad():
+        y2 = tgt(x)
+    assert torch.equal(y2, y.detach())
+    # uint8 observations are accepted as they come out of the replay ring
+    with torch.no_grad():
+        assert torch.equal(enc(torch.as_tensor(obs).cuda()), y.detach())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B", [64, 512])
+def test_encoder_baseline_geometry_against_oracle(B):
+    """BASELINE config 4: 9 x 84 x 84 uint8 frames, out_dim 50 (B = 512 is the bench's batch)."""
+    rng = np.random.default_rng(5)
+    torch.manual_seed(5)
+    C, H, W, O = 9, 84, 84, 50
+    from super_sac_b200.nets import cnns
+
+    enc = cnns.BigPixelEncoder((C, H, W), out_dim=O)
+    with torch.no_grad():
+        for p in enc.parameters():
+            p.add_(0.02 * torch.randn_like(p))
+    params = {k: v.detach().numpy() for k, v in enc.named_parameters()}
+    obs = rng.integers(0, 256, (B, C, H, W)).astype(np.float32)
+    dout = rng.standard_normal((B, O)).astype(np.float32)
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    ref_out, cache = eo.forward(params, obs)
+    nat = _Native(params, B, C, H, W, O)
+    out = nat.forward(obs)
+    masks = _native_masks(nat, cache, f"B{B}")
+    g = eo.backward(cache, dout, masks)   # both sides differentiate through the same ReLU pattern
+    _close(out, ref_out.numpy(), "out")
+    grads = nat.backward(dout)
+    _check_layers(nat, cache, g, f"B{B}")
+    for n in reversed(eo.PARAM_NAMES):
+        _close(grads[n], g[n].numpy(), f"grad {n}")

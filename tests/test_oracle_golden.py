@@ -211,3 +211,19 @@ def test_afbc_oracle_matches_reference():
         gu.assert_close(buf.it_sum.value, tr["sum_tree"], 1e-5, 1e-9, "sum tree")  # priorities come from fp32 advantages
         assert np.array_equal(np.isinf(buf.it_min.value), np.isinf(tr["min_tree"]))
         assert abs(buf.max_priority - float(tr["max_priority"])) <= 1e-5 * float(tr["max_priority"])
+
+
+@pytest.mark.parametrize("tag", ["rgb20", "stack24"])
+def test_encoder_oracle_matches_reference(tag):
+    """oracle/encoder_oracle.py (explicit tap-by-tap forward / backward) == the unmodified BigPixelEncoder + autograd."""
+    from oracle import encoder_oracle as eo
+
+    torch.set_num_threads(1)
+    fx = gu.load("encoder")
+    params = gu.sub(fx, f"{tag}/params")
+    want = gu.sub(fx, f"{tag}/grads")
+    out, cache = eo.forward(params, fx[f"{tag}/obs"].astype(np.float32))
+    gu.assert_close(out.numpy(), fx[f"{tag}/out"], 2e-5, 2e-6, f"{tag} out")
+    g = eo.backward(cache, fx[f"{tag}/dout"])
+    for n in eo.PARAM_NAMES:
+        gu.assert_close(g[n].numpy(), want[n], 1e-4, 1e-5, f"{tag} grad {n}")
