@@ -383,7 +383,8 @@ int ssac_peer_wait(const void* my_buf_dev, int64_t half_bytes, int64_t nbytes, c
  * (not accumulated).  ssac_conv_encoder_ws_offsets (tests / tools): int64[24] = float offsets of {x0, y1..y4, d0, d1, wfc,
  * gwfc, fc partials, xhat, rstd, dfc, dl} followed by {pixels per image, pitch, pixels, kf, kf padded, split size, splits,
  * total}. */
-/* debugging switch (results do not depend on it): 0 = one TMA box per filter tap, 1 = one halo box per tile (default) */
+/* debugging switch (results do not depend on it): bit 0 = halo tiles (one TMA box per tile instead of one per filter tap) in
+ * the forward / data-gradient kernel, bit 1 = in the weight-gradient kernel; default 3 */
 int ssac_set_conv_halo(int mode);
 int ssac_conv_encoder_ws_floats(int B, int C, int H, int W, int out_dim, int save, int64_t* n_floats_out);
 int ssac_conv_encoder_ws_offsets(int B, int C, int H, int W, int out_dim, int save, int64_t* offsets_out);

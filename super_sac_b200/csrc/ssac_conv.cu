@@ -45,7 +45,7 @@ constexpr int kConvStageBytes = 32768;   // A_hi + A_lo
 constexpr int kConvSmem = kWBytes + kConvStages * kConvStageBytes + 16384 + 1024;
 
 struct ConvP {
-  CUtensorMap tmIn;    // (channels, pixels), box 32 x 128, SWIZZLE_128B
+  CUtensorMap tmIn;    // (channels, pixels), SWIZZLE_128B; box 32 x 128 (one per tap-block) or 32 x hr (one halo box per tile)
   CUtensorMap tmOut;   // (32, pixels), box 32 x 128, SWIZZLE_128B
   const float* wpack;  // ntb x 8 KB shared-memory images (conv_pack_kernel)
   const float* bias;   // mode 0
@@ -55,17 +55,84 @@ struct ConvP {
   int ntiles, mode;
   int64_t np;
   int pp, pw, vh, vw;  // mode 1: pixels per image, pitch, valid rows / cols of yprev
-  // halo > 0 (32-channel layers): ONE box of hr rows per tile -- pixels base .. base + hr - 1, base = q0 + halo_base --
+  // halo kernel (32-channel layers): ONE box of hr rows per tile -- pixels base .. base + hr - 1, base = q0 + halo_base --
   // and tap t reads it at row offset toff[t] through the start address of its UMMA descriptor, so every input pixel
   // crosses shared memory once instead of nine times.  MEASURED on B200: the 128-byte swizzle is a function of the
   // absolute shared-memory address, so a descriptor whose start address is offset by whole rows inside a 1024-byte
   // aligned tile reads exactly the rows TMA wrote there -- with the descriptor's base-offset field left at 0 (setting it
   // to (start >> 7) & 7 gives wrong results).
-  int halo, hr, halo_base;
+  int hr, halo_base, nhi;
   int toff[kMaxTB];
 };
-constexpr int kHaloStages = 2;
 
+// Epilogue warps 0-3 (thread = pixel = TMEM lane) of both convolution kernels: accumulator halves added, bias + ReLU
+// (forward) or ReLU / valid-region mask (data gradient), tile staged in the SWIZZLE_128B image of a [32 x 128] box and
+// stored by TMA (clipped at the end of the tensor).
+__device__ __forceinline__ void conv_epilogue(const ConvP& q, uint32_t tmem_d, uint64_t* bar_accf, uint64_t* bar_acce,
+                                              uint8_t* osm, const float* bias_sh, int ntl) {
+  const int t = threadIdx.x, warp = t >> 5, row = t;
+  const uint32_t r7 = (uint32_t)(row & 7);
+  uint8_t* orow = osm + (uint32_t)(row >> 3) * 1024u + r7 * 128u;
+  for (int i = 0; i < ntl; ++i) {
+    const int buf = i & 1;
+    const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+    const int64_t pix = (int64_t)tile * 128 + row;
+    float4 mk[8];
+    bool valid = true;
+    if (q.mode == 1) {
+      valid = pix < q.np;
+      if (valid) {
+        const int r = (int)(pix % q.pp);
+        valid = (r / q.pw) < q.vh && (r % q.pw) < q.vw;
+      }
+      if (valid) {
+        const float4* yp = reinterpret_cast<const float4*>(q.yprev + pix * 32);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) mk[c] = __ldg(yp + c);
+      }
+    }
+    mbar_wait(&bar_accf[buf], (uint32_t)((i >> 1) & 1));
+    fence_after_sync();
+    uint32_t r0[32], r1[32];
+    const uint32_t ta = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * 64);
+    tmem_ld32_issue(ta, r0);
+    tmem_ld32_issue(ta + 32u, r1);
+    tmem_wait_ld();
+    fence_before_sync();
+    mbar_arrive(&bar_acce[buf]);
+    if (t == 0) tma_store_wait_read();                 // the previous tile's store has read the staging tile
+    asm volatile("bar.sync 2, 128;" ::: "memory");
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float4 o;
+      o.x = __uint_as_float(r0[4 * c + 0]) + __uint_as_float(r1[4 * c + 0]);
+      o.y = __uint_as_float(r0[4 * c + 1]) + __uint_as_float(r1[4 * c + 1]);
+      o.z = __uint_as_float(r0[4 * c + 2]) + __uint_as_float(r1[4 * c + 2]);
+      o.w = __uint_as_float(r0[4 * c + 3]) + __uint_as_float(r1[4 * c + 3]);
+      if (q.mode == 0) {
+        o.x = fmaxf(o.x + bias_sh[4 * c + 0], 0.f); o.y = fmaxf(o.y + bias_sh[4 * c + 1], 0.f);
+        o.z = fmaxf(o.z + bias_sh[4 * c + 2], 0.f); o.w = fmaxf(o.w + bias_sh[4 * c + 3], 0.f);
+      } else {
+        if (valid) {
+          o.x = mk[c].x > 0.f ? o.x : 0.f; o.y = mk[c].y > 0.f ? o.y : 0.f;
+          o.z = mk[c].z > 0.f ? o.z : 0.f; o.w = mk[c].w > 0.f ? o.w : 0.f;
+        } else {
+          o = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      *reinterpret_cast<float4*>(orow + (((uint32_t)c ^ r7) << 4)) = o;
+    }
+    fence_async_smem();
+    asm volatile("bar.sync 2, 128;" ::: "memory");
+    if (t == 0) {
+      tma_store_2d(&q.tmOut, smem_u32(osm), 0, tile * 128);
+      tma_store_commit();
+    }
+  }
+  if (t == 0) tma_store_wait_all();
+}
+
+// ---- per-tap kernel: the 64-channel first layer (and any geometry whose halo does not fit) --------------------------
 __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_constant__ ConvP q) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_raw[kConvStages], bar_full[kConvStages], bar_empty[kConvStages];
@@ -76,7 +143,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* wsm = smem;
   uint8_t* stg = smem + kWBytes;
-  uint8_t* osm = stg + (q.halo ? kHaloStages * 2 * q.hr * 128 : kConvStages * kConvStageBytes);
+  uint8_t* osm = stg + kConvStages * kConvStageBytes;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
 
   if (warp == 0) tmem_alloc(&tmem_base_sh, 128);
@@ -110,16 +177,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
 
   if (warp == 9) {
     // ===== TMA producer: one 16 KB box (128 pixels x 32 channels) per tap-block ====================================
-    if (lane == 0 && q.halo) {
-      const uint32_t hrb = (uint32_t)q.hr * 128u;
-      for (int i = 0; i < ntl; ++i) {
-        const int q0 = ((int)blockIdx.x + i * (int)gridDim.x) * 128;
-        const int s = i % kHaloStages, use = i / kHaloStages;
-        if (i >= kHaloStages) mbar_wait(&bar_empty[s], (uint32_t)((use - 1) & 1));
-        mbar_arrive_expect_tx(&bar_raw[s], hrb);
-        tma_load_2d(smem_u32(stg) + (uint32_t)s * 2u * hrb, &q.tmIn, &bar_raw[s], 0, q0 + q.halo_base);
-      }
-    } else if (lane == 0) {
+    if (lane == 0) {
       int it = 0;
       for (int i = 0; i < ntl; ++i) {
         const int q0 = ((int)blockIdx.x + i * (int)gridDim.x) * 128;
@@ -134,6 +192,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
   } else if (warp == 8) {
     // ===== MMA issuer ==============================================================================================
     const uint32_t idesc64 = instr_desc(64, 0, 0), idesc32 = instr_desc(32, 0, 0);
+    const uint64_t dah0 = smem_desc(smem_u32(stg), 16u, 1024u, 2u), db0 = smem_desc(smem_u32(wsm), 16u, 1024u, 2u);
     int it = 0;
     for (int i = 0; i < ntl; ++i) {
       const int buf = i & 1;
@@ -142,45 +201,21 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
         mbar_wait(&bar_acce[buf], (uint32_t)(((i >> 1) - 1) & 1));   // the epilogue has drained this accumulator
         fence_after_sync();
       }
-      if (q.halo) {
-        const uint32_t hrb = (uint32_t)q.hr * 128u;
-        const int s = i % kHaloStages, use = i / kHaloStages;
-        mbar_wait(&bar_full[s], (uint32_t)(use & 1));
-        fence_after_sync();
-        if (lane == 0) {
-          const uint32_t h_hi = smem_u32(stg) + (uint32_t)s * 2u * hrb, h_lo = h_hi + hrb;
-          for (int tb = 0; tb < ntb; ++tb) {
-            const uint32_t roff = (uint32_t)q.toff[tb] * 128u;
-            const uint32_t b = smem_u32(wsm) + (uint32_t)tb * 8192u;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint64_t dah = smem_desc(h_hi + roff + j * 32, 16u, 1024u, 2u);
-              const uint64_t dal = smem_desc(h_lo + roff + j * 32, 16u, 1024u, 2u);
-              const uint64_t db = smem_desc(b + j * 32, 16u, 1024u, 2u);
-              mma_tf32(d, dah, db, idesc64, (tb | j) != 0);
-              mma_tf32(d, dal, db, idesc32, 1u);
-            }
-          }
-          mma_commit(&bar_empty[s]);
-          mma_commit(&bar_accf[buf]);
-        }
-        __syncwarp();
-        continue;
-      }
       for (int tb = 0; tb < ntb; ++tb, ++it) {
         const int s = it % kConvStages, use = it / kConvStages;
         mbar_wait(&bar_full[s], (uint32_t)(use & 1));
         fence_after_sync();
         if (lane == 0) {
-          const uint32_t a_hi = smem_u32(stg + s * kConvStageBytes), a_lo = a_hi + 16384u;
-          const uint32_t b = smem_u32(wsm) + (uint32_t)tb * 8192u;
+          // descriptors differ only in their 14-bit start-address field (bytes >> 4): one add per MMA instead of a rebuild --
+          // with N = 64 / 32 the MMAs are short and the issuing thread's instruction count is what limits the kernel
+          const uint64_t dah = dah0 + (uint64_t)(s * (kConvStageBytes >> 4)), dal = dah + (16384u >> 4);
+          const uint64_t db = db0 + (uint64_t)(tb * (8192 >> 4));
+          mma_tf32(d, dah, db, idesc64, tb != 0);           // A_hi . [B_hi | B_lo] -> columns 0..63
+          mma_tf32(d, dal, db, idesc32, 1u);                // A_lo . B_hi          -> columns 0..31
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint64_t dah = smem_desc(a_hi + j * 32, 16u, 1024u, 2u);
-            const uint64_t dal = smem_desc(a_lo + j * 32, 16u, 1024u, 2u);
-            const uint64_t db = smem_desc(b + j * 32, 16u, 1024u, 2u);
-            mma_tf32(d, dah, db, idesc64, (tb | j) != 0);   // A_hi . [B_hi | B_lo] -> columns 0..63
-            mma_tf32(d, dal, db, idesc32, 1u);              // A_lo . B_hi          -> columns 0..31
+          for (int j = 1; j < 4; ++j) {
+            mma_tf32(d, dah + 2 * j, db + 2 * j, idesc64, 1u);
+            mma_tf32(d, dal + 2 * j, db + 2 * j, idesc32, 1u);
           }
           mma_commit(&bar_empty[s]);
           if (tb == ntb - 1) mma_commit(&bar_accf[buf]);
@@ -191,21 +226,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
   } else if (warp >= 4) {
     // ===== lo planes ===============================================================================================
     const int tl = t - 128;
-    if (q.halo) {
-      const uint32_t hrb = (uint32_t)q.hr * 128u;
-      const int n16 = q.hr * 8;
-      for (int i = 0; i < ntl; ++i) {
-        const int s = i % kHaloStages, use = i / kHaloStages;
-        mbar_wait(&bar_raw[s], (uint32_t)(use & 1));
-        uint8_t* hi = stg + (size_t)s * 2u * hrb;
-        uint8_t* lo = hi + hrb;
-        for (int k = tl; k < n16; k += 128)
-          *reinterpret_cast<float4*>(lo + k * 16) = lo4(*reinterpret_cast<const float4*>(hi + k * 16));
-        fence_async_smem();
-        mbar_arrive(&bar_full[s]);
-      }
-    }
-    const int nit = q.halo ? 0 : ntl * ntb;
+    const int nit = ntl * ntb;
     for (int it = 0; it < nit; ++it) {
       const int s = it % kConvStages, use = it / kConvStages;
       mbar_wait(&bar_raw[s], (uint32_t)(use & 1));
@@ -220,67 +241,128 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
       mbar_arrive(&bar_full[s]);
     }
   } else {
-    // ===== epilogue: thread = pixel = TMEM lane ====================================================================
-    const int row = t;
-    const uint32_t r7 = (uint32_t)(row & 7);
-    uint8_t* orow = osm + (uint32_t)(row >> 3) * 1024u + r7 * 128u;
-    for (int i = 0; i < ntl; ++i) {
-      const int buf = i & 1;
-      const int tile = (int)blockIdx.x + i * (int)gridDim.x;
-      const int64_t pix = (int64_t)tile * 128 + row;
-      float4 mk[8];
-      bool valid = true;
-      if (q.mode == 1) {
-        valid = pix < q.np;
-        if (valid) {
-          const int r = (int)(pix % q.pp);
-          valid = (r / q.pw) < q.vh && (r % q.pw) < q.vw;
-        }
-        if (valid) {
-          const float4* yp = reinterpret_cast<const float4*>(q.yprev + pix * 32);
-#pragma unroll
-          for (int c = 0; c < 8; ++c) mk[c] = __ldg(yp + c);
-        }
-      }
-      mbar_wait(&bar_accf[buf], (uint32_t)((i >> 1) & 1));
-      fence_after_sync();
-      uint32_t r0[32], r1[32];
-      const uint32_t ta = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * 64);
-      tmem_ld32_issue(ta, r0);
-      tmem_ld32_issue(ta + 32u, r1);
-      tmem_wait_ld();
-      fence_before_sync();
-      mbar_arrive(&bar_acce[buf]);
-      if (t == 0) tma_store_wait_read();                 // the previous tile's store has read the staging tile
-      asm volatile("bar.sync 2, 128;" ::: "memory");
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        float4 o;
-        o.x = __uint_as_float(r0[4 * c + 0]) + __uint_as_float(r1[4 * c + 0]);
-        o.y = __uint_as_float(r0[4 * c + 1]) + __uint_as_float(r1[4 * c + 1]);
-        o.z = __uint_as_float(r0[4 * c + 2]) + __uint_as_float(r1[4 * c + 2]);
-        o.w = __uint_as_float(r0[4 * c + 3]) + __uint_as_float(r1[4 * c + 3]);
-        if (q.mode == 0) {
-          o.x = fmaxf(o.x + bias_sh[4 * c + 0], 0.f); o.y = fmaxf(o.y + bias_sh[4 * c + 1], 0.f);
-          o.z = fmaxf(o.z + bias_sh[4 * c + 2], 0.f); o.w = fmaxf(o.w + bias_sh[4 * c + 3], 0.f);
-        } else {
-          if (valid) {
-            o.x = mk[c].x > 0.f ? o.x : 0.f; o.y = mk[c].y > 0.f ? o.y : 0.f;
-            o.z = mk[c].z > 0.f ? o.z : 0.f; o.w = mk[c].w > 0.f ? o.w : 0.f;
-          } else {
-            o = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
-        *reinterpret_cast<float4*>(orow + (((uint32_t)c ^ r7) << 4)) = o;
-      }
-      fence_async_smem();
-      asm volatile("bar.sync 2, 128;" ::: "memory");
-      if (t == 0) {
-        tma_store_2d(&q.tmOut, smem_u32(osm), 0, tile * 128);
-        tma_store_commit();
+    conv_epilogue(q, tmem_d, bar_accf, bar_acce, osm, bias_sh, ntl);
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_d, 128);
+}
+
+// ---- halo kernel: the 32-channel layers, forward and data gradient ---------------------------------------------------
+// 14 warps: 0-3 epilogue, 4-11 lo planes, 12 MMA issuer, 13 TMA producer.  Shared memory: resident weights (72 KB), a ring
+// of nhi raw halo tiles (the TMA prefetch depth), a ring of 2 lo planes, the output staging tile.
+constexpr int kHaloThreads = 448;
+constexpr int kMaxHi = 3;
+__global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid_constant__ ConvP q) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_raw[kMaxHi], bar_hie[kMaxHi], bar_lof[2], bar_loe[2];
+  __shared__ __align__(8) uint64_t bar_accf[2], bar_acce[2];
+  __shared__ uint32_t tmem_base_sh;
+  __shared__ float bias_sh[32];
+
+  const uint32_t hrb = (uint32_t)q.hr * 128u;
+  const int nhi = q.nhi;
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* wsm = smem;
+  uint8_t* his = smem + kWBytes;
+  uint8_t* los = his + (size_t)nhi * hrb;
+  uint8_t* osm = los + 2 * (size_t)hrb;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+
+  if (warp == 0) tmem_alloc(&tmem_base_sh, 128);
+  if (t == 0) {
+    for (int s = 0; s < kMaxHi; ++s) {
+      mbar_init(&bar_raw[s], 1);
+      mbar_init(&bar_hie[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bar_lof[b], 256);
+      mbar_init(&bar_loe[b], 1);
+      mbar_init(&bar_accf[b], 1);
+      mbar_init(&bar_acce[b], 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  pdl_wait();
+  pdl_trigger();
+  {
+    const float4* src = reinterpret_cast<const float4*>(q.wpack);
+    float4* dst = reinterpret_cast<float4*>(wsm);
+    for (int i = t; i < q.ntb * 512; i += kHaloThreads) dst[i] = __ldg(src + i);
+  }
+  if (t < 32) bias_sh[t] = q.bias ? __ldg(q.bias + t) : 0.f;
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_d = tmem_base_sh;
+  const int ntl = ((int)blockIdx.x < q.ntiles) ? (q.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int ntb = q.ntb;
+
+  if (warp == 13) {
+    if (lane == 0) {
+      for (int i = 0; i < ntl; ++i) {
+        const int q0 = ((int)blockIdx.x + i * (int)gridDim.x) * 128;
+        const int h = i % nhi, use = i / nhi;
+        if (i >= nhi) mbar_wait(&bar_hie[h], (uint32_t)((use - 1) & 1));
+        mbar_arrive_expect_tx(&bar_raw[h], hrb);
+        tma_load_2d(smem_u32(his) + (uint32_t)h * hrb, &q.tmIn, &bar_raw[h], 0, q0 + q.halo_base);
       }
     }
-    if (t == 0) tma_store_wait_all();
+  } else if (warp == 12) {
+    const uint32_t idesc64 = instr_desc(64, 0, 0), idesc32 = instr_desc(32, 0, 0);
+    const uint64_t dah0 = smem_desc(smem_u32(his), 16u, 1024u, 2u), dal0 = smem_desc(smem_u32(los), 16u, 1024u, 2u);
+    const uint64_t db0 = smem_desc(smem_u32(wsm), 16u, 1024u, 2u);
+    for (int i = 0; i < ntl; ++i) {
+      const int buf = i & 1, h = i % nhi, l = i & 1;
+      const uint32_t d = tmem_d + (uint32_t)(buf * 64);
+      if (i >= 2) {
+        mbar_wait(&bar_acce[buf], (uint32_t)(((i >> 1) - 1) & 1));
+        fence_after_sync();
+      }
+      mbar_wait(&bar_lof[l], (uint32_t)((i >> 1) & 1));     // lo plane written (its writers waited for the raw tile)
+      fence_after_sync();
+      if (lane == 0) {
+        const uint64_t dh = dah0 + (uint64_t)((uint32_t)h * (hrb >> 4)), dl = dal0 + (uint64_t)((uint32_t)l * (hrb >> 4));
+        for (int tb = 0; tb < ntb; ++tb) {
+          const uint64_t ro = (uint64_t)(q.toff[tb] * 8);          // rows of 128 bytes, in 16-byte units
+          const uint64_t dah = dh + ro, dal = dl + ro, db = db0 + (uint64_t)(tb * (8192 >> 4));
+          mma_tf32(d, dah, db, idesc64, tb != 0);
+          mma_tf32(d, dal, db, idesc32, 1u);
+#pragma unroll
+          for (int j = 1; j < 4; ++j) {
+            mma_tf32(d, dah + 2 * j, db + 2 * j, idesc64, 1u);
+            mma_tf32(d, dal + 2 * j, db + 2 * j, idesc32, 1u);
+          }
+        }
+        mma_commit(&bar_hie[h]);
+        mma_commit(&bar_loe[l]);
+        mma_commit(&bar_accf[buf]);
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    const int tl = t - 128;          // 0..255
+    const int n16 = q.hr * 8;
+    for (int i = 0; i < ntl; ++i) {
+      const int h = i % nhi, l = i & 1;
+      mbar_wait(&bar_raw[h], (uint32_t)((i / nhi) & 1));
+      if (i >= 2) mbar_wait(&bar_loe[l], (uint32_t)(((i >> 1) - 1) & 1));
+      const uint8_t* hi = his + (size_t)h * hrb;
+      uint8_t* lo = los + (size_t)l * hrb;
+      int k = tl;
+      for (; k + 256 < n16; k += 512) {
+        const float4 v0 = *reinterpret_cast<const float4*>(hi + k * 16);
+        const float4 v1 = *reinterpret_cast<const float4*>(hi + (k + 256) * 16);
+        *reinterpret_cast<float4*>(lo + k * 16) = lo4(v0);
+        *reinterpret_cast<float4*>(lo + (k + 256) * 16) = lo4(v1);
+      }
+      if (k < n16) *reinterpret_cast<float4*>(lo + k * 16) = lo4(*reinterpret_cast<const float4*>(hi + k * 16));
+      fence_async_smem();
+      mbar_arrive(&bar_lof[l]);
+    }
+  } else {
+    conv_epilogue(q, tmem_d, bar_accf, bar_acce, osm, bias_sh, ntl);
   }
   fence_before_sync();
   __syncthreads();
@@ -347,24 +429,25 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_tc_kernel(const __gr
     }
   } else if (warp == 8) {
     const uint32_t idesc64 = instr_desc(64, 1, 1), idesc32 = instr_desc(32, 1, 1);
+    const uint64_t da0 = smem_desc(smem_u32(smem), 4096u, 512u, 1u);
+    const uint64_t db0 = smem_desc(smem_u32(smem) + 2u * kABytes, 4096u, 512u, 1u);
     for (int i = 0; i < nst; ++i) {
       const int s = i % kNS, use = i / kNS;
       mbar_wait(&bar_full[s], (uint32_t)(use & 1));
       fence_after_sync();
       if (lane == 0) {
-        const uint32_t base = smem_u32(smem + s * kStage);
-        const uint32_t b_hi = base + 2u * kABytes;     // B_lo follows at + 4096 = the second 32-column group
+        const uint64_t so = (uint64_t)(s * (kStage >> 4));
+        const uint64_t db = db0 + so;                  // B_lo follows at + 4096 = the second 32-column group
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
-          const uint32_t a_hi = base + (uint32_t)g * 16384u, a_lo = a_hi + (uint32_t)kABytes;
+          const uint64_t dah = da0 + so + (uint64_t)(g * (16384 >> 4)), dal = dah + (uint64_t)(kABytes >> 4);
           const uint32_t d = tmem_d + (uint32_t)(g * 64);
+          mma_tf32(d, dah, db, idesc64, i != 0);
+          mma_tf32(d, dal, db, idesc32, 1u);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint64_t dah = smem_desc(a_hi + j * 1024, 4096u, 512u, 1u);
-            const uint64_t dal = smem_desc(a_lo + j * 1024, 4096u, 512u, 1u);
-            const uint64_t db = smem_desc(b_hi + j * 1024, 4096u, 512u, 1u);
-            mma_tf32(d, dah, db, idesc64, (i | j) != 0);
-            mma_tf32(d, dal, db, idesc32, 1u);
+          for (int j = 1; j < 4; ++j) {
+            mma_tf32(d, dah + 64 * j, db + 64 * j, idesc64, 1u);
+            mma_tf32(d, dal + 64 * j, db + 64 * j, idesc32, 1u);
           }
         }
         mma_commit(&bar_empty[s]);
@@ -446,6 +529,166 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_tc_kernel(const __gr
   if (warp == 0) tmem_dealloc(tmem_d, 256);
 }
 
+// ---- weight gradient, halo variant (32-channel layers) -------------------------------------------------------------
+// One box of xr = 64 + reach + 1 input pixels per 64-pixel stage instead of twelve 32-pixel boxes: the three taps (kh, 0..2)
+// are the SAME rows shifted by one pixel each, i.e. the 32-column groups of an MN-major M = 128 operand that starts kh*gw
+// rows into the tile and whose leading-dimension byte offset is ONE row (128 bytes; the fourth group, kw = 3, is computed
+// and ignored).  Three accumulators (kh = 0, 1, 2) of 64 columns ([dZ_hi | dZ_lo]) each.
+struct WgradH {
+  CUtensorMap tmX;   // (32, pixels), box 32 x xr, SWIZZLE_128B_ATOM_32B
+  CUtensorMap tmD;   // (32, pixels), box 32 x 64
+  float* part;       // [grid][kMaxTB][32 ci][32 co]
+  float* bpart;      // [grid][32]
+  int gw, xr;
+  int nstages, spc;  // 64-pixel stages in total / per CTA
+};
+constexpr int kWhStages = 4;
+__global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_halo_kernel(const __grid_constant__ WgradH q) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_raw[kWhStages], bar_full[kWhStages], bar_empty[kWhStages], bar_done;
+  __shared__ uint32_t tmem_base_sh;
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const uint32_t xrb = (uint32_t)q.xr * 128u;
+  const uint32_t stage_bytes = 2u * xrb + 16384u;     // X_hi, X_lo, D_hi (8 KB), D_lo (8 KB)
+
+  if (warp == 0) tmem_alloc(&tmem_base_sh, 256);
+  if (t == 0) {
+    for (int s = 0; s < kWhStages; ++s) {
+      mbar_init(&bar_raw[s], 1);
+      mbar_init(&bar_full[s], 256);
+      mbar_init(&bar_empty[s], 1);
+    }
+    mbar_init(&bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  pdl_wait();
+  pdl_trigger();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_d = tmem_base_sh;
+  const int st0 = (int)blockIdx.x * q.spc;
+  const int nst = max(0, min(q.spc, q.nstages - st0));
+
+  if (warp == 9) {
+    if (lane == 0) {
+      for (int i = 0; i < nst; ++i) {
+        const int s = i % kWhStages, use = i / kWhStages;
+        if (i >= kWhStages) mbar_wait(&bar_empty[s], (uint32_t)((use - 1) & 1));
+        mbar_arrive_expect_tx(&bar_raw[s], xrb + 8192u);
+        const uint32_t base = smem_u32(smem) + (uint32_t)s * stage_bytes;
+        const int p0 = (st0 + i) * 64;
+        tma_load_2d(base, &q.tmX, &bar_raw[s], 0, p0);
+        tma_load_2d(base + 2u * xrb, &q.tmD, &bar_raw[s], 0, p0);
+      }
+    }
+  } else if (warp == 8) {
+    const uint32_t idesc64 = instr_desc(64, 1, 1), idesc32 = instr_desc(32, 1, 1);
+    const uint64_t da0 = smem_desc(smem_u32(smem), 128u, 512u, 1u);
+    const uint64_t db0 = smem_desc(smem_u32(smem) + 2u * xrb, 8192u, 512u, 1u);
+    for (int i = 0; i < nst; ++i) {
+      const int s = i % kWhStages, use = i / kWhStages;
+      mbar_wait(&bar_full[s], (uint32_t)(use & 1));
+      fence_after_sync();
+      if (lane == 0) {
+        // (descriptor = constant bits + start address >> 4: one add per MMA, see conv_tc_kernel)
+        const uint64_t so = (uint64_t)((uint32_t)s * (stage_bytes >> 4));
+        const uint64_t db = db0 + so;              // D_lo follows D_hi at + 8192 = the second 32-column group of B
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          const uint64_t dah = da0 + so + (uint64_t)(g * q.gw * 8), dal = dah + (uint64_t)(xrb >> 4);
+          const uint32_t d = tmem_d + (uint32_t)(g * 64);
+          mma_tf32(d, dah, db, idesc64, i != 0);
+          mma_tf32(d, dal, db, idesc32, 1u);
+#pragma unroll
+          for (int j = 1; j < 8; ++j) {
+            mma_tf32(d, dah + 64 * j, db + 64 * j, idesc64, 1u);
+            mma_tf32(d, dal + 64 * j, db + 64 * j, idesc32, 1u);
+          }
+        }
+        mma_commit(&bar_empty[s]);
+        if (i == nst - 1) mma_commit(&bar_done);
+      }
+      __syncwarp();
+    }
+  } else {
+    float cs[4] = {0.f, 0.f, 0.f, 0.f};
+    const int nx = q.xr * 8;
+    for (int i = 0; i < nst; ++i) {
+      const int s = i % kWhStages, use = i / kWhStages;
+      mbar_wait(&bar_raw[s], (uint32_t)(use & 1));
+      uint8_t* x_hi = smem + (size_t)s * stage_bytes;
+      uint8_t* x_lo = x_hi + xrb;
+      uint8_t* d_hi = x_hi + 2 * (size_t)xrb;
+      {
+        const float4 v0 = *reinterpret_cast<const float4*>(d_hi + t * 16);
+        const float4 v1 = *reinterpret_cast<const float4*>(d_hi + (t + 256) * 16);
+        *reinterpret_cast<float4*>(d_hi + 8192 + t * 16) = lo4(v0);
+        *reinterpret_cast<float4*>(d_hi + 8192 + (t + 256) * 16) = lo4(v1);
+        cs[0] += v0.x + v1.x; cs[1] += v0.y + v1.y; cs[2] += v0.z + v1.z; cs[3] += v0.w + v1.w;
+      }
+      int k = t;
+      for (; k + 256 < nx; k += 512) {
+        const float4 v0 = *reinterpret_cast<const float4*>(x_hi + k * 16);
+        const float4 v1 = *reinterpret_cast<const float4*>(x_hi + (k + 256) * 16);
+        *reinterpret_cast<float4*>(x_lo + k * 16) = lo4(v0);
+        *reinterpret_cast<float4*>(x_lo + (k + 256) * 16) = lo4(v1);
+      }
+      if (k < nx) *reinterpret_cast<float4*>(x_lo + k * 16) = lo4(*reinterpret_cast<const float4*>(x_hi + k * 16));
+      fence_async_smem();
+      mbar_arrive(&bar_full[s]);
+    }
+    if (nst > 0) mbar_wait(&bar_done, 0);
+    fence_after_sync();
+    // bias gradient: chunks t and t + 256 of the dZ tile sit on k rows t/8 and t/8 + 32 (same row % 4, same columns)
+    float* scr = reinterpret_cast<float*>(smem);
+    {
+      const int krow = t >> 3;
+      const int col = 8 * (((t >> 1) & 3) ^ (krow & 3)) + 4 * (t & 1);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) scr[krow * 32 + col + e] = cs[e];
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (t < 32) {
+      float tot = 0.f;
+      for (int k = 0; k < 32; ++k) tot += scr[k * 32 + t];
+      q.bpart[(int64_t)blockIdx.x * 32 + t] = tot;
+    }
+    if (warp < 3) {
+      // TMEM lane m = 32 kw + ci of accumulator kh
+#pragma unroll
+      for (int g = 0; g < 3; ++g) {
+        const int tb = g * 3 + warp;
+        float4 o[8];
+        if (nst > 0) {
+          uint32_t r0[32], r1[32];
+          const uint32_t ta = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g * 64);
+          tmem_ld32_issue(ta, r0);
+          tmem_ld32_issue(ta + 32u, r1);
+          tmem_wait_ld();
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            o[c].x = __uint_as_float(r0[4 * c + 0]) + __uint_as_float(r1[4 * c + 0]);
+            o[c].y = __uint_as_float(r0[4 * c + 1]) + __uint_as_float(r1[4 * c + 1]);
+            o[c].z = __uint_as_float(r0[4 * c + 2]) + __uint_as_float(r1[4 * c + 2]);
+            o[c].w = __uint_as_float(r0[4 * c + 3]) + __uint_as_float(r1[4 * c + 3]);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) o[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float4* dst = reinterpret_cast<float4*>(q.part + (((int64_t)blockIdx.x * kMaxTB + tb) * 32 + lane) * 32);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) dst[c] = o[c];
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_d, 256);
+}
+
 // ---- small kernels -----------------------------------------------------------------------------------------------
 // Shared-memory images of the per-tap weight matrices: rows n = 0..31 hold B[n][k] as the tensor core sees it, rows
 // 32..63 the lo parts; K-major SWIZZLE_128B.
@@ -475,20 +718,27 @@ __global__ void conv_pack_kernel(const float* __restrict__ W, float* __restrict_
 }
 
 // obs [B,C,H,W] fp32 (0..255) -> X0[(b*pp + gy*gw + gx)*64 + (ph*2+pw)*C + c] = obs[b][c][2gy+ph][2gx+pw] / 255 - 0.5
-// (nets/cnns.py:58: two separately rounded fp32 operations).  One block per (image, row pair).
-__global__ void s2d_norm_kernel(const float* __restrict__ obs, float* __restrict__ x0, int C, int H, int W) {
+// (nets/cnns.py:58: two separately rounded fp32 operations).  One block per (image, group of `rp` row pairs): coalesced
+// reads along x, transposed through shared memory, 4C-float runs written per pixel.
+__global__ void s2d_norm_kernel(const float* __restrict__ obs, float* __restrict__ x0, int C, int H, int W, int rp) {
   extern __shared__ float sh[];
   const int gw = W / 2, gh = H / 2;
-  const int b = blockIdx.x / gh, gy = blockIdx.x % gh;
+  const int groups = (gh + rp - 1) / rp;
+  const int b = blockIdx.x / groups, gy0 = (blockIdx.x % groups) * rp;
+  const int nrp = min(rp, gh - gy0);
   const int c4 = 4 * C;
-  for (int idx = threadIdx.x; idx < C * 2 * W; idx += blockDim.x) {
-    const int c = idx / (2 * W), rem = idx % (2 * W), ph = rem / W, x = rem % W;
-    const float v = __ldg(obs + (((int64_t)b * C + c) * H + 2 * gy + ph) * W + x);
-    sh[(x >> 1) * c4 + (ph * 2 + (x & 1)) * C + c] = __fsub_rn(__fdiv_rn(v, 255.0f), 0.5f);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const float* src = obs + (int64_t)b * C * H * W + (int64_t)(2 * gy0) * W;
+  for (int row = warp; row < C * nrp * 2; row += nw) {        // row = (c, row pair r, ph): W contiguous floats
+    const int c = row / (nrp * 2), rr = row - c * (nrp * 2), r = rr >> 1, ph = rr & 1;
+    const float* rp_ = src + (int64_t)c * H * W + (int64_t)rr * W;
+    float* d = sh + (r * gw) * c4 + (ph * 2) * C + c;
+    for (int x = lane; x < W; x += 32) d[(x >> 1) * c4 + (x & 1) * C] = __fsub_rn(__fdiv_rn(__ldg(rp_ + x), 255.0f), 0.5f);
   }
   __syncthreads();
-  float* dst = x0 + ((int64_t)b * gh * gw + (int64_t)gy * gw) * 64;
-  for (int idx = threadIdx.x; idx < gw * c4; idx += blockDim.x) dst[(idx / c4) * 64 + idx % c4] = sh[idx];
+  float* dst = x0 + ((int64_t)b * gh * gw + (int64_t)gy0 * gw) * 64;
+  for (int pix = warp; pix < nrp * gw; pix += nw)
+    for (int c = lane; c < c4; c += 32) dst[pix * 64 + c] = sh[pix * c4 + c];
 }
 
 // gW[co][ci][kh][kw] (mode 0) or the first layer's gW[co][c][kh][kw] (mode 2) = sum over CTAs of the partial tap-block
@@ -675,11 +925,13 @@ int make_plan(int B, int C, int H, int W, int O, int save, EncPlan* p) {
   return 0;
 }
 
-int g_conv_halo = 1;
+int g_conv_halo = 3;   // bit 0: halo tiles in the forward / data-gradient kernel, bit 1: in the weight-gradient kernel
 bool g_conv_attr = false;
 int conv_attrs() {
   if (g_conv_attr) return 0;
   cudaError_t e = cudaFuncSetAttribute(cv::conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cv::kConvSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(cv::conv_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 231424);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(cv::conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 231424);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(cv::conv_wgrad_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (6 * 16384 + 8192) + 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(cv::conv_wgrad_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (4 * 16384 + 8192) + 1024);
   if (e != cudaSuccess) {
@@ -714,8 +966,11 @@ int launch_conv(const EncPlan& pl, int layer, bool dgrad, const float* in, int i
   taps_of(layer, pl.gw, dgrad, &q.ntb, q.shift, q.cb);
   const int reach = 2 * pl.gw + 2;                       // largest tap shift
   const int hr = (128 + reach + 7) & ~7;
-  if (g_conv_halo && in_ch == 32 && hr <= 256) {
-    q.halo = g_conv_halo; q.hr = hr;
+  bool halo = false;
+  if ((g_conv_halo & 1) && in_ch == 32 && hr <= 256) {
+    halo = true;
+    q.hr = hr;
+    q.nhi = (cv::kWBytes + 5 * hr * 128 + 16384 + 1024 <= 231424) ? 3 : 2;
     q.halo_base = dgrad ? -reach : 0;
     for (int t = 0; t < q.ntb; ++t) q.toff[t] = dgrad ? reach + q.shift[t] : q.shift[t];   // dgrad shifts are negative
     if (!tc::make_map2d(in, 32, 32, pl.np, hr, false, &q.tmIn)) return fail(SSAC_E_UNSUPPORTED, "conv encoder: tensor map");
@@ -724,6 +979,12 @@ int launch_conv(const EncPlan& pl, int layer, bool dgrad, const float* in, int i
   q.mode = dgrad ? 1 : 0;
   q.np = pl.np; q.pp = pl.pp; q.pw = pl.gw; q.vh = vh; q.vw = vw;
   const int grid = std::min(q.ntiles, kNumSMs);
+  if (halo) {
+    const size_t smem = cv::kWBytes + (size_t)(q.nhi + 2) * hr * 128 + 16384 + 1024;
+    cv::conv_halo_kernel<<<grid, cv::kHaloThreads, smem, s>>>(q);
+    SSAC_CHECK_LAUNCH("conv_halo_kernel");
+    return 0;
+  }
   cv::conv_tc_kernel<<<grid, cv::kConvThreads, cv::kConvSmem, s>>>(q);
   SSAC_CHECK_LAUNCH("conv_tc_kernel");
   return 0;
@@ -731,6 +992,23 @@ int launch_conv(const EncPlan& pl, int layer, bool dgrad, const float* in, int i
 
 int launch_wgrad(const EncPlan& pl, int layer, const float* x, int x_ch, const float* dz, float* ws, float* gW, float* gb,
                  cudaStream_t s) {
+  const int xr = (64 + 2 * pl.gw + 2 + 1 + 7) & ~7;
+  if ((g_conv_halo & 2) && x_ch == 32 && xr <= 256 && 4 * (2 * xr * 128 + 16384) + 1024 <= 232448) {
+    cv::WgradH h;
+    memset(&h, 0, sizeof(h));
+    if (!tc::make_map2d(x, 32, 32, pl.np, xr, true, &h.tmX) || !tc::make_map2d(dz, 32, 32, pl.np, 64, true, &h.tmD))
+      return fail(SSAC_E_UNSUPPORTED, "conv encoder: tensor map");
+    h.part = ws + pl.wpart; h.bpart = ws + pl.bpart;
+    h.gw = pl.gw; h.xr = xr;
+    h.nstages = (int)((pl.np + 63) / 64);
+    const int grid = std::min(h.nstages, kNumSMs);
+    h.spc = (h.nstages + grid - 1) / grid;
+    cv::conv_wgrad_halo_kernel<<<grid, cv::kWgThreads, 4 * (2 * xr * 128 + 16384) + 1024, s>>>(h);
+    SSAC_CHECK_LAUNCH("conv_wgrad_halo_kernel");
+    cv::wgrad_reduce_kernel<<<(9 * 1024 + 32 + 255) / 256, 256, 0, s>>>(h.part, h.bpart, grid, 0, pl.C, gW, gb);
+    SSAC_CHECK_LAUNCH("wgrad_reduce_kernel");
+    return 0;
+  }
   cv::WgradP q;
   memset(&q, 0, sizeof(q));
   if (!tc::make_map2d(x, x_ch, x_ch, pl.np, 32, true, &q.tmX) || !tc::make_map2d(dz, 32, 32, pl.np, 32, true, &q.tmD))
@@ -793,7 +1071,11 @@ extern "C" int ssac_conv_encoder_forward(const float* obs_dev, int B, int C, int
   SSAC_REQUIRE(obs_dev && params && ws_dev && out_dev, "conv encoder: null pointer");
   cudaStream_t s = (cudaStream_t)stream;
   float* ws = ws_dev;
-  cv::s2d_norm_kernel<<<B * pl.gh, 256, (size_t)pl.gw * 4 * C * sizeof(float), s>>>(obs_dev, ws + pl.x0, C, H, W);
+  {
+    int rp = std::max(1, std::min(pl.gh, (int)(40960 / ((size_t)pl.gw * 4 * C * sizeof(float)))));   // <= 40 KB of smem
+    while (pl.gh % rp) --rp;
+    cv::s2d_norm_kernel<<<B * (pl.gh / rp), 512, (size_t)rp * pl.gw * 4 * C * sizeof(float), s>>>(obs_dev, ws + pl.x0, C, H, W, rp);
+  }
   SSAC_CHECK_LAUNCH("s2d_norm_kernel");
   cv::conv_pack_kernel<<<(8 * 2048 + 255) / 256, 256, 0, s>>>(params[0], ws + pl.pack_f[1], 2, C, 8);
   SSAC_CHECK_LAUNCH("conv_pack_kernel");
