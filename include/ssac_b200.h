@@ -379,19 +379,21 @@ int ssac_peer_wait(const void* my_buf_dev, int64_t half_bytes, int64_t nbytes, c
  * ws_dev: caller-owned workspace of ssac_conv_encoder_ws_floats floats, ZERO-INITIALISED once by the caller (padding
  * channels / pixels are never written); it carries the activations from a forward with save = 1 to its backward.
  * save = 0: no backward will follow (target encoder, acting path): activations ping-pong between two buffers.
- * out_dev f32 [B,out_dim].  backward: dout_dev = dL/dout, out_dev = the forward's output; every gradient is WRITTEN
+ * out_dev f32 [B,out_dim].  backward: dout_dev = dL/dout, out_dev = the forward's output, obs_dev = the forward's input (the
+ * first layer's weight gradient re-reads the image patches instead of keeping an im2col copy); every gradient is WRITTEN
  * (not accumulated).  ssac_conv_encoder_ws_offsets (tests / tools): int64[24] = float offsets of {x0, y1..y4, d0, d1, wfc,
  * gwfc, fc partials, xhat, rstd, dfc, dl} followed by {pixels per image, pitch, pixels, kf, kf padded, split size, splits,
  * total}. */
 /* debugging switch (results do not depend on it): bit 0 = halo tiles (one TMA box per tile instead of one per filter tap) in
- * the forward / data-gradient kernel, bit 1 = in the weight-gradient kernel; default 3 */
+ * the forward / data-gradient kernel, bit 1 = in the weight-gradient kernel, bit 2 = first layer built straight from the
+ * observation (else through a space-to-depth copy); default 7.  Set before the first workspace is planned. */
 int ssac_set_conv_halo(int mode);
 int ssac_conv_encoder_ws_floats(int B, int C, int H, int W, int out_dim, int save, int64_t* n_floats_out);
 int ssac_conv_encoder_ws_offsets(int B, int C, int H, int W, int out_dim, int save, int64_t* offsets_out);
 int ssac_conv_encoder_forward(const float* obs_dev, int B, int C, int H, int W, int out_dim, const float* const* params,
                               float* ws_dev, int save, float* out_dev, void* stream);
-int ssac_conv_encoder_backward(const float* dout_dev, const float* out_dev, int B, int C, int H, int W, int out_dim,
-                               const float* const* params, float* ws_dev, float* const* grads, void* stream);
+int ssac_conv_encoder_backward(const float* dout_dev, const float* out_dev, const float* obs_dev, int B, int C, int H, int W,
+                               int out_dim, const float* const* params, float* ws_dev, float* const* grads, void* stream);
 
 /* ---- host-side helpers of the graph-replayed path (graphed.py) ---------------------------------------------------- */
 /* Raw runtime calls behind one C call each (handles: cudaEvent_t / cudaStream_t / cudaGraphExec_t as void*): what a

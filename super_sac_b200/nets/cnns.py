@@ -56,7 +56,7 @@ class _EncoderFn(torch.autograd.Function):
         lib.conv_encoder_forward(obs.data_ptr(), B, C, H, W, O, pp, ws.data_ptr(), save, out.data_ptr(), _lib.stream_ptr())
         if save:
             ctx.module, ctx.key, ctx.ws, ctx.dims = module, key, ws, (B, C, H, W, O)
-            ctx.save_for_backward(out, *params)
+            ctx.save_for_backward(out, obs, *params)
         else:
             module._ws.give(key, ws)
         return out
@@ -66,13 +66,13 @@ class _EncoderFn(torch.autograd.Function):
         from .. import _lib
 
         lib = _lib.lib()
-        out, *params = ctx.saved_tensors
+        out, obs, *params = ctx.saved_tensors
         B, C, H, W, O = ctx.dims
         dout = dout.contiguous()
         grads = [torch.empty_like(p) for p in params]
         pp = _lib.host_array(ctypes.c_void_p, [p.data_ptr() for p in params])
         gp = _lib.host_array(ctypes.c_void_p, [g.data_ptr() for g in grads])
-        lib.conv_encoder_backward(dout.data_ptr(), out.data_ptr(), B, C, H, W, O, pp, ctx.ws.data_ptr(), gp, _lib.stream_ptr())
+        lib.conv_encoder_backward(dout.data_ptr(), out.data_ptr(), obs.data_ptr(), B, C, H, W, O, pp, ctx.ws.data_ptr(), gp, _lib.stream_ptr())
         ctx.module._ws.give(ctx.key, ctx.ws)
         ctx.ws = None
         return (None, None, *grads)

@@ -44,7 +44,7 @@ def test_workspace_plan_cpu():
     pp, gw, npx, kf, kfp, ks, nsplit, total = [off[i] for i in range(14, 22)]
     assert (pp, gw, npx) == (42 * 42, 42, 512 * 42 * 42)
     assert kf == 42 * 42 * 32 and kfp == ks * nsplit >= kf and ks % 32 == 0
-    assert total == n.value and all(off[i] % 256 == 0 for i in range(14))
+    assert total == n.value and all(off[i] % 256 == 0 or off[i] == -1 for i in range(14))
     with pytest.raises(_lib.SsacError):
         lib.conv_encoder_ws_floats(4, 17, 84, 84, 50, 1, ctypes.byref(n))   # 4C must fit 64 channels
     with pytest.raises(_lib.SsacError):
@@ -85,7 +85,7 @@ class _Native:
     def backward(self, dout):
         B, C, H, W, O = self.dims
         d = torch.as_tensor(np.asarray(dout)).float().cuda().contiguous()
-        self.lib.conv_encoder_backward(d.data_ptr(), self.out.data_ptr(), B, C, H, W, O, self._ptrs(self.params),
+        self.lib.conv_encoder_backward(d.data_ptr(), self.out.data_ptr(), self.obs.data_ptr(), B, C, H, W, O, self._ptrs(self.params),
                                        self.ws.data_ptr(), self._ptrs(self.grads), self._lib.stream_ptr())
         torch.cuda.synchronize()
         return {n: g.cpu().numpy() for n, g in zip(eo.PARAM_NAMES, self.grads)}
