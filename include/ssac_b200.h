@@ -386,7 +386,7 @@ int ssac_peer_wait(const void* my_buf_dev, int64_t half_bytes, int64_t nbytes, c
  * total}. */
 /* debugging switch (results do not depend on it): bit 0 = halo tiles (one TMA box per tile instead of one per filter tap) in
  * the forward / data-gradient kernel, bit 1 = in the weight-gradient kernel, bit 2 = first layer built straight from the
- * observation (else through a space-to-depth copy); default 7.  Set before the first workspace is planned. */
+ * observation (measured slower than the default space-to-depth copy); default 3.  Set before the first workspace is planned. */
 int ssac_set_conv_halo(int mode);
 int ssac_conv_encoder_ws_floats(int B, int C, int H, int W, int out_dim, int save, int64_t* n_floats_out);
 int ssac_conv_encoder_ws_offsets(int B, int C, int H, int W, int out_dim, int save, int64_t* offsets_out);

@@ -61,7 +61,7 @@ struct ConvP {
   // absolute shared-memory address, so a descriptor whose start address is offset by whole rows inside a 1024-byte
   // aligned tile reads exactly the rows TMA wrote there -- with the descriptor's base-offset field left at 0 (setting it
   // to (start >> 7) & 7 gives wrong results).
-  int hr, halo_base, nhi;
+  int hr, halo_base, nhi, nlo, ncb;   // ncb: 32-channel blocks per input pixel (2 for the space-to-depth first layer)
   int toff[kMaxTB];
   int ksteps[kMaxTB];  // per-tap kernel: 8-deep k-steps of tap-block tb that hold non-zero channels (1..4)
 };
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
         const int s = it % kConvStages, use = it / kConvStages;
         mbar_wait(&bar_full[s], (uint32_t)(use & 1));
         fence_after_sync();
-        if (lane == 0) {
+        if (elect_one()) {
           // descriptors differ only in their 14-bit start-address field (bytes >> 4): one add per MMA instead of a rebuild --
           // with N = 64 / 32 the MMAs are short and the issuing thread's instruction count is what limits the kernel
           const uint64_t dah = dah0 + (uint64_t)(s * (kConvStageBytes >> 4)), dal = dah + (16384u >> 4);
@@ -264,13 +264,14 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   __shared__ uint32_t tmem_base_sh;
   __shared__ float bias_sh[32];
 
-  const uint32_t hrb = (uint32_t)q.hr * 128u;
-  const int nhi = q.nhi;
+  const uint32_t hrb = (uint32_t)q.hr * 128u * (uint32_t)q.ncb;   // one tile: ncb channel blocks of hr rows each
+  const uint32_t cbb = (uint32_t)q.hr * 128u;
+  const int nhi = q.nhi, nlo = q.nlo;
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* wsm = smem;
-  uint8_t* his = smem + kWBytes;
+  uint8_t* his = smem + (size_t)q.ntb * 8192;
   uint8_t* los = his + (size_t)nhi * hrb;
-  uint8_t* osm = los + 2 * (size_t)hrb;
+  uint8_t* osm = los + (size_t)nlo * hrb;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
 
   if (warp == 0) tmem_alloc(&tmem_base_sh, 128);
@@ -310,7 +311,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         const int h = i % nhi, use = i / nhi;
         if (i >= nhi) mbar_wait(&bar_hie[h], (uint32_t)((use - 1) & 1));
         mbar_arrive_expect_tx(&bar_raw[h], hrb);
-        tma_load_2d(smem_u32(his) + (uint32_t)h * hrb, &q.tmIn, &bar_raw[h], 0, q0 + q.halo_base);
+        for (int c = 0; c < q.ncb; ++c)
+          tma_load_2d(smem_u32(his) + (uint32_t)h * hrb + (uint32_t)c * cbb, &q.tmIn, &bar_raw[h], 32 * c, q0 + q.halo_base);
       }
     }
   } else if (warp == 12) {
@@ -318,25 +320,28 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     const uint64_t dah0 = smem_desc(smem_u32(his), 16u, 1024u, 2u), dal0 = smem_desc(smem_u32(los), 16u, 1024u, 2u);
     const uint64_t db0 = smem_desc(smem_u32(wsm), 16u, 1024u, 2u);
     for (int i = 0; i < ntl; ++i) {
-      const int buf = i & 1, h = i % nhi, l = i & 1;
+      const int buf = i & 1, h = i % nhi, l = i % nlo;
       const uint32_t d = tmem_d + (uint32_t)(buf * 64);
       if (i >= 2) {
         mbar_wait(&bar_acce[buf], (uint32_t)(((i >> 1) - 1) & 1));
         fence_after_sync();
       }
-      mbar_wait(&bar_lof[l], (uint32_t)((i >> 1) & 1));     // lo plane written (its writers waited for the raw tile)
+      mbar_wait(&bar_lof[l], (uint32_t)((i / nlo) & 1));     // lo plane written (its writers waited for the raw tile)
       fence_after_sync();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint64_t dh = dah0 + (uint64_t)((uint32_t)h * (hrb >> 4)), dl = dal0 + (uint64_t)((uint32_t)l * (hrb >> 4));
         for (int tb = 0; tb < ntb; ++tb) {
-          const uint64_t ro = (uint64_t)(q.toff[tb] * 8);          // rows of 128 bytes, in 16-byte units
+          const uint64_t ro = (uint64_t)(q.toff[tb] * 8) + (uint64_t)((uint32_t)q.cb[tb] * (cbb >> 4));   // 16-byte units
           const uint64_t dah = dh + ro, dal = dl + ro, db = db0 + (uint64_t)(tb * (8192 >> 4));
           mma_tf32(d, dah, db, idesc64, tb != 0);
           mma_tf32(d, dal, db, idesc32, 1u);
+          const int ks = q.ksteps[tb];
 #pragma unroll
           for (int j = 1; j < 4; ++j) {
-            mma_tf32(d, dah + 2 * j, db + 2 * j, idesc64, 1u);
-            mma_tf32(d, dal + 2 * j, db + 2 * j, idesc32, 1u);
+            if (j < ks) {
+              mma_tf32(d, dah + 2 * j, db + 2 * j, idesc64, 1u);
+              mma_tf32(d, dal + 2 * j, db + 2 * j, idesc32, 1u);
+            }
           }
         }
         mma_commit(&bar_hie[h]);
@@ -347,11 +352,11 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     }
   } else if (warp >= 4) {
     const int tl = t - 128;          // 0..255
-    const int n16 = q.hr * 8;
+    const int n16 = q.hr * 8 * q.ncb;
     for (int i = 0; i < ntl; ++i) {
-      const int h = i % nhi, l = i & 1;
+      const int h = i % nhi, l = i % nlo;
       mbar_wait(&bar_raw[h], (uint32_t)((i / nhi) & 1));
-      if (i >= 2) mbar_wait(&bar_loe[l], (uint32_t)(((i >> 1) - 1) & 1));
+      if (i >= nlo) mbar_wait(&bar_loe[l], (uint32_t)(((i / nlo) - 1) & 1));
       const uint8_t* hi = his + (size_t)h * hrb;
       uint8_t* lo = los + (size_t)l * hrb;
       int k = tl;
@@ -439,7 +444,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_tc_kernel(const __gr
       const int s = i % kNS, use = i / kNS;
       mbar_wait(&bar_full[s], (uint32_t)(use & 1));
       fence_after_sync();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint64_t so = (uint64_t)(s * (kStage >> 4));
         const uint64_t db = db0 + so;                  // B_lo follows at + 4096 = the second 32-column group
 #pragma unroll
@@ -595,7 +600,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_halo_kernel(const __
       const int s = i % kWhStages, use = i / kWhStages;
       mbar_wait(&bar_full[s], (uint32_t)(use & 1));
       fence_after_sync();
-      if (lane == 0) {
+      if (elect_one()) {
         // (descriptor = constant bits + start address >> 4: one add per MMA, see conv_tc_kernel)
         const uint64_t so = (uint64_t)((uint32_t)s * (stage_bytes >> 4));
         const uint64_t db = db0 + so;              // D_lo follows D_hi at + 8192 = the second 32-column group of B
@@ -793,7 +798,7 @@ __global__ void __launch_bounds__(kDirThreads, 1) conv1_direct_kernel(const __gr
         const int s = it % kConvStages, use = it / kConvStages;
         mbar_wait(&bar_full[s], (uint32_t)(use & 1));
         fence_after_sync();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint64_t dah = dah0 + (uint64_t)(s * (kConvStageBytes >> 4)), dal = dah + (16384u >> 4);
           const uint64_t db = db0 + (uint64_t)(kb * (8192 >> 4));
           mma_tf32(d, dah, db, idesc64, kb != 0);
@@ -901,7 +906,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv1_wgrad_direct_kernel(const
       const int s = i % kW1Stages, use = i / kW1Stages;
       mbar_wait(&bar_full[s], (uint32_t)(use & 1));
       fence_after_sync();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint64_t so = (uint64_t)(s * (kW1Stage >> 4));
         const uint64_t dah = da0 + so, dal = dah + (16384u >> 4), db = db0 + so;
         mma_tf32(tmem_d, dah, db, idesc64, i != 0);
@@ -1208,7 +1213,7 @@ __global__ void fc_colred_kernel(const float* __restrict__ dl, const float* __re
 namespace {
 
 // bit 0: halo tiles in the forward / data-gradient kernel, bit 1: in the weight-gradient kernel, bit 2: direct first layer
-int g_conv_halo = 7;
+int g_conv_halo = 3;
 
 struct EncPlan {
   int B, C, H, W, O, save;
@@ -1306,24 +1311,34 @@ int launch_conv(const EncPlan& pl, int layer, bool dgrad, const float* in, int i
   q.wpack = wpack; q.bias = bias; q.yprev = yprev;
   taps_of(layer, pl.gw, dgrad, &q.ntb, q.shift, q.cb);
   for (int t = 0; t < q.ntb; ++t) q.ksteps[t] = (layer == 1 && q.cb[t] == 1) ? std::max(1, (4 * pl.C - 32 + 7) / 8) : 4;
-  const int reach = 2 * pl.gw + 2;                       // largest tap shift
+  const int reach = layer == 1 ? pl.gw + 1 : 2 * pl.gw + 2;   // largest tap shift
   const int hr = (128 + reach + 7) & ~7;
+  const int ncb = in_ch / 32;
   bool halo = false;
-  if ((g_conv_halo & 1) && in_ch == 32 && hr <= 256) {
-    halo = true;
-    q.hr = hr;
-    q.nhi = (cv::kWBytes + 5 * hr * 128 + 16384 + 1024 <= 231424) ? 3 : 2;
+  size_t halo_smem = 0;
+  if ((g_conv_halo & 1) && hr <= 256) {
+    // deepest rings that fit: raw tiles (TMA prefetch depth) first, then a second lo tile
+    const size_t tile = (size_t)ncb * hr * 128, fixed = (size_t)q.ntb * 8192 + 16384 + 1024;
+    for (int nhi = 3; nhi >= 2 && !halo; --nhi)
+      for (int nlo = 2; nlo >= 1 && !halo; --nlo)
+        if (fixed + (nhi + nlo) * tile <= 231424) {
+          halo = true;
+          q.nhi = nhi; q.nlo = nlo;
+          halo_smem = fixed + (nhi + nlo) * tile;
+        }
+  }
+  if (halo) {
+    q.hr = hr; q.ncb = ncb;
     q.halo_base = dgrad ? -reach : 0;
     for (int t = 0; t < q.ntb; ++t) q.toff[t] = dgrad ? reach + q.shift[t] : q.shift[t];   // dgrad shifts are negative
-    if (!tc::make_map2d(in, 32, 32, pl.np, hr, false, &q.tmIn)) return fail(SSAC_E_UNSUPPORTED, "conv encoder: tensor map");
+    if (!tc::make_map2d(in, in_ch, in_ch, pl.np, hr, false, &q.tmIn)) return fail(SSAC_E_UNSUPPORTED, "conv encoder: tensor map");
   }
   q.ntiles = (int)((pl.np + 127) / 128);
   q.mode = dgrad ? 1 : 0;
   q.np = pl.np; q.pp = pl.pp; q.pw = pl.gw; q.vh = vh; q.vw = vw;
   const int grid = std::min(q.ntiles, kNumSMs);
   if (halo) {
-    const size_t smem = cv::kWBytes + (size_t)(q.nhi + 2) * hr * 128 + 16384 + 1024;
-    cv::conv_halo_kernel<<<grid, cv::kHaloThreads, smem, s>>>(q);
+    cv::conv_halo_kernel<<<grid, cv::kHaloThreads, halo_smem, s>>>(q);
     SSAC_CHECK_LAUNCH("conv_halo_kernel");
     return 0;
   }

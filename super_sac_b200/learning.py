@@ -12,7 +12,7 @@ import random
 
 import torch
 
-from . import _arena, _lib, _logs, _ops, _rng, graphed, parallel
+from . import _arena, _encoder_opt, _lib, _logs, _ops, _rng, graphed, parallel
 from . import learning_utils as lu
 
 
@@ -312,10 +312,14 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
         torch.autograd.backward([s for s, _ in enc_outs], [g for _, g in enc_outs])
     if critic_clip:
         opt.grad_norm_sq(stream)
-    if encoder_clip and enc_outs:
-        torch.nn.utils.clip_grad_norm_(agent.encoder.parameters(), encoder_clip)
+    enc_net = None
     if enc_outs:
-        encoder_optimizer.step()
+        # a native pixel encoder whose gradients sit in its flat buffer: clip + Adam as two launches (_encoder_opt.py)
+        enc_net = _encoder_opt.fused_step(agent.encoder, encoder_optimizer, encoder_clip)
+        if enc_net is None:
+            if encoder_clip:
+                torch.nn.utils.clip_grad_norm_(agent.encoder.parameters(), encoder_clip)
+            encoder_optimizer.step()
     member = random.choice(range(E))
     side = None if critic_clip else lu.side_stream(dev)   # clipping rescales the gradients that get logged
     if side is not None:
@@ -355,7 +359,11 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
     logs.defer("losses/last_member_critic_td_error", loss_slot + 2 * (E - 1) + 1)
     logs.defer("losses/critic_overall_loss", [loss_slot + 2 * i for i in range(E)])
     logs.defer("gradients/critic_random_grad", gslot, transform=lambda v: v**0.5)
-    if enc_outs:
+    if enc_net is not None:
+        v, eslot = logs.slots(1)
+        _encoder_opt.grad_norm_sq_into(enc_net, v)
+        logs.defer("gradients/encoder_criticloss_grad_norm", eslot, transform=lambda v: v**0.5)
+    elif enc_outs:
         gn = torch.linalg.vector_norm(torch.stack([p.grad.norm() for p in agent.encoder.parameters() if p.grad is not None]))
         logs.put_tensor("gradients/encoder_criticloss_grad_norm", gn)
     else:

@@ -69,7 +69,7 @@ class _EncoderFn(torch.autograd.Function):
         out, obs, *params = ctx.saved_tensors
         B, C, H, W, O = ctx.dims
         dout = dout.contiguous()
-        grads = [torch.empty_like(p) for p in params]
+        grads = ctx.module._grad_targets(params)
         pp = _lib.host_array(ctypes.c_void_p, [p.data_ptr() for p in params])
         gp = _lib.host_array(ctypes.c_void_p, [g.data_ptr() for g in grads])
         lib.conv_encoder_backward(dout.data_ptr(), out.data_ptr(), obs.data_ptr(), B, C, H, W, O, pp, ctx.ws.data_ptr(), gp, _lib.stream_ptr())
@@ -105,8 +105,43 @@ class BigPixelEncoder(nn.Module):
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
+            if k in ("_flat", "_flat_off", "_flat_grad"):
+                continue
             new.__dict__[k] = _Workspace() if k == "_ws" else copy.deepcopy(v, memo)
         return new
+
+    def _flatten(self):
+        """Parameters as views of ONE contiguous buffer (and a twin gradient buffer), so that Adam, gradient clipping and
+        the logged gradient norm are one launch each (_encoder_opt.py) instead of a dozen per tensor.  Lazy: `.to()` /
+        deepcopy / load_state_dict(assign=True) give the parameters fresh storage, noticed here by address."""
+        ps = self._native_params()
+        flat = self.__dict__.get("_flat")
+        if flat is not None and flat.device == ps[0].device and all(
+                p.data_ptr() == flat.data_ptr() + 4 * o for p, o in zip(ps, self._flat_off)):
+            return
+        offs, n = [], 0
+        for p in ps:
+            offs.append(n)
+            n += (p.numel() + 3) & ~3
+        flat = torch.zeros(n, dtype=torch.float32, device=ps[0].device)
+        with torch.no_grad():
+            for p, o in zip(ps, offs):
+                view = flat[o:o + p.numel()].view(p.shape)
+                view.copy_(p)
+                p.data = view
+        self.__dict__["_flat"], self.__dict__["_flat_off"] = flat, offs
+        self.__dict__["_flat_grad"] = torch.zeros_like(flat)
+
+    def _grad_targets(self, params):
+        """Where a backward writes its gradients: the views of the flat gradient buffer when nothing lives there yet (autograd
+        then adopts them as `.grad` without a copy), else fresh tensors that autograd accumulates as usual."""
+        flat = self.__dict__.get("_flat")
+        own = self._native_params()
+        if (flat is None or any(p.grad is not None for p in own)
+                or any(q.data_ptr() != flat.data_ptr() + 4 * o for q, o in zip(params, self._flat_off))):
+            return [torch.empty_like(p) for p in params]
+        g = self._flat_grad
+        return [g[o:o + p.numel()].view(p.shape) for p, o in zip(params, self._flat_off)]
 
     def _native_params(self):
         return (self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias, self.conv3.weight, self.conv3.bias,
@@ -121,6 +156,7 @@ class BigPixelEncoder(nn.Module):
             if not self.native_supported(obs):
                 raise NotImplementedError("BigPixelEncoder on CUDA: <= 16 channels, even sides >= 16, out_dim <= 64")
             x = obs if obs.dtype == torch.float32 else obs.float()
+            self._flatten()
             params = self._native_params()
             if not torch.is_grad_enabled():
                 params = tuple(p.detach() for p in params)

@@ -217,3 +217,61 @@ def test_encoder_baseline_geometry_against_oracle(B):
     _check_layers(nat, cache, g, f"B{B}")
     for n in reversed(eo.PARAM_NAMES):
         _close(grads[n], g[n].numpy(), f"grad {n}")
+
+
+@pytest.mark.gpu
+def test_fused_encoder_optimizer_step_matches_torch():
+    """clip_grad_norm_ + torch.optim.Adam.step() over the encoder's parameters (learning.py:122-131) == ssac_sumsq +
+    ssac_adam_step over its flat gradient buffer (_encoder_opt.fused_step), step after step, and the optimiser's state
+    (what a checkpoint saves) is the one torch would have produced."""
+    from super_sac_b200 import _encoder_opt, nets
+    from super_sac_b200.nets import cnns
+
+    class Enc(nets.Encoder):   # experiments/dmc/train_dmc_from_pixels.py:15-27
+        def __init__(self):
+            super().__init__()
+            self.net = cnns.BigPixelEncoder((3, 20, 20), 10)
+
+        @property
+        def embedding_dim(self):
+            return 10
+
+        def forward(self, obs_dict):
+            return self.net(obs_dict["obs"])
+
+    torch.manual_seed(3)
+    a = Enc().cuda()
+    with torch.no_grad():
+        for p in a.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+    import copy
+
+    b = copy.deepcopy(a)
+    oa = torch.optim.Adam(a.parameters(), lr=1e-3)
+    ob = torch.optim.Adam(b.parameters(), lr=1e-3)
+    for step in range(4):
+        obs = {"obs": torch.randint(0, 256, (6, 3, 20, 20), device="cuda").float()}
+        w = torch.randn(6, 10, device="cuda") * (30.0 if step % 2 else 0.3)    # clipping active on odd steps
+        for enc, opt in ((a, oa), (b, ob)):
+            opt.zero_grad()
+            (enc(obs) * w).sum().backward()
+        assert _encoder_opt.fused_step(a, oa, 5.0) is a.net
+        torch.nn.utils.clip_grad_norm_(b.parameters(), 5.0)
+        ob.step()
+        for (n, pa), pb in zip(a.named_parameters(), b.parameters()):
+            _close(pa.detach().cpu().numpy(), pb.detach().cpu().numpy(), f"step {step} {n}", rtol=2e-6, rel_atol=1e-6)
+            if pa.grad is not None:   # clip_grad_norm_ scales .grad in place: so does the fused step
+                _close(pa.grad.cpu().numpy(), pb.grad.cpu().numpy(), f"step {step} grad {n}", rtol=2e-6, rel_atol=1e-6)
+    sa, sb = oa.state_dict()["state"], ob.state_dict()["state"]
+    for k in sb:
+        if k in sa or len(sb[k]):
+            assert float(sa[k]["step"]) == float(sb[k]["step"]) == 4.0
+            _close(sa[k]["exp_avg"].cpu().numpy(), sb[k]["exp_avg"].cpu().numpy(), f"exp_avg {k}", rtol=2e-6, rel_atol=1e-6)
+            _close(sa[k]["exp_avg_sq"].cpu().numpy(), sb[k]["exp_avg_sq"].cpu().numpy(), f"exp_avg_sq {k}", rtol=2e-6, rel_atol=1e-6)
+    # two backward passes before a step: the second one accumulates (in place, into the flat buffer) like autograd always does
+    oa.zero_grad()
+    (a(obs) * w).sum().backward()
+    g1 = a.net.conv2.weight.grad.clone()
+    (a(obs) * w).sum().backward()
+    _close(a.net.conv2.weight.grad.cpu().numpy(), 2.0 * g1.cpu().numpy(), "accumulated gradient", rtol=1e-6, rel_atol=1e-7)
+    assert _encoder_opt.eligible(a, oa) is a.net
