@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_forward_kernel(const __grid_
     // ===== MMA issuer ============================================================================================
     mbar_wait(&bar_l1in, 0);
     fence_after_sync();
-    if (lane == 0) {
+    if (elect_one()) {
       // layer 1: x planes in the A region of stage 0, W1 hi / lo in the A regions of stages 1 / 2 (32 KB each)
       const uint32_t a_hi = sbase, a_lo = sbase + kPlane, b_hi = sbase + kStage, b_lo = sbase + 2 * kStage;
       const uint32_t idesc = instr_desc(H, 0, 0);
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_forward_kernel(const __grid_
       const int s = qi % kNumStages;
       mbar_wait(&bar_full[s], (uint32_t)((qi / kNumStages) & 1));
       fence_after_sync();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t st = sbase + (uint32_t)(s * kStage);
         const uint32_t a_hi = st, a_lo = st + kPlane, b_hi = st + 2 * kPlane, b_lo = st + 3 * kPlane;
 #pragma unroll

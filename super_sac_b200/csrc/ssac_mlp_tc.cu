@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(kThreads, 1) grouped_gemm_tc_kernel(const __gr
       const int s = kc % kStages, use = kc / kStages, k0 = kc * TK;
       mbar_wait(&bar_full[s], (uint32_t)(use & 1));
       fence_after_sync();
-      if (lane == 0) {
+      if (elect_one()) {   // (one lane of the converged warp: no per-instruction uniformisation loops around the MMAs)
         const uint32_t st = smem_u32(smem) + (uint32_t)(s * kStageBytes);
         const uint32_t a_hi = st, a_lo = st + kPlaneBytes, b_hi = st + 2 * kPlaneBytes, b_lo = st + 3 * kPlaneBytes;
         // K-major (SWIZZLE_128B)        : a k-step of 8 = 32 bytes further along the swizzled 128-byte rows,
