@@ -376,6 +376,11 @@ def run_secondary(args, sampler):
         out[name] = ent
     try:
         with sampler.region():
+            out["pixel_encoder"] = time_pixel_encoder()
+    except Exception as e:  # noqa: BLE001
+        out["pixel_encoder"] = {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
+    try:
+        with sampler.region():
             out["hbm_kernels"] = hbm_kernels()
     except Exception as e:  # noqa: BLE001
         out["hbm_kernels"] = {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
@@ -459,6 +464,37 @@ def time_nstep_ring_sampling(W, n_frames=12_000):
             "bytes_per_transition": nb.bytes_per_transition(), "classic_ring_bytes_per_transition": classic,
             "host_push_us_incl_frame_generation": push_us, "ring_frames": n_frames,
             "note": "one-step ring, every frame stored once; n-step return, next-state stack and done flag assembled by the sampler"}
+
+
+def time_pixel_encoder(B=512, iters=10):
+    """The native DrQ encoder (csrc/ssac_conv.cu behind nets.cnns.BigPixelEncoder) alone at the C4 geometry: tensor-core
+    bound implicit GEMMs in 3xTF32.  Algorithmic FLOPs = the reference module's own (88.5 MFLOP per sample forward, SURVEY 8d;
+    backward = 2x), not the pitch-layout work the kernels actually do."""
+    import super_sac_b200 as ssb
+
+    dev = torch.device("cuda", torch.cuda.current_device())
+    torch.manual_seed(0)
+    enc = ssb.nets.cnns.BigPixelEncoder((9, 84, 84), 50).to(dev)
+    obs = torch.randint(0, 256, (B, 9, 84, 84), device=dev).float()     # 130 MB: larger than L2 together with the activations
+    dout = torch.randn(B, 50, device=dev)
+    flop = 2 * (41 * 41 * 32 * 81 + (39 * 39 + 37 * 37 + 35 * 35) * 32 * 288 + 39200 * 50) * B
+
+    def fwd():
+        with torch.no_grad():
+            enc(obs)
+
+    def fwd_bwd():
+        enc.zero_grad(set_to_none=True)
+        enc(obs).backward(dout)
+
+    out = {"workload": f"BigPixelEncoder(9x84x84 -> 50), B={B}, fp32 via 3xTF32 tcgen05 implicit GEMMs"}
+    peak = bl.measured_peaks()["bf16_tflops"]
+    for name, fn, mult in (("forward", fwd, 1), ("forward_backward", fwd_bwd, 3)):
+        ms = bl.timed_events(lambda k: fn(), iters, warmup=3)    # per call
+        tf = mult * flop / (ms * 1e-3) / 1e12
+        out[name] = {"us": ms * 1e3, "algorithmic_TFLOPs": tf, "frac_of_bf16_peak": tf / peak,
+                     "frac_of_3xTF32_ceiling": tf / (peak / 6)}
+    return out
 
 
 def hbm_kernels():

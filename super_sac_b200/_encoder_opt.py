@@ -79,13 +79,25 @@ def eligible(encoder, optimizer):
         return None
     g0 = net._flat_grad.data_ptr()
     own = {id(p): o for p, o in zip(net._native_params(), net._flat_off)}
+    adopt = []
     for p in pg["params"]:
         o = own.get(id(p))
         if o is None:
             if p.grad is not None:
                 return None
-        elif p.grad is None or p.grad.data_ptr() != g0 + 4 * o or p.data_ptr() != flat.data_ptr() + 4 * o:
+        elif p.grad is None or p.data_ptr() != flat.data_ptr() + 4 * o:
             return None
+        elif p.grad.data_ptr() != g0 + 4 * o:
+            adopt.append((p, o))
+    # autograd normally adopts the views the backward wrote as `.grad`; where it chose to copy instead (it may, e.g. when
+    # something else still references the gradient), move the copy into the flat buffer and alias it
+    for p, o in adopt:
+        if p.grad.dtype != torch.float32 or not p.grad.is_contiguous():
+            return None
+        view = net._flat_grad[o:o + p.numel()].view(p.shape)
+        with torch.no_grad():
+            view.copy_(p.grad)
+        p.grad = view
     return net
 
 
