@@ -566,14 +566,40 @@ def time_sharded(cfg, args, device, rank, world, dist):
             return out
 
         mode = "cuda-graph replay (exchange captured)"
-        try:
-            g = graphed.GraphedCall(upd)
-            step = g.replay
-        except Exception as e:  # noqa: BLE001  (capture of the exchange is driver / NCCL dependent)
-            mode = "eager launches (graph capture of the exchange unavailable: %s)" % type(e).__name__
-            step = upd
-        steps = min(args.steps, 1000)
-        for _ in range(10):
+        per_call = 1
+        utd = cfg.get("utd", 1)
+        step = None
+        if not members and utd > 1 and utd % cfg["target_delay"] == 0 and not args.no_pipeline:
+            # like the headline: the UTD block as ONE graph, software pipelined -- the target side of update k+1 INCLUDING
+            # its exchange over NVLink runs next to update k's backward (learning.py, lu.pipelined_updates)
+            from super_sac_b200 import learning_utils as lu
+
+            def utd_block():
+                with lu.pipelined_updates():
+                    for u in range(utd):
+                        out = W.step(u)
+                return out
+
+            try:
+                W.critic_update()          # creates the exchange sites outside the capture
+                torch.cuda.synchronize()
+                dist.barrier()
+                step = graphed.GraphedCall(utd_block, warmup=1).replay
+                per_call = utd
+                mode = "cuda-graph replay of the UTD block (%d updates per graph; exchange captured, on the target side's stream)" % utd
+            except Exception as e:  # noqa: BLE001
+                torch.cuda.synchronize()
+                print("[bench] sharded UTD block not capturable: %s: %s" % (type(e).__name__, str(e)[:300]), file=sys.stderr, flush=True)
+                step = None
+        if step is None:
+            try:
+                g = graphed.GraphedCall(upd)
+                step = g.replay
+            except Exception as e:  # noqa: BLE001  (capture of the exchange is driver / NCCL dependent)
+                mode = "eager launches (graph capture of the exchange unavailable: %s)" % type(e).__name__
+                step = upd
+        steps = max(1, min(args.steps, 1000) // per_call)
+        for _ in range(max(2, 10 // per_call)):
             step()
         torch.cuda.synchronize()
         dist.barrier()
@@ -588,6 +614,7 @@ def time_sharded(cfg, args, device, rank, world, dist):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
         n_units = cfg["E"] if members else cfg["N"]
+        steps *= per_call
         return {"value": steps / (ms * 1e-3), "unit": "updates/s of ONE learner", "ms_per_step": ms / steps, "mode": mode,
                 "partitioned": "members" if members else "critics", "exchange": parallel.exchange_name(),
                 "per_rank": [parallel.local_range(n_units, world, r)[1] - parallel.local_range(n_units, world, r)[0] for r in range(world)],

@@ -61,7 +61,13 @@ __global__ void __launch_bounds__(1024) peer_wait_kernel(const uint8_t* __restri
   pdl_trigger();
   const uint32_t e = *epoch;   // the put of this exchange (same stream, earlier) stored it
   if ((int)threadIdx.x < world) {
-    while ((int32_t)(ld_acquire_sys(my_sigs + threadIdx.x) - e) < 0) { __nanosleep(20); }
+    // bounded (tens of seconds): a peer that never arrives -- a crashed rank, a schedule that deadlocks -- traps this kernel
+    // instead of hanging the GPU
+    uint32_t spins = 0;
+    while ((int32_t)(ld_acquire_sys(my_sigs + threadIdx.x) - e) < 0) {
+      __nanosleep(100);
+      if (++spins > 200000000u) __trap();
+    }
   }
   __syncthreads();
   const uint8_t* half = my_buf + (int64_t)(e & 1u) * half_bytes;

@@ -94,9 +94,13 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
     # front stream, which is NOT joined at the end of the update -- the next update's target side starts next to this
     # update's backward / Adam.  One member, plain Bellman weights, uniform sampling, no trainable encoder.
     pipe = lu.pipeline()
+    # Critics sharded over ranks: the exchange of the target values (put + wait, parallel.all_gather_q) belongs to the target
+    # side and moves to the front stream with it -- its round trip over NVLink then runs under the previous update's
+    # backward.  Both halves of an exchange site stay safe: put(k+2) follows wait(k+1) on the front stream, and a peer's
+    # put(k+1) follows ITS wait(k), so nobody still reads the half that put(k+2) overwrites.  (NCCL fallback: serial.)
     if pipe is not None and (E != 1 or per or update_priorities or weight_type is not None or _encoder_trainable(agent) or
-                             parallel.is_sharded() or parallel.members_sharded() or lu.side_stream(dev) is None or
-                             pipe.device != dev):
+                             (parallel.is_sharded() and not parallel.peer_exchange_ready()) or parallel.members_sharded() or
+                             lu.side_stream(dev) is None or pipe.device != dev):
         lu.pipeline_barrier()
         pipe = None
     # (the log buffer is cleared by the first member's draw kernel, i.e. on the front stream when pipelined: it then has to

@@ -88,6 +88,11 @@ def _site(name, nbytes, group, device):
     return site
 
 
+def peer_exchange_ready():
+    """True when the exchanges run over peer memory (kernels on the caller's current stream), not NCCL collectives."""
+    return bool(_peer["sites"]) and _peer["why_not"] is None and not _peer["disabled"]
+
+
 def exchange_name():
     if _peer["sites"] and _peer["why_not"] is None:
         return "NVLink peer stores + signals (ssac_peer_put / ssac_peer_wait over symmetric memory)"

@@ -62,24 +62,27 @@ def build(N, S, A, H, device, seed):
     return agent
 
 
-def run(agent, target, buf, draws, B, M, cfg):
+def run(agent, target, buf, draws, B, M, cfg, pipelined=False):
+    import contextlib
+
     critic_opt, actor_opt, enc_opt, log_alphas, _ = optimizers(agent, cfg)
     aug = augmentations.AugmentationSequence([augmentations.IdentityAug(B)])
     out = {}
     old = _rng.set_source(_rng.ScriptedSource())
     try:
+      with (lu.pipelined_updates() if pipelined else contextlib.nullcontext()):
         for step, dr in enumerate(draws):
-            src = _rng.ScriptedSource()
-            _rng.set_source(src)
-            src.push("indices", dr["idx"]).push("normal", dr["eps"]).push("subsets", dr["subset"])
-            logs, rds = learning.critic_update(
-                buffer=buf, agent=agent, target_agent=target, critic_optimizer=critic_opt, encoder_optimizer=enc_opt,
-                log_alphas=log_alphas, batch_size=B, gamma=0.99, critic_clip=None, encoder_clip=None,
-                target_critic_ensemble_n=M, weighted_bellman_temp=None, weight_type=None, pop=False, augmenter=aug,
-                encoder_lambda=0.0, random_process=None, noise_clip=None, aug_mix=0.0)
-            for ac, tc in zip(agent.critics, target.critics):
-                lu.soft_update(tc, ac, 0.005)
-            out[f"loss{step}"] = logs["losses/critic_overall_loss"]
+              src = _rng.ScriptedSource()
+              _rng.set_source(src)
+              src.push("indices", dr["idx"]).push("normal", dr["eps"]).push("subsets", dr["subset"])
+              logs, rds = learning.critic_update(
+                  buffer=buf, agent=agent, target_agent=target, critic_optimizer=critic_opt, encoder_optimizer=enc_opt,
+                  log_alphas=log_alphas, batch_size=B, gamma=0.99, critic_clip=None, encoder_clip=None,
+                  target_critic_ensemble_n=M, weighted_bellman_temp=None, weight_type=None, pop=False, augmenter=aug,
+                  encoder_lambda=0.0, random_process=None, noise_clip=None, aug_mix=0.0)
+              for ac, tc in zip(agent.critics, target.critics):
+                  lu.soft_update(tc, ac, 0.005)
+              out[f"loss{step}"] = logs["losses/critic_overall_loss"]
         src = _rng.ScriptedSource()
         _rng.set_source(src)
         src.push("normal", draws[-1]["eps2"])
@@ -212,6 +215,20 @@ def critics_check(rank, world, dev):
     shard._actor_arena.flat.copy_(init_a)
     shard_t = copy.deepcopy(shard)
     got = run(shard, shard_t, buffer(), draws, B, M, cfg)
+    # the software-pipelined block (target side + exchange of update k+1 next to update k) must give the same bits
+    if parallel.peer_exchange_ready():
+        pshard = build(hi - lo, S, A, H, dev, seed=7)
+        for n in init_c:
+            pshard._critic_arena.p[n].copy_(init_c[n][lo:hi])
+        pshard._actor_arena.flat.copy_(init_a)
+        pshard_t = copy.deepcopy(pshard)
+        pgot = run(pshard, pshard_t, buffer(), draws, B, M, cfg, pipelined=True)
+        torch.cuda.synchronize()
+        for n in init_c:
+            assert torch.equal(pshard._critic_arena.p[n], shard._critic_arena.p[n]), f"pipelined sharded block: critics {n} differ"
+            assert torch.equal(pshard_t._critic_arena.p[n], shard_t._critic_arena.p[n]), f"pipelined sharded block: targets {n} differ"
+        assert torch.equal(pshard._actor_arena.flat, shard._actor_arena.flat), "pipelined sharded block: actor differs"
+        print(f"[rank {rank}] pipelined sharded block == sequential sharded updates (bit-identical); losses {pgot}", flush=True)
     parallel.disable()
 
     for n in init_c:
