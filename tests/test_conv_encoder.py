@@ -275,3 +275,30 @@ def test_fused_encoder_optimizer_step_matches_torch():
     (a(obs) * w).sum().backward()
     _close(a.net.conv2.weight.grad.cpu().numpy(), 2.0 * g1.cpu().numpy(), "accumulated gradient", rtol=1e-6, rel_atol=1e-7)
     assert _encoder_opt.eligible(a, oa) is a.net
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,C,H,W,O", [(1, 9, 84, 84, 50), (2, 1, 16, 16, 8), (3, 16, 20, 28, 64), (7, 4, 32, 18, 33)])
+def test_encoder_edge_geometries_against_oracle(B, C, H, W, O):
+    """Batch of one (the acting path), one channel, the widest channel count (4C = 64), non-square images, the smallest
+    image (a single valid output pixel in the last layer), an odd output width."""
+    from super_sac_b200.nets import cnns
+
+    rng = np.random.default_rng(B * 1000 + C)
+    torch.manual_seed(B * 1000 + C)
+    enc = cnns.BigPixelEncoder((C, H, W), out_dim=O)
+    with torch.no_grad():
+        for p in enc.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+    params = {k: v.detach().numpy() for k, v in enc.named_parameters()}
+    obs = rng.integers(0, 256, (B, C, H, W)).astype(np.float32)
+    dout = rng.standard_normal((B, O)).astype(np.float32)
+    ref_out, cache = eo.forward(params, obs)
+    nat = _Native(params, B, C, H, W, O)
+    out = nat.forward(obs)
+    masks = _native_masks(nat, cache, f"{B}x{C}x{H}x{W}")
+    g = eo.backward(cache, dout, masks)
+    _close(out, ref_out.numpy(), "out")
+    grads = nat.backward(dout)
+    for n in reversed(eo.PARAM_NAMES):
+        _close(grads[n], g[n].numpy(), f"grad {n}")
