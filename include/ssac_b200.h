@@ -381,9 +381,10 @@ int ssac_peer_wait(const void* my_buf_dev, int64_t half_bytes, int64_t nbytes, c
  * save = 0: no backward will follow (target encoder, acting path): activations ping-pong between two buffers.
  * out_dev f32 [B,out_dim].  backward: dout_dev = dL/dout, out_dev = the forward's output, obs_dev = the forward's input (the
  * first layer's weight gradient re-reads the image patches instead of keeping an im2col copy); every gradient is WRITTEN
- * (not accumulated).  ssac_conv_encoder_ws_offsets (tests / tools): int64[24] = float offsets of {x0, y1..y4, d0, d1, wfc,
- * gwfc, fc partials, xhat, rstd, dfc, dl} followed by {pixels per image, pitch, pixels, kf, kf padded, split size, splits,
- * total}. */
+ * (not accumulated).  ssac_conv_encoder_ws_offsets (tests / tools): int64[32] = float offsets of {x0, y1..y4, dz1..dz4, wfc,
+ * gwfc, fc partials, xhat, rstd, dfc, dl} followed by {rows R1..R4, pitches P1..P4 of the four layers' grids, kf, kf padded,
+ * split size, splits, total}.  Layer l works on its INPUT grid R_l x P_l per image: y_l (l = 1..3) is stored compacted on
+ * layer l+1's grid, y4 on layer 4's own grid (valid region R4-2 x P4-2), dz_l on layer l's grid. */
 /* debugging switch (results do not depend on it): bit 0 = halo tiles (one TMA box per tile instead of one per filter tap) in
  * the forward / data-gradient kernel, bit 1 = in the weight-gradient kernel, bit 2 = first layer built straight from the
  * observation (measured slower than the default space-to-depth copy); default 3.  Set before the first workspace is planned. */

@@ -54,7 +54,12 @@ struct ConvP {
   int shift[kMaxTB], cb[kMaxTB];
   int ntiles, mode;
   int64_t np;
-  int pp, pw, vh, vw;  // mode 1: pixels per image, pitch, valid rows / cols of yprev
+  int pp, pw;          // this layer's grid: pixels per image, pitch
+  // the epilogue scatters grid position (y, x) of image b -- if y < out_vh and x < out_vw -- to row
+  // (b*dst_pp + y*dst_pw + x) of `out`: forward layers 1-3 compact their valid outputs onto the next layer's (smaller) grid,
+  // a data gradient lands on the previous layer's (larger) grid, whose border stays zero
+  float* out;
+  int out_vh, out_vw, dst_pp, dst_pw;
   // halo kernel (32-channel layers): ONE box of hr rows per tile -- pixels base .. base + hr - 1, base = q0 + halo_base --
   // and tap t reads it at row offset toff[t] through the start address of its UMMA descriptor, so every input pixel
   // crosses shared memory once instead of nine times.  MEASURED on B200: the 128-byte swizzle is a function of the
@@ -66,31 +71,27 @@ struct ConvP {
   int ksteps[kMaxTB];  // per-tap kernel: 8-deep k-steps of tap-block tb that hold non-zero channels (1..4)
 };
 
-// Epilogue warps 0-3 (thread = pixel = TMEM lane) of both convolution kernels: accumulator halves added, bias + ReLU
-// (forward) or ReLU / valid-region mask (data gradient), tile staged in the SWIZZLE_128B image of a [32 x 128] box and
-// stored by TMA (clipped at the end of the tensor).
+// Epilogue warps 0-3 (thread = pixel = TMEM lane) of the convolution kernels: accumulator halves added, bias + ReLU
+// (forward) or ReLU mask (data gradient), and the pixel's 128 bytes stored at its place on the destination grid.
 __device__ __forceinline__ void conv_epilogue(const ConvP& q, uint32_t tmem_d, uint64_t* bar_accf, uint64_t* bar_acce,
-                                              uint8_t* osm, const float* bias_sh, int ntl) {
+                                              uint8_t* /*osm*/, const float* bias_sh, int ntl) {
   const int t = threadIdx.x, warp = t >> 5, row = t;
-  const uint32_t r7 = (uint32_t)(row & 7);
-  uint8_t* orow = osm + (uint32_t)(row >> 3) * 1024u + r7 * 128u;
   for (int i = 0; i < ntl; ++i) {
     const int buf = i & 1;
     const int tile = (int)blockIdx.x + i * (int)gridDim.x;
     const int64_t pix = (int64_t)tile * 128 + row;
+    bool wr = pix < q.np;
+    float4* dst = nullptr;
+    if (wr) {
+      const int b = (int)(pix / q.pp), r = (int)(pix - (int64_t)b * q.pp), y = r / q.pw, x = r - y * q.pw;
+      wr = y < q.out_vh && x < q.out_vw;
+      dst = reinterpret_cast<float4*>(q.out + ((int64_t)b * q.dst_pp + (int64_t)y * q.dst_pw + x) * 32);
+    }
     float4 mk[8];
-    bool valid = true;
-    if (q.mode == 1) {
-      valid = pix < q.np;
-      if (valid) {
-        const int r = (int)(pix % q.pp);
-        valid = (r / q.pw) < q.vh && (r % q.pw) < q.vw;
-      }
-      if (valid) {
-        const float4* yp = reinterpret_cast<const float4*>(q.yprev + pix * 32);
+    if (q.mode == 1 && wr) {
+      const float4* yp = reinterpret_cast<const float4*>(q.yprev + pix * 32);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) mk[c] = __ldg(yp + c);
-      }
+      for (int c = 0; c < 8; ++c) mk[c] = __ldg(yp + c);
     }
     mbar_wait(&bar_accf[buf], (uint32_t)((i >> 1) & 1));
     fence_after_sync();
@@ -101,8 +102,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvP& q, uint32_t tmem_d, u
     tmem_wait_ld();
     fence_before_sync();
     mbar_arrive(&bar_acce[buf]);
-    if (t == 0) tma_store_wait_read();                 // the previous tile's store has read the staging tile
-    asm volatile("bar.sync 2, 128;" ::: "memory");
+    if (!wr) continue;
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       float4 o;
@@ -114,23 +114,12 @@ __device__ __forceinline__ void conv_epilogue(const ConvP& q, uint32_t tmem_d, u
         o.x = fmaxf(o.x + bias_sh[4 * c + 0], 0.f); o.y = fmaxf(o.y + bias_sh[4 * c + 1], 0.f);
         o.z = fmaxf(o.z + bias_sh[4 * c + 2], 0.f); o.w = fmaxf(o.w + bias_sh[4 * c + 3], 0.f);
       } else {
-        if (valid) {
-          o.x = mk[c].x > 0.f ? o.x : 0.f; o.y = mk[c].y > 0.f ? o.y : 0.f;
-          o.z = mk[c].z > 0.f ? o.z : 0.f; o.w = mk[c].w > 0.f ? o.w : 0.f;
-        } else {
-          o = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        o.x = mk[c].x > 0.f ? o.x : 0.f; o.y = mk[c].y > 0.f ? o.y : 0.f;
+        o.z = mk[c].z > 0.f ? o.z : 0.f; o.w = mk[c].w > 0.f ? o.w : 0.f;
       }
-      *reinterpret_cast<float4*>(orow + (((uint32_t)c ^ r7) << 4)) = o;
-    }
-    fence_async_smem();
-    asm volatile("bar.sync 2, 128;" ::: "memory");
-    if (t == 0) {
-      tma_store_2d(&q.tmOut, smem_u32(osm), 0, tile * 128);
-      tma_store_commit();
+      dst[c] = o;
     }
   }
-  if (t == 0) tma_store_wait_all();
 }
 
 // ---- per-tap kernel: the 64-channel first layer (and any geometry whose halo does not fit) --------------------------
@@ -1236,12 +1225,15 @@ int g_conv_halo = 3;
 
 struct EncPlan {
   int B, C, H, W, O, save;
-  int gh, gw, pp;
-  int64_t np;
+  int gh, gw;
+  // Layer l works on ITS INPUT grid R[l] x P[l] per image (rows x pitch): the space-to-depth grid gh x gw for layer 1, the
+  // previous layer's valid outputs for layers 2-4 (its epilogue compacts them).  vh / vw[l] = valid outputs of layer l.
+  int R[5], P[5];
+  int64_t npl[5];
   int vh[5], vw[5];
   int64_t kf, kfp;
   int ks, nsplit, direct;
-  int64_t x0, y[5], d[2], wfc, gwfc, part_fc, xhat, rstd, dfc, dl, pack_f[5], pack_d[5], wpart, bpart, total;
+  int64_t x0, y[5], d[5], wfc, gwfc, part_fc, xhat, rstd, dfc, dl, pack_f[5], pack_d[5], wpart, bpart, total;
 };
 
 inline int64_t up256(int64_t v) { return (v + 255) & ~(int64_t)255; }
@@ -1251,12 +1243,17 @@ int make_plan(int B, int C, int H, int W, int O, int save, EncPlan* p) {
   SSAC_REQUIRE(H >= 16 && W >= 16 && (H % 2) == 0 && (W % 2) == 0, "conv encoder: even image sides >= 16");
   SSAC_REQUIRE(O > 0 && O <= 64, "conv encoder: 1 <= out_dim <= 64");
   p->B = B; p->C = C; p->H = H; p->W = W; p->O = O; p->save = save;
-  p->gh = H / 2; p->gw = W / 2; p->pp = p->gh * p->gw;
-  p->np = (int64_t)B * p->pp;
-  SSAC_REQUIRE(p->np + 4 * p->gw < (int64_t)1 << 30, "conv encoder: too many pixels for 32-bit TMA coordinates");
+  p->gh = H / 2; p->gw = W / 2;
   for (int l = 1; l <= 4; ++l) { p->vh[l] = p->gh - 1 - 2 * (l - 1); p->vw[l] = p->gw - 1 - 2 * (l - 1); }
   SSAC_REQUIRE(p->vh[4] > 0 && p->vw[4] > 0, "conv encoder: image too small");
-  p->kf = (int64_t)p->pp * 32;
+  for (int l = 1; l <= 4; ++l) {
+    p->R[l] = l == 1 ? p->gh : p->vh[l - 1];
+    p->P[l] = l == 1 ? p->gw : p->vw[l - 1];
+    p->npl[l] = (int64_t)B * p->R[l] * p->P[l];
+  }
+  SSAC_REQUIRE(p->npl[1] + 4 * p->gw < (int64_t)1 << 30, "conv encoder: too many pixels for 32-bit TMA coordinates");
+  // the FC layer reads layer 4's output on layer 4's own grid (its invalid border meets zero weights)
+  p->kf = (int64_t)p->R[4] * p->P[4] * 32;
   const int64_t k32 = p->kf / 32;
   p->ks = (int)(32 * ((k32 + 63) / 64));
   p->nsplit = (int)((p->kf + p->ks - 1) / p->ks);
@@ -1265,15 +1262,18 @@ int make_plan(int B, int C, int H, int W, int O, int save, EncPlan* p) {
   int64_t o = 0;
   auto take = [&](int64_t n) { const int64_t at = o; o += up256(n); return at; };
   p->direct = (g_conv_halo & 4) && 9 * C <= 128;     // first layer straight from the NCHW observation: no s2d image
-  p->x0 = p->direct ? -1 : take(p->np * 64 + pad);
-  const int64_t ybytes = p->np * 32 + pad;
+  p->x0 = p->direct ? -1 : take(p->npl[1] * 64 + pad);
+  // y[l]: output of layer l -- compacted onto layer l+1's grid (l = 1..3), on layer 4's own grid for l = 4
+  const int64_t ysz[5] = {0, p->npl[2] * 32 + pad, p->npl[3] * 32 + pad, p->npl[4] * 32 + pad, p->npl[4] * 32 + pad};
+  p->d[0] = -1;
   if (save) {
-    for (int l = 1; l <= 4; ++l) p->y[l] = take(ybytes);
-    p->d[0] = take(ybytes); p->d[1] = take(ybytes);
+    for (int l = 1; l <= 4; ++l) p->y[l] = take(ysz[l]);
+    // dZ_l on layer l's grid, one buffer each: the border a data gradient leaves untouched must stay zero
+    for (int l = 1; l <= 4; ++l) p->d[l] = take(p->npl[l] * 32 + pad);
   } else {
-    p->y[1] = p->y[3] = take(ybytes);
-    p->y[2] = p->y[4] = take(ybytes);
-    p->d[0] = p->d[1] = -1;
+    p->y[1] = p->y[3] = take(std::max(ysz[1], ysz[3]));
+    p->y[2] = p->y[4] = take(std::max(ysz[2], ysz[4]));
+    for (int l = 1; l <= 4; ++l) p->d[l] = -1;
   }
   p->wfc = take(64 * p->kfp);
   p->gwfc = save ? take(64 * p->kfp) : -1;
@@ -1322,22 +1322,33 @@ void taps_of(int layer, int gw, bool dgrad, int* ntb, int* shift, int* cb) {
 }
 
 int launch_conv(const EncPlan& pl, int layer, bool dgrad, const float* in, int in_ch, float* out, const float* wpack,
-                const float* bias, const float* yprev, int vh, int vw, cudaStream_t s) {
+                const float* bias, const float* yprev, cudaStream_t s) {
   cv::ConvP q;
   memset(&q, 0, sizeof(q));
-  if (!tc::make_map2d(in, in_ch, in_ch, pl.np, 128, false, &q.tmIn) || !tc::make_map2d(out, 32, 32, pl.np, 128, false, &q.tmOut))
-    return fail(SSAC_E_UNSUPPORTED, "conv encoder: tensor map");
-  q.wpack = wpack; q.bias = bias; q.yprev = yprev;
-  taps_of(layer, pl.gw, dgrad, &q.ntb, q.shift, q.cb);
+  const int R = pl.R[layer], P = pl.P[layer];
+  const int64_t np = pl.npl[layer];
+  if (!tc::make_map2d(in, in_ch, in_ch, np, 128, false, &q.tmIn)) return fail(SSAC_E_UNSUPPORTED, "conv encoder: tensor map");
+  q.wpack = wpack; q.bias = bias; q.yprev = yprev; q.out = out;
+  taps_of(layer, P, dgrad, &q.ntb, q.shift, q.cb);
   for (int t = 0; t < q.ntb; ++t) q.ksteps[t] = (layer == 1 && q.cb[t] == 1) ? std::max(1, (4 * pl.C - 32 + 7) / 8) : 4;
-  const int reach = layer == 1 ? pl.gw + 1 : 2 * pl.gw + 2;   // largest tap shift
+  q.np = np; q.pp = R * P; q.pw = P;
+  if (dgrad) {                   // dL/d(input of layer `layer`) -> dZ of layer - 1, on that layer's grid
+    q.out_vh = R; q.out_vw = P;
+    q.dst_pp = pl.R[layer - 1] * pl.P[layer - 1]; q.dst_pw = pl.P[layer - 1];
+  } else if (layer < 4) {        // valid outputs compacted onto the next layer's grid
+    q.out_vh = pl.vh[layer]; q.out_vw = pl.vw[layer];
+    q.dst_pp = pl.vh[layer] * pl.vw[layer]; q.dst_pw = pl.vw[layer];
+  } else {                       // the FC layer reads layer 4's output in place
+    q.out_vh = R; q.out_vw = P; q.dst_pp = R * P; q.dst_pw = P;
+  }
+  const int reach = layer == 1 ? P + 1 : 2 * P + 2;   // largest tap shift
   const int hr = (128 + reach + 7) & ~7;
   const int ncb = in_ch / 32;
   bool halo = false;
   size_t halo_smem = 0;
   if ((g_conv_halo & 1) && hr <= 256) {
     // deepest rings that fit: raw tiles (TMA prefetch depth) first, then a second lo tile
-    const size_t tile = (size_t)ncb * hr * 128, fixed = (size_t)q.ntb * 8192 + 16384 + 1024;
+    const size_t tile = (size_t)ncb * hr * 128, fixed = (size_t)q.ntb * 8192 + 1024;
     for (int nhi = 3; nhi >= 2 && !halo; --nhi)
       for (int nlo = 2; nlo >= 1 && !halo; --nlo)
         if (fixed + (nhi + nlo) * tile <= 231424) {
@@ -1350,11 +1361,10 @@ int launch_conv(const EncPlan& pl, int layer, bool dgrad, const float* in, int i
     q.hr = hr; q.ncb = ncb;
     q.halo_base = dgrad ? -reach : 0;
     for (int t = 0; t < q.ntb; ++t) q.toff[t] = dgrad ? reach + q.shift[t] : q.shift[t];   // dgrad shifts are negative
-    if (!tc::make_map2d(in, in_ch, in_ch, pl.np, hr, false, &q.tmIn)) return fail(SSAC_E_UNSUPPORTED, "conv encoder: tensor map");
+    if (!tc::make_map2d(in, in_ch, in_ch, np, hr, false, &q.tmIn)) return fail(SSAC_E_UNSUPPORTED, "conv encoder: tensor map");
   }
-  q.ntiles = (int)((pl.np + 127) / 128);
+  q.ntiles = (int)((np + 127) / 128);
   q.mode = dgrad ? 1 : 0;
-  q.np = pl.np; q.pp = pl.pp; q.pw = pl.gw; q.vh = vh; q.vw = vw;
   const int grid = std::min(q.ntiles, kNumSMs);
   if (halo) {
     cv::conv_halo_kernel<<<grid, cv::kHaloThreads, halo_smem, s>>>(q);
@@ -1368,15 +1378,17 @@ int launch_conv(const EncPlan& pl, int layer, bool dgrad, const float* in, int i
 
 int launch_wgrad(const EncPlan& pl, int layer, const float* x, int x_ch, const float* dz, float* ws, float* gW, float* gb,
                  cudaStream_t s) {
-  const int xr = (64 + 2 * pl.gw + 2 + 1 + 7) & ~7;
+  const int P = pl.P[layer];
+  const int64_t np = pl.npl[layer];
+  const int xr = (64 + 2 * P + 2 + 1 + 7) & ~7;
   if ((g_conv_halo & 2) && x_ch == 32 && xr <= 256 && 4 * (2 * xr * 128 + 16384) + 1024 <= 232448) {
     cv::WgradH h;
     memset(&h, 0, sizeof(h));
-    if (!tc::make_map2d(x, 32, 32, pl.np, xr, true, &h.tmX) || !tc::make_map2d(dz, 32, 32, pl.np, 64, true, &h.tmD))
+    if (!tc::make_map2d(x, 32, 32, np, xr, true, &h.tmX) || !tc::make_map2d(dz, 32, 32, np, 64, true, &h.tmD))
       return fail(SSAC_E_UNSUPPORTED, "conv encoder: tensor map");
     h.part = ws + pl.wpart; h.bpart = ws + pl.bpart;
-    h.gw = pl.gw; h.xr = xr;
-    h.nstages = (int)((pl.np + 63) / 64);
+    h.gw = P; h.xr = xr;
+    h.nstages = (int)((np + 63) / 64);
     const int grid = std::min(h.nstages, kNumSMs);
     h.spc = (h.nstages + grid - 1) / grid;
     cv::conv_wgrad_halo_kernel<<<grid, cv::kWgThreads, 4 * (2 * xr * 128 + 16384) + 1024, s>>>(h);
@@ -1387,12 +1399,12 @@ int launch_wgrad(const EncPlan& pl, int layer, const float* x, int x_ch, const f
   }
   cv::WgradP q;
   memset(&q, 0, sizeof(q));
-  if (!tc::make_map2d(x, x_ch, x_ch, pl.np, 32, true, &q.tmX) || !tc::make_map2d(dz, 32, 32, pl.np, 32, true, &q.tmD))
+  if (!tc::make_map2d(x, x_ch, x_ch, np, 32, true, &q.tmX) || !tc::make_map2d(dz, 32, 32, np, 32, true, &q.tmD))
     return fail(SSAC_E_UNSUPPORTED, "conv encoder: tensor map");
-  taps_of(layer, pl.gw, false, &q.ntb, q.shift, q.cb);
+  taps_of(layer, P, false, &q.ntb, q.shift, q.cb);
   q.ng = (q.ntb + 3) / 4;
   q.part = ws + pl.wpart; q.bpart = ws + pl.bpart;
-  q.nstages = (int)((pl.np + 31) / 32);
+  q.nstages = (int)((np + 31) / 32);
   const int grid = std::min(q.nstages, kNumSMs);
   q.spc = (q.nstages + grid - 1) / grid;
   if (q.ng == 3) cv::conv_wgrad_tc_kernel<3><<<grid, cv::kWgThreads, 2 * (6 * 16384 + 8192) + 1024, s>>>(q);
@@ -1407,20 +1419,21 @@ int launch_wgrad(const EncPlan& pl, int layer, const float* x, int x_ch, const f
 
 cv::DirectGeo direct_geo(const EncPlan& pl, const float* obs) {
   cv::DirectGeo g;
-  g.obs = obs; g.C = pl.C; g.H = pl.H; g.W = pl.W; g.gw = pl.gw; g.pp = pl.pp; g.k_real = 9 * pl.C; g.np = pl.np;
+  g.obs = obs; g.C = pl.C; g.H = pl.H; g.W = pl.W; g.gw = pl.gw; g.pp = pl.gh * pl.gw; g.k_real = 9 * pl.C; g.np = pl.npl[1];
   return g;
 }
 
 int launch_conv1_direct(const EncPlan& pl, const float* obs, float* out, const float* wpack, const float* bias, cudaStream_t s) {
   cv::Conv1P q;
   memset(&q, 0, sizeof(q));
-  if (!tc::make_map2d(out, 32, 32, pl.np, 128, false, &q.c.tmOut)) return fail(SSAC_E_UNSUPPORTED, "conv encoder: tensor map");
-  q.c.wpack = wpack; q.c.bias = bias;
+  q.c.wpack = wpack; q.c.bias = bias; q.c.out = out;
+  q.c.pp = pl.gh * pl.gw; q.c.pw = pl.gw;
+  q.c.out_vh = pl.vh[1]; q.c.out_vw = pl.vw[1]; q.c.dst_pp = pl.vh[1] * pl.vw[1]; q.c.dst_pw = pl.vw[1];
   q.c.ntb = (9 * pl.C + 31) / 32;
   for (int kb = 0; kb < q.c.ntb; ++kb) q.c.ksteps[kb] = std::min(4, (9 * pl.C - 32 * kb + 7) / 8);
-  q.c.ntiles = (int)((pl.np + 127) / 128);
+  q.c.ntiles = (int)((pl.npl[1] + 127) / 128);
   q.c.mode = 0;
-  q.c.np = pl.np;
+  q.c.np = pl.npl[1];
   q.g = direct_geo(pl, obs);
   cv::conv1_direct_kernel<<<std::min(q.c.ntiles, kNumSMs), cv::kDirThreads, cv::kDirSmem, s>>>(q);
   SSAC_CHECK_LAUNCH("conv1_direct_kernel");
@@ -1430,10 +1443,10 @@ int launch_conv1_direct(const EncPlan& pl, const float* obs, float* out, const f
 int launch_wgrad1_direct(const EncPlan& pl, const float* obs, const float* dz, float* ws, float* gW, float* gb, cudaStream_t s) {
   cv::Wgrad1P q;
   memset(&q, 0, sizeof(q));
-  if (!tc::make_map2d(dz, 32, 32, pl.np, 32, true, &q.tmD)) return fail(SSAC_E_UNSUPPORTED, "conv encoder: tensor map");
+  if (!tc::make_map2d(dz, 32, 32, pl.npl[1], 32, true, &q.tmD)) return fail(SSAC_E_UNSUPPORTED, "conv encoder: tensor map");
   q.g = direct_geo(pl, obs);
   q.part = ws + pl.wpart; q.bpart = ws + pl.bpart;
-  q.nstages = (int)((pl.np + 31) / 32);
+  q.nstages = (int)((pl.npl[1] + 31) / 32);
   const int grid = std::min(q.nstages, kNumSMs);
   q.spc = (q.nstages + grid - 1) / grid;
   cv::conv1_wgrad_direct_kernel<<<grid, cv::kWgThreads, cv::kW1Stages * cv::kW1Stage + 1024, s>>>(q);
@@ -1471,9 +1484,10 @@ extern "C" int ssac_conv_encoder_ws_floats(int B, int C, int H, int W, int out_d
 extern "C" int ssac_conv_encoder_ws_offsets(int B, int C, int H, int W, int out_dim, int save, int64_t* offsets_out) {
   EncPlan pl;
   if (int rc = make_plan(B, C, H, W, out_dim, save, &pl)) return rc;
-  const int64_t v[24] = {pl.x0, pl.y[1], pl.y[2], pl.y[3], pl.y[4], pl.d[0], pl.d[1], pl.wfc, pl.gwfc, pl.part_fc, pl.xhat,
-                         pl.rstd, pl.dfc, pl.dl, pl.pp, pl.gw, pl.np, pl.kf, pl.kfp, pl.ks, pl.nsplit, pl.total, 0, 0};
-  for (int i = 0; i < 24; ++i) offsets_out[i] = v[i];
+  const int64_t v[32] = {pl.x0, pl.y[1], pl.y[2], pl.y[3], pl.y[4], pl.d[1], pl.d[2], pl.d[3], pl.d[4], pl.wfc, pl.gwfc,
+                         pl.part_fc, pl.xhat, pl.rstd, pl.dfc, pl.dl, pl.R[1], pl.R[2], pl.R[3], pl.R[4], pl.P[1], pl.P[2],
+                         pl.P[3], pl.P[4], pl.kf, pl.kfp, pl.ks, pl.nsplit, pl.total, 0, 0, 0};
+  for (int i = 0; i < 32; ++i) offsets_out[i] = v[i];
   return 0;
 }
 
@@ -1502,16 +1516,16 @@ extern "C" int ssac_conv_encoder_forward(const float* obs_dev, int B, int C, int
   }
   {
     const int64_t n = (int64_t)out_dim * 32 * pl.vh[4] * pl.vw[4];
-    cv::fc_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(params[8], ws + pl.wfc, out_dim, pl.vh[4], pl.vw[4], pl.gw, pl.kfp, 0);
+    cv::fc_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(params[8], ws + pl.wfc, out_dim, pl.vh[4], pl.vw[4], pl.P[4], pl.kfp, 0);
     SSAC_CHECK_LAUNCH("fc_pack_kernel");
   }
   if (pl.direct) {
     if (int rc = launch_conv1_direct(pl, obs_dev, ws + pl.y[1], ws + pl.pack_f[1], params[1], s)) return rc;
   } else {
-    if (int rc = launch_conv(pl, 1, false, ws + pl.x0, 64, ws + pl.y[1], ws + pl.pack_f[1], params[1], nullptr, 0, 0, s)) return rc;
+    if (int rc = launch_conv(pl, 1, false, ws + pl.x0, 64, ws + pl.y[1], ws + pl.pack_f[1], params[1], nullptr, s)) return rc;
   }
   for (int l = 2; l <= 4; ++l)
-    if (int rc = launch_conv(pl, l, false, ws + pl.y[l - 1], 32, ws + pl.y[l], ws + pl.pack_f[l], params[2 * (l - 1) + 1], nullptr, 0, 0, s)) return rc;
+    if (int rc = launch_conv(pl, l, false, ws + pl.y[l - 1], 32, ws + pl.y[l], ws + pl.pack_f[l], params[2 * (l - 1) + 1], nullptr, s)) return rc;
   // FC: split-K as groups of the grouped GEMM
   GemmP g = zero_gemm();
   g.A = ws + pl.y[4]; g.lda = pl.kf; g.a_gs = pl.ks;
@@ -1546,7 +1560,7 @@ extern "C" int ssac_conv_encoder_backward(const float* dout_dev, const float* ou
     g.M = 64; g.N = (int)pl.kf; g.K = B;
     if (int rc = launch_gemm_tc(L_TN, g, 1, s, "conv encoder fc wgrad")) return rc;
     const int64_t n = (int64_t)out_dim * 32 * pl.vh[4] * pl.vw[4];
-    cv::fc_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(grads[8], ws + pl.gwfc, out_dim, pl.vh[4], pl.vw[4], pl.gw, pl.kfp, 1);
+    cv::fc_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(grads[8], ws + pl.gwfc, out_dim, pl.vh[4], pl.vw[4], pl.P[4], pl.kfp, 1);
     SSAC_CHECK_LAUNCH("fc_pack_kernel (unpack)");
   }
   {  // dZ4 = (dfc . W') .* (Y4 > 0)   (W' is zero outside the valid region).  Measured: a CUDA-core kernel with the weight
@@ -1555,20 +1569,17 @@ extern "C" int ssac_conv_encoder_backward(const float* dout_dev, const float* ou
     GemmP g = zero_gemm();
     g.A = ws + pl.dfc; g.lda = 64;
     g.Bm = ws + pl.wfc; g.ldb = pl.kfp;
-    g.C = ws + pl.d[0]; g.ldc = pl.kf;
+    g.C = ws + pl.d[4]; g.ldc = pl.kf;
     g.mask = ws + pl.y[4]; g.ldmask = pl.kf;
     g.M = B; g.N = (int)pl.kf; g.K = 64;
     if (int rc = launch_gemm_tc(L_NN, g, 1, s, "conv encoder fc dgrad")) return rc;
   }
-  int cur = 0;
-  for (int l = 4; l >= 2; --l) {
-    if (int rc = launch_wgrad(pl, l, ws + pl.y[l - 1], 32, ws + pl.d[cur], ws, grads[2 * (l - 1)], grads[2 * (l - 1) + 1], s)) return rc;
+  for (int l = 4; l >= 2; --l) {   // everything layer l touches lives on layer l's grid: y[l-1] (its input), dZ_l
+    if (int rc = launch_wgrad(pl, l, ws + pl.y[l - 1], 32, ws + pl.d[l], ws, grads[2 * (l - 1)], grads[2 * (l - 1) + 1], s)) return rc;
     cv::conv_pack_kernel<<<(9 * 2048 + 255) / 256, 256, 0, s>>>(params[2 * (l - 1)], ws + pl.pack_d[l], 1, C, 9);
     SSAC_CHECK_LAUNCH("conv_pack_kernel");
-    if (int rc = launch_conv(pl, l, true, ws + pl.d[cur], 32, ws + pl.d[cur ^ 1], ws + pl.pack_d[l], nullptr, ws + pl.y[l - 1],
-                             pl.vh[l - 1], pl.vw[l - 1], s)) return rc;
-    cur ^= 1;
+    if (int rc = launch_conv(pl, l, true, ws + pl.d[l], 32, ws + pl.d[l - 1], ws + pl.pack_d[l], nullptr, ws + pl.y[l - 1], s)) return rc;
   }
-  if (pl.direct) return launch_wgrad1_direct(pl, obs_dev, ws + pl.d[cur], ws, grads[0], grads[1], s);
-  return launch_wgrad(pl, 1, ws + pl.x0, 64, ws + pl.d[cur], ws, grads[0], grads[1], s);
+  if (pl.direct) return launch_wgrad1_direct(pl, obs_dev, ws + pl.d[1], ws, grads[0], grads[1], s);
+  return launch_wgrad(pl, 1, ws + pl.x0, 64, ws + pl.d[1], ws, grads[0], grads[1], s);
 }

@@ -39,12 +39,13 @@ def test_workspace_plan_cpu():
     lib = _lib.lib()
     n = ctypes.c_int64()
     lib.conv_encoder_ws_floats(512, 9, 84, 84, 50, 1, ctypes.byref(n))
-    off = (ctypes.c_int64 * 24)()
+    off = (ctypes.c_int64 * 32)()
     lib.conv_encoder_ws_offsets(512, 9, 84, 84, 50, 1, off)
-    pp, gw, npx, kf, kfp, ks, nsplit, total = [off[i] for i in range(14, 22)]
-    assert (pp, gw, npx) == (42 * 42, 42, 512 * 42 * 42)
-    assert kf == 42 * 42 * 32 and kfp == ks * nsplit >= kf and ks % 32 == 0
-    assert total == n.value and all(off[i] % 256 == 0 or off[i] == -1 for i in range(14))
+    rows, pitch = [off[i] for i in range(16, 20)], [off[i] for i in range(20, 24)]
+    kf, kfp, ks, nsplit, total = [off[i] for i in range(24, 29)]
+    assert rows == pitch == [42, 41, 39, 37]      # layer l works on its input grid: s2d 42, then the valid outputs 41 / 39 / 37
+    assert kf == 37 * 37 * 32 and kfp == ks * nsplit >= kf and ks % 32 == 0
+    assert total == n.value and all(off[i] % 256 == 0 or off[i] == -1 for i in range(16))
     with pytest.raises(_lib.SsacError):
         lib.conv_encoder_ws_floats(4, 17, 84, 84, 50, 1, ctypes.byref(n))   # 4C must fit 64 channels
     with pytest.raises(_lib.SsacError):
@@ -64,10 +65,10 @@ class _Native:
         n = ctypes.c_int64()
         self.lib.conv_encoder_ws_floats(B, C, H, W, O, save, ctypes.byref(n))
         self.ws = torch.zeros(n.value, device="cuda")
-        off = (ctypes.c_int64 * 24)()
+        off = (ctypes.c_int64 * 32)()
         self.lib.conv_encoder_ws_offsets(B, C, H, W, O, save, off)
         self.off = list(off)
-        self.pp, self.gw = self.off[14], self.off[15]
+        self.rows, self.pitch = [0] + self.off[16:20], [0] + self.off[20:24]     # grid of layer l = 1..4
         self.out = torch.empty(B, O, device="cuda")
         self.grads = [torch.full_like(p, float("nan")) for p in self.params]
 
@@ -90,14 +91,26 @@ class _Native:
         torch.cuda.synchronize()
         return {n: g.cpu().numpy() for n, g in zip(eo.PARAM_NAMES, self.grads)}
 
-    def act(self, slot, layer):
-        """Valid region of pitch-layout buffer `slot` (ws offset index) as NCHW, for conv layer `layer`'s output size."""
+    def act(self, layer):
+        """Output of conv layer `layer` as NCHW (valid region only): y1..y3 are stored compacted on the next layer's grid,
+        y4 on layer 4's own grid."""
         B = self.dims[0]
-        gh = self.pp // self.gw
-        v_h, v_w = gh - 1 - 2 * (layer - 1), self.gw - 1 - 2 * (layer - 1)
-        o = self.off[slot]
-        x = self.ws[o:o + B * self.pp * 32].view(B, gh, self.gw, 32)
-        return x[:, :v_h, :v_w, :].permute(0, 3, 1, 2).contiguous().cpu().numpy(), x
+        g = min(layer + 1, 4)
+        R, P = self.rows[g], self.pitch[g]
+        o = self.off[layer]
+        x = self.ws[o:o + B * R * P * 32].view(B, R, P, 32)
+        if layer == 4:
+            x = x[:, :R - 2, :P - 2, :]
+        return x.permute(0, 3, 1, 2).contiguous().cpu().numpy()
+
+    def dz(self, layer):
+        """dL/d(pre-activation) of conv layer `layer`: stored on that layer's grid; returns (valid region as NCHW, full view)."""
+        B = self.dims[0]
+        R, P = self.rows[layer], self.pitch[layer]
+        o = self.off[4 + layer]
+        full = self.ws[o:o + B * R * P * 32].view(B, R, P, 32)
+        v_h, v_w = (R - 1, P - 1) if layer == 1 else (R - 2, P - 2)
+        return full[:, :v_h, :v_w, :].permute(0, 3, 1, 2).contiguous().cpu().numpy(), full, (v_h, v_w)
 
 
 def _native_masks(nat, cache, tag):
@@ -105,7 +118,7 @@ def _native_masks(nat, cache, tag):
     rounding of zero -- and that happens for a handful of elements only."""
     masks = {}
     for l in range(1, 5):
-        got, _ = nat.act(l, l)
+        got = nat.act(l)
         want = cache["acts"][l].numpy()
         _close(got, want, f"{tag} y{l}")
         masks[l] = got > 0
@@ -117,12 +130,9 @@ def _native_masks(nat, cache, tag):
 
 
 def _check_layers(nat, cache, g, tag):
-    # d0 / d1 hold dz4, dz3, dz2, dz1 alternately; after the backward dz1 and dz2 are still there: 4 -> d0, 3 -> d1, 2 -> d0, 1 -> d1
-    for l, slot in ((2, 5), (1, 6)):
-        got, full = nat.act(slot, l)
+    for l in (4, 3, 2, 1):
+        got, full, (v_h, v_w) = nat.dz(l)
         _close(got, g[f"dz{l}"].numpy(), f"{tag} dz{l}")
-        gh = nat.pp // nat.gw
-        v_h, v_w = gh - 1 - 2 * (l - 1), nat.gw - 1 - 2 * (l - 1)
         assert float(full[:, v_h:, :, :].abs().max()) == 0.0 and float(full[:, :, v_w:, :].abs().max()) == 0.0, \
             f"{tag} dz{l}: gradient outside the valid region"
 

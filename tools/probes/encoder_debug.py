@@ -32,12 +32,12 @@ for n in eo.PARAM_NAMES:
     w = g[n].numpy().astype(np.float64)
     e = np.abs(grads[n] - w)
     print(f"{n:14s} max|want| {np.abs(w).max():.4e}  max err {e.max():.3e}  rel-to-max {e.max()/np.abs(w).max():.3e}")
-for l, slot in ((2, 5), (1, 6)):
-    got, full = nat.act(slot, l)
+for l in (4, 3, 2, 1):
+    got, full, _ = nat.dz(l)
     w = g[f"dz{l}"].numpy().astype(np.float64)
     e = np.abs(got - w)
     tol = 1e-4 * np.abs(w).max() + 1e-4 * np.abs(w)
     print(f"dz{l}: mismatches {(e > tol).sum()} of {e.size}; max err {e.max():.3e} vs max {np.abs(w).max():.3e}")
     cs = full.reshape(-1, 32).double().sum(0).cpu().numpy()
     name = f"conv{l}.bias"
-    print(f"  colsum(torch over the d buffer) vs kernel {name}: {np.abs(cs - grads[name]).max():.3e}; vs oracle {np.abs(cs - g[name].numpy()).max():.3e}")
+    print(f"  colsum(torch over the dz buffer) vs kernel {name}: {np.abs(cs - grads[name]).max():.3e}; vs oracle {np.abs(cs - g[name].numpy()).max():.3e}")
