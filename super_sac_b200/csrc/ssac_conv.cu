@@ -5,24 +5,29 @@
 //
 // Layout.  Activations are NHWC fp32 with 32 channels = one 128-byte row per pixel, which is exactly one SWIZZLE_128B row
 // of a K-major UMMA operand: a tile of 128 consecutive pixels IS a [128 x 32] A operand and TMA drops it into shared memory
-// ready for tcgen05.mma.  Every layer keeps the SAME pixel grid -- gh x gw = H/2 x W/2 per image (42 x 42 for 84 x 84) --
-// and only the valid region shrinks (41, 39, 37, 35): with one pitch for input and output, tap (kh,kw) of a 3x3
-// convolution is a constant shift of the flat pixel index,  out[q] = sum_taps W_tap . in[q + kh*gw + kw],  so the implicit
-// GEMM needs no im2col at all: tap t of output tile q0 is the TMA box at pixel q0 + shift_t (zero-filled outside the
-// tensor).  Outputs outside the valid region are finite garbage that no valid output ever reads; the backward zeroes them.
+// ready for tcgen05.mma.  Layer l works on ITS INPUT grid R_l x P_l per image -- the space-to-depth grid H/2 x W/2 for layer
+// 1 (42 x 42 for 84 x 84), the previous layer's valid outputs for layers 2-4 (41, 39, 37) -- on which tap (kh,kw) of a 3x3
+// convolution is a constant shift of the flat pixel index,  out[q] = sum_taps W_tap . in[q + kh*P_l + kw],  so the implicit
+// GEMM needs no im2col at all: tap t of output tile q0 is the rows q0 + shift_t .. of the input (zero-filled outside the
+// tensor).  Positions whose window leaves the image are computed and dropped: the epilogue (thread = pixel) stores each
+// valid output at its place on the next layer's grid; a data gradient goes to its place on the previous layer's grid,
+// whose border is never written and stays zero.
 // The stride-2 first layer becomes a stride-1 2x2 convolution over the space-to-depth(2) image (4C channels padded to 64 =
 // two 32-channel k-blocks per tap), so it runs through the same kernel.
 //
 // Arithmetic: 3xTF32 like the MLP GEMMs: x = hi + lo, D = A_hi.[B_hi | B_lo] + A_lo.B_hi with the two B planes
 // concatenated along N (one N = 64 MMA instead of two N = 32 ones; the epilogue adds the halves).
 //
-//   conv_tc_kernel       forward (bias + ReLU) and data gradient (transposed taps, negative shifts, ReLU / valid mask):
-//                        persistent CTAs over 128-pixel tiles, warp 9 = TMA producer (one 16 KB box per tap-block),
-//                        warps 4-7 = lo planes, warp 8 = MMA issuer, warps 0-3 = epilogue out of a double-buffered TMEM
-//                        accumulator (tile i+1's MMAs run under tile i's epilogue) -> swizzled smem -> TMA store.
-//   conv_wgrad_tc_kernel weight gradient: K = pixels; A = 4 tap-blocks of the layer input side by side as the four
-//                        32-column groups of an MN-major M = 128 operand, B = dZ [pixels x 32]; each CTA reduces a
-//                        contiguous pixel range into TMEM and writes one partial; bias gradients ride on the lo pass.
+//   conv_halo_kernel     forward (bias + ReLU) and data gradient (transposed taps, negative shifts, ReLU mask): persistent
+//                        CTAs over 128-pixel tiles, ONE TMA box per tile (the tile plus the pixels its taps reach) read by
+//                        the nine taps through row-offset UMMA descriptors; warps 4-11 = lo planes, warp 12 = MMA issuer
+//                        (elect.sync), warp 13 = TMA, warps 0-3 = epilogue out of a double-buffered TMEM accumulator
+//                        (tile i+1's MMAs run under tile i's epilogue) -> 128-byte row per pixel to its place.
+//                        (conv_tc_kernel: the same with one box per tap, for geometries whose halo does not fit.)
+//   conv_wgrad_halo_kernel  weight gradient: K = pixels; A = the layer input as an MN-major M = 128 operand whose four
+//                        32-column groups are the same rows one pixel apart (taps kw = 0..3), B = dZ [pixels x 32]; each
+//                        CTA reduces a contiguous pixel range into TMEM and writes one partial; bias gradients ride on the
+//                        lo pass.  (conv_wgrad_tc_kernel: one box per tap-block; the 64-channel first layer.)
 //   the FC layer         three launches of the grouped tcgen05 GEMM (split-K forward as groups; dX with the ReLU mask fused;
 //                        dW) over a zero-padded copy of the weight in the pitch layout.
 #include <cuda.h>
