@@ -51,6 +51,11 @@ def _cmp_logs(got, want, what, skip=("gradients/",)):
         gu.assert_close(float(got[k]), float(v), 2e-4, 2e-5, f"{what} log {k}")
 
 
+def _stack_norm(stack):
+    """sqrt(sum g^2) over every array of an oracle gradient stack (learning_utils.py:95-106 get_grad_norm)."""
+    return float(sum(float((getattr(stack, n).double() ** 2).sum()) for n in uo.PARAM_NAMES)) ** 0.5
+
+
 def _cmp_sum_tree(buf, obuf, what, delta_adv=3e-5):
     """PER sum tree after a priority refresh.  Leaves are (relu(A) + 1e-4)^0.6 with A = Q(s,a) - mean Q(s,a'~pi) an fp32
     difference of O(1) values: its absolute error delta_adv (a few 1e-6 per Q value) is amplified by
@@ -122,6 +127,9 @@ def _run_state_steps(E, N, M, S, A, H, B, steps, popart=False, pop=False, weight
             if strict:   # single-step parity: the gradients themselves, then the post-Adam / post-Polyak parameters
                 tw.cmp_stacks(agent._critic_arena, aux["grads"], f"step{t} critic grads", RTOL, 1e-5, grad=True)
                 _cmp_logs(logs, ologs, f"step{t}")
+                if E == 1:   # the logged gradient norm (learning.py:134): with one member the "random" member is member 0
+                    gu.assert_close(float(logs["gradients/critic_random_grad"]), _stack_norm(aux["grads"]), RTOL, 1e-7,
+                                    f"step{t} log gradients/critic_random_grad")
                 tw.cmp_stacks(agent._critic_arena, o_agent.critics, f"step{t} critics", RTOL, 0.0, 3e-4 * 0.05, noise_lr=3e-4)
                 tw.cmp_stacks(target._critic_arena, o_target.critics, f"step{t} target critics", RTOL, 0.0, 3e-4 * 0.05, noise_lr=3e-4)
                 tw.resync(agent, target, o_agent, o_target)
@@ -159,6 +167,9 @@ def _run_state_steps(E, N, M, S, A, H, B, steps, popart=False, pop=False, weight
         assert src.empty()
         oalogs, aaux = uo.online_actor_update(o_agent, abatches, arands, hp, o_las, o_a)
         tw.cmp_stacks(agent._actor_arena, aaux["grads"], "actor grads", RTOL, 1e-5, grad=True)
+        if E == 1:   # learning.py:417-419
+            gu.assert_close(float(alogs["gradients/random_actor_online_grad"]), _stack_norm(aaux["grads"]), RTOL, 1e-7,
+                            "log gradients/random_actor_online_grad")
         tw.cmp_stacks(agent._actor_arena, o_agent.actors, "actors", RTOL, 0.0, 3e-4 * 0.05, noise_lr=3e-4)
         _cmp_logs(alogs, oalogs, "actor")
         # ---- temperature update (no backward through the networks) ------------------------------------------------
