@@ -8,6 +8,8 @@ consume lives in the encoder's flat gradient buffer (``BigPixelEncoder._flatten`
 parameters, accumulated or copied gradients, several parameter groups, amsgrad ...) returns None and the caller runs the
 torch path.
 """
+import os
+
 import torch
 
 from . import _lib
@@ -104,6 +106,8 @@ def eligible(encoder, optimizer):
 def fused_step(encoder, optimizer, max_norm):
     """clip_grad_norm_(encoder.parameters(), max_norm) + optimizer.step() as sumsq + one Adam launch.  Returns the net whose
     flat gradient was consumed (its post-clip norm can then be logged with one more ssac_sumsq), or None if not eligible."""
+    if os.environ.get("SSAC_ENCODER_OPT") == "torch":   # A/B switch for tests: always the torch calls
+        return None
     net = eligible(encoder, optimizer)
     if net is None:
         return None

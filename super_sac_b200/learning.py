@@ -653,10 +653,13 @@ def offline_actor_update(buffer, agent, actor_optimizer, encoder_optimizer, batc
         torch.autograd.backward([s for s, _ in enc_outs], [g for _, g in enc_outs])
     if actor_clip:
         opt.grad_norm_sq(stream)
-    if encoder_clip and enc_outs:
+    enc_net = None
+    if update_encoder and enc_outs:   # (the same fused clip + Adam as in critic_update: one optimiser, one kind of state)
+        enc_net = _encoder_opt.fused_step(agent.encoder, encoder_optimizer, encoder_clip)
+    if enc_net is None and encoder_clip and enc_outs:
         torch.nn.utils.clip_grad_norm_(agent.encoder.parameters(), encoder_clip)
     opt.step(stream, max_norm=actor_clip if actor_clip else None)
-    if update_encoder and enc_outs:
+    if enc_net is None and update_encoder and enc_outs:
         encoder_optimizer.step()
     logs.put_tensor("losses/filtered_bc_overall_loss", total)
     member = random.choice(range(E))

@@ -312,3 +312,73 @@ def test_encoder_edge_geometries_against_oracle(B, C, H, W, O):
     grads = nat.backward(dout)
     for n in reversed(eo.PARAM_NAMES):
         _close(grads[n], g[n].numpy(), f"grad {n}")
+
+
+@pytest.mark.gpu
+def test_update_entry_points_with_native_encoder_fused_vs_torch_optimizer(monkeypatch):
+    """critic_update and offline_actor_update(update_encoder=True) on an agent whose encoder is the native BigPixelEncoder:
+    the fused clip + Adam over the flat buffers gives the parameters the torch calls give (same kernels everywhere else),
+    and one optimiser keeps one kind of state whichever entry point stepped it."""
+    import copy
+    import math
+    from itertools import chain
+
+    import super_sac_b200 as ssb
+    from super_sac_b200 import _rng, augmentations, learning, nets
+    from super_sac_b200.nets import cnns
+
+    class Enc(nets.Encoder):
+        def __init__(self):
+            super().__init__()
+            self.net = cnns.BigPixelEncoder((3, 20, 20), 12)
+
+        @property
+        def embedding_dim(self):
+            return 12
+
+        def forward(self, obs_dict):
+            return self.net(obs_dict["pixels"])
+
+    def build():
+        torch.manual_seed(11)
+        ssb.manual_seed(11)
+        agent = ssb.Agent(act_space_size=3, encoder=Enc(), actor_network_cls=nets.mlps.ContinuousStochasticActor,
+                          critic_network_cls=nets.mlps.ContinuousCritic, ensemble_size=1, num_critics=2, hidden_size=32,
+                          auto_rescale_targets=False, log_std_low=-5.0, log_std_high=2.0)
+        agent.to("cuda")
+        target = copy.deepcopy(agent)
+        rng = np.random.default_rng(11)
+        n = 64
+        buf = ssb.replay.ReplayBuffer(n, device="cuda")
+        buf.load_experience({"pixels": rng.integers(0, 256, (n, 3, 20, 20), dtype=np.uint8)}, rng.uniform(-0.9, 0.9, (n, 3)).astype(np.float32),
+                            rng.standard_normal(n).astype(np.float32), {"pixels": rng.integers(0, 256, (n, 3, 20, 20), dtype=np.uint8)},
+                            rng.uniform(size=n) < 0.05)
+        c_opt = torch.optim.Adam(chain(*(c.parameters() for c in agent.critics)), lr=3e-4)
+        a_opt = torch.optim.Adam(chain(*(a.parameters() for a in agent.actors)), lr=3e-4)
+        e_opt = torch.optim.Adam(agent.encoder.parameters(), lr=1e-3)
+        la = torch.Tensor([math.log(0.1)]).cuda()
+        la.requires_grad = True
+        return agent, target, buf, c_opt, a_opt, e_opt, [la]
+
+    def run(mode):
+        monkeypatch.setenv("SSAC_ENCODER_OPT", mode)
+        agent, target, buf, c_opt, a_opt, e_opt, las = build()
+        B = 16
+        aug = augmentations.AugmentationSequence([augmentations.IdentityAug(B)])
+        for _ in range(2):
+            learning.critic_update(buffer=buf, agent=agent, target_agent=target, critic_optimizer=c_opt, encoder_optimizer=e_opt,
+                                   log_alphas=las, batch_size=B, gamma=0.99, critic_clip=None, encoder_clip=0.5,
+                                   target_critic_ensemble_n=2, weighted_bellman_temp=None, weight_type=None, pop=False,
+                                   augmenter=aug, encoder_lambda=0.0, random_process=None, noise_clip=None, aug_mix=0.0)
+            learning.offline_actor_update(buffer=buf, agent=agent, actor_optimizer=a_opt, encoder_optimizer=e_opt, batch_size=B,
+                                          actor_clip=None, update_encoder=True, encoder_clip=0.5, augmenter=aug, actor_lambda=0.0,
+                                          aug_mix=0.0, per=False, filter_=False)
+        torch.cuda.synchronize()
+        st = e_opt.state[agent.encoder.net.conv2.weight]
+        return {k: v.detach().cpu().numpy().copy() for k, v in agent.encoder.net.named_parameters()}, float(st["step"])
+
+    fused, fs = run("fused")
+    plain, ps = run("torch")
+    assert fs == ps == 4.0      # two critic updates + two offline actor updates, each stepping the encoder once
+    for k in plain:
+        _close(fused[k], plain[k], f"encoder {k}", rtol=1e-5, rel_atol=1e-5)
