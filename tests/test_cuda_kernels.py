@@ -186,7 +186,7 @@ def test_per_tree_large_matches_oracle():
     import super_sac_b200 as ssb
 
     rng = np.random.default_rng(1)
-    n, cap = 300_000, 1 << 19
+    n, cap = 2_000_000, 1 << 21
     orc = ro.ReplayOracle(cap)
     pr = rng.uniform(0.01, 4.0, n)
     orc.it_sum.set(np.arange(n), pr**0.6)
