@@ -116,8 +116,8 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
         pipe.keep.append(logs)
     loss_all, loss_slot = logs.slots(2 * E)   # per member: {loss contribution, mean td error of its last net}
     opt = _arena.FlatAdam.attach(critic_optimizer, ca)
-    if parallel.is_sharded() and (E != 1 or dr3_coeff > 0 or critic_clip):
-        raise NotImplementedError("critic sharding covers the REDQ shape (one member, no DR3 / global-norm clip)")
+    if parallel.is_sharded() and E != 1:
+        raise NotImplementedError("critic sharding covers one member (REDQ / SAC shapes); SUNRISE members shard as a whole")
 
     enc_outs = []
     lu._mark("start")
@@ -242,9 +242,16 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
             dv, dslot = logs.slots(1)
             L.dr3_dot(h2.data_ptr(), h2b.data_ptr(), N, B, ca.H, dv.data_ptr(), _lib.stream_ptr())
             logs.defer(f"dr3_dotproduct_{i}", dslot)
-            # critic_loss += dr3 * dot, then the whole loss is divided by E*N (learning.py:108,112)
-            loss_v[0:1].add_(dv, alpha=dr3_coeff / (E * N))
-            extra, extra_scale, f1 = h2b, dr3_coeff / (E * N) / (N * B), (X1, h1b, h2b)
+            # critic_loss += dr3 * dot, then the whole loss is divided by E*N (learning.py:108,112).  Critics sharded over
+            # ranks: the mean runs over the GLOBAL ensemble -- this rank contributes its share to the loss (summed over the
+            # ranks with the rest of it below) and the logged dot product is summed right here
+            Ng = parallel.n_global() if parallel.is_sharded() else N
+            if Ng != N:
+                dv.mul_(N / Ng)
+            loss_v[0:1].add_(dv, alpha=dr3_coeff / (E * Ng))
+            if parallel.is_sharded():
+                parallel.all_reduce_sum_(dv, site="dr3_dot")
+            extra, extra_scale, f1 = h2b, dr3_coeff / (E * Ng) / (Ng * B), (X1, h1b, h2b)
         dxg = torch.empty((N, B, S + A), dtype=torch.float32, device=dev) if need_ds else None
         if pipe is not None:
             pipe.join_deferred(torch.cuda.current_stream(dev))   # the previous update's logged gradient norm reads what follows overwrites
@@ -316,6 +323,8 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
         torch.autograd.backward([s for s, _ in enc_outs], [g for _, g in enc_outs])
     if critic_clip:
         opt.grad_norm_sq(stream)
+        if parallel.is_sharded():   # the global norm runs over every rank's critics: one float per rank
+            parallel.all_reduce_sum_(opt.gnorm_sq, site="critic_gnorm")
     enc_net = None
     if enc_outs:
         # a native pixel encoder whose gradients sit in its flat buffer: clip + Adam as two launches (_encoder_opt.py)

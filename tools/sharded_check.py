@@ -62,7 +62,7 @@ def build(N, S, A, H, device, seed):
     return agent
 
 
-def run(agent, target, buf, draws, B, M, cfg, pipelined=False):
+def run(agent, target, buf, draws, B, M, cfg, pipelined=False, critic_clip=None, dr3_coeff=0.0):
     import contextlib
 
     critic_opt, actor_opt, enc_opt, log_alphas, _ = optimizers(agent, cfg)
@@ -77,12 +77,14 @@ def run(agent, target, buf, draws, B, M, cfg, pipelined=False):
               src.push("indices", dr["idx"]).push("normal", dr["eps"]).push("subsets", dr["subset"])
               logs, rds = learning.critic_update(
                   buffer=buf, agent=agent, target_agent=target, critic_optimizer=critic_opt, encoder_optimizer=enc_opt,
-                  log_alphas=log_alphas, batch_size=B, gamma=0.99, critic_clip=None, encoder_clip=None,
+                  log_alphas=log_alphas, batch_size=B, gamma=0.99, critic_clip=critic_clip, encoder_clip=None,
                   target_critic_ensemble_n=M, weighted_bellman_temp=None, weight_type=None, pop=False, augmenter=aug,
-                  encoder_lambda=0.0, random_process=None, noise_clip=None, aug_mix=0.0)
+                  encoder_lambda=0.0, random_process=None, noise_clip=None, aug_mix=0.0, dr3_coeff=dr3_coeff)
               for ac, tc in zip(agent.critics, target.critics):
                   lu.soft_update(tc, ac, 0.005)
               out[f"loss{step}"] = logs["losses/critic_overall_loss"]
+              if dr3_coeff > 0:
+                  out[f"dr3_{step}"] = logs["dr3_dotproduct_0"]
         src = _rng.ScriptedSource()
         _rng.set_source(src)
         src.push("normal", draws[-1]["eps2"])
@@ -230,6 +232,25 @@ def critics_check(rank, world, dev):
         assert torch.equal(pshard._actor_arena.flat, shard._actor_arena.flat), "pipelined sharded block: actor differs"
         print(f"[rank {rank}] pipelined sharded block == sequential sharded updates (bit-identical); losses {pgot}", flush=True)
     parallel.disable()
+
+    # the same with global-norm clipping (active: the norm is far above 0.05) and the DR3 regulariser: the
+    # clip coefficient needs sum ||g||^2 over EVERY rank's critics, DR3 the mean over the global ensemble
+    full2 = build(N, S, A, H, dev, seed=7)
+    full2_t = copy.deepcopy(full2)
+    ref2 = run(full2, full2_t, buffer(), draws, B, M, cfg, critic_clip=0.05, dr3_coeff=0.01)
+    parallel.enable_critic_sharding(N)
+    shard2 = build(hi - lo, S, A, H, dev, seed=7)
+    for n in init_c:
+        shard2._critic_arena.p[n].copy_(init_c[n][lo:hi])
+    shard2._actor_arena.flat.copy_(init_a)
+    shard2_t = copy.deepcopy(shard2)
+    got2 = run(shard2, shard2_t, buffer(), draws, B, M, cfg, critic_clip=0.05, dr3_coeff=0.01)
+    parallel.disable()
+    for n in init_c:
+        assert_close(shard2._critic_arena.p[n].cpu().numpy(), full2._critic_arena.p[n][lo:hi].cpu().numpy(), 1e-4, 1.5e-5, f"clip+DR3 critics {n}")
+    for k in ref2:
+        assert_close(got2[k], ref2[k], 2e-4, 1e-6, "clip+DR3 " + k)
+    print(f"[rank {rank}] sharded critics with global-norm clip + DR3 == single-GPU update; {got2}", flush=True)
 
     for n in init_c:
         assert_close(shard._critic_arena.p[n].cpu().numpy(), full._critic_arena.p[n][lo:hi].cpu().numpy(), 1e-4, 1.5e-5, f"critics {n}")
