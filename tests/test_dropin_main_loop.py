@@ -129,3 +129,110 @@ def test_reference_training_loop_runs_on_the_drop_in():
         assert torch.isfinite(p).all()
     # the caller-built torch.optim.Adam objects of main.py:188-227 were recognised: their state views moved
     assert int(agent._critic_arena.flat.isfinite().all())
+
+
+class _StubPixelEnv:
+    """uint8 frame stacks [3, 20, 20] under the key "obs" (what the reference's pixel wrappers hand out), 2-d actions."""
+
+    def __init__(self, seed, horizon=25):
+        self.rng = np.random.default_rng(seed)
+        self.action_space = _Box(2)
+        self.horizon = horizon
+
+    def _frame(self):
+        base = (np.add.outer(np.arange(20), np.arange(20)) * 3 + 40 * self.phase) % 256
+        img = np.stack([(base + 37 * c) % 256 for c in range(3)]).astype(np.int64)
+        return {"obs": ((img + self.rng.integers(0, 8, img.shape)) % 256).astype(np.uint8)}
+
+    def reset(self):
+        self.t, self.phase = 0, 0.0
+        return self._frame(), {}
+
+    def step(self, a):
+        self.t += 1
+        self.phase += float(np.asarray(a, np.float32).sum())
+        return self._frame(), float(np.cos(self.phase)), False, self.t >= self.horizon, {}
+
+
+def test_reference_training_loop_runs_on_the_drop_in_with_the_native_pixel_encoder():
+    """The same unmodified loop in its DrQv2 configuration (experiments/dmc/drqv2.gin): pixel observations, Drqv2Aug,
+    BigPixelEncoder (here the native tcgen05 encoder with its fused optimiser step), deterministic actor with the
+    exploration process, 3-step returns, encoder tau 1.0.  Finite logs, the reference's log keys, a trained encoder."""
+    if not ref_import.available():
+        pytest.skip("baseline/_ref (the unmodified reference) did not travel")
+    import super_sac_b200 as ssb
+
+    ref = ref_import.import_reference(device="cpu")
+    main = ref.main
+
+    def run(pkg, device, steps):
+        class PixelEncoder(pkg.nets.Encoder):   # experiments/dmc/train_dmc_from_pixels.py:15-27
+            def __init__(self):
+                super().__init__()
+                self._enc = pkg.nets.cnns.BigPixelEncoder((3, 20, 20), 12)
+
+            @property
+            def embedding_dim(self):
+                return 12
+
+            def forward(self, obs_dict):
+                return self._enc(obs_dict["obs"])
+
+        torch.manual_seed(0)
+        agent = pkg.Agent(act_space_size=2, encoder=PixelEncoder(), actor_network_cls=pkg.nets.mlps.ContinuousDeterministicActor,
+                          critic_network_cls=pkg.nets.mlps.ContinuousCritic, ensemble_size=1, num_critics=2, hidden_size=64,
+                          auto_rescale_targets=False)
+        ours = pkg.__name__ == "super_sac_b200"
+        buffer = pkg.replay.ReplayBuffer(2_000, **(dict(device=device) if ours else {}))
+        env = _StubPixelEnv(1)
+        pkg.learning_utils.warmup_buffer(buffer, env, 120, 25, 3, 0.99)
+        enc0 = {k: v.detach().clone() for k, v in agent.encoder._enc.state_dict().items()}
+        seen = {}
+        L = main.learning
+        wrapped = {}
+        for fn in ("critic_update", "online_actor_update"):
+            orig = getattr(L, fn)
+
+            def make(orig=orig, fn=fn):
+                def f(*a, **k):
+                    out = orig(*a, **k)
+                    logs = out[0] if isinstance(out, tuple) else out
+                    seen.setdefault(fn, set()).update(logs.keys())
+                    for key, v in logs.items():
+                        assert np.isfinite(float(v)), f"{fn}: {key} = {v}"
+                    return out
+                return f
+
+            wrapped[fn] = orig
+            setattr(L, fn, make())
+        try:
+            main.super_sac(agent, buffer, env, _StubPixelEnv(2), num_steps_offline=0, num_steps_online=steps, batch_size=32,
+                           critic_updates_per_step=1, use_afbc_update_online=False, use_pg_update_online=True, pop=False,
+                           weight_type=None, init_alpha=0, alpha_lr=0, use_exploration_process=True,
+                           exploration_param_init=1.0, exploration_param_final=0.1, exploration_param_anneal=500,
+                           exploration_update_clip=0.3, n_step=3, gamma=0.99, mlp_tau=0.01, encoder_tau=1.0, target_delay=1,
+                           actor_clip=None, critic_clip=None, encoder_clip=None,
+                           augmenter=pkg.augmentations.AugmentationSequence([pkg.augmentations.Drqv2Aug(32)]), aug_mix=1.0,
+                           eval_interval=10**9, evaluation_method=lambda *a, **k: {"eval/mean_return": 0.0},
+                           log_to_disk=False, save_to_disk=False, verbosity=0, max_episode_steps=25)
+        finally:
+            for fn, orig in wrapped.items():
+                setattr(L, fn, orig)
+        return agent, enc0, seen
+
+    _, _, want = run(ref, "cpu", steps=8)
+    saved = (main.learning, main.lu, main.augmentations, main.device)
+    main.learning, main.lu, main.augmentations, main.device = ssb.learning, ssb.learning_utils, ssb.augmentations, torch.device("cuda")
+    try:
+        agent, enc0, got = run(ssb, torch.device("cuda"), steps=60)
+    finally:
+        main.learning, main.lu, main.augmentations, main.device = saved
+    for fn in want:
+        assert got[fn] == want[fn], f"{fn}: log keys differ: {sorted(got[fn] ^ want[fn])}"
+    net = agent.encoder._enc
+    assert net.__dict__.get("_flat") is not None, "the native encoder path did not run"
+    moved = 0.0
+    for k, v in net.state_dict().items():
+        assert torch.isfinite(v).all(), k
+        moved = max(moved, float((v.cpu() - enc0[k].cpu()).abs().max()))
+    assert moved > 0.0, "the encoder was never updated"
