@@ -47,11 +47,10 @@ constexpr int kConvStages = 4;
 constexpr int kConvThreads = 320;
 constexpr int kWBytes = 9 * 8192;   // resident weights: per tap-block 64 rows (32 hi + 32 lo) x 128 bytes
 constexpr int kConvStageBytes = 32768;   // A_hi + A_lo
-constexpr int kConvSmem = kWBytes + kConvStages * kConvStageBytes + 16384 + 1024;
+constexpr int kConvSmem = kWBytes + kConvStages * kConvStageBytes + 1024;
 
 struct ConvP {
   CUtensorMap tmIn;    // (channels, pixels), SWIZZLE_128B; box 32 x 128 (one per tap-block) or 32 x hr (one halo box per tile)
-  CUtensorMap tmOut;   // (32, pixels), box 32 x 128, SWIZZLE_128B
   const float* wpack;  // ntb x 8 KB shared-memory images (conv_pack_kernel)
   const float* bias;   // mode 0
   const float* yprev;  // mode 1: the activations whose ReLU the gradient passes through [pixels][32]
@@ -79,7 +78,7 @@ struct ConvP {
 // Epilogue warps 0-3 (thread = pixel = TMEM lane) of the convolution kernels: accumulator halves added, bias + ReLU
 // (forward) or ReLU mask (data gradient), and the pixel's 128 bytes stored at its place on the destination grid.
 __device__ __forceinline__ void conv_epilogue(const ConvP& q, uint32_t tmem_d, uint64_t* bar_accf, uint64_t* bar_acce,
-                                              uint8_t* /*osm*/, const float* bias_sh, int ntl) {
+                                              const float* bias_sh, int ntl) {
   const int t = threadIdx.x, warp = t >> 5, row = t;
   for (int i = 0; i < ntl; ++i) {
     const int buf = i & 1;
@@ -138,7 +137,6 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* wsm = smem;
   uint8_t* stg = smem + kWBytes;
-  uint8_t* osm = stg + kConvStages * kConvStageBytes;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
 
   if (warp == 0) tmem_alloc(&tmem_base_sh, 128);
@@ -239,7 +237,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tc_kernel(const __grid_c
       mbar_arrive(&bar_full[s]);
     }
   } else {
-    conv_epilogue(q, tmem_d, bar_accf, bar_acce, osm, bias_sh, ntl);
+    conv_epilogue(q, tmem_d, bar_accf, bar_acce, bias_sh, ntl);
   }
   fence_before_sync();
   __syncthreads();
@@ -265,7 +263,6 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   uint8_t* wsm = smem;
   uint8_t* his = smem + (size_t)q.ntb * 8192;
   uint8_t* los = his + (size_t)nhi * hrb;
-  uint8_t* osm = los + (size_t)nlo * hrb;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
 
   if (warp == 0) tmem_alloc(&tmem_base_sh, 128);
@@ -365,7 +362,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       mbar_arrive(&bar_lof[l]);
     }
   } else {
-    conv_epilogue(q, tmem_d, bar_accf, bar_acce, osm, bias_sh, ntl);
+    conv_epilogue(q, tmem_d, bar_accf, bar_acce, bias_sh, ntl);
   }
   fence_before_sync();
   __syncthreads();
@@ -733,11 +730,11 @@ __device__ __forceinline__ float4 patch4(const DirectGeo& g, const PixelAt& a, i
 }
 
 struct Conv1P {
-  ConvP c;          // tmOut, bias, wpack, ntiles, mode = 0, np (the epilogue's view); ntb = number of k-blocks, ksteps[]
+  ConvP c;          // bias, wpack, out + destination grid, ntiles, mode = 0, np (the epilogue's view); ntb = number of k-blocks, ksteps[]
   DirectGeo g;
 };
 constexpr int kDirThreads = 416;   // warps 0-3 epilogue, 4-11 tile builders, 12 MMA issuer
-constexpr int kDirSmem = 5 * 8192 + kConvStages * kConvStageBytes + 16384 + 1024;
+constexpr int kDirSmem = 5 * 8192 + kConvStages * kConvStageBytes + 1024;
 __global__ void __launch_bounds__(kDirThreads, 1) conv1_direct_kernel(const __grid_constant__ Conv1P q) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[kConvStages], bar_empty[kConvStages], bar_accf[2], bar_acce[2];
@@ -746,7 +743,6 @@ __global__ void __launch_bounds__(kDirThreads, 1) conv1_direct_kernel(const __gr
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* wsm = smem;
   uint8_t* stg = smem + 5 * 8192;
-  uint8_t* osm = stg + kConvStages * kConvStageBytes;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int nkb = q.c.ntb;
 
@@ -839,7 +835,7 @@ __global__ void __launch_bounds__(kDirThreads, 1) conv1_direct_kernel(const __gr
       }
     }
   } else {
-    conv_epilogue(q.c, tmem_d, bar_accf, bar_acce, osm, bias_sh, ntl);
+    conv_epilogue(q.c, tmem_d, bar_accf, bar_acce, bias_sh, ntl);
   }
   fence_before_sync();
   __syncthreads();
