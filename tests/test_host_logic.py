@@ -130,3 +130,32 @@ def test_unsupported_features_fail_loudly():
 
     with pytest.raises(NotImplementedError):
         ssb.Agent(2, IdentityEncoder(3), nets.mlps.ContinuousStochasticActor, Odd)
+
+
+def test_big_pixel_encoder_module_shell_on_cpu():
+    """nets.cnns.BigPixelEncoder keeps the reference's nn.Module shell (nets/cnns.py:37-69): parameter names / shapes and the
+    state_dict of the reference module load into it, its CPU forward reproduces the golden output of the UNMODIFIED reference
+    module, and deepcopy / state_dict round trips work (target_agent = deepcopy(agent), Agent.save / load)."""
+    import copy
+
+    import numpy as np
+    import torch
+
+    import golden_util as gu
+    from super_sac_b200.nets import cnns
+
+    fx = gu.load("encoder")
+    for tag in ("rgb20", "stack24"):
+        obs = fx[f"{tag}/obs"]
+        params = gu.sub(fx, f"{tag}/params")
+        enc = cnns.BigPixelEncoder(obs.shape[1:], out_dim=fx[f"{tag}/out"].shape[1])
+        assert {k: tuple(v.shape) for k, v in enc.state_dict().items()} == {k: tuple(v.shape) for k, v in params.items()}
+        enc.load_state_dict({k: torch.as_tensor(v) for k, v in params.items()})
+        with torch.no_grad():
+            y = enc(torch.as_tensor(obs).float())
+        gu.assert_close(y.numpy(), fx[f"{tag}/out"], 2e-5, 2e-6, f"{tag} CPU module forward")
+        twin = copy.deepcopy(enc)
+        assert all(torch.equal(a, b) for a, b in zip(twin.state_dict().values(), enc.state_dict().values()))
+        assert twin._ws is not enc._ws                       # workspaces are per module
+        twin.load_state_dict(enc.state_dict())
+        assert enc.embedding_dim == fx[f"{tag}/out"].shape[1]
