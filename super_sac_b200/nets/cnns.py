@@ -47,7 +47,9 @@ class _EncoderFn(torch.autograd.Function):
         B, C, H, W = obs.shape
         O = module.embedding_dim
         save = 1 if any(ctx.needs_input_grad[2:]) else 0
-        key = (B, save, obs.device)
+        # (one workspace per shape: every update path that may run encoders on several streams at once -- member lanes,
+        # pipelined blocks -- excludes agents with a parameterised encoder, learning._encoder_trainable)
+        key = (B, C, H, W, save, obs.device)
         n = ctypes.c_int64()
         lib.conv_encoder_ws_floats(B, C, H, W, O, save, ctypes.byref(n))
         ws = module._ws.take(key, n.value, obs.device)
@@ -151,10 +153,19 @@ class BigPixelEncoder(nn.Module):
         return (obs.dim() == 4 and obs.shape[1] <= 16 and obs.shape[2] % 2 == 0 and obs.shape[3] % 2 == 0
                 and min(obs.shape[2], obs.shape[3]) >= 16 and self.embedding_dim <= 64)
 
+    def _check_geometry(self, obs):
+        """The kernels size everything from the observation's shape: it has to be the shape the module was built for."""
+        c, h, w = obs.shape[1:]
+        vh, vw = h // 2 - 7, w // 2 - 7
+        if c != self.conv1.in_channels or vh <= 0 or vw <= 0 or 32 * vh * vw != self.fc.in_features:
+            raise ValueError(f"BigPixelEncoder built for {self.conv1.in_channels} channels / {self.fc.in_features} features "
+                             f"got observations of shape {tuple(obs.shape[1:])}")
+
     def forward(self, obs):
         if obs.is_cuda and os.environ.get("SSAC_ENCODER_IMPL", "native") != "torch":
             if not self.native_supported(obs):
                 raise NotImplementedError("BigPixelEncoder on CUDA: <= 16 channels, even sides >= 16, out_dim <= 64")
+            self._check_geometry(obs)
             x = obs if obs.dtype == torch.float32 else obs.float()
             self._flatten()
             params = self._native_params()

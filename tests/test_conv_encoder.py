@@ -436,3 +436,15 @@ def test_encoder_training_drift_against_cpu_module():
     lc = float(((cpu({"obs": obs}) - tgt) ** 2).mean())
     lg = float(((gpu({"obs": obs_g}) - tgt_g) ** 2).mean())
     assert lc < 0.7 * l0 and abs(lc - lg) <= 1e-4 * abs(lc) + 1e-6      # it trains, and by the same amount on both sides
+
+
+@pytest.mark.gpu
+def test_encoder_rejects_observations_of_another_geometry():
+    from super_sac_b200.nets import cnns
+
+    enc = cnns.BigPixelEncoder((3, 20, 20), 10).cuda()
+    with pytest.raises(ValueError):
+        enc(torch.zeros(2, 3, 24, 24, device="cuda"))
+    with pytest.raises(ValueError):
+        enc(torch.zeros(2, 4, 20, 20, device="cuda"))
+    assert enc(torch.zeros(2, 3, 20, 20, device="cuda")).shape == (2, 10)
