@@ -659,10 +659,20 @@ def dominant_kernel_roofline(args, cfg, W):
 
     peaks = bl.measured_peaks()
     if cfg.get("pixels"):
+        # the pixel update is dominated by the native encoder's tensor-core convolutions (conv_halo_kernel: 11 of the ~74
+        # launches, ~46 % of the step); the HBM-bound pixel gather rides along as `hbm`
+        enc = time_pixel_encoder(B=cfg["B"])
         r = hbm_kernels()[0]
-        return {"kernel": r["kernel"], "bound": "hbm", "achieved": r["GBps"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": r["frac_of_hbm_peak"], "traffic": None, "us_per_launch": r["us"],
-                "algorithmic_bytes_per_launch": r["algorithmic_MB"] * 1e6, "peak_source": peaks["source"]}
+        f = enc["forward"]
+        return {"kernel": "native BigPixelEncoder forward (s2d + 4 x conv_halo_kernel + split-K FC; 3xTF32 tcgen05 implicit GEMMs)",
+                "bound": "tensor", "achieved": f["algorithmic_TFLOPs"], "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": f["frac_of_bf16_peak"], "frac_of_3xTF32_ceiling": f["frac_of_3xTF32_ceiling"], "traffic": None,
+                "us_per_launch": f["us"], "forward_backward": enc["forward_backward"], "peak_source": peaks["source"],
+                "note": "fp32 parity needs 3xTF32 and the 32-channel layers give the MMAs N = 64 / 32 only: ncu has the tensor "
+                        "pipe active 72-86 % of the convolution kernels' time (profiles/r2_15)",
+                "hbm": {"kernel": r["kernel"], "achieved": r["GBps"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": r["frac_of_hbm_peak"], "us_per_launch": r["us"],
+                        "algorithmic_bytes_per_launch": r["algorithmic_MB"] * 1e6}}
     ca = W.agent._critic_arena
     G, B, H, D = cfg["E"] * cfg["N"], cfg["B"], cfg["H"], cfg["S"] + cfg["A"]
     dev = ca.device
