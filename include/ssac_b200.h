@@ -58,6 +58,9 @@ int ssac_adam_step(float* p_dev, float* g_dev, float* m_dev, float* v_dev, int64
 int ssac_adam_polyak_step(float* p_dev, float* g_dev, float* m_dev, float* v_dev, float* target_dev, int64_t n,
                           int32_t* ctl_dev, double lr, double beta1, double beta2, double eps, double weight_decay,
                           const float* gnorm_sq_dev, double max_norm, int write_back_grad, double tau, void* stream);
+/* x_dev[i] = *scale_dev * x_dev[i]: the annealed exploration-noise scale of learning_utils.py:48-59 kept in device memory
+ * (GaussianExplorationNoise.scale_dev), so that a captured update follows it from replay to replay. */
+int ssac_scale_by_dev(float* x_dev, int64_t n, const float* scale_dev, void* stream);
 /* out_dev[0] (+)= sum x^2  (global grad norm for clipping / get_grad_norm, learning_utils.py:95-106). */
 int ssac_sumsq(const float* x_dev, int64_t n, float* out_dev, int accumulate, void* stream);
 

@@ -70,6 +70,33 @@ class FlatParamAdam:
             self._step_tensor.fill_(self.steps)
 
 
+def structurally_eligible(encoder, optimizer=None):
+    """What can be known BEFORE an update runs: the encoder's only trainable parameters of any size are those of one native
+    net that has already been flattened (and, given the optimiser, that it is a plain single-group Adam over them).  Such
+    an update hands nothing to torch.autograd that a CUDA graph could not replay."""
+    nets = native_nets(encoder)
+    if len(nets) != 1 or nets[0].__dict__.get("_flat") is None:
+        return False
+    own = {id(p) for p in nets[0]._native_params()}
+    if any(p.numel() > 2 and p.requires_grad and id(p) not in own for p in encoder.parameters()):
+        return False
+    if optimizer is not None:
+        if not isinstance(optimizer, torch.optim.Adam) or len(optimizer.param_groups) != 1:
+            return False
+        pg = optimizer.param_groups[0]
+        if pg.get("amsgrad") or pg.get("maximize") or pg.get("capturable") or pg.get("differentiable"):
+            return False
+    return os.environ.get("SSAC_ENCODER_OPT") != "torch"
+
+
+def note_replayed_step(encoder, optimizer):
+    """A captured graph containing the fused encoder step was replayed: the device counter advanced by itself."""
+    st = getattr(optimizer, "_ssac_flat_param_adam", None)
+    if st is not None:
+        st.steps += 1
+        st._step_tensor.fill_(st.steps)
+
+
 def eligible(encoder, optimizer):
     """The native net whose flat gradient buffer holds every gradient `optimizer` would consume, or None."""
     nets = native_nets(encoder)

@@ -698,6 +698,21 @@ int ssac_adam_polyak_step(float* p, float* g, float* m, float* v, float* target,
                      write_back_grad, tau, stream, 0, 0);
 }
 
+// x[i] *= *scale_dev: a factor that lives in device memory (the annealed TD3 noise scale), so that a captured graph
+// follows it from replay to replay
+__global__ void scale_by_dev_kernel(float* __restrict__ x, int64_t n, const float* __restrict__ scale) {
+  const float sc = __ldg(scale);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] = sc * x[i];
+}
+
+int ssac_scale_by_dev(float* x, int64_t n, const float* scale_dev, void* stream) {
+  SSAC_REQUIRE(x && scale_dev && n >= 0, "ssac_scale_by_dev: bad args");
+  if (n == 0) return 0;
+  scale_by_dev_kernel<<<grid_for(n, 256, 2), 256, 0, (cudaStream_t)stream>>>(x, n, scale_dev);
+  SSAC_CHECK_LAUNCH("ssac_scale_by_dev");
+  return 0;
+}
+
 int ssac_sumsq(const float* x, int64_t n, float* out, int accumulate, void* stream) {
   SSAC_REQUIRE(out, "ssac_sumsq: null out");
   if (!accumulate) {

@@ -39,11 +39,14 @@ def _encoder_trainable(agent):
     return any(p.requires_grad for p in ps)
 
 
-def _graphable(agent, random_process, per, update_priorities):
-    """Static shapes, device-side randomness, no PyTorch autograd hand-off, no host-side decisions."""
+def _graphable(agent, random_process, per, update_priorities, encoder_optimizer=None):
+    """Static shapes, device-side randomness (incl. the exploration-noise scale, GaussianExplorationNoise.scale_dev), no
+    PyTorch autograd hand-off -- a parameterised encoder only if it is the native pixel encoder with its fused optimiser
+    step (_encoder_opt.structurally_eligible) --, no host-side decisions."""
     return (graphed.auto_graphs_enabled() and isinstance(_rng.source(), _rng.PhiloxSource) and not per and
-            not update_priorities and random_process is None and not parallel.is_sharded() and
-            not parallel.members_sharded() and not _encoder_trainable(agent))
+            not update_priorities and (random_process is None or hasattr(random_process, "scale_dev")) and
+            not parallel.is_sharded() and not parallel.members_sharded() and
+            (not _encoder_trainable(agent) or _encoder_opt.structurally_eligible(agent.encoder, encoder_optimizer)))
 
 
 def critic_update(buffer, agent, target_agent, critic_optimizer, encoder_optimizer, log_alphas, batch_size, gamma,
@@ -55,22 +58,27 @@ def critic_update(buffer, agent, target_agent, critic_optimizer, encoder_optimiz
     args = (buffer, agent, target_agent, critic_optimizer, encoder_optimizer, log_alphas, batch_size, gamma, critic_clip,
             encoder_clip, target_critic_ensemble_n, weighted_bellman_temp, weight_type, pop, augmenter, encoder_lambda,
             random_process, noise_clip, aug_mix, discrete, per, update_priorities, dr3_coeff)
-    if not discrete and not encoder_lambda and _graphable(agent, random_process, per, update_priorities):
+    if not discrete and not encoder_lambda and _graphable(agent, random_process, per, update_priorities, encoder_optimizer):
         key = ("critic", id(buffer), id(agent), id(target_agent), _opt_sig(critic_optimizer), id(encoder_optimizer),
+               id(random_process),
                tuple(id(l) for l in log_alphas), batch_size, gamma, critic_clip, encoder_clip, target_critic_ensemble_n,
                weighted_bellman_temp, weight_type, pop, id(augmenter), noise_clip, aug_mix, dr3_coeff,
                _lib.lib().default_mlp_impl())
         opt = _arena.FlatAdam.attach(critic_optimizer, agent._critic_arena)
 
+        enc_trained = _encoder_trainable(agent)
+
         def on_replay():
             opt.note_replayed_step()
+            if enc_trained:
+                _encoder_opt.note_replayed_step(agent.encoder, encoder_optimizer)
             buffer.total_sample_calls += agent.ensemble_size
 
-        refs = (buffer, agent, target_agent, critic_optimizer, encoder_optimizer, tuple(log_alphas), augmenter)
+        refs = (buffer, agent, target_agent, critic_optimizer, encoder_optimizer, tuple(log_alphas), augmenter, random_process)
         # cross-call pipelining (graphed._Cross) covers what lu.pipelined_updates covers, minus PopArt (device state that
         # both sides of an update touch)
         cross_ok = (agent.ensemble_size == 1 and weight_type is None and not any(bool(p) for p in agent.popart)
-                    and lu.side_stream(agent._critic_arena.device) is not None)
+                    and lu.side_stream(agent._critic_arena.device) is not None and not enc_trained)
         return graphed.run_cached(key, lambda: _critic_update_impl(*args), on_replay, refs=refs, cross_ok=cross_ok)
     graphed.join()
     return _critic_update_impl(*args)
@@ -399,9 +407,9 @@ def online_actor_update(buffer, agent, pop, actor_optimizer, log_alphas, batch_s
             and all(graphed.is_static(rd) for rd in premade_replay_dicts)
             and _graphable(agent, random_process, per, False)):
         key = ("actor", id(agent), _opt_sig(actor_optimizer), tuple(id(l) for l in log_alphas), batch_size, clip, pop,
-               tuple(id(rd) for rd in premade_replay_dicts), _lib.lib().default_mlp_impl())
+               tuple(id(rd) for rd in premade_replay_dicts), _lib.lib().default_mlp_impl(), id(random_process), noise_clip)
         opt = _arena.FlatAdam.attach(actor_optimizer, agent._actor_arena)
-        refs = (agent, actor_optimizer, tuple(log_alphas), tuple(premade_replay_dicts))
+        refs = (agent, actor_optimizer, tuple(log_alphas), tuple(premade_replay_dicts), random_process)
         return graphed.run_cached(key, lambda: _online_actor_update_impl(*args), opt.note_replayed_step, refs=refs)
     return _online_actor_update_impl(*args)
 

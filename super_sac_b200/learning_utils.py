@@ -30,11 +30,29 @@ class GaussianExplorationNoise:
         assert start_scale >= final_scale
         self.action_space = action_space
         self.start_scale, self.final_scale, self.steps_annealed = start_scale, final_scale, steps_annealed
+        self._scale_dev = None
         self.current_scale = start_scale
         self._scale_slope = (start_scale - final_scale) / steps_annealed
         self.eps = eps
         if not (np.allclose(action_space.low, -1.0) and np.allclose(action_space.high, 1.0)):
             raise NotImplementedError("the fused noise head assumes actions normalised to [-1, 1] (NormActionSpace)")
+
+    @property
+    def current_scale(self):
+        return self._current_scale
+
+    @current_scale.setter
+    def current_scale(self, v):
+        self._current_scale = v
+        if self._scale_dev is not None:
+            self._scale_dev.fill_(float(v))
+
+    def scale_dev(self, device):
+        """The current scale as a 1-element device tensor that follows every change of ``current_scale``: the update
+        kernels read sigma from it, so a CUDA graph captured over an update keeps annealing with the acting path."""
+        if self._scale_dev is None or self._scale_dev.device != torch.device(device):
+            self._scale_dev = torch.full((1,), float(self._current_scale), dtype=torch.float32, device=device)
+        return self._scale_dev
 
     def sample(self, action, clip=None, update_schedule=False):
         if isinstance(action, np.ndarray):
@@ -604,7 +622,13 @@ def _policy_sample(agent, i, X, B, S, A, random_process, noise_clip, rsample=Fal
             if noise is None:
                 noise = torch.empty((B, A), dtype=torch.float32, device=dev)
                 _rng.source().normal(noise)
-            sigma = float(random_process.current_scale)
+            if hasattr(random_process, "scale_dev"):
+                # noise <- sigma * noise with sigma read ON THE DEVICE (bit-identical to passing it by value: one product,
+                # and 1.0 * x below is exact), so the launch sequence does not depend on the annealing state
+                _lib.lib().scale_by_dev(noise.data_ptr(), noise.numel(), random_process.scale_dev(dev).data_ptr(), _lib.stream_ptr())
+                sigma = 1.0
+            else:
+                sigma = float(random_process.current_scale)
             clip = float(noise_clip) if noise_clip is not None else 0.0
         else:
             noise = None

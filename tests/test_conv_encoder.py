@@ -448,3 +448,86 @@ def test_encoder_rejects_observations_of_another_geometry():
     with pytest.raises(ValueError):
         enc(torch.zeros(2, 4, 20, 20, device="cuda"))
     assert enc(torch.zeros(2, 3, 20, 20, device="cuda")).shape == (2, 10)
+
+
+@pytest.mark.gpu
+def test_auto_graphed_pixel_update_follows_the_annealed_noise_scale():
+    """enable_auto_graphs() on the DrQv2-shaped update (native encoder + fused optimiser step, deterministic actor with the
+    exploration-noise process): the replayed graphs give the bits the eager calls give, while the acting path keeps
+    annealing sigma between the updates (the kernels read it from device memory)."""
+    import copy
+    import math
+    from itertools import chain
+
+    import super_sac_b200 as ssb
+    from super_sac_b200 import augmentations, graphed, learning, learning_utils as lu, nets
+    from super_sac_b200.nets import cnns
+
+    class Enc(nets.Encoder):
+        def __init__(self):
+            super().__init__()
+            self.net = cnns.BigPixelEncoder((3, 20, 20), 12)
+
+        @property
+        def embedding_dim(self):
+            return 12
+
+        def forward(self, obs_dict):
+            return self.net(obs_dict["pixels"])
+
+    class Space:
+        low, high, shape = -np.ones(3, np.float32), np.ones(3, np.float32), (3,)
+
+    def run(graphs):
+        torch.manual_seed(5)
+        ssb.manual_seed(5)
+        agent = ssb.Agent(act_space_size=3, encoder=Enc(), actor_network_cls=nets.mlps.ContinuousDeterministicActor,
+                          critic_network_cls=nets.mlps.ContinuousCritic, ensemble_size=1, num_critics=2, hidden_size=32,
+                          auto_rescale_targets=False)
+        agent.to("cuda")
+        target = copy.deepcopy(agent)
+        rng = np.random.default_rng(5)
+        n, B = 64, 16
+        buf = ssb.replay.ReplayBuffer(n, device="cuda")
+        buf.load_experience({"pixels": rng.integers(0, 256, (n, 3, 20, 20), dtype=np.uint8)}, rng.uniform(-0.9, 0.9, (n, 3)).astype(np.float32),
+                            rng.standard_normal(n).astype(np.float32), {"pixels": rng.integers(0, 256, (n, 3, 20, 20), dtype=np.uint8)},
+                            rng.uniform(size=n) < 0.05)
+        c_opt = torch.optim.Adam(chain(*(c.parameters() for c in agent.critics)), lr=3e-4)
+        a_opt = torch.optim.Adam(chain(*(a.parameters() for a in agent.actors)), lr=3e-4)
+        e_opt = torch.optim.Adam(agent.encoder.parameters(), lr=1e-3)
+        la = torch.Tensor([math.log(1e-15)]).cuda()
+        la.requires_grad = True
+        noise = lu.GaussianExplorationNoise(Space(), start_scale=1.0, final_scale=0.1, steps_annealed=10)
+        aug = augmentations.AugmentationSequence([augmentations.Drqv2Aug(B)])
+        graphed.enable_auto_graphs(graphs)
+        losses = []
+        try:
+            for step in range(7):
+                logs, rds = learning.critic_update(
+                    buffer=buf, agent=agent, target_agent=target, critic_optimizer=c_opt, encoder_optimizer=e_opt, log_alphas=[la],
+                    batch_size=B, gamma=0.99, critic_clip=None, encoder_clip=5.0, target_critic_ensemble_n=2,
+                    weighted_bellman_temp=None, weight_type=None, pop=False, augmenter=aug, encoder_lambda=0.0,
+                    random_process=noise, noise_clip=0.3, aug_mix=1.0)
+                for ac, tc in zip(agent.critics, target.critics):
+                    lu.soft_update(tc, ac, 0.01)
+                lu.soft_update(target.encoder, agent.encoder, 1.0)
+                learning.online_actor_update(buffer=buf, agent=agent, pop=False, actor_optimizer=a_opt, log_alphas=[la], batch_size=B,
+                                             clip=None, random_process=noise, noise_clip=0.3, augmenter=aug, aug_mix=1.0,
+                                             premade_replay_dicts=rds)
+                losses.append(float(logs["losses/critic_overall_loss"]))
+                noise.sample(np.zeros(3, np.float32), update_schedule=True)     # the acting path anneals sigma (main.py:350)
+            torch.cuda.synchronize()
+            captured = sorted(k[0] for k, e in graphed._auto["cache"].items() if any(sl.graph is not None for sl in e.slots))
+            assert captured == (["actor", "critic"] if graphs else []), captured    # both entry points really replay graphs
+        finally:
+            graphed.enable_auto_graphs(False)
+        st = e_opt.state[agent.encoder.net.conv2.weight]
+        return ([p.detach().clone() for p in chain(agent.encoder.net.parameters(), agent.critics[0].parameters(), agent.actors[0].parameters())],
+                losses, float(st["step"]), noise.current_scale)
+
+    eager, le, se, sc_e = run(False)
+    graph, lg, sg, sc_g = run(True)
+    assert se == sg == 7.0 and sc_e == sc_g and abs(sc_e - 0.37) < 1e-6
+    assert le == lg, (le, lg)
+    for a, b in zip(eager, graph):
+        assert torch.equal(a, b)
