@@ -223,9 +223,15 @@ def test_reference_training_loop_runs_on_the_drop_in_with_the_native_pixel_encod
     _, _, want = run(ref, "cpu", steps=8)
     saved = (main.learning, main.lu, main.augmentations, main.device)
     main.learning, main.lu, main.augmentations, main.device = ssb.learning, ssb.learning_utils, ssb.augmentations, torch.device("cuda")
+    from super_sac_b200 import graphed
+
+    graphed.enable_auto_graphs(True)   # the native encoder and the device-side noise scale make this configuration capturable
     try:
         agent, enc0, got = run(ssb, torch.device("cuda"), steps=60)
+        captured = sorted(k[0] for k, e in graphed._auto["cache"].items() if any(sl.graph is not None for sl in e.slots))
+        assert "critic" in captured, captured
     finally:
+        graphed.enable_auto_graphs(False)
         main.learning, main.lu, main.augmentations, main.device = saved
     for fn in want:
         assert got[fn] == want[fn], f"{fn}: log keys differ: {sorted(got[fn] ^ want[fn])}"
