@@ -112,6 +112,17 @@ class BigPixelEncoder(nn.Module):
             new.__dict__[k] = _Workspace() if k == "_ws" else copy.deepcopy(v, memo)
         return new
 
+    def __getstate__(self):
+        # pickling (torch.save(agent)): parameters travel, device workspaces and the flat-buffer bookkeeping do not
+        state = dict(self.__dict__)
+        for k in ("_ws", "_flat", "_flat_off", "_flat_grad"):
+            state.pop(k, None)
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self.__dict__["_ws"] = _Workspace()
+
     def _flatten(self):
         """Parameters as views of ONE contiguous buffer (and a twin gradient buffer), so that Adam, gradient clipping and
         the logged gradient norm are one launch each (_encoder_opt.py) instead of a dozen per tensor.  Lazy: `.to()` /

@@ -159,3 +159,11 @@ def test_big_pixel_encoder_module_shell_on_cpu():
         assert twin._ws is not enc._ws                       # workspaces are per module
         twin.load_state_dict(enc.state_dict())
         assert enc.embedding_dim == fx[f"{tag}/out"].shape[1]
+        import io
+        import pickle
+
+        buf = io.BytesIO()
+        pickle.dump(enc, buf)          # torch.save(module): workspaces stay behind, a fresh pool comes back
+        back = pickle.loads(buf.getvalue())
+        assert all(torch.equal(a, b) for a, b in zip(back.state_dict().values(), enc.state_dict().values()))
+        assert isinstance(back._ws, cnns._Workspace) and not back._ws.free
