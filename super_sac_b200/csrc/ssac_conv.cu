@@ -1122,20 +1122,31 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, const float*
   }
 }
 
-// FC weight [O][32*vh*vw] (NCHW flatten, nets/cnns.py:63) <-> zero-padded pitch layout Wp[64][kfp], column (h*gw+w)*32 + c
-__global__ void fc_pack_kernel(const float* __restrict__ fcw, float* __restrict__ wp, int O, int vh, int vw, int gw, int64_t kfp,
-                               int unpack) {
-  const int64_t n = (int64_t)O * 32 * vh * vw;
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n) return;
-  // thread order (o, h, w, c): the pitch-layout side is contiguous
-  const int c = (int)(idx & 31);
-  const int64_t r = idx >> 5;
-  const int w = (int)(r % vw), h = (int)((r / vw) % vh), o = (int)(r / ((int64_t)vw * vh));
-  const int64_t a = (int64_t)o * 32 * vh * vw + (int64_t)c * vh * vw + h * vw + w;
-  const int64_t b = (int64_t)o * kfp + ((int64_t)h * gw + w) * 32 + c;
-  if (unpack) const_cast<float*>(fcw)[a] = wp[b];
-  else wp[b] = __ldg(fcw + a);
+// FC weight [O][32*vh*vw] (NCHW flatten, nets/cnns.py:63) <-> zero-padded pitch layout Wp[64][kfp], column (h*gw+w)*32 + c.
+// One block per (output o, image row h): the 32 x vw slab is transposed through shared memory so that both sides move in
+// contiguous runs (vw floats per channel on the module side, 32 * vw floats on the pitch side).
+__global__ void __launch_bounds__(256) fc_pack_kernel(const float* __restrict__ fcw, float* __restrict__ wp, int O, int vh,
+                                                      int vw, int gw, int64_t kfp, int unpack) {
+  extern __shared__ float tile[];   // [32][vw + 1]
+  const int o = blockIdx.x / vh, h = blockIdx.x - o * vh;
+  const int pitch = vw + 1;
+  float* mod = const_cast<float*>(fcw) + (int64_t)o * 32 * vh * vw + (int64_t)h * vw;      // + c*vh*vw + w
+  float* pit = wp + (int64_t)o * kfp + (int64_t)h * gw * 32;                               // + w*32 + c
+  if (!unpack) {
+    for (int i = threadIdx.x; i < 32 * vw; i += blockDim.x) {
+      const int c = i / vw, w = i - c * vw;
+      tile[c * pitch + w] = mod[(int64_t)c * vh * vw + w];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * vw; i += blockDim.x) pit[i] = tile[(i & 31) * pitch + (i >> 5)];
+  } else {
+    for (int i = threadIdx.x; i < 32 * vw; i += blockDim.x) tile[(i & 31) * pitch + (i >> 5)] = pit[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * vw; i += blockDim.x) {
+      const int c = i / vw, w = i - c * vw;
+      mod[(int64_t)c * vh * vw + w] = tile[c * pitch + w];
+    }
+  }
 }
 
 // z = fc bias + split-K partials (fixed order) -> LayerNorm (biased variance, eps 1e-5) -> tanh.  One block of 64 threads per row.
@@ -1516,8 +1527,7 @@ extern "C" int ssac_conv_encoder_forward(const float* obs_dev, int B, int C, int
     SSAC_CHECK_LAUNCH("conv_pack_kernel");
   }
   {
-    const int64_t n = (int64_t)out_dim * 32 * pl.vh[4] * pl.vw[4];
-    cv::fc_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(params[8], ws + pl.wfc, out_dim, pl.vh[4], pl.vw[4], pl.P[4], pl.kfp, 0);
+    cv::fc_pack_kernel<<<out_dim * pl.vh[4], 256, (size_t)32 * (pl.vw[4] + 1) * sizeof(float), s>>>(params[8], ws + pl.wfc, out_dim, pl.vh[4], pl.vw[4], pl.P[4], pl.kfp, 0);
     SSAC_CHECK_LAUNCH("fc_pack_kernel");
   }
   if (pl.direct) {
@@ -1560,8 +1570,7 @@ extern "C" int ssac_conv_encoder_backward(const float* dout_dev, const float* ou
     g.C = ws + pl.gwfc; g.ldc = pl.kfp;
     g.M = 64; g.N = (int)pl.kf; g.K = B;
     if (int rc = launch_gemm_tc(L_TN, g, 1, s, "conv encoder fc wgrad")) return rc;
-    const int64_t n = (int64_t)out_dim * 32 * pl.vh[4] * pl.vw[4];
-    cv::fc_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(grads[8], ws + pl.gwfc, out_dim, pl.vh[4], pl.vw[4], pl.P[4], pl.kfp, 1);
+    cv::fc_pack_kernel<<<out_dim * pl.vh[4], 256, (size_t)32 * (pl.vw[4] + 1) * sizeof(float), s>>>(grads[8], ws + pl.gwfc, out_dim, pl.vh[4], pl.vw[4], pl.P[4], pl.kfp, 1);
     SSAC_CHECK_LAUNCH("fc_pack_kernel (unpack)");
   }
   {  // dZ4 = (dfc . W') .* (Y4 > 0)   (W' is zero outside the valid region).  Measured: a CUDA-core kernel with the weight
