@@ -63,28 +63,36 @@ def build(N, S, A, H, device, seed):
 
 
 def run(agent, target, buf, draws, B, M, cfg, pipelined=False, critic_clip=None, dr3_coeff=0.0):
+    """The scripted update sequence: len(draws) critic updates (+ Polyak) -- inside one lu.pipelined_updates() block when
+    ``pipelined`` -- then one actor update on the last batch.  Returns the logged losses."""
     import contextlib
 
     critic_opt, actor_opt, enc_opt, log_alphas, _ = optimizers(agent, cfg)
     aug = augmentations.AugmentationSequence([augmentations.IdentityAug(B)])
     out = {}
     old = _rng.set_source(_rng.ScriptedSource())
-    try:
-      with (lu.pipelined_updates() if pipelined else contextlib.nullcontext()):
+
+    def critic_steps():
+        rds = None
         for step, dr in enumerate(draws):
-              src = _rng.ScriptedSource()
-              _rng.set_source(src)
-              src.push("indices", dr["idx"]).push("normal", dr["eps"]).push("subsets", dr["subset"])
-              logs, rds = learning.critic_update(
-                  buffer=buf, agent=agent, target_agent=target, critic_optimizer=critic_opt, encoder_optimizer=enc_opt,
-                  log_alphas=log_alphas, batch_size=B, gamma=0.99, critic_clip=critic_clip, encoder_clip=None,
-                  target_critic_ensemble_n=M, weighted_bellman_temp=None, weight_type=None, pop=False, augmenter=aug,
-                  encoder_lambda=0.0, random_process=None, noise_clip=None, aug_mix=0.0, dr3_coeff=dr3_coeff)
-              for ac, tc in zip(agent.critics, target.critics):
-                  lu.soft_update(tc, ac, 0.005)
-              out[f"loss{step}"] = logs["losses/critic_overall_loss"]
-              if dr3_coeff > 0:
-                  out[f"dr3_{step}"] = logs["dr3_dotproduct_0"]
+            src = _rng.ScriptedSource()
+            _rng.set_source(src)
+            src.push("indices", dr["idx"]).push("normal", dr["eps"]).push("subsets", dr["subset"])
+            logs, rds = learning.critic_update(
+                buffer=buf, agent=agent, target_agent=target, critic_optimizer=critic_opt, encoder_optimizer=enc_opt,
+                log_alphas=log_alphas, batch_size=B, gamma=0.99, critic_clip=critic_clip, encoder_clip=None,
+                target_critic_ensemble_n=M, weighted_bellman_temp=None, weight_type=None, pop=False, augmenter=aug,
+                encoder_lambda=0.0, random_process=None, noise_clip=None, aug_mix=0.0, dr3_coeff=dr3_coeff)
+            for ac, tc in zip(agent.critics, target.critics):
+                lu.soft_update(tc, ac, 0.005)
+            out[f"loss{step}"] = logs["losses/critic_overall_loss"]
+            if dr3_coeff > 0:
+                out[f"dr3_{step}"] = logs["dr3_dotproduct_0"]
+        return rds
+
+    try:
+        with (lu.pipelined_updates() if pipelined else contextlib.nullcontext()):
+            rds = critic_steps()
         src = _rng.ScriptedSource()
         _rng.set_source(src)
         src.push("normal", draws[-1]["eps2"])
