@@ -49,6 +49,14 @@ def _worker(rank, world, port, n_global, out_q):
         assert torch.allclose(da, want), "sum of routed partial gradients == single-process gradient"
         loss = parallel.all_reduce_sum_(torch.tensor([float(hi - lo)]))
         assert float(loss) == n_global
+        # global-norm clipping under sharding (learning.py critic_clip): sum ||g||^2 over every rank's critics
+        g_full = torch.randn(n_global, 7, generator=gen)
+        gsq = parallel.all_reduce_sum_((g_full[lo:hi] ** 2).sum().reshape(1), site="critic_gnorm")
+        assert torch.allclose(gsq, (g_full ** 2).sum().reshape(1))
+        # DR3 under sharding: every rank adds its share N_local / N_global of the mean over the GLOBAL ensemble
+        dots = torch.randn(n_global, B, generator=gen)
+        share = dots[lo:hi].mean().reshape(1) * ((hi - lo) / n_global)
+        assert torch.allclose(parallel.all_reduce_sum_(share, site="dr3_dot"), dots.mean().reshape(1), atol=1e-6)
         out_q.put((rank, lo, hi))
     finally:
         parallel.disable()
