@@ -52,6 +52,17 @@ def test_workspace_plan_cpu():
         lib.conv_encoder_ws_floats(4, 9, 83, 84, 50, 1, ctypes.byref(n))
 
 
+def test_encoder_entry_point_fails_loudly_without_a_device():
+    """No GPU (or bad arguments): an error code and a message, never a silent CPU path."""
+    if torch.cuda.is_available():
+        pytest.skip("this check is for machines without a GPU")
+    from super_sac_b200 import _lib
+
+    ptrs = _lib.host_array(ctypes.c_void_p, [0] * 12)
+    with pytest.raises(_lib.SsacError):
+        _lib.lib().conv_encoder_forward(None, 4, 3, 20, 20, 10, ptrs, None, 0, None, None)
+
+
 class _Native:
     """The encoder through the C ABI with a test-owned workspace (so intermediates can be inspected)."""
 
