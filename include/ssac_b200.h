@@ -97,10 +97,11 @@ int ssac_scatter_fields(const void* staging_dev, void* const* dsts_dev, const in
  * for the leaf index (int64 at staging + tree_idx_off) and priority (float64 at staging + tree_val_off).  `slot`
  * (0..63) names the pinned row: the call records an event behind its copy, and ssac_push_row_wait(slot) blocks the host
  * until that copy has completed (call it before refilling the pinned row); wait_slot >= 0 does that wait for another
- * slot (the one the host fills next) at the end of this call, saving the separate call. */
+ * slot (the one the host fills next) at the end of this call, saving the separate call.  wait_event (nullable
+ * cudaEvent_t): the stream waits for it before anything else (an update in flight that may still read the ring slot). */
 int ssac_push_row(const void* host_row_pinned, void* staging_dev, int64_t row_bytes, int slot, void* const* dsts_dev,
                   const int64_t* nbytes, const int64_t* src_off, int n_fields, double* sum_tree_dev, double* min_tree_dev,
-                  int64_t capacity, int64_t tree_idx_off, int64_t tree_val_off, int wait_slot, void* stream);
+                  int64_t capacity, int64_t tree_idx_off, int64_t tree_val_off, int wait_slot, void* wait_event, void* stream);
 int ssac_push_row_wait(int slot);
 /* Fused pixel gather + DrQ / DrQv2 random shift + uint8 -> fp32 + aug_mix: augmentations.py:165-269,
  * learning_utils.py:193-206.   src u8 [capacity, C, H, W] -> dst f32 [B, C, H, W].

@@ -586,7 +586,7 @@ int ssac_push_row_wait(int slot) {
 
 int ssac_push_row(const void* host_row_pinned, void* staging_dev, int64_t row_bytes, int slot, void* const* dsts,
                   const int64_t* nbytes, const int64_t* src_off, int n_fields, double* sum_tree, double* min_tree,
-                  int64_t capacity, int64_t tree_idx_off, int64_t tree_val_off, int wait_slot, void* stream) {
+                  int64_t capacity, int64_t tree_idx_off, int64_t tree_val_off, int wait_slot, void* wait_event, void* stream) {
   SSAC_REQUIRE(host_row_pinned && staging_dev && row_bytes > 0 && dsts && nbytes && src_off && n_fields > 0 &&
                    n_fields < kMaxGatherArrays, "ssac_push_row: bad args (1..15 fields)");
   SSAC_REQUIRE(slot >= 0 && slot < 64, "ssac_push_row: slot must be in 0..63");
@@ -606,6 +606,10 @@ int ssac_push_row(const void* host_row_pinned, void* staging_dev, int64_t row_by
     SSAC_REQUIRE(dsts[k] && nbytes[k] > 0 && src_off[k] >= 0, "ssac_push_row: bad field");
     a.dst[k] = dsts[k]; a.nbytes[k] = nbytes[k]; a.src_off[k] = src_off[k];
     if (nbytes[k] > mx) mx = nbytes[k];
+  }
+  if (wait_event) {   // (cross-call pipelined updates: the latest gather may still read the ring slot this push overwrites)
+    e = cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)wait_event, 0);
+    if (e != cudaSuccess) { set_error(std::string("ssac_push_row (wait event): ") + cudaGetErrorString(e)); return (int)e; }
   }
   e = cudaMemcpyAsync(staging_dev, host_row_pinned, (size_t)row_bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream);
   if (e == cudaSuccess) e = cudaEventRecord(g_push_events[dev][slot], (cudaStream_t)stream);

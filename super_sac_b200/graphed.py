@@ -132,6 +132,15 @@ def before_push():
         _lib.lib().stream_wait_event(_lib.stream_ptr(), X.gather_ptrs[X.last])
 
 
+def push_wait_event():
+    """The same as ``before_push`` for callers that can hand the event to their own launch (ssac_push_row): the raw handle
+    of the event the caller's stream has to wait for, or None."""
+    X = _auto["cross"]
+    if X is not None and X.last is not None and X.capturing is None:
+        return X.gather_ptrs[X.last]
+    return None
+
+
 def auto_graphs_enabled():
     return _auto["on"]
 

@@ -192,7 +192,7 @@ class NStepReplayBuffer:
                 off += (nb + 15) // 16 * 16
             rb = self._stage.shape[1]
             L.push_row(self._stage.data_ptr() + slot * rb, self._stage_dev.data_ptr() + slot * rb, off, slot, dsts, nbytes, offs, n,
-                       None, None, 0, 0, 0, self._stage_next, _lib.stream_ptr())
+                       None, None, 0, 0, 0, self._stage_next, None, _lib.stream_ptr())
 
     # ---- sampling ----------------------------------------------------------------------------------------------------
     def sample_indices_uniform(self, batch_size, out=None):

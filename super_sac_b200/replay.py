@@ -167,7 +167,7 @@ class ReplayBuffer:
     # --- single-transition fast path: one pinned staging buffer, one H2D copy, one scatter kernel ----------------
     _STAGE_SLOTS = 64
 
-    def _push_one(self, state, action, reward, next_state, done, priority):
+    def _push_one(self, state, action, reward, next_state, done, priority, wait_event=None):
         import ctypes
 
         st = self._storage
@@ -242,17 +242,19 @@ class ReplayBuffer:
         nb = self._stage_bytes
         L.push_row(self._stage_host_ptr + slot * nb, self._stage_dev_ptr + slot * nb, nb, slot, dsts, self._c_nbytes,
                    self._c_offs, self._n_scatter, self._it_sum.data_ptr(), self._it_min.data_ptr(), self._capacity,
-                   lay[-2][0], lay[-1][0], self._stage_next, _lib.stream_ptr())
+                   lay[-2][0], lay[-1][0], self._stage_next, wait_event, _lib.stream_ptr())
         st._max_filled = filled
         st._next_idx = (pos + 1) % st.size
         return np.array([pos])
 
     def push(self, state, action, reward, next_state, done, priorities=None, **kwargs):
-        graphed.before_push()   # (cross-call pipelined updates: the latest gather may still read the slot this overwrites)
         self._ensure_storage(state, action)
         if np.asarray(action).ndim == 1 and (priorities is None or np.ndim(priorities) == 0):
             p = self._max_priority if priorities is None else float(priorities)
-            return self._push_one(state, action, reward, next_state, done, p**self.alpha)
+            # (cross-call pipelined updates: the latest gather may still read the slot this overwrites -- the push's own
+            # launch waits for it, one C call instead of two)
+            return self._push_one(state, action, reward, next_state, done, p**self.alpha, graphed.push_wait_event())
+        graphed.before_push()
         R = self._storage.add(state, action, reward, next_state, done)
         self._n_filled_dev.fill_(len(self._storage))
         if priorities is None:
