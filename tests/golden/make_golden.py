@@ -494,9 +494,155 @@ def run_encoder_case():
     np.savez_compressed(path, **out)
     print(f"wrote {path}  ({os.path.getsize(path)/1024:.1f} KiB)")
 
+def _last_of(m):
+    return m.out if hasattr(m, "out") else (m.act_p if hasattr(m, "act_p") else m.fc3)
+
+
+def _stack(modules, grad=False):
+    get = (lambda p: p.grad.detach().numpy().copy()) if grad else (lambda p: p.detach().numpy().copy())
+    return {
+        "W1": np.stack([get(m.fc1.weight) for m in modules]), "b1": np.stack([get(m.fc1.bias) for m in modules]),
+        "W2": np.stack([get(m.fc2.weight) for m in modules]), "b2": np.stack([get(m.fc2.bias) for m in modules]),
+        "W3": np.stack([get(_last_of(m).weight) for m in modules]), "b3": np.stack([get(_last_of(m).bias) for m in modules]),
+    }
+
+
+def run_discrete_case(name, cfg):
+    """SAC-Discrete: critic_update(discrete=True) + Polyak, online_actor_update(discrete=True) and
+    alpha_update(discrete=True) of the unmodified reference, driven as main.py:380-414 / :491-543 drive them.  The only
+    random draws on this path are the replay indices (replay.py:122) and the target-critic subset (agent.py:29)."""
+    rng = np.random.default_rng(cfg.get("seed", 0))
+    torch.manual_seed(cfg.get("seed", 0))
+    E, N, M = cfg["E"], cfg["N"], cfg["M"]
+    S, A, H, B = cfg["S"], cfg["A"], cfg["H"], cfg["B"]
+    popart_on = cfg.get("popart", False)
+    agent = ssac.Agent(act_space_size=A, encoder=IdentityEncoder(S), actor_network_cls=rnets.mlps.DiscreteActor,
+                       critic_network_cls=rnets.mlps.DiscreteCritic, discrete=True, ensemble_size=E, num_critics=N,
+                       hidden_size=H, auto_rescale_targets=popart_on)
+    for m in critic_nets(agent) + list(agent.actors):
+        for p in m.parameters():
+            if p.dim() == 1:
+                p.data.add_(0.05 * torch.randn_like(p))
+            elif p.shape[0] == A:
+                p.data.mul_(4.0)   # spread the policies / Q rows out (the orthogonal init leaves them near-uniform)
+    if popart_on and cfg.get("popart_warm", False):
+        for p in agent.popart:
+            p._t = 1500
+            p.mu = torch.tensor([0.3])
+            p.nu = torch.tensor([1.7])
+            p.w = torch.tensor([0.9])
+            p.b = torch.tensor([0.1])
+    target = copy.deepcopy(agent)
+    for m in critic_nets(target):
+        for p in m.parameters():
+            p.data.add_(0.01 * torch.randn_like(p))
+
+    nbuf = cfg.get("nbuf", 64)
+    s = rng.standard_normal((nbuf, S)).astype(np.float32)
+    a = rng.integers(0, A, size=(nbuf, 1)).astype(np.float32)
+    r = rng.standard_normal((nbuf,)).astype(np.float32)
+    s1 = rng.standard_normal((nbuf, S)).astype(np.float32)
+    d = (rng.uniform(size=(nbuf,)) < 0.1).astype(np.float32)
+    buffer = rreplay.ReplayBuffer(size=nbuf + 8)
+    buffer.load_experience({"obs": s}, a, r, {"obs": s1}, d)
+
+    out = {"cfg": np.array(repr(cfg))}
+    put(out, "buffer", dict(s=s, a=a, r=r, s1=s1, d=d))
+    put(out, "init/actors", _stack(agent.actors))
+    put(out, "init/critics", _stack(critic_nets(agent)))
+    put(out, "init/target_critics", _stack(critic_nets(target)))
+    put(out, "init/popart", popart_state(agent))
+
+    critic_opt = torch.optim.Adam(chain(*(c.parameters() for c in agent.critics)), lr=cfg.get("critic_lr", 3e-4),
+                                  weight_decay=cfg.get("critic_l2", 0.0), betas=(0.9, 0.999))
+    actor_opt = torch.optim.Adam(chain(*(ac.parameters() for ac in agent.actors)), lr=cfg.get("actor_lr", 3e-4),
+                                 betas=(0.9, 0.999))
+    enc_opt = torch.optim.Adam(agent.encoder.parameters(), lr=1e-4, betas=(0.9, 0.999))
+    init_alpha = cfg.get("init_alpha", 0.1)
+    log_alphas, alpha_opts = [], []
+    for _ in range(E):
+        la = torch.Tensor([math.log(init_alpha)])
+        la.requires_grad = True
+        log_alphas.append(la)
+        alpha_opts.append(torch.optim.Adam([la], lr=cfg.get("alpha_lr", 1e-4), betas=(0.5, 0.999)))
+    augmenter = raug.AugmentationSequence([raug.IdentityAug(B)])
+    target_entropy = -math.log(1.0 / A) * 0.98   # main.py:240-241
+
+    rec = {}
+    o_td, o_bw = lu.compute_td_targets, lu.compute_backup_weights
+
+    def td_rec(*a_, **k_):
+        res = o_td(*a_, **k_)
+        rec.setdefault("td", []).append(res[0].detach().numpy().copy())
+        return res
+
+    def bw_rec(*a_, **k_):
+        res = o_bw(*a_, **k_)
+        rec.setdefault("w", []).append(res.detach().numpy().copy() if torch.is_tensor(res) else np.array(res, dtype=np.float32))
+        return res
+
+    lu.compute_td_targets, lu.compute_backup_weights = td_rec, bw_rec
+    try:
+        replay_dicts = None
+        for t in range(cfg["steps"]):
+            idx = rng.integers(0, nbuf, size=(E, B))
+            subsets = [list(rng.permutation(N)[:M]) for _ in range(E)]
+            put(out, f"step{t}/rand", dict(idx=idx, subsets=np.array(subsets)))
+            rec.clear()
+            with rh.injected(randint=list(idx), subsets=subsets) as q:
+                logs, replay_dicts = learning.critic_update(
+                    buffer=buffer, agent=agent, target_agent=target, critic_optimizer=critic_opt,
+                    encoder_optimizer=enc_opt, log_alphas=log_alphas, batch_size=B, gamma=cfg.get("gamma", 0.99),
+                    critic_clip=cfg.get("critic_clip"), encoder_clip=None, target_critic_ensemble_n=M,
+                    weighted_bellman_temp=cfg.get("weight_temp"), weight_type=cfg.get("weight_type"),
+                    pop=cfg.get("pop", False), augmenter=augmenter, encoder_lambda=0.0, aug_mix=0.0, discrete=True,
+                    random_process=None, noise_clip=None, per=False, update_priorities=False,
+                    dr3_coeff=cfg.get("dr3_coeff", 0.0))
+                assert not q["randint"].items and not q["subsets"].items
+            put(out, f"step{t}/td_target", {str(i): v for i, v in enumerate(rec["td"])})
+            put(out, f"step{t}/weights", {str(i): v for i, v in enumerate(rec["w"])})
+            put(out, f"step{t}/critic_grads", _stack(critic_nets(agent), grad=True))
+            put(out, f"step{t}/logs", {k.replace("/", "|"): float(v) for k, v in logs.items()})
+            for ac, tc in zip(agent.critics, target.critics):
+                lu.soft_update(tc, ac, cfg.get("tau", 0.005))
+            put(out, f"step{t}/critics", _stack(critic_nets(agent)))
+            put(out, f"step{t}/target_critics", _stack(critic_nets(target)))
+            put(out, f"step{t}/popart", popart_state(agent))
+    finally:
+        lu.compute_td_targets, lu.compute_backup_weights = o_td, o_bw
+
+    alogs = learning.online_actor_update(
+        buffer=buffer, agent=agent, pop=cfg.get("pop", False), actor_optimizer=actor_opt, log_alphas=log_alphas,
+        batch_size=B, clip=cfg.get("actor_clip"), random_process=None, noise_clip=None, augmenter=augmenter, aug_mix=0.0,
+        premade_replay_dicts=replay_dicts, per=False, discrete=True, use_baseline=False)
+    put(out, "actor/grads", _stack(agent.actors, grad=True))
+    put(out, "actor/actors", _stack(agent.actors))
+    put(out, "actor/logs", {k.replace("/", "|"): float(v) for k, v in alogs.items()})
+    llogs = learning.alpha_update(
+        buffer=buffer, agent=agent, optimizers=alpha_opts, batch_size=B, log_alphas=log_alphas, augmenter=augmenter,
+        aug_mix=0.0, target_entropy=target_entropy, premade_replay_dicts=replay_dicts, discrete=True)
+    put(out, "alpha/log_alphas", {str(i): la.detach().numpy().copy() for i, la in enumerate(log_alphas)})
+    put(out, "alpha/logs", {k.replace("/", "|"): float(v) for k, v in llogs.items()})
+    out["alpha/target_entropy"] = np.array(target_entropy)
+    path = os.path.join(HERE, f"update_{name}.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}  ({os.path.getsize(path)/1024:.1f} KiB)")
+
+
+DISCRETE_CASES = {
+    # SAC-Discrete with a REDQ-style target subset (2 of 3 critics), DR3 on
+    "discrete_sac": dict(E=1, N=3, M=2, S=6, A=5, H=32, B=16, steps=2, dr3_coeff=0.01, critic_clip=40.0, seed=11),
+    # ensemble of 2 members: sunrise Bellman weights on gathered Q(s, a), warm PopArt, actor clipping
+    "discrete_sunrise_popart": dict(E=2, N=2, M=2, S=4, A=3, H=32, B=16, steps=2, weight_type="sunrise",
+                                    weight_temp=20.0, popart=True, pop=True, popart_warm=True, actor_clip=40.0, seed=12),
+}
+
 
 if __name__ == "__main__":
     only = set(sys.argv[1:])   # e.g. ``python make_golden.py rad`` regenerates one fixture
+    for name, cfg in DISCRETE_CASES.items():
+        if not only or name in only:
+            run_discrete_case(name, cfg)
     for name, cfg in UPDATE_CASES.items():
         if not only or name in only:
             run_update_case(name, cfg)

@@ -12,6 +12,7 @@ from oracle import update_oracle as uo
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 UPDATE_CASES = ["sac", "redq", "sunrise_popart", "td3_encoder", "softmax_dr3"]
+DISCRETE_CASES = ["discrete_sac", "discrete_sunrise_popart"]
 
 
 def load(name):
@@ -81,6 +82,20 @@ def oracle_agents(fx):
     if cfg.get("encoder") == "shared":
         agent.encoder = encoder_from(fx, "init/encoder", S)
         target.encoder = encoder_from(fx, "init/target_encoder", S)
+    return cfg, agent, target
+
+
+def discrete_oracle_agents(fx):
+    from oracle import discrete_oracle as do
+
+    cfg = cfg_of(fx)
+    E, N, S, A, H = cfg["E"], cfg["N"], cfg["S"], cfg["A"], cfg["H"]
+    agent = do.DiscreteOracleAgent(E, N, S, A, H)
+    agent.actors = uo.MLPStack.from_arrays(sub(fx, "init/actors"))
+    agent.critics = uo.MLPStack.from_arrays(sub(fx, "init/critics"))
+    agent.popart = popart_from(fx, "init/popart", E)
+    target = agent.clone()
+    target.critics = uo.MLPStack.from_arrays(sub(fx, "init/target_critics"))
     return cfg, agent, target
 
 

@@ -10,6 +10,7 @@ import torch
 
 import golden_util as gu
 from oracle import aug_oracle as ao
+from oracle import discrete_oracle as do
 from oracle import replay_oracle as ro
 from oracle import update_oracle as uo
 
@@ -90,6 +91,50 @@ def test_update_oracle_matches_reference(case):
         for i, la in enumerate(log_alphas):
             gu.assert_close(la.numpy(), fx[f"alpha/log_alphas/{i}"], 1e-6, 1e-7, f"log_alpha[{i}]")
         _cmp_logs(logs, gu.sub(fx, "alpha/logs"), "alpha")
+
+
+@pytest.mark.parametrize("case", gu.DISCRETE_CASES)
+def test_discrete_oracle_matches_reference(case):
+    """SAC-Discrete: the restated discrete branches against the unmodified reference's outputs."""
+    torch.set_num_threads(1)
+    fx = gu.load("update_" + case)
+    cfg, agent, target = gu.discrete_oracle_agents(fx)
+    E = cfg["E"]
+    hp = gu.hp_from(cfg)
+    log_alphas = gu.log_alphas_from(cfg)
+    critic_opt = uo.Adam(agent.critics.tensors(), lr=cfg.get("critic_lr", 3e-4))
+    actor_opt = uo.Adam(agent.actors.tensors(), lr=cfg.get("actor_lr", 3e-4))
+    alpha_opts = [uo.Adam([la], lr=cfg.get("alpha_lr", 1e-4), betas=(0.5, 0.999)) for la in log_alphas]
+    batches = None
+    for t in range(cfg["steps"]):
+        idx, subsets = fx[f"step{t}/rand/idx"], fx[f"step{t}/rand/subsets"]
+        batches = [gu.batch_from(fx, idx[i]) for i in range(E)]
+        logs, aux = do.critic_update(agent, target, batches, [[int(x) for x in subsets[i]] for i in range(E)], hp,
+                                     log_alphas, critic_opt)
+        for i in range(E):
+            gu.assert_close(aux["td_target"][i].numpy(), fx[f"step{t}/td_target/{i}"], RTOL, ATOL, f"step{t} td_target[{i}]")
+            w = aux["weights"][i]
+            w = w.numpy() if torch.is_tensor(w) else np.array(w, dtype=np.float32)
+            gu.assert_close(w, fx[f"step{t}/weights/{i}"], RTOL, ATOL, f"step{t} weights[{i}]")
+        _cmp_stack(aux["grads"], gu.sub(fx, f"step{t}/critic_grads"), f"step{t} critic_grads", rtol=1e-4, atol=1e-7)
+        _cmp_logs(logs, gu.sub(fx, f"step{t}/logs"), f"step{t}")
+        uo.soft_update(target.critics.tensors(), agent.critics.tensors(), cfg.get("tau", 0.005))
+        _cmp_stack(agent.critics, gu.sub(fx, f"step{t}/critics"), f"step{t} critics", rtol=1e-5, atol=3e-4 * 2e-2)
+        _cmp_stack(target.critics, gu.sub(fx, f"step{t}/target_critics"), f"step{t} target_critics", rtol=1e-5, atol=1e-6)
+        want_pop = gu.sub(fx, f"step{t}/popart")
+        for i, p in enumerate(agent.popart):
+            if p is None:
+                continue
+            for n in ("mu", "nu", "w", "b"):
+                gu.assert_close(getattr(p, n).numpy(), want_pop[f"{i}/{n}"], 1e-5, 1e-7, f"step{t} popart[{i}].{n}")
+    logs, aux = do.online_actor_update(agent, batches, hp, log_alphas, actor_opt)
+    _cmp_stack(aux["grads"], gu.sub(fx, "actor/grads"), "actor grads", rtol=1e-4, atol=1e-7)
+    _cmp_stack(agent.actors, gu.sub(fx, "actor/actors"), "actors", rtol=1e-5, atol=3e-4 * 2e-2)
+    _cmp_logs(logs, gu.sub(fx, "actor/logs"), "actor")
+    logs = do.alpha_update(agent, batches, log_alphas, alpha_opts, float(fx["alpha/target_entropy"]))
+    for i, la in enumerate(log_alphas):
+        gu.assert_close(la.numpy(), fx[f"alpha/log_alphas/{i}"], 1e-6, 1e-7, f"log_alpha[{i}]")
+    _cmp_logs(logs, gu.sub(fx, "alpha/logs"), "alpha")
 
 
 def test_replay_oracle_matches_reference():
