@@ -355,6 +355,32 @@ int ssac_advantage(const float* q_pi_dev, int n, const float* q_data_dev, int B,
 /* min over the N rows of q [N,B] with optional PopArt affine (agent.py:37-38, adv_estimator.py:30-35). */
 int ssac_min_over_nets(const float* q_dev, int N, int B, const float* popart_dev, float* out_dev, void* stream);
 
+/* ---- SAC-Discrete heads: SURVEY 8f N4 (learning_utils.py:322-328, learning.py:84-92, :252-253, :382-390) ---------- */
+/* The discrete-action branches run the same grouped MLP launches (ssac_mlp_forward / _backward with O = number of
+ * actions A); these entry points are the categorical-policy arithmetic around them.  logits [B,A] row-major = the
+ * actor's output (Categorical(logits=...), nets/mlps.py:147-148); actions are stored as floats holding the index
+ * (replay row [B,1], read as (int)act[b], clamped to [0,A)).
+ *
+ * ssac_discrete_value (learning_utils.py:322-328): q_t [M,B,A] target-critic rows of the REDQ subset;
+ *   v[b] = sum_a p_a (min_M q_t[.,b,a] - exp(log_alpha) log p_a);  ent_dev[0] += mean_{b,a} exp(log_alpha) log p_a
+ *   (nullable; the caller zeroes it).  v then goes through ssac_td_target(M = 1, logp = NULL) for PopArt / r / d. */
+int ssac_discrete_value(const float* logits_dev, const float* q_t_dev, int M, int B, int A, const float* log_alpha_dev,
+                        float* v_dev, float* ent_dev, void* stream);
+/* out[g,b] = q[g,b,act[b]]  (q.gather(-1, a.long()): learning_utils.py:373-376 for the sunrise weights). */
+int ssac_discrete_gather_q(const float* q_dev, const float* act_dev, int G, int B, int A, float* out_dev, void* stream);
+/* ssac_critic_loss_seed on the gathered Q(s, a_b) (learning.py:90-98): q [N,B,A]; dy [N,B,A] receives the seed at
+ * column act[b] and zeros elsewhere (the dense output gradient ssac_mlp_backward takes); loss_dev as there. */
+int ssac_discrete_critic_loss_seed(const float* q_dev, int N, int B, int A, const float* act_dev, const float* y_dev,
+                                   const float* w_dev, const float* imp_dev, const float* popart_dev, int pop, int E,
+                                   int n_total, float* dy_dev, float* loss_dev, void* stream);
+/* Actor loss (learning.py:382-390, :408-409): q [N,B,A] online critics on s; vals = popart(min_N q) if pop;
+ * f[b] = sum_a p_a (vals_a - exp(log_alpha) log p_a); loss_dev[0] += -(1/E) mean_b f;
+ * dlogits[b,k] = -(1/(E B)) p_k ((vals_k - alpha log p_k) - f[b]). */
+int ssac_discrete_actor_seed(const float* logits_dev, const float* q_dev, int N, int B, int A, const float* log_alpha_dev,
+                             const float* popart_dev, int pop, int E, float* dlogits_dev, float* loss_dev, void* stream);
+/* out[b] = sum_a p_a log p_a (learning.py:252-253; feeds ssac_alpha_step as its logp). */
+int ssac_discrete_neg_entropy(const float* logits_dev, int B, int A, float* out_dev, void* stream);
+
 /* ---- ensemble sharding over NVLink peer memory: SURVEY 8e (no counterpart in the reference: it is single-device) ---- */
 /* The exchanges of the sharded learner (target Q rows, Q(s,pi(s)) rows, dL/da partials, SUNRISE batches / values) as two
  * small kernels over SYMMETRIC buffers (one allocation of 2 x half_bytes per rank, mapped into every peer; the mappings

@@ -20,7 +20,9 @@ _ALIGN = 32  # floats (128 B)
 
 
 def _last_linear(module):
-    return module.out if hasattr(module, "out") else module.fc3
+    if hasattr(module, "out"):
+        return module.out
+    return module.act_p if hasattr(module, "act_p") else module.fc3   # act_p: DiscreteActor (nets/mlps.py:137)
 
 
 def supported_mlp(module):

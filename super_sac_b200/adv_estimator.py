@@ -11,15 +11,15 @@ class AdvantageEstimator(nn.Module):
                  discrete=False):
         super().__init__()
         assert continuous_method in ["mean", "max"]
-        if discrete:
-            raise NotImplementedError("discrete actions are out of scope")
+        assert discrete_method in ["indirect"]   # adv_estimator.py:41-43: 'direct' raises in the reference too
         # plain attributes (not sub-modules): the Agent owns these objects
         object.__setattr__(self, "encoder", encoder)
         object.__setattr__(self, "actors", actors)
         object.__setattr__(self, "critics", critics)
         object.__setattr__(self, "popart", popart)
         self.cont_method = continuous_method
-        self.discrete = False
+        self.discrete_method = discrete_method
+        self.discrete = bool(discrete)
         self._agent = None
 
     def bind(self, agent):
@@ -30,6 +30,9 @@ class AdvantageEstimator(nn.Module):
 
         if self._agent is None:
             raise RuntimeError("AdvantageEstimator must be created by an Agent")
+        if self.discrete:
+            raise NotImplementedError("the discrete (indirect) advantage, i.e. offline / AFBC updates of a discrete agent, "
+                                      "is not implemented; the online SAC-Discrete updates are (discrete.py)")
         rd = {"primary_batch": (obs, action, None, None, None)}
         adv, _, _ = lu._advantage(self._agent, rd, ensemble_idx, n=n)
         return adv.unsqueeze(-1)

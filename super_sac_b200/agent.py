@@ -127,12 +127,11 @@ class Agent:
                  num_critics=2, ucb_bonus=0.0, hidden_size=256, auto_rescale_targets=True, log_std_low=-10.0,
                  log_std_high=2.0, adv_method=None, beta_dist=False):
         assert hasattr(encoder, "embedding_dim")
-        if discrete:
-            raise NotImplementedError("discrete-action agents are out of scope of the B200 update path (SURVEY 8f N4)")
         if beta_dist:
             raise NotImplementedError("beta-distribution policies are out of scope (unused by every shipped config)")
-        actor_kwargs = dict(state_size=encoder.embedding_dim, action_size=act_space_size, hidden_size=hidden_size,
-                            log_std_low=log_std_low, log_std_high=log_std_high, dist_impl="pyd")
+        actor_kwargs = dict(state_size=encoder.embedding_dim, action_size=act_space_size, hidden_size=hidden_size)
+        if not discrete:   # agent.py:76-83
+            actor_kwargs.update(log_std_low=log_std_low, log_std_high=log_std_high, dist_impl="pyd")
         critic_kwargs = dict(state_size=encoder.embedding_dim, action_size=act_space_size, hidden_size=hidden_size)
 
         self.encoder = encoder
@@ -146,13 +145,24 @@ class Agent:
         self.log_std_low, self.log_std_high = log_std_low, log_std_high
         self.deterministic = getattr(self.actors[0], "dist_impl", "pyd") == "deterministic"
         self.popart = [popart.PopArtLayer() if auto_rescale_targets else False for _ in range(ensemble_size)]
-        self.adv_estimator = adv_estimator.AdvantageEstimator(
-            encoder=self.encoder, actors=self.actors, critics=self.critics, popart=self.popart, discrete=False,
-            continuous_method=adv_method if adv_method else "mean")
+        if discrete:   # agent.py:103-113 (the estimator object exists; its discrete forward is not implemented)
+            self.adv_estimator = adv_estimator.AdvantageEstimator(
+                encoder=self.encoder, actors=self.actors, critics=self.critics, popart=self.popart, discrete=True,
+                discrete_method=adv_method if adv_method else "indirect")
+            self.inverse_model = nets.mlps.DiscreteInverseModel(**actor_kwargs)
+            c0, a0 = self.critics[0].nets[0], self.actors[0]
+            if (c0.fc1.in_features != encoder.embedding_dim or c0.out.out_features != act_space_size
+                    or _arena._last_linear(a0).out_features != act_space_size):
+                raise NotImplementedError("discrete agents need S -> H -> H -> A actor and critic networks "
+                                          "(nets.mlps.DiscreteActor / DiscreteCritic)")
+        else:
+            self.adv_estimator = adv_estimator.AdvantageEstimator(
+                encoder=self.encoder, actors=self.actors, critics=self.critics, popart=self.popart, discrete=False,
+                continuous_method=adv_method if adv_method else "mean")
+            self.inverse_model = nets.mlps.ContinuousInverseModel(**actor_kwargs)
         self.adv_estimator.bind(self)
-        self.inverse_model = nets.mlps.ContinuousInverseModel(**actor_kwargs)
         self.contrastive_model = nets.mlps.ContrastiveModel(state_size=encoder.embedding_dim, hidden_size=hidden_size)
-        self.discrete = False
+        self.discrete = bool(discrete)
         self.ucb_bonus = ucb_bonus
         self._critic_arena = self._actor_arena = None
         self._pack(self.critics[0]._arena.device)
@@ -162,7 +172,7 @@ class Agent:
         """(Re)build the two arenas from the modules' current values and bind every Parameter to them."""
         E, N = self.ensemble_size, self.num_critics
         c0 = self.critics[0].nets[0]
-        ca = _arena.MLPArena(E * N, c0.fc1.in_features, c0.fc1.out_features, 1, device)
+        ca = _arena.MLPArena(E * N, c0.fc1.in_features, c0.fc1.out_features, c0.out.out_features, device)
         ca.bind([net for c in self.critics for net in c.nets])
         for i, c in enumerate(self.critics):
             c._adopt(ca, i * N)
@@ -196,8 +206,8 @@ class Agent:
                 continue
             setattr(new, k, copy.deepcopy(v, memo))
         new.adv_estimator = adv_estimator.AdvantageEstimator(
-            encoder=new.encoder, actors=new.actors, critics=new.critics, popart=new.popart, discrete=False,
-            continuous_method=self.adv_estimator.cont_method)
+            encoder=new.encoder, actors=new.actors, critics=new.critics, popart=new.popart, discrete=self.discrete,
+            discrete_method=self.adv_estimator.discrete_method, continuous_method=self.adv_estimator.cont_method)
         new.adv_estimator.bind(new)
         new._pack(self._critic_arena.device)
         return new
@@ -255,7 +265,30 @@ class Agent:
 
     def _process_act(self, act, num_envs=1):
         act = act.squeeze(0) if num_envs == 1 else act
+        if self.discrete:   # action indices (agent.py:323-327)
+            return act.cpu().numpy()
         return act.clamp(-1.0, 1.0).cpu().numpy()
+
+    # discrete acting (agent.py:204-221, :262-320): B = num_envs rows through the module views of the arenas
+    def _discrete_forward(self, s_rep):
+        probs = torch.stack([actor(s_rep).probs for actor in self.actors], dim=0).mean(0)
+        return torch.argmax(probs, dim=-1, keepdim=True)
+
+    def _discrete_sample(self, s_rep, num_envs):
+        if self.ucb_bonus > 0:
+            dists = [actor(s_rep) for actor in self.actors]
+            cands = torch.stack([d.sample() for d in dists], dim=0).unsqueeze(-1)          # [E, envs, 1]
+            act_dist = random.choice(dists)
+            q = torch.stack([critic(s_rep) for critic in self.critics], dim=0)              # [E_c, envs, A]
+            acts = []
+            for e in range(cands.shape[1]):   # per environment, as agent.py:293-306
+                c_e = cands[:, e, 0]                                                        # [E]
+                q_e = q[:, e, :][:, c_e]                                                    # [E_c, E]
+                ucb = q_e.mean(0) + self.ucb_bonus * q_e.std(0)
+                acts.append(cands[torch.argmax(ucb), e])
+            return torch.stack(acts, dim=0), act_dist
+        act_dist = random.choice(self.actors)(s_rep)
+        return act_dist.sample().unsqueeze(-1), act_dist
 
     def _encode(self, obs, rolling):
         return self.encoder.forward_rolling(obs) if rolling else self.encoder(obs)
@@ -284,7 +317,9 @@ class Agent:
         self.eval()
         with torch.no_grad():
             s_rep = self._encode(state, rolling)
-            if self._kernel_path(s_rep):
+            if self.discrete:
+                act = self._discrete_forward(s_rep)
+            elif self._kernel_path(s_rep):
                 zero = None if self.deterministic else torch.zeros((s_rep.shape[0], self.act_space_size), dtype=torch.float32,
                                                                    device=s_rep.device)
                 acts = [self._policy_rows(s_rep, i, zero) for i in range(self.ensemble_size)]
@@ -307,7 +342,9 @@ class Agent:
             s_rep = self._encode(obs, rolling)
             kernels = self._kernel_path(s_rep) and not return_dist
             act_dist = None
-            if kernels:
+            if self.discrete:
+                act, act_dist = self._discrete_sample(s_rep, num_envs)
+            elif kernels:
                 from . import learning_utils as lu
 
                 E, N, A = self.ensemble_size, self.num_critics, self.act_space_size

@@ -12,7 +12,7 @@ import random
 
 import torch
 
-from . import _arena, _encoder_opt, _lib, _logs, _ops, _rng, graphed, parallel
+from . import _arena, _encoder_opt, _lib, _logs, _ops, _rng, discrete as _discrete, graphed, parallel
 from . import learning_utils as lu
 
 
@@ -88,8 +88,11 @@ def _critic_update_impl(buffer, agent, target_agent, critic_optimizer, encoder_o
                         critic_clip, encoder_clip, target_critic_ensemble_n, weighted_bellman_temp, weight_type, pop,
                         augmenter, encoder_lambda, random_process, noise_clip, aug_mix=0.75, discrete=False, per=False,
                         update_priorities=False, dr3_coeff=0.0):
-    if discrete:
-        raise NotImplementedError("discrete actions are out of scope")
+    if discrete:   # SAC-Discrete (learning.py:84-92, learning_utils.py:322-328): discrete.py
+        return _discrete.critic_update(buffer, agent, target_agent, critic_optimizer, encoder_optimizer, log_alphas,
+                                       batch_size, gamma, critic_clip, encoder_clip, target_critic_ensemble_n,
+                                       weighted_bellman_temp, weight_type, pop, augmenter, encoder_lambda, aug_mix, per,
+                                       update_priorities, dr3_coeff)
     if encoder_lambda:
         raise NotImplementedError("encoder invariance regulariser (lambda = 0 in every shipped config) is out of scope")
     ca = agent._critic_arena
@@ -417,8 +420,11 @@ def online_actor_update(buffer, agent, pop, actor_optimizer, log_alphas, batch_s
 def _online_actor_update_impl(buffer, agent, pop, actor_optimizer, log_alphas, batch_size, clip, random_process,
                               noise_clip, augmenter, aug_mix, premade_replay_dicts=None, per=False, discrete=False,
                               use_baseline=False):
-    if discrete or use_baseline:
-        raise NotImplementedError("discrete actions / advantage baselines are out of scope")
+    if use_baseline:
+        raise NotImplementedError("advantage baselines are out of scope")
+    if discrete:   # learning.py:382-390
+        return _discrete.online_actor_update(buffer, agent, pop, actor_optimizer, log_alphas, batch_size, clip, augmenter,
+                                             aug_mix, premade_replay_dicts, per)
     lu.pipeline_barrier()
     aa, ca = agent._actor_arena, agent._critic_arena
     dev = aa.device
@@ -554,8 +560,9 @@ class _AlphaState:
 
 def alpha_update(buffer, agent, optimizers, batch_size, log_alphas, augmenter, aug_mix, target_entropy,
                  premade_replay_dicts, discrete):
-    if discrete:
-        raise NotImplementedError("discrete actions are out of scope")
+    if discrete:   # learning.py:252-253
+        return _discrete.alpha_update(buffer, agent, optimizers, batch_size, log_alphas, augmenter, aug_mix, target_entropy,
+                                      premade_replay_dicts, _AlphaState)
     lu.pipeline_barrier()
     dev = agent._actor_arena.device
     L, stream = _lib.lib(), _lib.stream_ptr()

@@ -714,6 +714,11 @@ def compute_td_targets(logs, replay_dict, agent, target_agent, ensemble_idx, ens
     Returns ``td_target [B,1], (s1_rep, a_s1)``.  ``_fuse_into_loss`` (critic_update only, no PopArt): the final
     reduction is left to the critic loss kernel -- the returned tensor is filled by that launch and carries the operands
     as ``_ssac_pending``."""
+    if discrete:   # learning_utils.py:322-328
+        from . import discrete as _discrete
+
+        return _discrete.compute_td_targets(logs, replay_dict, agent, target_agent, ensemble_idx, ensemble_n, log_alphas, pop,
+                                            gamma)
     if discrete:
         raise NotImplementedError("discrete actions are out of scope")
     dlogs, user_logs = _logs.as_device_logs(logs, agent._critic_arena.device)
@@ -797,8 +802,10 @@ def compute_backup_weights(logs, replay_dict, agent, target_agent, weight_type, 
     (member-sharded ensembles, parallel.enable_member_sharding)."""
     if weight_type is None or weight_temp is None or parallel.members_global(agent.ensemble_size) == 1:
         return 1.0
-    if discrete:
-        raise NotImplementedError("discrete actions are out of scope")
+    if discrete:   # learning_utils.py:373-376
+        from . import discrete as _discrete
+
+        return _discrete.compute_backup_weights(logs, replay_dict, agent, target_agent, weight_type, weight_temp, batch_size)
     dlogs, user_logs = _logs.as_device_logs(logs, agent._critic_arena.device)
     o, a, _, o1, _ = replay_dict["primary_batch"]
     S, A = _dims(agent)

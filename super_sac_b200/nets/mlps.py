@@ -1,4 +1,4 @@
-"""The 3-Linear MLP heads of the agent (reference nets/mlps.py:11-41, :78-93, :113-129).
+"""The 3-Linear MLP heads of the agent (reference nets/mlps.py:11-41, :78-93, :113-129; discrete: :132-185).
 
 Layer names (fc1, fc2, out / fc3) and shapes match the reference so ``state_dict()`` keys are interchangeable.
 Inside an ``Agent`` the Parameters of these modules are views into one flat fp32 arena (see _arena.py) and the
@@ -80,6 +80,76 @@ class ContinuousInverseModel(nn.Module):
         x = F.relu(self.fc1(torch.cat((state, next_state), dim=-1)))
         x = F.relu(self.fc2(x))
         return distributions.create_tanh_normal(self.fc3(x), self.log_std_low, self.log_std_high)
+
+
+class _Categorical:
+    """What the acting path and the reference API read from Categorical(logits=...) (nets/mlps.py:147-148):
+    normalised ``logits``, ``probs``, ``sample()`` / ``log_prob`` / ``entropy``.  The update path never builds it: the
+    softmax and its gradient live in the ssac_discrete_* kernels."""
+
+    def __init__(self, logits):
+        self.logits = logits - logits.logsumexp(dim=-1, keepdim=True)
+        self.probs = torch.softmax(logits, dim=-1)
+
+    def sample(self):
+        return torch.multinomial(self.probs.reshape(-1, self.probs.shape[-1]), 1).reshape(self.probs.shape[:-1])
+
+    def log_prob(self, value):
+        return self.logits.gather(-1, value.long().unsqueeze(-1)).squeeze(-1)
+
+    def entropy(self):
+        return -(self.probs * self.logits).sum(-1)
+
+
+class DiscreteActor(nn.Module):
+    """S -> H -> H -> A logits (nets/mlps.py:132-149); the last layer keeps the reference's name ``act_p``."""
+
+    def __init__(self, state_size, action_size, hidden_size=256):
+        super().__init__()
+        self.fc1 = nn.Linear(state_size, hidden_size)
+        self.fc2 = nn.Linear(hidden_size, hidden_size)
+        self.act_p = nn.Linear(hidden_size, action_size)
+        self.apply(weight_init)
+
+    def forward(self, state):
+        x = F.relu(self.fc1(state))
+        x = F.relu(self.fc2(x))
+        return _Categorical(self.act_p(x))
+
+
+class DiscreteCritic(nn.Module):
+    """S -> H -> H -> A action values (nets/mlps.py:170-185)."""
+
+    def __init__(self, state_size, action_size, hidden_size=300):
+        super().__init__()
+        self.fc1 = nn.Linear(state_size, hidden_size)
+        self.fc2 = nn.Linear(hidden_size, hidden_size)
+        self.out = nn.Linear(hidden_size, action_size)
+        self.features = None
+        self.apply(weight_init)
+
+    def forward(self, state):
+        x = F.relu(self.fc1(state))
+        x = F.relu(self.fc2(x))
+        self.features = x
+        return self.out(x)
+
+
+class DiscreteInverseModel(nn.Module):
+    """Kept so a discrete Agent exposes ``inverse_model`` like the reference (nets/mlps.py:152-167); the
+    Markov-abstraction update that trains it is out of scope."""
+
+    def __init__(self, state_size, action_size, hidden_size, **kwargs):
+        super().__init__()
+        self.fc1 = nn.Linear(state_size * 2, hidden_size)
+        self.fc2 = nn.Linear(hidden_size, hidden_size)
+        self.act_p = nn.Linear(hidden_size, action_size)
+        self.apply(weight_init)
+
+    def forward(self, state, next_state):
+        x = F.relu(self.fc1(torch.cat((state, next_state), dim=-1)))
+        x = F.relu(self.fc2(x))
+        return _Categorical(self.act_p(x))
 
 
 class ContrastiveModel(nn.Module):
