@@ -242,3 +242,113 @@ def test_reference_training_loop_runs_on_the_drop_in_with_the_native_pixel_encod
         assert torch.isfinite(v).all(), k
         moved = max(moved, float((v.cpu() - enc0[k].cpu()).abs().max()))
     assert moved > 0.0, "the encoder was never updated"
+
+
+class _Discrete:
+    def __init__(self, n):
+        self.n, self.shape = n, ()
+        self._rng = np.random.default_rng(0)
+
+    def sample(self):
+        return int(self._rng.integers(0, self.n))
+
+
+class _StubDiscreteEnv:
+    """An 8-d state driven by one of 4 discrete pushes; dict observations, gym's Discrete action space surface."""
+
+    def __init__(self, seed, horizon=40):
+        self.rng = np.random.default_rng(seed)
+        self.action_space = _Discrete(4)
+        self.horizon = horizon
+        self.A = self.rng.standard_normal((8, 8)).astype(np.float32) * 0.2
+        self.push = self.rng.standard_normal((4, 8)).astype(np.float32) * 0.5
+        self.actions_seen = []
+
+    def reset(self):
+        self.t = 0
+        self.x = self.rng.standard_normal(8).astype(np.float32)
+        return {"obs": self.x.copy()}, {}
+
+    def step(self, a):
+        a = int(np.asarray(a).reshape(-1)[0])
+        assert 0 <= a < 4, a
+        self.actions_seen.append(a)
+        self.t += 1
+        self.x = np.tanh(self.A @ self.x + self.push[a] + 0.05 * self.rng.standard_normal(8)).astype(np.float32)
+        return {"obs": self.x.copy()}, float(-np.square(self.x).mean()), False, self.t >= self.horizon, {}
+
+
+def test_reference_training_loop_runs_on_the_drop_in_with_discrete_actions():
+    """the same unmodified loop with a discrete agent (DiscreteActor / DiscreteCritic, SAC-Discrete updates,
+    target entropy from action_space.n, main.py:240-241): finite logs, the reference's log keys, valid action indices."""
+    if not ref_import.available():
+        pytest.skip("baseline/_ref (the unmodified reference) did not travel")
+    import super_sac_b200 as ssb
+
+    ref = ref_import.import_reference(device="cpu")
+    main = ref.main
+
+    def run(pkg, device, steps):
+        class IdentityEncoder(pkg.nets.Encoder):
+            def __init__(self):
+                super().__init__()
+
+            @property
+            def embedding_dim(self):
+                return 8
+
+            def forward(self, obs):
+                return obs["obs"]
+
+        torch.manual_seed(0)
+        agent = pkg.Agent(act_space_size=4, encoder=IdentityEncoder(), actor_network_cls=pkg.nets.mlps.DiscreteActor,
+                          critic_network_cls=pkg.nets.mlps.DiscreteCritic, discrete=True, ensemble_size=1, num_critics=2,
+                          hidden_size=64, auto_rescale_targets=True)
+        ours = pkg.__name__ == "super_sac_b200"
+        buffer = pkg.replay.ReplayBuffer(5_000, **(dict(device=device) if ours else {}))
+        env = _StubDiscreteEnv(1)
+        pkg.learning_utils.warmup_buffer(buffer, env, 200, 40, 1, 0.99)
+        seen = {}
+        L = main.learning
+        wrapped = {}
+        for fn in ("critic_update", "online_actor_update", "alpha_update"):
+            orig = getattr(L, fn)
+
+            def make(orig=orig, fn=fn):
+                def f(*a, **k):
+                    assert k.get("discrete", False) is True, f"{fn} was not called with discrete=True"
+                    out = orig(*a, **k)
+                    logs = out[0] if isinstance(out, tuple) else out
+                    seen.setdefault(fn, set()).update(logs.keys())
+                    for key, v in logs.items():
+                        assert np.isfinite(float(v)), f"{fn}: {key} = {v}"
+                    return out
+                return f
+
+            wrapped[fn] = orig
+            setattr(L, fn, make())
+        try:
+            main.super_sac(agent, buffer, env, _StubDiscreteEnv(2), num_steps_offline=0, num_steps_online=steps,
+                           batch_size=64, critic_updates_per_step=1, use_afbc_update_online=False,
+                           use_pg_update_online=True, pop=True, weight_type=None, eval_interval=10**9,
+                           evaluation_method=lambda *a, **k: {"eval/mean_return": 0.0}, log_to_disk=False,
+                           save_to_disk=False, verbosity=0, max_episode_steps=40, target_delay=2)
+        finally:
+            for fn, orig in wrapped.items():
+                setattr(L, fn, orig)
+        return agent, buffer, env, seen
+
+    _, _, _, want = run(ref, "cpu", steps=10)
+    saved = (main.learning, main.lu, main.augmentations, main.device)
+    main.learning, main.lu, main.augmentations, main.device = ssb.learning, ssb.learning_utils, ssb.augmentations, torch.device("cuda")
+    try:
+        agent, buffer, env, got = run(ssb, torch.device("cuda"), steps=120)
+    finally:
+        main.learning, main.lu, main.augmentations, main.device = saved
+    assert set(want) == {"critic_update", "online_actor_update", "alpha_update"}
+    for fn in want:
+        assert got[fn] == want[fn], f"{fn}: log keys differ: {sorted(got[fn] ^ want[fn])}"
+    assert len(buffer) == 200 + 119
+    assert len(set(env.actions_seen[200:])) > 1, "the policy never explored"
+    for p in list(agent.critics[0].parameters()) + list(agent.actors[0].parameters()):
+        assert torch.isfinite(p).all()
