@@ -171,3 +171,55 @@ def alpha_update(agent, batches, log_alphas, alpha_opts, target_entropy):
         logs[f"losses/alpha_loss_{i}"] = alpha_loss.item()
         logs[f"alphas/alpha_{i}"] = log_alphas[i].exp().item()
     return logs
+
+
+def advantage(agent, i, s, a):
+    """adv_estimator.py:45-56 (discrete 'indirect'): A(s,a) = Q_min(s,a) - sum_a' mean_e pi_e(a'|s) Q_min(s,a'), with
+    member i's critics (+ PopArt whenever the member has one: adv_estimator.py:30-35 has no ``pop`` switch)."""
+    probs = torch.stack([policy(mlp_forward(agent.actors, e, s)[0])[0] for e in range(agent.E)], 0).mean(0)
+    min_q = agent.critic_min(i, s)
+    if agent.popart[i] is not None:
+        min_q = agent.popart[i].forward(min_q)
+    value = (probs * min_q).sum(-1, keepdim=True)
+    return min_q.gather(-1, a.long()) - value
+
+
+def offline_actor_update(agent, batches, hp, actor_opt, filter_=True):
+    """learning.py:144-219 with discrete=True, update_encoder=False; learning_utils.py:241-269: masked log-likelihood of
+    the data action under Categorical(logits).  d(-mean(mask * log p_a))/dlogit_k = -(mask/B) (1[k=a] - p_k)."""
+    E = agent.E
+    logs, aux = {}, dict(adv=[])
+    grads = agent.actors.zeros_like()
+    loss = 0.0
+    for i in range(E):
+        o, a, *_ = batches[i]
+        s = o["obs"]
+        B = s.shape[0]
+        if filter_:
+            adv = advantage(agent, i, s, a)
+            mask = (adv >= 0.0).float()
+            aux["adv"].append(adv)
+            logs["losses/adv_weights_mean"] = mask.mean().item()
+        else:
+            mask = torch.ones(B, 1)
+        logits, h1, h2 = mlp_forward(agent.actors, i, s)
+        probs, logp = policy(logits)
+        member = -(logp.gather(-1, a.long()) * mask).mean()
+        logs[f"losses/filterd_bc_loss_{i}"] = member.item()
+        loss = loss + member
+        onehot = torch.zeros(B, agent.A).scatter_(1, a.long(), 1.0)
+        mlp_backward(agent.actors, i, s, h1, h2, (-1.0 / (E * B)) * mask * (onehot - probs), grads)
+    loss = loss / E
+    glist = grads.tensors()
+    if hp.get("actor_clip"):
+        clip_grad_norm(glist, hp["actor_clip"])
+    aux["grads"] = grads
+    actor_opt.step(glist)
+    logs["losses/filtered_bc_overall_loss"] = float(loss)
+    return logs, aux
+
+
+def priorities(agent, member, batch):
+    """learning_utils.py:288-295: relu(A) + 1e-4 with one (randomly chosen) member's advantage."""
+    o, a, *_ = batch
+    return torch.relu(advantage(agent, member, o["obs"], a)).squeeze(1).double() + 1e-4

@@ -629,6 +629,82 @@ def run_discrete_case(name, cfg):
     print(f"wrote {path}  ({os.path.getsize(path)/1024:.1f} KiB)")
 
 
+def run_discrete_afbc_case():
+    """Offline (AFBC) actor update of a DISCRETE agent (learning.py:144-219 with discrete=True, learning_utils.py:241-269)
+    with the indirect advantage filter (adv_estimator.py:45-56), and the priority refresh (learning_utils.py:288-295)."""
+    cfg = dict(E=2, N=2, S=4, A=3, H=32, B=16, seed=21, actor_clip=40.0)
+    rng = np.random.default_rng(cfg["seed"])
+    torch.manual_seed(cfg["seed"])
+    E, N, S, A, H, B = cfg["E"], cfg["N"], cfg["S"], cfg["A"], cfg["H"], cfg["B"]
+    agent = ssac.Agent(act_space_size=A, encoder=IdentityEncoder(S), actor_network_cls=rnets.mlps.DiscreteActor,
+                       critic_network_cls=rnets.mlps.DiscreteCritic, discrete=True, ensemble_size=E, num_critics=N,
+                       hidden_size=H, auto_rescale_targets=True)
+    for m in critic_nets(agent) + list(agent.actors):
+        for p in m.parameters():
+            if p.dim() == 1:
+                p.data.add_(0.05 * torch.randn_like(p))
+            elif p.shape[0] == A:
+                p.data.mul_(4.0)
+    for p in agent.popart:
+        p._t = 1500
+        p.mu, p.nu, p.w, p.b = torch.tensor([0.3]), torch.tensor([1.7]), torch.tensor([0.9]), torch.tensor([0.1])
+    nbuf = 64
+    s = rng.standard_normal((nbuf, S)).astype(np.float32)
+    a = rng.integers(0, A, size=(nbuf, 1)).astype(np.float32)
+    r = rng.standard_normal((nbuf,)).astype(np.float32)
+    s1 = rng.standard_normal((nbuf, S)).astype(np.float32)
+    d = (rng.uniform(size=(nbuf,)) < 0.1).astype(np.float32)
+    buffer = rreplay.ReplayBuffer(size=nbuf + 8)
+    buffer.load_experience({"obs": s}, a, r, {"obs": s1}, d)
+    out = {"cfg": np.array(repr(cfg))}
+    put(out, "buffer", dict(s=s, a=a, r=r, s1=s1, d=d))
+    put(out, "init/actors", _stack(agent.actors))
+    put(out, "init/critics", _stack(critic_nets(agent)))
+    put(out, "init/popart", popart_state(agent))
+    actor_opt = torch.optim.Adam(chain(*(ac.parameters() for ac in agent.actors)), lr=3e-4, betas=(0.9, 0.999))
+    enc_opt = torch.optim.Adam(agent.encoder.parameters(), lr=1e-4)
+    augmenter = raug.AugmentationSequence([raug.IdentityAug(B)])
+    idx = rng.integers(0, nbuf, size=(E, B))
+    out["rand/idx"] = idx
+    for i in range(E):   # the advantage of every member on its own batch (adv_estimator.py:45-56)
+        o = {"obs": torch.as_tensor(s[idx[i]])}
+        with torch.no_grad():
+            out[f"adv/{i}"] = agent.adv_estimator(o, torch.as_tensor(a[idx[i]]), i).numpy().copy()
+    rds = []
+    o_sma = lu.sample_move_and_augment
+
+    def sma_rec(*a_, **k_):
+        rd = o_sma(*a_, **k_)
+        rds.append(rd)
+        return rd
+
+    lu.sample_move_and_augment = sma_rec
+    try:
+        with rh.injected(randint=list(idx)):
+            logs = learning.offline_actor_update(
+                buffer=buffer, agent=agent, actor_optimizer=actor_opt, encoder_optimizer=enc_opt, batch_size=B,
+                actor_clip=cfg["actor_clip"], update_encoder=False, encoder_clip=None, augmenter=augmenter, actor_lambda=0.0,
+                aug_mix=0.0, premade_replay_dicts=None, per=False, discrete=True, filter_=True)
+    finally:
+        lu.sample_move_and_augment = o_sma
+    put(out, "actor/grads", _stack(agent.actors, grad=True))
+    put(out, "actor/actors", _stack(agent.actors))
+    put(out, "actor/logs", {k.replace("/", "|"): float(v) for k, v in logs.items()})
+    # priority refresh on the last member's batch with ensemble member 1 (random.choice is seeded on both sides)
+    got = {}
+    buffer.update_priorities = lambda idxs, prios: got.update(idxs=np.asarray(idxs).copy(), prios=np.asarray(prios).copy())
+    import random as _r
+    _r.seed(7)
+    out["priorities/member"] = np.array(_r.choice(range(E)))
+    _r.seed(7)
+    rds[-1]["priority_idxs"] = idx[-1]
+    lu.adjust_priorities({}, rds[-1], agent, buffer)
+    out["priorities/idxs"], out["priorities/values"] = got["idxs"], got["prios"].astype(np.float64)
+    path = os.path.join(HERE, "discrete_afbc.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}  ({os.path.getsize(path)/1024:.1f} KiB)")
+
+
 DISCRETE_CASES = {
     # SAC-Discrete with a REDQ-style target subset (2 of 3 critics), DR3 on
     "discrete_sac": dict(E=1, N=3, M=2, S=6, A=5, H=32, B=16, steps=2, dr3_coeff=0.01, critic_clip=40.0, seed=11),
@@ -643,6 +719,8 @@ if __name__ == "__main__":
     for name, cfg in DISCRETE_CASES.items():
         if not only or name in only:
             run_discrete_case(name, cfg)
+    if not only or "discrete_afbc" in only:
+        run_discrete_afbc_case()
     for name, cfg in UPDATE_CASES.items():
         if not only or name in only:
             run_update_case(name, cfg)

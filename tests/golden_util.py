@@ -85,7 +85,7 @@ def oracle_agents(fx):
     return cfg, agent, target
 
 
-def discrete_oracle_agents(fx):
+def discrete_oracle_agents(fx, with_target=True):
     from oracle import discrete_oracle as do
 
     cfg = cfg_of(fx)
@@ -95,7 +95,8 @@ def discrete_oracle_agents(fx):
     agent.critics = uo.MLPStack.from_arrays(sub(fx, "init/critics"))
     agent.popart = popart_from(fx, "init/popart", E)
     target = agent.clone()
-    target.critics = uo.MLPStack.from_arrays(sub(fx, "init/target_critics"))
+    if with_target:
+        target.critics = uo.MLPStack.from_arrays(sub(fx, "init/target_critics"))
     return cfg, agent, target
 
 

@@ -137,6 +137,26 @@ def test_discrete_oracle_matches_reference(case):
     _cmp_logs(logs, gu.sub(fx, "alpha/logs"), "alpha")
 
 
+def test_discrete_afbc_oracle_matches_reference():
+    """Offline (AFBC) actor update of a discrete agent + indirect advantage + priority refresh against the reference."""
+    torch.set_num_threads(1)
+    fx = gu.load("discrete_afbc")
+    cfg, agent, _ = gu.discrete_oracle_agents(fx, with_target=False)
+    E = cfg["E"]
+    idx = fx["rand/idx"]
+    batches = [gu.batch_from(fx, idx[i]) for i in range(E)]
+    for i in range(E):
+        adv = do.advantage(agent, i, batches[i][0]["obs"], batches[i][1])
+        gu.assert_close(adv.numpy(), fx[f"adv/{i}"], RTOL, ATOL, f"adv[{i}]")
+    actor_opt = uo.Adam(agent.actors.tensors(), lr=3e-4)
+    logs, aux = do.offline_actor_update(agent, batches, dict(actor_clip=cfg["actor_clip"]), actor_opt)
+    _cmp_stack(aux["grads"], gu.sub(fx, "actor/grads"), "actor grads", rtol=1e-4, atol=1e-7)
+    _cmp_stack(agent.actors, gu.sub(fx, "actor/actors"), "actors", rtol=1e-5, atol=3e-4 * 2e-2)
+    _cmp_logs(logs, gu.sub(fx, "actor/logs"), "offline actor")
+    pr = do.priorities(agent, int(fx["priorities/member"]), batches[-1])
+    gu.assert_close(pr.numpy(), fx["priorities/values"], 1e-5, 1e-6, "priorities")
+
+
 def test_replay_oracle_matches_reference():
     fx = gu.load("replay_per")
     buf = ro.ReplayOracle(50, alpha=0.6, beta=0.7)
