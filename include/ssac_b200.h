@@ -381,6 +381,18 @@ int ssac_discrete_actor_seed(const float* logits_dev, const float* q_dev, int N,
 /* out[b] = sum_a p_a log p_a (learning.py:252-253; feeds ssac_alpha_step as its logp). */
 int ssac_discrete_neg_entropy(const float* logits_dev, int B, int A, float* out_dev, void* stream);
 
+/* Indirect advantage of a discrete agent (adv_estimator.py:45-56; filter learning_utils.py:257-262, priorities :288-295):
+ * logits [E,B,A] = every actor of the ensemble on the batch, q [N,B,A] = the member's critics; min_q = min_N q with the
+ * member's PopArt affine when popart_dev is given; V[b] = sum_a (mean_E p_e[b,a]) min_q[b,a]; adv = min_q[b,act[b]] - V;
+ * mask = (adv >= 0); priority (float64) = relu(adv) + 1e-4.  Any output nullable. */
+int ssac_discrete_advantage(const float* logits_dev, int E, const float* q_dev, int N, int B, int A, const float* act_dev,
+                            const float* popart_dev, float* adv_dev, float* mask_dev, double* priority_dev, void* stream);
+/* Filtered behaviour cloning on a categorical policy (learning_utils.py:241-269 with discrete=True):
+ * loss_dev[0] += -(1/B) sum_b mask[b] log p[b,act[b]] (mask nullable = 1);
+ * dlogits[b,k] = -(mask[b] / (B E)) (1[k = act[b]] - p[b,k]). */
+int ssac_discrete_bc_seed(const float* logits_dev, const float* act_dev, const float* mask_dev, int B, int A, int E,
+                          float* dlogits_dev, float* loss_dev, void* stream);
+
 /* ---- ensemble sharding over NVLink peer memory: SURVEY 8e (no counterpart in the reference: it is single-device) ---- */
 /* The exchanges of the sharded learner (target Q rows, Q(s,pi(s)) rows, dL/da partials, SUNRISE batches / values) as two
  * small kernels over SYMMETRIC buffers (one allocation of 2 x half_bytes per rank, mapped into every peer; the mappings

@@ -1,4 +1,4 @@
-"""Advantage estimator A(s,a) = Q(s,a) - V(s) (reference adv_estimator.py:8-89, continuous 'mean' / 'max').
+"""Advantage estimator A(s,a) = Q(s,a) - V(s) (reference adv_estimator.py:8-89: continuous 'mean' / 'max', discrete 'indirect').
 
 Kept as an nn.Module with the reference's constructor so ``agent.adv_estimator(o, a, ensemble_idx)`` keeps working;
 the arithmetic runs on the grouped critic / actor kernels (see learning_utils._advantage)."""
@@ -30,9 +30,6 @@ class AdvantageEstimator(nn.Module):
 
         if self._agent is None:
             raise RuntimeError("AdvantageEstimator must be created by an Agent")
-        if self.discrete:
-            raise NotImplementedError("the discrete (indirect) advantage, i.e. offline / AFBC updates of a discrete agent, "
-                                      "is not implemented; the online SAC-Discrete updates are (discrete.py)")
         rd = {"primary_batch": (obs, action, None, None, None)}
         adv, _, _ = lu._advantage(self._agent, rd, ensemble_idx, n=n)
         return adv.unsqueeze(-1)

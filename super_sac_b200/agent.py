@@ -145,7 +145,7 @@ class Agent:
         self.log_std_low, self.log_std_high = log_std_low, log_std_high
         self.deterministic = getattr(self.actors[0], "dist_impl", "pyd") == "deterministic"
         self.popart = [popart.PopArtLayer() if auto_rescale_targets else False for _ in range(ensemble_size)]
-        if discrete:   # agent.py:103-113 (the estimator object exists; its discrete forward is not implemented)
+        if discrete:   # agent.py:103-113
             self.adv_estimator = adv_estimator.AdvantageEstimator(
                 encoder=self.encoder, actors=self.actors, critics=self.critics, popart=self.popart, discrete=True,
                 discrete_method=adv_method if adv_method else "indirect")

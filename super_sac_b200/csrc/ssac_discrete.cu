@@ -151,6 +151,66 @@ __global__ void __launch_bounds__(32 * kRowsPerBlock) discrete_neg_entropy_kerne
   if (lane == 0) out[b] = s;
 }
 
+// adv_estimator.py:45-56 (discrete 'indirect') + learning_utils.py:257-262, :288-295.  logits [E,B,A]: EVERY actor of the
+// ensemble on the batch (V uses the ensemble-mean policy), q [N,B,A]: the member's critics.  min_q = popart(min_N q) when the
+// member has a PopArt layer (adv_estimator.py:30-35 has no `pop` switch); V = sum_a mean_e p_e,a min_q_a;
+// adv = min_q[a_b] - V; mask = adv >= 0; priority (float64) = relu(adv) + 1e-4.
+__global__ void __launch_bounds__(32 * kRowsPerBlock) discrete_advantage_kernel(const float* __restrict__ logits, int E,
+                                                                               const float* __restrict__ q, int N, int B,
+                                                                               int A, const float* __restrict__ act,
+                                                                               const float* __restrict__ popart,
+                                                                               float* __restrict__ adv,
+                                                                               float* __restrict__ mask,
+                                                                               double* __restrict__ prio) {
+  const int lane = threadIdx.x & 31, b = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const float pw = popart ? popart[2] : 1.f, pb = popart ? popart[3] : 0.f;
+  int ab = (int)act[b];
+  ab = ab < 0 ? 0 : (ab >= A ? A - 1 : ab);
+  float value = 0.f, q_data = 0.f;
+  for (int e = 0; e < E; ++e) {
+    const float* z = logits + ((int64_t)e * B + b) * A;
+    const RowSoftmax sm = row_softmax(z, A, lane);
+    for (int a = lane; a < A; a += 32) {
+      float qq = q[(int64_t)b * A + a];
+      for (int n = 1; n < N; ++n) qq = fminf(qq, q[((int64_t)n * B + b) * A + a]);
+      if (popart) qq = __fadd_rn(__fmul_rn(pw, qq), pb);
+      value += expf(z[a] - sm.zmax - sm.lse) * qq;
+      if (e == 0 && a == ab) q_data = qq;
+    }
+  }
+  value = warp_sum(value) / (float)E;
+  q_data = warp_sum(q_data);   // exactly one lane holds it
+  if (lane == 0) {
+    const float ad = q_data - value;
+    if (adv) adv[b] = ad;
+    if (mask) mask[b] = ad >= 0.f ? 1.f : 0.f;
+    if (prio) prio[b] = (double)fmaxf(ad, 0.f) + 1e-4;
+  }
+}
+
+// learning_utils.py:257-269 with discrete=True: logp = log p_{a_b}; loss[0] += -(1/B) sum_b mask_b logp_b (the member's
+// filtered BC loss; mask nullable = 1); dlogits[b,k] = -(mask_b / (B E)) (1[k = a_b] - p_k).
+__global__ void __launch_bounds__(32 * kRowsPerBlock) discrete_bc_seed_kernel(const float* __restrict__ logits,
+                                                                             const float* __restrict__ act,
+                                                                             const float* __restrict__ mask, int B, int A,
+                                                                             int E, float* __restrict__ dlogits,
+                                                                             float* __restrict__ loss) {
+  const int lane = threadIdx.x & 31, b = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
+  if (b >= B) return;
+  int ab = (int)act[b];
+  ab = ab < 0 ? 0 : (ab >= A ? A - 1 : ab);
+  const float m = mask ? mask[b] : 1.f;
+  const float* z = logits + (int64_t)b * A;
+  const RowSoftmax sm = row_softmax(z, A, lane);
+  const float scale = -m / ((float)B * (float)E);
+  for (int a = lane; a < A; a += 32) {
+    const float p = expf(z[a] - sm.zmax - sm.lse);
+    dlogits[(int64_t)b * A + a] = scale * ((a == ab ? 1.f : 0.f) - p);
+  }
+  if (lane == 0 && loss) atomicAdd(loss, -m * (z[ab] - sm.zmax - sm.lse) / (float)B);
+}
+
 inline int row_grid(int B) { return (B + kRowsPerBlock - 1) / kRowsPerBlock; }
 
 }  // namespace
@@ -201,6 +261,24 @@ int ssac_discrete_neg_entropy(const float* logits, int B, int A, float* out, voi
   SSAC_REQUIRE(logits && out && B > 0 && A > 0, "ssac_discrete_neg_entropy: bad args");
   discrete_neg_entropy_kernel<<<row_grid(B), 32 * kRowsPerBlock, 0, (cudaStream_t)stream>>>(logits, B, A, out);
   SSAC_CHECK_LAUNCH("ssac_discrete_neg_entropy");
+  return 0;
+}
+
+int ssac_discrete_advantage(const float* logits, int E, const float* q, int N, int B, int A, const float* act,
+                            const float* popart, float* adv, float* mask, double* priority, void* stream) {
+  SSAC_REQUIRE(logits && q && act && E > 0 && N > 0 && B > 0 && A > 0, "ssac_discrete_advantage: bad args");
+  discrete_advantage_kernel<<<row_grid(B), 32 * kRowsPerBlock, 0, (cudaStream_t)stream>>>(logits, E, q, N, B, A, act,
+                                                                                         popart, adv, mask, priority);
+  SSAC_CHECK_LAUNCH("ssac_discrete_advantage");
+  return 0;
+}
+
+int ssac_discrete_bc_seed(const float* logits, const float* act, const float* mask, int B, int A, int E, float* dlogits,
+                          float* loss, void* stream) {
+  SSAC_REQUIRE(logits && act && dlogits && B > 0 && A > 0 && E > 0, "ssac_discrete_bc_seed: bad args");
+  discrete_bc_seed_kernel<<<row_grid(B), 32 * kRowsPerBlock, 0, (cudaStream_t)stream>>>(logits, act, mask, B, A, E, dlogits,
+                                                                                       loss);
+  SSAC_CHECK_LAUNCH("ssac_discrete_bc_seed");
   return 0;
 }
 

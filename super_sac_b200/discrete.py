@@ -5,9 +5,9 @@ Same flat arenas, grouped MLP launches (ssac_mlp_forward / ssac_mlp_backward wit
 net emits its whole Q row), fused Adam and device-side logs as the continuous path in learning.py; the categorical
 arithmetic around the networks (softmax, expectation over actions, gather at the taken action and its scatter back into
 the dense output gradient) runs in the ssac_discrete_* kernels (csrc/ssac_discrete.cu).  This is the first correct path:
-eager launches, members in series, no CUDA-graph capture / cross-update pipelining yet.  Not implemented (raise):
-softmax Bellman weights (they draw Categorical samples), the discrete advantage (offline / AFBC updates and priority
-refresh of a discrete agent), the invariance regulariser, sharded ensembles.
+eager launches, members in series, no CUDA-graph capture / cross-update pipelining yet.  The offline (AFBC) actor update
+with the indirect advantage filter (adv_estimator.py:45-56) and the priority refresh are here too.  Not implemented
+(raise): softmax Bellman weights (they draw Categorical samples), the invariance regularisers, sharded ensembles.
 """
 import random
 
@@ -124,8 +124,6 @@ def critic_update(buffer, agent, target_agent, critic_optimizer, encoder_optimiz
     _check(agent)
     if encoder_lambda:
         raise NotImplementedError("encoder invariance regulariser (lambda = 0 in every shipped config) is out of scope")
-    if update_priorities:
-        raise NotImplementedError("priority refresh needs the discrete advantage estimator (not implemented)")
     lu.pipeline_barrier()
     ca = agent._critic_arena
     dev = ca.device
@@ -206,6 +204,8 @@ def critic_update(buffer, agent, target_agent, critic_optimizer, encoder_optimiz
         logs.put_tensor("gradients/encoder_criticloss_grad_norm", gn)
     else:
         logs["gradients/encoder_criticloss_grad_norm"] = 0.0
+    if update_priorities:
+        lu.adjust_priorities(logs, rd, agent, buffer)
     return logs.finalize(), replay_dicts
 
 
@@ -281,4 +281,99 @@ def alpha_update(buffer, agent, optimizers, batch_size, log_alphas, augmenter, a
         st._step_tensor.fill_(st.steps)
         logs.defer(f"losses/alpha_loss_{i}", slot)
         logs.defer(f"alphas/alpha_{i}", slot + 1)
+    return logs.finalize()
+
+
+def _advantage(agent, replay_dict, ensemble_idx, want_priority=False):
+    """Indirect advantage of a discrete agent (adv_estimator.py:45-56): A(s,a) = Q_min(s,a) - sum_a' pibar(a'|s) Q_min(s,a')
+    with pibar the mean policy of ALL actors and Q_min member ``ensemble_idx``'s critics (+ its PopArt layer).
+    Returns (adv [B], mask [B], priority float64 [B] or None) like learning_utils._advantage."""
+    _check(agent)
+    o, a, *_ = replay_dict["primary_batch"]
+    i, E, N, A = ensemble_idx, agent.ensemble_size, agent.num_critics, agent.act_space_size
+    L, stream = _lib.lib(), _lib.stream_ptr()
+    with torch.no_grad():
+        s_rep = agent.encoder(o)
+    X, ld = _rows(s_rep)
+    B, dev = X.shape[0], X.device
+    logits = _forward(agent._actor_arena, 0, E, X, ld, B)                  # [E,B,A]: every actor, one launch
+    q = _forward(agent._critic_arena, i * N, N, X, ld, B)                  # [N,B,A]
+    act = _actions(a, B)
+    popart = agent.popart[i]
+    adv = torch.empty(B, dtype=torch.float32, device=dev)
+    mask = torch.empty(B, dtype=torch.float32, device=dev)
+    prio = torch.empty(B, dtype=torch.float64, device=dev) if want_priority else None
+    L.discrete_advantage(logits.data_ptr(), E, q.data_ptr(), N, B, A, act.data_ptr(), popart.state_ptr() if popart else None,
+                         adv.data_ptr(), mask.data_ptr(), None if prio is None else prio.data_ptr(), stream)
+    return adv, mask, prio
+
+
+def offline_actor_update(buffer, agent, actor_optimizer, encoder_optimizer, batch_size, actor_clip, update_encoder,
+                         encoder_clip, augmenter, actor_lambda, aug_mix, premade_replay_dicts, per, filter_):
+    """learning.py:144-219 with discrete=True (learning_utils.py:241-269): advantage-filtered log-likelihood of the data
+    actions under the categorical policy."""
+    _check(agent)
+    if actor_lambda:
+        raise NotImplementedError("action invariance regulariser (lambda = 0 in every shipped config) is out of scope")
+    lu.pipeline_barrier()
+    aa = agent._actor_arena
+    dev = aa.device
+    L, stream = _lib.lib(), _lib.stream_ptr()
+    E, B, A = agent.ensemble_size, batch_size, agent.act_space_size
+    logs = _logs.DeviceLogs(dev)
+    loss_all, loss_slot = logs.slots(E)
+    opt = _arena.FlatAdam.attach(actor_optimizer, aa)
+    enc_outs = []
+    for i in range(E):
+        if premade_replay_dicts is not None:
+            rd = premade_replay_dicts[i]
+        else:
+            rd = lu.sample_move_and_augment(buffer=buffer, batch_size=B, augmenter=augmenter, aug_mix=aug_mix, per=per)
+        o, a, *_ = rd["primary_batch"]
+        mask = None
+        if filter_:
+            _, mask, _ = _advantage(agent, rd, i)
+            logs.put_tensor("losses/adv_weights_mean", mask.mean())
+        if update_encoder:
+            s_rep = agent.encoder(o)
+        else:
+            with torch.no_grad():
+                s_rep = agent.encoder(o)
+        need_ds = torch.is_tensor(s_rep) and s_rep.requires_grad
+        X, ld = _rows(s_rep)
+        S = X.shape[1]
+        logits, h1, h2 = _forward(aa, i, 1, X, ld, B, keep=True)
+        act = _actions(a, B)
+        dlogits = torch.empty((1, B, A), dtype=torch.float32, device=dev)
+        L.discrete_bc_seed(logits.data_ptr(), act.data_ptr(), None if mask is None else mask.data_ptr(), B, A, E,
+                           dlogits.data_ptr(), loss_all[i:i + 1].data_ptr(), stream)
+        logs.defer(f"losses/filterd_bc_loss_{i}", loss_slot + i)
+        dxg = torch.empty((1, B, S), dtype=torch.float32, device=dev) if need_ds else None
+        _ops.mlp_backward(aa, i, 1, X, B, h1, h2, dlogits, ldx=ld, want_dw=True, accumulate=False, dx=dxg, lddx=S)
+        if need_ds:
+            enc_outs.append((s_rep, dxg[0]))
+    encoder_optimizer.zero_grad()
+    if enc_outs:
+        torch.autograd.backward([s for s, _ in enc_outs], [g for _, g in enc_outs])
+    if actor_clip:
+        opt.grad_norm_sq(stream)
+    enc_net = None
+    if update_encoder and enc_outs:
+        enc_net = _encoder_opt.fused_step(agent.encoder, encoder_optimizer, encoder_clip)
+    if enc_net is None and encoder_clip and enc_outs:
+        torch.nn.utils.clip_grad_norm_(agent.encoder.parameters(), encoder_clip)
+    opt.step(stream, max_norm=actor_clip if actor_clip else None)
+    if enc_net is None and update_encoder and enc_outs:
+        encoder_optimizer.step()
+    logs.defer("losses/filtered_bc_overall_loss", [loss_slot + i for i in range(E)], transform=lambda v: v / E)
+    member = random.choice(range(E))
+    gslot = lu._member_grad_norm_slot(logs, aa, member, member + 1)
+    logs.defer("gradients/actor_offline_grad_norm", gslot, transform=lambda v: v**0.5)
+    if enc_outs:
+        gn = torch.linalg.vector_norm(torch.stack([p.grad.norm() for p in agent.encoder.parameters() if p.grad is not None]))
+        logs.put_tensor("gradients/encoder_offline_actorloss_grad_norm", gn)
+    else:
+        logs["gradients/encoder_offline_actorloss_grad_norm"] = 0.0
+    if per:
+        lu.adjust_priorities(logs, rd, agent, buffer)
     return logs.finalize()

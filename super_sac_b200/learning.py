@@ -622,8 +622,10 @@ def offline_actor_update(buffer, agent, actor_optimizer, encoder_optimizer, batc
                          encoder_clip, augmenter, actor_lambda, aug_mix, premade_replay_dicts=None, per=True,
                          discrete=False, filter_=True):
     """AFBC / behaviour cloning actor update (reference learning.py:144-219, learning_utils.py:241-269)."""
-    if discrete:
-        raise NotImplementedError("discrete actions are out of scope")
+    if discrete:   # learning_utils.py:257-258: Categorical log-likelihood, indirect advantage filter
+        return _discrete.offline_actor_update(buffer, agent, actor_optimizer, encoder_optimizer, batch_size, actor_clip,
+                                              update_encoder, encoder_clip, augmenter, actor_lambda, aug_mix,
+                                              premade_replay_dicts, per, filter_)
     if actor_lambda:
         raise NotImplementedError("action invariance regulariser (lambda = 0 in every shipped config) is out of scope")
     if agent.deterministic:

@@ -847,6 +847,10 @@ def compute_backup_weights(logs, replay_dict, agent, target_agent, weight_type, 
 def _advantage(agent, replay_dict, ensemble_idx, n=4, want_priority=False):
     """A(s,a) = Q(s,a) - mean_n Q(s, a'~pi) with min-over-N critics and PopArt (reference adv_estimator.py:58-79).
     Returns (adv [B], mask [B], priority float64 [B] or None)."""
+    if agent.discrete:   # adv_estimator.py:45-56 ('indirect')
+        from . import discrete as _discrete
+
+        return _discrete._advantage(agent, replay_dict, ensemble_idx, want_priority=want_priority)
     o, a, *_ = replay_dict["primary_batch"]
     i = ensemble_idx
     S, A = _dims(agent)

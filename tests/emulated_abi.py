@@ -134,6 +134,31 @@ class EmulatedLib:
         p, lp = _softmax_stats(_f32(logits, B * A).reshape(B, A))
         _f32(out, B)[:] = (p * lp).sum(-1)
 
+    def discrete_advantage(self, logits, E, q, N, B, A, act, popart, adv, mask, priority, stream):
+        self.calls.append("discrete_advantage")
+        pm = np.mean([_softmax_stats(_f32(logits + 4 * e * B * A, B * A).reshape(B, A))[0] for e in range(E)], axis=0)
+        mq = _f32(q, N * B * A).reshape(N, B, A).min(0)
+        if popart:
+            mq = _f32(popart, 4)[2] * mq + _f32(popart, 4)[3]
+        a = _f32(act, B).astype(np.int64)
+        ad = mq[np.arange(B), a] - (pm * mq).sum(-1)
+        if adv:
+            _f32(adv, B)[:] = ad
+        if mask:
+            _f32(mask, B)[:] = ad >= 0
+        if priority:
+            np.ctypeslib.as_array((ctypes.c_double * B).from_address(priority))[:] = np.maximum(ad, 0).astype(np.float64) + 1e-4
+
+    def discrete_bc_seed(self, logits, act, mask, B, A, E, dlogits, loss, stream):
+        self.calls.append("discrete_bc_seed")
+        p, lp = _softmax_stats(_f32(logits, B * A).reshape(B, A))
+        a = _f32(act, B).astype(np.int64)
+        m = _f32(mask, B) if mask else np.ones(B, np.float32)
+        onehot = np.zeros((B, A), np.float32)
+        onehot[np.arange(B), a] = 1
+        _f32(dlogits, B * A)[:] = ((-m / (B * E))[:, None] * (onehot - p)).ravel()
+        _f32(loss, 1)[0] += -(m * lp[np.arange(B), a]).sum() / B
+
     # ---- shared with the continuous path (csrc/ssac_elementwise.cu) ------------------------------------------------
     def td_target(self, q_t, M, B, logp, log_alpha, r, d, gamma, popart, popart_ctl, pop, beta, min_steps, y, logs, stream):
         self.calls.append("td_target")

@@ -193,6 +193,79 @@ def test_discrete_updates_host_logic(case, emulated, monkeypatch):
         _rng.set_source(old_src)
 
 
+def test_discrete_offline_update_host_logic(emulated, monkeypatch):
+    """offline_actor_update(discrete=True) with the indirect advantage filter, the AdvantageEstimator call surface and
+    adjust_priorities, on CPU through the emulated C ABI, against the golden of the unmodified reference."""
+    import random
+    from itertools import chain
+
+    import super_sac_b200 as ssb
+    from super_sac_b200 import _rng, augmentations, learning, learning_utils as lu, nets
+
+    fx = gu.load("discrete_afbc")
+    cfg = gu.cfg_of(fx)
+    E, N, S, A, H, B = cfg["E"], cfg["N"], cfg["S"], cfg["A"], cfg["H"], cfg["B"]
+    agent = ssb.Agent(act_space_size=A, encoder=IdentityEncoder(S), actor_network_cls=nets.mlps.DiscreteActor,
+                      critic_network_cls=nets.mlps.DiscreteCritic, discrete=True, ensemble_size=E, num_critics=N,
+                      hidden_size=H, auto_rescale_targets=True)
+    _load_stack(agent._actor_arena, gu.sub(fx, "init/actors"))
+    _load_stack(agent._critic_arena, gu.sub(fx, "init/critics"))
+    pst = gu.sub(fx, "init/popart")
+    for i, p in enumerate(agent.popart):
+        p.mu, p.nu, p.w, p.b = pst[f"{i}/mu"], pst[f"{i}/nu"], pst[f"{i}/w"], pst[f"{i}/b"]
+        p._t = int(pst[f"{i}/t"])
+    bufd, idx = gu.sub(fx, "buffer"), fx["rand/idx"]
+
+    def make_rd(ix):
+        XA = torch.as_tensor(np.concatenate([bufd["s"][ix], bufd["a"][ix]], 1).astype(np.float32))
+        rd = lu.ReplayDict()
+        rd["primary_batch"] = ({"obs": XA[:, :S]}, XA[:, S:], None, None, None)
+        rd["priority_idxs"], rd["imp_weights"] = torch.as_tensor(ix), torch.ones(1)
+        return rd
+
+    for i in range(E):   # agent.adv_estimator(o, a, i) -> [B, 1] (adv_estimator.py:81-89 call surface)
+        rd = make_rd(idx[i])
+        adv = agent.adv_estimator(rd["primary_batch"][0], rd["primary_batch"][1], i)
+        gu.assert_close(adv.numpy(), fx[f"adv/{i}"], RTOL, 1e-6, f"adv[{i}]")
+
+    def fake_sample(buffer, batch_size, augmenter, aug_mix, per=True, _idx=None):
+        ix = torch.empty(batch_size, dtype=torch.int64)
+        _rng.source().indices(ix, len(bufd["a"]))
+        return make_rd(ix.numpy())
+
+    monkeypatch.setattr(lu, "sample_move_and_augment", fake_sample)
+    actor_opt = torch.optim.Adam(chain(*(a.parameters() for a in agent.actors)), lr=3e-4, betas=(0.9, 0.999))
+    enc_opt = torch.optim.Adam(agent.encoder.parameters(), lr=1e-4)
+    augmenter = augmentations.AugmentationSequence([augmentations.IdentityAug(B)])
+    src = _rng.ScriptedSource()
+    old_src = _rng.set_source(src)
+    try:
+        for i in range(E):
+            src.push("indices", idx[i])
+        logs = learning.offline_actor_update(
+            buffer=None, agent=agent, actor_optimizer=actor_opt, encoder_optimizer=enc_opt, batch_size=B,
+            actor_clip=cfg["actor_clip"], update_encoder=False, encoder_clip=None, augmenter=augmenter, actor_lambda=0.0,
+            aug_mix=0.0, premade_replay_dicts=None, per=False, discrete=True, filter_=True)
+        assert src.empty()
+    finally:
+        _rng.set_source(old_src)
+    _cmp_stack(agent._actor_arena.g, gu.sub(fx, "actor/grads"), "actor grads", atol=2e-7)
+    _cmp_stack(agent._actor_arena.p, gu.sub(fx, "actor/actors"), "actors", atol=3e-4 * 0.05)
+    _cmp_logs(logs, gu.sub(fx, "actor/logs"), "offline actor")
+
+    class Buf:
+        def update_priorities(self, idxs, prios):
+            self.idxs, self.prios = idxs, prios
+
+    buf = Buf()
+    random.seed(7)
+    lu.adjust_priorities({}, make_rd(idx[-1]), agent, buf)
+    assert np.array_equal(np.asarray(buf.idxs), fx["priorities/idxs"])
+    gu.assert_close(buf.prios.numpy(), fx["priorities/values"], 1e-5, 1e-6, "priorities")
+    assert buf.prios.dtype == torch.float64
+    assert "discrete_advantage" in emulated.calls and "discrete_bc_seed" in emulated.calls
+
+
 def test_discrete_acting_path_shapes(emulated):
     """Agent.forward / sample_action of a discrete agent (agent.py:204-221, :262-320) return action indices."""
     import super_sac_b200 as ssb

@@ -321,3 +321,116 @@ def test_discrete_update_baseline_size_matches_oracle():
         assert act.shape == (7, 1) and act.min() >= 0 and act.max() < A
     finally:
         _rng.set_source(old_src)
+
+
+@pytest.mark.parametrize("B,A,N,E", [(256, 18, 2, 1), (37, 5, 3, 3), (64, 40, 2, 2)])
+def test_discrete_advantage_and_bc_kernels_match_oracle(B, A, N, E):
+    from oracle import discrete_oracle as do
+
+    L, stream = _L()
+    g = torch.Generator().manual_seed(B * 17 + A)
+    logits = torch.randn(E, B, A, generator=g) * 2.0
+    q = torch.randn(N, B, A, generator=g)
+    act = torch.randint(0, A, (B,), generator=g).float()
+    popart = torch.tensor([0.3, 1.7, 0.9, 0.1])
+    dev = "cuda"
+    lg, qd, ad, pd = (t.to(dev).contiguous() for t in (logits, q, act, popart))
+    idx = act.long().unsqueeze(-1)
+    for use_pop in (False, True):
+        adv = torch.empty(B, device=dev)
+        mask = torch.empty(B, device=dev)
+        prio = torch.empty(B, dtype=torch.float64, device=dev)
+        L.discrete_advantage(lg.data_ptr(), E, qd.data_ptr(), N, B, A, ad.data_ptr(), pd.data_ptr() if use_pop else None,
+                             adv.data_ptr(), mask.data_ptr(), prio.data_ptr(), stream)
+        pm = torch.stack([do.policy(logits[e])[0] for e in range(E)], 0).mean(0)
+        mq = q.min(0).values
+        if use_pop:
+            mq = popart[2] * mq + popart[3]
+        want = (mq.gather(-1, idx) - (pm * mq).sum(-1, keepdim=True)).squeeze(-1)
+        gu.assert_close(adv.cpu().numpy(), want.numpy(), 1e-5, 2e-6, f"advantage (popart={use_pop})")
+        clear = want.abs() > 1e-5   # rows whose sign is not a rounding question
+        assert np.array_equal(mask.cpu().numpy()[clear.numpy()], (want >= 0).float().numpy()[clear.numpy()])
+        gu.assert_close(prio.cpu().numpy(), (torch.relu(want).double() + 1e-4).numpy(), 1e-5, 2e-6, "priority")
+    m = (torch.rand(B, generator=g) > 0.5).float()
+    md = m.to(dev)
+    probs, logp = do.policy(logits[0])
+    onehot = torch.zeros(B, A).scatter_(1, idx, 1.0)
+    for use_mask in (False, True):
+        dl = torch.empty(B, A, device=dev)
+        loss = torch.zeros(1, device=dev)
+        L.discrete_bc_seed(lg.data_ptr(), ad.data_ptr(), md.data_ptr() if use_mask else None, B, A, 2, dl.data_ptr(),
+                           loss.data_ptr(), stream)
+        mm = m if use_mask else torch.ones(B)
+        gu.assert_close(dl.cpu().numpy(), ((-mm / (B * 2)).unsqueeze(-1) * (onehot - probs)).numpy(), 1e-4, 1e-8, "bc seed")
+        gu.assert_close(loss.cpu().numpy(), (-(mm * logp.gather(-1, idx).squeeze(-1)).mean()).reshape(1).numpy(), 1e-4, 1e-6,
+                        "bc loss")
+
+
+@pytest.mark.parametrize("impl", ["tcgen05", "ffma"])
+def test_discrete_offline_update_matches_reference(impl):
+    """offline_actor_update(discrete=True) with the advantage filter, agent.adv_estimator, compute_filter_stats and
+    adjust_priorities (PER trees written) on the golden of the unmodified reference."""
+    import random
+
+    import cuda_util as cu
+    import super_sac_b200 as ssb
+    from super_sac_b200 import _rng, augmentations, learning, learning_utils as lu
+
+    ssb.set_mlp_impl(impl)
+    fx = gu.load("discrete_afbc")
+    cfg = gu.cfg_of(fx)
+    cfg["popart"] = True
+    E, B = cfg["E"], cfg["B"]
+    agent, _ = _discrete_agent(cfg, dict(actors=gu.sub(fx, "init/actors"), critics=gu.sub(fx, "init/critics"),
+                                         target_critics=gu.sub(fx, "init/critics")))
+    pst = gu.sub(fx, "init/popart")
+    for i, p in enumerate(agent.popart):
+        p.mu, p.nu, p.w, p.b = pst[f"{i}/mu"], pst[f"{i}/nu"], pst[f"{i}/w"], pst[f"{i}/b"]
+        p._t = int(pst[f"{i}/t"])
+    buf = cu.buffer_from_fixture(fx)
+    idx = fx["rand/idx"]
+    bufd = gu.sub(fx, "buffer")
+    dev = agent._critic_arena.device
+    old_src = _rng.set_source(_rng.ScriptedSource())
+    try:
+        for i in range(E):
+            o = {"obs": torch.as_tensor(bufd["s"][idx[i]]).to(dev)}
+            adv = agent.adv_estimator(o, torch.as_tensor(bufd["a"][idx[i]]).to(dev), i)
+            gu.assert_close(adv.cpu().numpy(), fx[f"adv/{i}"], RTOL, 2e-6, f"adv[{i}]")
+        _, actor_opt, enc_opt, _, _ = _optimizers(agent, cfg)
+        augmenter = augmentations.AugmentationSequence([augmentations.IdentityAug(B)])
+        src = _rng.ScriptedSource()
+        _rng.set_source(src)
+        for i in range(E):
+            src.push("indices", idx[i])
+        logs = learning.offline_actor_update(
+            buffer=buf, agent=agent, actor_optimizer=actor_opt, encoder_optimizer=enc_opt, batch_size=B,
+            actor_clip=cfg["actor_clip"], update_encoder=False, encoder_clip=None, augmenter=augmenter, actor_lambda=0.0,
+            aug_mix=0.0, premade_replay_dicts=None, per=False, discrete=True, filter_=True)
+        assert src.empty()
+        _cmp_stack(cu.grads_of(agent._actor_arena), gu.sub(fx, "actor/grads"), "actor grads", atol=2e-7)
+        _cmp_stack(cu.stack_of(agent._actor_arena), gu.sub(fx, "actor/actors"), "actors", atol=3e-4 * 0.05)
+        _cmp_logs(logs, gu.sub(fx, "actor/logs"), "offline actor")
+        # priority refresh on the last member's batch (random.choice seeded like the generator): values, then the trees
+        src.push("indices", idx[-1])
+        rd = lu.sample_move_and_augment(buffer=buf, batch_size=B, augmenter=augmenter, aug_mix=0.0, per=False)
+        got = {}
+        o_up = buf.update_priorities
+
+        def rec(idxs, prios):
+            got["idxs"], got["prios"] = idxs, prios
+            return o_up(idxs, prios)
+
+        buf.update_priorities = rec
+        random.seed(7)
+        lu.adjust_priorities({}, rd, agent, buf)
+        ii = got["idxs"].cpu().numpy() if torch.is_tensor(got["idxs"]) else np.asarray(got["idxs"])
+        assert np.array_equal(ii, fx["priorities/idxs"])
+        pr = got["prios"].cpu().numpy() if torch.is_tensor(got["prios"]) else np.asarray(got["prios"])
+        gu.assert_close(pr, fx["priorities/values"], 1e-5, 1e-6, "priorities")
+        src.push("indices", idx[0])
+        pct = lu.compute_filter_stats(buf, agent, augmenter, B)
+        assert 0.0 <= pct <= 100.0
+    finally:
+        _rng.set_source(old_src)
+        ssb.set_mlp_impl("tcgen05")
