@@ -286,3 +286,28 @@ def test_discrete_acting_path_shapes(emulated):
         act, dist = agent._discrete_sample(s, 5)
     assert act.shape == (5, 1)
     del obs
+
+
+def test_discrete_unsupported_options_fail_loudly(emulated):
+    """What the discrete path does not implement raises instead of silently computing something else."""
+    import super_sac_b200 as ssb
+    from super_sac_b200 import discrete, learning, nets
+
+    cont = ssb.Agent(2, IdentityEncoder(3), nets.mlps.ContinuousStochasticActor, nets.mlps.ContinuousCritic,
+                     ensemble_size=1, num_critics=2, hidden_size=16)
+    with pytest.raises(ValueError, match="discrete=True"):
+        learning.alpha_update(buffer=None, agent=cont, optimizers=[], batch_size=4, log_alphas=[], augmenter=None,
+                              aug_mix=0.0, target_entropy=0.0, premade_replay_dicts=None, discrete=True)
+    agent = ssb.Agent(act_space_size=4, encoder=IdentityEncoder(3), actor_network_cls=nets.mlps.DiscreteActor,
+                      critic_network_cls=nets.mlps.DiscreteCritic, discrete=True, ensemble_size=2, num_critics=2,
+                      hidden_size=16)
+    with pytest.raises(NotImplementedError, match="sunrise"):
+        discrete.compute_backup_weights({}, {"primary_batch": (None,) * 5}, agent, agent, "softmax", 10.0, 4)
+    with pytest.raises(NotImplementedError, match="invariance"):
+        discrete.critic_update(None, agent, agent, None, None, [], 4, 0.99, None, None, 2, None, None, False, None, 0.5, 0.0,
+                               False, False, 0.0)
+    with pytest.raises(NotImplementedError, match="invariance"):
+        discrete.offline_actor_update(None, agent, None, None, 4, None, False, None, None, 0.5, 0.0, None, False, True)
+    # a discrete Agent needs S -> H -> H -> A networks (the continuous critic takes [s | a])
+    with pytest.raises(NotImplementedError):
+        ssb.Agent(4, IdentityEncoder(3), nets.mlps.DiscreteActor, nets.mlps.ContinuousCritic, discrete=True)
