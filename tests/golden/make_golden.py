@@ -101,7 +101,7 @@ def popart_state(agent):
     return out
 
 
-def run_update_case(name, cfg):
+def run_update_case(name, cfg, out_dir=None):
     """Drives critic_update (+Polyak by the target_delay rule of main.py:409), then online_actor_update and
     alpha_update, exactly as main.py:380-414 / :491-543 call them."""
     rng = np.random.default_rng(cfg.get("seed", 0))
@@ -266,7 +266,7 @@ def run_update_case(name, cfg):
                 discrete=False)
         put(out, "alpha/log_alphas", {str(i): la.detach().numpy().copy() for i, la in enumerate(log_alphas)})
         put(out, "alpha/logs", {k.replace("/", "|"): float(v) for k, v in llogs.items()})
-    path = os.path.join(HERE, f"update_{name}.npz")
+    path = os.path.join(out_dir or HERE, f"update_{name}.npz")
     np.savez_compressed(path, **out)
     print(f"wrote {path}  ({os.path.getsize(path)/1024:.1f} KiB)")
 
@@ -507,7 +507,7 @@ def _stack(modules, grad=False):
     }
 
 
-def run_discrete_case(name, cfg):
+def run_discrete_case(name, cfg, out_dir=None):
     """SAC-Discrete: critic_update(discrete=True) + Polyak, online_actor_update(discrete=True) and
     alpha_update(discrete=True) of the unmodified reference, driven as main.py:380-414 / :491-543 drive them.  The only
     random draws on this path are the replay indices (replay.py:122) and the target-critic subset (agent.py:29)."""
@@ -624,7 +624,7 @@ def run_discrete_case(name, cfg):
     put(out, "alpha/log_alphas", {str(i): la.detach().numpy().copy() for i, la in enumerate(log_alphas)})
     put(out, "alpha/logs", {k.replace("/", "|"): float(v) for k, v in llogs.items()})
     out["alpha/target_entropy"] = np.array(target_entropy)
-    path = os.path.join(HERE, f"update_{name}.npz")
+    path = os.path.join(out_dir or HERE, f"update_{name}.npz")
     np.savez_compressed(path, **out)
     print(f"wrote {path}  ({os.path.getsize(path)/1024:.1f} KiB)")
 

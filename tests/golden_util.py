@@ -15,8 +15,8 @@ UPDATE_CASES = ["sac", "redq", "sunrise_popart", "td3_encoder", "softmax_dr3"]
 DISCRETE_CASES = ["discrete_sac", "discrete_sunrise_popart"]
 
 
-def load(name):
-    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
+def load(name, directory=None):
+    z = np.load(os.path.join(directory or GOLDEN_DIR, name + ".npz"), allow_pickle=False)
     return {k: z[k] for k in z.files}
 
 

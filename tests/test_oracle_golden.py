@@ -33,8 +33,11 @@ def _cmp_logs(logs, want, what):
 
 @pytest.mark.parametrize("case", gu.UPDATE_CASES)
 def test_update_oracle_matches_reference(case):
+    check_update_oracle(gu.load("update_" + case))
+
+
+def check_update_oracle(fx):
     torch.set_num_threads(1)
-    fx = gu.load("update_" + case)
     cfg, agent, target = gu.oracle_agents(fx)
     E = cfg["E"]
     hp = gu.hp_from(cfg)
@@ -96,8 +99,11 @@ def test_update_oracle_matches_reference(case):
 @pytest.mark.parametrize("case", gu.DISCRETE_CASES)
 def test_discrete_oracle_matches_reference(case):
     """SAC-Discrete: the restated discrete branches against the unmodified reference's outputs."""
+    check_discrete_oracle(gu.load("update_" + case))
+
+
+def check_discrete_oracle(fx):
     torch.set_num_threads(1)
-    fx = gu.load("update_" + case)
     cfg, agent, target = gu.discrete_oracle_agents(fx)
     E = cfg["E"]
     hp = gu.hp_from(cfg)

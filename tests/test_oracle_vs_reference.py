@@ -1,0 +1,48 @@
+"""Live cross-check of the oracle against the UNMODIFIED reference on FRESH seeds and shapes (CPU; runs only where
+/root/reference exists, i.e. in the build container -- the committed fixtures in tests/golden/ are what travels).
+
+The golden generator (tests/golden/make_golden.py) drives the imported reference with injected randomness; here it writes
+new fixtures into a temporary directory with seeds / sizes that no committed fixture uses, and the same checks as
+tests/test_oracle_golden.py run on them.  This guards the oracle against having been fitted to the committed cases.
+"""
+import os
+import sys
+
+import pytest
+
+import golden_util as gu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import ref_harness as rh  # noqa: E402
+
+pytestmark = pytest.mark.skipif(not rh.reference_available(), reason="the reference tree is not present on this machine")
+
+FRESH_UPDATE = {
+    "redq_fresh": dict(E=1, N=4, M=3, S=9, A=4, H=40, B=24, steps=2, target_delay=1, seed=101),
+    "sunrise_fresh": dict(E=2, N=2, M=2, S=7, A=3, H=24, B=12, steps=2, weight_type="sunrise", weight_temp=15.0,
+                          popart=True, pop=True, popart_warm=True, seed=102),
+}
+FRESH_DISCRETE = {
+    "discrete_fresh": dict(E=1, N=2, M=1, S=10, A=7, H=24, B=20, steps=3, seed=103),
+    "discrete_ens_fresh": dict(E=3, N=2, M=2, S=5, A=4, H=16, B=12, steps=2, weight_type="sunrise", weight_temp=10.0,
+                               popart=True, pop=True, popart_warm=True, dr3_coeff=0.02, actor_clip=1.0, seed=104),
+}
+
+
+@pytest.mark.parametrize("name", sorted(FRESH_UPDATE))
+def test_update_oracle_on_fresh_reference_runs(name, tmp_path):
+    import make_golden as mg
+    from test_oracle_golden import check_update_oracle
+
+    mg.run_update_case(name, FRESH_UPDATE[name], out_dir=str(tmp_path))
+    check_update_oracle(gu.load("update_" + name, directory=str(tmp_path)))
+
+
+@pytest.mark.parametrize("name", sorted(FRESH_DISCRETE))
+def test_discrete_oracle_on_fresh_reference_runs(name, tmp_path):
+    import make_golden as mg
+    from test_oracle_golden import check_discrete_oracle
+
+    mg.run_discrete_case(name, FRESH_DISCRETE[name], out_dir=str(tmp_path))
+    check_discrete_oracle(gu.load("update_" + name, directory=str(tmp_path)))
