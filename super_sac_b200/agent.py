@@ -329,6 +329,16 @@ class Agent:
         self.train()
         return self._process_act(act, num_envs) if from_cpu else act
 
+    def discrete_forward(self, obs, from_cpu=True, num_envs=1, rolling=False):
+        """Reference agent.py:204-221 (``forward`` dispatches here for a discrete agent)."""
+        assert self.discrete
+        return self.forward(obs, from_cpu=from_cpu, num_envs=num_envs, rolling=rolling)
+
+    def continuous_forward(self, obs, from_cpu=True, num_envs=1, rolling=False):
+        """Reference agent.py:223-237."""
+        assert not self.discrete
+        return self.forward(obs, from_cpu=from_cpu, num_envs=num_envs, rolling=rolling)
+
     def sample_action(self, obs, from_cpu=True, num_envs=1, return_dist=False, rolling=False):
         """Exploration action (reference agent.py:228-327): a sample of a randomly chosen actor, or -- with
         ``ucb_bonus > 0`` -- SUNRISE's UCB choice among every actor's proposal, scored by every member's critics.  On the

@@ -285,7 +285,15 @@ def test_discrete_acting_path_shapes(emulated):
     with torch.no_grad():
         act, dist = agent._discrete_sample(s, 5)
     assert act.shape == (5, 1)
-    del obs
+    # the public call surface with numpy observations (agent.py:204-221, :262-327): indices come back as numpy arrays
+    g = agent.forward(obs, num_envs=5)
+    assert g.shape == (5, 1) and np.array_equal(g, greedy.numpy())
+    assert np.array_equal(agent.discrete_forward(obs, num_envs=5), g)
+    one = agent.forward({"obs": np.zeros(3, np.float32)})          # num_envs = 1: the env axis is squeezed away
+    assert one.shape == (1,)
+    a, dist = agent.sample_action(obs, num_envs=5, return_dist=True)
+    assert a.shape == (5, 1) and a.dtype.kind == "i" and dist.probs.shape == (5, 4)
+    assert agent.sample_action({"obs": np.zeros(3, np.float32)}).shape == (1,)
 
 
 def test_discrete_unsupported_options_fail_loudly(emulated):
