@@ -699,3 +699,11 @@ def offline_actor_update(buffer, agent, actor_optimizer, encoder_optimizer, batc
     if per:
         lu.adjust_priorities(logs, rd, agent, buffer)
     return logs.finalize()
+
+
+def markov_state_abstraction_update(buffer, agent, optimizer, batch_size, augmenter, aug_mix, discrete, inverse_coeff,
+                                    contrastive_coeff, smoothness_coeff, smoothness_max_dist, grad_clip):
+    """Reference learning.py:266-341 (self-supervised Markov state abstraction).  Not part of the B200 update path
+    (DESIGN 9): it trains the user's encoder and two plain nn.Module heads through autograd; refuse loudly."""
+    raise NotImplementedError("markov_state_abstraction_update is out of scope of super_sac_b200 (DESIGN.md section 9); "
+                              "run the reference's own function on the agent's encoder / inverse_model / contrastive_model")
