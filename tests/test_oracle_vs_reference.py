@@ -46,3 +46,55 @@ def test_discrete_oracle_on_fresh_reference_runs(name, tmp_path):
 
     mg.run_discrete_case(name, FRESH_DISCRETE[name], out_dir=str(tmp_path))
     check_discrete_oracle(gu.load("update_" + name, directory=str(tmp_path)))
+
+
+def test_discrete_checkpoints_interchange_with_the_reference(tmp_path):
+    """Agent.save / load of a discrete agent use the reference's file names and state_dict keys (agent.py:172-202): a
+    checkpoint written by the unmodified reference loads into this package's Agent (the values land in the flat arenas)
+    and one written by this package loads back into the reference."""
+    import numpy as np
+    import torch
+
+    import super_sac_b200 as ssb
+
+    ref = rh.import_reference()
+
+    def build(pkg):
+        class Enc(pkg.nets.Encoder):
+            def __init__(self):
+                super().__init__()
+
+            @property
+            def embedding_dim(self):
+                return 6
+
+            def forward(self, obs):
+                return obs["obs"]
+
+        return pkg.Agent(act_space_size=5, encoder=Enc(), actor_network_cls=pkg.nets.mlps.DiscreteActor,
+                         critic_network_cls=pkg.nets.mlps.DiscreteCritic, discrete=True, ensemble_size=2, num_critics=2,
+                         hidden_size=16, auto_rescale_targets=False)
+
+    torch.manual_seed(3)
+    theirs, ours = build(ref), build(ssb)
+    d1, d2 = tmp_path / "ref", tmp_path / "ours"
+    d1.mkdir(), d2.mkdir()
+    theirs.save(str(d1))
+    ours.load(str(d1))
+    for i in range(2):
+        want = theirs.actors[i].state_dict()
+        got = ours.actors[i].state_dict()
+        assert set(want) == set(got)
+        for k in want:
+            assert torch.equal(want[k], got[k]), k
+        for k, v in theirs.critics[i].state_dict().items():
+            assert torch.equal(v, ours.critics[i].state_dict()[k]), k
+    # the loaded values live in the arenas the kernels read (net g = member * N + k)
+    assert torch.equal(ours._critic_arena.p["W3"][3], theirs.critics[1].nets[1].out.weight)
+    assert torch.equal(ours._actor_arena.p["W3"][1], theirs.actors[1].act_p.weight)
+    with torch.no_grad():
+        ours._critic_arena.flat.mul_(0.5)
+    ours.save(str(d2))
+    theirs.load(str(d2))
+    assert torch.equal(theirs.critics[0].nets[0].fc1.weight, ours._critic_arena.p["W1"][0])
+    assert np.isfinite(theirs.critics[0].nets[0].fc1.weight.detach().numpy()).all()
