@@ -14,16 +14,23 @@ class DiscreteOracleAgent:
     """agent.Agent(discrete=True) (agent.py:43-130): actors = DiscreteActor (nets/mlps.py:132-149, S -> H -> H -> A
     logits), critics = DiscreteCritic (nets/mlps.py:170-185, S -> H -> H -> A values), identity encoder."""
 
-    def __init__(self, E, N, S, A, H, popart=False):
+    def __init__(self, E, N, S, A, H, popart=False, encoder=None):
         self.E, self.N, self.S, self.A, self.H = E, N, S, A, H
         self.actors = MLPStack(E, S, H, A)
         self.critics = MLPStack(E * N, S, H, A)
         self.popart = [PopArt() if popart else None for _ in range(E)]
+        self.encoder = encoder   # a user plugin (torch module on the obs dict, differentiated by autograd) or None = identity
+
+    def encode(self, obs):
+        return obs["obs"] if self.encoder is None else self.encoder(obs)
 
     def clone(self):
+        import copy
+
         c = DiscreteOracleAgent(self.E, self.N, self.S, self.A, self.H)
         c.actors, c.critics = self.actors.clone(), self.critics.clone()
         c.popart = [p.clone() if p is not None else None for p in self.popart]
+        c.encoder = copy.deepcopy(self.encoder)
         return c
 
     def critic_min(self, i, s_rep, nets=None):
@@ -42,7 +49,8 @@ def compute_td_target(agent, target, i, batch, subset, hp, log_alpha, logs):
     """learning_utils.py:298-354, discrete branch (:322-328)."""
     o, a, r, o1, d = batch
     popart = agent.popart[i]
-    s1 = o1["obs"]
+    with torch.no_grad():
+        s1 = target.encode(o1)
     probs, logp = policy(mlp_forward(agent.actors, i, s1)[0])
     q1 = target.critic_min(i, s1, nets=subset)
     entropy_bonus = log_alpha.exp() * logp
@@ -67,7 +75,9 @@ def compute_backup_weights(agent, target, batch, hp, logs):
     if wt != "sunrise":
         raise NotImplementedError("discrete softmax weights draw Categorical samples; not restated")
     o, a, *_ = batch
-    q_std = torch.stack([target.critic_min(j, o["obs"]).gather(-1, a.long()) for j in range(agent.E)], 0).std(0)
+    with torch.no_grad():
+        s_t = target.encode(o)
+    q_std = torch.stack([target.critic_min(j, s_t).gather(-1, a.long()) for j in range(agent.E)], 0).std(0)
     weights = torch.sigmoid(-q_std * temp) + 0.5
     logs["bellman_weights/mean"] = weights.mean().item()
     logs["bellman_weights/max"] = weights.max().item()
@@ -76,10 +86,12 @@ def compute_backup_weights(agent, target, batch, hp, logs):
     return weights
 
 
-def critic_update(agent, target, batches, subsets, hp, log_alphas, critic_opt):
-    """learning.py:18-141 with discrete=True, per=False: every net's Q row is gathered at the taken action (:90-92)."""
+def critic_update(agent, target, batches, subsets, hp, log_alphas, critic_opt, encoder_opt=None):
+    """learning.py:18-141 with discrete=True, per=False: every net's Q row is gathered at the taken action (:90-92).
+    A trainable encoder receives the summed input gradients of the member's critics through autograd (:121)."""
     E, N = agent.E, agent.N
     logs, aux = {}, dict(td_target=[], weights=[])
+    enc_outs = []
     grads = agent.critics.zeros_like()
     loss = 0.0
     scale = 1.0 / (E * N)
@@ -91,7 +103,10 @@ def critic_update(agent, target, batches, subsets, hp, log_alphas, critic_opt):
         w = compute_backup_weights(agent, target, batches[i], hp, logs)
         aux["td_target"].append(td_target)
         aux["weights"].append(w)
-        x = o["obs"]
+        s_rep = agent.encode(o)
+        needs_enc_grad = agent.encoder is not None and s_rep.requires_grad
+        x = s_rep.detach()
+        dx_sum = torch.zeros_like(x) if needs_enc_grad else None
         popart = agent.popart[i]
         pop_on = popart is not None and hp.get("pop", False)
         outs = [mlp_forward(agent.critics, i * N + k, x) for k in range(N)]
@@ -111,16 +126,29 @@ def critic_update(agent, target, batches, subsets, hp, log_alphas, critic_opt):
             if pop_on:
                 dq = dq * popart.w
             extra = (dr3 * scale / (N * B)) * f1[k][2] if dr3 > 0 else None
-            mlp_backward(agent.critics, i * N + k, x, h1, h2, dq * onehot, grads, dh2_extra=extra)
+            dx = mlp_backward(agent.critics, i * N + k, x, h1, h2, dq * onehot, grads, dh2_extra=extra,
+                              need_dx=needs_enc_grad)
+            if needs_enc_grad:
+                dx_sum += dx
             if dr3 > 0:
                 _, h1b, h2b = f1[k]
                 mlp_backward(agent.critics, i * N + k, s1, h1b, h2b, torch.zeros(B, agent.A), grads,
                              dh2_extra=(dr3 * scale / (N * B)) * h2)
+        if needs_enc_grad:
+            enc_outs.append((s_rep, dx_sum))
     loss = loss / (E * N)
+    if encoder_opt is not None:
+        encoder_opt.zero_grad()
+    if enc_outs:
+        torch.autograd.backward([s_ for s_, _ in enc_outs], [g for _, g in enc_outs])
     glist = grads.tensors()
     if hp.get("critic_clip"):
         clip_grad_norm(glist, hp["critic_clip"])
+    if hp.get("encoder_clip") and agent.encoder is not None:
+        torch.nn.utils.clip_grad_norm_(agent.encoder.parameters(), hp["encoder_clip"])
     aux["grads"] = grads
+    if encoder_opt is not None:
+        encoder_opt.step()
     critic_opt.step(glist)
     logs["losses/last_member_critic_td_error"] = td_error.mean().item()
     logs["losses/critic_overall_loss"] = float(loss)
@@ -134,7 +162,8 @@ def online_actor_update(agent, batches, hp, log_alphas, actor_opt):
     grads = agent.actors.zeros_like()
     loss = 0.0
     for i in range(E):
-        s = batches[i][0]["obs"]
+        with torch.no_grad():
+            s = agent.encode(batches[i][0])
         B = s.shape[0]
         popart = agent.popart[i]
         logits, h1, h2 = mlp_forward(agent.actors, i, s)
@@ -163,7 +192,8 @@ def alpha_update(agent, batches, log_alphas, alpha_opts, target_entropy):
     """learning.py:222-263, discrete branch (:252-253): logp = sum_a p log p (the negative entropy)."""
     logs = {}
     for i in range(agent.E):
-        s = batches[i][0]["obs"]
+        with torch.no_grad():
+            s = agent.encode(batches[i][0])
         probs, logp = policy(mlp_forward(agent.actors, i, s)[0])
         t = (probs * logp).sum(-1) + target_entropy
         alpha_loss = -(log_alphas[i] * t).mean()

@@ -516,7 +516,8 @@ def run_discrete_case(name, cfg, out_dir=None):
     E, N, M = cfg["E"], cfg["N"], cfg["M"]
     S, A, H, B = cfg["S"], cfg["A"], cfg["H"], cfg["B"]
     popart_on = cfg.get("popart", False)
-    agent = ssac.Agent(act_space_size=A, encoder=IdentityEncoder(S), actor_network_cls=rnets.mlps.DiscreteActor,
+    enc = SharedEncoder(S) if cfg.get("encoder") == "shared" else IdentityEncoder(S)
+    agent = ssac.Agent(act_space_size=A, encoder=enc, actor_network_cls=rnets.mlps.DiscreteActor,
                        critic_network_cls=rnets.mlps.DiscreteCritic, discrete=True, ensemble_size=E, num_critics=N,
                        hidden_size=H, auto_rescale_targets=popart_on)
     for m in critic_nets(agent) + list(agent.actors):
@@ -552,6 +553,9 @@ def run_discrete_case(name, cfg, out_dir=None):
     put(out, "init/critics", _stack(critic_nets(agent)))
     put(out, "init/target_critics", _stack(critic_nets(target)))
     put(out, "init/popart", popart_state(agent))
+    if cfg.get("encoder") == "shared":
+        put(out, "init/encoder", {k: v.numpy().copy() for k, v in enc.state_dict().items()})
+        put(out, "init/target_encoder", {k: v.numpy().copy() for k, v in target.encoder.state_dict().items()})
 
     critic_opt = torch.optim.Adam(chain(*(c.parameters() for c in agent.critics)), lr=cfg.get("critic_lr", 3e-4),
                                   weight_decay=cfg.get("critic_l2", 0.0), betas=(0.9, 0.999))
@@ -593,7 +597,7 @@ def run_discrete_case(name, cfg, out_dir=None):
                 logs, replay_dicts = learning.critic_update(
                     buffer=buffer, agent=agent, target_agent=target, critic_optimizer=critic_opt,
                     encoder_optimizer=enc_opt, log_alphas=log_alphas, batch_size=B, gamma=cfg.get("gamma", 0.99),
-                    critic_clip=cfg.get("critic_clip"), encoder_clip=None, target_critic_ensemble_n=M,
+                    critic_clip=cfg.get("critic_clip"), encoder_clip=cfg.get("encoder_clip"), target_critic_ensemble_n=M,
                     weighted_bellman_temp=cfg.get("weight_temp"), weight_type=cfg.get("weight_type"),
                     pop=cfg.get("pop", False), augmenter=augmenter, encoder_lambda=0.0, aug_mix=0.0, discrete=True,
                     random_process=None, noise_clip=None, per=False, update_priorities=False,
@@ -608,6 +612,10 @@ def run_discrete_case(name, cfg, out_dir=None):
             put(out, f"step{t}/critics", _stack(critic_nets(agent)))
             put(out, f"step{t}/target_critics", _stack(critic_nets(target)))
             put(out, f"step{t}/popart", popart_state(agent))
+            if cfg.get("encoder") == "shared":
+                lu.soft_update(target.encoder, agent.encoder, cfg.get("encoder_tau", 0.01))
+                put(out, f"step{t}/encoder", {k: v.numpy().copy() for k, v in enc.state_dict().items()})
+                put(out, f"step{t}/target_encoder", {k: v.numpy().copy() for k, v in target.encoder.state_dict().items()})
     finally:
         lu.compute_td_targets, lu.compute_backup_weights = o_td, o_bw
 
@@ -706,6 +714,9 @@ def run_discrete_afbc_case():
 
 
 DISCRETE_CASES = {
+    # a trainable encoder in front (what a pixel SAC-Discrete agent has): critic gradients flow into it, the actor's do not
+    "discrete_encoder": dict(E=2, N=2, M=2, S=6, A=4, H=32, B=16, steps=2, encoder="shared", critic_clip=10.0,
+                             encoder_clip=5.0, dr3_coeff=0.01, seed=13),
     # SAC-Discrete with a REDQ-style target subset (2 of 3 critics), DR3 on
     "discrete_sac": dict(E=1, N=3, M=2, S=6, A=5, H=32, B=16, steps=2, dr3_coeff=0.01, critic_clip=40.0, seed=11),
     # ensemble of 2 members: sunrise Bellman weights on gathered Q(s, a), warm PopArt, actor clipping

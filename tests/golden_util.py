@@ -12,7 +12,8 @@ from oracle import update_oracle as uo
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 UPDATE_CASES = ["sac", "redq", "sunrise_popart", "td3_encoder", "softmax_dr3"]
-DISCRETE_CASES = ["discrete_sac", "discrete_sunrise_popart"]
+DISCRETE_CASES = ["discrete_sac", "discrete_sunrise_popart"]   # GPU + CPU
+DISCRETE_ENCODER_CASE = "discrete_encoder"                      # trainable encoder in front: oracle + host logic (CPU)
 
 
 def load(name, directory=None):
@@ -94,9 +95,13 @@ def discrete_oracle_agents(fx, with_target=True):
     agent.actors = uo.MLPStack.from_arrays(sub(fx, "init/actors"))
     agent.critics = uo.MLPStack.from_arrays(sub(fx, "init/critics"))
     agent.popart = popart_from(fx, "init/popart", E)
+    if cfg.get("encoder") == "shared":
+        agent.encoder = encoder_from(fx, "init/encoder", S)
     target = agent.clone()
     if with_target:
         target.critics = uo.MLPStack.from_arrays(sub(fx, "init/target_critics"))
+    if cfg.get("encoder") == "shared":
+        target.encoder = encoder_from(fx, "init/target_encoder", S)
     return cfg, agent, target
 
 

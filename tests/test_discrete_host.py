@@ -74,7 +74,7 @@ def emulated(monkeypatch):
     return emu
 
 
-@pytest.mark.parametrize("case", gu.DISCRETE_CASES)
+@pytest.mark.parametrize("case", gu.DISCRETE_CASES + [gu.DISCRETE_ENCODER_CASE])
 def test_discrete_updates_host_logic(case, emulated, monkeypatch):
     import copy
     import math
@@ -86,7 +86,9 @@ def test_discrete_updates_host_logic(case, emulated, monkeypatch):
     fx = gu.load("update_" + case)
     cfg = gu.cfg_of(fx)
     E, N, M, S, A, H, B = cfg["E"], cfg["N"], cfg["M"], cfg["S"], cfg["A"], cfg["H"], cfg["B"]
-    agent = ssb.Agent(act_space_size=A, encoder=IdentityEncoder(S), actor_network_cls=nets.mlps.DiscreteActor,
+    shared = cfg.get("encoder") == "shared"   # a trainable (user, PyTorch) encoder in front: critic gradients train it
+    agent = ssb.Agent(act_space_size=A, encoder=gu.encoder_from(fx, "init/encoder", S) if shared else IdentityEncoder(S),
+                      actor_network_cls=nets.mlps.DiscreteActor,
                       critic_network_cls=nets.mlps.DiscreteCritic, discrete=True, ensemble_size=E, num_critics=N,
                       hidden_size=H, auto_rescale_targets=cfg.get("popart", False))
     assert agent._critic_arena.O == A and agent._critic_arena.D == S and agent._actor_arena.O == A
@@ -100,6 +102,8 @@ def test_discrete_updates_host_logic(case, emulated, monkeypatch):
     target = copy.deepcopy(agent)
     assert target.discrete and target._critic_arena.O == A
     _load_stack(target._critic_arena, gu.sub(fx, "init/target_critics"))
+    if shared:
+        target.encoder.load_state_dict({k: torch.as_tensor(v) for k, v in gu.sub(fx, "init/target_encoder").items()})
     # the module views see the arena (state_dict keys as the reference's: fc1 / fc2 / act_p, fc1 / fc2 / out)
     assert set(agent.actors[0].state_dict()) == {"fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias", "act_p.weight", "act_p.bias"}
     assert agent.actors[0].act_p.weight.data_ptr() == agent._actor_arena.p["W3"][0].data_ptr()
@@ -152,7 +156,7 @@ def test_discrete_updates_host_logic(case, emulated, monkeypatch):
             logs, replay_dicts = learning.critic_update(
                 buffer=None, agent=agent, target_agent=target, critic_optimizer=critic_opt, encoder_optimizer=enc_opt,
                 log_alphas=log_alphas, batch_size=B, gamma=cfg.get("gamma", 0.99), critic_clip=cfg.get("critic_clip"),
-                encoder_clip=None, target_critic_ensemble_n=M, weighted_bellman_temp=cfg.get("weight_temp"),
+                encoder_clip=cfg.get("encoder_clip"), target_critic_ensemble_n=M, weighted_bellman_temp=cfg.get("weight_temp"),
                 weight_type=cfg.get("weight_type"), pop=cfg.get("pop", False), augmenter=augmenter, encoder_lambda=0.0,
                 aug_mix=0.0, discrete=True, random_process=None, noise_clip=None, per=False, update_priorities=False,
                 dr3_coeff=cfg.get("dr3_coeff", 0.0))
@@ -169,6 +173,14 @@ def test_discrete_updates_host_logic(case, emulated, monkeypatch):
                 tf, sf = target._critic_arena.flat, agent._critic_arena.flat
                 tf.copy_(tf * (1.0 - tau) + sf * tau)
             _cmp_stack(agent._critic_arena.p, gu.sub(fx, f"step{t}/critics"), f"step{t} critics", atol=3e-4 * 0.05)
+            if shared:
+                with torch.no_grad():
+                    for tp, sp in zip(target.encoder.parameters(), agent.encoder.parameters()):
+                        tp.copy_(tp * (1.0 - 0.01) + sp * 0.01)
+                for which, enc in (("encoder", agent.encoder), ("target_encoder", target.encoder)):
+                    want = gu.sub(fx, f"step{t}/{which}")
+                    for k, v in enc.state_dict().items():
+                        gu.assert_close(v.numpy(), want[k], RTOL, 1e-4 * 0.05, f"step{t} {which}.{k}")
             want_pop = gu.sub(fx, f"step{t}/popart")
             for i, p in enumerate(agent.popart):
                 if p:

@@ -96,7 +96,7 @@ def check_update_oracle(fx):
         _cmp_logs(logs, gu.sub(fx, "alpha/logs"), "alpha")
 
 
-@pytest.mark.parametrize("case", gu.DISCRETE_CASES)
+@pytest.mark.parametrize("case", gu.DISCRETE_CASES + [gu.DISCRETE_ENCODER_CASE])
 def test_discrete_oracle_matches_reference(case):
     """SAC-Discrete: the restated discrete branches against the unmodified reference's outputs."""
     check_discrete_oracle(gu.load("update_" + case))
@@ -111,12 +111,13 @@ def check_discrete_oracle(fx):
     critic_opt = uo.Adam(agent.critics.tensors(), lr=cfg.get("critic_lr", 3e-4))
     actor_opt = uo.Adam(agent.actors.tensors(), lr=cfg.get("actor_lr", 3e-4))
     alpha_opts = [uo.Adam([la], lr=cfg.get("alpha_lr", 1e-4), betas=(0.5, 0.999)) for la in log_alphas]
+    enc_opt = torch.optim.Adam(agent.encoder.parameters(), lr=1e-4) if agent.encoder is not None else None
     batches = None
     for t in range(cfg["steps"]):
         idx, subsets = fx[f"step{t}/rand/idx"], fx[f"step{t}/rand/subsets"]
         batches = [gu.batch_from(fx, idx[i]) for i in range(E)]
         logs, aux = do.critic_update(agent, target, batches, [[int(x) for x in subsets[i]] for i in range(E)], hp,
-                                     log_alphas, critic_opt)
+                                     log_alphas, critic_opt, enc_opt)
         for i in range(E):
             gu.assert_close(aux["td_target"][i].numpy(), fx[f"step{t}/td_target/{i}"], RTOL, ATOL, f"step{t} td_target[{i}]")
             w = aux["weights"][i]
@@ -127,6 +128,13 @@ def check_discrete_oracle(fx):
         uo.soft_update(target.critics.tensors(), agent.critics.tensors(), cfg.get("tau", 0.005))
         _cmp_stack(agent.critics, gu.sub(fx, f"step{t}/critics"), f"step{t} critics", rtol=1e-5, atol=3e-4 * 2e-2)
         _cmp_stack(target.critics, gu.sub(fx, f"step{t}/target_critics"), f"step{t} target_critics", rtol=1e-5, atol=1e-6)
+        if agent.encoder is not None:
+            uo.soft_update([p.data for p in target.encoder.parameters()], [p.data for p in agent.encoder.parameters()],
+                           cfg.get("encoder_tau", 0.01))
+            for which, enc in (("encoder", agent.encoder), ("target_encoder", target.encoder)):
+                want = gu.sub(fx, f"step{t}/{which}")
+                for k, v in enc.state_dict().items():
+                    gu.assert_close(v.numpy(), want[k], 1e-5, 1e-4 * 2e-2, f"step{t} {which}.{k}")
         want_pop = gu.sub(fx, f"step{t}/popart")
         for i, p in enumerate(agent.popart):
             if p is None:
