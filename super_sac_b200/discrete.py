@@ -51,7 +51,8 @@ def _check(agent):
 
 def compute_td_targets(logs, replay_dict, agent, target_agent, ensemble_idx, ensemble_n, log_alphas, pop, gamma):
     """learning_utils.py:298-354 with discrete=True: y = r + gamma (1-d) E_{a~pi(s1)}[min_M Q_target(s1, a) - alpha log pi(a|s1)],
-    PopArt as in the continuous branch.  Returns (y [B,1], (s1_rep, probs-free placeholder None))."""
+    PopArt as in the continuous branch.  Returns (y [B,1], (s1_rep, None)): the reference hands back the policy's
+    probabilities in the second slot (:328), which nothing on the update path reads -- they never leave the kernel here."""
     dlogs, user_logs = _logs.as_device_logs(logs, agent._critic_arena.device)
     i, M = ensemble_idx, ensemble_n
     o, a, r, o1, d = replay_dict["primary_batch"]
