@@ -98,3 +98,30 @@ def test_discrete_checkpoints_interchange_with_the_reference(tmp_path):
     theirs.load(str(d2))
     assert torch.equal(theirs.critics[0].nets[0].fc1.weight, ours._critic_arena.p["W1"][0])
     assert np.isfinite(theirs.critics[0].nets[0].fc1.weight.detach().numpy()).all()
+
+
+def test_epsilon_greedy_process_follows_the_reference():
+    """learning_utils.EpsilonGreedyExplorationNoise (the discrete agents' exploration process, main.py:246-253): the same
+    python / numpy random streams give the same actions and the same epsilon schedule as the reference's class."""
+    import random
+
+    import numpy as np
+
+    from super_sac_b200 import learning_utils as lu
+
+    ref = rh.import_reference()
+
+    class Space:
+        n = 6
+
+    outs = []
+    for cls in (ref.learning_utils.EpsilonGreedyExplorationNoise, lu.EpsilonGreedyExplorationNoise):
+        random.seed(5)
+        np.random.seed(5)
+        proc = cls(Space(), eps_start=0.9, eps_final=0.05, steps_annealed=40)
+        seq = []
+        for t in range(60):
+            a = proc.sample(np.array([t % 6], dtype=np.int64), update_schedule=(t % 3 != 0))
+            seq.append((int(a[0]), proc.current_scale))
+        outs.append(seq)
+    assert outs[0] == outs[1]
